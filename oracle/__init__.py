@@ -1,0 +1,253 @@
+"""CPU oracle for the frame-alignment hot path - TEST INFRASTRUCTURE ONLY.
+
+``oracle/mt_oracle.c`` is the restatement (each function cites the reference
+file:line it follows); this module is its numpy/ctypes face.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it.  The product package
+``master_thesis_b200`` never does.
+
+Parity pinning: the reference has no tests or golden vectors of its own
+(SURVEY.md section 4), so the oracle is pinned against outputs of the
+UNMODIFIED reference run in the build container
+(``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``,
+checked by ``tests/test_oracle_golden.py``).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmt_oracle.so")
+_lib = None
+
+_f = ctypes.POINTER(ctypes.c_float)
+_u8 = ctypes.POINTER(ctypes.c_uint8)
+_d = ctypes.POINTER(ctypes.c_double)
+_i = ctypes.c_int
+_l = ctypes.c_int64
+
+
+def build(force=False):
+    """Compiles oracle/libmt_oracle.so with the committed Makefile."""
+    src = os.path.join(_HERE, "mt_oracle.c")
+    if (not force and os.path.exists(_LIB_PATH)
+            and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-C", _HERE, "-B", "libmt_oracle.so"],
+                          stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = ctypes.CDLL(_LIB_PATH)
+        L.mto_masked_l1.restype = ctypes.c_float
+        L.mto_hole_update.restype = ctypes.c_float
+        L.mto_num_threads.restype = _i
+        _lib = L
+    return _lib
+
+
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_f)
+
+
+def num_threads():
+    return lib().mto_num_threads()
+
+
+def set_num_threads(n):
+    lib().mto_set_num_threads(_i(n))
+
+
+def grid_sample(inp, grid, mode="bilinear", align_corners=True):
+    inp, grid = _c(inp), _c(grid)
+    n, c, h, w = inp.shape
+    _, ho, wo, _ = grid.shape
+    out = np.empty((n, c, ho, wo), np.float32)
+    lib().mto_grid_sample(_p(inp), _p(grid), _i(n), _i(c), _i(h), _i(w), _i(ho), _i(wo),
+                          _i(0 if mode == "bilinear" else 1), _i(int(align_corners)), _p(out))
+    return out
+
+
+def affine_grid(theta, h, w, align_corners=False):
+    theta = _c(theta)
+    n = theta.shape[0]
+    out = np.empty((n, h, w, 2), np.float32)
+    lib().mto_affine_grid(_p(theta), _i(n), _i(h), _i(w), _i(int(align_corners)), _p(out))
+    return out
+
+
+def align_set(x, v, flow):
+    """a1 - utils.py:78-104."""
+    x, v, flow = _c(x), _c(v), _c(flow)
+    b, c, f, h, w = x.shape
+    xa = np.empty_like(x)
+    va = np.empty((b, 1, f, h, w), np.float32)
+    lib().mto_align_set(_p(x), _p(v), _p(flow), _i(b), _i(c), _i(f), _i(h), _i(w), _p(xa), _p(va))
+    return xa, va
+
+
+def dfpn_align_tail(x_refs, m_refs, m_target, flow):
+    """a2 - model_dfpn.py:128-133."""
+    x_refs, m_refs, m_target, flow = _c(x_refs), _c(m_refs), _c(m_target), _c(flow)
+    b, c, f, h, w = x_refs.shape
+    xa = np.empty_like(x_refs)
+    va = np.empty((b, 1, f, h, w), np.float32)
+    vm = np.empty((b, 1, f, h, w), np.float32)
+    lib().mto_dfpn_align_tail(_p(x_refs), _p(m_refs), _p(m_target), _p(flow), _i(b), _i(c), _i(f),
+                              _i(h), _i(w), _p(xa), _p(va), _p(vm))
+    return xa, va, vm
+
+
+def cpn_align_tail(x_refs, m_refs, m_target, theta=None, grid=None):
+    """a3 - model_cpn.py:75-89 (theta (b*f,2,3), or an explicit dense grid)."""
+    x_refs, m_refs, m_target = _c(x_refs), _c(m_refs), _c(m_target)
+    theta = None if theta is None else _c(theta)
+    grid = None if grid is None else _c(grid)
+    b, c, f, h, w = x_refs.shape
+    xa = np.empty_like(x_refs)
+    va = np.empty((b, 1, f, h, w), np.float32)
+    vm = np.empty((b, 1, f, h, w), np.float32)
+    lib().mto_cpn_align_tail(_p(x_refs), _p(m_refs), _p(m_target), _p(theta), _p(grid), _i(b),
+                             _i(c), _i(f), _i(h), _i(w), _p(xa), _p(va), _p(vm))
+    return xa, va, vm
+
+
+def mask_out(flow):
+    """a4 - model_dfpn.py:269-272; flow (b,f,h,w,2) -> (b,1,f,h,w)."""
+    flow = _c(flow)
+    b, f, h, w, _ = flow.shape
+    out = np.empty((b, 1, f, h, w), np.float32)
+    lib().mto_mask_out(_p(flow), _l(flow.size // 2), _p(out))
+    return out
+
+
+def _l1_args(y_hat, y, mask, batch_mask):
+    y_hat, y, mask = _c(y_hat), _c(y), _c(mask)
+    b, c = y_hat.shape[0], y_hat.shape[1]
+    inner = int(np.prod(y_hat.shape[2:]))
+    if mask.shape == y_hat.shape:
+        mask_c = c
+    else:
+        assert mask.shape[0] == b and mask.shape[1] == 1 and mask.shape[2:] == y_hat.shape[2:]
+        mask_c = 1
+    bm = None
+    if batch_mask is not None:
+        bm = np.ascontiguousarray(np.asarray(batch_mask).astype(np.uint8))
+    return y_hat, y, mask, b, c, inner, mask_c, bm
+
+
+def masked_l1(y_hat, y, mask, batch_mask=None, reduction="mean", weight=1.0):
+    """a5 - utils.py:139-169.  Returns a python float."""
+    y_hat, y, mask, b, c, inner, mask_c, bm = _l1_args(y_hat, y, mask, batch_mask)
+    return float(lib().mto_masked_l1(
+        _p(y_hat), _p(y), _p(mask), _i(b), _i(c), _l(inner), _i(mask_c),
+        None if bm is None else bm.ctypes.data_as(_u8), _i(1 if reduction == "sum" else 0),
+        ctypes.c_float(weight), None))
+
+
+def masked_l1_bwd(y_hat, y, mask, batch_mask=None, reduction="mean", weight=1.0, grad_out=1.0):
+    """Gradient of a5 w.r.t. ``y`` (grad w.r.t. ``y_hat`` is its negation)."""
+    y_hat, y, mask, b, c, inner, mask_c, bm = _l1_args(y_hat, y, mask, batch_mask)
+    g = np.empty_like(y)
+    lib().mto_masked_l1_bwd(
+        _p(y_hat), _p(y), _p(mask), _i(b), _i(c), _l(inner), _i(mask_c),
+        None if bm is None else bm.ctypes.data_as(_u8), _i(1 if reduction == "sum" else 0),
+        ctypes.c_float(weight), ctypes.c_float(grad_out), _p(g))
+    return g
+
+
+def align_set_bwd_flow(x, flow, gout, align_corners=True):
+    """a6 - gradient of a1's bilinear warp w.r.t. the flow."""
+    x, flow, gout = _c(x), _c(flow), _c(gout)
+    b, c, f, h, w = x.shape
+    g = np.empty_like(flow)
+    lib().mto_align_set_bwd_flow(_p(x), _p(flow), _p(gout), _i(b), _i(c), _i(f), _i(h), _i(w),
+                                 _i(int(align_corners)), _p(g))
+    return g
+
+
+def corr4d(ft, vt, fr, vr):
+    """a7 - model_dfpn.py:534-565."""
+    ft, fr = _c(ft), _c(fr)
+    vt = None if vt is None else _c(vt)
+    vr = None if vr is None else _c(vr)
+    b, c, f, h, w = fr.shape
+    out = np.empty((b, f, h, w, h, w), np.float32)
+    lib().mto_corr4d(_p(ft), _p(vt), _p(fr), _p(vr), _i(b), _i(c), _i(f), _i(h * w), _p(out))
+    return out
+
+
+def cm_module(c_feats, v_t, v_aligned, return_gs=False):
+    """a8 - model_cpn.py:206-254."""
+    c_feats, v_t, v_aligned = _c(c_feats), _c(v_t), _c(v_aligned)
+    b, c, f, h, w = c_feats.shape
+    H, W = v_t.shape[-2:]
+    out = np.empty((b, 2 * c + 1, h, w), np.float32)
+    cmask = np.empty((b, 1, h, w), np.float32)
+    gs = np.empty((b, f - 1), np.float32)
+    lib().mto_cm_module(_p(c_feats), _p(v_t), _p(v_aligned), _i(b), _i(c), _i(f), _i(h), _i(w),
+                        _i(H), _i(W), _p(out), _p(cmask), _p(gs))
+    return (out, cmask, gs) if return_gs else (out, cmask)
+
+
+def chn_pack(x_t, v_t, x_al, v_al, v_map):
+    """a9 - model_chn.py:68-80."""
+    x_t, v_t, x_al, v_al, v_map = _c(x_t), _c(v_t), _c(x_al), _c(v_al), _c(v_map)
+    b, _, f, h, w = x_al.shape
+    out = np.empty((b * f, 9, h, w), np.float32)
+    lib().mto_chn_pack(_p(x_t), _p(v_t), _p(x_al), _p(v_al), _p(v_map), _i(b), _i(f), _l(h * w),
+                       _p(out))
+    return out
+
+
+def chn_composite(nn_out, x_t, v_t, b, f):
+    """a10 - model_chn.py:80-85."""
+    nn_out, x_t, v_t = _c(nn_out), _c(x_t), _c(v_t)
+    h, w = nn_out.shape[-2:]
+    yh = np.empty((b, 3, f, h, w), np.float32)
+    yc = np.empty((b, 3, f, h, w), np.float32)
+    lib().mto_chn_composite(_p(nn_out), _p(x_t), _p(v_t), _i(b), _i(f), _l(h * w), _p(yh), _p(yc))
+    return yh, yc
+
+
+def chn_composite_bwd(nn_out, v_t, g_yhat, g_comp, b, f):
+    nn_out, v_t = _c(nn_out), _c(v_t)
+    g_yhat = None if g_yhat is None else _c(g_yhat)
+    g_comp = None if g_comp is None else _c(g_comp)
+    h, w = nn_out.shape[-2:]
+    g = np.empty_like(nn_out)
+    lib().mto_chn_composite_bwd(_p(nn_out), _p(v_t), _p(g_yhat), _p(g_comp), _i(b), _i(f),
+                                _l(h * w), _p(g))
+    return g
+
+
+def hole_update(m_t, v_map0, y_comp0):
+    """a11 - model_chn.py:128-131."""
+    m_t, v_map0, y_comp0 = _c(m_t), _c(v_map0), _c(y_comp0)
+    b = m_t.shape[0]
+    P = int(np.prod(m_t.shape[2:]))
+    m_new = np.empty_like(m_t)
+    x_new = np.empty_like(y_comp0)
+    per = lib().mto_hole_update(_p(m_t), _p(v_map0), _p(y_comp0), _i(b), _l(P), _p(m_new),
+                                _p(x_new))
+    return m_new, x_new, float(per)
+
+
+def trivial_copy(x_t, x_al, v_map):
+    """a12 - model_dfpn.py:427-429."""
+    x_t, x_al, v_map = _c(x_t), _c(x_al), _c(v_map)
+    b, _, f, h, w = x_al.shape
+    y = np.empty_like(x_al)
+    lib().mto_trivial_copy(_p(x_t), _p(x_al), _p(v_map), _i(b), _i(f), _l(h * w), _p(y))
+    return y

@@ -1,0 +1,137 @@
+"""Case tables + input builders shared by make_golden.py and the tests.
+
+Inputs are regenerated from ``master_thesis_b200.synth`` (numpy RandomState:
+bit-identical on every machine); only reference OUTPUTS are stored in the
+.npz fixtures.  Edge cases follow SURVEY.md section 8(c): half-pixel ties,
+-0.5 / size-0.5 borders, |g| > 1, all-masked target, all-refs-invisible,
+batch_mask all-False, v=None in the correlation, F=1 and F=4, non-square.
+"""
+import numpy as np
+
+from master_thesis_b200 import synth
+
+# a1/a2 -------------------------------------------------------------------
+WARP_CASES = {
+    # name: b, f, h, w, flow kind
+    "smooth_f4": dict(seed=11, b=2, f=4, h=32, w=48, flow="smooth", sigma=0.05),
+    "noisy_oob": dict(seed=12, b=2, f=2, h=24, w=40, flow="white", sigma=0.5),
+    "ties": dict(seed=13, b=1, f=2, h=20, w=28, flow="ties"),
+    "f1_odd": dict(seed=14, b=3, f=1, h=17, w=23, flow="smooth", sigma=0.1),
+    "identity": dict(seed=15, b=1, f=1, h=16, w=16, flow="identity"),
+}
+
+
+def warp_inputs(spec):
+    b, f, h, w = spec["b"], spec["f"], spec["h"], spec["w"]
+    x, m, _ = synth.frames(spec["seed"], b, f + 1, h, w)
+    x_refs, m_refs = x[:, :, 1:].copy(), m[:, :, 1:].copy()
+    m_target = m[:, :, 0].copy()
+    kind = spec["flow"]
+    if kind == "smooth":
+        flow = synth.dense_flow(spec["seed"] + 1, b, f, h, w, spec["sigma"], True)
+    elif kind == "white":
+        flow = synth.dense_flow(spec["seed"] + 1, b, f, h, w, spec["sigma"], False)
+    elif kind == "ties":
+        flow = synth.tie_flow(spec["seed"] + 1, b, f, h, w)
+    else:
+        flow = np.broadcast_to(synth.identity_grid(h, w, True), (b, f, h, w, 2)).copy()
+    return x_refs, m_refs, m_target, flow
+
+
+# a3 ----------------------------------------------------------------------
+CPN_CASES = {
+    "rand_f4": dict(seed=21, b=2, f=4, h=32, w=48, sigma=0.1),
+    "big_f1": dict(seed=22, b=2, f=1, h=24, w=24, sigma=0.6),
+    "halfpix": dict(seed=23, b=1, f=3, h=16, w=20, sigma=0.0),
+}
+
+
+def cpn_inputs(spec):
+    b, f, h, w = spec["b"], spec["f"], spec["h"], spec["w"]
+    x, m, _ = synth.frames(spec["seed"], b, f + 1, h, w)
+    theta = synth.thetas(spec["seed"] + 1, b * f, spec["sigma"])
+    if spec["sigma"] == 0.0:
+        # pure translations by exactly half / one / 1.5 pixels: the bilinear
+        # visibility lands exactly on 0.5 (strict > 0.5 must say 0)
+        for i in range(b * f):
+            theta[i, 0, 2] = (i + 1) * 1.0 / w
+            theta[i, 1, 2] = (i % 2) * 1.0 / h
+    return x[:, :, 1:].copy(), m[:, :, 1:].copy(), m[:, :, 0].copy(), theta
+
+
+# a4/a5/a6 ----------------------------------------------------------------
+LOSS_CASES = {
+    "f4": dict(seed=31, b=3, frames=5, h=24, w=32, sigma=0.08, use=[1, 0, 1]),
+    "f1_oob": dict(seed=32, b=2, frames=2, h=16, w=24, sigma=0.6, use=[1, 1]),
+}
+
+
+def loss_inputs(spec):
+    b, n, h, w = spec["b"], spec["frames"], spec["h"], spec["w"]
+    x, m, _ = synth.frames(spec["seed"], b, n, h, w)
+    t = n // 2                         # model_dfpn.py:471-473
+    r_list = [i for i in range(n) if i != t]
+    f = len(r_list)
+    flow = synth.dense_flow(spec["seed"] + 1, b, f, h, w, spec["sigma"], True)
+    flow_gt = synth.dense_flow(spec["seed"] + 2, b, f, h, w, spec["sigma"], True)
+    flows_use = np.array(spec["use"], dtype=bool)
+    return x, m, flow, flow_gt, flows_use, t, r_list
+
+
+# a7 ----------------------------------------------------------------------
+CORR_CASES = {
+    "small_masked": dict(seed=41, b=2, f=2, c=32, h=4, w=4, masked=True),
+    "small_nomask": dict(seed=42, b=1, f=3, c=16, h=4, w=4, masked=False),
+    "real_masked": dict(seed=43, b=1, f=2, c=512, h=16, w=16, masked=True),
+    "real_nomask": dict(seed=44, b=2, f=1, c=512, h=16, w=16, masked=False),
+}
+
+
+def corr_inputs(spec):
+    ft, vt, fr, vr = synth.vgg_feats(spec["seed"], spec["b"], spec["f"], spec["c"],
+                                     spec["h"], spec["w"])
+    if not spec["masked"]:
+        return ft, None, fr, None
+    vt[0, 0, 0, :] = 0.0          # a fully masked row of target pixels
+    return ft, vt, fr, vr
+
+
+# a8 ----------------------------------------------------------------------
+CM_CASES = {
+    "small": dict(seed=51, b=2, f=3, c=8, h=8, w=8, up=4),
+    "edge": dict(seed=52, b=3, f=4, c=4, h=6, w=10, up=4, edge=True),
+    "real": dict(seed=53, b=1, f=5, c=128, h=64, w=64, up=4),
+}
+
+
+def cm_inputs(spec):
+    cf, vt, va = synth.cm_inputs(spec["seed"], spec["b"], spec["f"], spec["c"], spec["h"],
+                                 spec["w"], spec["up"])
+    if spec.get("edge"):
+        vt[0] = 0.0               # all-masked target: v_sum guard (:221-228)
+        va[1] = 0.0               # all refs invisible: masked_sums guard (:251-253)
+        va[2, 0, 0] = 0.0         # one invisible ref among visible ones
+    return cf, vt, va
+
+
+# a9..a12 -----------------------------------------------------------------
+CHN_CASES = {
+    "f4": dict(seed=61, b=2, f=4, h=16, w=24),
+    "f1_odd": dict(seed=62, b=1, f=1, h=15, w=21),
+}
+
+
+def chn_inputs(spec):
+    b, f, h, w = spec["b"], spec["f"], spec["h"], spec["w"]
+    x, m, _ = synth.frames(spec["seed"], b, f + 1, h, w)
+    x_t, m_t = x[:, :, 0].copy(), m[:, :, 0].copy()
+    flow = synth.dense_flow(spec["seed"] + 1, b, f, h, w, 0.08, True)
+    r = synth.rng(spec["seed"] + 2)
+    x_al = r.random_sample((b, 3, f, h, w)).astype(np.float32)
+    v_al = (r.random_sample((b, 1, f, h, w)) < 0.8).astype(np.float32)
+    v_map = np.clip(v_al - (1 - m_t[:, :, None]), 0, 1).astype(np.float32)
+    nn_out = synth.nn_output(spec["seed"] + 3, b * f, h, w)
+    # put some pre-clamp values exactly on the clamp edges 0 and 1
+    nn_out.reshape(-1)[::97] = ((0.0 - 0.485) / 0.229)
+    del flow
+    return x_t, (1 - m_t).astype(np.float32), x_al, v_al, v_map, nn_out

@@ -1,0 +1,181 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference has no tests, fixtures or golden vectors,
+so these files are the pin for the oracle (tests/test_oracle_golden.py) and
+for the CUDA path (tests/test_gpu_*.py).  Inputs are NOT stored: they are
+regenerated bit-identically from ``master_thesis_b200.synth`` (numpy
+RandomState).  Every case calls a reference function as is; where the
+function needs a CNN (``DFPN.align``, ``CPN.align``, ``CHN.forward``) the
+network is replaced by a stand-in object returning preset tensors, so the
+reference lines under test (cited per case) run unmodified.
+
+torch 2.11.0+cu128 CPU, fp32, generated on the build container.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from master_thesis_b200 import synth  # noqa: E402
+from oracle.ref_import import import_reference  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, OUT)
+T = torch.from_numpy
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrays.items()})
+    print("%-28s %8.1f KB" % (name, os.path.getsize(path) / 1024.0))
+
+
+# --------------------------------------------------------------------------
+# case tables (shared with the tests through cases.py)
+# --------------------------------------------------------------------------
+from cases import WARP_CASES, CPN_CASES, CORR_CASES, CM_CASES, CHN_CASES, LOSS_CASES  # noqa: E402
+from cases import warp_inputs, cpn_inputs, corr_inputs, cm_inputs, chn_inputs, loss_inputs  # noqa: E402
+
+
+def main():
+    torch.set_num_threads(1)
+    mt = import_reference()
+    DFPN = mt.model_dfpn.DFPN
+    CorrelationVGG = mt.model_dfpn.CorrelationVGG
+    CPN = mt.model_cpn.CPN
+    CM_Module = mt.model_cpn.CM_Module
+    CHN = mt.model_chn.CHN
+
+    # ---- a1 + a2: FlowsUtils.align_set (utils.py:78-104) and the DFPN.align
+    # tail (model_dfpn.py:125-133) with the flow network replaced.
+    for name, spec in WARP_CASES.items():
+        x, m, mt_, flow = warp_inputs(spec)
+
+        class FakeDFPN(object):
+            def __call__(self, *a):
+                return None, None, None, T(flow)
+
+        xa, va, vm = DFPN.align(FakeDFPN(), T(x[:, :, 0] * 0), T(mt_), T(x), T(m))
+        xa2, va2 = mt.FlowsUtils.align_set(T(x), T(1 - m), T(flow))
+        assert torch.equal(xa, xa2) and torch.equal(va, va2)
+        save("warp_" + name, x_aligned=xa.contiguous().numpy(), v_aligned=va.contiguous().numpy(),
+             v_map=vm.contiguous().numpy())
+
+    # ---- a3: CPN.align (model_cpn.py:31-91) with encoder/regressor replaced.
+    for name, spec in CPN_CASES.items():
+        x, m, mt_, theta = cpn_inputs(spec)
+        b, _, f, h, w = x.shape
+
+        class FakeCPN(object):
+            def A_Encoder(self, xx, mm):
+                return torch.zeros(xx.size(0), 1, 1, 1)
+
+            def A_Regressor(self, a, bb):
+                return T(theta)
+
+        xa, va, vm = CPN.align(FakeCPN(), T(x[:, :, 0] * 0), T(mt_), T(x), T(m))
+        grid = torch.nn.functional.affine_grid(T(theta), [b * f, 3, h, w], align_corners=False)
+        # the pre-threshold bilinear visibility, to classify near-threshold pixels
+        vs = torch.nn.functional.grid_sample(
+            1 - T(m).transpose(1, 2).reshape(-1, 1, h, w), grid, align_corners=False)
+        save("cpn_" + name, x_aligned=xa.contiguous().numpy(), v_aligned=va.contiguous().numpy(),
+             v_map=vm.contiguous().numpy(), grid=grid.numpy().reshape(b, f, h, w, 2),
+             v_soft=vs.reshape(b, f, 1, h, w).transpose(1, 2).contiguous().numpy())
+
+    # ---- a4 + a5 + a6: mask_out (model_dfpn.py:269-272), masked_l1
+    # (utils.py:139-169) as DFPN.compute_loss builds its arguments
+    # (model_dfpn.py:259-287), and autograd of align_set -> masked_l1.
+    for name, spec in LOSS_CASES.items():
+        x, m, flow, flow_gt, flows_use, t, r_list = loss_inputs(spec)
+        xt = T(x)
+        vt = 1 - T(m)
+        fl = T(flow).clone().requires_grad_(True)
+        xa, va = mt.FlowsUtils.align_set(xt[:, :, r_list], vt[:, :, r_list], fl)
+        mask_out = ((fl < -1).float() + (fl > 1).float()).sum(4).clamp(0, 1).unsqueeze(1)
+        nref = len(r_list)
+        y_hat = xt[:, :, t].unsqueeze(2).repeat(1, 1, nref, 1, 1)
+        mask = vt[:, :, t].unsqueeze(2).repeat(1, 1, nref, 1, 1) * (1 - mask_out)
+        recons = mt.LossesUtils.masked_l1(y_hat, xa, mask, reduction='sum')
+        g_xa, = torch.autograd.grad(recons, xa, retain_graph=True)
+        g_flow, = torch.autograd.grad(recons, fl, retain_graph=True)
+        flow_l1 = mt.LossesUtils.masked_l1(fl, T(flow_gt), torch.ones_like(fl),
+                                           T(flows_use))
+        g_flow_l1, = torch.autograd.grad(flow_l1, fl, allow_unused=True) \
+            if flow_l1.requires_grad else (torch.zeros_like(fl),)
+        none_sel = mt.LossesUtils.masked_l1(fl, T(flow_gt), torch.ones_like(fl),
+                                            torch.zeros(x.shape[0], dtype=torch.bool))
+        mean_l1 = mt.LossesUtils.masked_l1(y_hat, xa, mask, reduction='mean', weight=2)
+        save("loss_" + name, mask_out=mask_out.detach().numpy(), recons=recons.detach().numpy(),
+             g_x_aligned=g_xa.contiguous().numpy(), g_flow=g_flow.numpy(),
+             flow_l1=flow_l1.detach().numpy(), g_flow_l1=g_flow_l1.numpy(),
+             none_selected=none_sel.numpy(), mean_l1=mean_l1.detach().numpy())
+
+    # ---- a7: CorrelationVGG.correlation_masked_4d (model_dfpn.py:534-565)
+    for name, spec in CORR_CASES.items():
+        ft, vt, fr, vr = corr_inputs(spec)
+        c = CorrelationVGG.correlation_masked_4d(
+            T(ft), None if vt is None else T(vt), T(fr), None if vr is None else T(vr))
+        c = c.numpy()
+        if c.size > 300000:   # keep the fixture small: strided sample + checksum
+            save("corr_" + name, sample=c.reshape(-1)[::37].copy(), total=np.float64(c.astype(np.float64).sum()),
+                 abs_total=np.float64(np.abs(c).astype(np.float64).sum()))
+        else:
+            save("corr_" + name, corr=c)
+
+    # ---- a8: CM_Module.forward (model_cpn.py:206-254)
+    for name, spec in CM_CASES.items():
+        cf, vt, va = cm_inputs(spec)
+        out, cmask = CM_Module()(T(cf), T(vt), T(va))
+        out = out.numpy()
+        if out.size > 300000:
+            save("cm_" + name, sample=out.reshape(-1)[::53].copy(), c_mask=cmask.numpy(),
+                 total=np.float64(out.astype(np.float64).sum()))
+        else:
+            save("cm_" + name, out=out, c_mask=cmask.numpy())
+
+    # ---- a9 + a10 (+ backward) : CHN.forward (model_chn.py:44-85) with the
+    # RRDBNet replaced; a11: hole update via CHN.inpaint_ff (model_chn.py:87-133);
+    # a12: trivial copy (model_dfpn.py:427-429).
+    for name, spec in CHN_CASES.items():
+        x_t, v_t, x_al, v_al, v_map, nn_out = chn_inputs(spec)
+        b, _, f, h, w = x_al.shape
+        seen = {}
+
+        class FakeCHN(object):
+            mean = torch.as_tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1, 1)
+            std = torch.as_tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1, 1)
+
+            def nn(self, inp):
+                seen['nn_input'] = inp.detach().clone()
+                return seen['nn_out']
+
+        seen['nn_out'] = T(nn_out).clone().requires_grad_(True)
+        y_hat, y_comp = CHN.forward(FakeCHN(), T(x_t), T(v_t), T(x_al), T(v_al), T(v_map))
+        r = synth.rng(spec['seed'] + 7)
+        gy = r.standard_normal(y_hat.shape).astype(np.float32)
+        gc = r.standard_normal(y_hat.shape).astype(np.float32)
+        (y_hat * T(gy)).sum().add((y_comp * T(gc)).sum()).backward()
+        # a11: the three reference lines, model_chn.py:128-131
+        m_target = 1 - T(v_t)
+        fill_color = torch.as_tensor([0.485, 0.456, 0.406], dtype=torch.float32).view(1, 3, 1, 1)
+        m_new = m_target - T(v_map)[:, :, 0]
+        x_new = (1 - m_new) * y_comp[:, :, 0] + m_new.repeat(1, 3, 1, 1) * fill_color
+        inp_per = torch.sum(m_new) * 100 / m_new.numel()
+        # a12: model_dfpn.py:427-429
+        triv = T(x_t).unsqueeze(2).repeat(1, 1, f, 1, 1) * (1 - T(v_map)) + T(x_al) * T(v_map)
+        save("chn_" + name, nn_input=seen['nn_input'].numpy(), y_hat=y_hat.detach().contiguous().numpy(),
+             y_hat_comp=y_comp.detach().contiguous().numpy(), g_nn_out=seen['nn_out'].grad.numpy(),
+             m_new=m_new.numpy(), x_new=x_new.detach().numpy(), inp_per=inp_per.numpy(),
+             trivial=triv.numpy())
+
+
+if __name__ == "__main__":
+    main()

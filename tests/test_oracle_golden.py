@@ -1,0 +1,123 @@
+"""Pins the CPU oracle (oracle/mt_oracle.c) to the reference's golden vectors.
+
+The reference has no tests; the golden vectors were produced by running the
+unmodified reference in the build container (tests/golden/make_golden.py).
+Tolerances: bit-exact for index / mask logic; <= 1e-6 abs for fp32 values
+that go through the same operation order; reductions <= 1e-5 relative
+(the oracle accumulates in double, torch in blocked fp32).
+"""
+import numpy as np
+import pytest
+
+import cases
+import oracle
+from conftest import load_golden
+
+
+@pytest.mark.parametrize("name", sorted(cases.WARP_CASES))
+def test_align_set_and_dfpn_tail(name):
+    x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES[name])
+    g = load_golden("warp_" + name)
+    xa, va, vm = oracle.dfpn_align_tail(x, m, m_t, flow)
+    assert np.array_equal(va, g["v_aligned"])          # nearest: bit-exact
+    assert np.array_equal(vm, g["v_map"])
+    assert np.array_equal(xa, g["x_aligned"])          # same op order + FMA: bit-exact
+    xa2, va2 = oracle.align_set(x, 1 - m, flow)
+    assert np.array_equal(xa2, xa) and np.array_equal(va2, va)
+
+
+@pytest.mark.parametrize("name", sorted(cases.CPN_CASES))
+def test_cpn_align_tail(name):
+    x, m, m_t, theta = cases.cpn_inputs(cases.CPN_CASES[name])
+    g = load_golden("cpn_" + name)
+    b, _, f, h, w = x.shape
+    # (i) with the reference's own dense grid everything is bit-exact
+    xa, va, vm = oracle.cpn_align_tail(x, m, m_t, grid=g["grid"])
+    assert np.array_equal(xa, g["x_aligned"])
+    assert np.array_equal(va, g["v_aligned"])
+    assert np.array_equal(vm, g["v_map"])
+    # (ii) with theta: the oracle's affine grid follows torch's scalar
+    # linspace, ATen's vectorised linspace differs in the last ulp
+    grid = oracle.affine_grid(theta, h, w, False).reshape(b, f, h, w, 2)
+    assert np.abs(grid - g["grid"]).max() <= 2.5e-7
+    xa, va, vm = oracle.cpn_align_tail(x, m, m_t, theta=theta)
+    assert np.abs(xa - g["x_aligned"]).max() <= 1e-5
+    bad = va != g["v_aligned"]
+    # a threshold flip is only legitimate where the soft visibility is within
+    # float noise of the 0.5 threshold
+    assert np.all(np.abs(g["v_soft"][bad] - 0.5) <= 1e-5)
+    assert bad.mean() <= 2e-3
+    assert np.array_equal(vm != g["v_map"], bad & (vm != g["v_map"]))
+
+
+@pytest.mark.parametrize("name", sorted(cases.LOSS_CASES))
+def test_losses_and_backward(name):
+    x, m, flow, flow_gt, use, t, r_list = cases.loss_inputs(cases.LOSS_CASES[name])
+    g = load_golden("loss_" + name)
+    f = len(r_list)
+    mo = oracle.mask_out(flow)
+    assert np.array_equal(mo, g["mask_out"])
+    xa, _ = oracle.align_set(x[:, :, r_list], 1 - m[:, :, r_list], flow)
+    y_hat = np.repeat(x[:, :, t][:, :, None], f, axis=2)
+    mask = np.repeat((1 - m)[:, :, t][:, :, None], f, axis=2) * (1 - mo)
+    rec = oracle.masked_l1(y_hat, xa, mask, reduction="sum")
+    assert rec == pytest.approx(float(g["recons"]), rel=1e-5)
+    mean = oracle.masked_l1(y_hat, xa, mask, reduction="mean", weight=2.0)
+    assert mean == pytest.approx(float(g["mean_l1"]), rel=1e-5)
+    fl1 = oracle.masked_l1(flow, flow_gt, np.ones_like(flow), batch_mask=use)
+    assert fl1 == pytest.approx(float(g["flow_l1"]), rel=1e-5)
+    none = oracle.masked_l1(flow, flow_gt, np.ones_like(flow), batch_mask=np.zeros(len(use), bool))
+    assert none == 0.0 and g["none_selected"].shape == (1,) and float(g["none_selected"][0]) == 0.0
+    gxa = oracle.masked_l1_bwd(y_hat, xa, mask, reduction="sum")
+    assert np.abs(gxa - g["g_x_aligned"]).max() <= 1e-6 * max(1.0, np.abs(g["g_x_aligned"]).max())
+    gfl = oracle.align_set_bwd_flow(x[:, :, r_list], flow, gxa)
+    scale = np.abs(g["g_flow"]).max()
+    assert np.abs(gfl - g["g_flow"]).max() <= 2e-5 * scale
+    gfl1 = oracle.masked_l1_bwd(flow, flow_gt, np.ones_like(flow), batch_mask=use)
+    assert np.abs(-gfl1 - g["g_flow_l1"]).max() <= 1e-6 * np.abs(g["g_flow_l1"]).max() + 1e-12
+
+
+@pytest.mark.parametrize("name", sorted(cases.CORR_CASES))
+def test_corr4d(name):
+    ft, vt, fr, vr = cases.corr_inputs(cases.CORR_CASES[name])
+    g = load_golden("corr_" + name)
+    c = oracle.corr4d(ft, vt, fr, vr)
+    ref = g["corr"]
+    assert c.shape == ref.shape
+    assert np.abs(c - ref).max() <= 2e-6          # cosine values are <= 1
+    if vt is not None:                            # masked rows / cols are exactly 0
+        assert np.all(c[0, :, 0, :] == 0.0)
+
+
+@pytest.mark.parametrize("name", sorted(cases.CM_CASES))
+def test_cm_module(name):
+    cf, vt, va = cases.cm_inputs(cases.CM_CASES[name])
+    g = load_golden("cm_" + name)
+    out, cmask = oracle.cm_module(cf, vt, va)
+    assert np.abs(cmask - g["c_mask"]).max() <= 2e-6
+    if "out" in g:
+        assert np.abs(out - g["out"]).max() <= 1e-5
+    else:
+        assert np.abs(out.reshape(-1)[::53] - g["sample"]).max() <= 1e-5
+        assert out.astype(np.float64).sum() == pytest.approx(float(g["total"]), rel=1e-5, abs=1e-2)
+
+
+@pytest.mark.parametrize("name", sorted(cases.CHN_CASES))
+def test_chn(name):
+    x_t, v_t, x_al, v_al, v_map, nn_out = cases.chn_inputs(cases.CHN_CASES[name])
+    g = load_golden("chn_" + name)
+    b, _, f, h, w = x_al.shape
+    assert np.array_equal(oracle.chn_pack(x_t, v_t, x_al, v_al, v_map), g["nn_input"])
+    yh, yc = oracle.chn_composite(nn_out, x_t, v_t, b, f)
+    assert np.array_equal(yh, g["y_hat"])
+    assert np.array_equal(yc, g["y_hat_comp"])
+    r = cases.synth.rng(cases.CHN_CASES[name]["seed"] + 7)
+    gy = r.standard_normal(yh.shape).astype(np.float32)
+    gc = r.standard_normal(yh.shape).astype(np.float32)
+    gn = oracle.chn_composite_bwd(nn_out, v_t, gy, gc, b, f)
+    assert np.abs(gn - g["g_nn_out"]).max() <= 1e-6
+    m_new, x_new, per = oracle.hole_update(1 - v_t, v_map[:, :, 0], yc[:, :, 0])
+    assert np.array_equal(m_new, g["m_new"])
+    assert np.array_equal(x_new, g["x_new"])
+    assert per == pytest.approx(float(g["inp_per"]), rel=1e-5)
+    assert np.array_equal(oracle.trivial_copy(x_t, x_al, v_map), g["trivial"])
