@@ -1,0 +1,615 @@
+#!/usr/bin/env python
+"""bench.py - aligned frames/s of the frame-alignment hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input.  The
+default workload is BASELINE.json configs[1] (cfg2): CPN context-matching
+alignment, frames_n=5, batch_size=8, 256x256 = the CPN.align tail (affine warp
++ visibility + v_maps, model_cpn.py:75-89) on 32 (b, ref) frames followed by
+CM_Module (model_cpn.py:206-254) on their features.  Other workloads
+(--workload) cover the remaining configs' hot paths; see WORKLOADS.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the meaning
+of every key.  N > 1: launched under torchrun (one rank per GPU); the batch is
+sharded by sample, every rank runs the same per-GPU batch (weak scaling), no
+data-path collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------
+class Workload(object):
+    """Synthetic inputs + one hot-path step.  ``calls`` names the C-ABI calls of a
+    step in order with their algorithmic bytes and kernel launches."""
+    name = ""
+    describe = ""
+    frames_per_step = 0
+
+    def host_inputs(self, seed):
+        raise NotImplementedError
+
+    def gpu_step(self, mtb, d):
+        raise NotImplementedError
+
+    def cpu_step(self, tp, d):
+        raise NotImplementedError
+
+    def calls(self):
+        raise NotImplementedError
+
+
+class Cfg2(Workload):
+    """CPN alignment tail + context matching, B=8, frames_n=5, 256x256."""
+    name = "cfg2"
+
+    def __init__(self, b=8, f=4, h=256, w=256, c=128):
+        self.b, self.f, self.h, self.w, self.c = b, f, h, w, c
+        self.frames_per_step = b * f
+        self.describe = ("cfg2: CPN.align tail (affine warp+visibility+v_maps) + CM_Module, "
+                         "batch_size=%d frames_n=%d %dx%d c_feats=%dx%dx%d per GPU"
+                         % (b, f + 1, h, w, c, h // 4, w // 4))
+
+    def host_inputs(self, seed):
+        import numpy as np
+        from master_thesis_b200 import synth
+        b, f, h, w, c = self.b, self.f, self.h, self.w, self.c
+        x, m, _ = synth.frames(seed, b, f + 1, h, w)
+        t = (f + 1) // 2                                    # model_dfpn.py:471-473
+        refs = [i for i in range(f + 1) if i != t]
+        r = synth.rng(seed + 3)
+        return {
+            "x_refs": np.ascontiguousarray(x[:, :, refs]),
+            "m_refs": np.ascontiguousarray(m[:, :, refs]),
+            "m_target": np.ascontiguousarray(m[:, :, t]),
+            "v_target": np.ascontiguousarray(1 - m[:, :, t]),
+            "theta": synth.thetas(seed + 1, b * f, 0.1),
+            "c_feats": r.standard_normal((b, c, f + 1, h // 4, w // 4)).astype(np.float32),
+        }
+
+    inputs_h2d = ("x_refs", "m_refs", "m_target", "v_target", "theta", "c_feats")
+
+    def gpu_step(self, mtb, d):
+        xa, va, vm = mtb.cpn_align_tail(d["x_refs"], d["m_refs"], d["m_target"], d["theta"])
+        out, cmask = mtb.ops.cm_match(d["c_feats"], d["v_target"], va)
+        return {"x_aligned": xa, "v_aligned": va, "v_maps": vm, "cm_out": out, "c_mask": cmask}
+
+    def cpu_step(self, tp, d):
+        xa, va, vm = tp.cpn_align_tail(d["x_refs"], d["m_refs"], d["m_target"], d["theta"])
+        out, cmask = tp.cm_module(d["c_feats"], d["v_target"], va)
+        return xa, va, vm, out, cmask
+
+    def calls(self):
+        px = self.h * self.w
+        n = self.b * self.f
+        p = (self.h // 4) * (self.w // 4)
+        # a3 with in-kernel affine grid: 36*px + 4*px/F per frame (44px+4px/F minus the 8px grid)
+        warp = n * 36 * px + self.b * 4 * px
+        # a8 per sample: c_feats + full-res masks in; (2C+1)*P + P out
+        cm = self.b * (self.c * (self.f + 1) * p * 4 + (self.f + 1) * px * 4
+                       + (2 * self.c + 1) * p * 4 + p * 4)
+        return [("mt_warp_fwd", 1, warp, "hbm"), ("mt_cm_match_fwd", 4, cm, "hbm")]
+
+    def sub(self, b):
+        return Cfg2(b, self.f, self.h, self.w, self.c)
+
+
+class Cfg1(Workload):
+    """DFPN alignment hot path: masked correlation + flow warp, B=8, frames_n=2, 256x256."""
+    name = "cfg1"
+
+    def __init__(self, b=8, f=1, h=256, w=256):
+        self.b, self.f, self.h, self.w = b, f, h, w
+        self.frames_per_step = b * f
+        self.describe = ("cfg1: DFPN hot path (correlation_masked_4d 512x16x16 + align tail), "
+                         "batch_size=%d frames_n=%d %dx%d per GPU" % (b, f + 1, h, w))
+
+    def host_inputs(self, seed):
+        import numpy as np
+        from master_thesis_b200 import synth
+        b, f, h, w = self.b, self.f, self.h, self.w
+        x, m, _ = synth.frames(seed, b, f + 1, h, w)
+        t = (f + 1) // 2
+        refs = [i for i in range(f + 1) if i != t]
+        ft, vt, fr, vr = synth.vgg_feats(seed + 2, b, f)
+        return {
+            "x_refs": np.ascontiguousarray(x[:, :, refs]),
+            "m_refs": np.ascontiguousarray(m[:, :, refs]),
+            "m_target": np.ascontiguousarray(m[:, :, t]),
+            "flow": synth.dense_flow(seed + 1, b, f, h, w, 0.05, True),
+            "feats_t": ft, "v_t16": vt, "feats_r": fr, "v_r16": vr,
+        }
+
+    inputs_h2d = ("x_refs", "m_refs", "m_target", "flow", "feats_t", "v_t16", "feats_r", "v_r16")
+
+    def gpu_step(self, mtb, d):
+        corr = mtb.ops.corr4d(d["feats_t"], d["v_t16"], d["feats_r"], d["v_r16"])
+        xa, va, vm = mtb.dfpn_align_tail(d["x_refs"], d["m_refs"], d["m_target"], d["flow"])
+        return {"corr": corr, "x_aligned": xa, "v_aligned": va, "v_maps": vm}
+
+    def cpu_step(self, tp, d):
+        corr = tp.corr4d(d["feats_t"], d["v_t16"], d["feats_r"], d["v_r16"])
+        return (corr,) + tuple(tp.dfpn_align_tail(d["x_refs"], d["m_refs"], d["m_target"], d["flow"]))
+
+    def calls(self):
+        px = self.h * self.w
+        n = self.b * self.f
+        warp = n * 44 * px + self.b * 4 * px
+        corr = n * (524288 + 262144) + self.b * 524288 + (n + self.b) * 1024
+        return [("mt_corr4d_fwd", 3, corr, "hbm"), ("mt_warp_fwd", 1, warp, "hbm")]
+
+    def sub(self, b):
+        return Cfg1(b, self.f, self.h, self.w)
+
+
+class Cfg4(Workload):
+    """CHN inference hot path with the DFPN aligner on one DAVIS-shaped frame pair."""
+    name = "cfg4"
+
+    def __init__(self, b=1, f=1, h=480, w=854):
+        self.b, self.f, self.h, self.w = b, f, h, w
+        self.frames_per_step = b * f
+        self.describe = ("cfg4: CHN inference hot path, DFPN aligner (warp + pack + composite + "
+                         "hole update), batch_size=%d F=%d %dx%d per GPU" % (b, f, h, w))
+
+    def host_inputs(self, seed):
+        import numpy as np
+        from master_thesis_b200 import synth
+        b, f, h, w = self.b, self.f, self.h, self.w
+        x, m, _ = synth.frames(seed, b, f + 1, h, w)
+        return {
+            "x_target": np.ascontiguousarray(x[:, :, 0]),
+            "x_refs": np.ascontiguousarray(x[:, :, 1:]),
+            "m_refs": np.ascontiguousarray(m[:, :, 1:]),
+            "m_target": np.ascontiguousarray(m[:, :, 0]),
+            "v_target": np.ascontiguousarray(1 - m[:, :, 0]),
+            "flow": synth.dense_flow(seed + 1, b, f, h, w, 0.03, True),
+            "nn_out": synth.nn_output(seed + 2, b * f, h, w),
+        }
+
+    inputs_h2d = ("x_target", "x_refs", "m_refs", "m_target", "v_target", "flow", "nn_out")
+
+    def gpu_step(self, mtb, d):
+        ops = mtb.ops
+        xa, va, vm = mtb.dfpn_align_tail(d["x_refs"], d["m_refs"], d["m_target"], d["flow"])
+        nn_in = ops.chn_pack(d["x_target"], d["v_target"], xa, va, vm)
+        y_hat, y_comp = ops.chn_composite(d["nn_out"], d["x_target"], d["v_target"], self.b, self.f)
+        m_new, x_new, per = ops.hole_update(d["m_target"], vm[:, :, 0], y_comp[:, :, 0])
+        return {"nn_in": nn_in, "y_comp": y_comp, "m_new": m_new, "x_new": x_new, "inp_per": per}
+
+    def cpu_step(self, tp, d):
+        xa, va, vm = tp.dfpn_align_tail(d["x_refs"], d["m_refs"], d["m_target"], d["flow"])
+        nn_in = tp.chn_pack(d["x_target"], d["v_target"], xa, va, vm)
+        y_hat, y_comp = tp.chn_composite(d["nn_out"], d["x_target"], d["v_target"], self.b, self.f)
+        return nn_in, tp.hole_update(d["m_target"], vm[:, :, 0], y_comp[:, :, 0])
+
+    def calls(self):
+        px = self.h * self.w
+        n = self.b * self.f
+        return [("mt_warp_fwd", 1, n * 44 * px + self.b * 4 * px, "hbm"),
+                ("mt_chn_pack", 1, n * 56 * px + self.b * 16 * px, "hbm"),
+                ("mt_chn_composite_fwd", 1, n * 36 * px + self.b * 16 * px, "hbm"),
+                ("mt_hole_update", 1, self.b * 36 * px, "hbm")]
+
+    def sub(self, b):
+        return Cfg4(b, self.f, self.h, self.w)
+
+
+class Cfg3(Workload):
+    """DFPN training hot path: fused warp + mask_out + masked L1 forward and backward."""
+    name = "cfg3"
+
+    def __init__(self, b=32, f=4, h=256, w=256):
+        self.b, self.f, self.h, self.w = b, f, h, w
+        self.frames_per_step = b * f
+        self.describe = ("cfg3: DFPN training hot path (fused warp+mask_out+masked-L1 fwd and bwd "
+                         "w.r.t. flow), batch_size=%d frames_n=%d %dx%d per GPU" % (b, f + 1, h, w))
+
+    def host_inputs(self, seed):
+        import numpy as np
+        from master_thesis_b200 import synth
+        b, f, h, w = self.b, self.f, self.h, self.w
+        x, m, _ = synth.frames(seed, b, f + 1, h, w)
+        t = (f + 1) // 2
+        refs = [i for i in range(f + 1) if i != t]
+        return {
+            "x_target": np.ascontiguousarray(x[:, :, t]),
+            "v_target": np.ascontiguousarray(1 - m[:, :, t]),
+            "x_refs": np.ascontiguousarray(x[:, :, refs]),
+            "v_refs": np.ascontiguousarray(1 - m[:, :, refs]),
+            "flow": synth.dense_flow(seed + 1, b, f, h, w, 0.05, True),
+            "grad_out": np.ones(1, np.float32),
+        }
+
+    inputs_h2d = ("x_target", "v_target", "x_refs", "v_refs", "flow")
+
+    def gpu_step(self, mtb, d):
+        # the two launches autograd issues for LossesUtils.alignment_recons(...).backward()
+        out3, _, _, saved = mtb.ops.warp_l1_fwd_raw(d["x_refs"], d["v_refs"], d["flow"],
+                                                    d["x_target"], d["v_target"])
+        g = mtb.ops.warp_l1_bwd_raw(saved, d["grad_out"])
+        return {"loss": out3, "g_flow": g}
+
+    def cpu_step(self, tp, d):
+        import torch
+        flow = d["flow"].detach().requires_grad_(True)
+        loss = tp.alignment_recons(d["x_target"], d["v_target"], d["x_refs"], d["v_refs"], flow)
+        g, = torch.autograd.grad(loss, flow)
+        return loss, g
+
+    def calls(self):
+        px = self.h * self.w
+        n = self.b * self.f
+        # loss-only fused forward: 12+8 per frame + 16/F target; backward: + 8 written
+        return [("mt_warp_l1_fwd", 1, n * 20 * px + self.b * 16 * px, "hbm"),
+                ("mt_warp_l1_bwd", 1, n * 28 * px + self.b * 16 * px, "hbm")]
+
+    def sub(self, b):
+        return Cfg3(b, self.f, self.h, self.w)
+
+
+WORKLOADS = {"cfg1": Cfg1, "cfg2": Cfg2, "cfg3": Cfg3, "cfg4": Cfg4}
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, device_index, period=0.003):
+        super().__init__(daemon=True)
+        self.period, self.samples, self.reasons, self.ok = period, [], set(), False
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                if not uuid.startswith("GPU-"):
+                    uuid = "GPU-" + uuid
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:           # noqa: BLE001
+            log("clock sampling unavailable:", e)
+            self.max_mhz = None
+
+    def sample(self):
+        if not self.ok:
+            return
+        try:
+            self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            try:
+                bits = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                bits = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for bit, name in self.REASONS.items():
+                if bits & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._halt.is_set():
+            self.sample()
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arms
+# ---------------------------------------------------------------------------
+def cpu_time_workload(wl, seconds, threads=None, min_reps=2, max_reps=50):
+    """Times the torch-CPU port of the path (oracle/torch_port.py) on a bounded sample."""
+    import torch
+    from oracle import torch_port as tp
+    if threads:
+        torch.set_num_threads(threads)
+    d = {k: torch.from_numpy(v) for k, v in wl.host_inputs(1234).items()}
+    wl.cpu_step(tp, d)                       # warm-up
+    times, t_end = [], time.perf_counter() + seconds
+    while len(times) < min_reps or (time.perf_counter() < t_end and len(times) < max_reps):
+        t0 = time.perf_counter()
+        wl.cpu_step(tp, d)
+        times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return wl.frames_per_step / mean, mean, len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (torch-CPU port of
+    its call sequence; the Python reference itself cannot travel to the GPU box)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    from oracle import torch_port as tp
+    wl = WORKLOADS[args.workload]()
+    # bounded sample: shrink the batch until (steps + warmup) steps fit in ~150 s
+    d = {k: torch.from_numpy(v) for k, v in wl.host_inputs(1234).items()}
+    t0 = time.perf_counter()
+    wl.cpu_step(tp, d)
+    t1 = time.perf_counter() - t0
+    budget = 150.0
+    b = wl.b
+    while b > 1 and (args.steps + args.warmup) * t1 * (b / wl.b) > budget:
+        b = max(1, b // 2)
+    sample = wl.sub(b)
+    d = {k: torch.from_numpy(v) for k, v in sample.host_inputs(1234).items()}
+    for _ in range(args.warmup):
+        sample.cpu_step(tp, d)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sample.cpu_step(tp, d)
+    dt = time.perf_counter() - t0
+    value = sample.frames_per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "aligned_frames_per_sec", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.describe, "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(),
+                         "kind": "port",
+                         "sample": "%s at batch_size=%d (%d aligned frames per step), torch %s CPU"
+                                   % (wl.name, b, sample.frames_per_step, torch.__version__)},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import master_thesis_b200 as mtb
+    from master_thesis_b200 import _lib, ops
+    _lib.load()
+    wl = WORKLOADS[args.workload]()
+    calls = wl.calls()
+    hbm_peak, tf_peak, peak_src = measured_peaks()
+
+    # input sets rotate so that every step reads inputs last touched >= 2 steps ago
+    nsets = args.sets
+    host_sets = [wl.host_inputs(1000 * rank + 17 * i) for i in range(nsets)]
+    dsets = [{k: torch.from_numpy(v).to(dev) for k, v in hs.items()} for hs in host_sets]
+    step_bytes = sum(c[2] for c in calls)
+    plans, outs = [], []
+    for d in dsets:
+        with ops.record() as plan:
+            outs.append(wl.gpu_step(mtb, d))
+        plans.append(plan)
+    names = plans[0].names()
+    # group the recorded launches by C-ABI call
+    assert names == [c[0] for c in calls], (names, calls)
+    launches_per_step = sum(c[1] for c in calls)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        plans[i % nsets]()
+    barrier()
+
+    K = args.steps
+    stride = max(1, K // 256)                       # instrument <= 256 steps with per-call events
+    ev = {}
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record()
+    for i in range(K):
+        plan = plans[i % nsets]
+        if i % stride == 0:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(calls) + 1)]
+            evs[0].record()
+            for j in range(len(calls)):
+                plan.run_entry(j)
+                evs[j + 1].record()
+            ev[i] = evs
+        else:
+            plan()
+    e1.record()
+    sampler.sample()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = wl.frames_per_step * world * K / (ms * 1e-3)
+
+    # per-call device time inside the timed region
+    per_call = []
+    for j, (cname, nl, nbytes, bound) in enumerate(calls):
+        ts = [evs[j].elapsed_time(evs[j + 1]) for evs in ev.values()]
+        avg = sum(ts) / len(ts)
+        per_call.append({"call": cname, "launches": nl, "avg_us": 1e3 * avg,
+                         "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (avg * 1e-3) / 1e9,
+                         "frac_hbm": nbytes / (avg * 1e-3) / 1e9 / hbm_peak})
+    dom = max(per_call, key=lambda c: c["avg_us"])
+    roofline = {"bound": "hbm", "kernel": dom["call"], "launches_in_call": dom["launches"],
+                "achieved": dom["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": dom["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                "avg_us": dom["avg_us"], "algorithmic_bytes": dom["algorithmic_bytes"]}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(args.workload, {}).get(dom["call"])
+        except Exception:
+            pass
+
+    # ---- end-to-end: pinned host inputs -> H2D -> kernels -> D2H, every step ----
+    e2e = run_e2e(args, wl, mtb, ops, host_sets[0], dev, world)
+
+    line = {
+        "metric": "aligned_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.describe, "frames_per_step_per_gpu": wl.frames_per_step,
+                   "l2": "inputs rotate over %d buffer sets; %.0f MB algorithmic traffic per step, "
+                         ">= %.0f MB between reuses of a set (L2 = 126 MB)"
+                         % (nsets, step_bytes / 1e6, (nsets - 1) * step_bytes / 1e6),
+                   "sharding": "by sample, %d ranks, no data-path collective" % world},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K,
+        "roofline": roofline, "kernels": per_call,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = wl.sub(max(1, wl.b // 4)) if wl.b >= 4 else wl
+        v, mean, reps, cores = cpu_time_workload(sample, args.cpu_seconds)
+        line["cpu_baseline"] = {
+            "value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": "%s at batch_size=%d: %d reps of %.3f s (torch %s CPU port of the reference "
+                      "call sequence)" % (wl.name, sample.b, reps, mean, torch.__version__)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, wl, mtb, ops, host, dev, world):
+    """Same metric through the public API with HOST buffers: every step copies its inputs
+    from pinned host memory, runs the kernels, and copies every result back.  Two
+    pipeline slots (streams) overlap step i+1's H2D with step i's D2H."""
+    import torch
+    import torch.distributed as dist
+    slots = []
+    for _ in range(2):
+        st = torch.cuda.Stream(device=dev)
+        pin_in = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+        with torch.cuda.stream(st):
+            d_in = {k: torch.empty_like(v, device=dev) for k, v in pin_in.items()}
+            for k in d_in:
+                d_in[k].copy_(pin_in[k], non_blocking=True)
+            with ops.record() as plan:
+                out = wl.gpu_step(mtb, d_in)
+            out = {k: v for k, v in out.items()}
+            pin_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+        st.synchronize()
+        slots.append((st, pin_in, d_in, plan, out, pin_out))
+    h2d = sum(v.numel() * v.element_size() for v in slots[0][1].values())
+    d2h = sum(v.numel() * v.element_size() for v in slots[0][5].values())
+    K = min(args.steps, args.e2e_steps)
+
+    def one(i):
+        st, pin_in, d_in, plan, out, pin_out = slots[i % 2]
+        with torch.cuda.stream(st):
+            for k in d_in:
+                d_in[k].copy_(pin_in[k], non_blocking=True)
+            plan()
+            for k in out:
+                pin_out[k].copy_(out[k], non_blocking=True)
+
+    for i in range(4):
+        one(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    main = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    for st, *_ in slots:
+        st.wait_stream(main)
+    for i in range(K):
+        one(i)
+    for st, *_ in slots:
+        main.wait_stream(st)
+    e1.record(main)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": wl.frames_per_step * world * K / (ms * 1e-3), "unit": "frames/s",
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": K,
+            "ms_per_step": ms / K,
+            "api": "master_thesis_b200 plug-point mirrors on pinned host tensors, 2 pipelined streams"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--sets", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: re-launch under torchrun (the driver launches torchrun itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

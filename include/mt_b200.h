@@ -1,0 +1,225 @@
+/*
+ * mt_b200.h - C ABI of libmt_b200.so: the B200 (sm_100a) kernels for the
+ * frame-alignment / temporal-copying hot path of davidalvarezdlt/master_thesis.
+ *
+ * The reference has NO FFI / plugin registry for this path: its
+ * seams are late-bound Python attributes.  Each entry point below therefore
+ * cites the reference Python lines it replaces; INTEGRATION.md shows the
+ * ctypes stub + the one-line rebinding a maintainer adds.
+ *
+ * Conventions
+ *  - plain C: device pointers, int64 strides IN ELEMENTS, sizes, a
+ *    cudaStream_t passed as void*.  No torch types.  No allocation inside:
+ *    the caller owns inputs, outputs and the workspace.
+ *  - every function returns MT_OK (0) or a negative error code and records a
+ *    message readable with mt_last_error().  Nothing is launched on error.
+ *  - all tensors are fp32.  Masks / visibility maps are fp32 {0,1}.
+ *  - 5-D inputs are given as (B, C, F, H, W) with explicit strides for B, C,
+ *    F and a CONTIGUOUS (H, W) plane (stride_w == 1, stride_h == W); this
+ *    covers x[:, :, t] / x[:, :, r_list] views and the frame-major tensors
+ *    this library itself produces.
+ *  - "frame-major" outputs: x_aligned is written as contiguous (B, F, C, H, W)
+ *    memory, i.e. exactly the memory the reference's
+ *    `.reshape(b, -1, 3, h, w).transpose(1, 2)` view has (utils.py:97); the
+ *    host shim returns the same transposed view, logical shape (B, C, F, H, W).
+ *  - kernels launch asynchronously on `stream`; no host synchronisation.
+ */
+#ifndef MT_B200_H
+#define MT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MT_OK 0
+#define MT_ERR_INVALID (-1)   /* bad argument (shape, NULL, unsupported C)   */
+#define MT_ERR_CUDA (-2)      /* a CUDA runtime call failed                  */
+#define MT_ERR_NO_DEVICE (-3) /* no sm_100 device / kernel image not loadable */
+
+typedef void *mt_stream_t; /* cudaStream_t */
+
+#define MT_API __attribute__((visibility("default")))
+
+/* flags of mt_warp_fwd / mt_warp_bwd_grid */
+#define MT_ALIGN_CORNERS 1 /* grid_sample(align_corners=True)  [DFPN, utils.py:95]  */
+#define MT_VIS_BILINEAR 2  /* v_aligned = bilinear(v) > 0.5    [CPN, model_cpn.py:84-88];
+                              default: nearest, half-to-even    [DFPN, utils.py:98-103] */
+#define MT_GRID_AFFINE 4   /* `grid` holds theta (B*F, 2, 3); the kernel generates
+                              affine_grid(theta, align_corners) [model_cpn.py:75-77]    */
+#define MT_VIS_FROM_MASK 8 /* `vis` holds masks m; v = 1 - m is formed on load
+                              [model_dfpn.py:129, model_cpn.py:85]                       */
+
+/* reduction modes of mt_masked_l1_* (utils.py:166-169) */
+#define MT_REDUCE_MEAN 0
+#define MT_REDUCE_SUM 1
+
+MT_API int mt_version(void);
+MT_API const char *mt_last_error(void);
+/* sm count and compute capability of the current device */
+MT_API int mt_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* bytes of zero-initialised device workspace the reducing kernels need; the
+   kernels leave it zeroed again, so it is allocated and cleared ONCE. */
+MT_API int64_t mt_workspace_bytes(void);
+
+/* ---- K1  flow-guided warp + visibility + v_map ---------------------------
+ * replaces  FlowsUtils.align_set                    utils.py:78-104      (a1)
+ *           DFPN.align tail                         model_dfpn.py:128-133 (a2)
+ *           CPN.align tail                          model_cpn.py:75-89    (a3)
+ * x        (B,C,F,H,W) strided, C in {1,3}
+ * vis      (B,1,F,H,W) strided: visibility maps, or masks with MT_VIS_FROM_MASK
+ * grid     dense absolute flow (B,F,H,W,2) contiguous, or theta (B*F,2,3)
+ * m_target (B,1,H,W) or NULL (then v_map must be NULL)
+ * x_aligned strided (xa_sb, xa_sc, xa_sf; plane contiguous) - the host shim
+ *          passes frame-major strides (F*C*P, P, C*P); v_aligned, v_map
+ *          (B,F,H,W) contiguous; v_map = clamp(v_aligned - (1 - m_target), 0, 1);
+ *          any output may be NULL.
+ */
+MT_API int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
+                const float *vis, int64_t vis_sb, int64_t vis_sf,
+                const float *grid, const float *m_target, int64_t mt_sb,
+                float *x_aligned, int64_t xa_sb, int64_t xa_sc, int64_t xa_sf,
+                float *v_aligned, float *v_map,
+                int B, int C, int F, int H, int W, int flags, mt_stream_t stream);
+
+/* ---- K1b  backward of the bilinear warp w.r.t. the dense grid ------------
+ * replaces autograd of F.grid_sample in align_set (utils.py:93-97)       (a6)
+ * gout (B,C,F,H,W) strided (plane contiguous) -> ggrid (B,F,H,W,2) contiguous.
+ * No gradient to x (the reference never needs it: x has no grad). */
+MT_API int mt_warp_bwd_grid(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
+                     const float *grid,
+                     const float *gout, int64_t g_sb, int64_t g_sc, int64_t g_sf,
+                     float *ggrid, int B, int C, int F, int H, int W, int flags,
+                     mt_stream_t stream);
+
+/* ---- K1c  fused warp + mask_out + masked-L1 ('sum') forward --------------
+ * replaces align_set (utils.py:78-104) + mask_out (model_dfpn.py:269-272) +
+ * masked_l1(x_t repeated, x_aligned, v_t * (1 - mask_out), 'sum')
+ * (model_dfpn.py:274-287, utils.py:166-169)                      (a1+a4+a5)
+ * x_target (B,3,H,W), v_target (B,1,H,W): target frame and its visibility.
+ * x_aligned / v_aligned may be NULL (loss-only).  out3[0] = loss,
+ * out3[1] = sum|.|, out3[2] = sum(mask)  (device floats).
+ * workspace: mt_workspace_bytes() of zeroed device memory. */
+MT_API int mt_warp_l1_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
+                   const float *vis, int64_t vis_sb, int64_t vis_sf,
+                   const float *flow,
+                   const float *x_target, int64_t xt_sb, int64_t xt_sc,
+                   const float *v_target, int64_t vt_sb,
+                   float *x_aligned, float *v_aligned, float *out3, void *workspace,
+                   int B, int F, int H, int W, float weight, int flags, mt_stream_t stream);
+
+/* backward of K1c w.r.t. the flow: one pass, no x_aligned / grad tensors (a6).
+ * out3 = forward's out3 (uses sum(mask)); grad_out: device scalar (upstream). */
+MT_API int mt_warp_l1_bwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
+                   const float *flow,
+                   const float *x_target, int64_t xt_sb, int64_t xt_sc,
+                   const float *v_target, int64_t vt_sb,
+                   const float *out3, const float *grad_out, float *gflow,
+                   int B, int F, int H, int W, float weight, int flags, mt_stream_t stream);
+
+/* ---- mask_out  (model_dfpn.py:269-272)                               (a4)
+ * flow (n,2) -> out (n) = clamp((gx<-1)+(gx>1)+(gy<-1)+(gy>1), 0, 1) */
+MT_API int mt_mask_out(const float *flow, int64_t n, float *out, mt_stream_t stream);
+
+/* ---- masked L1  (LossesUtils.masked_l1, utils.py:139-169)            (a5)
+ * y_hat, y: (B,C,F,P) strided (P contiguous); mask: (B,mask_c,F,P), mask_c in
+ * {1,C}.  batch_mask: B device bytes or NULL (selection without the
+ * reference's host sync, utils.py:158-165).  out3[0] = weight * l1 / den with
+ * den = sum(mask)+1e-9 ('sum') or numel ('mean'); out3[1] = sum|.|;
+ * out3[2] = den.  0 if nothing is selected. */
+MT_API int mt_masked_l1_fwd(const float *y_hat, int64_t a_sb, int64_t a_sc, int64_t a_sf,
+                     const float *y, int64_t b_sb, int64_t b_sc, int64_t b_sf,
+                     const float *mask, int64_t m_sb, int64_t m_sc, int64_t m_sf,
+                     const uint8_t *batch_mask, float *out3, void *workspace,
+                     int B, int C, int F, int64_t P, int mask_c, int reduction, float weight,
+                     mt_stream_t stream);
+/* grads (contiguous (B,C,F,P)); either may be NULL. grad_y = -grad_y_hat. */
+MT_API int mt_masked_l1_bwd(const float *y_hat, int64_t a_sb, int64_t a_sc, int64_t a_sf,
+                     const float *y, int64_t b_sb, int64_t b_sc, int64_t b_sf,
+                     const float *mask, int64_t m_sb, int64_t m_sc, int64_t m_sf,
+                     const uint8_t *batch_mask, const float *out3, const float *grad_out,
+                     float *grad_y_hat, float *grad_y,
+                     int B, int C, int F, int64_t P, int mask_c, int reduction, float weight,
+                     mt_stream_t stream);
+
+/* ---- K2  masked cosine correlation on tcgen05 ----------------------------
+ * replaces CorrelationVGG.correlation_masked_4d  model_dfpn.py:534-565  (a7)
+ * feats_t (B,C,P) contiguous, v_t (B,P) or NULL, feats_r (B,C,F,P) contiguous,
+ * v_r (B,F,P) or NULL, P = h*w.  out (B,F,P,P).  Shapes for which
+ * mt_corr4d_uses_tensor_cores(C, P) is 1 run on tcgen05 (TF32 inputs, fp32
+ * accumulate); every other shape runs an fp32 SIMT kernel.
+ * workspace: mt_corr4d_workspace_bytes(B, C, F, P) bytes. */
+MT_API int mt_corr4d_fwd(const float *feats_t, const float *v_t, const float *feats_r, const float *v_r,
+                  float *out, void *workspace, int64_t workspace_bytes,
+                  int B, int C, int F, int P, mt_stream_t stream);
+MT_API int64_t mt_corr4d_workspace_bytes(int B, int C, int F, int P);
+/* 1 if the tcgen05 path serves this shape, 0 if the SIMT fallback does */
+MT_API int mt_corr4d_uses_tensor_cores(int C, int P);
+
+/* ---- K3  CPN context matching --------------------------------------------
+ * replaces CM_Module.forward + masked_softmax   model_cpn.py:206-254    (a8)
+ * c_feats (B,C,f,h,w) contiguous (index 0 of f = target), v_t (B,1,H,W),
+ * v_aligned (B,1,f-1,H,W) contiguous.  out (B,2C+1,h,w) = cat[c_t,c_out,c_mask],
+ * c_mask (B,1,h,w).  1 <= f-1 <= 8, h*w % 4 == 0.
+ * workspace: mt_cm_workspace_bytes(B, C, f, h, w) bytes (no zeroing needed). */
+MT_API int mt_cm_match_fwd(const float *c_feats, const float *v_t, const float *v_aligned,
+                    float *out, float *c_mask, void *workspace,
+                    int B, int C, int f, int h, int w, int H, int W, mt_stream_t stream);
+MT_API int64_t mt_cm_workspace_bytes(int B, int C, int f, int h, int w);
+/* the (B, f-1) similarities the last mt_cm_match_fwd left in its workspace */
+MT_API const float *mt_cm_workspace_gs(const void *workspace, int B, int C, int f, int h, int w);
+
+/* ---- K4  CHN pack / composite / hole update ------------------------------
+ * mt_chn_pack         replaces CHN.forward model_chn.py:68-80           (a9)
+ *   x_t (B,3,H,W), v_t (B,1,H,W), x_al (B,3,F,H,W) strided, v_al, v_map
+ *   (B,1,F,H,W) strided -> nn_in (B*F,9,H,W) contiguous NCHW for cuDNN.
+ * mt_chn_composite_fwd replaces model_chn.py:80-85                      (a10)
+ *   nn_out (B*F,3,H,W) -> y_hat, y_comp as frame-major (B,F,3,H,W).
+ * mt_chn_composite_bwd: g_nn (B*F,3,H,W) from grads of both outputs
+ *   ((B,3,F,H,W) strided; either may be NULL).
+ * mt_hole_update      replaces model_chn.py:128-131,181-186,242-248     (a11)
+ *   m_new = m_t - v_map0; x_new = (1-m_new)*y_comp0 + m_new*fill;
+ *   inp_per[0] = sum(m_new)*100/numel (device float, no host sync).
+ * mt_trivial_copy     replaces model_dfpn.py:427-429                    (a12)
+ */
+MT_API int mt_chn_pack(const float *x_t, int64_t xt_sb, int64_t xt_sc, const float *v_t, int64_t vt_sb,
+                const float *x_al, int64_t xa_sb, int64_t xa_sc, int64_t xa_sf,
+                const float *v_al, int64_t va_sb, int64_t va_sf,
+                const float *v_map, int64_t vm_sb, int64_t vm_sf,
+                float *nn_in, int B, int F, int64_t P, mt_stream_t stream);
+MT_API int mt_chn_composite_fwd(const float *nn_out, const float *x_t, int64_t xt_sb, int64_t xt_sc,
+                         const float *v_t, int64_t vt_sb, float *y_hat, float *y_comp,
+                         int B, int F, int64_t P, mt_stream_t stream);
+MT_API int mt_chn_composite_bwd(const float *nn_out, const float *v_t, int64_t vt_sb,
+                         const float *g_yhat, int64_t gy_sb, int64_t gy_sc, int64_t gy_sf,
+                         const float *g_comp, int64_t gc_sb, int64_t gc_sc, int64_t gc_sf,
+                         float *g_nn, int B, int F, int64_t P, mt_stream_t stream);
+MT_API int mt_hole_update(const float *m_t, int64_t mt_sb, const float *v_map0, int64_t vm_sb,
+                   const float *y_comp0, int64_t yc_sb, int64_t yc_sc,
+                   float *m_new, float *x_new, float *inp_per, void *workspace,
+                   int B, int64_t P, mt_stream_t stream);
+MT_API int mt_trivial_copy(const float *x_t, int64_t xt_sb, int64_t xt_sc,
+                    const float *x_al, int64_t xa_sb, int64_t xa_sc, int64_t xa_sf,
+                    const float *v_map, int64_t vm_sb, int64_t vm_sf,
+                    float *y, int B, int F, int64_t P, mt_stream_t stream);
+
+/* ---- host-buffer entry points (end-to-end: H2D + kernels + D2H inside) ----
+ * The reference-facing calls with HOST memory, used for the e2e metric.
+ * All pointers are host pointers (pinned memory recommended); tensors are
+ * contiguous in the reference's logical layouts.  The call is synchronous.
+ * mt_cpn_align_host:  a3 on (B,3,F,H,W)/(B,1,F,H,W)/(B,1,H,W)/theta (B*F,2,3)
+ *                     -> x_aligned (B,3,F,H,W), v_aligned, v_maps (B,1,F,H,W).
+ * mt_dfpn_align_host: a1+a2 with a dense flow (B,F,H,W,2).
+ */
+MT_API int mt_cpn_align_host(const float *x_refs, const float *m_refs, const float *m_target,
+                      const float *theta, float *x_aligned, float *v_aligned, float *v_maps,
+                      int B, int F, int H, int W);
+MT_API int mt_dfpn_align_host(const float *x_refs, const float *m_refs, const float *m_target,
+                       const float *flow, float *x_aligned, float *v_aligned, float *v_maps,
+                       int B, int F, int H, int W);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MT_B200_H */

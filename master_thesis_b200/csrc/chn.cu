@@ -1,0 +1,466 @@
+// chn.cu - K4: CHN pack / composite / hole update / trivial copy, and the
+// generic masked-L1 loss (forward reduction + backward).
+//
+// Replaces (reference file:line):
+//   CHN.forward pack                 master_thesis/model_chn.py:68-80     (a9)
+//   CHN.forward composite            master_thesis/model_chn.py:80-85     (a10)
+//   hole update in CHN.inpaint_*     master_thesis/model_chn.py:128-131,181-186,242-248 (a11)
+//   DFPN._log_frames trivial copy    master_thesis/model_dfpn.py:427-429  (a12)
+//   LossesUtils.masked_l1            master_thesis/utils.py:139-169       (a5)
+//
+// All are touch-once streaming kernels: one thread owns VEC = 4 consecutive
+// pixels of a plane, 16 B streaming loads/stores, grid sized to the data.
+// Arithmetic is written un-fused (-fmad=false) in the reference's operation
+// order, so the outputs are bit-identical to eager PyTorch on the CPU.
+#include "mt_common.cuh"
+
+namespace mt {
+namespace {
+
+bool mult4(int64_t v) { return (v & 3) == 0; }
+
+// ---- a9 pack ----------------------------------------------------------------
+struct PackArgs {
+    const float *x_t; int64_t xt_sb, xt_sc;
+    const float *v_t; int64_t vt_sb;
+    const float *x_al; int64_t xa_sb, xa_sc, xa_sf;
+    const float *v_al; int64_t va_sb, va_sf;
+    const float *v_map; int64_t vm_sb, vm_sf;
+    float *nn_in;
+    int F; int64_t P;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) chn_pack_kernel(const PackArgs a) {
+    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (p0 >= a.P) return;
+    const int n = blockIdx.y, b = n / a.F, f = n - b * a.F;
+    float *o = a.nn_in + (int64_t)n * 9 * a.P + p0;
+    Vec<VEC> t[3], r[3], vt, va, vm;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        t[c].load_cached(a.x_t + b * a.xt_sb + c * a.xt_sc + p0);  // re-read F times: keep in L1/L2
+        r[c].load_stream(a.x_al + b * a.xa_sb + c * a.xa_sc + f * a.xa_sf + p0);
+    }
+    vt.load_cached(a.v_t + b * a.vt_sb + p0);
+    va.load_stream(a.v_al + b * a.va_sb + f * a.va_sf + p0);
+    vm.load_stream(a.v_map + b * a.vm_sb + f * a.vm_sf + p0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float m = chan_mean(c), s = chan_std(c);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {  // (x - mean) / std   model_chn.py:73-74
+            t[c].v[i] = __fdiv_rn(__fsub_rn(t[c].v[i], m), s);
+            r[c].v[i] = __fdiv_rn(__fsub_rn(r[c].v[i], m), s);
+        }
+        t[c].store_stream(o + c * a.P);
+        r[c].store_stream(o + (3 + c) * a.P);
+    }
+    vt.store_stream(o + 6 * a.P);
+    va.store_stream(o + 7 * a.P);
+    vm.store_stream(o + 8 * a.P);
+}
+
+// ---- a10 composite ------------------------------------------------------------
+struct CompArgs {
+    const float *nn_out;
+    const float *x_t; int64_t xt_sb, xt_sc;
+    const float *v_t; int64_t vt_sb;
+    float *y_hat, *y_comp;  // frame-major (B,F,3,P)
+    const float *g_yhat; int64_t gy_sb, gy_sc, gy_sf;
+    const float *g_comp; int64_t gc_sb, gc_sc, gc_sf;
+    float *g_nn;
+    int F; int64_t P;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) chn_composite_fwd_kernel(const CompArgs a) {
+    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (p0 >= a.P) return;
+    const int n = blockIdx.y, b = n / a.F;
+    Vec<VEC> vt;
+    vt.load_cached(a.v_t + b * a.vt_sb + p0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        Vec<VEC> o, xt, yh, yc;
+        o.load_stream(a.nn_out + ((int64_t)n * 3 + c) * a.P + p0);
+        xt.load_cached(a.x_t + b * a.xt_sb + c * a.xt_sc + p0);
+        const float m = chan_mean(c), s = chan_std(c);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            yh.v[i] = clamp01(__fadd_rn(__fmul_rn(o.v[i], s), m));            // :83
+            yc.v[i] = __fadd_rn(__fmul_rn(vt.v[i], xt.v[i]),                   // :84
+                                __fmul_rn(__fsub_rn(1.0f, vt.v[i]), yh.v[i]));
+        }
+        yh.store_stream(a.y_hat + ((int64_t)n * 3 + c) * a.P + p0);
+        yc.store_stream(a.y_comp + ((int64_t)n * 3 + c) * a.P + p0);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) chn_composite_bwd_kernel(const CompArgs a) {
+    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (p0 >= a.P) return;
+    const int n = blockIdx.y, b = n / a.F, f = n - b * a.F;
+    Vec<VEC> vt;
+    vt.load_cached(a.v_t + b * a.vt_sb + p0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        Vec<VEC> o, gy, gc, g;
+        o.load_stream(a.nn_out + ((int64_t)n * 3 + c) * a.P + p0);
+        if (a.g_yhat) gy.load_stream(a.g_yhat + b * a.gy_sb + c * a.gy_sc + f * a.gy_sf + p0);
+        if (a.g_comp) gc.load_stream(a.g_comp + b * a.gc_sb + c * a.gc_sc + f * a.gc_sf + p0);
+        const float m = chan_mean(c), s = chan_std(c);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float pre = __fadd_rn(__fmul_rn(o.v[i], s), m);
+            float gg = 0.0f;
+            if (a.g_yhat) gg = gy.v[i];
+            if (a.g_comp) gg = __fadd_rn(gg, __fmul_rn(__fsub_rn(1.0f, vt.v[i]), gc.v[i]));
+            g.v[i] = (pre >= 0.0f && pre <= 1.0f) ? __fmul_rn(gg, s) : 0.0f;  // clamp passes grad on [0,1]
+        }
+        g.store_stream(a.g_nn + ((int64_t)n * 3 + c) * a.P + p0);
+    }
+}
+
+// ---- a11 hole update ------------------------------------------------------------
+struct HoleArgs {
+    const float *m_t; int64_t mt_sb;
+    const float *v_map0; int64_t vm_sb;
+    const float *y_comp0; int64_t yc_sb, yc_sc;
+    float *m_new, *x_new, *inp_per;
+    void *ws;
+    int B; int64_t P; int chunks; int64_t total_chunks;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) hole_update_kernel(const HoleArgs a) {
+    __shared__ float red[32];
+    float acc[1] = {0.0f};
+    for (int64_t ch = blockIdx.x; ch < a.total_chunks; ch += gridDim.x) {
+        const int b = (int)(ch / a.chunks);
+        const int64_t p0 = ((ch - (int64_t)b * a.chunks) * blockDim.x + threadIdx.x) * VEC;
+        if (p0 >= a.P) continue;
+        Vec<VEC> m, vm;
+        m.load_stream(a.m_t + b * a.mt_sb + p0);
+        vm.load_stream(a.v_map0 + b * a.vm_sb + p0);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            m.v[i] = __fsub_rn(m.v[i], vm.v[i]);  // m_t - v_map[:, :, 0]       :128
+            acc[0] += m.v[i];
+        }
+        m.store_stream(a.m_new + (int64_t)b * a.P + p0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Vec<VEC> y;
+            y.load_stream(a.y_comp0 + b * a.yc_sb + c * a.yc_sc + p0);
+            const float fill = chan_mean(c);  // fill colour == mean, model_chn.py:102-104
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)    // (1 - m)*y_comp + m*fill                :129-130
+                y.v[i] = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, m.v[i]), y.v[i]), __fmul_rn(m.v[i], fill));
+            y.store_stream(a.x_new + ((int64_t)b * 3 + c) * a.P + p0);
+        }
+    }
+    float *out = a.inp_per;
+    const float numel = (float)((double)a.B * (double)a.P);
+    grid_reduce_finish<1>(acc, a.ws, red, [out, numel](const double *tot) {
+        out[0] = (float)tot[0] * 100.0f / numel;  // sum(m)*100/numel               :131
+    });
+}
+
+// ---- a12 trivial copy ------------------------------------------------------------
+struct TrivArgs {
+    const float *x_t; int64_t xt_sb, xt_sc;
+    const float *x_al; int64_t xa_sb, xa_sc, xa_sf;
+    const float *v_map; int64_t vm_sb, vm_sf;
+    float *y;  // (B,3,F,P) contiguous
+    int F; int64_t P;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) trivial_copy_kernel(const TrivArgs a) {
+    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (p0 >= a.P) return;
+    const int n = blockIdx.y, b = n / a.F, f = n - b * a.F;
+    Vec<VEC> vm;
+    vm.load_stream(a.v_map + b * a.vm_sb + f * a.vm_sf + p0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        Vec<VEC> xt, xa;
+        xt.load_cached(a.x_t + b * a.xt_sb + c * a.xt_sc + p0);
+        xa.load_stream(a.x_al + b * a.xa_sb + c * a.xa_sc + f * a.xa_sf + p0);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)  // x_t*(1 - v_map) + x_al*v_map
+            xt.v[i] = __fadd_rn(__fmul_rn(xt.v[i], __fsub_rn(1.0f, vm.v[i])), __fmul_rn(xa.v[i], vm.v[i]));
+        xt.store_stream(a.y + (((int64_t)b * 3 + c) * a.F + f) * a.P + p0);
+    }
+}
+
+// ---- a5 masked L1 -------------------------------------------------------------
+struct L1Args {
+    const float *a; int64_t a_sb, a_sc, a_sf;
+    const float *b; int64_t b_sb, b_sc, b_sf;
+    const float *m; int64_t m_sb, m_sc, m_sf;
+    const uint8_t *bm;
+    float *out3; void *ws;
+    const float *out3_in; const float *grad_out; float *ga, *gb;
+    int B, C, F; int64_t P; int mask_c, reduction; float weight;
+    int chunks; int64_t total_chunks;  // over (B, F, chunk)
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) masked_l1_fwd_kernel(const L1Args a) {
+    __shared__ float red[3 * 32];
+    float acc[3] = {0.0f, 0.0f, 0.0f};  // sum |.|, sum(mask), selected element count / P-chunks
+    for (int64_t ch = blockIdx.x; ch < a.total_chunks; ch += gridDim.x) {
+        const int64_t bf = ch / a.chunks;
+        const int b = (int)(bf / a.F), f = (int)(bf - (int64_t)b * a.F);
+        if (a.bm && !a.bm[b]) continue;
+        const int64_t p0 = ((ch - bf * a.chunks) * blockDim.x + threadIdx.x) * VEC;
+        if (p0 >= a.P) continue;
+        Vec<VEC> mk;
+        if (a.mask_c == 1) {
+            mk.load_stream(a.m + b * a.m_sb + f * a.m_sf + p0);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[1] += mk.v[i];
+        }
+        for (int c = 0; c < a.C; ++c) {
+            if (a.mask_c != 1) {
+                mk.load_stream(a.m + b * a.m_sb + c * a.m_sc + f * a.m_sf + p0);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[1] += mk.v[i];
+            }
+            Vec<VEC> ya, yb;
+            ya.load_stream(a.a + b * a.a_sb + c * a.a_sc + f * a.a_sf + p0);
+            yb.load_stream(a.b + b * a.b_sb + c * a.b_sc + f * a.b_sf + p0);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)  // |y_hat*mask - y*mask|   utils.py:166
+                acc[0] += fabsf(__fsub_rn(__fmul_rn(ya.v[i], mk.v[i]), __fmul_rn(yb.v[i], mk.v[i])));
+        }
+    }
+    // selected batch items (for the 'mean' divisor), counted once by CTA 0
+    if (blockIdx.x == 0) {
+        for (int b = threadIdx.x; b < a.B; b += blockDim.x)
+            if (!a.bm || a.bm[b]) acc[2] += 1.0f;
+    }
+    float *out3 = a.out3;
+    const float weight = a.weight;
+    const int reduction = a.reduction;
+    const double per_item = (double)a.C * (double)a.F * (double)a.P;
+    grid_reduce_finish<3>(acc, a.ws, red, [out3, weight, reduction, per_item](const double *tot) {
+        const float num = (float)tot[0];
+        if (tot[2] == 0.0) {  // nothing selected: zeros(1)   utils.py:158-159
+            out3[0] = 0.0f; out3[1] = 0.0f; out3[2] = 1.0f;
+            return;
+        }
+        const float den = reduction == MT_REDUCE_SUM ? (float)tot[1] + 1e-9f : (float)(tot[2] * per_item);
+        out3[0] = weight * (reduction == MT_REDUCE_SUM ? num / den : (float)(tot[0] / (tot[2] * per_item)));
+        out3[1] = num;
+        out3[2] = den;
+    });
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) masked_l1_bwd_kernel(const L1Args a) {
+    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (p0 >= a.P) return;
+    const int bf = blockIdx.y, b = bf / a.F, f = bf - b * a.F;
+    const bool sel = !a.bm || a.bm[b];
+    const float scale = a.weight * __ldg(a.grad_out) / __ldg(a.out3_in + 2);
+    for (int c = 0; c < a.C; ++c) {
+        Vec<VEC> g;
+        if (sel) {
+            Vec<VEC> mk, ya, yb;
+            mk.load_stream(a.m + b * a.m_sb + (a.mask_c == 1 ? 0 : c) * a.m_sc + f * a.m_sf + p0);
+            ya.load_stream(a.a + b * a.a_sb + c * a.a_sc + f * a.a_sf + p0);
+            yb.load_stream(a.b + b * a.b_sb + c * a.b_sc + f * a.b_sf + p0);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float d = __fsub_rn(__fmul_rn(ya.v[i], mk.v[i]), __fmul_rn(yb.v[i], mk.v[i]));
+                const float sg = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+                g.v[i] = sg * mk.v[i] * scale;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) g.v[i] = 0.0f;
+        }
+        const int64_t o = (((int64_t)b * a.C + c) * a.F + f) * a.P + p0;
+        if (a.ga) g.store_stream(a.ga + o);
+        if (a.gb) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) g.v[i] = -g.v[i];
+            g.store_stream(a.gb + o);
+        }
+    }
+}
+
+int reduce_blocks(int64_t total) {
+    int64_t want = (int64_t)sm_count() * 8;
+    int64_t n = total < want ? total : want;
+    if (n > kMaxReduceBlocks) n = kMaxReduceBlocks;
+    return n < 1 ? 1 : (int)n;
+}
+
+}  // namespace
+}  // namespace mt
+
+using namespace mt;
+
+extern "C" int mt_chn_pack(const float *x_t, int64_t xt_sb, int64_t xt_sc, const float *v_t,
+                           int64_t vt_sb, const float *x_al, int64_t xa_sb, int64_t xa_sc,
+                           int64_t xa_sf, const float *v_al, int64_t va_sb, int64_t va_sf,
+                           const float *v_map, int64_t vm_sb, int64_t vm_sf, float *nn_in, int B,
+                           int F, int64_t P, mt_stream_t stream) {
+    MT_REQUIRE(x_t && v_t && x_al && v_al && v_map && nn_in, "mt_chn_pack: NULL argument");
+    MT_REQUIRE(B > 0 && F > 0 && P > 0 && (int64_t)B * F <= 65535, "mt_chn_pack: bad shape");
+    PackArgs a{x_t, xt_sb, xt_sc, v_t, vt_sb, x_al, xa_sb, xa_sc, xa_sf, v_al, va_sb, va_sf,
+               v_map, vm_sb, vm_sf, nn_in, F, P};
+    bool v4 = mult4(P) && aligned16(x_t) && aligned16(v_t) && aligned16(x_al) && aligned16(v_al) &&
+              aligned16(v_map) && aligned16(nn_in) && mult4(xt_sb) && mult4(xt_sc) && mult4(vt_sb) &&
+              mult4(xa_sb) && mult4(xa_sc) && mult4(xa_sf) && mult4(va_sb) && mult4(va_sf) &&
+              mult4(vm_sb) && mult4(vm_sf);
+    const int vec = v4 ? 4 : 1;
+    dim3 grid((unsigned)((P + 256 * vec - 1) / (256 * vec)), B * F);
+    if (v4) chn_pack_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else chn_pack_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_status("mt_chn_pack");
+}
+
+extern "C" int mt_chn_composite_fwd(const float *nn_out, const float *x_t, int64_t xt_sb,
+                                    int64_t xt_sc, const float *v_t, int64_t vt_sb, float *y_hat,
+                                    float *y_comp, int B, int F, int64_t P, mt_stream_t stream) {
+    MT_REQUIRE(nn_out && x_t && v_t && y_hat && y_comp, "mt_chn_composite_fwd: NULL argument");
+    MT_REQUIRE(B > 0 && F > 0 && P > 0 && (int64_t)B * F <= 65535, "mt_chn_composite_fwd: bad shape");
+    CompArgs a{};
+    a.nn_out = nn_out; a.x_t = x_t; a.xt_sb = xt_sb; a.xt_sc = xt_sc; a.v_t = v_t; a.vt_sb = vt_sb;
+    a.y_hat = y_hat; a.y_comp = y_comp; a.F = F; a.P = P;
+    bool v4 = mult4(P) && aligned16(nn_out) && aligned16(x_t) && aligned16(v_t) && aligned16(y_hat) &&
+              aligned16(y_comp) && mult4(xt_sb) && mult4(xt_sc) && mult4(vt_sb);
+    const int vec = v4 ? 4 : 1;
+    dim3 grid((unsigned)((P + 256 * vec - 1) / (256 * vec)), B * F);
+    if (v4) chn_composite_fwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else chn_composite_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_status("mt_chn_composite_fwd");
+}
+
+extern "C" int mt_chn_composite_bwd(const float *nn_out, const float *v_t, int64_t vt_sb,
+                                    const float *g_yhat, int64_t gy_sb, int64_t gy_sc, int64_t gy_sf,
+                                    const float *g_comp, int64_t gc_sb, int64_t gc_sc, int64_t gc_sf,
+                                    float *g_nn, int B, int F, int64_t P, mt_stream_t stream) {
+    MT_REQUIRE(nn_out && v_t && g_nn, "mt_chn_composite_bwd: NULL argument");
+    MT_REQUIRE(B > 0 && F > 0 && P > 0 && (int64_t)B * F <= 65535, "mt_chn_composite_bwd: bad shape");
+    CompArgs a{};
+    a.nn_out = nn_out; a.v_t = v_t; a.vt_sb = vt_sb; a.g_yhat = g_yhat; a.gy_sb = gy_sb;
+    a.gy_sc = gy_sc; a.gy_sf = gy_sf; a.g_comp = g_comp; a.gc_sb = gc_sb; a.gc_sc = gc_sc;
+    a.gc_sf = gc_sf; a.g_nn = g_nn; a.F = F; a.P = P;
+    bool v4 = mult4(P) && aligned16(nn_out) && aligned16(v_t) && aligned16(g_yhat) && aligned16(g_comp) &&
+              aligned16(g_nn) && mult4(vt_sb) && mult4(gy_sb) && mult4(gy_sc) && mult4(gy_sf) &&
+              mult4(gc_sb) && mult4(gc_sc) && mult4(gc_sf);
+    const int vec = v4 ? 4 : 1;
+    dim3 grid((unsigned)((P + 256 * vec - 1) / (256 * vec)), B * F);
+    if (v4) chn_composite_bwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else chn_composite_bwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_status("mt_chn_composite_bwd");
+}
+
+extern "C" int mt_hole_update(const float *m_t, int64_t mt_sb, const float *v_map0, int64_t vm_sb,
+                              const float *y_comp0, int64_t yc_sb, int64_t yc_sc, float *m_new,
+                              float *x_new, float *inp_per, void *workspace, int B, int64_t P,
+                              mt_stream_t stream) {
+    MT_REQUIRE(m_t && v_map0 && y_comp0 && m_new && x_new && inp_per && workspace,
+               "mt_hole_update: NULL argument");
+    MT_REQUIRE(B > 0 && P > 0, "mt_hole_update: bad shape");
+    HoleArgs a{m_t, mt_sb, v_map0, vm_sb, y_comp0, yc_sb, yc_sc, m_new, x_new, inp_per, workspace, B, P, 0, 0};
+    bool v4 = mult4(P) && aligned16(m_t) && aligned16(v_map0) && aligned16(y_comp0) && aligned16(m_new) &&
+              aligned16(x_new) && mult4(mt_sb) && mult4(vm_sb) && mult4(yc_sb) && mult4(yc_sc);
+    const int vec = v4 ? 4 : 1;
+    a.chunks = (int)((P + 256 * vec - 1) / (256 * vec));
+    a.total_chunks = (int64_t)B * a.chunks;
+    const int nblk = reduce_blocks(a.total_chunks);
+    if (v4) hole_update_kernel<4><<<nblk, 256, 0, (cudaStream_t)stream>>>(a);
+    else hole_update_kernel<1><<<nblk, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_status("mt_hole_update");
+}
+
+extern "C" int mt_trivial_copy(const float *x_t, int64_t xt_sb, int64_t xt_sc, const float *x_al,
+                               int64_t xa_sb, int64_t xa_sc, int64_t xa_sf, const float *v_map,
+                               int64_t vm_sb, int64_t vm_sf, float *y, int B, int F, int64_t P,
+                               mt_stream_t stream) {
+    MT_REQUIRE(x_t && x_al && v_map && y, "mt_trivial_copy: NULL argument");
+    MT_REQUIRE(B > 0 && F > 0 && P > 0 && (int64_t)B * F <= 65535, "mt_trivial_copy: bad shape");
+    TrivArgs a{x_t, xt_sb, xt_sc, x_al, xa_sb, xa_sc, xa_sf, v_map, vm_sb, vm_sf, y, F, P};
+    bool v4 = mult4(P) && aligned16(x_t) && aligned16(x_al) && aligned16(v_map) && aligned16(y) &&
+              mult4(xt_sb) && mult4(xt_sc) && mult4(xa_sb) && mult4(xa_sc) && mult4(xa_sf) &&
+              mult4(vm_sb) && mult4(vm_sf);
+    const int vec = v4 ? 4 : 1;
+    dim3 grid((unsigned)((P + 256 * vec - 1) / (256 * vec)), B * F);
+    if (v4) trivial_copy_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else trivial_copy_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_status("mt_trivial_copy");
+}
+
+static int fill_l1(L1Args &a, const float *y_hat, int64_t a_sb, int64_t a_sc, int64_t a_sf,
+                   const float *y, int64_t b_sb, int64_t b_sc, int64_t b_sf, const float *mask,
+                   int64_t m_sb, int64_t m_sc, int64_t m_sf, const uint8_t *batch_mask, int B, int C,
+                   int F, int64_t P, int mask_c, int reduction, float weight, const char *who) {
+    MT_REQUIRE(y_hat && y && mask, "%s: NULL input", who);
+    MT_REQUIRE(B > 0 && C > 0 && F > 0 && P > 0, "%s: empty shape", who);
+    MT_REQUIRE(mask_c == 1 || mask_c == C, "%s: mask_c must be 1 or C", who);
+    MT_REQUIRE(reduction == MT_REDUCE_MEAN || reduction == MT_REDUCE_SUM, "%s: bad reduction", who);
+    a = L1Args{};
+    a.a = y_hat; a.a_sb = a_sb; a.a_sc = a_sc; a.a_sf = a_sf;
+    a.b = y; a.b_sb = b_sb; a.b_sc = b_sc; a.b_sf = b_sf;
+    a.m = mask; a.m_sb = m_sb; a.m_sc = m_sc; a.m_sf = m_sf;
+    a.bm = batch_mask; a.B = B; a.C = C; a.F = F; a.P = P; a.mask_c = mask_c;
+    a.reduction = reduction; a.weight = weight;
+    return MT_OK;
+}
+
+static bool l1_vec4(const L1Args &a) {
+    return mult4(a.P) && aligned16(a.a) && aligned16(a.b) && aligned16(a.m) && mult4(a.a_sb) &&
+           mult4(a.a_sc) && mult4(a.a_sf) && mult4(a.b_sb) && mult4(a.b_sc) && mult4(a.b_sf) &&
+           mult4(a.m_sb) && mult4(a.m_sc) && mult4(a.m_sf);
+}
+
+extern "C" int mt_masked_l1_fwd(const float *y_hat, int64_t a_sb, int64_t a_sc, int64_t a_sf,
+                                const float *y, int64_t b_sb, int64_t b_sc, int64_t b_sf,
+                                const float *mask, int64_t m_sb, int64_t m_sc, int64_t m_sf,
+                                const uint8_t *batch_mask, float *out3, void *workspace, int B,
+                                int C, int F, int64_t P, int mask_c, int reduction, float weight,
+                                mt_stream_t stream) {
+    L1Args a;
+    int rc = fill_l1(a, y_hat, a_sb, a_sc, a_sf, y, b_sb, b_sc, b_sf, mask, m_sb, m_sc, m_sf,
+                     batch_mask, B, C, F, P, mask_c, reduction, weight, "mt_masked_l1_fwd");
+    if (rc) return rc;
+    MT_REQUIRE(out3 && workspace, "mt_masked_l1_fwd: NULL out3 / workspace");
+    a.out3 = out3; a.ws = workspace;
+    const bool v4 = l1_vec4(a);
+    const int vec = v4 ? 4 : 1;
+    a.chunks = (int)((P + 256 * vec - 1) / (256 * vec));
+    a.total_chunks = (int64_t)B * F * a.chunks;
+    const int nblk = reduce_blocks(a.total_chunks);
+    if (v4) masked_l1_fwd_kernel<4><<<nblk, 256, 0, (cudaStream_t)stream>>>(a);
+    else masked_l1_fwd_kernel<1><<<nblk, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_status("mt_masked_l1_fwd");
+}
+
+extern "C" int mt_masked_l1_bwd(const float *y_hat, int64_t a_sb, int64_t a_sc, int64_t a_sf,
+                                const float *y, int64_t b_sb, int64_t b_sc, int64_t b_sf,
+                                const float *mask, int64_t m_sb, int64_t m_sc, int64_t m_sf,
+                                const uint8_t *batch_mask, const float *out3, const float *grad_out,
+                                float *grad_y_hat, float *grad_y, int B, int C, int F, int64_t P,
+                                int mask_c, int reduction, float weight, mt_stream_t stream) {
+    L1Args a;
+    int rc = fill_l1(a, y_hat, a_sb, a_sc, a_sf, y, b_sb, b_sc, b_sf, mask, m_sb, m_sc, m_sf,
+                     batch_mask, B, C, F, P, mask_c, reduction, weight, "mt_masked_l1_bwd");
+    if (rc) return rc;
+    MT_REQUIRE(out3 && grad_out && (grad_y_hat || grad_y), "mt_masked_l1_bwd: NULL argument");
+    MT_REQUIRE((int64_t)B * F <= 65535, "mt_masked_l1_bwd: B*F > 65535");
+    a.out3_in = out3; a.grad_out = grad_out; a.ga = grad_y_hat; a.gb = grad_y;
+    const bool v4 = l1_vec4(a) && aligned16(grad_y_hat) && aligned16(grad_y);
+    const int vec = v4 ? 4 : 1;
+    dim3 grid((unsigned)((P + 256 * vec - 1) / (256 * vec)), B * F);
+    if (v4) masked_l1_bwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else masked_l1_bwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_status("mt_masked_l1_bwd");
+}

@@ -1,0 +1,289 @@
+// cm.cu - K3: CPN context matching.
+//
+// Replaces CM_Module.forward + CM_Module.masked_softmax
+//   master_thesis/model_cpn.py:206-254                                   (a8)
+//
+// The reference's "correlation" here is ONE masked global dot product per
+// (sample, reference) - K = C*h*w = 524 288 terms, M = N = 1 - followed by a
+// per-pixel softmax over the references and a weighted copy.  It is HBM-bound
+// (AI ~ 0.6 flop/B), not a GEMM, so it stays on the SIMT pipes:
+//   pass 0  cm_masks:  v' = bilinear_resize(v, (h,w)) > 0.5 for target + refs
+//   pass 1  cm_sim:    partial sums of vt'*vr'*c_t*c_r per (b, r); reads
+//                      c_feats exactly once from HBM (16 B loads, 20 in flight
+//                      per thread)
+//   pass 2  cm_copy:   gs -> masked softmax over refs -> c_out, c_mask and the
+//                      concatenated output; re-reads c_feats from L2 (a sample
+//                      is 10.5 MB, a cfg2 batch 84 MB < 126 MB of L2)
+// Reductions are two-level and fixed-order (deterministic, no atomics).
+#include <math.h>
+
+#include "mt_common.cuh"
+
+namespace mt {
+namespace {
+
+constexpr int kSimChannels = 4;   // channels per CTA slab in pass 1
+constexpr int kCopyChannels = 8;  // channels per CTA slab in pass 2
+constexpr int kMaxRefs = 8;
+
+struct CmArgs {
+    const float *c_feats, *v_t, *v_al;
+    float *out, *c_mask;
+    float *masks;     // workspace: (B, f, P)   index 0 = target
+    float *partials;  // workspace: (B, nparts, R + 1)
+    float *gs;        // workspace: (B, R)  (exported for tests)
+    int B, C, f, h, w, H, W, P, R, nparts, chunks;
+};
+
+// F.interpolate(bilinear, align_corners=False) source index (UpSample.h)
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int &i0, int &i1, float &l0,
+                                          float &l1) {
+    float s = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+    s = s < 0.0f ? 0.0f : s;
+    i0 = (int)s;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = __fsub_rn(s, (float)i0);
+    l0 = __fsub_rn(1.0f, l1);
+}
+
+__global__ void __launch_bounds__(256) cm_masks_kernel(const CmArgs a) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.P) return;
+    const int j = blockIdx.y, b = blockIdx.z;  // j = 0: target, j >= 1: reference j-1
+    const float *src = (j == 0) ? a.v_t + (int64_t)b * a.H * a.W
+                                : a.v_al + ((int64_t)b * a.R + (j - 1)) * a.H * a.W;
+    const int y = p / a.w, x = p - y * a.w;
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    src_index(y, __fdiv_rn((float)a.H, (float)a.h), a.H, y0, y1, ly0, ly1);
+    src_index(x, __fdiv_rn((float)a.W, (float)a.w), a.W, x0, x1, lx0, lx1);
+    const float v00 = __ldg(src + y0 * a.W + x0), v01 = __ldg(src + y0 * a.W + x1);
+    const float v10 = __ldg(src + y1 * a.W + x0), v11 = __ldg(src + y1 * a.W + x1);
+    const float top = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
+    const float bot = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
+    const float val = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+    a.masks[((int64_t)b * a.f + j) * a.P + p] = val > 0.5f ? 1.0f : 0.0f;  // model_cpn.py:208-217
+}
+
+// pass 1: grid (chunks, C / kSimChannels, B); thread = 4 pixels x kSimChannels channels
+template <int R>
+__global__ void __launch_bounds__(256) cm_sim_kernel(const CmArgs a) {
+    __shared__ float red[R * 32];
+    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int slab = blockIdx.y, b = blockIdx.z;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0f;
+    if (p0 < a.P) {
+        const float *mk = a.masks + (int64_t)b * a.f * a.P + p0;
+        const float4 vt = *reinterpret_cast<const float4 *>(mk);
+        float4 vm[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float4 vr = *reinterpret_cast<const float4 *>(mk + (int64_t)(r + 1) * a.P);
+            vm[r] = make_float4(vt.x * vr.x, vt.y * vr.y, vt.z * vr.z, vt.w * vr.w);  // :220
+        }
+        const int c0 = slab * kSimChannels;
+        float4 ct[kSimChannels], cr[kSimChannels][R];
+#pragma unroll
+        for (int k = 0; k < kSimChannels; ++k) {
+            const int c = c0 + k;
+            if (c < a.C) {
+                const float *base = a.c_feats + ((int64_t)b * a.C + c) * a.f * a.P + p0;
+                // default L2 policy (NOT evict-first): pass 2 re-reads these from L2
+                ct[k] = __ldg(reinterpret_cast<const float4 *>(base));
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    cr[k][r] = __ldg(reinterpret_cast<const float4 *>(base + (int64_t)(r + 1) * a.P));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kSimChannels; ++k) {
+            if (c0 + k < a.C) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {  // vmap * c_t * c_r            :226
+                    acc[r] += vm[r].x * ct[k].x * cr[k][r].x;
+                    acc[r] += vm[r].y * ct[k].y * cr[k][r].y;
+                    acc[r] += vm[r].z * ct[k].z * cr[k][r].z;
+                    acc[r] += vm[r].w * ct[k].w * cr[k][r].w;
+                }
+            }
+        }
+    }
+    block_sum<R>(acc, red);
+    if (threadIdx.x == 0) {
+        float *o = a.partials + ((int64_t)b * a.nparts + slab * a.chunks + blockIdx.x) * R;
+#pragma unroll
+        for (int r = 0; r < R; ++r) o[r] = acc[r];
+    }
+}
+
+// gs[b, r] from the partials + the masks: one CTA per sample (tiny)
+template <int R>
+__global__ void __launch_bounds__(256) cm_gs_kernel(const CmArgs a) {
+    __shared__ double dred[2 * R * 32];
+    const int b = blockIdx.x;
+    double dot[R], vs[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { dot[r] = 0.0; vs[r] = 0.0; }
+    for (int i = threadIdx.x; i < a.nparts; i += blockDim.x) {
+        const float *o = a.partials + ((int64_t)b * a.nparts + i) * R;
+#pragma unroll
+        for (int r = 0; r < R; ++r) dot[r] += (double)o[r];
+    }
+    const float *mk = a.masks + (int64_t)b * a.f * a.P;
+    for (int p = threadIdx.x; p < a.P; p += blockDim.x) {
+        const float vt = mk[p];
+#pragma unroll
+        for (int r = 0; r < R; ++r) vs[r] += (double)(vt * mk[(int64_t)(r + 1) * a.P + p]);  // :221
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        dot[r] = warp_sum(dot[r]);
+        vs[r] = warp_sum(vs[r]);
+        if (lane == 0) { dred[(2 * r) * 32 + wid] = dot[r]; dred[(2 * r + 1) * 32 + wid] = vs[r]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < R) {
+        const int r = threadIdx.x;
+        double d = 0.0, v = 0.0;
+        for (int w = 0; w < nw; ++w) { d += dred[(2 * r) * 32 + w]; v += dred[(2 * r + 1) * 32 + w]; }
+        const bool zero = v < 1e-4;                                       // :222
+        const float v_sum = (float)v + (zero ? 1.0f : 0.0f);              // :223
+        const float g = (float)d / (v_sum * (float)a.C);                  // :225-227
+        a.gs[(int64_t)b * R + r] = zero ? 0.0f : g;                        // :228
+    }
+}
+
+// pass 2: grid (chunks, ceil(C / kCopyChannels), B)
+template <int R>
+__global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
+    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (p0 >= a.P) return;
+    const int slab = blockIdx.y, b = blockIdx.z;
+    float gsr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) gsr[r] = __ldg(a.gs + (int64_t)b * R + r);
+    const float *mk = a.masks + (int64_t)b * a.f * a.P + p0;
+    float wgt[R][4], vr[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float4 t = *reinterpret_cast<const float4 *>(mk + (int64_t)(r + 1) * a.P);
+        vr[r][0] = t.x; vr[r][1] = t.y; vr[r][2] = t.z; vr[r][3] = t.w;
+    }
+    float cmv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // masked_softmax over refs               :245-254
+        float mx = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < R; ++r) mx = fmaxf(mx, __fmul_rn(gsr[r], vr[r][i]));
+        float s = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            wgt[r][i] = __fmul_rn(expf(__fsub_rn(__fmul_rn(gsr[r], vr[r][i]), mx)), vr[r][i]);
+            s = __fadd_rn(s, wgt[r][i]);
+        }
+        if (s < 1e-4f) s = __fadd_rn(s, 1.0f);
+        float cm = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            wgt[r][i] = __fdiv_rn(wgt[r][i], s);
+            cm = __fadd_rn(cm, __fmul_rn(wgt[r][i], vr[r][i]));              // :240
+        }
+        cmv[i] = __fsub_rn(1.0f, cm);                                        // :241
+    }
+    float *ob = a.out + (int64_t)b * (2 * a.C + 1) * a.P + p0;
+    if (slab == 0) {
+        const float4 cm4 = make_float4(cmv[0], cmv[1], cmv[2], cmv[3]);
+        st_stream4(ob + (int64_t)2 * a.C * a.P, cm4);
+        st_stream4(a.c_mask + (int64_t)b * a.P + p0, cm4);
+    }
+    const int c0 = slab * kCopyChannels;
+#pragma unroll 2
+    for (int k = 0; k < kCopyChannels; ++k) {
+        const int c = c0 + k;
+        if (c >= a.C) break;
+        const float *base = a.c_feats + ((int64_t)b * a.C + c) * a.f * a.P + p0;
+        const float4 ct = ld_stream4(base);
+        float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {  // sum_r c_r * w_r, sequential over r    :238
+            const float4 cr = ld_stream4(base + (int64_t)(r + 1) * a.P);
+            o[0] = __fadd_rn(o[0], __fmul_rn(cr.x, wgt[r][0]));
+            o[1] = __fadd_rn(o[1], __fmul_rn(cr.y, wgt[r][1]));
+            o[2] = __fadd_rn(o[2], __fmul_rn(cr.z, wgt[r][2]));
+            o[3] = __fadd_rn(o[3], __fmul_rn(cr.w, wgt[r][3]));
+        }
+        st_stream4(ob + (int64_t)c * a.P, ct);                                // cat[c_t, ...]  :243
+        st_stream4(ob + (int64_t)(a.C + c) * a.P, make_float4(o[0], o[1], o[2], o[3]));
+    }
+}
+
+template <int R>
+int launch_cm(const CmArgs &a, cudaStream_t st) {
+    dim3 g0((a.P + 255) / 256, a.f, a.B);
+    cm_masks_kernel<<<g0, 256, 0, st>>>(a);
+    dim3 g1(a.chunks, (a.C + kSimChannels - 1) / kSimChannels, a.B);
+    cm_sim_kernel<R><<<g1, 256, 0, st>>>(a);
+    cm_gs_kernel<R><<<a.B, 256, 0, st>>>(a);
+    dim3 g2(a.chunks, (a.C + kCopyChannels - 1) / kCopyChannels, a.B);
+    cm_copy_kernel<R><<<g2, 256, 0, st>>>(a);
+    return launch_status("mt_cm_match_fwd");
+}
+
+int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
+
+}  // namespace
+}  // namespace mt
+
+using namespace mt;
+
+extern "C" int64_t mt_cm_workspace_bytes(int B, int C, int f, int h, int w) {
+    if (B <= 0 || C <= 0 || f < 2 || h <= 0 || w <= 0) return 0;
+    const int64_t P = (int64_t)h * w, R = f - 1;
+    const int64_t chunks = (P + 1023) / 1024, nparts = chunks * ((C + kSimChannels - 1) / kSimChannels);
+    return align256(B * f * P * 4) + align256(B * nparts * R * 4) + align256(B * R * 4);
+}
+
+extern "C" int mt_cm_match_fwd(const float *c_feats, const float *v_t, const float *v_aligned,
+                               float *out, float *c_mask, void *workspace, int B, int C, int f,
+                               int h, int w, int H, int W, mt_stream_t stream) {
+    MT_REQUIRE(c_feats && v_t && v_aligned && out && c_mask && workspace, "mt_cm_match_fwd: NULL argument");
+    MT_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "mt_cm_match_fwd: empty shape");
+    MT_REQUIRE(f >= 2 && f - 1 <= kMaxRefs, "mt_cm_match_fwd: needs 1..%d reference frames, got %d", kMaxRefs, f - 1);
+    MT_REQUIRE(B <= 65535, "mt_cm_match_fwd: B > 65535");
+    MT_REQUIRE(((int64_t)h * w) % 4 == 0, "mt_cm_match_fwd: h*w must be a multiple of 4 (got %dx%d)", h, w);
+    MT_REQUIRE(aligned16(c_feats) && aligned16(out) && aligned16(c_mask) && aligned16(workspace),
+               "mt_cm_match_fwd: pointers must be 16 B aligned");
+    CmArgs a;
+    a.c_feats = c_feats; a.v_t = v_t; a.v_al = v_aligned; a.out = out; a.c_mask = c_mask;
+    a.B = B; a.C = C; a.f = f; a.h = h; a.w = w; a.H = H; a.W = W; a.P = h * w; a.R = f - 1;
+    a.chunks = (a.P + 1023) / 1024;
+    a.nparts = a.chunks * ((C + kSimChannels - 1) / kSimChannels);
+    char *ws = reinterpret_cast<char *>(workspace);
+    a.masks = reinterpret_cast<float *>(ws);
+    ws += align256((int64_t)B * f * a.P * 4);
+    a.partials = reinterpret_cast<float *>(ws);
+    ws += align256((int64_t)B * a.nparts * a.R * 4);
+    a.gs = reinterpret_cast<float *>(ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (a.R) {
+        case 1: return launch_cm<1>(a, st);
+        case 2: return launch_cm<2>(a, st);
+        case 3: return launch_cm<3>(a, st);
+        case 4: return launch_cm<4>(a, st);
+        case 5: return launch_cm<5>(a, st);
+        case 6: return launch_cm<6>(a, st);
+        case 7: return launch_cm<7>(a, st);
+        default: return launch_cm<8>(a, st);
+    }
+}
+
+// gs (B, f-1) as left in the workspace by the last mt_cm_match_fwd (for tests)
+extern "C" const float *mt_cm_workspace_gs(const void *workspace, int B, int C, int f, int h, int w) {
+    const int64_t P = (int64_t)h * w, R = f - 1;
+    const int64_t chunks = (P + 1023) / 1024, nparts = chunks * ((C + kSimChannels - 1) / kSimChannels);
+    return reinterpret_cast<const float *>(reinterpret_cast<const char *>(workspace) +
+                                           align256(B * f * P * 4) + align256(B * nparts * R * 4));
+}

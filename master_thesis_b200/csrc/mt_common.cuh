@@ -1,0 +1,164 @@
+// mt_common.cuh - shared host/device helpers for libmt_b200.so (sm_100a only).
+//
+// Arithmetic contract (see DESIGN.md "bit-exactness"): every expression whose
+// rounding decides an index, a mask bit or a threshold is written with explicit
+// round-to-nearest intrinsics (__fadd_rn / __fmul_rn / __fmaf_rn) in exactly the
+// order the reference's CPU path (ATen, torch 2.11) evaluates it, and the
+// library is compiled with -fmad=false so nvcc cannot contract anything else.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mt_b200.h"
+
+namespace mt {
+
+// ---- host side ------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int launch_status(const char *what);  // cudaGetLastError -> MT_OK / MT_ERR_CUDA
+int sm_count();
+
+#define MT_REQUIRE(cond, ...)            \
+    do {                                 \
+        if (!(cond)) {                   \
+            ::mt::set_error(__VA_ARGS__); \
+            return MT_ERR_INVALID;       \
+        }                                \
+    } while (0)
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// workspace layout used by the reducing kernels
+constexpr int kMaxReduceBlocks = 4096;
+constexpr int kPartialsPerBlock = 4;
+constexpr int64_t kWsTicketBytes = 256;
+constexpr int64_t kWorkspaceBytes = kWsTicketBytes + int64_t(kMaxReduceBlocks) * kPartialsPerBlock * 4;
+
+// ---- device side ----------------------------------------------------------
+#ifdef __CUDACC__
+
+constexpr float kMean0 = 0.485f, kMean1 = 0.456f, kMean2 = 0.406f;  // model_chn.py:32-37
+constexpr float kStd0 = 0.229f, kStd1 = 0.224f, kStd2 = 0.225f;
+
+__device__ __forceinline__ float chan_mean(int c) { return c == 0 ? kMean0 : (c == 1 ? kMean1 : kMean2); }
+__device__ __forceinline__ float chan_std(int c) { return c == 0 ? kStd0 : (c == 1 ? kStd1 : kStd2); }
+
+// streaming (touch-once) global accesses: keep them out of L1, evict-first in L2
+__device__ __forceinline__ float4 ld_stream4(const float *p) {
+    return __ldcs(reinterpret_cast<const float4 *>(p));
+}
+__device__ __forceinline__ float ld_stream1(const float *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream4(float *p, float4 v) {
+    __stcs(reinterpret_cast<float4 *>(p), v);
+}
+__device__ __forceinline__ void st_stream1(float *p, float v) { __stcs(p, v); }
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<1> {
+    float v[1];
+    __device__ __forceinline__ void load_stream(const float *p) { v[0] = ld_stream1(p); }
+    __device__ __forceinline__ void load_cached(const float *p) { v[0] = __ldg(p); }
+    __device__ __forceinline__ void store_stream(float *p) const { st_stream1(p, v[0]); }
+};
+template <>
+struct Vec<4> {
+    float v[4];
+    __device__ __forceinline__ void load_stream(const float *p) {
+        float4 t = ld_stream4(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void load_cached(const float *p) {
+        float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void store_stream(float *p) const {
+        st_stream4(p, make_float4(v[0], v[1], v[2], v[3]));
+    }
+};
+
+__device__ __forceinline__ float clamp01(float a) { return fminf(fmaxf(a, 0.0f), 1.0f); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum of K per-thread values over the CTA; result valid in thread 0.
+// smem: K * 32 floats.  Fixed order => deterministic for a fixed launch shape.
+template <int K>
+__device__ __forceinline__ void block_sum(float (&v)[K], float *smem) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        v[k] = warp_sum(v[k]);
+        if (lane == 0) smem[k * 32 + wid] = v[k];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float t = lane < nw ? smem[k * 32 + lane] : 0.0f;
+            v[k] = warp_sum(t);
+        }
+    }
+}
+
+// Grid-wide deterministic reduction tail: every CTA stores its K partials, the
+// last CTA to arrive (ticket) sums all partials in a fixed order in double and
+// calls fin(totals).  The ticket is left at 0 again.
+template <int K, typename Fin>
+__device__ __forceinline__ void grid_reduce_finish(float (&v)[K], void *workspace, float *smem, Fin fin) {
+    static_assert(K <= kPartialsPerBlock, "too many partials");
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(workspace);
+    float *partials = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + kWsTicketBytes);
+    __shared__ bool is_last;
+    block_sum<K>(v, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) partials[blockIdx.x * kPartialsPerBlock + k] = v[k];
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            acc[k] += (double)__ldcg(&partials[i * kPartialsPerBlock + k]);
+    }
+    __shared__ double dsm[K * 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        acc[k] = warp_sum(acc[k]);
+        if (lane == 0) dsm[k * 32 + wid] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            tot[k] = 0.0;
+            for (int w = 0; w < nw; ++w) tot[k] += dsm[k * 32 + w];
+        }
+        fin(tot);
+        *ticket = 0u;
+    }
+}
+
+#endif  // __CUDACC__
+}  // namespace mt

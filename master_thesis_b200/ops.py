@@ -1,0 +1,439 @@
+"""Torch-facing operators over the C ABI of libmt_b200.so.
+
+PyTorch is plumbing here: it owns device memory (caching allocator), streams
+and autograd bookkeeping.  Every computation is a hand-written sm_100a kernel
+reached through ``_lib.call`` with raw device pointers.  CUDA fp32 tensors
+only; anything else raises - there is no CPU / eager fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+ALIGN_CORNERS = 1
+VIS_BILINEAR = 2
+GRID_AFFINE = 4
+VIS_FROM_MASK = 8
+REDUCE = {"mean": 0, "sum": 1}
+
+_workspaces = {}
+record = _lib.record      # with ops.record() as plan: ...   (see _lib.Plan)
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise RuntimeError("master_thesis_b200: CUDA tensors required (the hot path has no CPU "
+                               "fallback); got %s" % (t.device if isinstance(t, torch.Tensor) else type(t)))
+        if t.dtype != torch.float32:
+            raise RuntimeError("master_thesis_b200: fp32 tensors required, got %s" % t.dtype)
+
+
+def reduce_workspace(t):
+    """Zero-initialised ticket/partials workspace, one per (device, stream)."""
+    key = ("r", t.device.index, torch.cuda.current_stream(t.device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_lib.load().mt_workspace_bytes()), dtype=torch.uint8, device=t.device)
+        _workspaces[key] = ws
+    return ws
+
+
+def scratch(t, tag, nbytes):
+    """Uninitialised scratch of at least nbytes, cached per (tag, device, stream)."""
+    key = (tag, t.device.index, torch.cuda.current_stream(t.device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=t.device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _planes(t, plane_dims=2):
+    """Makes the trailing ``plane_dims`` dims one contiguous plane (copying only if needed)."""
+    exp = 1
+    for d in range(t.dim() - 1, t.dim() - 1 - plane_dims, -1):
+        if t.size(d) != 1 and t.stride(d) != exp:
+            return t.contiguous()
+        exp *= t.size(d)
+    return t
+
+
+def _s5(t):
+    """(B,C,F,H,W) tensor with contiguous planes -> (tensor, sb, sc, sf)."""
+    t = _planes(t)
+    return t, t.stride(0), t.stride(1), t.stride(2)
+
+
+def _frame_major(b, c, f, h, w, like):
+    """x_aligned memory: contiguous (B,F,C,H,W), returned as the (B,C,F,H,W) view the
+    reference's `.reshape(b,-1,3,h,w).transpose(1,2)` produces (utils.py:97)."""
+    mem = torch.empty((b, f, c, h, w), dtype=torch.float32, device=like.device)
+    return mem, mem.transpose(1, 2)
+
+
+# --------------------------------------------------------------------------
+# K1 warp
+# --------------------------------------------------------------------------
+def warp_fwd(x, vis, grid, m_target=None, flags=ALIGN_CORNERS, want_x=True, want_v=True):
+    """x (B,C,F,H,W), vis (B,1,F,H,W), grid dense (B,F,H,W,2) or theta (B*F,2,3).
+
+    Returns (x_aligned (B,C,F,H,W) view, v_aligned (B,1,F,H,W), v_map (B,1,F,H,W) | None).
+    """
+    _need_cuda(x, vis, grid, m_target)
+    b, c, f, h, w = x.shape
+    x, x_sb, x_sc, x_sf = _s5(x)
+    vis, v_sb, _, v_sf = _s5(vis)
+    grid = grid.contiguous()
+    if flags & GRID_AFFINE:
+        if grid.numel() != b * f * 6:
+            raise RuntimeError("theta must have shape (B*F,2,3)")
+    elif tuple(grid.shape) != (b, f, h, w, 2):
+        raise RuntimeError("flow must have shape (B,F,H,W,2), got %s" % (tuple(grid.shape),))
+    mt_sb = 0
+    if m_target is not None:
+        m_target = _planes(m_target)
+        mt_sb = m_target.stride(0)
+    xa_mem = xa = None
+    if want_x:
+        xa_mem, xa = _frame_major(b, c, f, h, w, x)
+    va = torch.empty((b, 1, f, h, w), dtype=torch.float32, device=x.device) if want_v else None
+    vm = torch.empty((b, 1, f, h, w), dtype=torch.float32, device=x.device) \
+        if m_target is not None else None
+    p = h * w
+    _lib.call("mt_warp_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis), v_sb, v_sf, _ptr(grid),
+              _ptr(m_target), mt_sb, _ptr(xa_mem), f * c * p, p, c * p, _ptr(va), _ptr(vm),
+              b, c, f, h, w, flags, _stream(x))
+    return xa, va, vm
+
+
+def warp_bwd_grid(x, grid, gout, flags=ALIGN_CORNERS):
+    _need_cuda(x, grid, gout)
+    b, c, f, h, w = x.shape
+    x, x_sb, x_sc, x_sf = _s5(x)
+    gout, g_sb, g_sc, g_sf = _s5(gout)
+    grid = grid.contiguous()
+    gg = torch.empty_like(grid)
+    _lib.call("mt_warp_bwd_grid", _ptr(x), x_sb, x_sc, x_sf, _ptr(grid), _ptr(gout), g_sb, g_sc,
+              g_sf, _ptr(gg), b, c, f, h, w, flags, _stream(x))
+    return gg
+
+
+class AlignSetFn(torch.autograd.Function):
+    """FlowsUtils.align_set (utils.py:78-104) with its autograd (grad w.r.t. flow only)."""
+
+    @staticmethod
+    def forward(ctx, x, v, flow):
+        xa, va, _ = warp_fwd(x, v, flow, None, ALIGN_CORNERS)
+        ctx.save_for_backward(x, flow)
+        return xa, va
+
+    @staticmethod
+    def backward(ctx, g_xa, g_va):
+        x, flow = ctx.saved_tensors
+        if not ctx.needs_input_grad[2] or g_xa is None:
+            return None, None, None
+        # the nearest sampler has zero gradient w.r.t. the grid: g_va is ignored
+        return None, None, warp_bwd_grid(x, flow, g_xa, ALIGN_CORNERS)
+
+
+def align_set(x, v, flow):
+    if x.requires_grad or v.requires_grad:
+        raise RuntimeError("align_set: gradients w.r.t. x / v are not provided (the reference "
+                           "never requests them); only the flow is differentiable")
+    return AlignSetFn.apply(x, v, flow)
+
+
+def mask_out(flow):
+    """model_dfpn.py:269-272: flow (B,F,H,W,2) -> (B,1,F,H,W)."""
+    _need_cuda(flow)
+    flow = flow.detach().contiguous()
+    b, f, h, w, _ = flow.shape
+    out = torch.empty((b, 1, f, h, w), dtype=torch.float32, device=flow.device)
+    _lib.call("mt_mask_out", _ptr(flow), flow.numel() // 2, _ptr(out), _stream(flow))
+    return out
+
+
+# --------------------------------------------------------------------------
+# masked L1
+# --------------------------------------------------------------------------
+def _l1_layout(y_hat, y, mask):
+    """Common (B,C,F,P) decomposition + strides for the three operands."""
+    if y_hat.shape != y.shape:
+        raise RuntimeError("masked_l1: y_hat %s vs y %s" % (tuple(y_hat.shape), tuple(y.shape)))
+    if y_hat.dim() == 5 and mask.dim() == 5 and mask.shape[0] == y_hat.shape[0] \
+            and mask.shape[2:] == y_hat.shape[2:] and mask.shape[1] in (1, y_hat.shape[1]):
+        b, c, f, h, w = y_hat.shape
+        ts = [_s5(t) for t in (y_hat, y, mask)]
+        return ts, b, c, f, h * w, mask.shape[1]
+    if mask.shape != y_hat.shape:
+        mask = mask.expand_as(y_hat)
+    b = y_hat.shape[0]
+    ts = []
+    for t in (y_hat, y, mask):
+        t = t.contiguous().view(b, 1, 1, -1)
+        ts.append((t, t.stride(0), 0, 0))
+    return ts, b, 1, 1, ts[0][0].shape[-1], 1
+
+
+def _bm(batch_mask, like):
+    if batch_mask is None:
+        return None
+    bm = torch.as_tensor(batch_mask)
+    return bm.to(device=like.device, dtype=torch.uint8).contiguous()
+
+
+class MaskedL1Fn(torch.autograd.Function):
+    """LossesUtils.masked_l1 (utils.py:139-169) + autograd w.r.t. y_hat and y."""
+
+    @staticmethod
+    def forward(ctx, y_hat, y, mask, batch_mask, reduction, weight):
+        _need_cuda(y_hat, y, mask)
+        (a, b_, m), B, C, F, P, mask_c = _l1_layout(y_hat, y, mask)
+        bm = _bm(batch_mask, y_hat)
+        out3 = torch.empty(3, dtype=torch.float32, device=y_hat.device)
+        _lib.call("mt_masked_l1_fwd", _ptr(a[0]), a[1], a[2], a[3], _ptr(b_[0]), b_[1], b_[2], b_[3],
+                  _ptr(m[0]), m[1], m[2], m[3], _ptr(bm), _ptr(out3), _ptr(reduce_workspace(y_hat)),
+                  B, C, F, P, mask_c, REDUCE[reduction], float(weight), _stream(y_hat))
+        ctx.save_for_backward(a[0], b_[0], m[0], out3, bm if bm is not None else out3)
+        ctx.meta = (a[1:], b_[1:], m[1:], B, C, F, P, mask_c, REDUCE[reduction], float(weight),
+                    bm is not None, y_hat.shape)
+        return out3[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b_, m, out3, bm = ctx.saved_tensors
+        sa, sb, sm, B, C, F, P, mask_c, red, weight, has_bm, shape = ctx.meta
+        need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if ctx.needs_input_grad[2]:
+            raise RuntimeError("masked_l1: gradient w.r.t. the mask is not provided")
+        if not (need_a or need_b):
+            return (None,) * 6
+        g = g.contiguous().to(torch.float32)
+        ga = torch.empty((B, C, F, P), dtype=torch.float32, device=a.device) if need_a else None
+        gb = torch.empty((B, C, F, P), dtype=torch.float32, device=a.device) if need_b else None
+        _lib.call("mt_masked_l1_bwd", _ptr(a), sa[0], sa[1], sa[2], _ptr(b_), sb[0], sb[1], sb[2],
+                  _ptr(m), sm[0], sm[1], sm[2], _ptr(bm) if has_bm else None, _ptr(out3), _ptr(g),
+                  _ptr(ga), _ptr(gb), B, C, F, P, mask_c, red, weight, _stream(a))
+        ga = ga.view(shape) if ga is not None else None
+        gb = gb.view(shape) if gb is not None else None
+        return ga, gb, None, None, None, None
+
+
+def masked_l1(y_hat, y, mask, batch_mask=None, reduction="mean", weight=1):
+    """Drop-in for LossesUtils.masked_l1.  Differences: never synchronises the host
+    (utils.py:158 iterates a device tensor in Python); returns a 0-d tensor also when
+    ``batch_mask`` selects nothing (the reference returns ``zeros(1)``, same value)."""
+    return MaskedL1Fn.apply(y_hat, y, mask, batch_mask, reduction, weight)
+
+
+# --------------------------------------------------------------------------
+# K1c fused warp + mask_out + masked L1
+# --------------------------------------------------------------------------
+def warp_l1_fwd_raw(x_refs, vis, flow, x_target, v_target, weight=1.0, materialize=False,
+                    flags=ALIGN_CORNERS):
+    """mt_warp_l1_fwd without autograd.  Returns (out3, x_aligned | None, v_aligned | None, saved)
+    where out3 = [loss, sum|.|, sum(mask)] on the device and ``saved`` feeds warp_l1_bwd_raw."""
+    _need_cuda(x_refs, vis if materialize else None, flow, x_target, v_target)
+    b, c, f, h, w = x_refs.shape
+    if c != 3:
+        raise RuntimeError("warp_masked_l1: C must be 3")
+    x, x_sb, x_sc, x_sf = _s5(x_refs)
+    flow_c = flow.detach().contiguous()
+    xt = _planes(x_target)
+    vt = _planes(v_target)
+    out3 = torch.empty(3, dtype=torch.float32, device=x.device)
+    xa_mem = xa = va = None
+    vis_t, v_sb, v_sf = None, 0, 0
+    if materialize:
+        xa_mem, xa = _frame_major(b, 3, f, h, w, x)
+        va = torch.empty((b, 1, f, h, w), dtype=torch.float32, device=x.device)
+        vis_t, v_sb, _, v_sf = _s5(vis)
+    _lib.call("mt_warp_l1_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis_t), v_sb, v_sf, _ptr(flow_c),
+              _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0), _ptr(xa_mem),
+              _ptr(va), _ptr(out3), _ptr(reduce_workspace(x)), b, f, h, w, float(weight),
+              flags, _stream(x))
+    saved = (x, flow_c, xt, vt, out3, (x_sb, x_sc, x_sf, b, f, h, w, float(weight), flags))
+    return out3, xa, va, saved
+
+
+def warp_l1_bwd_raw(saved, grad_out):
+    """mt_warp_l1_bwd: d loss / d flow (B,F,H,W,2); grad_out is a 1-element device tensor."""
+    x, flow, xt, vt, out3, (x_sb, x_sc, x_sf, b, f, h, w, weight, flags) = saved
+    gflow = torch.empty_like(flow)
+    _lib.call("mt_warp_l1_bwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(flow), _ptr(xt), xt.stride(0),
+              xt.stride(1), _ptr(vt), vt.stride(0), _ptr(out3), _ptr(grad_out), _ptr(gflow), b, f, h, w,
+              weight, flags, _stream(x))
+    return gflow
+
+
+class WarpL1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_refs, vis, flow, x_target, v_target, weight, materialize, flags):
+        out3, xa, va, saved = warp_l1_fwd_raw(x_refs, vis, flow, x_target, v_target, weight,
+                                              materialize, flags)
+        ctx.save_for_backward(*saved[:5])
+        ctx.meta = saved[5]
+        if materialize:
+            ctx.mark_non_differentiable(xa, va)
+            return out3[0], xa, va
+        return out3[0], None, None
+
+    @staticmethod
+    def backward(ctx, g, _gx, _gv):
+        if not ctx.needs_input_grad[2]:
+            return (None,) * 8
+        g = g.contiguous().to(torch.float32)
+        gflow = warp_l1_bwd_raw(tuple(ctx.saved_tensors) + (ctx.meta,), g)
+        return None, None, gflow, None, None, None, None, None
+
+
+def warp_masked_l1(x_refs, vis, flow, x_target, v_target, weight=1.0, materialize=False,
+                   vis_from_mask=False):
+    """Fused a1+a4+a5: loss = masked_l1(x_target repeated, align_set(x_refs, vis, flow)[0],
+    v_target * (1 - mask_out(flow)), 'sum') (model_dfpn.py:269-287) in one pass.
+    Returns (loss, x_aligned | None, v_aligned | None)."""
+    flags = ALIGN_CORNERS | (VIS_FROM_MASK if vis_from_mask else 0)
+    return WarpL1Fn.apply(x_refs, vis, flow, x_target, v_target, weight, materialize, flags)
+
+
+# --------------------------------------------------------------------------
+# K2 correlation
+# --------------------------------------------------------------------------
+def corr4d(feats_t, v_t, feats_r, v_r):
+    """CorrelationVGG.correlation_masked_4d (model_dfpn.py:534-565)."""
+    _need_cuda(feats_t, v_t, feats_r, v_r)
+    b, c, f, h, w = feats_r.shape
+    p = h * w
+    ft = feats_t.contiguous()
+    fr = feats_r.contiguous()
+    vt = None if v_t is None else v_t.contiguous()
+    vr = None if v_r is None else v_r.contiguous()
+    out = torch.empty((b, f, h, w, h, w), dtype=torch.float32, device=fr.device)
+    lib = _lib.load()
+    nbytes = int(lib.mt_corr4d_workspace_bytes(b, c, f, p))
+    ws = scratch(fr, "corr", nbytes)
+    _lib.call("mt_corr4d_fwd", _ptr(ft), _ptr(vt), _ptr(fr), _ptr(vr), _ptr(out), _ptr(ws),
+              ws.numel(), b, c, f, p, _stream(fr))
+    return out
+
+
+# --------------------------------------------------------------------------
+# K3 context matching
+# --------------------------------------------------------------------------
+def cm_match(c_feats, v_t, v_aligned, return_gs=False):
+    """CM_Module.forward (model_cpn.py:206-243)."""
+    _need_cuda(c_feats, v_t, v_aligned)
+    b, c, f, h, w = c_feats.shape
+    H, W = v_t.shape[-2:]
+    cf = c_feats.contiguous()
+    vt = v_t.contiguous()
+    va = v_aligned.contiguous()
+    out = torch.empty((b, 2 * c + 1, h, w), dtype=torch.float32, device=cf.device)
+    cmask = torch.empty((b, 1, h, w), dtype=torch.float32, device=cf.device)
+    lib = _lib.load()
+    ws = scratch(cf, "cm", int(lib.mt_cm_workspace_bytes(b, c, f, h, w)))
+    _lib.call("mt_cm_match_fwd", _ptr(cf), _ptr(vt), _ptr(va), _ptr(out), _ptr(cmask), _ptr(ws),
+              b, c, f, h, w, H, W, _stream(cf))
+    if return_gs:
+        addr = lib.mt_cm_workspace_gs(_ptr(ws), b, c, f, h, w)
+        off = ctypes.cast(addr, ctypes.c_void_p).value - ws.data_ptr()
+        gs = ws[off:off + 4 * b * (f - 1)].view(torch.float32).view(b, f - 1).clone()
+        return out, cmask, gs
+    return out, cmask
+
+
+# --------------------------------------------------------------------------
+# K4 CHN
+# --------------------------------------------------------------------------
+def chn_pack(x_t, v_t, x_al, v_al, v_map):
+    """model_chn.py:68-80 -> nn_input (B*F,9,H,W) NCHW."""
+    _need_cuda(x_t, v_t, x_al, v_al, v_map)
+    b, _, f, h, w = x_al.shape
+    xt, vt = _planes(x_t), _planes(v_t)
+    xa, xa_sb, xa_sc, xa_sf = _s5(x_al)
+    va, va_sb, _, va_sf = _s5(v_al)
+    vm, vm_sb, _, vm_sf = _s5(v_map)
+    out = torch.empty((b * f, 9, h, w), dtype=torch.float32, device=xa.device)
+    _lib.call("mt_chn_pack", _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0), _ptr(xa),
+              xa_sb, xa_sc, xa_sf, _ptr(va), va_sb, va_sf, _ptr(vm), vm_sb, vm_sf, _ptr(out), b, f,
+              h * w, _stream(xa))
+    return out
+
+
+class ChnCompositeFn(torch.autograd.Function):
+    """model_chn.py:80-85 with autograd w.r.t. the CNN output."""
+
+    @staticmethod
+    def forward(ctx, nn_out, x_t, v_t, b, f):
+        _need_cuda(nn_out, x_t, v_t)
+        h, w = nn_out.shape[-2:]
+        no = nn_out.contiguous()
+        xt, vt = _planes(x_t), _planes(v_t)
+        yh_mem, yh = _frame_major(b, 3, f, h, w, no)
+        yc_mem, yc = _frame_major(b, 3, f, h, w, no)
+        _lib.call("mt_chn_composite_fwd", _ptr(no), _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt),
+                  vt.stride(0), _ptr(yh_mem), _ptr(yc_mem), b, f, h * w, _stream(no))
+        ctx.save_for_backward(no, vt)
+        ctx.meta = (b, f, h, w)
+        return yh, yc
+
+    @staticmethod
+    def backward(ctx, g_yh, g_yc):
+        no, vt = ctx.saved_tensors
+        b, f, h, w = ctx.meta
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        gy = gc = None
+        gy_s = gc_s = (0, 0, 0)
+        if g_yh is not None:
+            gy, *gy_s = _s5(g_yh)
+        if g_yc is not None:
+            gc, *gc_s = _s5(g_yc)
+        g = torch.empty_like(no)
+        _lib.call("mt_chn_composite_bwd", _ptr(no), _ptr(vt), vt.stride(0), _ptr(gy), *gy_s, _ptr(gc),
+                  *gc_s, _ptr(g), b, f, h * w, _stream(no))
+        return g, None, None, None, None
+
+
+def chn_composite(nn_out, x_t, v_t, b, f):
+    return ChnCompositeFn.apply(nn_out, x_t, v_t, b, f)
+
+
+def hole_update(m_t, v_map0, y_comp0):
+    """model_chn.py:128-131: returns (m_new (B,1,H,W), x_new (B,3,H,W), inp_per 0-d device tensor)."""
+    _need_cuda(m_t, v_map0, y_comp0)
+    b = m_t.shape[0]
+    h, w = m_t.shape[-2:]
+    mt, vm, yc = _planes(m_t), _planes(v_map0), _planes(y_comp0)
+    m_new = torch.empty((b, 1, h, w), dtype=torch.float32, device=mt.device)
+    x_new = torch.empty((b, 3, h, w), dtype=torch.float32, device=mt.device)
+    per = torch.empty(1, dtype=torch.float32, device=mt.device)
+    _lib.call("mt_hole_update", _ptr(mt), mt.stride(0), _ptr(vm), vm.stride(0), _ptr(yc), yc.stride(0),
+              yc.stride(1), _ptr(m_new), _ptr(x_new), _ptr(per), _ptr(reduce_workspace(mt)), b, h * w,
+              _stream(mt))
+    return m_new, x_new, per[0]
+
+
+def trivial_copy(x_t, x_al, v_map):
+    """model_dfpn.py:427-429."""
+    _need_cuda(x_t, x_al, v_map)
+    b, _, f, h, w = x_al.shape
+    xt = _planes(x_t)
+    xa, xa_sb, xa_sc, xa_sf = _s5(x_al)
+    vm, vm_sb, _, vm_sf = _s5(v_map)
+    y = torch.empty((b, 3, f, h, w), dtype=torch.float32, device=xa.device)
+    _lib.call("mt_trivial_copy", _ptr(xt), xt.stride(0), xt.stride(1), _ptr(xa), xa_sb, xa_sc, xa_sf,
+              _ptr(vm), vm_sb, vm_sf, _ptr(y), b, f, h * w, _stream(xa))
+    return y

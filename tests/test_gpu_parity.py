@@ -1,0 +1,310 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI and the plug-point
+mirrors) against the CPU oracle and the reference's golden vectors.
+
+Bar (BASELINE.json north_star): index / mask logic bit-exact; fp32 warp /
+composite within 1e-5 abs (the kernels follow the reference's CPU operation
+order, so most are in fact bit-exact and asserted as such); reductions within
+1e-5 relative; correlation within 1e-2 relative when it runs on tensor cores
+(TF32), 2e-6 abs on the fp32 SIMT path.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import oracle
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mtb():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    import master_thesis_b200 as m
+    from master_thesis_b200 import _lib
+    _lib.load()
+    return m
+
+
+def dev(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().contiguous().cpu().numpy()
+
+
+# ---------------------------------------------------------------- a1 / a2
+@pytest.mark.parametrize("name", sorted(cases.WARP_CASES))
+def test_dfpn_align_tail(mtb, name):
+    x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES[name])
+    g = load_golden("warp_" + name)
+    xa, va, vm = mtb.dfpn_align_tail(dev(x), dev(m), dev(m_t), dev(flow))
+    assert xa.shape == x.shape and va.shape == m.shape and vm.shape == m.shape
+    # same strides as the reference's transposed view (utils.py:97)
+    b, c, f, h, w = x.shape
+    assert xa.stride() == (f * c * h * w, h * w, c * h * w, w, 1)
+    oxa, ova, ovm = oracle.dfpn_align_tail(x, m, m_t, flow)
+    for got, orc, gold in ((xa, oxa, g["x_aligned"]), (va, ova, g["v_aligned"]), (vm, ovm, g["v_map"])):
+        got = host(got)
+        assert np.array_equal(got, orc)
+        assert np.array_equal(got, gold)
+
+
+@pytest.mark.parametrize("name", ["smooth_f4", "f1_odd"])
+def test_align_set_plug_and_views(mtb, name):
+    x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES[name])
+    g = load_golden("warp_" + name)
+    b, c, f, h, w = x.shape
+    # non-contiguous inputs: slices of a larger clip, like x[:, :, r_list] views
+    big = torch.zeros((b, c, f + 2, h, w), device="cuda")
+    big[:, :, 1:f + 1] = dev(x)
+    vbig = torch.zeros((b, 1, f + 2, h, w), device="cuda")
+    vbig[:, :, 1:f + 1] = dev(1 - m)
+    xa, va = mtb.FlowsUtils.align_set(big[:, :, 1:f + 1], vbig[:, :, 1:f + 1], dev(flow))
+    assert np.array_equal(host(xa), g["x_aligned"])
+    assert np.array_equal(host(va), g["v_aligned"])
+
+
+def test_warp_rejects_cpu_tensors(mtb):
+    with pytest.raises(RuntimeError):
+        mtb.FlowsUtils.align_set(torch.zeros(1, 3, 1, 4, 4), torch.zeros(1, 1, 1, 4, 4),
+                                 torch.zeros(1, 1, 4, 4, 2))
+
+
+# ---------------------------------------------------------------- a3
+@pytest.mark.parametrize("name", sorted(cases.CPN_CASES))
+def test_cpn_align_tail(mtb, name):
+    x, m, m_t, theta = cases.cpn_inputs(cases.CPN_CASES[name])
+    g = load_golden("cpn_" + name)
+    # theta mode: bit-exact against the oracle (same scalar linspace algorithm) ...
+    xa, va, vm = mtb.cpn_align_tail(dev(x), dev(m), dev(m_t), dev(theta))
+    oxa, ova, ovm = oracle.cpn_align_tail(x, m, m_t, theta=theta)
+    assert np.array_equal(host(xa), oxa)
+    assert np.array_equal(host(va), ova)
+    assert np.array_equal(host(vm), ovm)
+    # ... and within tolerance of the reference (its vectorised linspace differs by 1 ulp)
+    assert np.abs(host(xa) - g["x_aligned"]).max() <= 1e-5
+    bad = host(va) != g["v_aligned"]
+    assert np.all(np.abs(g["v_soft"][bad] - 0.5) <= 1e-5) and bad.mean() <= 2e-3
+    # dense-grid mode with the reference's own grid: bit-exact against the reference
+    from master_thesis_b200 import ops
+    xa, va, vm = ops.warp_fwd(dev(x), dev(m), dev(g["grid"]), dev(m_t),
+                              ops.VIS_BILINEAR | ops.VIS_FROM_MASK)
+    assert np.array_equal(host(xa), g["x_aligned"])
+    assert np.array_equal(host(va), g["v_aligned"])
+    assert np.array_equal(host(vm), g["v_map"])
+
+
+class _FakeCPN(object):
+    def __init__(self, theta):
+        self.theta = theta
+
+    def A_Encoder(self, xx, mm):
+        return torch.zeros(xx.size(0), 1, 1, 1, device=xx.device)
+
+    def A_Regressor(self, a, b):
+        return self.theta
+
+
+class _FakeDFPN(object):
+    def __init__(self, flow):
+        self.flow = flow
+
+    def __call__(self, *a):
+        return None, None, None, self.flow
+
+
+def test_aligner_protocol_mirrors(mtb):
+    """DFPN.align / CPN.align replacements with the CNNs stubbed, as in make_golden.py."""
+    x, m, m_t, theta = cases.cpn_inputs(cases.CPN_CASES["rand_f4"])
+    xa, va, vm = mtb.cpn_align(_FakeCPN(dev(theta)), dev(x[:, :, 0]), dev(m_t), dev(x), dev(m))
+    oxa, ova, ovm = oracle.cpn_align_tail(x, m, m_t, theta=theta)
+    assert np.array_equal(host(xa), oxa) and np.array_equal(host(va), ova) and np.array_equal(host(vm), ovm)
+    x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES["smooth_f4"])
+    g = load_golden("warp_smooth_f4")
+    xa, va, vm = mtb.dfpn_align(_FakeDFPN(dev(flow)), dev(x[:, :, 0]), dev(m_t), dev(x), dev(m))
+    assert np.array_equal(host(xa), g["x_aligned"]) and np.array_equal(host(vm), g["v_map"])
+
+
+# ---------------------------------------------------------------- a4 / a5 / a6
+@pytest.mark.parametrize("name", sorted(cases.LOSS_CASES))
+def test_losses_and_backward(mtb, name):
+    x, m, flow, flow_gt, use, t, r_list = cases.loss_inputs(cases.LOSS_CASES[name])
+    g = load_golden("loss_" + name)
+    f = len(r_list)
+    xt, vt = dev(x), dev(1 - m)
+    fl = dev(flow).requires_grad_(True)
+    mo = mtb.LossesUtils.mask_out(fl)
+    assert np.array_equal(host(mo), g["mask_out"])
+    # the reference's own sequence (model_dfpn.py:377-383, 269-287) on the patched ops
+    xa, va = mtb.FlowsUtils.align_set(xt[:, :, r_list], vt[:, :, r_list], fl)
+    y_hat = xt[:, :, t].unsqueeze(2).repeat(1, 1, f, 1, 1)
+    mask = vt[:, :, t].unsqueeze(2).repeat(1, 1, f, 1, 1) * (1 - mo)
+    rec = mtb.LossesUtils.masked_l1(y_hat, xa, mask, reduction='sum')
+    assert float(rec) == pytest.approx(float(g["recons"]), rel=1e-5)
+    g_xa, = torch.autograd.grad(rec, xa, retain_graph=True)
+    scale = np.abs(g["g_x_aligned"]).max()
+    assert np.abs(host(g_xa) - g["g_x_aligned"]).max() <= 1e-5 * scale
+    g_fl, = torch.autograd.grad(rec, fl)
+    gscale = np.abs(g["g_flow"]).max()
+    assert np.abs(host(g_fl) - g["g_flow"]).max() <= 2e-5 * gscale
+    mean = mtb.LossesUtils.masked_l1(y_hat, xa.detach(), mask, reduction='mean', weight=2)
+    assert float(mean) == pytest.approx(float(g["mean_l1"]), rel=1e-5)
+    # flow L1 with batch selection (model_dfpn.py:259-267), no host sync
+    fl1 = mtb.LossesUtils.masked_l1(fl, dev(flow_gt), torch.ones_like(fl), dev(use.astype(np.uint8)))
+    assert float(fl1) == pytest.approx(float(g["flow_l1"]), rel=1e-5)
+    g_fl1, = torch.autograd.grad(fl1, fl)
+    assert np.abs(host(g_fl1) - g["g_flow_l1"]).max() <= 1e-6 * np.abs(g["g_flow_l1"]).max() + 1e-12
+    none = mtb.LossesUtils.masked_l1(fl, dev(flow_gt), torch.ones_like(fl),
+                                     torch.zeros(len(use), dtype=torch.bool))
+    assert float(none) == 0.0
+    # fused one-pass form (K1c): same loss, same flow gradient
+    fl2 = dev(flow).requires_grad_(True)
+    fused = mtb.LossesUtils.alignment_recons(xt[:, :, t], vt[:, :, t], xt[:, :, r_list],
+                                             vt[:, :, r_list], fl2)
+    assert float(fused) == pytest.approx(float(g["recons"]), rel=1e-5)
+    fused.backward()
+    assert np.abs(host(fl2.grad) - g["g_flow"]).max() <= 2e-5 * gscale
+    # fused + materialised outputs
+    from master_thesis_b200 import ops
+    loss, xa2, va2 = ops.warp_masked_l1(xt[:, :, r_list], vt[:, :, r_list], dev(flow), xt[:, :, t],
+                                        vt[:, :, t], materialize=True)
+    assert np.array_equal(host(xa2), host(xa)) and np.array_equal(host(va2), host(va))
+    assert float(loss) == pytest.approx(float(g["recons"]), rel=1e-5)
+
+
+# ---------------------------------------------------------------- a7
+@pytest.mark.parametrize("name", sorted(cases.CORR_CASES))
+def test_corr4d(mtb, name):
+    from master_thesis_b200 import _lib
+    spec = cases.CORR_CASES[name]
+    ft, vt, fr, vr = cases.corr_inputs(spec)
+    g = load_golden("corr_" + name)
+    c = host(mtb.CorrelationVGG.correlation_masked_4d(dev(ft), dev(vt), dev(fr), dev(vr)))
+    assert c.shape == g["corr"].shape
+    tc = _lib.load().mt_corr4d_uses_tensor_cores(spec["c"], spec["h"] * spec["w"])
+    if tc:   # TF32 operands, fp32 accumulate: north_star tolerance <= 1e-2 relative
+        assert np.abs(c - g["corr"]).max() <= 1e-2 * max(np.abs(g["corr"]).max(), 1e-6)
+        assert np.abs(c - g["corr"]).max() <= 2e-3
+    else:
+        assert np.abs(c - g["corr"]).max() <= 2e-6
+    if vt is not None:       # masked rows are exactly zero
+        assert np.all(c[0, :, 0, :] == 0.0)
+
+
+# ---------------------------------------------------------------- a8
+@pytest.mark.parametrize("name", sorted(cases.CM_CASES))
+def test_cm_module(mtb, name):
+    from master_thesis_b200 import ops
+    cf, vt, va = cases.cm_inputs(cases.CM_CASES[name])
+    g = load_golden("cm_" + name)
+    out, cmask = mtb.CM_Module()(dev(cf), dev(vt), dev(va))
+    out, cmask = host(out), host(cmask)
+    oout, ocmask, ogs = oracle.cm_module(cf, vt, va, return_gs=True)
+    _, _, gs = ops.cm_match(dev(cf), dev(vt), dev(va), return_gs=True)
+    assert np.abs(host(gs) - ogs).max() <= 1e-6 * max(1.0, np.abs(ogs).max())
+    assert np.abs(out - oout).max() <= 1e-5 and np.abs(cmask - ocmask).max() <= 2e-6
+    assert np.abs(cmask - g["c_mask"]).max() <= 2e-6
+    if "out" in g:
+        assert np.abs(out - g["out"]).max() <= 1e-5
+    else:
+        assert np.abs(out.reshape(-1)[::53] - g["sample"]).max() <= 1e-5
+
+
+# ---------------------------------------------------------------- a9 .. a12
+class _FakeCHN(object):
+    def __init__(self, nn_out):
+        self.nn_out = nn_out
+        self.seen = None
+
+    def nn(self, inp):
+        self.seen = inp
+        return self.nn_out
+
+
+@pytest.mark.parametrize("name", sorted(cases.CHN_CASES))
+def test_chn(mtb, name):
+    from master_thesis_b200 import ops
+    x_t, v_t, x_al, v_al, v_map, nn_out = cases.chn_inputs(cases.CHN_CASES[name])
+    g = load_golden("chn_" + name)
+    b, _, f, h, w = x_al.shape
+    fake = _FakeCHN(dev(nn_out).requires_grad_(True))
+    y_hat, y_comp = mtb.chn_forward(fake, dev(x_t), dev(v_t), dev(x_al), dev(v_al), dev(v_map))
+    assert np.array_equal(host(fake.seen), g["nn_input"])
+    assert y_hat.shape == (b, 3, f, h, w)
+    assert np.array_equal(host(y_hat), g["y_hat"])
+    assert np.array_equal(host(y_comp), g["y_hat_comp"])
+    r = cases.synth.rng(cases.CHN_CASES[name]["seed"] + 7)
+    gy = r.standard_normal(y_hat.shape).astype(np.float32)
+    gc = r.standard_normal(y_hat.shape).astype(np.float32)
+    ((y_hat * dev(gy)).sum() + (y_comp * dev(gc)).sum()).backward()
+    assert np.abs(host(fake.nn_out.grad) - g["g_nn_out"]).max() <= 1e-6
+    m_new, x_new, per = ops.hole_update(dev(1 - v_t), dev(v_map)[:, :, 0], y_comp.detach()[:, :, 0])
+    assert np.array_equal(host(m_new), g["m_new"])
+    assert np.array_equal(host(x_new), g["x_new"])
+    assert float(per) == pytest.approx(float(g["inp_per"]), rel=1e-5)
+    assert np.array_equal(host(mtb.trivial_copy(dev(x_t), dev(x_al), dev(v_map))), g["trivial"])
+    # strided (frame-major) inputs, as produced by the warp kernel
+    xa_fm = dev(x_al).transpose(1, 2).contiguous().transpose(1, 2)
+    assert np.array_equal(host(ops.chn_pack(dev(x_t), dev(v_t), xa_fm, dev(v_al), dev(v_map))),
+                          g["nn_input"])
+
+
+# ---------------------------------------------------------------- full-size properties
+def test_full_size_properties(mtb):
+    """BASELINE cfg2 sizes (B=8, F=4, 256x256): size-independent properties."""
+    from master_thesis_b200 import ops, synth
+    b, f, h, w = 8, 4, 256, 256
+    x, m, _ = synth.frames(7, b, f + 1, h, w)
+    xr, mr, mt_ = dev(x[:, :, 1:]), dev(m[:, :, 1:]), dev(m[:, :, 0])
+    # (1) identity flow: the warp is the identity (to fp32 noise of the grid itself), the
+    #     nearest visibility is exact, and v_map = clamp(v_al - (1 - m_t))
+    ident = dev(np.broadcast_to(synth.identity_grid(h, w, True), (b, f, h, w, 2)).copy())
+    xa, va, vm = mtb.dfpn_align_tail(xr, mr, mt_, ident)
+    assert (xa - xr).abs().max() <= 1e-5 and torch.equal(va, 1 - mr)
+    assert torch.equal(vm, (va - (1 - mt_).unsqueeze(2)).clamp(0, 1))
+    # (2) integer translation by (dx, dy) pixels == shifted frame with zero padding
+    dx, dy = 5, -3
+    shift = ident.clone()
+    shift[..., 0] += 2.0 * dx / (w - 1)
+    shift[..., 1] += 2.0 * dy / (h - 1)
+    xa, va, _ = mtb.dfpn_align_tail(xr, mr, mt_, shift)
+    ref = torch.zeros_like(xr)
+    ref[..., 3:, :w - dx] = xr[..., :h - 3, dx:]
+    inner = (slice(None),) * 3 + (slice(8, h - 8), slice(8, w - 8))
+    assert (xa[inner] - ref[inner]).abs().max() <= 1e-5
+    # (3) affine identity theta == dense identity grid path (align_corners=False)
+    theta = dev(synth.thetas(0, b * f, 0.0))
+    xa, va, vm = mtb.cpn_align_tail(xr, mr, mt_, theta)
+    assert (xa - xr).abs().max() <= 1e-5 and torch.equal(va, 1 - mr)
+    # (4) oracle spot check on one sample at full resolution
+    flow = synth.dense_flow(9, 1, f, h, w, 0.05, True)
+    xa, va, vm = mtb.dfpn_align_tail(xr[:1], mr[:1], mt_[:1], dev(flow))
+    oxa, ova, ovm = oracle.dfpn_align_tail(x[:1, :, 1:], m[:1, :, 1:], m[:1, :, 0], flow)
+    assert np.array_equal(host(xa), oxa) and np.array_equal(host(va), ova) and np.array_equal(host(vm), ovm)
+    # (5) CM at full size: scaling c_feats of one reference by 0 removes it (weights renormalise)
+    cf, vt, vaa = synth.cm_inputs(3, 2, 5, 128, 64, 64)
+    out, cmask = ops.cm_match(dev(cf), dev(vt), dev(vaa))
+    oout, ocm = oracle.cm_module(cf, vt, vaa)
+    assert np.abs(host(out) - oout).max() <= 1e-5 and np.abs(host(cmask) - ocm).max() <= 2e-6
+    # (6) correlation at the real shape: cosine bounds, symmetry of self-correlation
+    ft, vt_, fr, vr = synth.vgg_feats(5, 2, 2)
+    c = ops.corr4d(dev(ft), None, dev(ft).unsqueeze(2), None)
+    assert float(c.max()) <= 1.0 + 1e-2 and float(c.min()) >= -1e-3
+    c2 = c[:, 0].reshape(2, 256, 256)
+    assert (c2 - c2.transpose(1, 2)).abs().max() <= 2e-3
+    assert (torch.diagonal(c2, dim1=1, dim2=2) - 1).abs().max() <= 2e-3
+
+
+def test_480x854_davis_shape(mtb):
+    """cfg4 shape: non-square, W % 4 != 0 (plane still 16 B aligned)."""
+    from master_thesis_b200 import synth
+    b, f, h, w = 1, 1, 480, 854
+    x, m, _ = synth.frames(17, b, f + 1, h, w)
+    flow = synth.dense_flow(18, b, f, h, w, 0.03, True)
+    xa, va, vm = mtb.dfpn_align_tail(dev(x[:, :, 1:]), dev(m[:, :, 1:]), dev(m[:, :, 0]), dev(flow))
+    oxa, ova, ovm = oracle.dfpn_align_tail(x[:, :, 1:], m[:, :, 1:], m[:, :, 0], flow)
+    assert np.array_equal(host(xa), oxa) and np.array_equal(host(va), ova) and np.array_equal(host(vm), ovm)

@@ -121,3 +121,34 @@ def test_chn(name):
     assert np.array_equal(x_new, g["x_new"])
     assert per == pytest.approx(float(g["inp_per"]), rel=1e-5)
     assert np.array_equal(oracle.trivial_copy(x_t, x_al, v_map), g["trivial"])
+
+
+# --------------------------------------------------------------------------
+# the torch-CPU port (bench.py's cpu_baseline / --impl reference) is pinned too
+# --------------------------------------------------------------------------
+def test_torch_port_matches_golden():
+    import torch
+    from oracle import torch_port as tp
+    T = torch.from_numpy
+    torch.set_num_threads(2)
+    x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES["noisy_oob"])
+    g = load_golden("warp_noisy_oob")
+    xa, va, vm = tp.dfpn_align_tail(T(x), T(m), T(m_t), T(flow))
+    assert np.array_equal(xa.numpy(), g["x_aligned"]) and np.array_equal(vm.numpy(), g["v_map"])
+    x, m, m_t, theta = cases.cpn_inputs(cases.CPN_CASES["rand_f4"])
+    g = load_golden("cpn_rand_f4")
+    xa, va, vm = tp.cpn_align_tail(T(x), T(m), T(m_t), T(theta))
+    assert np.array_equal(xa.numpy(), g["x_aligned"]) and np.array_equal(va.numpy(), g["v_aligned"])
+    ft, vt, fr, vr = cases.corr_inputs(cases.CORR_CASES["small_masked"])
+    assert np.array_equal(tp.corr4d(T(ft), T(vt), T(fr), T(vr)).numpy(), load_golden("corr_small_masked")["corr"])
+    cf, vt, va = cases.cm_inputs(cases.CM_CASES["edge"])
+    out, cmask = tp.cm_module(T(cf), T(vt), T(va))
+    assert np.array_equal(out.numpy(), load_golden("cm_edge")["out"])
+    x_t, v_t, x_al, v_al, v_map, nn_out = cases.chn_inputs(cases.CHN_CASES["f4"])
+    g = load_golden("chn_f4")
+    assert np.array_equal(tp.chn_pack(T(x_t), T(v_t), T(x_al), T(v_al), T(v_map)).numpy(), g["nn_input"])
+    yh, yc = tp.chn_composite(T(nn_out), T(x_t), T(v_t), 2, 4)
+    assert np.array_equal(yc.numpy(), g["y_hat_comp"])
+    x, m, flow, flow_gt, use, t, r_list = cases.loss_inputs(cases.LOSS_CASES["f4"])
+    rec = tp.alignment_recons(T(x)[:, :, t], T(1 - m)[:, :, t], T(x)[:, :, r_list], T(1 - m)[:, :, r_list], T(flow))
+    assert float(rec) == float(load_golden("loss_f4")["recons"])
