@@ -8,13 +8,15 @@
 // per-pixel softmax over the references and a weighted copy.  It is HBM-bound
 // (AI ~ 0.6 flop/B), not a GEMM, so it stays on the SIMT pipes:
 //   pass 0  cm_masks:  v' = bilinear_resize(v, (h,w)) > 0.5 for target + refs
-//   pass 1  cm_sim:    partial sums of vt'*vr'*c_t*c_r per (b, r); reads
-//                      c_feats exactly once from HBM (16 B loads, 20 in flight
-//                      per thread)
-//   pass 2  cm_copy:   gs -> masked softmax over refs -> c_out, c_mask and the
-//                      concatenated output; re-reads c_feats from L2 (a sample
-//                      is 10.5 MB, a cfg2 batch 84 MB < 126 MB of L2)
-// Reductions are two-level and fixed-order (deterministic, no atomics).
+//   pass 1  cm_sim:    partial sums of vt'*vr'*c_t*c_r (and of vt'*vr') per (b, r);
+//                      reads c_feats exactly once from HBM (16 B loads, 20 in
+//                      flight per thread)
+//   pass 2  cm_copy:   every CTA first folds the partials of its sample into gs
+//                      (fixed order, double), then masked softmax over refs ->
+//                      c_out, c_mask and the concatenated output; re-reads
+//                      c_feats (L2 where it still is: a sample is 10.5 MB)
+// Reductions are two-level and fixed-order (deterministic, no atomics, no
+// separate reduction launch: a 14 us single-CTA-per-sample kernel was removed).
 #include <math.h>
 
 #include "mt_common.cuh"
@@ -30,7 +32,7 @@ struct CmArgs {
     const float *c_feats, *v_t, *v_al;
     float *out, *c_mask;
     float *masks;     // workspace: (B, f, P)   index 0 = target
-    float *partials;  // workspace: (B, nparts, R + 1)
+    float *partials;  // workspace: (B, nparts, 2R): [dot_r ..., vsum_r ...]
     float *gs;        // workspace: (B, R)  (exported for tests)
     int B, C, f, h, w, H, W, P, R, nparts, chunks;
 };
@@ -68,12 +70,12 @@ __global__ void __launch_bounds__(256) cm_masks_kernel(const CmArgs a) {
 // pass 1: grid (chunks, C / kSimChannels, B); thread = 4 pixels x kSimChannels channels
 template <int R>
 __global__ void __launch_bounds__(256) cm_sim_kernel(const CmArgs a) {
-    __shared__ float red[R * 32];
+    __shared__ float red[2 * R * 32];
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int slab = blockIdx.y, b = blockIdx.z;
-    float acc[R];
+    float acc[2 * R];  // [0, R): dot products, [R, 2R): sum of vt'*vr' (slab 0 only)
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.0f;
+    for (int r = 0; r < 2 * R; ++r) acc[r] = 0.0f;
     if (p0 < a.P) {
         const float *mk = a.masks + (int64_t)b * a.f * a.P + p0;
         const float4 vt = *reinterpret_cast<const float4 *>(mk);
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(256) cm_sim_kernel(const CmArgs a) {
         for (int r = 0; r < R; ++r) {
             const float4 vr = *reinterpret_cast<const float4 *>(mk + (int64_t)(r + 1) * a.P);
             vm[r] = make_float4(vt.x * vr.x, vt.y * vr.y, vt.z * vr.z, vt.w * vr.w);  // :220
+            if (slab == 0) acc[R + r] = (vm[r].x + vm[r].y) + (vm[r].z + vm[r].w);     // :221
         }
         const int c0 = slab * kSimChannels;
         float4 ct[kSimChannels], cr[kSimChannels][R];
@@ -110,61 +113,58 @@ __global__ void __launch_bounds__(256) cm_sim_kernel(const CmArgs a) {
             }
         }
     }
-    block_sum<R>(acc, red);
+    block_sum<2 * R>(acc, red);
     if (threadIdx.x == 0) {
-        float *o = a.partials + ((int64_t)b * a.nparts + slab * a.chunks + blockIdx.x) * R;
+        float *o = a.partials + ((int64_t)b * a.nparts + slab * a.chunks + blockIdx.x) * (2 * R);
 #pragma unroll
-        for (int r = 0; r < R; ++r) o[r] = acc[r];
+        for (int r = 0; r < 2 * R; ++r) o[r] = acc[r];
     }
 }
 
-// gs[b, r] from the partials + the masks: one CTA per sample (tiny)
+// gs[b, :] from the partials of sample b, computed redundantly (same fixed order, so
+// bit-identical) by every CTA of pass 2.  Result in smem gs[R].
 template <int R>
-__global__ void __launch_bounds__(256) cm_gs_kernel(const CmArgs a) {
-    __shared__ double dred[2 * R * 32];
-    const int b = blockIdx.x;
-    double dot[R], vs[R];
+__device__ __forceinline__ void fold_gs(const CmArgs &a, int b, float *gs_smem) {
+    __shared__ double dred[2 * R * 8];
+    double v[2 * R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { dot[r] = 0.0; vs[r] = 0.0; }
+    for (int r = 0; r < 2 * R; ++r) v[r] = 0.0;
     for (int i = threadIdx.x; i < a.nparts; i += blockDim.x) {
-        const float *o = a.partials + ((int64_t)b * a.nparts + i) * R;
+        const float *o = a.partials + ((int64_t)b * a.nparts + i) * (2 * R);
 #pragma unroll
-        for (int r = 0; r < R; ++r) dot[r] += (double)o[r];
-    }
-    const float *mk = a.masks + (int64_t)b * a.f * a.P;
-    for (int p = threadIdx.x; p < a.P; p += blockDim.x) {
-        const float vt = mk[p];
-#pragma unroll
-        for (int r = 0; r < R; ++r) vs[r] += (double)(vt * mk[(int64_t)(r + 1) * a.P + p]);  // :221
+        for (int r = 0; r < 2 * R; ++r) v[r] += (double)__ldcg(o + r);
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        dot[r] = warp_sum(dot[r]);
-        vs[r] = warp_sum(vs[r]);
-        if (lane == 0) { dred[(2 * r) * 32 + wid] = dot[r]; dred[(2 * r + 1) * 32 + wid] = vs[r]; }
+    for (int r = 0; r < 2 * R; ++r) {
+        v[r] = warp_sum(v[r]);
+        if (lane == 0) dred[r * 8 + wid] = v[r];
     }
     __syncthreads();
     if (threadIdx.x < R) {
         const int r = threadIdx.x;
-        double d = 0.0, v = 0.0;
-        for (int w = 0; w < nw; ++w) { d += dred[(2 * r) * 32 + w]; v += dred[(2 * r + 1) * 32 + w]; }
-        const bool zero = v < 1e-4;                                       // :222
-        const float v_sum = (float)v + (zero ? 1.0f : 0.0f);              // :223
-        const float g = (float)d / (v_sum * (float)a.C);                  // :225-227
-        a.gs[(int64_t)b * R + r] = zero ? 0.0f : g;                        // :228
+        double d = 0.0, vs = 0.0;
+        for (int w = 0; w < nw; ++w) { d += dred[r * 8 + w]; vs += dred[(R + r) * 8 + w]; }
+        const bool zero = vs < 1e-4;                                       // :222
+        const float v_sum = (float)vs + (zero ? 1.0f : 0.0f);              // :223
+        const float g = (float)d / (v_sum * (float)a.C);                   // :225-227
+        gs_smem[r] = zero ? 0.0f : g;                                      // :228
     }
+    __syncthreads();
 }
 
 // pass 2: grid (chunks, ceil(C / kCopyChannels), B)
 template <int R>
 __global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
+    __shared__ float gs_smem[R];
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (p0 >= a.P) return;
     const int slab = blockIdx.y, b = blockIdx.z;
+    fold_gs<R>(a, b, gs_smem);
+    if (blockIdx.x == 0 && slab == 0 && threadIdx.x < R) a.gs[(int64_t)b * R + threadIdx.x] = gs_smem[threadIdx.x];
+    if (p0 >= a.P) return;
     float gsr[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) gsr[r] = __ldg(a.gs + (int64_t)b * R + r);
+    for (int r = 0; r < R; ++r) gsr[r] = gs_smem[r];
     const float *mk = a.masks + (int64_t)b * a.f * a.P + p0;
     float wgt[R][4], vr[R][4];
 #pragma unroll
@@ -226,7 +226,6 @@ int launch_cm(const CmArgs &a, cudaStream_t st) {
     cm_masks_kernel<<<g0, 256, 0, st>>>(a);
     dim3 g1(a.chunks, (a.C + kSimChannels - 1) / kSimChannels, a.B);
     cm_sim_kernel<R><<<g1, 256, 0, st>>>(a);
-    cm_gs_kernel<R><<<a.B, 256, 0, st>>>(a);
     dim3 g2(a.chunks, (a.C + kCopyChannels - 1) / kCopyChannels, a.B);
     cm_copy_kernel<R><<<g2, 256, 0, st>>>(a);
     return launch_status("mt_cm_match_fwd");
@@ -243,7 +242,7 @@ extern "C" int64_t mt_cm_workspace_bytes(int B, int C, int f, int h, int w) {
     if (B <= 0 || C <= 0 || f < 2 || h <= 0 || w <= 0) return 0;
     const int64_t P = (int64_t)h * w, R = f - 1;
     const int64_t chunks = (P + 1023) / 1024, nparts = chunks * ((C + kSimChannels - 1) / kSimChannels);
-    return align256(B * f * P * 4) + align256(B * nparts * R * 4) + align256(B * R * 4);
+    return align256(B * f * P * 4) + align256(B * nparts * 2 * R * 4) + align256(B * R * 4);
 }
 
 extern "C" int mt_cm_match_fwd(const float *c_feats, const float *v_t, const float *v_aligned,
@@ -265,7 +264,7 @@ extern "C" int mt_cm_match_fwd(const float *c_feats, const float *v_t, const flo
     a.masks = reinterpret_cast<float *>(ws);
     ws += align256((int64_t)B * f * a.P * 4);
     a.partials = reinterpret_cast<float *>(ws);
-    ws += align256((int64_t)B * a.nparts * a.R * 4);
+    ws += align256((int64_t)B * a.nparts * 2 * a.R * 4);
     a.gs = reinterpret_cast<float *>(ws);
     cudaStream_t st = (cudaStream_t)stream;
     switch (a.R) {
@@ -285,5 +284,5 @@ extern "C" const float *mt_cm_workspace_gs(const void *workspace, int B, int C, 
     const int64_t P = (int64_t)h * w, R = f - 1;
     const int64_t chunks = (P + 1023) / 1024, nparts = chunks * ((C + kSimChannels - 1) / kSimChannels);
     return reinterpret_cast<const float *>(reinterpret_cast<const char *>(workspace) +
-                                           align256(B * f * P * 4) + align256(B * nparts * R * 4));
+                                           align256(B * f * P * 4) + align256(B * nparts * 2 * R * 4));
 }

@@ -10,11 +10,13 @@
 //   autograd of the above           (a6)
 //
 // HBM-bound gather kernels.  Layout: every tensor is a set of contiguous
-// (H, W) planes.  One thread owns VEC = 4 consecutive pixels of the flattened
-// plane: the grid is read with two 16 B streaming loads, the outputs leave
-// with one 16 B streaming store per plane, and the 4-corner gathers go through
-// L1 (neighbouring pixels of a coherent flow share cache lines).  No shared
-// memory staging in this version: see DESIGN.md for the ncu evidence.
+// (H, W) planes.  Lanes of a warp own CONSECUTIVE pixels of the flattened plane,
+// so a gather instruction of a coherent flow touches 1-2 cache lines (a
+// 4-pixels-per-thread mapping was measured at 30% of HBM peak: every gather
+// spanned 4 lines, see profiles/).  Each thread processes U = 4 pixels 256 apart
+// for memory-level parallelism: all 4 * (4C + 1..4) gathers are issued before
+// the first use.  Grid loads (8 B/lane) and all stores (4 B/lane) are fully
+// coalesced 128 B-per-warp streaming accesses.
 #include <math.h>
 
 #include "mt_common.cuh"
@@ -23,9 +25,10 @@ namespace mt {
 namespace {
 
 struct Sampler {
-    float sfx, sfy;  // (W-1)/2 | W/2, (H-1)/2 | H/2   (host-computed in fp32)
+    float sfx, sfy;      // (W-1)/2 | W/2, (H-1)/2 | H/2   (host-computed in fp32)
     float wmax, hmax;
-    int W;
+    float stepx, stepy;  // 2/(W-1), 2/(H-1): torch.linspace step for affine grids
+    int W, H;
     bool ac;
 };
 
@@ -93,18 +96,21 @@ __device__ __forceinline__ float nearest(const float *__restrict__ plane, float 
 }
 
 // torch.linspace(-1, 1, n)[i] (scalar CPU algorithm), scaled for align_corners=False
-__device__ __forceinline__ float base_coord(int idx, int size, bool ac) {
+// step = 2 / (size - 1) in fp32, computed once on the host (same IEEE division)
+__device__ __forceinline__ float base_coord(int idx, int size, float step, bool ac) {
     float v;
     if (size <= 1) {
         v = -1.0f;
     } else {
-        const float step = __fdiv_rn(2.0f, (float)(size - 1));
         v = (idx < size / 2) ? __fadd_rn(-1.0f, __fmul_rn(step, (float)idx))
                              : __fsub_rn(1.0f, __fmul_rn(step, (float)(size - idx - 1)));
     }
     if (!ac) v = __fdiv_rn(__fmul_rn(v, (float)(size - 1)), (float)size);
     return v;
 }
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;  // pixels per thread, kThreads apart
 
 struct WarpArgs {
     const float *x; int64_t x_sb, x_sc, x_sf;
@@ -113,107 +119,90 @@ struct WarpArgs {
     const float *m_target; int64_t mt_sb;
     float *x_al; int64_t xa_sb, xa_sc, xa_sf;
     float *v_al; float *v_map;
-    int F, H, W; int P;
+    int F; int P;
     Sampler sp;
     bool affine, from_mask;
 };
 
-// grid coordinates of VEC consecutive pixels starting at flat index p0
-template <int VEC>
-__device__ __forceinline__ void load_coords(const WarpArgs &a, int64_t n, int p0, float (&gx)[VEC],
-                                            float (&gy)[VEC]) {
-    if (!a.affine) {
-        const float *g = a.grid + (n * a.P + p0) * 2;
-        if (VEC == 4) {
-            const float4 g0 = ld_stream4(g), g1 = ld_stream4(g + 4);
-            gx[0] = g0.x; gy[0] = g0.y; gx[1 % VEC] = g0.z; gy[1 % VEC] = g0.w;
-            gx[2 % VEC] = g1.x; gy[2 % VEC] = g1.y; gx[3 % VEC] = g1.z; gy[3 % VEC] = g1.w;
-        } else {
-            const float2 t = __ldcs(reinterpret_cast<const float2 *>(g));
-            gx[0] = t.x; gy[0] = t.y;
-        }
+// grid coordinate of pixel p of frame n; NaN for p >= P (=> every corner out of
+// bounds, no gather is issued for the slot)
+__device__ __forceinline__ void load_coord(const float *__restrict__ grid, bool affine, const Sampler &sp,
+                                           int64_t n, int p, int P, float &gx, float &gy) {
+    if (p >= P) {
+        gx = gy = __int_as_float(0x7fc00000);
+        return;
+    }
+    if (!affine) {
+        const float2 t = __ldcs(reinterpret_cast<const float2 *>(grid) + n * P + p);
+        gx = t.x;
+        gy = t.y;
     } else {
-        const float *th = a.grid + n * 6;
-        const float t0 = __ldg(th), t1 = __ldg(th + 1), t2 = __ldg(th + 2);
-        const float t3 = __ldg(th + 3), t4 = __ldg(th + 4), t5 = __ldg(th + 5);
-        int y = p0 / a.W, xx = p0 - y * a.W;
-        float by = base_coord(y, a.H, a.sp.ac);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const float bx = base_coord(xx, a.W, a.sp.ac);
-            // base_grid (x, y, 1) @ theta^T: fma(by, t1, bx*t0) + t2  (pinned order)
-            gx[i] = __fadd_rn(__fmaf_rn(by, t1, __fmul_rn(bx, t0)), t2);
-            gy[i] = __fadd_rn(__fmaf_rn(by, t4, __fmul_rn(bx, t3)), t5);
-            if (++xx == a.W) { xx = 0; ++y; by = base_coord(y, a.H, a.sp.ac); }
-        }
+        const float *th = grid + n * 6;
+        const int y = p / sp.W, xx = p - y * sp.W;
+        const float bx = base_coord(xx, sp.W, sp.stepx, sp.ac), by = base_coord(y, sp.H, sp.stepy, sp.ac);
+        // base_grid (x, y, 1) @ theta^T: fma(by, t1, bx*t0) + t2  (pinned order)
+        gx = __fadd_rn(__fmaf_rn(by, __ldg(th + 1), __fmul_rn(bx, __ldg(th))), __ldg(th + 2));
+        gy = __fadd_rn(__fmaf_rn(by, __ldg(th + 4), __fmul_rn(bx, __ldg(th + 3))), __ldg(th + 5));
     }
 }
 
-template <int C, int VEC, bool VIS_BIL>
-__global__ void __launch_bounds__(256) warp_fwd_kernel(const WarpArgs a) {
-    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (p0 >= a.P) return;
+template <int C, int U, bool VIS_BIL>
+__global__ void __launch_bounds__(kThreads) warp_fwd_kernel(const WarpArgs a) {
+    const int p0 = blockIdx.x * (kThreads * U) + threadIdx.x;
     const int64_t n = blockIdx.y;
     const int b = (int)(n / a.F), f = (int)(n - (int64_t)b * a.F);
-
-    float gx[VEC], gy[VEC];
-    load_coords<VEC>(a, n, p0, gx, gy);
-    Vec<VEC> mt;
-    if (a.v_map) mt.load_stream(a.m_target + b * a.mt_sb + p0);
-
     const float *xb = a.x + b * a.x_sb + f * a.x_sf;
     const float *vp = a.vis + b * a.vis_sb + f * a.vis_sf;
 
-    Bil bl[VEC];
-    float ix[VEC], iy[VEC];
+    Bil bl[U];
+    float ix[U], iy[U], mt[U];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        ix[i] = unnormalize(gx[i], a.sp.sfx, a.sp.ac);
-        iy[i] = unnormalize(gy[i], a.sp.sfy, a.sp.ac);
-        bl[i] = bil_params(ix[i], iy[i], a.sp);
+    for (int k = 0; k < U; ++k) {
+        const int p = p0 + k * kThreads;
+        float gx, gy;
+        load_coord(a.grid, a.affine, a.sp, n, p, a.P, gx, gy);
+        mt[k] = (a.v_map && p < a.P) ? __ldcs(a.m_target + b * a.mt_sb + p) : 0.0f;
+        ix[k] = unnormalize(gx, a.sp.sfx, a.sp.ac);
+        iy[k] = unnormalize(gy, a.sp.sfy, a.sp.ac);
+        bl[k] = bil_params(ix[k], iy[k], a.sp);
     }
-    // issue every gather before any use: VEC * (4C + 1..4) loads in flight
-    Corners cx[C][VEC];
+    // issue every gather before any use: U * (4C + 1..4) loads in flight per thread
+    Corners cx[C][U];
 #pragma unroll
     for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) cx[c][i] = gather(xb + c * a.x_sc, bl[i], a.W);
-    Vec<VEC> va;
+        for (int k = 0; k < U; ++k) cx[c][k] = gather(xb + c * a.x_sc, bl[k], a.sp.W);
+    float va[U];
     if (VIS_BIL) {
-        Corners cv[VEC];
+        Corners cv[U];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            cv[i] = gather(vp, bl[i], a.W);
+        for (int k = 0; k < U; ++k) cv[k] = gather(vp, bl[k], a.sp.W);
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
             if (a.from_mask) {  // v = 1 - m inside the frame, 0 outside (zero padding of v)
-                cv[i].nw = (bl[i].y0 && bl[i].x0) ? __fsub_rn(1.0f, cv[i].nw) : 0.0f;
-                cv[i].ne = (bl[i].y0 && bl[i].x1) ? __fsub_rn(1.0f, cv[i].ne) : 0.0f;
-                cv[i].sw = (bl[i].y1 && bl[i].x0) ? __fsub_rn(1.0f, cv[i].sw) : 0.0f;
-                cv[i].se = (bl[i].y1 && bl[i].x1) ? __fsub_rn(1.0f, cv[i].se) : 0.0f;
+                cv[k].nw = (bl[k].y0 && bl[k].x0) ? __fsub_rn(1.0f, cv[k].nw) : 0.0f;
+                cv[k].ne = (bl[k].y0 && bl[k].x1) ? __fsub_rn(1.0f, cv[k].ne) : 0.0f;
+                cv[k].sw = (bl[k].y1 && bl[k].x0) ? __fsub_rn(1.0f, cv[k].sw) : 0.0f;
+                cv[k].se = (bl[k].y1 && bl[k].x1) ? __fsub_rn(1.0f, cv[k].se) : 0.0f;
             }
-            va.v[i] = interp(cv[i], bl[i]) > 0.5f ? 1.0f : 0.0f;  // strict, model_cpn.py:88
+            va[k] = interp(cv[k], bl[k]) > 0.5f ? 1.0f : 0.0f;  // strict, model_cpn.py:88
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) va.v[i] = nearest(vp, ix[i], iy[i], a.sp, a.from_mask);
+        for (int k = 0; k < U; ++k) va[k] = nearest(vp, ix[k], iy[k], a.sp, a.from_mask);
     }
-
-    if (a.x_al) {
-        float *o = a.x_al + b * a.xa_sb + f * a.xa_sf + p0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            Vec<VEC> r;
+    for (int k = 0; k < U; ++k) {
+        const int p = p0 + k * kThreads;
+        if (p >= a.P) continue;
+        if (a.x_al) {
+            float *o = a.x_al + b * a.xa_sb + f * a.xa_sf + p;
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) r.v[i] = interp(cx[c][i], bl[i]);
-            r.store_stream(o + c * a.xa_sc);
+            for (int c = 0; c < C; ++c) st_stream1(o + c * a.xa_sc, interp(cx[c][k], bl[k]));
         }
-    }
-    if (a.v_al) va.store_stream(a.v_al + n * a.P + p0);
-    if (a.v_map) {
-        Vec<VEC> vm;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i)  // clamp(v_al - (1 - m_t), 0, 1)
-            vm.v[i] = clamp01(__fsub_rn(va.v[i], __fsub_rn(1.0f, mt.v[i])));
-        vm.store_stream(a.v_map + n * a.P + p0);
+        if (a.v_al) st_stream1(a.v_al + n * a.P + p, va[k]);
+        if (a.v_map)  // clamp(v_al - (1 - m_t), 0, 1)
+            st_stream1(a.v_map + n * a.P + p, clamp01(__fsub_rn(va[k], __fsub_rn(1.0f, mt[k]))));
     }
 }
 
@@ -223,46 +212,45 @@ struct WarpBwdArgs {
     const float *grid;
     const float *gout; int64_t g_sb, g_sc, g_sf;
     float *ggrid;
-    int F, H, W; int P;
+    int F; int P;
     Sampler sp;
 };
 
-template <int C, int VEC>
-__global__ void __launch_bounds__(256) warp_bwd_grid_kernel(const WarpBwdArgs a) {
-    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (p0 >= a.P) return;
+template <int C, int U>
+__global__ void __launch_bounds__(kThreads) warp_bwd_grid_kernel(const WarpBwdArgs a) {
+    const int p0 = blockIdx.x * (kThreads * U) + threadIdx.x;
     const int64_t n = blockIdx.y;
     const int b = (int)(n / a.F), f = (int)(n - (int64_t)b * a.F);
-    WarpArgs wa;
-    wa.grid = a.grid; wa.P = a.P; wa.affine = false;
-    float gx[VEC], gy[VEC];
-    load_coords<VEC>(wa, n, p0, gx, gy);
     const float *xb = a.x + b * a.x_sb + f * a.x_sf;
-    const float *gb = a.gout + b * a.g_sb + f * a.g_sf + p0;
-    float ax[VEC], ay[VEC];
-    Bil bl[VEC];
+    const float *gb = a.gout + b * a.g_sb + f * a.g_sf;
+    Bil bl[U];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        bl[i] = bil_params(unnormalize(gx[i], a.sp.sfx, a.sp.ac), unnormalize(gy[i], a.sp.sfy, a.sp.ac), a.sp);
-        ax[i] = 0.0f; ay[i] = 0.0f;
+    for (int k = 0; k < U; ++k) {
+        float gx, gy;
+        load_coord(a.grid, false, a.sp, n, p0 + k * kThreads, a.P, gx, gy);
+        bl[k] = bil_params(unnormalize(gx, a.sp.sfx, a.sp.ac), unnormalize(gy, a.sp.sfy, a.sp.ac), a.sp);
     }
+    Corners cx[C][U];
+    float go[C][U];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-        Vec<VEC> go;
-        go.load_stream(gb + c * a.g_sc);
+    for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const Corners k = gather(xb + c * a.x_sc, bl[i], a.W);
-            ax[i] += ((k.ne - k.nw) * bl[i].s + (k.se - k.sw) * bl[i].n) * go.v[i];
-            ay[i] += ((k.sw - k.nw) * bl[i].e + (k.se - k.ne) * bl[i].w) * go.v[i];
+        for (int k = 0; k < U; ++k) {
+            cx[c][k] = gather(xb + c * a.x_sc, bl[k], a.sp.W);
+            go[c][k] = (p0 + k * kThreads < a.P) ? __ldcs(gb + c * a.g_sc + p0 + k * kThreads) : 0.0f;
         }
-    }
-    float *o = a.ggrid + (n * a.P + p0) * 2;
-    if (VEC == 4) {
-        st_stream4(o, make_float4(ax[0] * a.sp.sfx, ay[0] * a.sp.sfy, ax[1 % VEC] * a.sp.sfx, ay[1 % VEC] * a.sp.sfy));
-        st_stream4(o + 4, make_float4(ax[2 % VEC] * a.sp.sfx, ay[2 % VEC] * a.sp.sfy, ax[3 % VEC] * a.sp.sfx, ay[3 % VEC] * a.sp.sfy));
-    } else {
-        __stcs(reinterpret_cast<float2 *>(o), make_float2(ax[0] * a.sp.sfx, ay[0] * a.sp.sfy));
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+        const int p = p0 + k * kThreads;
+        if (p >= a.P) continue;
+        float ax = 0.0f, ay = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const Corners &q = cx[c][k];
+            ax += ((q.ne - q.nw) * bl[k].s + (q.se - q.sw) * bl[k].n) * go[c][k];
+            ay += ((q.sw - q.nw) * bl[k].e + (q.se - q.ne) * bl[k].w) * go[c][k];
+        }
+        __stcs(reinterpret_cast<float2 *>(a.ggrid) + n * a.P + p, make_float2(ax * a.sp.sfx, ay * a.sp.sfy));
     }
 }
 
@@ -276,8 +264,8 @@ struct WarpL1Args {
     float *x_al; float *v_al;  // frame-major, may be NULL
     float *out3; void *ws;
     const float *out3_in; const float *grad_out; float *gflow;  // backward only
-    int F, H, W; int P; int chunks;  // chunks = ceil(P / (256*VEC))
-    int64_t total_chunks;            // B*F*chunks
+    int F; int P; int tiles;  // tiles = ceil(P / (kThreads*U))
+    int64_t total_tiles;      // B*F*tiles
     float weight;
     Sampler sp;
     bool from_mask;
@@ -288,49 +276,52 @@ __device__ __forceinline__ float mask_out_of(float gx, float gy) {
     return (gx < -1.0f || gx > 1.0f || gy < -1.0f || gy > 1.0f) ? 1.0f : 0.0f;
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(256) warp_l1_fwd_kernel(const WarpL1Args a) {
+template <int U>
+__global__ void __launch_bounds__(kThreads) warp_l1_fwd_kernel(const WarpL1Args a) {
     __shared__ float red[2 * 32];
     float acc[2] = {0.0f, 0.0f};  // sum |x_t*M - x_al*M| over 3 channels, sum M
-    WarpArgs wa;
-    wa.grid = a.flow; wa.P = a.P; wa.affine = false;
-    for (int64_t ch = blockIdx.x; ch < a.total_chunks; ch += gridDim.x) {
-        const int64_t n = ch / a.chunks;
-        const int p0 = ((int)(ch - n * a.chunks) * blockDim.x + threadIdx.x) * VEC;
-        if (p0 >= a.P) continue;
+    for (int64_t t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        const int64_t n = t / a.tiles;
+        const int p0 = (int)(t - n * a.tiles) * (kThreads * U) + threadIdx.x;
         const int b = (int)(n / a.F), f = (int)(n - (int64_t)b * a.F);
-        float gx[VEC], gy[VEC];
-        load_coords<VEC>(wa, n, p0, gx, gy);
         const float *xb = a.x + b * a.x_sb + f * a.x_sf;
-        Vec<VEC> vt;
-        vt.load_cached(a.vt + b * a.vt_sb + p0);
-        Bil bl[VEC];
-        float ix[VEC], iy[VEC], M[VEC];
+        Bil bl[U];
+        float ix[U], iy[U], M[U];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            ix[i] = unnormalize(gx[i], a.sp.sfx, a.sp.ac);
-            iy[i] = unnormalize(gy[i], a.sp.sfy, a.sp.ac);
-            bl[i] = bil_params(ix[i], iy[i], a.sp);
-            M[i] = __fmul_rn(vt.v[i], __fsub_rn(1.0f, mask_out_of(gx[i], gy[i])));
-            acc[1] += M[i];
+        for (int k = 0; k < U; ++k) {
+            const int p = p0 + k * kThreads;
+            float gx, gy;
+            load_coord(a.flow, false, a.sp, n, p, a.P, gx, gy);
+            const float vt = p < a.P ? __ldg(a.vt + b * a.vt_sb + p) : 0.0f;
+            ix[k] = unnormalize(gx, a.sp.sfx, a.sp.ac);
+            iy[k] = unnormalize(gy, a.sp.sfy, a.sp.ac);
+            bl[k] = bil_params(ix[k], iy[k], a.sp);
+            M[k] = p < a.P ? __fmul_rn(vt, __fsub_rn(1.0f, mask_out_of(gx, gy))) : 0.0f;
+            acc[1] += M[k];
         }
+        Corners cx[3][U];
+        float xt[3][U];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            Vec<VEC> xt, r;
-            xt.load_cached(a.xt + b * a.xt_sb + c * a.xt_sc + p0);
+        for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                r.v[i] = interp(gather(xb + c * a.x_sc, bl[i], a.W), bl[i]);
-                acc[0] += fabsf(__fsub_rn(__fmul_rn(xt.v[i], M[i]), __fmul_rn(r.v[i], M[i])));
+            for (int k = 0; k < U; ++k) {
+                cx[c][k] = gather(xb + c * a.x_sc, bl[k], a.sp.W);
+                xt[c][k] = (p0 + k * kThreads < a.P) ? __ldg(a.xt + b * a.xt_sb + c * a.xt_sc + p0 + k * kThreads) : 0.0f;
             }
-            if (a.x_al) r.store_stream(a.x_al + (n * 3 + c) * a.P + p0);
-        }
-        if (a.v_al) {
-            const float *vp = a.vis + b * a.vis_sb + f * a.vis_sf;
-            Vec<VEC> va;
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) va.v[i] = nearest(vp, ix[i], iy[i], a.sp, a.from_mask);
-            va.store_stream(a.v_al + n * a.P + p0);
+        for (int k = 0; k < U; ++k) {
+            const int p = p0 + k * kThreads;
+            if (p >= a.P) continue;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float r = interp(cx[c][k], bl[k]);
+                acc[0] += fabsf(__fsub_rn(__fmul_rn(xt[c][k], M[k]), __fmul_rn(r, M[k])));
+                if (a.x_al) st_stream1(a.x_al + (n * 3 + c) * a.P + p, r);
+            }
+            if (a.v_al) {
+                const float *vp = a.vis + b * a.vis_sb + f * a.vis_sf;
+                st_stream1(a.v_al + n * a.P + p, nearest(vp, ix[k], iy[k], a.sp, a.from_mask));
+            }
         }
     }
     float *out3 = a.out3;
@@ -345,48 +336,48 @@ __global__ void __launch_bounds__(256) warp_l1_fwd_kernel(const WarpL1Args a) {
 
 // d loss / d flow in one pass: recomputes the sampling, never materialises
 // x_aligned or its gradient.
-template <int VEC>
-__global__ void __launch_bounds__(256) warp_l1_bwd_kernel(const WarpL1Args a) {
-    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (p0 >= a.P) return;
+template <int U>
+__global__ void __launch_bounds__(kThreads) warp_l1_bwd_kernel(const WarpL1Args a) {
+    const int p0 = blockIdx.x * (kThreads * U) + threadIdx.x;
     const int64_t n = blockIdx.y;
     const int b = (int)(n / a.F), f = (int)(n - (int64_t)b * a.F);
-    WarpArgs wa;
-    wa.grid = a.flow; wa.P = a.P; wa.affine = false;
-    float gx[VEC], gy[VEC];
-    load_coords<VEC>(wa, n, p0, gx, gy);
     const float scale = a.weight * __ldg(a.grad_out) / (__ldg(a.out3_in + 2) + 1e-9f);
     const float *xb = a.x + b * a.x_sb + f * a.x_sf;
-    Vec<VEC> vt;
-    vt.load_cached(a.vt + b * a.vt_sb + p0);
-    Bil bl[VEC];
-    float M[VEC], ax[VEC], ay[VEC];
+    Bil bl[U];
+    float M[U];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        bl[i] = bil_params(unnormalize(gx[i], a.sp.sfx, a.sp.ac), unnormalize(gy[i], a.sp.sfy, a.sp.ac), a.sp);
-        M[i] = __fmul_rn(vt.v[i], __fsub_rn(1.0f, mask_out_of(gx[i], gy[i])));
-        ax[i] = 0.0f; ay[i] = 0.0f;
+    for (int k = 0; k < U; ++k) {
+        const int p = p0 + k * kThreads;
+        float gx, gy;
+        load_coord(a.flow, false, a.sp, n, p, a.P, gx, gy);
+        const float vt = p < a.P ? __ldg(a.vt + b * a.vt_sb + p) : 0.0f;
+        bl[k] = bil_params(unnormalize(gx, a.sp.sfx, a.sp.ac), unnormalize(gy, a.sp.sfy, a.sp.ac), a.sp);
+        M[k] = p < a.P ? __fmul_rn(vt, __fsub_rn(1.0f, mask_out_of(gx, gy))) : 0.0f;
     }
+    Corners cx[3][U];
+    float xt[3][U];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        Vec<VEC> xt;
-        xt.load_cached(a.xt + b * a.xt_sb + c * a.xt_sc + p0);
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const Corners k = gather(xb + c * a.x_sc, bl[i], a.W);
-            const float d = __fsub_rn(__fmul_rn(xt.v[i], M[i]), __fmul_rn(interp(k, bl[i]), M[i]));
-            const float sg = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
-            const float go = -sg * M[i] * scale;  // d loss / d x_aligned
-            ax[i] += ((k.ne - k.nw) * bl[i].s + (k.se - k.sw) * bl[i].n) * go;
-            ay[i] += ((k.sw - k.nw) * bl[i].e + (k.se - k.ne) * bl[i].w) * go;
+        for (int k = 0; k < U; ++k) {
+            cx[c][k] = gather(xb + c * a.x_sc, bl[k], a.sp.W);
+            xt[c][k] = (p0 + k * kThreads < a.P) ? __ldg(a.xt + b * a.xt_sb + c * a.xt_sc + p0 + k * kThreads) : 0.0f;
         }
-    }
-    float *o = a.gflow + (n * a.P + p0) * 2;
-    if (VEC == 4) {
-        st_stream4(o, make_float4(ax[0] * a.sp.sfx, ay[0] * a.sp.sfy, ax[1 % VEC] * a.sp.sfx, ay[1 % VEC] * a.sp.sfy));
-        st_stream4(o + 4, make_float4(ax[2 % VEC] * a.sp.sfx, ay[2 % VEC] * a.sp.sfy, ax[3 % VEC] * a.sp.sfx, ay[3 % VEC] * a.sp.sfy));
-    } else {
-        __stcs(reinterpret_cast<float2 *>(o), make_float2(ax[0] * a.sp.sfx, ay[0] * a.sp.sfy));
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+        const int p = p0 + k * kThreads;
+        if (p >= a.P) continue;
+        float ax = 0.0f, ay = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const Corners &q = cx[c][k];
+            const float d = __fsub_rn(__fmul_rn(xt[c][k], M[k]), __fmul_rn(interp(q, bl[k]), M[k]));
+            const float sg = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+            const float go = -sg * M[k] * scale;  // d loss / d x_aligned
+            ax += ((q.ne - q.nw) * bl[k].s + (q.se - q.sw) * bl[k].n) * go;
+            ay += ((q.sw - q.nw) * bl[k].e + (q.se - q.ne) * bl[k].w) * go;
+        }
+        __stcs(reinterpret_cast<float2 *>(a.gflow) + n * a.P + p, make_float2(ax * a.sp.sfx, ay * a.sp.sfy));
     }
 }
 
@@ -405,12 +396,15 @@ Sampler make_sampler(int H, int W, bool ac) {
     s.sfy = ac ? (float)(H - 1) / 2.0f : (float)H / 2.0f;
     s.wmax = (float)(W - 1);
     s.hmax = (float)(H - 1);
+    s.stepx = W > 1 ? 2.0f / (float)(W - 1) : 0.0f;
+    s.stepy = H > 1 ? 2.0f / (float)(H - 1) : 0.0f;
     s.W = W;
+    s.H = H;
     s.ac = ac;
     return s;
 }
 
-bool mult4(int64_t v) { return (v & 3) == 0; }
+bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
 }  // namespace
 }  // namespace mt
@@ -428,33 +422,27 @@ extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x
     MT_REQUIRE((int64_t)H * W < (1ll << 30), "mt_warp_fwd: plane too large");
     MT_REQUIRE((int64_t)B * F <= 65535, "mt_warp_fwd: B*F > 65535");
     MT_REQUIRE(!v_map || m_target, "mt_warp_fwd: v_map needs m_target");
+    MT_REQUIRE((flags & MT_GRID_AFFINE) || aligned8(grid), "mt_warp_fwd: dense grid must be 8 B aligned");
     WarpArgs a;
     a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sf = x_sf;
     a.vis = vis; a.vis_sb = vis_sb; a.vis_sf = vis_sf;
     a.grid = grid; a.m_target = m_target; a.mt_sb = mt_sb;
     a.x_al = x_aligned; a.xa_sb = xa_sb; a.xa_sc = xa_sc; a.xa_sf = xa_sf;
     a.v_al = v_aligned; a.v_map = v_map;
-    a.F = F; a.H = H; a.W = W; a.P = H * W;
+    a.F = F; a.P = H * W;
     a.sp = make_sampler(H, W, (flags & MT_ALIGN_CORNERS) != 0);
     a.affine = (flags & MT_GRID_AFFINE) != 0;
     a.from_mask = (flags & MT_VIS_FROM_MASK) != 0;
     const bool vis_bil = (flags & MT_VIS_BILINEAR) != 0;
-    // VEC=4 needs every per-frame base 16 B aligned
-    bool v4 = mult4(a.P) && aligned16(x_aligned) && aligned16(v_aligned) && aligned16(v_map) &&
-              aligned16(m_target) && mult4(mt_sb) && mult4(xa_sb) && mult4(xa_sc) && mult4(xa_sf) &&
-              (a.affine || aligned16(grid));
-    const int vec = v4 ? 4 : 1;
-    dim3 block(256), gridd((a.P + 256 * vec - 1) / (256 * vec), B * F);
+    dim3 block(kThreads), gridd((a.P + kThreads * kUnroll - 1) / (kThreads * kUnroll), B * F);
     cudaStream_t st = (cudaStream_t)stream;
-#define MT_LAUNCH_WARP(CC, VV, BB) warp_fwd_kernel<CC, VV, BB><<<gridd, block, 0, st>>>(a)
     if (C == 3) {
-        if (v4) { if (vis_bil) MT_LAUNCH_WARP(3, 4, true); else MT_LAUNCH_WARP(3, 4, false); }
-        else    { if (vis_bil) MT_LAUNCH_WARP(3, 1, true); else MT_LAUNCH_WARP(3, 1, false); }
+        if (vis_bil) warp_fwd_kernel<3, kUnroll, true><<<gridd, block, 0, st>>>(a);
+        else warp_fwd_kernel<3, kUnroll, false><<<gridd, block, 0, st>>>(a);
     } else {
-        if (v4) { if (vis_bil) MT_LAUNCH_WARP(1, 4, true); else MT_LAUNCH_WARP(1, 4, false); }
-        else    { if (vis_bil) MT_LAUNCH_WARP(1, 1, true); else MT_LAUNCH_WARP(1, 1, false); }
+        if (vis_bil) warp_fwd_kernel<1, kUnroll, true><<<gridd, block, 0, st>>>(a);
+        else warp_fwd_kernel<1, kUnroll, false><<<gridd, block, 0, st>>>(a);
     }
-#undef MT_LAUNCH_WARP
     return launch_status("mt_warp_fwd");
 }
 
@@ -467,18 +455,16 @@ extern "C" int mt_warp_bwd_grid(const float *x, int64_t x_sb, int64_t x_sc, int6
     MT_REQUIRE(C == 1 || C == 3, "mt_warp_bwd_grid: C must be 1 or 3, got %d", C);
     MT_REQUIRE(!(flags & MT_GRID_AFFINE), "mt_warp_bwd_grid: dense grids only");
     MT_REQUIRE((int64_t)H * W < (1ll << 30) && (int64_t)B * F <= 65535, "mt_warp_bwd_grid: too large");
+    MT_REQUIRE(aligned8(grid) && aligned8(ggrid), "mt_warp_bwd_grid: grids must be 8 B aligned");
     WarpBwdArgs a;
     a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sf = x_sf; a.grid = grid;
     a.gout = gout; a.g_sb = g_sb; a.g_sc = g_sc; a.g_sf = g_sf; a.ggrid = ggrid;
-    a.F = F; a.H = H; a.W = W; a.P = H * W;
+    a.F = F; a.P = H * W;
     a.sp = make_sampler(H, W, (flags & MT_ALIGN_CORNERS) != 0);
-    bool v4 = mult4(a.P) && aligned16(grid) && aligned16(ggrid) && aligned16(gout) && mult4(g_sb) &&
-              mult4(g_sc) && mult4(g_sf);
-    const int vec = v4 ? 4 : 1;
-    dim3 block(256), gridd((a.P + 256 * vec - 1) / (256 * vec), B * F);
+    dim3 block(kThreads), gridd((a.P + kThreads * kUnroll - 1) / (kThreads * kUnroll), B * F);
     cudaStream_t st = (cudaStream_t)stream;
-    if (C == 3) { if (v4) warp_bwd_grid_kernel<3, 4><<<gridd, block, 0, st>>>(a); else warp_bwd_grid_kernel<3, 1><<<gridd, block, 0, st>>>(a); }
-    else        { if (v4) warp_bwd_grid_kernel<1, 4><<<gridd, block, 0, st>>>(a); else warp_bwd_grid_kernel<1, 1><<<gridd, block, 0, st>>>(a); }
+    if (C == 3) warp_bwd_grid_kernel<3, kUnroll><<<gridd, block, 0, st>>>(a);
+    else warp_bwd_grid_kernel<1, kUnroll><<<gridd, block, 0, st>>>(a);
     return launch_status("mt_warp_bwd_grid");
 }
 
@@ -489,13 +475,16 @@ static int fill_l1_args(WarpL1Args &a, const float *x, int64_t x_sb, int64_t x_s
     MT_REQUIRE(x && flow && x_target && v_target, "%s: NULL input", who);
     MT_REQUIRE(B > 0 && F > 0 && H > 0 && W > 0, "%s: empty shape", who);
     MT_REQUIRE((int64_t)H * W < (1ll << 30) && (int64_t)B * F <= 65535, "%s: too large", who);
+    MT_REQUIRE(aligned8(flow), "%s: flow must be 8 B aligned", who);
     a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sf = x_sf; a.flow = flow;
     a.xt = x_target; a.xt_sb = xt_sb; a.xt_sc = xt_sc; a.vt = v_target; a.vt_sb = vt_sb;
-    a.F = F; a.H = H; a.W = W; a.P = H * W; a.weight = weight;
+    a.F = F; a.P = H * W; a.weight = weight;
     a.sp = make_sampler(H, W, (flags & MT_ALIGN_CORNERS) != 0);
     a.from_mask = (flags & MT_VIS_FROM_MASK) != 0;
     a.vis = nullptr; a.vis_sb = a.vis_sf = 0; a.x_al = a.v_al = nullptr; a.out3 = nullptr; a.ws = nullptr;
-    a.out3_in = nullptr; a.grad_out = nullptr; a.gflow = nullptr; a.chunks = 0; a.total_chunks = 0;
+    a.out3_in = nullptr; a.grad_out = nullptr; a.gflow = nullptr;
+    a.tiles = (a.P + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+    a.total_tiles = (int64_t)B * F * a.tiles;
     return MT_OK;
 }
 
@@ -513,17 +502,10 @@ extern "C" int mt_warp_l1_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_
     MT_REQUIRE(!v_aligned || vis, "mt_warp_l1_fwd: v_aligned needs vis");
     a.vis = vis; a.vis_sb = vis_sb; a.vis_sf = vis_sf; a.x_al = x_aligned; a.v_al = v_aligned;
     a.out3 = out3; a.ws = workspace;
-    bool v4 = mult4(a.P) && aligned16(flow) && aligned16(x_target) && aligned16(v_target) &&
-              mult4(xt_sb) && mult4(xt_sc) && mult4(vt_sb) && aligned16(x_aligned) && aligned16(v_aligned);
-    const int vec = v4 ? 4 : 1;
-    a.chunks = (a.P + 256 * vec - 1) / (256 * vec);
-    a.total_chunks = (int64_t)B * F * a.chunks;
     int64_t want = (int64_t)sm_count() * 8;
-    int nblk = (int)(a.total_chunks < want ? a.total_chunks : want);
+    int nblk = (int)(a.total_tiles < want ? a.total_tiles : want);
     if (nblk > kMaxReduceBlocks) nblk = kMaxReduceBlocks;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (v4) warp_l1_fwd_kernel<4><<<nblk, 256, 0, st>>>(a);
-    else warp_l1_fwd_kernel<1><<<nblk, 256, 0, st>>>(a);
+    warp_l1_fwd_kernel<kUnroll><<<nblk, kThreads, 0, (cudaStream_t)stream>>>(a);
     return launch_status("mt_warp_l1_fwd");
 }
 
@@ -537,14 +519,10 @@ extern "C" int mt_warp_l1_bwd(const float *x, int64_t x_sb, int64_t x_sc, int64_
                           F, H, W, weight, flags, "mt_warp_l1_bwd");
     if (rc) return rc;
     MT_REQUIRE(out3 && grad_out && gflow, "mt_warp_l1_bwd: NULL out3 / grad_out / gflow");
+    MT_REQUIRE(aligned8(gflow), "mt_warp_l1_bwd: gflow must be 8 B aligned");
     a.out3_in = out3; a.grad_out = grad_out; a.gflow = gflow;
-    bool v4 = mult4(a.P) && aligned16(flow) && aligned16(gflow) && aligned16(x_target) &&
-              aligned16(v_target) && mult4(xt_sb) && mult4(xt_sc) && mult4(vt_sb);
-    const int vec = v4 ? 4 : 1;
-    dim3 block(256), gridd((a.P + 256 * vec - 1) / (256 * vec), B * F);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (v4) warp_l1_bwd_kernel<4><<<gridd, block, 0, st>>>(a);
-    else warp_l1_bwd_kernel<1><<<gridd, block, 0, st>>>(a);
+    dim3 block(kThreads), gridd(a.tiles, B * F);
+    warp_l1_bwd_kernel<kUnroll><<<gridd, block, 0, (cudaStream_t)stream>>>(a);
     return launch_status("mt_warp_l1_bwd");
 }
 
