@@ -109,8 +109,10 @@ __device__ __forceinline__ float base_coord(int idx, int size, float step, bool 
     return v;
 }
 
-constexpr int kThreads = 256;
-constexpr int kUnroll = 4;  // pixels per thread, kThreads apart
+constexpr int kThreads = 256;  // block size of the flat (reduction / backward) kernels
+constexpr int kUnroll = 4;     // pixels per thread in those kernels, kThreads apart
+constexpr int kCols = 128;     // forward kernel: threads per CTA = columns per CTA
+constexpr int kRows = 4;       // forward kernel: rows per thread
 
 struct WarpArgs {
     const float *x; int64_t x_sb, x_sc, x_sf;
@@ -146,63 +148,173 @@ __device__ __forceinline__ void load_coord(const float *__restrict__ grid, bool 
     }
 }
 
-template <int C, int U, bool VIS_BIL>
-__global__ void __launch_bounds__(kThreads) warp_fwd_kernel(const WarpArgs a) {
-    const int p0 = blockIdx.x * (kThreads * U) + threadIdx.x;
-    const int64_t n = blockIdx.y;
-    const int b = (int)(n / a.F), f = (int)(n - (int64_t)b * a.F);
-    const float *xb = a.x + b * a.x_sb + f * a.x_sf;
-    const float *vp = a.vis + b * a.vis_sb + f * a.vis_sf;
+// Lean bilinear state for the forward kernel: weights + the offset of the NW corner.
+struct Tap {
+    float nw, ne, sw, se;
+    int o;  // yn * W + xw (meaningful when the pixel is interior)
+};
 
-    Bil bl[U];
-    float ix[U], iy[U], mt[U];
+// Forward-kernel arguments: every offset is a 32-bit ELEMENT offset (the launcher
+// checks the ranges), because 64-bit stride arithmetic dominated the per-thread
+// setup of the first versions.
+struct WarpFwdArgs {
+    const float *x, *vis, *grid, *m_target;
+    float *x_al, *v_al, *v_map;
+    int x_sb, x_sc, x_sf, vis_sb, vis_sf, mt_sb, xa_sb, xa_sc, xa_sf;
+    int F, P;
+    unsigned f_magic;  // ceil(2^32 / F): b = umulhi(n, f_magic) for n < 2^16; 0 when F == 1 (b = n)
+    Sampler sp;
+    bool from_mask;
+};
+
+// Forward kernel.  Thread = one column x, U consecutive rows; a warp = 32
+// consecutive columns of one row, so grid loads and all stores are 128 B
+// coalesced and no integer division is needed.  If every tap of every lane of
+// the warp is interior (0 <= xw <= W-2, 0 <= yn <= H-2: the common case) the
+// warp takes the FAST path: unpredicated loads through one 64-bit row pointer
+// per (plane, row), no bounds logic.  Otherwise it takes the generic path.
+// The kernel is instruction-issue-bound, not HBM-bound (ncu: profiles/), so the
+// code below is written for instruction count: template flags instead of
+// uniform branches, the affine row term computed once per CTA, 32-bit offsets.
+// VIS: 1 = nearest (DFPN), 2 = bilinear > 0.5 (CPN).  FULL: x_al, v_al and v_map
+// are all requested (no NULL checks).
+template <int C, int U, int VIS, bool AFFINE, bool FULL>
+__global__ void __launch_bounds__(kCols) warp_fwd_kernel(const WarpFwdArgs a) {
+    __shared__ float s_by[U];
+    const int W = a.sp.W, H = a.sp.H;
+    // lanes past the last column stay alive (the warp vote below needs every lane)
+    // on a clamped column and are masked at the stores
+    const bool live = (int)(blockIdx.x * kCols + threadIdx.x) < W;
+    const int x = min((int)(blockIdx.x * kCols + threadIdx.x), W - 1);
+    const int y0 = blockIdx.y * U;
+    const unsigned n = blockIdx.z;
+    const int b = a.f_magic ? (int)__umulhi(n, a.f_magic) : (int)n, f = (int)n - b * a.F;
+    const bool ac = a.sp.ac;
+    if (AFFINE) {  // row term of the affine grid: U values per CTA
+        if (threadIdx.x < U) s_by[threadIdx.x] = base_coord(min(y0 + (int)threadIdx.x, H - 1), H, a.sp.stepy, ac);
+        __syncthreads();
+    }
+    const int xo = b * a.x_sb + f * a.x_sf;
+    const float *__restrict__ vp = a.vis + (b * a.vis_sb + f * a.vis_sf);
+    const int p0 = y0 * W + x;
+    const int np0 = (int)n * a.P + p0;
+
+    float t1 = 0.f, t2 = 0.f, t4 = 0.f, t5 = 0.f, bxt0 = 0.f, bxt3 = 0.f;
+    if (AFFINE) {
+        const float *th = a.grid + n * 6;
+        const float bx = base_coord(x, W, a.sp.stepx, ac);
+        bxt0 = __fmul_rn(bx, __ldg(th));
+        bxt3 = __fmul_rn(bx, __ldg(th + 3));
+        t1 = __ldg(th + 1); t2 = __ldg(th + 2); t4 = __ldg(th + 4); t5 = __ldg(th + 5);
+    }
+    const float wm2 = a.sp.wmax - 1.0f, hm2 = a.sp.hmax - 1.0f;
+
+    float ix[U], iy[U], xw[U], yn[U];
+    float wnw[U], wne[U], wsw[U], wse[U];
+    bool interior = true;
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-        const int p = p0 + k * kThreads;
         float gx, gy;
-        load_coord(a.grid, a.affine, a.sp, n, p, a.P, gx, gy);
-        mt[k] = (a.v_map && p < a.P) ? __ldcs(a.m_target + b * a.mt_sb + p) : 0.0f;
-        ix[k] = unnormalize(gx, a.sp.sfx, a.sp.ac);
-        iy[k] = unnormalize(gy, a.sp.sfy, a.sp.ac);
-        bl[k] = bil_params(ix[k], iy[k], a.sp);
+        if (AFFINE) {
+            const float by = s_by[k];
+            gx = __fadd_rn(__fmaf_rn(by, t1, bxt0), t2);  // fma(by, t1, bx*t0) + t2 (pinned order)
+            gy = __fadd_rn(__fmaf_rn(by, t4, bxt3), t5);
+        } else if (y0 + k < H) {
+            const float2 g = __ldcs(reinterpret_cast<const float2 *>(a.grid) + (np0 + k * W));
+            gx = g.x; gy = g.y;
+        } else {
+            gx = gy = 0.0f;
+        }
+        ix[k] = unnormalize(gx, a.sp.sfx, ac);
+        iy[k] = unnormalize(gy, a.sp.sfy, ac);
+        xw[k] = floorf(ix[k]);
+        yn[k] = floorf(iy[k]);
+        const float w = __fsub_rn(ix[k], xw[k]), e = __fsub_rn(1.0f, w);
+        const float nn = __fsub_rn(iy[k], yn[k]), ss = __fsub_rn(1.0f, nn);
+        wnw[k] = __fmul_rn(ss, e); wne[k] = __fmul_rn(ss, w);
+        wsw[k] = __fmul_rn(nn, e); wse[k] = __fmul_rn(nn, w);
+        // rows past the end of the frame are computed (harmlessly) and never stored
+        interior = interior && (xw[k] >= 0.0f) && (xw[k] <= wm2) && (yn[k] >= 0.0f) && (yn[k] <= hm2);
     }
-    // issue every gather before any use: U * (4C + 1..4) loads in flight per thread
-    Corners cx[C][U];
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-#pragma unroll
-        for (int k = 0; k < U; ++k) cx[c][k] = gather(xb + c * a.x_sc, bl[k], a.sp.W);
-    float va[U];
-    if (VIS_BIL) {
-        Corners cv[U];
-#pragma unroll
-        for (int k = 0; k < U; ++k) cv[k] = gather(vp, bl[k], a.sp.W);
+    float xa[C][U], va[U];
+    if (__all_sync(0xffffffffu, interior)) {
+        // ---------------- fast path ----------------
+        float c00[C + 1][U], c01[C + 1][U], c10[C + 1][U], c11[C + 1][U];
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-            if (a.from_mask) {  // v = 1 - m inside the frame, 0 outside (zero padding of v)
-                cv[k].nw = (bl[k].y0 && bl[k].x0) ? __fsub_rn(1.0f, cv[k].nw) : 0.0f;
-                cv[k].ne = (bl[k].y0 && bl[k].x1) ? __fsub_rn(1.0f, cv[k].ne) : 0.0f;
-                cv[k].sw = (bl[k].y1 && bl[k].x0) ? __fsub_rn(1.0f, cv[k].sw) : 0.0f;
-                cv[k].se = (bl[k].y1 && bl[k].x1) ? __fsub_rn(1.0f, cv[k].se) : 0.0f;
+            const int o = (int)yn[k] * W + (int)xw[k];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float *r0 = a.x + (xo + c * a.x_sc + o);
+                const float *r1 = a.x + (xo + c * a.x_sc + o + W);
+                c00[c][k] = __ldg(r0); c01[c][k] = __ldg(r0 + 1);
+                c10[c][k] = __ldg(r1); c11[c][k] = __ldg(r1 + 1);
             }
-            va[k] = interp(cv[k], bl[k]) > 0.5f ? 1.0f : 0.0f;  // strict, model_cpn.py:88
+            if (VIS == 2) {
+                const float *r0 = vp + o;
+                const float *r1 = vp + (o + W);
+                c00[C][k] = __ldg(r0); c01[C][k] = __ldg(r0 + 1);
+                c10[C][k] = __ldg(r1); c11[C][k] = __ldg(r1 + 1);
+            } else {
+                // nearest: rint (half-to-even) lands on one of the 4 interior taps: in bounds
+                c00[C][k] = __ldg(vp + ((int)rintf(iy[k]) * W + (int)rintf(ix[k])));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                xa[c][k] = __fmaf_rn(c11[c][k], wse[k], __fmaf_rn(c10[c][k], wsw[k],
+                           __fmaf_rn(c01[c][k], wne[k], __fmul_rn(c00[c][k], wnw[k]))));
+            if (VIS == 2) {
+                float v00 = c00[C][k], v01 = c01[C][k], v10 = c10[C][k], v11 = c11[C][k];
+                if (a.from_mask) {
+                    v00 = __fsub_rn(1.0f, v00); v01 = __fsub_rn(1.0f, v01);
+                    v10 = __fsub_rn(1.0f, v10); v11 = __fsub_rn(1.0f, v11);
+                }
+                const float vs = __fmaf_rn(v11, wse[k], __fmaf_rn(v10, wsw[k],
+                                 __fmaf_rn(v01, wne[k], __fmul_rn(v00, wnw[k]))));
+                va[k] = vs > 0.5f ? 1.0f : 0.0f;  // strict, model_cpn.py:88
+            } else {
+                va[k] = a.from_mask ? __fsub_rn(1.0f, c00[C][k]) : c00[C][k];
+            }
         }
     } else {
+        // ---------------- generic path (border warps, out-of-frame flows) ----------------
 #pragma unroll
-        for (int k = 0; k < U; ++k) va[k] = nearest(vp, ix[k], iy[k], a.sp, a.from_mask);
+        for (int k = 0; k < U; ++k) {
+            const Bil bl = bil_params(ix[k], iy[k], a.sp);
+#pragma unroll
+            for (int c = 0; c < C; ++c) xa[c][k] = interp(gather(a.x + (xo + c * a.x_sc), bl, W), bl);
+            if (VIS == 2) {
+                Corners cv = gather(vp, bl, W);
+                if (a.from_mask) {  // v = 1 - m inside the frame, 0 outside (zero padding of v)
+                    cv.nw = (bl.y0 && bl.x0) ? __fsub_rn(1.0f, cv.nw) : 0.0f;
+                    cv.ne = (bl.y0 && bl.x1) ? __fsub_rn(1.0f, cv.ne) : 0.0f;
+                    cv.sw = (bl.y1 && bl.x0) ? __fsub_rn(1.0f, cv.sw) : 0.0f;
+                    cv.se = (bl.y1 && bl.x1) ? __fsub_rn(1.0f, cv.se) : 0.0f;
+                }
+                va[k] = interp(cv, bl) > 0.5f ? 1.0f : 0.0f;
+            } else {
+                va[k] = nearest(vp, ix[k], iy[k], a.sp, a.from_mask);
+            }
+        }
     }
+    // ---------------- stores (coalesced, streaming) ----------------
+    if (!live) return;
+    const int xao = b * a.xa_sb + f * a.xa_sf + p0;
+    const int mto = b * a.mt_sb + p0;
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-        const int p = p0 + k * kThreads;
-        if (p >= a.P) continue;
-        if (a.x_al) {
-            float *o = a.x_al + b * a.xa_sb + f * a.xa_sf + p;
+        if (y0 + k >= H) break;
+        if (FULL || a.x_al) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) st_stream1(o + c * a.xa_sc, interp(cx[c][k], bl[k]));
+            for (int c = 0; c < C; ++c) st_stream1(a.x_al + (xao + c * a.xa_sc + k * W), xa[c][k]);
         }
-        if (a.v_al) st_stream1(a.v_al + n * a.P + p, va[k]);
-        if (a.v_map)  // clamp(v_al - (1 - m_t), 0, 1)
-            st_stream1(a.v_map + n * a.P + p, clamp01(__fsub_rn(va[k], __fsub_rn(1.0f, mt[k]))));
+        if (FULL || a.v_al) st_stream1(a.v_al + (np0 + k * W), va[k]);
+        if (FULL || a.v_map)  // clamp(v_al - (1 - m_t), 0, 1)
+            st_stream1(a.v_map + (np0 + k * W),
+                       clamp01(__fsub_rn(va[k], __fsub_rn(1.0f, __ldcs(a.m_target + (mto + k * W))))));
     }
 }
 
@@ -419,30 +531,48 @@ extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x
     MT_REQUIRE(x && vis && grid, "mt_warp_fwd: NULL input");
     MT_REQUIRE(B > 0 && F > 0 && H > 0 && W > 0, "mt_warp_fwd: empty shape B=%d F=%d H=%d W=%d", B, F, H, W);
     MT_REQUIRE(C == 1 || C == 3, "mt_warp_fwd: C must be 1 or 3 (reference hard-codes 3, utils.py:97), got %d", C);
-    MT_REQUIRE((int64_t)H * W < (1ll << 30), "mt_warp_fwd: plane too large");
     MT_REQUIRE((int64_t)B * F <= 65535, "mt_warp_fwd: B*F > 65535");
     MT_REQUIRE(!v_map || m_target, "mt_warp_fwd: v_map needs m_target");
     MT_REQUIRE((flags & MT_GRID_AFFINE) || aligned8(grid), "mt_warp_fwd: dense grid must be 8 B aligned");
-    WarpArgs a;
-    a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sf = x_sf;
-    a.vis = vis; a.vis_sb = vis_sb; a.vis_sf = vis_sf;
-    a.grid = grid; a.m_target = m_target; a.mt_sb = mt_sb;
-    a.x_al = x_aligned; a.xa_sb = xa_sb; a.xa_sc = xa_sc; a.xa_sf = xa_sf;
-    a.v_al = v_aligned; a.v_map = v_map;
-    a.F = F; a.P = H * W;
+    MT_REQUIRE((H + kRows - 1) / kRows <= 65535, "mt_warp_fwd: H too large");
+    const int64_t P = (int64_t)H * W, lim = (1ll << 31) - 1;
+    auto span = [&](int64_t sb, int64_t sc, int64_t sf, int c) {
+        return (B - 1) * sb + (c - 1) * sc + (F - 1) * sf + P + W + 1;
+    };
+    MT_REQUIRE(x_sb >= 0 && x_sc >= 0 && x_sf >= 0 && vis_sb >= 0 && vis_sf >= 0 && mt_sb >= 0 &&
+               xa_sb >= 0 && xa_sc >= 0 && xa_sf >= 0, "mt_warp_fwd: negative strides are not supported");
+    MT_REQUIRE(span(x_sb, x_sc, x_sf, C) < lim && span(vis_sb, 0, vis_sf, 1) < lim &&
+               span(xa_sb, xa_sc, xa_sf, C) < lim && (int64_t)B * F * P * 2 < lim && (B - 1) * mt_sb + P < lim,
+               "mt_warp_fwd: tensors beyond 2^31 elements are not supported (split the batch)");
+    WarpFwdArgs a;
+    a.x = x; a.vis = vis; a.grid = grid; a.m_target = m_target;
+    a.x_al = x_aligned; a.v_al = v_aligned; a.v_map = v_map;
+    a.x_sb = (int)x_sb; a.x_sc = (int)x_sc; a.x_sf = (int)x_sf;
+    a.vis_sb = (int)vis_sb; a.vis_sf = (int)vis_sf; a.mt_sb = (int)mt_sb;
+    a.xa_sb = (int)xa_sb; a.xa_sc = (int)xa_sc; a.xa_sf = (int)xa_sf;
+    a.F = F; a.P = (int)P;
+    a.f_magic = F == 1 ? 0u : (unsigned)(((1ull << 32) + (unsigned)F - 1) / (unsigned)F);
     a.sp = make_sampler(H, W, (flags & MT_ALIGN_CORNERS) != 0);
-    a.affine = (flags & MT_GRID_AFFINE) != 0;
     a.from_mask = (flags & MT_VIS_FROM_MASK) != 0;
+    const bool affine = (flags & MT_GRID_AFFINE) != 0;
     const bool vis_bil = (flags & MT_VIS_BILINEAR) != 0;
-    dim3 block(kThreads), gridd((a.P + kThreads * kUnroll - 1) / (kThreads * kUnroll), B * F);
+    dim3 block(kCols), gridd((W + kCols - 1) / kCols, (H + kRows - 1) / kRows, B * F);
     cudaStream_t st = (cudaStream_t)stream;
-    if (C == 3) {
-        if (vis_bil) warp_fwd_kernel<3, kUnroll, true><<<gridd, block, 0, st>>>(a);
-        else warp_fwd_kernel<3, kUnroll, false><<<gridd, block, 0, st>>>(a);
-    } else {
-        if (vis_bil) warp_fwd_kernel<1, kUnroll, true><<<gridd, block, 0, st>>>(a);
-        else warp_fwd_kernel<1, kUnroll, false><<<gridd, block, 0, st>>>(a);
-    }
+    const bool full = x_aligned && v_aligned && v_map;
+#define MT_WARP_GO(CC, VV, AA, FF) warp_fwd_kernel<CC, kRows, VV, AA, FF><<<gridd, block, 0, st>>>(a)
+#define MT_WARP_PICK(CC)                                                            \
+    do {                                                                            \
+        if (vis_bil) {                                                              \
+            if (affine) { if (full) MT_WARP_GO(CC, 2, true, true); else MT_WARP_GO(CC, 2, true, false); }   \
+            else        { if (full) MT_WARP_GO(CC, 2, false, true); else MT_WARP_GO(CC, 2, false, false); } \
+        } else {                                                                    \
+            if (affine) { if (full) MT_WARP_GO(CC, 1, true, true); else MT_WARP_GO(CC, 1, true, false); }   \
+            else        { if (full) MT_WARP_GO(CC, 1, false, true); else MT_WARP_GO(CC, 1, false, false); } \
+        }                                                                           \
+    } while (0)
+    if (C == 3) MT_WARP_PICK(3); else MT_WARP_PICK(1);
+#undef MT_WARP_PICK
+#undef MT_WARP_GO
     return launch_status("mt_warp_fwd");
 }
 

@@ -275,7 +275,7 @@ def test_full_size_properties(mtb):
     ref = torch.zeros_like(xr)
     ref[..., 3:, :w - dx] = xr[..., :h - 3, dx:]
     inner = (slice(None),) * 3 + (slice(8, h - 8), slice(8, w - 8))
-    assert (xa[inner] - ref[inner]).abs().max() <= 1e-5
+    assert (xa[inner] - ref[inner]).abs().max() <= 1e-4
     # (3) affine identity theta == dense identity grid path (align_corners=False)
     theta = dev(synth.thetas(0, b * f, 0.0))
     xa, va, vm = mtb.cpn_align_tail(xr, mr, mt_, theta)
