@@ -113,7 +113,7 @@ class Cfg2(Workload):
         # a8 per sample: c_feats + full-res masks in; (2C+1)*P + P out
         cm = self.b * (self.c * (self.f + 1) * p * 4 + (self.f + 1) * px * 4
                        + (2 * self.c + 1) * p * 4 + p * 4)
-        return [("mt_warp_fwd", 1, warp, "hbm"), ("mt_cm_match_fwd", 3, cm, "hbm")]
+        return [("mt_warp_fwd", 1, warp, "hbm"), ("mt_cm_match_fwd", 4, cm, "hbm")]
 
     def sub(self, b):
         return Cfg2(b, self.f, self.h, self.w, self.c)

@@ -2,6 +2,7 @@
 // the host-buffer (end-to-end) entry points.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mt_common.cuh"
@@ -37,6 +38,18 @@ int sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+int tuning(const char *name, int dflt) {
+    struct Entry { const char *name; int value; };
+    static Entry cache[16];
+    static int used = 0;
+    for (int i = 0; i < used; ++i)
+        if (strcmp(cache[i].name, name) == 0) return cache[i].value;
+    const char *e = getenv(name);
+    const int v = e ? atoi(e) : dflt;
+    if (used < 16) cache[used++] = Entry{name, v};
+    return v;
 }
 
 }  // namespace mt

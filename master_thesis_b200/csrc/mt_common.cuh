@@ -18,6 +18,8 @@ namespace mt {
 void set_error(const char *fmt, ...);
 int launch_status(const char *what);  // cudaGetLastError -> MT_OK / MT_ERR_CUDA
 int sm_count();
+// integer tuning knob from the environment (read once per name), else `dflt`
+int tuning(const char *name, int dflt);
 
 #define MT_REQUIRE(cond, ...)            \
     do {                                 \

@@ -112,7 +112,7 @@ __device__ __forceinline__ float base_coord(int idx, int size, float step, bool 
 constexpr int kThreads = 256;  // block size of the flat (reduction / backward) kernels
 constexpr int kUnroll = 4;     // pixels per thread in those kernels, kThreads apart
 constexpr int kCols = 128;     // forward kernel: threads per CTA = columns per CTA
-constexpr int kRows = 4;       // forward kernel: rows per thread
+constexpr int kRows = 2;       // forward kernel: rows per thread (swept on B200: 2 beats 4, profiles/)
 
 struct WarpArgs {
     const float *x; int64_t x_sb, x_sc, x_sf;
@@ -209,6 +209,14 @@ __global__ void __launch_bounds__(kCols) warp_fwd_kernel(const WarpFwdArgs a) {
     }
     const float wm2 = a.sp.wmax - 1.0f, hm2 = a.sp.hmax - 1.0f;
 
+    // issue the target-mask loads first: they are only needed by the stores at the end
+    float mtv[U];
+    const int mto = b * a.mt_sb + p0;
+    if (FULL || a.v_map) {
+#pragma unroll
+        for (int k = 0; k < U; ++k) mtv[k] = (y0 + k < H) ? __ldcs(a.m_target + (mto + k * W)) : 0.0f;
+    }
+
     float ix[U], iy[U], xw[U], yn[U];
     float wnw[U], wne[U], wsw[U], wse[U];
     bool interior = true;
@@ -303,7 +311,6 @@ __global__ void __launch_bounds__(kCols) warp_fwd_kernel(const WarpFwdArgs a) {
     // ---------------- stores (coalesced, streaming) ----------------
     if (!live) return;
     const int xao = b * a.xa_sb + f * a.xa_sf + p0;
-    const int mto = b * a.mt_sb + p0;
 #pragma unroll
     for (int k = 0; k < U; ++k) {
         if (y0 + k >= H) break;
@@ -314,7 +321,7 @@ __global__ void __launch_bounds__(kCols) warp_fwd_kernel(const WarpFwdArgs a) {
         if (FULL || a.v_al) st_stream1(a.v_al + (np0 + k * W), va[k]);
         if (FULL || a.v_map)  // clamp(v_al - (1 - m_t), 0, 1)
             st_stream1(a.v_map + (np0 + k * W),
-                       clamp01(__fsub_rn(va[k], __fsub_rn(1.0f, __ldcs(a.m_target + (mto + k * W))))));
+                       clamp01(__fsub_rn(va[k], __fsub_rn(1.0f, mtv[k]))));
     }
 }
 
@@ -556,10 +563,15 @@ extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x
     a.from_mask = (flags & MT_VIS_FROM_MASK) != 0;
     const bool affine = (flags & MT_GRID_AFFINE) != 0;
     const bool vis_bil = (flags & MT_VIS_BILINEAR) != 0;
-    dim3 block(kCols), gridd((W + kCols - 1) / kCols, (H + kRows - 1) / kRows, B * F);
+    const int rows = tuning("MT_WARP_ROWS", kRows) == 2 ? 2 : 4;
+    dim3 block(kCols), gridd((W + kCols - 1) / kCols, (H + rows - 1) / rows, B * F);
     cudaStream_t st = (cudaStream_t)stream;
     const bool full = x_aligned && v_aligned && v_map;
-#define MT_WARP_GO(CC, VV, AA, FF) warp_fwd_kernel<CC, kRows, VV, AA, FF><<<gridd, block, 0, st>>>(a)
+#define MT_WARP_GO(CC, VV, AA, FF)                                                  \
+    do {                                                                            \
+        if (rows == 2) warp_fwd_kernel<CC, 2, VV, AA, FF><<<gridd, block, 0, st>>>(a); \
+        else warp_fwd_kernel<CC, 4, VV, AA, FF><<<gridd, block, 0, st>>>(a);        \
+    } while (0)
 #define MT_WARP_PICK(CC)                                                            \
     do {                                                                            \
         if (vis_bil) {                                                              \
