@@ -221,53 +221,68 @@ class Cfg4(Workload):
 
 
 class Cfg3(Workload):
-    """DFPN training hot path: fused warp + mask_out + masked L1 forward and backward."""
+    """DFPN training-step hot path (model_dfpn.py:310-394, 210-293): masked correlation of the
+    forward pass, unmasked correlation of the ground truth, and the fused warp + mask_out +
+    masked-L1 reconstruction loss forward and backward at the 256 and 64 scales."""
     name = "cfg3"
 
     def __init__(self, b=32, f=4, h=256, w=256):
         self.b, self.f, self.h, self.w = b, f, h, w
         self.frames_per_step = b * f
-        self.describe = ("cfg3: DFPN training hot path (fused warp+mask_out+masked-L1 fwd and bwd "
-                         "w.r.t. flow), batch_size=%d frames_n=%d %dx%d per GPU" % (b, f + 1, h, w))
+        self.describe = ("cfg3: DFPN training hot path (2x correlation_masked_4d 512x16x16 + fused "
+                         "warp+mask_out+masked-L1 fwd/bwd at %dx%d and %dx%d), batch_size=%d "
+                         "frames_n=%d per GPU" % (h, w, h // 4, w // 4, b, f + 1))
 
     def host_inputs(self, seed):
         import numpy as np
         from master_thesis_b200 import synth
         b, f, h, w = self.b, self.f, self.h, self.w
-        x, m, _ = synth.frames(seed, b, f + 1, h, w)
         t = (f + 1) // 2
         refs = [i for i in range(f + 1) if i != t]
-        return {
-            "x_target": np.ascontiguousarray(x[:, :, t]),
-            "v_target": np.ascontiguousarray(1 - m[:, :, t]),
-            "x_refs": np.ascontiguousarray(x[:, :, refs]),
-            "v_refs": np.ascontiguousarray(1 - m[:, :, refs]),
-            "flow": synth.dense_flow(seed + 1, b, f, h, w, 0.05, True),
-            "grad_out": np.ones(1, np.float32),
-        }
-
-    inputs_h2d = ("x_target", "v_target", "x_refs", "v_refs", "flow")
+        d = {"grad_out": np.ones(1, np.float32)}
+        for tag, (hh, ww) in (("", (h, w)), ("_s", (h // 4, w // 4))):
+            x, m, _ = synth.frames(seed + len(tag), b, f + 1, hh, ww)
+            d["x_target" + tag] = np.ascontiguousarray(x[:, :, t])
+            d["v_target" + tag] = np.ascontiguousarray(1 - m[:, :, t])
+            d["x_refs" + tag] = np.ascontiguousarray(x[:, :, refs])
+            d["v_refs" + tag] = np.ascontiguousarray(1 - m[:, :, refs])
+            d["flow" + tag] = synth.dense_flow(seed + 1, b, f, hh, ww, 0.05, True)
+        ft, vt, fr, vr = synth.vgg_feats(seed + 2, b, f)
+        d.update({"feats_t": ft, "v_t16": vt, "feats_r": fr, "v_r16": vr})
+        return d
 
     def gpu_step(self, mtb, d):
-        # the two launches autograd issues for LossesUtils.alignment_recons(...).backward()
-        out3, _, _, saved = mtb.ops.warp_l1_fwd_raw(d["x_refs"], d["v_refs"], d["flow"],
-                                                    d["x_target"], d["v_target"])
-        g = mtb.ops.warp_l1_bwd_raw(saved, d["grad_out"])
-        return {"loss": out3, "g_flow": g}
+        ops = mtb.ops
+        out = {"corr": ops.corr4d(d["feats_t"], d["v_t16"], d["feats_r"], d["v_r16"]),
+               "corr_y": ops.corr4d(d["feats_t"], None, d["feats_r"], None)}
+        for tag in ("", "_s"):
+            # the two launches autograd issues for LossesUtils.alignment_recons(...).backward()
+            out3, _, _, saved = ops.warp_l1_fwd_raw(d["x_refs" + tag], d["v_refs" + tag], d["flow" + tag],
+                                                    d["x_target" + tag], d["v_target" + tag])
+            out["loss" + tag] = out3
+            out["g_flow" + tag] = ops.warp_l1_bwd_raw(saved, d["grad_out"])
+        return out
 
     def cpu_step(self, tp, d):
         import torch
-        flow = d["flow"].detach().requires_grad_(True)
-        loss = tp.alignment_recons(d["x_target"], d["v_target"], d["x_refs"], d["v_refs"], flow)
-        g, = torch.autograd.grad(loss, flow)
-        return loss, g
+        res = [tp.corr4d(d["feats_t"], d["v_t16"], d["feats_r"], d["v_r16"]),
+               tp.corr4d(d["feats_t"], None, d["feats_r"], None)]
+        for tag in ("", "_s"):
+            flow = d["flow" + tag].detach().requires_grad_(True)
+            loss = tp.alignment_recons(d["x_target" + tag], d["v_target" + tag], d["x_refs" + tag],
+                                       d["v_refs" + tag], flow)
+            res.append(torch.autograd.grad(loss, flow)[0])
+        return res
 
     def calls(self):
-        px = self.h * self.w
         n = self.b * self.f
-        # loss-only fused forward: 12+8 per frame + 16/F target; backward: + 8 written
-        return [("mt_warp_l1_fwd", 1, n * 20 * px + self.b * 16 * px, "hbm"),
-                ("mt_warp_l1_bwd", 1, n * 28 * px + self.b * 16 * px, "hbm")]
+        corr = n * (524288 + 262144) + self.b * 524288 + (n + self.b) * 1024
+        out = [("mt_corr4d_fwd", 3, corr, "hbm"), ("mt_corr4d_fwd", 3, corr - (n + self.b) * 1024, "hbm")]
+        for px in (self.h * self.w, (self.h // 4) * (self.w // 4)):
+            # loss-only fused forward: 12+8 per frame + 16/F target; backward: + 8 written
+            out += [("mt_warp_l1_fwd", 1, n * 20 * px + self.b * 16 * px, "hbm"),
+                    ("mt_warp_l1_bwd", 1, n * 28 * px + self.b * 16 * px, "hbm")]
+        return out
 
     def sub(self, b):
         return Cfg3(b, self.f, self.h, self.w)
@@ -428,11 +443,20 @@ def run_gpu(args):
     host_sets = [wl.host_inputs(1000 * rank + 17 * i) for i in range(nsets)]
     dsets = [{k: torch.from_numpy(v).to(dev) for k, v in hs.items()} for hs in host_sets]
     step_bytes = sum(c[2] for c in calls)
-    plans, outs = [], []
+    plans, outs, graphs = [], [], []
     for d in dsets:
         with ops.record() as plan:
             outs.append(wl.gpu_step(mtb, d))
         plans.append(plan)
+    torch.cuda.synchronize()
+    if args.graph:
+        # the same step captured as a CUDA graph: one launch per step instead of one foreign
+        # call per kernel (small configs are host-issue-bound otherwise)
+        for d in dsets:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs.append(wl.gpu_step(mtb, d))
+            graphs.append(g)
     names = plans[0].names()
     # group the recorded launches by C-ABI call
     assert names == [c[0] for c in calls], (names, calls)
@@ -447,6 +471,8 @@ def run_gpu(args):
 
     for i in range(max(args.warmup, 3)):
         plans[i % nsets]()
+        if graphs:
+            graphs[i % nsets].replay()
     barrier()
 
     K = args.steps
@@ -465,6 +491,8 @@ def run_gpu(args):
                 plan.run_entry(j)
                 evs[j + 1].record()
             ev[i] = evs
+        elif graphs:
+            graphs[i % nsets].replay()
         else:
             plan()
     e1.record()
@@ -483,7 +511,8 @@ def run_gpu(args):
     for j, (cname, nl, nbytes, bound) in enumerate(calls):
         ts = [evs[j].elapsed_time(evs[j + 1]) for evs in ev.values()]
         avg = sum(ts) / len(ts)
-        per_call.append({"call": cname, "launches": nl, "avg_us": 1e3 * avg,
+        per_call.append({"call": cname if [c[0] for c in calls].count(cname) == 1 else "%s#%d" % (cname, j),
+                         "launches": nl, "avg_us": 1e3 * avg,
                          "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (avg * 1e-3) / 1e9,
                          "frac_hbm": nbytes / (avg * 1e-3) / 1e9 / hbm_peak})
     dom = max(per_call, key=lambda c: c["avg_us"])
@@ -509,7 +538,9 @@ def run_gpu(args):
                    "l2": "inputs rotate over %d buffer sets; %.0f MB algorithmic traffic per step, "
                          ">= %.0f MB between reuses of a set (L2 = 126 MB)"
                          % (nsets, step_bytes / 1e6, (nsets - 1) * step_bytes / 1e6),
-                   "sharding": "by sample, %d ranks, no data-path collective" % world},
+                   "sharding": "by sample, %d ranks, no data-path collective" % world,
+                   "launch": ("CUDA graph replay per step (per-call events on %d instrumented steps)"
+                              % len(ev)) if graphs else "one C-ABI call per kernel group"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K,
         "roofline": roofline, "kernels": per_call,
     }
@@ -599,6 +630,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="issue every step as individual C-ABI calls instead of a CUDA graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

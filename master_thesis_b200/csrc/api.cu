@@ -28,6 +28,8 @@ int launch_status(const char *what) {
                : MT_ERR_CUDA;
 }
 
+int tuning(const char *name, int dflt);
+
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -39,6 +41,8 @@ int sm_count() {
     }
     return cached[dev];
 }
+
+bool pdl_enabled() { return tuning("MT_PDL", 1) != 0; }
 
 int tuning(const char *name, int dflt) {
     struct Entry { const char *name; int value; };

@@ -32,6 +32,7 @@ struct PackArgs {
 
 template <int VEC>
 __global__ void __launch_bounds__(256) chn_pack_kernel(const PackArgs a) {
+    pdl_sync();
     const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (p0 >= a.P) return;
     const int n = blockIdx.y, b = n / a.F, f = n - b * a.F;
@@ -75,6 +76,7 @@ struct CompArgs {
 
 template <int VEC>
 __global__ void __launch_bounds__(256) chn_composite_fwd_kernel(const CompArgs a) {
+    pdl_sync();
     const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (p0 >= a.P) return;
     const int n = blockIdx.y, b = n / a.F;
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(256) chn_composite_fwd_kernel(const CompArgs a
 
 template <int VEC>
 __global__ void __launch_bounds__(256) chn_composite_bwd_kernel(const CompArgs a) {
+    pdl_sync();
     const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (p0 >= a.P) return;
     const int n = blockIdx.y, b = n / a.F, f = n - b * a.F;
@@ -135,6 +138,7 @@ struct HoleArgs {
 
 template <int VEC>
 __global__ void __launch_bounds__(256) hole_update_kernel(const HoleArgs a) {
+    pdl_sync();
     __shared__ float red[32];
     float acc[1] = {0.0f};
     for (int64_t ch = blockIdx.x; ch < a.total_chunks; ch += gridDim.x) {
@@ -179,6 +183,7 @@ struct TrivArgs {
 
 template <int VEC>
 __global__ void __launch_bounds__(256) trivial_copy_kernel(const TrivArgs a) {
+    pdl_sync();
     const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (p0 >= a.P) return;
     const int n = blockIdx.y, b = n / a.F, f = n - b * a.F;
@@ -210,6 +215,7 @@ struct L1Args {
 
 template <int VEC>
 __global__ void __launch_bounds__(256) masked_l1_fwd_kernel(const L1Args a) {
+    pdl_sync();
     __shared__ float red[3 * 32];
     float acc[3] = {0.0f, 0.0f, 0.0f};  // sum |.|, sum(mask), selected element count / P-chunks
     for (int64_t ch = blockIdx.x; ch < a.total_chunks; ch += gridDim.x) {
@@ -262,6 +268,7 @@ __global__ void __launch_bounds__(256) masked_l1_fwd_kernel(const L1Args a) {
 
 template <int VEC>
 __global__ void __launch_bounds__(256) masked_l1_bwd_kernel(const L1Args a) {
+    pdl_sync();
     const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (p0 >= a.P) return;
     const int bf = blockIdx.y, b = bf / a.F, f = bf - b * a.F;
@@ -321,8 +328,8 @@ extern "C" int mt_chn_pack(const float *x_t, int64_t xt_sb, int64_t xt_sc, const
               mult4(vm_sb) && mult4(vm_sf);
     const int vec = v4 ? 4 : 1;
     dim3 grid((unsigned)((P + 256 * vec - 1) / (256 * vec)), B * F);
-    if (v4) chn_pack_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-    else chn_pack_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    if (v4) launch(chn_pack_kernel<4>, grid, 256, 0, (cudaStream_t)stream, a);
+    else launch(chn_pack_kernel<1>, grid, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_chn_pack");
 }
 
@@ -338,8 +345,8 @@ extern "C" int mt_chn_composite_fwd(const float *nn_out, const float *x_t, int64
               aligned16(y_comp) && mult4(xt_sb) && mult4(xt_sc) && mult4(vt_sb);
     const int vec = v4 ? 4 : 1;
     dim3 grid((unsigned)((P + 256 * vec - 1) / (256 * vec)), B * F);
-    if (v4) chn_composite_fwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-    else chn_composite_fwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    if (v4) launch(chn_composite_fwd_kernel<4>, grid, 256, 0, (cudaStream_t)stream, a);
+    else launch(chn_composite_fwd_kernel<1>, grid, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_chn_composite_fwd");
 }
 
@@ -358,8 +365,8 @@ extern "C" int mt_chn_composite_bwd(const float *nn_out, const float *v_t, int64
               mult4(gc_sb) && mult4(gc_sc) && mult4(gc_sf);
     const int vec = v4 ? 4 : 1;
     dim3 grid((unsigned)((P + 256 * vec - 1) / (256 * vec)), B * F);
-    if (v4) chn_composite_bwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-    else chn_composite_bwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    if (v4) launch(chn_composite_bwd_kernel<4>, grid, 256, 0, (cudaStream_t)stream, a);
+    else launch(chn_composite_bwd_kernel<1>, grid, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_chn_composite_bwd");
 }
 
@@ -377,8 +384,8 @@ extern "C" int mt_hole_update(const float *m_t, int64_t mt_sb, const float *v_ma
     a.chunks = (int)((P + 256 * vec - 1) / (256 * vec));
     a.total_chunks = (int64_t)B * a.chunks;
     const int nblk = reduce_blocks(a.total_chunks);
-    if (v4) hole_update_kernel<4><<<nblk, 256, 0, (cudaStream_t)stream>>>(a);
-    else hole_update_kernel<1><<<nblk, 256, 0, (cudaStream_t)stream>>>(a);
+    if (v4) launch(hole_update_kernel<4>, nblk, 256, 0, (cudaStream_t)stream, a);
+    else launch(hole_update_kernel<1>, nblk, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_hole_update");
 }
 
@@ -394,8 +401,8 @@ extern "C" int mt_trivial_copy(const float *x_t, int64_t xt_sb, int64_t xt_sc, c
               mult4(vm_sb) && mult4(vm_sf);
     const int vec = v4 ? 4 : 1;
     dim3 grid((unsigned)((P + 256 * vec - 1) / (256 * vec)), B * F);
-    if (v4) trivial_copy_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-    else trivial_copy_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    if (v4) launch(trivial_copy_kernel<4>, grid, 256, 0, (cudaStream_t)stream, a);
+    else launch(trivial_copy_kernel<1>, grid, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_trivial_copy");
 }
 
@@ -439,8 +446,8 @@ extern "C" int mt_masked_l1_fwd(const float *y_hat, int64_t a_sb, int64_t a_sc, 
     a.chunks = (int)((P + 256 * vec - 1) / (256 * vec));
     a.total_chunks = (int64_t)B * F * a.chunks;
     const int nblk = reduce_blocks(a.total_chunks);
-    if (v4) masked_l1_fwd_kernel<4><<<nblk, 256, 0, (cudaStream_t)stream>>>(a);
-    else masked_l1_fwd_kernel<1><<<nblk, 256, 0, (cudaStream_t)stream>>>(a);
+    if (v4) launch(masked_l1_fwd_kernel<4>, nblk, 256, 0, (cudaStream_t)stream, a);
+    else launch(masked_l1_fwd_kernel<1>, nblk, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_masked_l1_fwd");
 }
 
@@ -460,7 +467,7 @@ extern "C" int mt_masked_l1_bwd(const float *y_hat, int64_t a_sb, int64_t a_sc, 
     const bool v4 = l1_vec4(a) && aligned16(grad_y_hat) && aligned16(grad_y);
     const int vec = v4 ? 4 : 1;
     dim3 grid((unsigned)((P + 256 * vec - 1) / (256 * vec)), B * F);
-    if (v4) masked_l1_bwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-    else masked_l1_bwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    if (v4) launch(masked_l1_bwd_kernel<4>, grid, 256, 0, (cudaStream_t)stream, a);
+    else launch(masked_l1_bwd_kernel<1>, grid, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_masked_l1_bwd");
 }

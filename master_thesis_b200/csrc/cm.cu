@@ -52,6 +52,7 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
 }
 
 __global__ void __launch_bounds__(256) cm_masks_kernel(const CmArgs a) {
+    pdl_sync();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y, b = blockIdx.z;  // j = 0: target, j >= 1: reference j-1
     if (p >= a.P) return;
@@ -104,6 +105,7 @@ __device__ __forceinline__ void fold_gs(const CmArgs &a, int b, float *gs_smem) 
 // pass 1: grid (chunks, C / SC, B); thread = 4 pixels x SC channels
 template <int R, int SC>
 __global__ void __launch_bounds__(256) cm_sim_kernel(const CmArgs a) {
+    pdl_sync();
     __shared__ float red[2 * R * 32];
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int slab = blockIdx.y, b = blockIdx.z;
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(256) cm_sim_kernel(const CmArgs a) {
 // grid (ceil(P / 1024), B), 256 threads, one 4-pixel group per thread.
 template <int R>
 __global__ void __launch_bounds__(256) cm_weights_kernel(const CmArgs a) {
+    pdl_sync();
     __shared__ float gs_smem[R];
     const int b = blockIdx.y;
     fold_gs<R>(a, b, gs_smem);
@@ -225,6 +228,7 @@ __global__ void __launch_bounds__(256) cm_weights_kernel(const CmArgs a) {
 // pass 2: grid (chunks, ceil(C / CC), B); thread = 4 pixels x CC channels.
 template <int R, int CC>
 __global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
+    pdl_sync();
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (p0 >= a.P) return;
     const int slab = blockIdx.y, b = blockIdx.z;
@@ -264,19 +268,19 @@ __global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
 template <int R>
 int launch_cm(const CmArgs &a, cudaStream_t st) {
     dim3 g0((a.P + 255) / 256, a.f, a.B);
-    cm_masks_kernel<<<g0, 256, 0, st>>>(a);
+    launch(cm_masks_kernel, g0, 256, 0, st, a);
     dim3 g1(a.chunks, (a.C + a.sim_ch - 1) / a.sim_ch, a.B);
-    if (a.sim_ch == 2) cm_sim_kernel<R, 2><<<g1, 256, 0, st>>>(a);
-    else cm_sim_kernel<R, 4><<<g1, 256, 0, st>>>(a);
+    if (a.sim_ch == 2) launch(cm_sim_kernel<R, 2>, g1, 256, 0, st, a);
+    else launch(cm_sim_kernel<R, 4>, g1, 256, 0, st, a);
     dim3 gw(a.chunks, a.B);
-    cm_weights_kernel<R><<<gw, 256, 0, st>>>(a);
+    launch(cm_weights_kernel<R>, gw, 256, 0, st, a);
     const int cc = tuning("MT_CM_COPY_CH", kCopyChannels);
     if (cc == 2) {
         dim3 g2(a.chunks, (a.C + 1) / 2, a.B);
-        cm_copy_kernel<R, 2><<<g2, 256, 0, st>>>(a);
+        launch(cm_copy_kernel<R, 2>, g2, 256, 0, st, a);
     } else {
         dim3 g2(a.chunks, (a.C + 3) / 4, a.B);
-        cm_copy_kernel<R, 4><<<g2, 256, 0, st>>>(a);
+        launch(cm_copy_kernel<R, 4>, g2, 256, 0, st, a);
     }
     return launch_status("mt_cm_match_fwd");
 }

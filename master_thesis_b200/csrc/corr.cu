@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) corr_normalize_kernel(const float *__rest
                                                              const float *__restrict__ vis,
                                                              float *__restrict__ dst, int C, int F,
                                                              int P) {
+    pdl_sync();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     const int64_t n = blockIdx.y;
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(256) corr_gemm_simt_kernel(const float *__rest
                                                              const float *__restrict__ bn,
                                                              float *__restrict__ out, int C, int P,
                                                              int F) {
+    pdl_sync();
     __shared__ float As[16][64 + 4];
     __shared__ float Bs[16][64 + 4];
     const int64_t n = blockIdx.z;
@@ -131,9 +133,9 @@ extern "C" int mt_corr4d_fwd(const float *feats_t, const float *v_t, const float
     float *an = reinterpret_cast<float *>(workspace);
     float *bn = an + (int64_t)B * C * P;
     dim3 gt((P + 255) / 256, B), gr((P + 255) / 256, B * F);
-    corr_normalize_kernel<<<gt, 256, 0, st>>>(feats_t, v_t, an, C, 1, P);
-    corr_normalize_kernel<<<gr, 256, 0, st>>>(feats_r, v_r, bn, C, F, P);
+    launch(corr_normalize_kernel, gt, 256, 0, st, feats_t, v_t, an, C, 1, P);
+    launch(corr_normalize_kernel, gr, 256, 0, st, feats_r, v_r, bn, C, F, P);
     dim3 gg((P + 63) / 64, (P + 63) / 64, B * F);
-    corr_gemm_simt_kernel<<<gg, 256, 0, st>>>(an, bn, out, C, P, F);
+    launch(corr_gemm_simt_kernel, gg, 256, 0, st, an, bn, out, C, P, F);
     return launch_status("mt_corr4d_fwd");
 }

@@ -19,7 +19,9 @@
 // exactly in that canonical layout:
 //   4 channel rows x 128 B = one 512 B swizzle atom; SBO = 512 B between 4-channel groups;
 //   LBO = BK * 128 B between 32-pixel groups; one MMA (K = 8) spans two atoms.
-// One CTA = one 128 x 128 output tile of one (b, f) frame, K = C in BK = 32 slices, 4 stages.
+// One CTA = one 128 x 128 output tile of one (b, f) frame, K = C in BK = 32 slices, 3 stages
+// (100 KB of shared memory, so two CTAs share an SM and one's epilogue overlaps the other's
+// main loop; with 4 stages and one CTA per SM the tensor pipe was 21 % active, profiles/).
 // Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue (one TMEM lane
 // quarter each): tcgen05.ld 32 lanes x 32 columns -> scale -> 128 B per-row stores.
 #include <cuda.h>
@@ -29,7 +31,7 @@
 namespace mt {
 namespace {
 
-constexpr int kTileM = 128, kTileN = 128, kBK = 32, kStages = 4;
+constexpr int kTileM = 128, kTileN = 128, kBK = 32, kStages = 3;  // 3 x 32 KB: two CTAs per SM
 constexpr int kUmmaK = 8;  // tf32: 32 B of K per instruction
 constexpr int kStageBytesA = kTileM * kBK * 4, kStageBytesB = kTileN * kBK * 4;
 constexpr int kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + 1024 /*align*/ + 1024 /*barriers, scales*/;
@@ -116,7 +118,7 @@ struct CorrTcArgs {
     int C, F, P;
 };
 
-__global__ void __launch_bounds__(kThreadsTc, 1)
+__global__ void __launch_bounds__(kThreadsTc, 2)
 corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const CorrTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -148,6 +150,9 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                      ::"r"(smem_u32(tmem_slot)), "n"(kTileN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // everything above is on-chip setup and overlaps the tail of the previous kernel (PDL);
+    // from here on the scales written by corr_scales_kernel are read
+    pdl_sync();
     if (warp >= 2) {  // column scales of this tile
         const int t = threadIdx.x - 64;
         if (t < kTileN) s_sb[t] = __ldg(a.sb + ((int64_t)frame * a.P + n_tile * kTileN + t));
@@ -229,6 +234,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 __global__ void __launch_bounds__(256) corr_scales_kernel(const float *__restrict__ src,
                                                           const float *__restrict__ vis,
                                                           float *__restrict__ scale, int C, int F, int P) {
+    pdl_sync();
     __shared__ float part[8][33];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int p = blockIdx.x * 32 + lane;
@@ -238,7 +244,15 @@ __global__ void __launch_bounds__(256) corr_scales_kernel(const float *__restric
     float ss = 0.0f;
     if (p < P) {
         const float *s = src + b * C * sc + f * P + p;
-        for (int k = grp; k < C; k += 8) {
+        int k = grp;
+        for (; k + 56 < C; k += 64) {  // 8 independent loads in flight per thread
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(s + (int64_t)(k + 8 * u) * sc);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ss = __fmaf_rn(v[u], v[u], ss);
+        }
+        for (; k < C; k += 8) {
             const float v = __ldg(s + k * sc);
             ss = __fmaf_rn(v, v, ss);
         }
@@ -299,8 +313,8 @@ int corr4d_tc_launch(const float *ft, const float *vt, const float *fr, const fl
     float *sa = reinterpret_cast<float *>(ws);
     float *sb = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + align256((int64_t)B * P * 4));
     dim3 gs_t((P + 31) / 32, B), gs_r((P + 31) / 32, B * F);
-    corr_scales_kernel<<<gs_t, 256, 0, st>>>(ft, vt, sa, C, 1, P);
-    corr_scales_kernel<<<gs_r, 256, 0, st>>>(fr, vr, sb, C, F, P);
+    launch(corr_scales_kernel, gs_t, 256, 0, st, ft, vt, sa, C, 1, P);
+    launch(corr_scales_kernel, gs_r, 256, 0, st, fr, vr, sb, C, F, P);
 
     CUtensorMap map_a, map_b;
     {
@@ -340,7 +354,7 @@ int corr4d_tc_launch(const float *ft, const float *vt, const float *fr, const fl
     }
     CorrTcArgs a{sa, sb, out, C, F, P};
     dim3 grid(P / kTileM, P / kTileN, B * F);
-    corr_tc_kernel<<<grid, kThreadsTc, kSmemBytes, st>>>(map_a, map_b, a);
+    launch(corr_tc_kernel, grid, kThreadsTc, kSmemBytes, st, map_a, map_b, a);
     return launch_status("mt_corr4d_fwd");
 }
 

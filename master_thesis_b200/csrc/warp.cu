@@ -109,50 +109,8 @@ __device__ __forceinline__ float base_coord(int idx, int size, float step, bool 
     return v;
 }
 
-constexpr int kThreads = 256;  // block size of the flat (reduction / backward) kernels
-constexpr int kUnroll = 4;     // pixels per thread in those kernels, kThreads apart
 constexpr int kCols = 128;     // forward kernel: threads per CTA = columns per CTA
 constexpr int kRows = 2;       // forward kernel: rows per thread (swept on B200: 2 beats 4, profiles/)
-
-struct WarpArgs {
-    const float *x; int64_t x_sb, x_sc, x_sf;
-    const float *vis; int64_t vis_sb, vis_sf;
-    const float *grid;
-    const float *m_target; int64_t mt_sb;
-    float *x_al; int64_t xa_sb, xa_sc, xa_sf;
-    float *v_al; float *v_map;
-    int F; int P;
-    Sampler sp;
-    bool affine, from_mask;
-};
-
-// grid coordinate of pixel p of frame n; NaN for p >= P (=> every corner out of
-// bounds, no gather is issued for the slot)
-__device__ __forceinline__ void load_coord(const float *__restrict__ grid, bool affine, const Sampler &sp,
-                                           int64_t n, int p, int P, float &gx, float &gy) {
-    if (p >= P) {
-        gx = gy = __int_as_float(0x7fc00000);
-        return;
-    }
-    if (!affine) {
-        const float2 t = __ldcs(reinterpret_cast<const float2 *>(grid) + n * P + p);
-        gx = t.x;
-        gy = t.y;
-    } else {
-        const float *th = grid + n * 6;
-        const int y = p / sp.W, xx = p - y * sp.W;
-        const float bx = base_coord(xx, sp.W, sp.stepx, sp.ac), by = base_coord(y, sp.H, sp.stepy, sp.ac);
-        // base_grid (x, y, 1) @ theta^T: fma(by, t1, bx*t0) + t2  (pinned order)
-        gx = __fadd_rn(__fmaf_rn(by, __ldg(th + 1), __fmul_rn(bx, __ldg(th))), __ldg(th + 2));
-        gy = __fadd_rn(__fmaf_rn(by, __ldg(th + 4), __fmul_rn(bx, __ldg(th + 3))), __ldg(th + 5));
-    }
-}
-
-// Lean bilinear state for the forward kernel: weights + the offset of the NW corner.
-struct Tap {
-    float nw, ne, sw, se;
-    int o;  // yn * W + xw (meaningful when the pixel is interior)
-};
 
 // Forward-kernel arguments: every offset is a 32-bit ELEMENT offset (the launcher
 // checks the ranges), because 64-bit stride arithmetic dominated the per-thread
@@ -180,6 +138,7 @@ struct WarpFwdArgs {
 // are all requested (no NULL checks).
 template <int C, int U, int VIS, bool AFFINE, bool FULL>
 __global__ void __launch_bounds__(kCols) warp_fwd_kernel(const WarpFwdArgs a) {
+    pdl_sync();
     __shared__ float s_by[U];
     const int W = a.sp.W, H = a.sp.H;
     // lanes past the last column stay alive (the warp vote below needs every lane)
@@ -325,66 +284,128 @@ __global__ void __launch_bounds__(kCols) warp_fwd_kernel(const WarpFwdArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Shared pieces of the dense-flow kernels below (backward w.r.t. the grid, fused loss
+// forward / backward).  Same shape as the forward kernel: thread = column x U rows,
+// 32-bit offsets, warp-uniform interior fast path.
+// ---------------------------------------------------------------------------------
+template <int U>
+struct Taps {
+    float gx[U], gy[U], ix[U], iy[U], xw[U], yn[U], w[U], e[U], n[U], s[U];
+    bool interior;
+};
+
+// flow of pixel (y0 + k, x) of frame n for k < U; rows past H get a centred dummy
+template <int U>
+__device__ __forceinline__ void dense_taps(const float *__restrict__ flow, int np0, int y0, const Sampler &sp,
+                                           Taps<U> &t) {
+    const float wm2 = sp.wmax - 1.0f, hm2 = sp.hmax - 1.0f;
+    t.interior = true;
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+        if (y0 + k < sp.H) {
+            const float2 g = __ldcs(reinterpret_cast<const float2 *>(flow) + (np0 + k * sp.W));
+            t.gx[k] = g.x; t.gy[k] = g.y;
+        } else {
+            t.gx[k] = t.gy[k] = 0.0f;
+        }
+        t.ix[k] = unnormalize(t.gx[k], sp.sfx, sp.ac);
+        t.iy[k] = unnormalize(t.gy[k], sp.sfy, sp.ac);
+        t.xw[k] = floorf(t.ix[k]);
+        t.yn[k] = floorf(t.iy[k]);
+        t.w[k] = __fsub_rn(t.ix[k], t.xw[k]); t.e[k] = __fsub_rn(1.0f, t.w[k]);
+        t.n[k] = __fsub_rn(t.iy[k], t.yn[k]); t.s[k] = __fsub_rn(1.0f, t.n[k]);
+        t.interior = t.interior && (t.xw[k] >= 0.0f) && (t.xw[k] <= wm2) && (t.yn[k] >= 0.0f) && (t.yn[k] <= hm2);
+    }
+}
+
+// the four taps of C planes for every row slot: fast path when the whole warp is interior
+template <int C, int U>
+__device__ __forceinline__ void gather_taps(const float *__restrict__ x, int xo, int x_sc, const Sampler &sp,
+                                            const Taps<U> &t, Corners (&q)[C][U]) {
+    if (__all_sync(0xffffffffu, t.interior)) {
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int o = (int)t.yn[k] * sp.W + (int)t.xw[k];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float *r0 = x + (xo + c * x_sc + o);
+                const float *r1 = x + (xo + c * x_sc + o + sp.W);
+                q[c][k].nw = __ldg(r0); q[c][k].ne = __ldg(r0 + 1);
+                q[c][k].sw = __ldg(r1); q[c][k].se = __ldg(r1 + 1);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const Bil bl = bil_params(t.ix[k], t.iy[k], sp);
+#pragma unroll
+            for (int c = 0; c < C; ++c) q[c][k] = gather(x + (xo + c * x_sc), bl, sp.W);
+        }
+    }
+}
+
+template <int U>
+__device__ __forceinline__ float interp_k(const Corners &q, const Taps<U> &t, int k) {
+    return __fmaf_rn(q.se, __fmul_rn(t.n[k], t.w[k]), __fmaf_rn(q.sw, __fmul_rn(t.n[k], t.e[k]),
+           __fmaf_rn(q.ne, __fmul_rn(t.s[k], t.w[k]), __fmul_rn(q.nw, __fmul_rn(t.s[k], t.e[k])))));
+}
+
+constexpr int kRowsB = 2;  // rows per thread in the dense-flow kernels
+
 // ---- backward w.r.t. the dense grid (generic upstream gradient) -------------
 struct WarpBwdArgs {
-    const float *x; int64_t x_sb, x_sc, x_sf;
-    const float *grid;
-    const float *gout; int64_t g_sb, g_sc, g_sf;
+    const float *x, *grid, *gout;
     float *ggrid;
-    int F; int P;
+    int x_sb, x_sc, x_sf, g_sb, g_sc, g_sf;
+    int F, P;
+    unsigned f_magic;
     Sampler sp;
 };
 
 template <int C, int U>
-__global__ void __launch_bounds__(kThreads) warp_bwd_grid_kernel(const WarpBwdArgs a) {
-    const int p0 = blockIdx.x * (kThreads * U) + threadIdx.x;
-    const int64_t n = blockIdx.y;
-    const int b = (int)(n / a.F), f = (int)(n - (int64_t)b * a.F);
-    const float *xb = a.x + b * a.x_sb + f * a.x_sf;
-    const float *gb = a.gout + b * a.g_sb + f * a.g_sf;
-    Bil bl[U];
-#pragma unroll
-    for (int k = 0; k < U; ++k) {
-        float gx, gy;
-        load_coord(a.grid, false, a.sp, n, p0 + k * kThreads, a.P, gx, gy);
-        bl[k] = bil_params(unnormalize(gx, a.sp.sfx, a.sp.ac), unnormalize(gy, a.sp.sfy, a.sp.ac), a.sp);
-    }
-    Corners cx[C][U];
+__global__ void __launch_bounds__(kCols) warp_bwd_grid_kernel(const WarpBwdArgs a) {
+    pdl_sync();
+    const int W = a.sp.W, H = a.sp.H;
+    const bool live = (int)(blockIdx.x * kCols + threadIdx.x) < W;
+    const int x = min((int)(blockIdx.x * kCols + threadIdx.x), W - 1);
+    const int y0 = blockIdx.y * U;
+    const unsigned n = blockIdx.z;
+    const int b = a.f_magic ? (int)__umulhi(n, a.f_magic) : (int)n, f = (int)n - b * a.F;
+    const int p0 = y0 * W + x, np0 = (int)n * a.P + p0;
+    const int go0 = b * a.g_sb + f * a.g_sf + p0;
     float go[C][U];
 #pragma unroll
     for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            cx[c][k] = gather(xb + c * a.x_sc, bl[k], a.sp.W);
-            go[c][k] = (p0 + k * kThreads < a.P) ? __ldcs(gb + c * a.g_sc + p0 + k * kThreads) : 0.0f;
-        }
+        for (int k = 0; k < U; ++k) go[c][k] = (y0 + k < H) ? __ldcs(a.gout + (go0 + c * a.g_sc + k * W)) : 0.0f;
+    Taps<U> t;
+    dense_taps<U>(a.grid, np0, y0, a.sp, t);
+    Corners q[C][U];
+    gather_taps<C, U>(a.x, b * a.x_sb + f * a.x_sf, a.x_sc, a.sp, t, q);
+    if (!live) return;
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-        const int p = p0 + k * kThreads;
-        if (p >= a.P) continue;
+        if (y0 + k >= H) break;
         float ax = 0.0f, ay = 0.0f;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const Corners &q = cx[c][k];
-            ax += ((q.ne - q.nw) * bl[k].s + (q.se - q.sw) * bl[k].n) * go[c][k];
-            ay += ((q.sw - q.nw) * bl[k].e + (q.se - q.ne) * bl[k].w) * go[c][k];
+            ax += ((q[c][k].ne - q[c][k].nw) * t.s[k] + (q[c][k].se - q[c][k].sw) * t.n[k]) * go[c][k];
+            ay += ((q[c][k].sw - q[c][k].nw) * t.e[k] + (q[c][k].se - q[c][k].ne) * t.w[k]) * go[c][k];
         }
-        __stcs(reinterpret_cast<float2 *>(a.ggrid) + n * a.P + p, make_float2(ax * a.sp.sfx, ay * a.sp.sfy));
+        __stcs(reinterpret_cast<float2 *>(a.ggrid) + (np0 + k * W), make_float2(ax * a.sp.sfx, ay * a.sp.sfy));
     }
 }
 
 // ---- fused warp + mask_out + masked L1 ('sum') ------------------------------
 struct WarpL1Args {
-    const float *x; int64_t x_sb, x_sc, x_sf;
-    const float *vis; int64_t vis_sb, vis_sf;
-    const float *flow;
-    const float *xt; int64_t xt_sb, xt_sc;
-    const float *vt; int64_t vt_sb;
-    float *x_al; float *v_al;  // frame-major, may be NULL
+    const float *x, *vis, *flow, *xt, *vt;
+    float *x_al, *v_al;  // frame-major, may be NULL
     float *out3; void *ws;
-    const float *out3_in; const float *grad_out; float *gflow;  // backward only
-    int F; int P; int tiles;  // tiles = ceil(P / (kThreads*U))
-    int64_t total_tiles;      // B*F*tiles
+    const float *out3_in, *grad_out; float *gflow;  // backward only
+    int x_sb, x_sc, x_sf, vis_sb, vis_sf, xt_sb, xt_sc, vt_sb;
+    int F, P, row_blocks;
+    unsigned f_magic;
     float weight;
     Sampler sp;
     bool from_mask;
@@ -395,52 +416,48 @@ __device__ __forceinline__ float mask_out_of(float gx, float gy) {
     return (gx < -1.0f || gx > 1.0f || gy < -1.0f || gy > 1.0f) ? 1.0f : 0.0f;
 }
 
+// grid (col blocks, <= row blocks, frames); a CTA strides over row blocks so that the
+// number of partials stays within the reduction workspace
 template <int U>
-__global__ void __launch_bounds__(kThreads) warp_l1_fwd_kernel(const WarpL1Args a) {
+__global__ void __launch_bounds__(kCols) warp_l1_fwd_kernel(const WarpL1Args a) {
+    pdl_sync();
     __shared__ float red[2 * 32];
     float acc[2] = {0.0f, 0.0f};  // sum |x_t*M - x_al*M| over 3 channels, sum M
-    for (int64_t t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-        const int64_t n = t / a.tiles;
-        const int p0 = (int)(t - n * a.tiles) * (kThreads * U) + threadIdx.x;
-        const int b = (int)(n / a.F), f = (int)(n - (int64_t)b * a.F);
-        const float *xb = a.x + b * a.x_sb + f * a.x_sf;
-        Bil bl[U];
-        float ix[U], iy[U], M[U];
+    const int W = a.sp.W, H = a.sp.H;
+    const bool live = (int)(blockIdx.x * kCols + threadIdx.x) < W;
+    const int x = min((int)(blockIdx.x * kCols + threadIdx.x), W - 1);
+    const unsigned n = blockIdx.z;
+    const int b = a.f_magic ? (int)__umulhi(n, a.f_magic) : (int)n, f = (int)n - b * a.F;
+    const int xo = b * a.x_sb + f * a.x_sf;
+    for (int rb = blockIdx.y; rb < a.row_blocks; rb += gridDim.y) {
+        const int y0 = rb * U;
+        const int p0 = y0 * W + x, np0 = (int)n * a.P + p0;
+        float xt[3][U], vt[U];
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-            const int p = p0 + k * kThreads;
-            float gx, gy;
-            load_coord(a.flow, false, a.sp, n, p, a.P, gx, gy);
-            const float vt = p < a.P ? __ldg(a.vt + b * a.vt_sb + p) : 0.0f;
-            ix[k] = unnormalize(gx, a.sp.sfx, a.sp.ac);
-            iy[k] = unnormalize(gy, a.sp.sfy, a.sp.ac);
-            bl[k] = bil_params(ix[k], iy[k], a.sp);
-            M[k] = p < a.P ? __fmul_rn(vt, __fsub_rn(1.0f, mask_out_of(gx, gy))) : 0.0f;
-            acc[1] += M[k];
+            const bool in = y0 + k < H;
+            vt[k] = in ? __ldg(a.vt + (b * a.vt_sb + p0 + k * W)) : 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) xt[c][k] = in ? __ldg(a.xt + (b * a.xt_sb + c * a.xt_sc + p0 + k * W)) : 0.0f;
         }
-        Corners cx[3][U];
-        float xt[3][U];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-                cx[c][k] = gather(xb + c * a.x_sc, bl[k], a.sp.W);
-                xt[c][k] = (p0 + k * kThreads < a.P) ? __ldg(a.xt + b * a.xt_sb + c * a.xt_sc + p0 + k * kThreads) : 0.0f;
-            }
+        Taps<U> t;
+        dense_taps<U>(a.flow, np0, y0, a.sp, t);
+        Corners q[3][U];
+        gather_taps<3, U>(a.x, xo, a.x_sc, a.sp, t, q);
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-            const int p = p0 + k * kThreads;
-            if (p >= a.P) continue;
+            if (y0 + k >= H || !live) continue;
+            const float M = __fmul_rn(vt[k], __fsub_rn(1.0f, mask_out_of(t.gx[k], t.gy[k])));
+            acc[1] += M;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float r = interp(cx[c][k], bl[k]);
-                acc[0] += fabsf(__fsub_rn(__fmul_rn(xt[c][k], M[k]), __fmul_rn(r, M[k])));
-                if (a.x_al) st_stream1(a.x_al + (n * 3 + c) * a.P + p, r);
+                const float r = interp_k<U>(q[c][k], t, k);
+                acc[0] += fabsf(__fsub_rn(__fmul_rn(xt[c][k], M), __fmul_rn(r, M)));
+                if (a.x_al) st_stream1(a.x_al + (((int)n * 3 + c) * a.P + p0 + k * W), r);
             }
-            if (a.v_al) {
-                const float *vp = a.vis + b * a.vis_sb + f * a.vis_sf;
-                st_stream1(a.v_al + n * a.P + p, nearest(vp, ix[k], iy[k], a.sp, a.from_mask));
-            }
+            if (a.v_al)
+                st_stream1(a.v_al + (np0 + k * W),
+                           nearest(a.vis + (b * a.vis_sb + f * a.vis_sf), t.ix[k], t.iy[k], a.sp, a.from_mask));
         }
     }
     float *out3 = a.out3;
@@ -456,52 +473,49 @@ __global__ void __launch_bounds__(kThreads) warp_l1_fwd_kernel(const WarpL1Args 
 // d loss / d flow in one pass: recomputes the sampling, never materialises
 // x_aligned or its gradient.
 template <int U>
-__global__ void __launch_bounds__(kThreads) warp_l1_bwd_kernel(const WarpL1Args a) {
-    const int p0 = blockIdx.x * (kThreads * U) + threadIdx.x;
-    const int64_t n = blockIdx.y;
-    const int b = (int)(n / a.F), f = (int)(n - (int64_t)b * a.F);
+__global__ void __launch_bounds__(kCols) warp_l1_bwd_kernel(const WarpL1Args a) {
+    pdl_sync();
+    const int W = a.sp.W, H = a.sp.H;
+    const bool live = (int)(blockIdx.x * kCols + threadIdx.x) < W;
+    const int x = min((int)(blockIdx.x * kCols + threadIdx.x), W - 1);
+    const int y0 = blockIdx.y * U;
+    const unsigned n = blockIdx.z;
+    const int b = a.f_magic ? (int)__umulhi(n, a.f_magic) : (int)n, f = (int)n - b * a.F;
+    const int p0 = y0 * W + x, np0 = (int)n * a.P + p0;
     const float scale = a.weight * __ldg(a.grad_out) / (__ldg(a.out3_in + 2) + 1e-9f);
-    const float *xb = a.x + b * a.x_sb + f * a.x_sf;
-    Bil bl[U];
-    float M[U];
+    float xt[3][U], vt[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-        const int p = p0 + k * kThreads;
-        float gx, gy;
-        load_coord(a.flow, false, a.sp, n, p, a.P, gx, gy);
-        const float vt = p < a.P ? __ldg(a.vt + b * a.vt_sb + p) : 0.0f;
-        bl[k] = bil_params(unnormalize(gx, a.sp.sfx, a.sp.ac), unnormalize(gy, a.sp.sfy, a.sp.ac), a.sp);
-        M[k] = p < a.P ? __fmul_rn(vt, __fsub_rn(1.0f, mask_out_of(gx, gy))) : 0.0f;
+        const bool in = y0 + k < H;
+        vt[k] = in ? __ldg(a.vt + (b * a.vt_sb + p0 + k * W)) : 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xt[c][k] = in ? __ldg(a.xt + (b * a.xt_sb + c * a.xt_sc + p0 + k * W)) : 0.0f;
     }
-    Corners cx[3][U];
-    float xt[3][U];
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            cx[c][k] = gather(xb + c * a.x_sc, bl[k], a.sp.W);
-            xt[c][k] = (p0 + k * kThreads < a.P) ? __ldg(a.xt + b * a.xt_sb + c * a.xt_sc + p0 + k * kThreads) : 0.0f;
-        }
+    Taps<U> t;
+    dense_taps<U>(a.flow, np0, y0, a.sp, t);
+    Corners q[3][U];
+    gather_taps<3, U>(a.x, b * a.x_sb + f * a.x_sf, a.x_sc, a.sp, t, q);
+    if (!live) return;
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-        const int p = p0 + k * kThreads;
-        if (p >= a.P) continue;
+        if (y0 + k >= H) break;
+        const float M = __fmul_rn(vt[k], __fsub_rn(1.0f, mask_out_of(t.gx[k], t.gy[k])));
         float ax = 0.0f, ay = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const Corners &q = cx[c][k];
-            const float d = __fsub_rn(__fmul_rn(xt[c][k], M[k]), __fmul_rn(interp(q, bl[k]), M[k]));
+            const float d = __fsub_rn(__fmul_rn(xt[c][k], M), __fmul_rn(interp_k<U>(q[c][k], t, k), M));
             const float sg = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
-            const float go = -sg * M[k] * scale;  // d loss / d x_aligned
-            ax += ((q.ne - q.nw) * bl[k].s + (q.se - q.sw) * bl[k].n) * go;
-            ay += ((q.sw - q.nw) * bl[k].e + (q.se - q.ne) * bl[k].w) * go;
+            const float go = -sg * M * scale;  // d loss / d x_aligned
+            ax += ((q[c][k].ne - q[c][k].nw) * t.s[k] + (q[c][k].se - q[c][k].sw) * t.n[k]) * go;
+            ay += ((q[c][k].sw - q[c][k].nw) * t.e[k] + (q[c][k].se - q[c][k].ne) * t.w[k]) * go;
         }
-        __stcs(reinterpret_cast<float2 *>(a.gflow) + n * a.P + p, make_float2(ax * a.sp.sfx, ay * a.sp.sfy));
+        __stcs(reinterpret_cast<float2 *>(a.gflow) + (np0 + k * W), make_float2(ax * a.sp.sfx, ay * a.sp.sfy));
     }
 }
 
 __global__ void __launch_bounds__(256) mask_out_kernel(const float *__restrict__ flow, int64_t n,
                                                        float *__restrict__ out) {
+    pdl_sync();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const float2 g = __ldcs(reinterpret_cast<const float2 *>(flow) + i);
@@ -529,6 +543,10 @@ bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0
 }  // namespace mt
 
 using namespace mt;
+
+static unsigned frame_magic(int F) {
+    return F == 1 ? 0u : (unsigned)(((1ull << 32) + (unsigned)F - 1) / (unsigned)F);
+}
 
 extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
                            const float *vis, int64_t vis_sb, int64_t vis_sf, const float *grid,
@@ -558,7 +576,7 @@ extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x
     a.vis_sb = (int)vis_sb; a.vis_sf = (int)vis_sf; a.mt_sb = (int)mt_sb;
     a.xa_sb = (int)xa_sb; a.xa_sc = (int)xa_sc; a.xa_sf = (int)xa_sf;
     a.F = F; a.P = (int)P;
-    a.f_magic = F == 1 ? 0u : (unsigned)(((1ull << 32) + (unsigned)F - 1) / (unsigned)F);
+    a.f_magic = frame_magic(F);
     a.sp = make_sampler(H, W, (flags & MT_ALIGN_CORNERS) != 0);
     a.from_mask = (flags & MT_VIS_FROM_MASK) != 0;
     const bool affine = (flags & MT_GRID_AFFINE) != 0;
@@ -569,8 +587,8 @@ extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x
     const bool full = x_aligned && v_aligned && v_map;
 #define MT_WARP_GO(CC, VV, AA, FF)                                                  \
     do {                                                                            \
-        if (rows == 2) warp_fwd_kernel<CC, 2, VV, AA, FF><<<gridd, block, 0, st>>>(a); \
-        else warp_fwd_kernel<CC, 4, VV, AA, FF><<<gridd, block, 0, st>>>(a);        \
+        if (rows == 2) launch(warp_fwd_kernel<CC, 2, VV, AA, FF>, gridd, block, 0, st, a); \
+        else launch(warp_fwd_kernel<CC, 4, VV, AA, FF>, gridd, block, 0, st, a);        \
     } while (0)
 #define MT_WARP_PICK(CC)                                                            \
     do {                                                                            \
@@ -596,17 +614,24 @@ extern "C" int mt_warp_bwd_grid(const float *x, int64_t x_sb, int64_t x_sc, int6
     MT_REQUIRE(B > 0 && F > 0 && H > 0 && W > 0, "mt_warp_bwd_grid: empty shape");
     MT_REQUIRE(C == 1 || C == 3, "mt_warp_bwd_grid: C must be 1 or 3, got %d", C);
     MT_REQUIRE(!(flags & MT_GRID_AFFINE), "mt_warp_bwd_grid: dense grids only");
-    MT_REQUIRE((int64_t)H * W < (1ll << 30) && (int64_t)B * F <= 65535, "mt_warp_bwd_grid: too large");
+    MT_REQUIRE((int64_t)B * F <= 65535 && (H + kRowsB - 1) / kRowsB <= 65535, "mt_warp_bwd_grid: too large");
     MT_REQUIRE(aligned8(grid) && aligned8(ggrid), "mt_warp_bwd_grid: grids must be 8 B aligned");
+    const int64_t P = (int64_t)H * W, lim = (1ll << 31) - 1;
+    MT_REQUIRE(x_sb >= 0 && x_sc >= 0 && x_sf >= 0 && g_sb >= 0 && g_sc >= 0 && g_sf >= 0,
+               "mt_warp_bwd_grid: negative strides are not supported");
+    MT_REQUIRE((B - 1) * x_sb + (C - 1) * x_sc + (F - 1) * x_sf + P + W + 1 < lim &&
+               (B - 1) * g_sb + (C - 1) * g_sc + (F - 1) * g_sf + P < lim && (int64_t)B * F * P * 2 < lim,
+               "mt_warp_bwd_grid: tensors beyond 2^31 elements are not supported (split the batch)");
     WarpBwdArgs a;
-    a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sf = x_sf; a.grid = grid;
-    a.gout = gout; a.g_sb = g_sb; a.g_sc = g_sc; a.g_sf = g_sf; a.ggrid = ggrid;
-    a.F = F; a.P = H * W;
+    a.x = x; a.grid = grid; a.gout = gout; a.ggrid = ggrid;
+    a.x_sb = (int)x_sb; a.x_sc = (int)x_sc; a.x_sf = (int)x_sf;
+    a.g_sb = (int)g_sb; a.g_sc = (int)g_sc; a.g_sf = (int)g_sf;
+    a.F = F; a.P = (int)P; a.f_magic = frame_magic(F);
     a.sp = make_sampler(H, W, (flags & MT_ALIGN_CORNERS) != 0);
-    dim3 block(kThreads), gridd((a.P + kThreads * kUnroll - 1) / (kThreads * kUnroll), B * F);
+    dim3 block(kCols), gridd((W + kCols - 1) / kCols, (H + kRowsB - 1) / kRowsB, B * F);
     cudaStream_t st = (cudaStream_t)stream;
-    if (C == 3) warp_bwd_grid_kernel<3, kUnroll><<<gridd, block, 0, st>>>(a);
-    else warp_bwd_grid_kernel<1, kUnroll><<<gridd, block, 0, st>>>(a);
+    if (C == 3) launch(warp_bwd_grid_kernel<3, kRowsB>, gridd, block, 0, st, a);
+    else launch(warp_bwd_grid_kernel<1, kRowsB>, gridd, block, 0, st, a);
     return launch_status("mt_warp_bwd_grid");
 }
 
@@ -616,17 +641,23 @@ static int fill_l1_args(WarpL1Args &a, const float *x, int64_t x_sb, int64_t x_s
                         float weight, int flags, const char *who) {
     MT_REQUIRE(x && flow && x_target && v_target, "%s: NULL input", who);
     MT_REQUIRE(B > 0 && F > 0 && H > 0 && W > 0, "%s: empty shape", who);
-    MT_REQUIRE((int64_t)H * W < (1ll << 30) && (int64_t)B * F <= 65535, "%s: too large", who);
+    MT_REQUIRE((int64_t)B * F <= 65535 && (H + kRowsB - 1) / kRowsB <= 65535, "%s: too large", who);
     MT_REQUIRE(aligned8(flow), "%s: flow must be 8 B aligned", who);
-    a.x = x; a.x_sb = x_sb; a.x_sc = x_sc; a.x_sf = x_sf; a.flow = flow;
-    a.xt = x_target; a.xt_sb = xt_sb; a.xt_sc = xt_sc; a.vt = v_target; a.vt_sb = vt_sb;
-    a.F = F; a.P = H * W; a.weight = weight;
+    const int64_t P = (int64_t)H * W, lim = (1ll << 31) - 1;
+    MT_REQUIRE(x_sb >= 0 && x_sc >= 0 && x_sf >= 0 && xt_sb >= 0 && xt_sc >= 0 && vt_sb >= 0,
+               "%s: negative strides are not supported", who);
+    MT_REQUIRE((B - 1) * x_sb + 2 * x_sc + (F - 1) * x_sf + P + W + 1 < lim && (B - 1) * xt_sb + 2 * xt_sc + P < lim &&
+               (B - 1) * vt_sb + P < lim && (int64_t)B * F * P * 3 < lim,
+               "%s: tensors beyond 2^31 elements are not supported (split the batch)", who);
+    a.x = x; a.flow = flow; a.xt = x_target; a.vt = v_target;
+    a.x_sb = (int)x_sb; a.x_sc = (int)x_sc; a.x_sf = (int)x_sf;
+    a.xt_sb = (int)xt_sb; a.xt_sc = (int)xt_sc; a.vt_sb = (int)vt_sb;
+    a.F = F; a.P = (int)P; a.weight = weight; a.f_magic = frame_magic(F);
     a.sp = make_sampler(H, W, (flags & MT_ALIGN_CORNERS) != 0);
     a.from_mask = (flags & MT_VIS_FROM_MASK) != 0;
     a.vis = nullptr; a.vis_sb = a.vis_sf = 0; a.x_al = a.v_al = nullptr; a.out3 = nullptr; a.ws = nullptr;
     a.out3_in = nullptr; a.grad_out = nullptr; a.gflow = nullptr;
-    a.tiles = (a.P + kThreads * kUnroll - 1) / (kThreads * kUnroll);
-    a.total_tiles = (int64_t)B * F * a.tiles;
+    a.row_blocks = (H + kRowsB - 1) / kRowsB;
     return MT_OK;
 }
 
@@ -642,12 +673,22 @@ extern "C" int mt_warp_l1_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_
     if (rc) return rc;
     MT_REQUIRE(out3 && workspace, "mt_warp_l1_fwd: NULL out3 / workspace");
     MT_REQUIRE(!v_aligned || vis, "mt_warp_l1_fwd: v_aligned needs vis");
-    a.vis = vis; a.vis_sb = vis_sb; a.vis_sf = vis_sf; a.x_al = x_aligned; a.v_al = v_aligned;
+    MT_REQUIRE(vis_sb >= 0 && vis_sf >= 0 && (!vis || (B - 1) * vis_sb + (F - 1) * vis_sf + (int64_t)H * W < (1ll << 31) - 1),
+               "mt_warp_l1_fwd: vis beyond 2^31 elements");
+    a.vis = vis; a.vis_sb = (int)vis_sb; a.vis_sf = (int)vis_sf; a.x_al = x_aligned; a.v_al = v_aligned;
     a.out3 = out3; a.ws = workspace;
-    int64_t want = (int64_t)sm_count() * 8;
-    int nblk = (int)(a.total_tiles < want ? a.total_tiles : want);
-    if (nblk > kMaxReduceBlocks) nblk = kMaxReduceBlocks;
-    warp_l1_fwd_kernel<kUnroll><<<nblk, kThreads, 0, (cudaStream_t)stream>>>(a);
+    // keep the number of CTAs (= partials) within the reduction workspace
+    const int colb = (W + kCols - 1) / kCols;
+    int gy = a.row_blocks;
+    MT_REQUIRE((int64_t)colb * B * F <= kMaxReduceBlocks,
+               "mt_warp_l1_fwd: B*F*ceil(W/128) = %lld exceeds %d CTAs (split the batch)",
+               (long long)colb * B * F, kMaxReduceBlocks);
+    // about 16 CTAs per SM in total; each CTA strides over the remaining row blocks
+    int64_t cap = ((int64_t)sm_count() * 16) / ((int64_t)colb * B * F);
+    if (cap < 1) cap = 1;
+    if (gy > cap) gy = (int)cap;
+    dim3 block(kCols), gridd(colb, gy, B * F);
+    launch(warp_l1_fwd_kernel<kRowsB>, gridd, block, 0, (cudaStream_t)stream, a);
     return launch_status("mt_warp_l1_fwd");
 }
 
@@ -663,8 +704,8 @@ extern "C" int mt_warp_l1_bwd(const float *x, int64_t x_sb, int64_t x_sc, int64_
     MT_REQUIRE(out3 && grad_out && gflow, "mt_warp_l1_bwd: NULL out3 / grad_out / gflow");
     MT_REQUIRE(aligned8(gflow), "mt_warp_l1_bwd: gflow must be 8 B aligned");
     a.out3_in = out3; a.grad_out = grad_out; a.gflow = gflow;
-    dim3 block(kThreads), gridd(a.tiles, B * F);
-    warp_l1_bwd_kernel<kUnroll><<<gridd, block, 0, (cudaStream_t)stream>>>(a);
+    dim3 block(kCols), gridd((W + kCols - 1) / kCols, a.row_blocks, B * F);
+    launch(warp_l1_bwd_kernel<kRowsB>, gridd, block, 0, (cudaStream_t)stream, a);
     return launch_status("mt_warp_l1_bwd");
 }
 
@@ -672,6 +713,6 @@ extern "C" int mt_mask_out(const float *flow, int64_t n, float *out, mt_stream_t
     MT_REQUIRE(flow && out && n > 0, "mt_mask_out: bad argument");
     MT_REQUIRE((reinterpret_cast<uintptr_t>(flow) & 7u) == 0, "mt_mask_out: flow must be 8 B aligned");
     int64_t nb = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
-    mask_out_kernel<<<(int)(nb < cap ? nb : cap), 256, 0, (cudaStream_t)stream>>>(flow, n, out);
+    launch(mask_out_kernel, (int)(nb < cap ? nb : cap), 256, 0, (cudaStream_t)stream, flow, n, out);
     return launch_status("mt_mask_out");
 }
