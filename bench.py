@@ -88,7 +88,7 @@ class Cfg2(Workload):
             "m_refs": np.ascontiguousarray(m[:, :, refs]),
             "m_target": np.ascontiguousarray(m[:, :, t]),
             "v_target": np.ascontiguousarray(1 - m[:, :, t]),
-            "theta": synth.thetas(seed + 1, b * f, 0.1),
+            "theta": synth.thetas(seed + 1, b * f, float(os.environ.get("MT_BENCH_THETA_SIGMA", "0.1"))),
             "c_feats": r.standard_normal((b, c, f + 1, h // 4, w // 4)).astype(np.float32),
         }
 
@@ -429,6 +429,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("MT_NCCL_DEBUG", "WARN")  # keep stdout = the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     import master_thesis_b200 as mtb

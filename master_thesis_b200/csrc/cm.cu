@@ -37,7 +37,7 @@ struct CmArgs {
     float *partials;  // workspace: (B, nparts, 2R): [dot_r ..., vsum_r ...]
     float *gs;        // workspace: (B, R)  (exported for tests)
     float *weights;   // workspace: (B, R, P) softmax weights over references
-    int B, C, f, h, w, H, W, P, R, nparts, chunks, sim_ch;
+    int B, C, f, h, w, H, W, P, R, nparts, chunks, sim_ch, b_off;
 };
 
 // F.interpolate(bilinear, align_corners=False) source index (UpSample.h)
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) cm_sim_kernel(const CmArgs a) {
     pdl_sync();
     __shared__ float red[2 * R * 32];
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int slab = blockIdx.y, b = blockIdx.z;
+    const int slab = blockIdx.y, b = blockIdx.z + a.b_off;
     float acc[2 * R];  // [0, R): dot products, [R, 2R): sum of vt'*vr' (slab 0 only)
 #pragma unroll
     for (int r = 0; r < 2 * R; ++r) acc[r] = 0.0f;
@@ -163,7 +163,7 @@ template <int R>
 __global__ void __launch_bounds__(256) cm_weights_kernel(const CmArgs a) {
     pdl_sync();
     __shared__ float gs_smem[R];
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + a.b_off;
     fold_gs<R>(a, b, gs_smem);
     if (blockIdx.x == 0 && threadIdx.x < R) a.gs[(int64_t)b * R + threadIdx.x] = gs_smem[threadIdx.x];
     float gsr[R];
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
     pdl_sync();
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (p0 >= a.P) return;
-    const int slab = blockIdx.y, b = blockIdx.z;
+    const int slab = blockIdx.y, b = blockIdx.z + a.b_off;
     const int c0 = slab * CC;
     float4 ct[CC], cr[CC][R];
 #pragma unroll
@@ -266,21 +266,32 @@ __global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
 }
 
 template <int R>
-int launch_cm(const CmArgs &a, cudaStream_t st) {
+int launch_cm(CmArgs a, cudaStream_t st) {
+    a.b_off = 0;
     dim3 g0((a.P + 255) / 256, a.f, a.B);
     launch(cm_masks_kernel, g0, 256, 0, st, a);
-    dim3 g1(a.chunks, (a.C + a.sim_ch - 1) / a.sim_ch, a.B);
-    if (a.sim_ch == 2) launch(cm_sim_kernel<R, 2>, g1, 256, 0, st, a);
-    else launch(cm_sim_kernel<R, 4>, g1, 256, 0, st, a);
-    dim3 gw(a.chunks, a.B);
-    launch(cm_weights_kernel<R>, gw, 256, 0, st, a);
+    // MT_CM_CHUNK > 0 processes the samples in chunks (sim -> weights -> copy per chunk) so that
+    // pass 2 could re-read c_feats from L2.  Swept on B200 at B=8 (profiles/r1_sweep_cm.sh):
+    // 1/2/4/8 samples per chunk -> 111/72/55/48 us: the extra small launches cost more than the
+    // L2 reuse brings, so the default is the whole batch in one group.
+    int chunk = tuning("MT_CM_CHUNK", 0);
+    if (chunk < 1 || chunk > a.B) chunk = a.B;
     const int cc = tuning("MT_CM_COPY_CH", kCopyChannels);
-    if (cc == 2) {
-        dim3 g2(a.chunks, (a.C + 1) / 2, a.B);
-        launch(cm_copy_kernel<R, 2>, g2, 256, 0, st, a);
-    } else {
-        dim3 g2(a.chunks, (a.C + 3) / 4, a.B);
-        launch(cm_copy_kernel<R, 4>, g2, 256, 0, st, a);
+    for (int b0 = 0; b0 < a.B; b0 += chunk) {
+        const int nb = a.B - b0 < chunk ? a.B - b0 : chunk;
+        a.b_off = b0;
+        dim3 g1(a.chunks, (a.C + a.sim_ch - 1) / a.sim_ch, nb);
+        if (a.sim_ch == 2) launch(cm_sim_kernel<R, 2>, g1, 256, 0, st, a);
+        else launch(cm_sim_kernel<R, 4>, g1, 256, 0, st, a);
+        dim3 gw(a.chunks, nb);
+        launch(cm_weights_kernel<R>, gw, 256, 0, st, a);
+        if (cc == 2) {
+            dim3 g2(a.chunks, (a.C + 1) / 2, nb);
+            launch(cm_copy_kernel<R, 2>, g2, 256, 0, st, a);
+        } else {
+            dim3 g2(a.chunks, (a.C + 3) / 4, nb);
+            launch(cm_copy_kernel<R, 4>, g2, 256, 0, st, a);
+        }
     }
     return launch_status("mt_cm_match_fwd");
 }
