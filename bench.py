@@ -516,15 +516,20 @@ def run_gpu(args):
                          "launches": nl, "avg_us": 1e3 * avg,
                          "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (avg * 1e-3) / 1e9,
                          "frac_hbm": nbytes / (avg * 1e-3) / 1e9 / hbm_peak})
-    dom = max(per_call, key=lambda c: c["avg_us"])
-    roofline = {"bound": "hbm", "kernel": dom["call"], "launches_in_call": dom["launches"],
+    # dominant kernel = largest device time per LAUNCH; prefer single-launch calls, whose event
+    # interval is exactly one kernel (multi-launch calls are listed under "kernels")
+    single = [c for c in per_call if c["launches"] == 1] or per_call
+    dom = max(single, key=lambda c: c["avg_us"] / c["launches"])
+    kname = {"mt_warp_fwd": "warp_fwd_kernel", "mt_warp_l1_fwd": "warp_l1_fwd_kernel",
+             "mt_warp_l1_bwd": "warp_l1_bwd_kernel"}.get(dom["call"].split("#")[0], dom["call"])
+    roofline = {"bound": "hbm", "kernel": kname, "call": dom["call"], "launches_in_call": dom["launches"],
                 "achieved": dom["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": dom["frac_hbm"], "traffic": None, "peak_source": peak_src,
                 "avg_us": dom["avg_us"], "algorithmic_bytes": dom["algorithmic_bytes"]}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(args.workload, {}).get(dom["call"])
+            roofline["traffic"] = json.load(open(traffic_file)).get(args.workload, {}).get(kname)
         except Exception:
             pass
 

@@ -295,214 +295,6 @@ __global__ void __launch_bounds__(kCols) warp_fwd_kernel(const WarpFwdArgs a) {
 }
 
 // ---------------------------------------------------------------------------------
-// Staged forward kernel: the source footprint of a 128 x TH output tile is copied into
-// shared memory with bulk asynchronous copies (cp.async.bulk + mbarrier, one copy per
-// (plane, source row) segment), then the 4-tap gathers read shared memory.
-//
-// Why: PC sampling of the direct-gather kernel (profiles/) shows ~85 % of the stall samples
-// on the first use of gathered values: a warp can only keep ~1.3 KB of unique DRAM bytes in
-// flight in registers, i.e. <= ~60 KB per SM, a latency x bytes-in-flight ceiling near 50 %
-// of HBM peak.  With staging the bytes in flight are bounded by shared memory (tens of KB per
-// CTA, several CTAs per SM), not by registers or L1 miss tracking.
-// The footprint is data dependent (it follows the flow): every thread computes its taps, the
-// CTA reduces their bounding box (REDUX + smem), and stages it iff every tap is interior and
-// the box fits (kStageRows x kStageCols); otherwise the CTA takes the direct path.
-// ---------------------------------------------------------------------------------
-constexpr int kStageCols = 160;  // floats per staged row segment (128 columns + margin), multiple of 4
-constexpr int kTileRows = 8;     // output rows per CTA
-constexpr int kStageRows = 14;   // staged source rows per plane
-
-__device__ __forceinline__ uint32_t smem_addr(const void *p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-template <int C, int VIS, bool AFFINE>
-__global__ void __launch_bounds__(kCols) warp_fwd_staged_kernel(const WarpFwdArgs a) {
-    pdl_sync();
-    constexpr int NP = (VIS == 2) ? C + 1 : C;  // staged planes: x channels (+ the mask for CPN)
-    constexpr int TH = kTileRows;
-    __shared__ __align__(16) float s_tile[NP][kStageRows][kStageCols];
-    __shared__ float s_by[TH];
-    __shared__ int s_box[4][kCols / 32];
-    __shared__ __align__(8) unsigned long long s_bar;
-
-    const int W = a.sp.W, H = a.sp.H;
-    const bool live = (int)(blockIdx.x * kCols + threadIdx.x) < W;
-    const int x = min((int)(blockIdx.x * kCols + threadIdx.x), W - 1);
-    const int yb = blockIdx.y * TH;
-    const unsigned n = blockIdx.z;
-    const int b = a.f_magic ? (int)__umulhi(n, a.f_magic) : (int)n, f = (int)n - b * a.F;
-    const bool ac = a.sp.ac;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (AFFINE && (int)threadIdx.x < TH)
-        s_by[threadIdx.x] = base_coord(min(yb + (int)threadIdx.x, H - 1), H, a.sp.stepy, ac);
-    __syncthreads();
-
-    const int xo = b * a.x_sb + f * a.x_sf;
-    const int vo = b * a.vis_sb + f * a.vis_sf;
-    const int p00 = yb * W + x, np00 = (int)n * a.P + p00;
-    float t1 = 0.f, t2 = 0.f, t4 = 0.f, t5 = 0.f, bxt0 = 0.f, bxt3 = 0.f;
-    if (AFFINE) {
-        const float *th = a.grid + n * 6;
-        const float bx = base_coord(x, W, a.sp.stepx, ac);
-        bxt0 = __fmul_rn(bx, __ldg(th));
-        bxt3 = __fmul_rn(bx, __ldg(th + 3));
-        t1 = __ldg(th + 1); t2 = __ldg(th + 2); t4 = __ldg(th + 4); t5 = __ldg(th + 5);
-    }
-    // ---- phase A: coordinates of this thread's TH pixels, target mask, bounding box ----
-    float ix[TH], iy[TH], mtv[TH];
-    int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
-    bool interior = true;
-    const float wm2 = a.sp.wmax - 1.0f, hm2 = a.sp.hmax - 1.0f;
-#pragma unroll
-    for (int k = 0; k < TH; ++k) {
-        const bool row_ok = yb + k < H;
-        mtv[k] = (a.v_map && row_ok) ? __ldcs(a.m_target + (b * a.mt_sb + p00 + k * W)) : 0.0f;
-        float gx = 0.0f, gy = 0.0f;
-        if (AFFINE) {
-            gx = __fadd_rn(__fmaf_rn(s_by[k], t1, bxt0), t2);  // fma(by, t1, bx*t0) + t2 (pinned order)
-            gy = __fadd_rn(__fmaf_rn(s_by[k], t4, bxt3), t5);
-        } else if (row_ok) {
-            const float2 g = __ldcs(reinterpret_cast<const float2 *>(a.grid) + (np00 + k * W));
-            gx = g.x; gy = g.y;
-        }
-        ix[k] = unnormalize(gx, a.sp.sfx, ac);
-        iy[k] = unnormalize(gy, a.sp.sfy, ac);
-        const float xw = floorf(ix[k]), yn = floorf(iy[k]);
-        const bool in = (xw >= 0.0f) && (xw <= wm2) && (yn >= 0.0f) && (yn <= hm2);
-        interior = interior && in;
-        const int xi = in ? (int)xw : 0, yi = in ? (int)yn : 0;
-        xmin = min(xmin, xi); xmax = max(xmax, xi); ymin = min(ymin, yi); ymax = max(ymax, yi);
-    }
-    // CTA-wide box: REDUX per warp, then 4 warps through shared memory
-    const bool warp_in = __all_sync(0xffffffffu, interior);
-    xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
-    ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
-    if (lane == 0) {
-        s_box[0][wid] = warp_in ? xmin : -1;  // -1 poisons the box: some tap is out of the frame
-        s_box[1][wid] = xmax; s_box[2][wid] = ymin; s_box[3][wid] = ymax;
-    }
-    __syncthreads();
-    int bx0 = s_box[0][0], bx1 = s_box[1][0], by0 = s_box[2][0], by1 = s_box[3][0];
-    bool all_in = bx0 >= 0;
-#pragma unroll
-    for (int w2 = 1; w2 < kCols / 32; ++w2) {
-        all_in = all_in && s_box[0][w2] >= 0;
-        bx0 = min(bx0, s_box[0][w2]); bx1 = max(bx1, s_box[1][w2]);
-        by0 = min(by0, s_box[2][w2]); by1 = max(by1, s_box[3][w2]);
-    }
-    const int x0a = bx0 & ~3;                          // 16 B aligned first staged column
-    const int wseg = ((bx1 + 2 - x0a) + 3) & ~3;       // taps reach column bx1 + 1
-    const int ny = by1 + 2 - by0;                      // taps reach row by1 + 1
-    const bool staged = all_in && wseg <= kStageCols && ny <= kStageRows;
-
-    float xa[C], va;
-    if (staged) {
-        // ---- phase B: bulk copies, one per (plane, source row); warp 0 issues, everyone waits ----
-        if (wid == 0) {
-            const uint32_t bar = smem_addr(&s_bar);
-            const uint32_t bytes = (uint32_t)wseg * 4u;
-            if (lane == 0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                             ::"r"(bar), "r"(bytes * (uint32_t)(NP * ny)) : "memory");
-            }
-            __syncwarp();
-            for (int i = lane; i < NP * ny; i += 32) {
-                const int pl = i / ny, r = i - pl * ny;
-                const float *src = (pl < C) ? a.x + (xo + pl * a.x_sc + (by0 + r) * W + x0a)
-                                            : a.vis + (vo + (by0 + r) * W + x0a);
-                bulk_g2s(smem_addr(&s_tile[pl][r][0]), src, bytes, bar);
-            }
-        }
-        {
-            uint32_t ok = 0, spins = 0;
-            const uint32_t bar = smem_addr(&s_bar);
-            do {
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                             "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
-                if (!ok && ++spins > (1u << 26)) __trap();
-            } while (!ok);
-        }
-        // ---- phase C: taps from shared memory ----
-#pragma unroll
-        for (int k = 0; k < TH; ++k) {
-            if (yb + k >= H) break;
-            const float xw = floorf(ix[k]), yn = floorf(iy[k]);
-            const float w = __fsub_rn(ix[k], xw), e = __fsub_rn(1.0f, w);
-            const float nn = __fsub_rn(iy[k], yn), ss = __fsub_rn(1.0f, nn);
-            const float wnw = __fmul_rn(ss, e), wne = __fmul_rn(ss, w), wsw = __fmul_rn(nn, e), wse = __fmul_rn(nn, w);
-            const int cx = (int)xw - x0a, ry = (int)yn - by0;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float *r0 = &s_tile[c][ry][cx];
-                xa[c] = __fmaf_rn(r0[kStageCols + 1], wse, __fmaf_rn(r0[kStageCols], wsw,
-                        __fmaf_rn(r0[1], wne, __fmul_rn(r0[0], wnw))));
-            }
-            if (VIS == 2) {
-                const float *r0 = &s_tile[C][ry][cx];
-                float v00 = r0[0], v01 = r0[1], v10 = r0[kStageCols], v11 = r0[kStageCols + 1];
-                if (a.from_mask) {
-                    v00 = __fsub_rn(1.0f, v00); v01 = __fsub_rn(1.0f, v01);
-                    v10 = __fsub_rn(1.0f, v10); v11 = __fsub_rn(1.0f, v11);
-                }
-                const float vs = __fmaf_rn(v11, wse, __fmaf_rn(v10, wsw, __fmaf_rn(v01, wne, __fmul_rn(v00, wnw))));
-                va = vs > 0.5f ? 1.0f : 0.0f;  // strict, model_cpn.py:88
-            } else {
-                const float v = __ldg(a.vis + (vo + (int)rintf(iy[k]) * W + (int)rintf(ix[k])));
-                va = a.from_mask ? __fsub_rn(1.0f, v) : v;
-            }
-            if (live) {
-                const int p = p00 + k * W;
-                if (a.x_al) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) st_stream1(a.x_al + (b * a.xa_sb + f * a.xa_sf + p + c * a.xa_sc), xa[c]);
-                }
-                if (a.v_al) st_stream1(a.v_al + ((int)n * a.P + p), va);
-                if (a.v_map) st_stream1(a.v_map + ((int)n * a.P + p), clamp01(__fsub_rn(va, __fsub_rn(1.0f, mtv[k]))));
-            }
-        }
-    } else {
-        // ---- direct path: border tiles, out-of-frame or widely scattered flows ----
-#pragma unroll
-        for (int k = 0; k < TH; ++k) {
-            if (yb + k >= H) break;
-            const Bil bl = bil_params(ix[k], iy[k], a.sp);
-#pragma unroll
-            for (int c = 0; c < C; ++c) xa[c] = interp(gather(a.x + (xo + c * a.x_sc), bl, W), bl);
-            if (VIS == 2) {
-                Corners cv = gather(a.vis + vo, bl, W);
-                if (a.from_mask) {  // v = 1 - m inside the frame, 0 outside (zero padding of v)
-                    cv.nw = (bl.y0 && bl.x0) ? __fsub_rn(1.0f, cv.nw) : 0.0f;
-                    cv.ne = (bl.y0 && bl.x1) ? __fsub_rn(1.0f, cv.ne) : 0.0f;
-                    cv.sw = (bl.y1 && bl.x0) ? __fsub_rn(1.0f, cv.sw) : 0.0f;
-                    cv.se = (bl.y1 && bl.x1) ? __fsub_rn(1.0f, cv.se) : 0.0f;
-                }
-                va = interp(cv, bl) > 0.5f ? 1.0f : 0.0f;
-            } else {
-                va = nearest(a.vis + vo, ix[k], iy[k], a.sp, a.from_mask);
-            }
-            if (live) {
-                const int p = p00 + k * W;
-                if (a.x_al) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) st_stream1(a.x_al + (b * a.xa_sb + f * a.xa_sf + p + c * a.xa_sc), xa[c]);
-                }
-                if (a.v_al) st_stream1(a.v_al + ((int)n * a.P + p), va);
-                if (a.v_map) st_stream1(a.v_map + ((int)n * a.P + p), clamp01(__fsub_rn(va, __fsub_rn(1.0f, mtv[k]))));
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------
 // Shared pieces of the dense-flow kernels below (backward w.r.t. the grid, fused loss
 // forward / backward).  Same shape as the forward kernel: thread = column x U rows,
 // 32-bit offsets, warp-uniform interior fast path.
@@ -799,25 +591,6 @@ extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x
     a.from_mask = (flags & MT_VIS_FROM_MASK) != 0;
     const bool affine = (flags & MT_GRID_AFFINE) != 0;
     const bool vis_bil = (flags & MT_VIS_BILINEAR) != 0;
-    // staged variant: every staged row segment must start 16 B aligned
-    auto m4 = [](int64_t v) { return (v & 3) == 0; };
-    const bool can_stage = tuning("MT_WARP_STAGED", 1) != 0 && m4(W) && aligned16(x) && aligned16(vis) && m4(x_sb) &&
-                           m4(x_sc) && m4(x_sf) && m4(vis_sb) && m4(vis_sf) && (H + kTileRows - 1) / kTileRows <= 65535;
-    if (can_stage) {
-        a.iters = 1;
-        dim3 block(kCols), gridd((W + kCols - 1) / kCols, (H + kTileRows - 1) / kTileRows, B * F);
-        cudaStream_t st = (cudaStream_t)stream;
-#define MT_STAGED_GO(CC)                                                                        \
-    do {                                                                                        \
-        if (vis_bil) { if (affine) launch(warp_fwd_staged_kernel<CC, 2, true>, gridd, block, 0, st, a);   \
-                       else launch(warp_fwd_staged_kernel<CC, 2, false>, gridd, block, 0, st, a); }       \
-        else         { if (affine) launch(warp_fwd_staged_kernel<CC, 1, true>, gridd, block, 0, st, a);   \
-                       else launch(warp_fwd_staged_kernel<CC, 1, false>, gridd, block, 0, st, a); }       \
-    } while (0)
-        if (C == 3) MT_STAGED_GO(3); else MT_STAGED_GO(1);
-#undef MT_STAGED_GO
-        return launch_status("mt_warp_fwd");
-    }
     const int rows = tuning("MT_WARP_ROWS", kRows) == 2 ? 2 : 4;
     int iters = tuning("MT_WARP_ITERS", kIters);
     if (iters < 1) iters = 1;
