@@ -161,7 +161,7 @@ class Cfg1(Workload):
         n = self.b * self.f
         warp = n * 44 * px + self.b * 4 * px
         corr = n * (524288 + 262144) + self.b * 524288 + (n + self.b) * 1024
-        return [("mt_corr4d_fwd", 3, corr, "hbm"), ("mt_warp_fwd", 1, warp, "hbm")]
+        return [("mt_corr4d_fwd", 1, corr, "hbm"), ("mt_warp_fwd", 1, warp, "hbm")]
 
     def sub(self, b):
         return Cfg1(b, self.f, self.h, self.w)
@@ -277,7 +277,7 @@ class Cfg3(Workload):
     def calls(self):
         n = self.b * self.f
         corr = n * (524288 + 262144) + self.b * 524288 + (n + self.b) * 1024
-        out = [("mt_corr4d_fwd", 3, corr, "hbm"), ("mt_corr4d_fwd", 3, corr - (n + self.b) * 1024, "hbm")]
+        out = [("mt_corr4d_fwd", 1, corr, "hbm"), ("mt_corr4d_fwd", 1, corr - (n + self.b) * 1024, "hbm")]
         for px in (self.h * self.w, (self.h // 4) * (self.w // 4)):
             # loss-only fused forward: 12+8 per frame + 16/F target; backward: + 8 written
             out += [("mt_warp_l1_fwd", 1, n * 20 * px + self.b * 16 * px, "hbm"),

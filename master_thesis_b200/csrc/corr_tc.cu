@@ -1,12 +1,25 @@
 // corr_tc.cu - K2 on the 5th-generation tensor cores: tcgen05.mma (kind::tf32),
-// operands staged by TMA, accumulator in TMEM, normalisation + masks fused as a
-// rank-1 scaling in the tcgen05.ld epilogue.
+// operands staged by TMA, accumulators in TMEM, masks + L2 normalisation fused.
 //
 // Replaces CorrelationVGG.correlation_masked_4d, master_thesis/model_dfpn.py:534-565 (a7):
 //   out[b,f,m,n] = sum_k ft[b,k,m] fr[b,k,f,n] * sa[b,m] * sb[b,f,n]
 //   sa = v_t / (||ft * v_t||_2 + 1e-9)     (:551-560)     sb likewise for the reference (:561-562)
 // i.e. the reference's "mask, normalise, matmul" with the two normalisations factored out of
 // the contraction.  Masked rows / columns come out exactly 0 (scale 0 times a finite sum).
+//
+// One CTA computes one 256 x 256 output tile (= a whole (b, f) frame for the reference's
+// 16 x 16 feature maps): two M = 128 accumulators of N = 256 columns fill the 512 TMEM columns,
+// so every operand byte is loaded exactly once (128 x 128 tiles loaded everything twice:
+// 7 TB/s of L2->SM traffic, tensor pipe 21 % active, profiles/).  K = C in slices of 32, 3-stage
+// TMA ring (64 KB per stage).
+//
+// Warp roles (10 warps): 0 = TMA producer; 1 = TMEM owner + single-thread MMA issuer;
+// 2..9 = norm + epilogue.  While the MMA warp consumes a stage, thread t of the 8 worker warps
+// reads row t of the A tile and column t of the B tile from the same shared-memory stage
+// (de-swizzled) and accumulates their sums of squares: the L2 norms cost no extra pass over
+// the features and no extra launch (a separate scales kernel was 26 of 64 us at B=32, F=4).
+// The smem slot is released by the MMA commit AND one arrival per worker warp.
+// Epilogue: tcgen05.ld 32 lanes x 32 columns -> * sa[m] * sb[n] -> 128 B per-row stores.
 //
 // Data layout.  The features arrive fp32 and MN-major: ft (B,C,P) and fr (B,C,F,P) have the
 // pixel index contiguous, the contraction index (channel) strided.  They are consumed AS IS:
@@ -15,15 +28,10 @@
 // layout is "128 B swizzle with a 32 B base" (UMMA layout type 1, Swizzle<2,5,2>: the four 32 B
 // chunks of a 128 B row are permuted by the row index mod 4; a plain SWIZZLE_128B descriptor
 // is silently ignored - the first version of this kernel produced zeros).  TMA boxes of
-// {32 pixels = 128 B, BK channels, 4 pixel groups} with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B land
+// {32 pixels = 128 B, 32 channels, 8 pixel groups} with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B land
 // exactly in that canonical layout:
 //   4 channel rows x 128 B = one 512 B swizzle atom; SBO = 512 B between 4-channel groups;
 //   LBO = BK * 128 B between 32-pixel groups; one MMA (K = 8) spans two atoms.
-// One CTA = one 128 x 128 output tile of one (b, f) frame, K = C in BK = 32 slices, 3 stages
-// (100 KB of shared memory, so two CTAs share an SM and one's epilogue overlaps the other's
-// main loop; with 4 stages and one CTA per SM the tensor pipe was 21 % active, profiles/).
-// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue (one TMEM lane
-// quarter each): tcgen05.ld 32 lanes x 32 columns -> scale -> 128 B per-row stores.
 #include <cuda.h>
 
 #include "mt_common.cuh"
@@ -31,11 +39,17 @@
 namespace mt {
 namespace {
 
-constexpr int kTileM = 128, kTileN = 128, kBK = 32, kStages = 3;  // 3 x 32 KB: two CTAs per SM
-constexpr int kUmmaK = 8;  // tf32: 32 B of K per instruction
-constexpr int kStageBytesA = kTileM * kBK * 4, kStageBytesB = kTileN * kBK * 4;
-constexpr int kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + 1024 /*align*/ + 1024 /*barriers, scales*/;
-constexpr int kThreadsTc = 6 * 32;
+constexpr int kTile = 256;        // output tile rows (two UMMA M = 128 halves); columns TN <= 256
+constexpr int kBK = 32;
+constexpr int kUmmaK = 8;         // tf32: 32 B of K per instruction
+constexpr int kStageBytesA = kTile * kBK * 4;  // 32 KB
+constexpr int kWorkerWarps = 8;   // norm + epilogue warps (one per TMEM lane quarter and M half)
+constexpr int kThreadsTc = (2 + kWorkerWarps) * 32;
+// TN columns per CTA: 256 = every operand byte loaded once, 1 CTA/SM (large batches);
+// 128 / 64 = 2 / 4 CTAs per frame (A re-read from L2) with deeper TMA rings, for small batches
+// (swept on B200, profiles/r1_sweep_corr.sh: 8 frames 35/31/25 us, 128 frames 40/52/70 us).
+template <int TN, int STAGES>
+constexpr int smem_bytes() { return STAGES * (kStageBytesA + TN * kBK * 4) + 1024 /*align*/ + 4096 /*barriers, scales*/; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -45,6 +59,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0, spins = 0;
@@ -73,11 +90,11 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map
 // MN-major, SWIZZLE_128B_BASE32B shared-memory matrix descriptor (sm_100 "version 1").
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address  [0,14)
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;  // leading byte offset [16,30)
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset  [32,46)
-    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
-    d |= (uint64_t)1 << 61;                           // layout type: SWIZZLE_128B_BASE32B
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);            // start address  [0,14)
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // leading byte offset [16,30)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;   // stride byte offset  [32,46)
+    d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+    d |= (uint64_t)1 << 61;                               // layout type: SWIZZLE_128B_BASE32B
     return d;
 }
 // kind::tf32, fp32 accumulate, A and B MN-major, M x N
@@ -111,16 +128,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// byte offset of element (pixel p of the tile, channel k of the stage) in a staged operand:
+// [8 pixel groups][32 channels][128 B], 32 B chunks XOR-ed with (k mod 4)  (Swizzle<2,5,2>)
+__device__ __forceinline__ uint32_t staged_offset(int p, int k) {
+    const int g = p >> 5, px = p & 31;
+    return (uint32_t)(g * (kBK * 128) + k * 128 + ((((px >> 3) ^ (k & 3)) << 5) | ((px & 7) << 2)));
+}
+
 struct CorrTcArgs {
-    const float *sa;  // (B, P)      v_t / (||ft v_t|| + 1e-9)
-    const float *sb;  // (B, F, P)
+    const float *vt;  // (B, P) target visibility or NULL
+    const float *vr;  // (B, F, P) reference visibility or NULL
     float *out;       // (B, F, P, P)
     int C, F, P;
 };
 
-__global__ void __launch_bounds__(kThreadsTc, 2)
+template <int TN, int kStages>
+__global__ void __launch_bounds__(kThreadsTc, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const CorrTcArgs a) {
+    constexpr int kStageBytesB = TN * kBK * 4;
+    constexpr int kTmemCols = 2 * TN;  // two accumulators (M halves) of TN fp32 columns
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_a = smem;
@@ -128,7 +155,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * (kStageBytesA + kStageBytesB));
     uint64_t *full = bars, *empty = bars + kStages, *tmem_full = bars + 2 * kStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 1);
-    float *s_sb = reinterpret_cast<float *>(bars + 2 * kStages + 2);  // kTileN floats
+    float *s_sb = reinterpret_cast<float *>(bars + 2 * kStages + 2);  // TN column scales
+    float *s_sa = s_sb + kTile;                                         // kTile row scales
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x, n_tile = blockIdx.y, frame = blockIdx.z;
@@ -140,27 +168,22 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         for (int s = 0; s < kStages; ++s) {
             mbar_init(smem_u32(full + s), 1);
-            mbar_init(smem_u32(empty + s), 1);
+            mbar_init(smem_u32(empty + s), 1 + kWorkerWarps);  // MMA commit + one arrival per worker warp
         }
         mbar_init(smem_u32(tmem_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: kTileN fp32 accumulator columns x 128 lanes
+    if (warp == 1) {  // TMEM: two 128-lane x TN-column fp32 accumulators (all 512 columns at TN = 256)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32(tmem_slot)), "n"(kTileN) : "memory");
+                     ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // everything above is on-chip setup and overlaps the tail of the previous kernel (PDL);
-    // from here on the scales written by corr_scales_kernel are read
-    pdl_sync();
-    if (warp >= 2) {  // column scales of this tile
-        const int t = threadIdx.x - 64;
-        if (t < kTileN) s_sb[t] = __ldg(a.sb + ((int64_t)frame * a.P + n_tile * kTileN + t));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // everything above is on-chip setup and overlaps the tail of the previous kernel (PDL)
+    pdl_sync();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -172,16 +195,16 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_expect_tx(smem_u32(full + s), kStageBytesA + kStageBytesB);
                 // A: (pixel-in-group 32, channel C, pixel group P/32, batch B)
                 tma_load_4d(smem_u32(smem_a + s * kStageBytesA), &map_a, smem_u32(full + s), 0, kb * kBK,
-                            m_tile * (kTileM / 32), b);
+                            m_tile * (kTile / 32), b);
                 // B: (pixel-in-group 32, channel C, pixel group P/32, frame F, batch B)
                 tma_load_5d(smem_u32(smem_b + s * kStageBytesB), &map_b, smem_u32(full + s), 0, kb * kBK,
-                            n_tile * (kTileN / 32), f, b);
+                            n_tile * (TN / 32), f, b);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected lane) =====
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(kTileM, kTileN);
+            constexpr uint32_t idesc = instr_desc(128, TN);
             for (int kb = 0; kb < num_k; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
@@ -191,26 +214,64 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < kBK / kUmmaK; ++j) {
                     // K advance inside the stage: next 8 channels = two 512 B atoms = +1024 B
-                    const uint64_t ad = umma_desc(a0 + j * 1024, kBK * 128, 512);
                     const uint64_t bd = umma_desc(b0 + j * 1024, kBK * 128, 512);
-                    umma_tf32(tmem_base, ad, bd, idesc, (kb | j) != 0 ? 1u : 0u);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {  // M halves: pixel groups 0..3 and 4..7 of the A stage
+                        const uint64_t ad = umma_desc(a0 + h * (4 * kBK * 128) + j * 1024, kBK * 128, 512);
+                        umma_tf32(tmem_base + h * TN, ad, bd, idesc, (kb | j) != 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(smem_u32(empty + s));  // frees the smem slot when these MMAs retire
             }
-            umma_commit(smem_u32(tmem_full));      // accumulator complete
+            umma_commit(smem_u32(tmem_full));      // accumulators complete
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> scale -> global =====
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
-        const int m = m_tile * kTileM + q * 32 + lane;
-        const float sa = __ldg(a.sa + ((int64_t)b * a.P + m));
-        float *orow = a.out + (((int64_t)frame * a.P + m) * a.P + n_tile * kTileN);
+        // ===== workers: norms during the main loop, then the epilogue =====
+        const int t = threadIdx.x - 64;  // 0..255: row t of A, column t of B (if t < TN)
+        const int tb = t < TN ? t : 0;
+        // the swizzle phase repeats every 4 channels: channel k = 4 j + r lives at base[r] + 512 j,
+        // so the loop below is 32 LDS with immediate offsets + 32 FFMA per operand, no address math
+        uint32_t base_a[4], base_b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { base_a[r] = staged_offset(t, r); base_b[r] = staged_offset(tb, r); }
+        float qa[4] = {0.f, 0.f, 0.f, 0.f}, qb[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int kb = 0; kb < num_k; ++kb) {
+            const int s = kb % kStages;
+            const uint32_t ph = (kb / kStages) & 1;
+            mbar_wait(smem_u32(full + s), ph);
+            const uint8_t *pa = smem_a + s * kStageBytesA, *pb = smem_b + s * kStageBytesB;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int j = 0; j < kBK / 4; ++j) {
+                    const float va = *reinterpret_cast<const float *>(pa + base_a[r] + j * 512);
+                    const float vb = *reinterpret_cast<const float *>(pb + base_b[r] + j * 512);
+                    qa[r] = __fmaf_rn(va, va, qa[r]);
+                    qb[r] = __fmaf_rn(vb, vb, qb[r]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(empty + s));
+        }
+        const float ssa = (qa[0] + qa[1]) + (qa[2] + qa[3]), ssb = (qb[0] + qb[1]) + (qb[2] + qb[3]);
+        // scales: v / (|v| * ||f|| + 1e-9)   (||f * v|| = |v| * ||f||)
+        const float vt = a.vt ? __ldg(a.vt + ((int64_t)b * a.P + m_tile * kTile + t)) : 1.0f;
+        const float vr = a.vr ? __ldg(a.vr + ((int64_t)frame * a.P + n_tile * TN + tb)) : 1.0f;
+        s_sa[t] = __fdiv_rn(vt, __fadd_rn(__fmul_rn(fabsf(vt), sqrtf(ssa)), 1e-9f));
+        if (t < TN) s_sb[t] = __fdiv_rn(vr, __fadd_rn(__fmul_rn(fabsf(vr), sqrtf(ssb)), 1e-9f));
+        asm volatile("bar.sync 1, %0;" ::"n"(kWorkerWarps * 32) : "memory");  // workers only
+        // TMEM lane-quarter rule: warp w may touch lanes 32*(w%4)..32*(w%4)+31.  Warps 2..9 have
+        // (w%4) = 2,3,0,1,2,3,0,1; warps 2..5 drain the first M half, 6..9 the second.
+        const int lq = warp & 3, wh = (warp - 2) >> 2;
+        const int row = wh * 128 + lq * 32 + lane;
+        const float sa = s_sa[row];
+        float *orow = a.out + (((int64_t)frame * a.P + m_tile * kTile + row) * a.P + n_tile * TN);
         mbar_wait(smem_u32(tmem_full), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int c0 = 0; c0 < kTileN; c0 += 32) {
+        for (int c0 = 0; c0 < TN; c0 += 32) {
             float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(wh * TN + c0), v);
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
                 float4 o;
@@ -225,47 +286,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTileN) : "memory");
-    }
-}
-
-// scale[n, p] = v / (||feat[:, p] * v||_2 + 1e-9) for frame n = b*F + f (F = 1 for the target).
-// CTA = 32 pixels x 8 channel groups; coalesced 128 B rows; fixed-order reduction.
-__global__ void __launch_bounds__(256) corr_scales_kernel(const float *__restrict__ src,
-                                                          const float *__restrict__ vis,
-                                                          float *__restrict__ scale, int C, int F, int P) {
-    pdl_sync();
-    __shared__ float part[8][33];
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int p = blockIdx.x * 32 + lane;
-    const int64_t n = blockIdx.y;
-    const int64_t b = n / F, f = n - b * F;
-    const int64_t sc = (int64_t)F * P;
-    float ss = 0.0f;
-    if (p < P) {
-        const float *s = src + b * C * sc + f * P + p;
-        int k = grp;
-        for (; k + 56 < C; k += 64) {  // 8 independent loads in flight per thread
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldg(s + (int64_t)(k + 8 * u) * sc);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) ss = __fmaf_rn(v[u], v[u], ss);
-        }
-        for (; k < C; k += 8) {
-            const float v = __ldg(s + k * sc);
-            ss = __fmaf_rn(v, v, ss);
-        }
-    }
-    part[grp][lane] = ss;
-    __syncthreads();
-    if (grp == 0 && p < P) {
-        float tot = 0.0f;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) tot += part[g][lane];
-        const float v = vis ? __ldg(vis + n * P + p) : 1.0f;
-        // ||f * v|| = |v| * ||f||;  scale = v / (||f v|| + 1e-9)
-        scale[n * P + p] = __fdiv_rn(v, __fadd_rn(__fmul_rn(fabsf(v), sqrtf(tot)), 1e-9f));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
 }
 
@@ -286,42 +307,37 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
-
 }  // namespace
 
 int corr4d_tc_supported(int C, int P) {
     if (tuning("MT_CORR_SIMT", 0)) return 0;
-    return (P % kTileM == 0 && P % kTileN == 0 && C % kBK == 0 && C >= kBK && P <= 65536) ? 1 : 0;
+    return (P % kTile == 0 && C % kBK == 0 && C >= kBK && P <= 65536) ? 1 : 0;
 }
 
 int64_t corr4d_tc_workspace_bytes(int B, int C, int F, int P) {
-    (void)C;
-    return align256((int64_t)B * P * 4) + align256((int64_t)B * F * P * 4);
+    (void)B; (void)C; (void)F; (void)P;
+    return 0;  // norms are fused into the GEMM: no scratch
 }
 
 int corr4d_tc_launch(const float *ft, const float *vt, const float *fr, const float *vr, float *out, void *ws,
                      int64_t ws_bytes, int B, int C, int F, int P, cudaStream_t st) {
-    (void)ws_bytes;
-    MT_REQUIRE(aligned16(ft) && aligned16(fr) && aligned16(out) && aligned16(ws),
-               "mt_corr4d_fwd: pointers must be 16 B aligned");
+    (void)ws; (void)ws_bytes;
+    MT_REQUIRE(aligned16(ft) && aligned16(fr) && aligned16(out), "mt_corr4d_fwd: pointers must be 16 B aligned");
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
         set_error("mt_corr4d_fwd: cuTensorMapEncodeTiled is not available from the driver");
         return MT_ERR_NO_DEVICE;
     }
-    float *sa = reinterpret_cast<float *>(ws);
-    float *sb = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + align256((int64_t)B * P * 4));
-    dim3 gs_t((P + 31) / 32, B), gs_r((P + 31) / 32, B * F);
-    launch(corr_scales_kernel, gs_t, 256, 0, st, ft, vt, sa, C, 1, P);
-    launch(corr_scales_kernel, gs_r, 256, 0, st, fr, vr, sb, C, F, P);
-
+    // columns per CTA: split a frame across more CTAs when the batch alone cannot fill the GPU
+    const int frames = B * F * (P / kTile);
+    int tn = tuning("MT_CORR_TN", 0);
+    if (tn != 256 && tn != 128 && tn != 64) tn = frames >= sm_count() / 2 ? 256 : (frames * 2 >= sm_count() / 2 ? 128 : 64);
     CUtensorMap map_a, map_b;
     {
         // ft (B, C, P) viewed as (32, C, P/32, B): strides in bytes for dims 1..3
         cuuint64_t dims[4] = {32, (cuuint64_t)C, (cuuint64_t)(P / 32), (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)P * 4, 128, (cuuint64_t)C * P * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)kBK, (cuuint32_t)(kTileM / 32), 1};
+        cuuint32_t box[4] = {32, (cuuint32_t)kBK, (cuuint32_t)(kTile / 32), 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(ft), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
@@ -335,7 +351,7 @@ int corr4d_tc_launch(const float *ft, const float *vt, const float *fr, const fl
         // fr (B, C, F, P) viewed as (32, C, P/32, F, B)
         cuuint64_t dims[5] = {32, (cuuint64_t)C, (cuuint64_t)(P / 32), (cuuint64_t)F, (cuuint64_t)B};
         cuuint64_t strides[4] = {(cuuint64_t)F * P * 4, 128, (cuuint64_t)P * 4, (cuuint64_t)C * F * P * 4};
-        cuuint32_t box[5] = {32, (cuuint32_t)kBK, (cuuint32_t)(kTileN / 32), 1, 1};
+        cuuint32_t box[5] = {32, (cuuint32_t)kBK, (cuuint32_t)(tn / 32), 1, 1};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(fr), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
@@ -345,16 +361,23 @@ int corr4d_tc_launch(const float *ft, const float *vt, const float *fr, const fl
             return MT_ERR_CUDA;
         }
     }
-    {
-        cudaError_t e = cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) {
-            set_error("mt_corr4d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return MT_ERR_CUDA;
-        }
-    }
-    CorrTcArgs a{sa, sb, out, C, F, P};
-    dim3 grid(P / kTileM, P / kTileN, B * F);
-    launch(corr_tc_kernel, grid, kThreadsTc, kSmemBytes, st, map_a, map_b, a);
+    CorrTcArgs a{vt, vr, out, C, F, P};
+    dim3 grid(P / kTile, P / tn, B * F);
+#define MT_CORR_GO(TNV, STG)                                                                         \
+    do {                                                                                             \
+        cudaError_t e = cudaFuncSetAttribute(corr_tc_kernel<TNV, STG>,                               \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<TNV, STG>()); \
+        if (e != cudaSuccess) {                                                                      \
+            set_error("mt_corr4d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));             \
+            return MT_ERR_CUDA;                                                                      \
+        }                                                                                            \
+        launch(corr_tc_kernel<TNV, STG>, grid, dim3(kThreadsTc), (size_t)smem_bytes<TNV, STG>(), st, map_a, map_b, a); \
+    } while (0)
+    // narrower tiles run with fewer CTAs than SMs: spend the shared memory on pipeline depth
+    if (tn == 256) MT_CORR_GO(256, 3);       // 3 x 64 KB
+    else if (tn == 128) MT_CORR_GO(128, 4);  // 4 x 48 KB
+    else MT_CORR_GO(64, 5);                  // 5 x 40 KB
+#undef MT_CORR_GO
     return launch_status("mt_corr4d_fwd");
 }
 
