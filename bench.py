@@ -288,7 +288,86 @@ class Cfg3(Workload):
         return Cfg3(b, self.f, self.h, self.w)
 
 
-WORKLOADS = {"cfg1": Cfg1, "cfg2": Cfg2, "cfg3": Cfg3, "cfg4": Cfg4}
+class Cfg5(Workload):
+    """CHN training-step hot path with the CPN aligner (model_chn.py:256-280, 324-362): affine warp,
+    CNN-input pack, composite, the three masked-L1 terms, and their backward down to the CNN output."""
+    name = "cfg5"
+
+    def __init__(self, b=8, f=4, h=256, w=256):
+        self.b, self.f, self.h, self.w = b, f, h, w
+        self.frames_per_step = b * f
+        self.describe = ("cfg5: CHN training hot path, CPN aligner (affine warp + pack + composite "
+                         "fwd/bwd + 3x masked-L1 fwd/bwd), batch_size=%d per GPU (64 global on 8 GPUs) "
+                         "frames_n=%d %dx%d" % (b, f + 1, h, w))
+
+    def host_inputs(self, seed):
+        import numpy as np
+        from master_thesis_b200 import synth
+        b, f, h, w = self.b, self.f, self.h, self.w
+        x, m, y = synth.frames(seed, b, f + 1, h, w)
+        t = (f + 1) // 2
+        refs = [i for i in range(f + 1) if i != t]
+        return {
+            "x_target": np.ascontiguousarray(x[:, :, t]), "y_target": np.ascontiguousarray(y[:, :, t]),
+            "m_target": np.ascontiguousarray(m[:, :, t]), "v_target": np.ascontiguousarray(1 - m[:, :, t]),
+            "x_refs": np.ascontiguousarray(x[:, :, refs]), "m_refs": np.ascontiguousarray(m[:, :, refs]),
+            "theta": synth.thetas(seed + 1, b * f, 0.1), "nn_out": synth.nn_output(seed + 2, b * f, h, w),
+            "grad_out": np.ones(1, np.float32),
+        }
+
+    def gpu_step(self, mtb, d):
+        ops = mtb.ops
+        b, f = self.b, self.f
+        xa, va, vm = mtb.cpn_align_tail(d["x_refs"], d["m_refs"], d["m_target"], d["theta"])
+        nn_in = ops.chn_pack(d["x_target"], d["v_target"], xa, va, vm)
+        y_hat, y_comp = ops.chn_composite(d["nn_out"], d["x_target"], d["v_target"], b, f)
+        # compute_loss (model_chn.py:347-362); the repeats are stride-0 views here
+        tgt = d["y_target"].unsqueeze(2).expand(-1, -1, f, -1, -1)
+        nh = d["v_target"].unsqueeze(2).expand(-1, -1, f, -1, -1)
+        if "nvh" not in d:   # (1 - nh_mask) - vh_mask: a torch elementwise op, outside the measured kernels
+            d["nvh"] = ((1 - nh) - vm).contiguous()
+        l1, s1 = ops.masked_l1_fwd_raw(y_hat, tgt, nh, None, "sum", 0.5)
+        l2, s2 = ops.masked_l1_fwd_raw(y_hat, tgt, vm, None, "sum", 2.0)
+        l3, s3 = ops.masked_l1_fwd_raw(y_comp, tgt, d["nvh"], None, "sum", 1.0)
+        g1, _ = ops.masked_l1_bwd_raw(s1, d["grad_out"])
+        g2, _ = ops.masked_l1_bwd_raw(s2, d["grad_out"])
+        g3, _ = ops.masked_l1_bwd_raw(s3, d["grad_out"])
+        g_nn = ops.chn_composite_bwd_raw(d["nn_out"], d["v_target"], g1, g3, b, f)
+        return {"nn_in": nn_in, "losses": (l1, l2, l3), "g2": g2, "g_nn": g_nn, "keep": (xa, va, vm, y_hat, y_comp)}
+
+    def cpu_step(self, tp, d):
+        import torch
+        b, f = self.b, self.f
+        xa, va, vm = tp.cpn_align_tail(d["x_refs"], d["m_refs"], d["m_target"], d["theta"])
+        nn_in = tp.chn_pack(d["x_target"], d["v_target"], xa, va, vm)
+        nn_out = d["nn_out"].detach().requires_grad_(True)
+        y_hat, y_comp = tp.chn_composite(nn_out, d["x_target"], d["v_target"], b, f)
+        tgt = d["y_target"].unsqueeze(2).repeat(1, 1, f, 1, 1)
+        nh = d["v_target"].unsqueeze(2).repeat(1, 1, f, 1, 1)
+        loss = tp.masked_l1(y_hat, tgt, nh, reduction='sum', weight=0.5) + \
+            tp.masked_l1(y_hat, tgt, vm, reduction='sum', weight=2) + \
+            tp.masked_l1(y_comp, tgt, (1 - nh) - vm, reduction='sum', weight=1)
+        return nn_in, torch.autograd.grad(loss, nn_out)[0]
+
+    def calls(self):
+        px = self.h * self.w
+        n = self.b * self.f
+        l1f = n * 28 * px + self.b * 16 * px          # y_hat/y_comp 12 + mask 4 (+ target 12, mask 4 per sample)
+        l1b = n * 40 * px + self.b * 16 * px          # + 12 written
+        return [("mt_warp_fwd", 1, n * 36 * px + self.b * 4 * px, "hbm"),
+                ("mt_chn_pack", 1, n * 56 * px + self.b * 16 * px, "hbm"),
+                ("mt_chn_composite_fwd", 1, n * 36 * px + self.b * 16 * px, "hbm"),
+                ("mt_masked_l1_fwd", 1, l1f, "hbm"), ("mt_masked_l1_fwd", 1, l1f, "hbm"),
+                ("mt_masked_l1_fwd", 1, l1f - self.b * 4 * px + n * 4 * px, "hbm"),
+                ("mt_masked_l1_bwd", 1, l1b, "hbm"), ("mt_masked_l1_bwd", 1, l1b, "hbm"),
+                ("mt_masked_l1_bwd", 1, l1b, "hbm"),
+                ("mt_chn_composite_bwd", 1, n * 48 * px + self.b * 4 * px, "hbm")]
+
+    def sub(self, b):
+        return Cfg5(b, self.f, self.h, self.w)
+
+
+WORKLOADS = {"cfg1": Cfg1, "cfg2": Cfg2, "cfg3": Cfg3, "cfg4": Cfg4, "cfg5": Cfg5}
 
 
 # ---------------------------------------------------------------------------
@@ -580,7 +659,7 @@ def run_e2e(args, wl, mtb, ops, host, dev, world):
                 d_in[k].copy_(pin_in[k], non_blocking=True)
             with ops.record() as plan:
                 out = wl.gpu_step(mtb, d_in)
-            out = {k: v for k, v in out.items()}
+            out = {k: v for k, v in out.items() if isinstance(v, torch.Tensor)}   # results copied back
             pin_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
         st.synchronize()
         slots.append((st, pin_in, d_in, plan, out, pin_out))
@@ -591,7 +670,7 @@ def run_e2e(args, wl, mtb, ops, host, dev, world):
     def one(i):
         st, pin_in, d_in, plan, out, pin_out = slots[i % 2]
         with torch.cuda.stream(st):
-            for k in d_in:
+            for k in pin_in:
                 d_in[k].copy_(pin_in[k], non_blocking=True)
             plan()
             for k in out:

@@ -112,6 +112,7 @@ class Plan(object):
 
     def __init__(self):
         self.entries = []
+        self.keep = []      # every tensor allocated while recording: the plan owns its buffers
 
     def __call__(self):
         for name, fn, cargs in self.entries:
@@ -127,6 +128,13 @@ class Plan(object):
         rc = fn(*cargs)
         if rc:
             check(rc, name)
+
+
+def keep(t):
+    """Registers a tensor with the active recording (no-op otherwise) and returns it."""
+    if _recording is not None and t is not None:
+        _recording.keep.append(t)
+    return t
 
 
 class record(object):

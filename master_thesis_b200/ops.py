@@ -21,6 +21,20 @@ _workspaces = {}
 record = _lib.record      # with ops.record() as plan: ...   (see _lib.Plan)
 
 
+def _empty(*a, **k):
+    return _lib.keep(torch.empty(*a, **k))
+
+
+def _empty_like(*a, **k):
+    return _lib.keep(torch.empty_like(*a, **k))
+
+
+def _contig(t):
+    """contiguous() whose copy (if one is made) is owned by the active recording."""
+    c = t.contiguous()
+    return c if c is t else _lib.keep(c)
+
+
 def _stream(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
@@ -55,7 +69,7 @@ def scratch(t, tag, nbytes):
     key = (tag, t.device.index, torch.cuda.current_stream(t.device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=t.device)
+        ws = _empty(max(int(nbytes), 256), dtype=torch.uint8, device=t.device)
         _workspaces[key] = ws
     return ws
 
@@ -65,7 +79,7 @@ def _planes(t, plane_dims=2):
     exp = 1
     for d in range(t.dim() - 1, t.dim() - 1 - plane_dims, -1):
         if t.size(d) != 1 and t.stride(d) != exp:
-            return t.contiguous()
+            return _contig(t)
         exp *= t.size(d)
     return t
 
@@ -79,7 +93,7 @@ def _s5(t):
 def _frame_major(b, c, f, h, w, like):
     """x_aligned memory: contiguous (B,F,C,H,W), returned as the (B,C,F,H,W) view the
     reference's `.reshape(b,-1,3,h,w).transpose(1,2)` produces (utils.py:97)."""
-    mem = torch.empty((b, f, c, h, w), dtype=torch.float32, device=like.device)
+    mem = _empty((b, f, c, h, w), dtype=torch.float32, device=like.device)
     return mem, mem.transpose(1, 2)
 
 
@@ -95,7 +109,7 @@ def warp_fwd(x, vis, grid, m_target=None, flags=ALIGN_CORNERS, want_x=True, want
     b, c, f, h, w = x.shape
     x, x_sb, x_sc, x_sf = _s5(x)
     vis, v_sb, _, v_sf = _s5(vis)
-    grid = grid.contiguous()
+    grid = _contig(grid)
     if flags & GRID_AFFINE:
         if grid.numel() != b * f * 6:
             raise RuntimeError("theta must have shape (B*F,2,3)")
@@ -108,8 +122,8 @@ def warp_fwd(x, vis, grid, m_target=None, flags=ALIGN_CORNERS, want_x=True, want
     xa_mem = xa = None
     if want_x:
         xa_mem, xa = _frame_major(b, c, f, h, w, x)
-    va = torch.empty((b, 1, f, h, w), dtype=torch.float32, device=x.device) if want_v else None
-    vm = torch.empty((b, 1, f, h, w), dtype=torch.float32, device=x.device) \
+    va = _empty((b, 1, f, h, w), dtype=torch.float32, device=x.device) if want_v else None
+    vm = _empty((b, 1, f, h, w), dtype=torch.float32, device=x.device) \
         if m_target is not None else None
     p = h * w
     _lib.call("mt_warp_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis), v_sb, v_sf, _ptr(grid),
@@ -123,8 +137,8 @@ def warp_bwd_grid(x, grid, gout, flags=ALIGN_CORNERS):
     b, c, f, h, w = x.shape
     x, x_sb, x_sc, x_sf = _s5(x)
     gout, g_sb, g_sc, g_sf = _s5(gout)
-    grid = grid.contiguous()
-    gg = torch.empty_like(grid)
+    grid = _contig(grid)
+    gg = _empty_like(grid)
     _lib.call("mt_warp_bwd_grid", _ptr(x), x_sb, x_sc, x_sf, _ptr(grid), _ptr(gout), g_sb, g_sc,
               g_sf, _ptr(gg), b, c, f, h, w, flags, _stream(x))
     return gg
@@ -158,9 +172,9 @@ def align_set(x, v, flow):
 def mask_out(flow):
     """model_dfpn.py:269-272: flow (B,F,H,W,2) -> (B,1,F,H,W)."""
     _need_cuda(flow)
-    flow = flow.detach().contiguous()
+    flow = _contig(flow.detach())
     b, f, h, w, _ = flow.shape
-    out = torch.empty((b, 1, f, h, w), dtype=torch.float32, device=flow.device)
+    out = _empty((b, 1, f, h, w), dtype=torch.float32, device=flow.device)
     _lib.call("mt_mask_out", _ptr(flow), flow.numel() // 2, _ptr(out), _stream(flow))
     return out
 
@@ -182,7 +196,7 @@ def _l1_layout(y_hat, y, mask):
     b = y_hat.shape[0]
     ts = []
     for t in (y_hat, y, mask):
-        t = t.contiguous().view(b, 1, 1, -1)
+        t = _contig(t).view(b, 1, 1, -1)
         ts.append((t, t.stride(0), 0, 0))
     return ts, b, 1, 1, ts[0][0].shape[-1], 1
 
@@ -191,7 +205,34 @@ def _bm(batch_mask, like):
     if batch_mask is None:
         return None
     bm = torch.as_tensor(batch_mask)
-    return bm.to(device=like.device, dtype=torch.uint8).contiguous()
+    return _lib.keep(bm.to(device=like.device, dtype=torch.uint8).contiguous())
+
+
+def masked_l1_fwd_raw(y_hat, y, mask, batch_mask=None, reduction="mean", weight=1.0):
+    """mt_masked_l1_fwd without autograd.  Returns (out3, saved): out3 = [loss, sum|.|, den] on the
+    device, ``saved`` feeds masked_l1_bwd_raw."""
+    _need_cuda(y_hat, y, mask)
+    (a, b_, m), B, C, F, P, mask_c = _l1_layout(y_hat, y, mask)
+    bm = _bm(batch_mask, y_hat)
+    out3 = _empty(3, dtype=torch.float32, device=y_hat.device)
+    _lib.call("mt_masked_l1_fwd", _ptr(a[0]), a[1], a[2], a[3], _ptr(b_[0]), b_[1], b_[2], b_[3],
+              _ptr(m[0]), m[1], m[2], m[3], _ptr(bm), _ptr(out3), _ptr(reduce_workspace(y_hat)),
+              B, C, F, P, mask_c, REDUCE[reduction], float(weight), _stream(y_hat))
+    meta = (a[1:], b_[1:], m[1:], B, C, F, P, mask_c, REDUCE[reduction], float(weight), tuple(y_hat.shape))
+    return out3, (a[0], b_[0], m[0], out3, bm, meta)
+
+
+def masked_l1_bwd_raw(saved, grad_out, need_y_hat=True, need_y=False):
+    """mt_masked_l1_bwd: gradients w.r.t. y_hat and / or y (grad_y = -grad_y_hat)."""
+    a, b_, m, out3, bm, (sa, sb, sm, B, C, F, P, mask_c, red, weight, shape) = saved
+    ga = _empty((B, C, F, P), dtype=torch.float32, device=a.device) if need_y_hat else None
+    gb = _empty((B, C, F, P), dtype=torch.float32, device=a.device) if need_y else None
+    _lib.call("mt_masked_l1_bwd", _ptr(a), sa[0], sa[1], sa[2], _ptr(b_), sb[0], sb[1], sb[2],
+              _ptr(m), sm[0], sm[1], sm[2], _ptr(bm), _ptr(out3), _ptr(grad_out),
+              _ptr(ga), _ptr(gb), B, C, F, P, mask_c, red, weight, _stream(a))
+    ga = ga.view(shape) if ga is not None else None
+    gb = gb.view(shape) if gb is not None else None
+    return ga, gb
 
 
 class MaskedL1Fn(torch.autograd.Function):
@@ -199,35 +240,23 @@ class MaskedL1Fn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y_hat, y, mask, batch_mask, reduction, weight):
-        _need_cuda(y_hat, y, mask)
-        (a, b_, m), B, C, F, P, mask_c = _l1_layout(y_hat, y, mask)
-        bm = _bm(batch_mask, y_hat)
-        out3 = torch.empty(3, dtype=torch.float32, device=y_hat.device)
-        _lib.call("mt_masked_l1_fwd", _ptr(a[0]), a[1], a[2], a[3], _ptr(b_[0]), b_[1], b_[2], b_[3],
-                  _ptr(m[0]), m[1], m[2], m[3], _ptr(bm), _ptr(out3), _ptr(reduce_workspace(y_hat)),
-                  B, C, F, P, mask_c, REDUCE[reduction], float(weight), _stream(y_hat))
-        ctx.save_for_backward(a[0], b_[0], m[0], out3, bm if bm is not None else out3)
-        ctx.meta = (a[1:], b_[1:], m[1:], B, C, F, P, mask_c, REDUCE[reduction], float(weight),
-                    bm is not None, y_hat.shape)
+        out3, saved = masked_l1_fwd_raw(y_hat, y, mask, batch_mask, reduction, weight)
+        a, b_, m, _, bm, meta = saved
+        ctx.save_for_backward(a, b_, m, out3, bm if bm is not None else out3)
+        ctx.meta = (meta, bm is not None)
         return out3[0]
 
     @staticmethod
     def backward(ctx, g):
         a, b_, m, out3, bm = ctx.saved_tensors
-        sa, sb, sm, B, C, F, P, mask_c, red, weight, has_bm, shape = ctx.meta
+        meta, has_bm = ctx.meta
         need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if ctx.needs_input_grad[2]:
             raise RuntimeError("masked_l1: gradient w.r.t. the mask is not provided")
         if not (need_a or need_b):
             return (None,) * 6
-        g = g.contiguous().to(torch.float32)
-        ga = torch.empty((B, C, F, P), dtype=torch.float32, device=a.device) if need_a else None
-        gb = torch.empty((B, C, F, P), dtype=torch.float32, device=a.device) if need_b else None
-        _lib.call("mt_masked_l1_bwd", _ptr(a), sa[0], sa[1], sa[2], _ptr(b_), sb[0], sb[1], sb[2],
-                  _ptr(m), sm[0], sm[1], sm[2], _ptr(bm) if has_bm else None, _ptr(out3), _ptr(g),
-                  _ptr(ga), _ptr(gb), B, C, F, P, mask_c, red, weight, _stream(a))
-        ga = ga.view(shape) if ga is not None else None
-        gb = gb.view(shape) if gb is not None else None
+        g = _contig(g).to(torch.float32)
+        ga, gb = masked_l1_bwd_raw((a, b_, m, out3, bm if has_bm else None, meta), g, need_a, need_b)
         return ga, gb, None, None, None, None
 
 
@@ -250,15 +279,15 @@ def warp_l1_fwd_raw(x_refs, vis, flow, x_target, v_target, weight=1.0, materiali
     if c != 3:
         raise RuntimeError("warp_masked_l1: C must be 3")
     x, x_sb, x_sc, x_sf = _s5(x_refs)
-    flow_c = flow.detach().contiguous()
+    flow_c = _contig(flow.detach())
     xt = _planes(x_target)
     vt = _planes(v_target)
-    out3 = torch.empty(3, dtype=torch.float32, device=x.device)
+    out3 = _empty(3, dtype=torch.float32, device=x.device)
     xa_mem = xa = va = None
     vis_t, v_sb, v_sf = None, 0, 0
     if materialize:
         xa_mem, xa = _frame_major(b, 3, f, h, w, x)
-        va = torch.empty((b, 1, f, h, w), dtype=torch.float32, device=x.device)
+        va = _empty((b, 1, f, h, w), dtype=torch.float32, device=x.device)
         vis_t, v_sb, _, v_sf = _s5(vis)
     _lib.call("mt_warp_l1_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis_t), v_sb, v_sf, _ptr(flow_c),
               _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0), _ptr(xa_mem),
@@ -271,7 +300,7 @@ def warp_l1_fwd_raw(x_refs, vis, flow, x_target, v_target, weight=1.0, materiali
 def warp_l1_bwd_raw(saved, grad_out):
     """mt_warp_l1_bwd: d loss / d flow (B,F,H,W,2); grad_out is a 1-element device tensor."""
     x, flow, xt, vt, out3, (x_sb, x_sc, x_sf, b, f, h, w, weight, flags) = saved
-    gflow = torch.empty_like(flow)
+    gflow = _empty_like(flow)
     _lib.call("mt_warp_l1_bwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(flow), _ptr(xt), xt.stride(0),
               xt.stride(1), _ptr(vt), vt.stride(0), _ptr(out3), _ptr(grad_out), _ptr(gflow), b, f, h, w,
               weight, flags, _stream(x))
@@ -294,7 +323,7 @@ class WarpL1Fn(torch.autograd.Function):
     def backward(ctx, g, _gx, _gv):
         if not ctx.needs_input_grad[2]:
             return (None,) * 8
-        g = g.contiguous().to(torch.float32)
+        g = _contig(g).to(torch.float32)
         gflow = warp_l1_bwd_raw(tuple(ctx.saved_tensors) + (ctx.meta,), g)
         return None, None, gflow, None, None, None, None, None
 
@@ -316,11 +345,11 @@ def corr4d(feats_t, v_t, feats_r, v_r):
     _need_cuda(feats_t, v_t, feats_r, v_r)
     b, c, f, h, w = feats_r.shape
     p = h * w
-    ft = feats_t.contiguous()
-    fr = feats_r.contiguous()
-    vt = None if v_t is None else v_t.contiguous()
-    vr = None if v_r is None else v_r.contiguous()
-    out = torch.empty((b, f, h, w, h, w), dtype=torch.float32, device=fr.device)
+    ft = _contig(feats_t)
+    fr = _contig(feats_r)
+    vt = None if v_t is None else _contig(v_t)
+    vr = None if v_r is None else _contig(v_r)
+    out = _empty((b, f, h, w, h, w), dtype=torch.float32, device=fr.device)
     lib = _lib.load()
     nbytes = int(lib.mt_corr4d_workspace_bytes(b, c, f, p))
     ws = scratch(fr, "corr", nbytes)
@@ -337,11 +366,11 @@ def cm_match(c_feats, v_t, v_aligned, return_gs=False):
     _need_cuda(c_feats, v_t, v_aligned)
     b, c, f, h, w = c_feats.shape
     H, W = v_t.shape[-2:]
-    cf = c_feats.contiguous()
-    vt = v_t.contiguous()
-    va = v_aligned.contiguous()
-    out = torch.empty((b, 2 * c + 1, h, w), dtype=torch.float32, device=cf.device)
-    cmask = torch.empty((b, 1, h, w), dtype=torch.float32, device=cf.device)
+    cf = _contig(c_feats)
+    vt = _contig(v_t)
+    va = _contig(v_aligned)
+    out = _empty((b, 2 * c + 1, h, w), dtype=torch.float32, device=cf.device)
+    cmask = _empty((b, 1, h, w), dtype=torch.float32, device=cf.device)
     lib = _lib.load()
     ws = scratch(cf, "cm", int(lib.mt_cm_workspace_bytes(b, c, f, h, w)))
     _lib.call("mt_cm_match_fwd", _ptr(cf), _ptr(vt), _ptr(va), _ptr(out), _ptr(cmask), _ptr(ws),
@@ -365,7 +394,7 @@ def chn_pack(x_t, v_t, x_al, v_al, v_map):
     xa, xa_sb, xa_sc, xa_sf = _s5(x_al)
     va, va_sb, _, va_sf = _s5(v_al)
     vm, vm_sb, _, vm_sf = _s5(v_map)
-    out = torch.empty((b * f, 9, h, w), dtype=torch.float32, device=xa.device)
+    out = _empty((b * f, 9, h, w), dtype=torch.float32, device=xa.device)
     _lib.call("mt_chn_pack", _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0), _ptr(xa),
               xa_sb, xa_sc, xa_sf, _ptr(va), va_sb, va_sf, _ptr(vm), vm_sb, vm_sf, _ptr(out), b, f,
               h * w, _stream(xa))
@@ -379,7 +408,7 @@ class ChnCompositeFn(torch.autograd.Function):
     def forward(ctx, nn_out, x_t, v_t, b, f):
         _need_cuda(nn_out, x_t, v_t)
         h, w = nn_out.shape[-2:]
-        no = nn_out.contiguous()
+        no = _contig(nn_out)
         xt, vt = _planes(x_t), _planes(v_t)
         yh_mem, yh = _frame_major(b, 3, f, h, w, no)
         yc_mem, yc = _frame_major(b, 3, f, h, w, no)
@@ -395,16 +424,23 @@ class ChnCompositeFn(torch.autograd.Function):
         b, f, h, w = ctx.meta
         if not ctx.needs_input_grad[0]:
             return None, None, None, None, None
-        gy = gc = None
-        gy_s = gc_s = (0, 0, 0)
-        if g_yh is not None:
-            gy, *gy_s = _s5(g_yh)
-        if g_yc is not None:
-            gc, *gc_s = _s5(g_yc)
-        g = torch.empty_like(no)
-        _lib.call("mt_chn_composite_bwd", _ptr(no), _ptr(vt), vt.stride(0), _ptr(gy), *gy_s, _ptr(gc),
-                  *gc_s, _ptr(g), b, f, h * w, _stream(no))
-        return g, None, None, None, None
+        return chn_composite_bwd_raw(no, vt, g_yh, g_yc, b, f), None, None, None, None
+
+
+def chn_composite_bwd_raw(nn_out, v_t, g_yh, g_yc, b, f):
+    """mt_chn_composite_bwd: gradient w.r.t. the CNN output from the grads of both outputs."""
+    h, w = nn_out.shape[-2:]
+    no, vt = _contig(nn_out), _planes(v_t)
+    gy = gc = None
+    gy_s = gc_s = (0, 0, 0)
+    if g_yh is not None:
+        gy, *gy_s = _s5(g_yh)
+    if g_yc is not None:
+        gc, *gc_s = _s5(g_yc)
+    g = _empty_like(no)
+    _lib.call("mt_chn_composite_bwd", _ptr(no), _ptr(vt), vt.stride(0), _ptr(gy), *gy_s, _ptr(gc),
+              *gc_s, _ptr(g), b, f, h * w, _stream(no))
+    return g
 
 
 def chn_composite(nn_out, x_t, v_t, b, f):
@@ -417,9 +453,9 @@ def hole_update(m_t, v_map0, y_comp0):
     b = m_t.shape[0]
     h, w = m_t.shape[-2:]
     mt, vm, yc = _planes(m_t), _planes(v_map0), _planes(y_comp0)
-    m_new = torch.empty((b, 1, h, w), dtype=torch.float32, device=mt.device)
-    x_new = torch.empty((b, 3, h, w), dtype=torch.float32, device=mt.device)
-    per = torch.empty(1, dtype=torch.float32, device=mt.device)
+    m_new = _empty((b, 1, h, w), dtype=torch.float32, device=mt.device)
+    x_new = _empty((b, 3, h, w), dtype=torch.float32, device=mt.device)
+    per = _empty(1, dtype=torch.float32, device=mt.device)
     _lib.call("mt_hole_update", _ptr(mt), mt.stride(0), _ptr(vm), vm.stride(0), _ptr(yc), yc.stride(0),
               yc.stride(1), _ptr(m_new), _ptr(x_new), _ptr(per), _ptr(reduce_workspace(mt)), b, h * w,
               _stream(mt))
@@ -433,7 +469,7 @@ def trivial_copy(x_t, x_al, v_map):
     xt = _planes(x_t)
     xa, xa_sb, xa_sc, xa_sf = _s5(x_al)
     vm, vm_sb, _, vm_sf = _s5(v_map)
-    y = torch.empty((b, 3, f, h, w), dtype=torch.float32, device=xa.device)
+    y = _empty((b, 3, f, h, w), dtype=torch.float32, device=xa.device)
     _lib.call("mt_trivial_copy", _ptr(xt), xt.stride(0), xt.stride(1), _ptr(xa), xa_sb, xa_sc, xa_sf,
               _ptr(vm), vm_sb, vm_sf, _ptr(y), b, f, h * w, _stream(xa))
     return y

@@ -176,3 +176,22 @@ def test_two_rank_sharding_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_recorded_plan_owns_its_buffers():
+    """Buffers allocated by the operators while recording must stay alive with the Plan:
+    torch.cuda.graph() empties the allocator cache, which unmapped freed temporaries that a
+    plan still wrote to (an illegal address in bench.py's cfg5)."""
+    import weakref
+    t = torch.zeros(4)
+    assert _lib.keep(t) is t                      # no-op outside a recording
+    with _lib.record() as plan:
+        a = ops._empty(8)
+        b = ops._contig(torch.zeros(4, 4).t())    # non-contiguous: a copy is made and kept
+        c = ops._contig(torch.zeros(4))           # already contiguous: nothing to keep
+    refs = [weakref.ref(a), weakref.ref(b)]
+    assert len(plan.keep) == 2 and plan.keep[0] is a and plan.keep[1] is b and c is not None
+    del a, b
+    assert all(r() is not None for r in refs)     # the plan keeps them alive
+    del plan
+    assert all(r() is None for r in refs)
