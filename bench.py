@@ -27,6 +27,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+OUT = None
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -489,7 +492,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    OUT.emit(json.dumps(line))
     return 0
 
 
@@ -637,7 +640,7 @@ def run_gpu(args):
             "sample": "%s at batch_size=%d: %d reps of %.3f s (torch %s CPU port of the reference "
                       "call sequence)" % (wl.name, sample.b, reps, mean, torch.__version__)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        OUT.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -704,6 +707,20 @@ def run_e2e(args, wl, mtb, ops, host, dev, world):
             "api": "master_thesis_b200 plug-point mirrors on pinned host tensors, 2 pipelined streams"}
 
 
+class _RealStdout(object):
+    """Keeps stdout clean: fd 1 is pointed at stderr for the whole run (NCCL / libraries print
+    banners on it) and the single JSON line is written to the saved, real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.fd, (line + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -718,14 +735,16 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="issue every step as individual C-ABI calls instead of a CUDA graph replay")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    if args.gpus > 1 and "RANK" not in os.environ:
+    if args.gpus > 1 and "RANK" not in os.environ and args.impl != "reference":
         # convenience: re-launch under torchrun (the driver launches torchrun itself)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
                "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    global OUT
+    OUT = _RealStdout()
+    if args.impl == "reference":
+        return run_reference(args)
     return run_gpu(args)
 
 
