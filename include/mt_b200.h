@@ -57,6 +57,10 @@ typedef void *mt_stream_t; /* cudaStream_t */
 
 MT_API int mt_version(void);
 MT_API const char *mt_last_error(void);
+/* developer knob (tests, sweeps): overrides one of the MT_* tuning variables the library
+   otherwise reads once from the environment, e.g. ("MT_WARP_STAGED", 0) selects the
+   direct-gather warp kernel.  Never changes results, only which kernel variant runs. */
+MT_API int mt_set_tuning(const char *name, int value);
 /* sm count and compute capability of the current device */
 MT_API int mt_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* bytes of zero-initialised device workspace the reducing kernels need; the

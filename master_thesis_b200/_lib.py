@@ -12,7 +12,8 @@ import re
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 HEADER = os.path.join(ROOT, "include", "mt_b200.h")
-LIB_PATH = os.path.join(HERE, "libmt_b200.so")
+# MT_B200_LIB: developer knob for tuning sweeps (another build of the SAME library, see build.py)
+LIB_PATH = os.environ.get("MT_B200_LIB") or os.path.join(HERE, "libmt_b200.so")
 
 _CTYPES = {
     "int": ctypes.c_int,

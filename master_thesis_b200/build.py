@@ -47,13 +47,16 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    if not force and not needs_build():
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """defines / out: developer knobs for tuning sweeps (e.g. -DMT_WARP_MINB=8 into another
+    file name, selected at run time with MT_B200_LIB); the product build uses neither."""
+    if not force and not needs_build() and not defines and out is None:
         return LIB
     cmd = [find_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    cmd += ["-D" + d for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB] + sources()
+    cmd += ["-o", out or LIB] + sources()
     # the image exports CC=/opt/gcc/bin/gcc (a bare wrapper); let nvcc use the system g++
     env = dict(os.environ)
     env.pop("CC", None)
@@ -63,8 +66,11 @@ def build_library(force=False, verbose=False):
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed (%d): %s" % (res.returncode, " ".join(cmd)))
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[len("--out="):] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv,
+                        defines=defs, out=outs[0] if outs else None))

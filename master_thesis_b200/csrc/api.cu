@@ -44,16 +44,31 @@ int sm_count() {
 
 bool pdl_enabled() { return tuning("MT_PDL", 1) != 0; }
 
+namespace {
+struct TuningEntry { char name[32]; int value; };
+TuningEntry g_tuning[32];
+int g_tuning_used = 0;
+}  // namespace
+
 int tuning(const char *name, int dflt) {
-    struct Entry { const char *name; int value; };
-    static Entry cache[16];
-    static int used = 0;
-    for (int i = 0; i < used; ++i)
-        if (strcmp(cache[i].name, name) == 0) return cache[i].value;
+    for (int i = 0; i < g_tuning_used; ++i)
+        if (strcmp(g_tuning[i].name, name) == 0) return g_tuning[i].value;
     const char *e = getenv(name);
     const int v = e ? atoi(e) : dflt;
-    if (used < 16) cache[used++] = Entry{name, v};
+    if (g_tuning_used < 32 && strlen(name) < sizeof(g_tuning[0].name)) {
+        strcpy(g_tuning[g_tuning_used].name, name);
+        g_tuning[g_tuning_used++].value = v;
+    }
     return v;
+}
+
+int set_tuning(const char *name, int value) {
+    for (int i = 0; i < g_tuning_used; ++i)
+        if (strcmp(g_tuning[i].name, name) == 0) { g_tuning[i].value = value; return MT_OK; }
+    if (g_tuning_used >= 32 || strlen(name) >= sizeof(g_tuning[0].name)) return MT_ERR_INVALID;
+    strcpy(g_tuning[g_tuning_used].name, name);
+    g_tuning[g_tuning_used++].value = value;
+    return MT_OK;
 }
 
 }  // namespace mt
@@ -61,6 +76,12 @@ int tuning(const char *name, int dflt) {
 using namespace mt;
 
 extern "C" int mt_version(void) { return 100; }
+extern "C" int mt_set_tuning(const char *name, int value) {
+    MT_REQUIRE(name && name[0], "mt_set_tuning: empty name");
+    int rc = mt::set_tuning(name, value);
+    if (rc) set_error("mt_set_tuning: table full or name too long (%s)", name);
+    return rc;
+}
 extern "C" const char *mt_last_error(void) { return g_err; }
 extern "C" int64_t mt_workspace_bytes(void) { return kWorkspaceBytes; }
 

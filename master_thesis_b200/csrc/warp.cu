@@ -20,98 +20,25 @@
 #include <math.h>
 
 #include "mt_common.cuh"
+#include "warp_common.cuh"
 
 namespace mt {
 namespace {
 
-struct Sampler {
-    float sfx, sfy;      // (W-1)/2 | W/2, (H-1)/2 | H/2   (host-computed in fp32)
-    float wmax, hmax;
-    float stepx, stepy;  // 2/(W-1), 2/(H-1): torch.linspace step for affine grids
-    int W, H;
-    bool ac;
-};
-
-// ATen CPU ComputeLocationBase::unnormalize (pinned operation order: DESIGN.md "bit-exactness")
-__device__ __forceinline__ float unnormalize(float g, float sf, bool ac) {
-    const float t = __fadd_rn(g, 1.0f);
-    return ac ? __fmul_rn(t, sf) : __fmaf_rn(t, sf, -0.5f);
-}
-
-struct Bil {
-    float xw, yn, w, e, n, s, nw, ne, sw, se;
-    bool x0, x1, y0, y1;  // corner column / row inside the frame
-    int o00;              // offset of the (yn, xw) corner (valid only if y0 && x0 ...)
-};
-
-__device__ __forceinline__ Bil bil_params(float ix, float iy, const Sampler &sp) {
-    Bil b;
-    b.xw = floorf(ix);
-    b.yn = floorf(iy);
-    b.w = __fsub_rn(ix, b.xw);
-    b.e = __fsub_rn(1.0f, b.w);
-    b.n = __fsub_rn(iy, b.yn);
-    b.s = __fsub_rn(1.0f, b.n);
-    b.nw = __fmul_rn(b.s, b.e);
-    b.ne = __fmul_rn(b.s, b.w);
-    b.sw = __fmul_rn(b.n, b.e);
-    b.se = __fmul_rn(b.n, b.w);
-    const float xe = b.xw + 1.0f, ys = b.yn + 1.0f;
-    // float-domain bounds tests: NaN / inf / |v| >= 2^31 are out of bounds
-    b.x0 = (b.xw >= 0.0f) && (b.xw <= sp.wmax);
-    b.x1 = (xe >= 0.0f) && (xe <= sp.wmax);
-    b.y0 = (b.yn >= 0.0f) && (b.yn <= sp.hmax);
-    b.y1 = (ys >= 0.0f) && (ys <= sp.hmax);
-    // any in-bounds corner implies |xw|,|yn| small: the int conversion is exact
-    const bool any = (b.x0 || b.x1) && (b.y0 || b.y1);
-    b.o00 = any ? (int)b.yn * sp.W + (int)b.xw : 0;
-    return b;
-}
-
-struct Corners {
-    float nw, ne, sw, se;
-};
-
-__device__ __forceinline__ Corners gather(const float *__restrict__ plane, const Bil &b, int W) {
-    Corners c;
-    c.nw = (b.y0 && b.x0) ? __ldg(plane + b.o00) : 0.0f;
-    c.ne = (b.y0 && b.x1) ? __ldg(plane + b.o00 + 1) : 0.0f;
-    c.sw = (b.y1 && b.x0) ? __ldg(plane + b.o00 + W) : 0.0f;
-    c.se = (b.y1 && b.x1) ? __ldg(plane + b.o00 + W + 1) : 0.0f;
-    return c;
-}
-
-__device__ __forceinline__ float interp(const Corners &c, const Bil &b) {
-    // fma(se_v, se, fma(sw_v, sw, fma(ne_v, ne, nw_v * nw)))  (pinned order)
-    return __fmaf_rn(c.se, b.se, __fmaf_rn(c.sw, b.sw, __fmaf_rn(c.ne, b.ne, __fmul_rn(c.nw, b.nw))));
-}
-
-__device__ __forceinline__ float nearest(const float *__restrict__ plane, float ix, float iy,
-                                         const Sampler &sp, bool from_mask) {
-    const float xr = rintf(ix), yr = rintf(iy);  // half-to-even, like _mm256_round_ps
-    const bool in = (xr >= 0.0f) && (xr <= sp.wmax) && (yr >= 0.0f) && (yr <= sp.hmax);
-    if (!in) return 0.0f;
-    const float v = __ldg(plane + (int)yr * sp.W + (int)xr);
-    return from_mask ? __fsub_rn(1.0f, v) : v;
-}
-
-// torch.linspace(-1, 1, n)[i] (scalar CPU algorithm), scaled for align_corners=False
-// step = 2 / (size - 1) in fp32, computed once on the host (same IEEE division)
-__device__ __forceinline__ float base_coord(int idx, int size, float step, bool ac) {
-    float v;
-    if (size <= 1) {
-        v = -1.0f;
-    } else {
-        v = (idx < size / 2) ? __fadd_rn(-1.0f, __fmul_rn(step, (float)idx))
-                             : __fsub_rn(1.0f, __fmul_rn(step, (float)(size - idx - 1)));
-    }
-    if (!ac) v = __fdiv_rn(__fmul_rn(v, (float)(size - 1)), (float)size);
-    return v;
-}
-
 constexpr int kCols = 128;     // forward kernel: threads per CTA = columns per CTA
 constexpr int kRows = 2;       // forward kernel: rows per thread and iteration (swept on B200: 2 beats 4)
 constexpr int kIters = 1;      // forward kernel: row groups per thread (swept: more groups per thread is slower)
+// Minimum resident CTAs per SM given to ptxas.  This is a SCHEDULING knob, not an occupancy one:
+// with a bare __launch_bounds__(128) ptxas minimises registers (32-40) and does so by sinking the
+// gathers between the interpolation FMAs - 4 dependent batches of ~8 loads per thread instead of
+// all 32 in flight (SASS checked with cuobjdump; profiles/r1_experiments.md).  With a register
+// budget stated, all gathers of a thread are issued before the first use.
+#ifndef MT_WARP_MINB
+#define MT_WARP_MINB 6
+#endif
+#ifndef MT_WARPB_MINB
+#define MT_WARPB_MINB 6
+#endif
 
 // Forward-kernel arguments: every offset is a 32-bit ELEMENT offset (the launcher
 // checks the ranges), because 64-bit stride arithmetic dominated the per-thread
@@ -140,7 +67,7 @@ constexpr int kMaxRowsPerCta = 32;
 // VIS: 1 = nearest (DFPN), 2 = bilinear > 0.5 (CPN).  FULL: x_al, v_al and v_map
 // are all requested (no NULL checks).
 template <int C, int U, int VIS, bool AFFINE, bool FULL>
-__global__ void __launch_bounds__(kCols) warp_fwd_kernel(const WarpFwdArgs a) {
+__global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const WarpFwdArgs a) {
     pdl_sync();
     __shared__ float s_by[kMaxRowsPerCta];
     const int W = a.sp.W, H = a.sp.H;
@@ -374,7 +301,7 @@ struct WarpBwdArgs {
 };
 
 template <int C, int U>
-__global__ void __launch_bounds__(kCols) warp_bwd_grid_kernel(const WarpBwdArgs a) {
+__global__ void __launch_bounds__(kCols, MT_WARPB_MINB) warp_bwd_grid_kernel(const WarpBwdArgs a) {
     pdl_sync();
     const int W = a.sp.W, H = a.sp.H;
     const bool live = (int)(blockIdx.x * kCols + threadIdx.x) < W;
@@ -429,7 +356,7 @@ __device__ __forceinline__ float mask_out_of(float gx, float gy) {
 // grid (col blocks, <= row blocks, frames); a CTA strides over row blocks so that the
 // number of partials stays within the reduction workspace
 template <int U>
-__global__ void __launch_bounds__(kCols) warp_l1_fwd_kernel(const WarpL1Args a) {
+__global__ void __launch_bounds__(kCols, MT_WARPB_MINB) warp_l1_fwd_kernel(const WarpL1Args a) {
     pdl_sync();
     __shared__ float red[2 * 32];
     float acc[2] = {0.0f, 0.0f};  // sum |x_t*M - x_al*M| over 3 channels, sum M
@@ -483,7 +410,7 @@ __global__ void __launch_bounds__(kCols) warp_l1_fwd_kernel(const WarpL1Args a) 
 // d loss / d flow in one pass: recomputes the sampling, never materialises
 // x_aligned or its gradient.
 template <int U>
-__global__ void __launch_bounds__(kCols) warp_l1_bwd_kernel(const WarpL1Args a) {
+__global__ void __launch_bounds__(kCols, MT_WARPB_MINB) warp_l1_bwd_kernel(const WarpL1Args a) {
     pdl_sync();
     const int W = a.sp.W, H = a.sp.H;
     const bool live = (int)(blockIdx.x * kCols + threadIdx.x) < W;
@@ -533,24 +460,18 @@ __global__ void __launch_bounds__(256) mask_out_kernel(const float *__restrict__
     }
 }
 
-Sampler make_sampler(int H, int W, bool ac) {
-    Sampler s;
-    s.sfx = ac ? (float)(W - 1) / 2.0f : (float)W / 2.0f;
-    s.sfy = ac ? (float)(H - 1) / 2.0f : (float)H / 2.0f;
-    s.wmax = (float)(W - 1);
-    s.hmax = (float)(H - 1);
-    s.stepx = W > 1 ? 2.0f / (float)(W - 1) : 0.0f;
-    s.stepy = H > 1 ? 2.0f / (float)(H - 1) : 0.0f;
-    s.W = W;
-    s.H = H;
-    s.ac = ac;
-    return s;
-}
-
 bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
 }  // namespace
 }  // namespace mt
+
+namespace mt {
+int warp_staged_launch(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf, const float *vis,
+                       int64_t vis_sb, int64_t vis_sf, const float *theta, const float *m_target,
+                       int64_t mt_sb, float *x_aligned, int64_t xa_sb, int64_t xa_sc, int64_t xa_sf,
+                       float *v_aligned, float *v_map, int B, int F, int H, int W, bool ac, bool from_mask,
+                       cudaStream_t st);  // warp_tma.cu
+}
 
 using namespace mt;
 
@@ -599,6 +520,13 @@ extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x
     dim3 block(kCols), gridd((W + kCols - 1) / kCols, (H + rows * iters - 1) / (rows * iters), B * F);
     cudaStream_t st = (cudaStream_t)stream;
     const bool full = x_aligned && v_aligned && v_map;
+    if (affine && vis_bil && C == 3 && full) {
+        // CPN.align tail: persistent kernel with TMA-staged reference tiles (warp_tma.cu) when it applies
+        const int rc = warp_staged_launch(x, x_sb, x_sc, x_sf, vis, vis_sb, vis_sf, grid, m_target, mt_sb, x_aligned,
+                                          xa_sb, xa_sc, xa_sf, v_aligned, v_map, B, F, H, W, a.sp.ac, a.from_mask, st);
+        if (rc < 0) return rc;
+        if (rc == 1) return launch_status("mt_warp_fwd");
+    }
 #define MT_WARP_GO(CC, VV, AA, FF)                                                  \
     do {                                                                            \
         if (rows == 2) launch(warp_fwd_kernel<CC, 2, VV, AA, FF>, gridd, block, 0, st, a); \

@@ -1,0 +1,359 @@
+// warp_tma.cu - K1s: the CPN.align tail (affine grid -> bilinear warp of RGB + bilinear
+// visibility > 0.5 + v_map) as a PERSISTENT kernel whose reference tiles are staged in shared
+// memory by TMA.
+//
+// Replaces CPN.align tail, master_thesis/model_cpn.py:75-89 (a3): F.affine_grid (:75-77),
+// F.grid_sample of the frames (:79-83) and of 1 - masks (:84-88), v_maps (:89).
+//
+// Why (evidence in profiles/r1_experiments.md): the direct-gather kernel (warp.cu) peaks near
+// 46 % of HBM peak.  Its CTAs live for one 128 x 2 pixel strip: every CTA pays a dependent
+// chain "theta load -> coordinates -> gathers -> stores" with nothing in flight during the first
+// and last links, all CTAs of a wave are in the same phase, and more loads in flight per thread
+// (ptxas scheduling sweep) or fewer instructions per pixel (row loops) changed nothing.  Here the
+// memory pipeline is decoupled from the arithmetic:
+//   * one CTA per SM, persistent over 32 x 32 output tiles (static round-robin);
+//   * warp 16 = producer: for the tile kStages ahead it evaluates the affine map at the four
+//     corner pixels with EXACTLY the consumers' arithmetic (every step is monotone in the column
+//     and in the row index, so the corners bound the tile's taps), and issues two TMA box loads
+//     (RGB planes: 5-D map, one instruction; mask plane: 4-D map) of kBox x kBox source pixels
+//     into the stage; TMA zero-fills outside the frame = grid_sample's zero padding;
+//   * warps 0..15 = consumers: 2 rows x 32 columns each; coordinates from per-CTA tables of the
+//     linspace base grid (the IEEE division of align_corners=False is paid once per CTA, not per
+//     thread), 16 LDS with immediate offsets per pixel, interpolation in the pinned order,
+//     128 B-coalesced streaming stores.  Full/empty mbarriers per stage; no CTA-wide barrier in
+//     the loop, so the 16 warps drift apart and overlap each other's phases.
+// A tile whose footprint does not fit the box (|theta| far from identity, NaN) is flagged by the
+// producer and its pixels take the direct-gather path of warp.cu inside the same kernel.
+// Results are bit-identical to warp_fwd_kernel: same operations in the same order on the same
+// values (tests/test_gpu_parity.py compares the two paths as well as the oracle).
+#include "mt_common.cuh"
+#include "mt_tma.cuh"
+#include "warp_common.cuh"
+
+namespace mt {
+namespace {
+
+constexpr int kTile = 32;           // output tile: 32 x 32 pixels
+constexpr int kConsWarps = 16;      // 2 rows each
+constexpr int kStagedThreads = (kConsWarps + 1) * 32;
+constexpr int kMaxTable = 1024;     // W, H <= 1024 (tables of the base grid in shared memory)
+
+struct TileDesc {  // written by the producer, read by the consumers after the full barrier
+    int flags;     // bit 0: staged in smem; bit 1: every tap of the tile is inside the frame
+    int bx0, by0;  // frame coordinates of the box origin
+    int b, f, n;   // sample, reference frame, n = b * F + f
+    int tx, ty;
+    float th[6];
+    int pad[2];
+};
+static_assert(sizeof(TileDesc) == 64, "TileDesc is read as four 16 B words");
+
+struct WarpStagedArgs {
+    const float *x, *vis, *theta, *m_target;
+    float *x_al, *v_al, *v_map;
+    int x_sb, x_sc, x_sf, vis_sb, vis_sf, mt_sb, xa_sb, xa_sc, xa_sf;
+    int F, P, tiles_x, tiles_per_frame, n_tiles;
+    int debug;  // MT_WARP_DBG (developer): bit 0 = never stage (every tile takes the direct path)
+    Sampler sp;
+};
+
+template <int BOX, int STAGES>
+constexpr int staged_smem_bytes() {
+    return STAGES * 4 * BOX * BOX * 4 + 2 * kMaxTable * 4 + STAGES * (int)sizeof(TileDesc) + 2 * STAGES * 8 + 128;
+}
+
+__device__ __forceinline__ float unnorm_t(float g, float sf, bool ac) { return unnormalize(g, sf, ac); }
+
+// AC: align_corners; FM: `vis` holds masks (v = 1 - m inside the frame, 0 outside)
+template <int BOX, int STAGES, bool AC, bool FM>
+__global__ void __launch_bounds__(kStagedThreads, 1)
+warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_v,
+                   const WarpStagedArgs a) {
+    constexpr int kPlane = BOX * BOX;
+    constexpr uint32_t kStageBytes = 4u * kPlane * 4u;
+    // 128 B alignment (TMA destination) comes from the declaration: a manual round-up through
+    // uintptr_t makes the compiler lose the shared address space (generic LD/ST instead of LDS/STS)
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float *stage0 = reinterpret_cast<float *>(smem_raw);
+    float *s_bx = stage0 + STAGES * 4 * kPlane;
+    float *s_by = s_bx + kMaxTable;
+    TileDesc *desc = reinterpret_cast<TileDesc *>(s_by + kMaxTable);
+    uint64_t *full = reinterpret_cast<uint64_t *>(desc + STAGES), *empty = full + STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = a.sp.W, H = a.sp.H;
+
+    // ---- on-chip setup: overlaps the tail of the previous kernel (PDL) ----
+    for (int i = threadIdx.x; i < W; i += kStagedThreads) s_bx[i] = base_coord(i, W, a.sp.stepx, AC);
+    for (int i = threadIdx.x; i < H; i += kStagedThreads) s_by[i] = base_coord(i, H, a.sp.stepy, AC);
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(full + s), 1);
+            mbar_init(smem_u32(empty + s), kConsWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_sync();
+
+    const float wmax = a.sp.wmax, hmax = a.sp.hmax;
+
+    if (warp == kConsWarps) {
+        // ===================== producer =====================
+        if (lane == 0) {
+        int cur_n = -1;
+        float th[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int i = 0;
+        for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
+            const int s = i % STAGES;
+            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+            mbar_wait(smem_u32(empty + s), ph ^ 1u);
+            const int n = t / a.tiles_per_frame, r = t - n * a.tiles_per_frame;
+            const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+            if (n != cur_n) {
+                cur_n = n;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) th[j] = __ldg(a.theta + n * 6 + j);
+            }
+            const int b = n / a.F, f = n - b * a.F;
+            const int xs[2] = {tx * kTile, min(tx * kTile + kTile - 1, W - 1)};
+            const int ys[2] = {ty * kTile, min(ty * kTile + kTile - 1, H - 1)};
+            float xlo = 3.0e38f, xhi = -3.0e38f, ylo = 3.0e38f, yhi = -3.0e38f;
+            bool finite = true;
+#pragma unroll
+            for (int cy = 0; cy < 2; ++cy) {
+#pragma unroll
+                for (int cx = 0; cx < 2; ++cx) {
+                    const float bx = s_bx[xs[cx]], by = s_by[ys[cy]];
+                    // identical to the consumers' arithmetic below
+                    const float gx = __fadd_rn(__fmaf_rn(by, th[1], __fmul_rn(bx, th[0])), th[2]);
+                    const float gy = __fadd_rn(__fmaf_rn(by, th[4], __fmul_rn(bx, th[3])), th[5]);
+                    const float xw = floorf(unnorm_t(gx, a.sp.sfx, AC)), yn = floorf(unnorm_t(gy, a.sp.sfy, AC));
+                    finite = finite && (fabsf(xw) <= 1.0e6f) && (fabsf(yn) <= 1.0e6f);  // false for NaN / inf
+                    xlo = fminf(xlo, xw); xhi = fmaxf(xhi, xw);
+                    ylo = fminf(ylo, yn); yhi = fmaxf(yhi, yn);
+                }
+            }
+            // taps span [xlo, xhi + 1] x [ylo, yhi + 1].  TMA needs the innermost start coordinate on a 16 B
+            // boundary (an unaligned one faults with "illegal instruction", tools/tma_probe.cu), so the box
+            // origin is xlo rounded down to a multiple of 4 pixels (two's complement: also for negatives)
+            const int bx0 = finite ? ((int)xlo & ~3) : 0, by0 = finite ? (int)ylo : 0;
+            const bool fits = finite && ((int)xhi + 2 - bx0 <= BOX) && ((int)yhi + 2 - by0 <= BOX) && !(a.debug & 1);
+            const bool inside = fits && xlo >= 0.0f && xhi + 1.0f <= wmax && ylo >= 0.0f && yhi + 1.0f <= hmax;
+            TileDesc d;
+            d.flags = (fits ? 1 : 0) | (inside ? 2 : 0);
+            d.bx0 = bx0;
+            d.by0 = by0;
+            d.b = b; d.f = f; d.n = n; d.tx = tx; d.ty = ty;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) d.th[j] = th[j];
+            d.pad[0] = d.pad[1] = 0;
+            desc[s] = d;
+            if (fits) {
+                float *dst = stage0 + s * 4 * kPlane;
+                const uint32_t bytes = ((a.debug & 2) ? 0u : 3u * kPlane * 4u) + ((a.debug & 4) ? 0u : kPlane * 4u);
+                mbar_expect_tx(smem_u32(full + s), bytes);
+                // x as (W, H, C, F, B): box (BOX, BOX, 3, 1, 1); masks as (W, H, F, B): box (BOX, BOX, 1, 1)
+                if (!(a.debug & 2)) tma_load_5d(smem_u32(dst), &map_x, smem_u32(full + s), d.bx0, d.by0, 0, f, b);
+                if (!(a.debug & 4)) tma_load_4d(smem_u32(dst + 3 * kPlane), &map_v, smem_u32(full + s), d.bx0, d.by0, f, b);
+            } else {
+                mbar_arrive(smem_u32(full + s));
+            }
+        }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    const float wm2 = wmax - 1.0f, hm2 = hmax - 1.0f;
+    int i = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(smem_u32(full + s), ph);
+        const int4 d0 = reinterpret_cast<const int4 *>(desc + s)[0];      // flags, bx0, by0, b
+        const int4 d1 = reinterpret_cast<const int4 *>(desc + s)[1];      // f, n, tx, ty
+        const float4 d2 = reinterpret_cast<const float4 *>(desc + s)[2];  // th0..3
+        const float4 d3 = reinterpret_cast<const float4 *>(desc + s)[3];  // th4, th5
+        const int flags = d0.x, bx0 = d0.y, by0 = d0.z, b = d0.w, f = d1.x, n = d1.y;
+        const int xg = d1.z * kTile + lane, y0 = d1.w * kTile + 2 * warp;
+        const bool live = xg < W;
+        const int x = min(xg, W - 1);
+        const int p0 = y0 * W + x;
+        // target-mask loads first: only needed by the stores at the end
+        float mtv[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) mtv[k] = (live && y0 + k < H) ? __ldcs(a.m_target + (b * a.mt_sb + p0 + k * W)) : 0.0f;
+        const float bx = s_bx[x];
+        const float bxt0 = __fmul_rn(bx, d2.x), bxt3 = __fmul_rn(bx, d2.w);
+        float ix[2], iy[2], xw[2], yn[2], wnw[2], wne[2], wsw[2], wse[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float by = s_by[min(y0 + k, H - 1)];
+            const float gx = __fadd_rn(__fmaf_rn(by, d2.y, bxt0), d2.z);  // fma(by, t1, bx*t0) + t2 (pinned order)
+            const float gy = __fadd_rn(__fmaf_rn(by, d3.x, bxt3), d3.y);
+            ix[k] = unnorm_t(gx, a.sp.sfx, AC);
+            iy[k] = unnorm_t(gy, a.sp.sfy, AC);
+            xw[k] = floorf(ix[k]);
+            yn[k] = floorf(iy[k]);
+            const float w = __fsub_rn(ix[k], xw[k]), e = __fsub_rn(1.0f, w);
+            const float nn = __fsub_rn(iy[k], yn[k]), ss = __fsub_rn(1.0f, nn);
+            wnw[k] = __fmul_rn(ss, e); wne[k] = __fmul_rn(ss, w);
+            wsw[k] = __fmul_rn(nn, e); wse[k] = __fmul_rn(nn, w);
+        }
+        float xa[3][2], va[2];
+        if (flags & 1) {
+            // ---------------- taps from the staged box ----------------
+            const float *st = stage0 + s * 4 * kPlane;
+            float q[4][2][4];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float *p = st + (((int)yn[k] - by0) * BOX + ((int)xw[k] - bx0));
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    q[c][k][0] = p[c * kPlane]; q[c][k][1] = p[c * kPlane + 1];
+                    q[c][k][2] = p[c * kPlane + BOX]; q[c][k][3] = p[c * kPlane + BOX + 1];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(empty + s));
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    xa[c][k] = __fmaf_rn(q[c][k][3], wse[k], __fmaf_rn(q[c][k][2], wsw[k],
+                               __fmaf_rn(q[c][k][1], wne[k], __fmul_rn(q[c][k][0], wnw[k]))));
+                float v00 = q[3][k][0], v01 = q[3][k][1], v10 = q[3][k][2], v11 = q[3][k][3];
+                if (FM) {
+                    v00 = __fsub_rn(1.0f, v00); v01 = __fsub_rn(1.0f, v01);
+                    v10 = __fsub_rn(1.0f, v10); v11 = __fsub_rn(1.0f, v11);
+                    if (!(flags & 2)) {  // border tile: v is zero-padded, not 1 - 0
+                        const float xe = xw[k] + 1.0f, ys = yn[k] + 1.0f;
+                        const bool bx0i = (xw[k] >= 0.0f) && (xw[k] <= wmax), bx1i = (xe >= 0.0f) && (xe <= wmax);
+                        const bool by0i = (yn[k] >= 0.0f) && (yn[k] <= hmax), by1i = (ys >= 0.0f) && (ys <= hmax);
+                        v00 = (by0i && bx0i) ? v00 : 0.0f; v01 = (by0i && bx1i) ? v01 : 0.0f;
+                        v10 = (by1i && bx0i) ? v10 : 0.0f; v11 = (by1i && bx1i) ? v11 : 0.0f;
+                    }
+                }
+                const float vs = __fmaf_rn(v11, wse[k], __fmaf_rn(v10, wsw[k],
+                                 __fmaf_rn(v01, wne[k], __fmul_rn(v00, wnw[k]))));
+                va[k] = vs > 0.5f ? 1.0f : 0.0f;  // strict, model_cpn.py:88
+            }
+        } else {
+            // ---------------- direct gathers (footprint larger than the box) ----------------
+            if (lane == 0) mbar_arrive(smem_u32(empty + s));
+            const float *xp = a.x + (b * a.x_sb + f * a.x_sf);
+            const float *vp = a.vis + (b * a.vis_sb + f * a.vis_sf);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const Bil bl = bil_params(ix[k], iy[k], a.sp);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) xa[c][k] = interp(gather(xp + c * a.x_sc, bl, W), bl);
+                Corners cv = gather(vp, bl, W);
+                if (FM) {
+                    cv.nw = (bl.y0 && bl.x0) ? __fsub_rn(1.0f, cv.nw) : 0.0f;
+                    cv.ne = (bl.y0 && bl.x1) ? __fsub_rn(1.0f, cv.ne) : 0.0f;
+                    cv.sw = (bl.y1 && bl.x0) ? __fsub_rn(1.0f, cv.sw) : 0.0f;
+                    cv.se = (bl.y1 && bl.x1) ? __fsub_rn(1.0f, cv.se) : 0.0f;
+                }
+                va[k] = interp(cv, bl) > 0.5f ? 1.0f : 0.0f;
+            }
+        }
+        (void)wm2; (void)hm2;
+        // ---------------- stores (coalesced, streaming) ----------------
+        if (live) {
+            const int xao = b * a.xa_sb + f * a.xa_sf + p0, np0 = n * a.P + p0;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (y0 + k >= H) break;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) st_stream1(a.x_al + (xao + c * a.xa_sc + k * W), xa[c][k]);
+                st_stream1(a.v_al + (np0 + k * W), va[k]);
+                st_stream1(a.v_map + (np0 + k * W), clamp01(__fsub_rn(va[k], __fsub_rn(1.0f, mtv[k]))));
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// 1 = launched, 0 = not applicable (caller uses the direct-gather kernel), < 0 = error.
+int warp_staged_launch(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf, const float *vis,
+                       int64_t vis_sb, int64_t vis_sf, const float *theta, const float *m_target,
+                       int64_t mt_sb, float *x_aligned, int64_t xa_sb, int64_t xa_sc, int64_t xa_sf,
+                       float *v_aligned, float *v_map, int B, int F, int H, int W, bool ac, bool from_mask,
+                       cudaStream_t st) {
+    if (!tuning("MT_WARP_STAGED", 1)) return 0;
+    if (!(x_aligned && v_aligned && v_map && m_target)) return 0;
+    if (W > kMaxTable || H > kMaxTable) return 0;
+    // TMA: 16 B aligned base, every stride a multiple of 16 B
+    if ((W & 3) || (x_sb & 3) || (x_sc & 3) || (x_sf & 3) || (vis_sb & 3) || (vis_sf & 3)) return 0;
+    if (!aligned16(x) || !aligned16(vis)) return 0;
+    const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile;
+    const int64_t n_tiles = (int64_t)B * F * tiles_x * tiles_y;
+    // tiny problems cannot fill a persistent grid of 148 CTAs x 16 warps: keep the strip kernel
+    if (n_tiles < 2 * (int64_t)sm_count() || n_tiles > (1ll << 30)) return 0;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return 0;
+    const int box = tuning("MT_WARP_BOX", 48) == 40 ? 40 : 48;
+    CUtensorMap map_x, map_v;
+    {
+        cuuint64_t dims[5] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)F, (cuuint64_t)B};
+        cuuint64_t strides[4] = {(cuuint64_t)W * 4, (cuuint64_t)x_sc * 4, (cuuint64_t)x_sf * 4, (cuuint64_t)x_sb * 4};
+        // a stride of 0 bytes (B or F of extent 1 sliced out of a view) is not encodable: any multiple of 16 is fine there
+        for (int i = 1; i < 4; ++i) if (strides[i] == 0) strides[i] = 16;
+        cuuint32_t bx[5] = {(cuuint32_t)box, (cuuint32_t)box, 3, 1, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(x), dims, strides, bx, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 0;  // e.g. strides beyond the encodable range: direct kernel
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)F, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)vis_sf * 4, (cuuint64_t)vis_sb * 4};
+        for (int i = 1; i < 3; ++i) if (strides[i] == 0) strides[i] = 16;
+        cuuint32_t bx[4] = {(cuuint32_t)box, (cuuint32_t)box, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(vis), dims, strides, bx, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 0;
+    }
+    WarpStagedArgs a;
+    a.x = x; a.vis = vis; a.theta = theta; a.m_target = m_target;
+    a.x_al = x_aligned; a.v_al = v_aligned; a.v_map = v_map;
+    a.x_sb = (int)x_sb; a.x_sc = (int)x_sc; a.x_sf = (int)x_sf;
+    a.vis_sb = (int)vis_sb; a.vis_sf = (int)vis_sf; a.mt_sb = (int)mt_sb;
+    a.xa_sb = (int)xa_sb; a.xa_sc = (int)xa_sc; a.xa_sf = (int)xa_sf;
+    a.F = F; a.P = H * W; a.tiles_x = tiles_x; a.tiles_per_frame = tiles_x * tiles_y; a.n_tiles = (int)n_tiles;
+    a.sp = make_sampler(H, W, ac);
+    a.debug = tuning("MT_WARP_DBG", 0);
+    int ctas = sm_count() * tuning("MT_WARP_CTAS_PER_SM", 1);
+    if (ctas > n_tiles) ctas = (int)n_tiles;
+#define MT_STAGED_GO(BOXV, STG, ACV, FMV)                                                            \
+    do {                                                                                             \
+        auto kern = warp_staged_kernel<BOXV, STG, ACV, FMV>;                                         \
+        constexpr int smem = staged_smem_bytes<BOXV, STG>();                                         \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e != cudaSuccess) {                                                                      \
+            set_error("mt_warp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));               \
+            return MT_ERR_CUDA;                                                                      \
+        }                                                                                            \
+        launch(kern, dim3(ctas), dim3(kStagedThreads), (size_t)smem, st, map_x, map_v, a);           \
+    } while (0)
+#define MT_STAGED_PICK(BOXV, STG)                                                 \
+    do {                                                                          \
+        if (ac) { if (from_mask) MT_STAGED_GO(BOXV, STG, true, true); else MT_STAGED_GO(BOXV, STG, true, false); }   \
+        else    { if (from_mask) MT_STAGED_GO(BOXV, STG, false, true); else MT_STAGED_GO(BOXV, STG, false, false); } \
+    } while (0)
+    if (box == 40) MT_STAGED_PICK(40, 6);  // 6 x 25.6 KB
+    else MT_STAGED_PICK(48, 4);            // 4 x 36.9 KB
+#undef MT_STAGED_PICK
+#undef MT_STAGED_GO
+    return 1;
+}
+
+}  // namespace mt

@@ -98,6 +98,61 @@ def test_cpn_align_tail(mtb, name):
     assert np.array_equal(host(vm), g["v_map"])
 
 
+# Sizes that engage the persistent TMA-staged kernel (warp_tma.cu: >= 2 tiles per SM); the
+# golden cases above are small and take the direct-gather kernel.
+STAGED_CASES = {
+    # partial tiles on both axes, moderate thetas: almost every tile staged
+    "rand": dict(seed=71, b=3, f=4, h=200, w=204, sigma=0.1),
+    # large thetas: most footprints exceed the box -> in-kernel direct path, out-of-frame taps
+    "big": dict(seed=72, b=2, f=4, h=224, w=208, sigma=0.6),
+    # near-identity: every tile staged, border tiles exercise the zero-padded visibility
+    "ident": dict(seed=73, b=4, f=2, h=256, w=256, sigma=0.01),
+    # exact half-pixel translations: the soft visibility lands exactly on 0.5 (strict >)
+    "halfpix": dict(seed=74, b=2, f=4, h=192, w=256, sigma=0.0),
+}
+
+
+def _set_tuning(name, value):
+    from master_thesis_b200 import _lib
+    _lib.call("mt_set_tuning", name.encode(), value)
+
+
+@pytest.mark.parametrize("box", [48, 40])
+@pytest.mark.parametrize("name", sorted(STAGED_CASES))
+def test_cpn_align_tail_staged(mtb, name, box):
+    spec = STAGED_CASES[name]
+    x, m, m_t, theta = cases.cpn_inputs(spec)
+    oxa, ova, ovm = oracle.cpn_align_tail(x, m, m_t, theta=theta)
+    try:
+        _set_tuning("MT_WARP_BOX", box)
+        _set_tuning("MT_WARP_STAGED", 1)
+        xa, va, vm = mtb.cpn_align_tail(dev(x), dev(m), dev(m_t), dev(theta))
+        _set_tuning("MT_WARP_STAGED", 0)
+        xd, vd, vmd = mtb.cpn_align_tail(dev(x), dev(m), dev(m_t), dev(theta))
+    finally:
+        _set_tuning("MT_WARP_STAGED", 1)
+        _set_tuning("MT_WARP_BOX", 48)
+    for got, direct, orc in ((xa, xd, oxa), (va, vd, ova), (vm, vmd, ovm)):
+        assert np.array_equal(host(got), orc)           # staged kernel == oracle, bit for bit
+        assert np.array_equal(host(direct), orc)        # direct-gather kernel == oracle
+    b, c, f, h, w = x.shape
+    assert xa.stride() == (f * c * h * w, h * w, c * h * w, w, 1)
+
+
+def test_cpn_align_tail_staged_views(mtb):
+    """Strided inputs (x[:, :, r_list]-style slices of a longer clip) through the TMA maps."""
+    spec = STAGED_CASES["rand"]
+    x, m, m_t, theta = cases.cpn_inputs(spec)
+    b, c, f, h, w = x.shape
+    big = torch.full((b, c, f + 3, h, w), 7.0, device="cuda")
+    big[:, :, 2:f + 2] = dev(x)
+    mbig = torch.full((b, 1, f + 3, h, w), 1.0, device="cuda")
+    mbig[:, :, 2:f + 2] = dev(m)
+    xa, va, vm = mtb.cpn_align_tail(big[:, :, 2:f + 2], mbig[:, :, 2:f + 2], dev(m_t), dev(theta))
+    oxa, ova, ovm = oracle.cpn_align_tail(x, m, m_t, theta=theta)
+    assert np.array_equal(host(xa), oxa) and np.array_equal(host(va), ova) and np.array_equal(host(vm), ovm)
+
+
 class _FakeCPN(object):
     def __init__(self, theta):
         self.theta = theta
