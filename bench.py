@@ -517,7 +517,7 @@ def run_gpu(args):
     import master_thesis_b200 as mtb
     from master_thesis_b200 import _lib, ops
     _lib.load()
-    wl = WORKLOADS[args.workload]()
+    wl = WORKLOADS[args.workload](args.batch) if args.batch > 0 else WORKLOADS[args.workload]()
     calls = wl.calls()
     hbm_peak, tf_peak, peak_src = measured_peaks()
 
@@ -728,6 +728,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0,
+                    help="per-GPU batch size override (scaling experiments; 0 = the config's own)")
     ap.add_argument("--sets", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -16,7 +16,9 @@
 //     corner pixels with EXACTLY the consumers' arithmetic (every step is monotone in the column
 //     and in the row index, so the corners bound the tile's taps), and issues two TMA box loads
 //     (RGB planes: 5-D map, one instruction; mask plane: 4-D map) of kBox x kBox source pixels
-//     into the stage; TMA zero-fills outside the frame = grid_sample's zero padding;
+//     into the stage, plus the 32 x 32 tile of the target mask (v_map needs it; as a per-thread
+//     global load its DRAM latency bounded every warp's time per tile: 24.8 us, no better than
+//     the strip kernel); TMA zero-fills outside the frame = grid_sample's zero padding;
 //   * warps 0..15 = consumers: 2 rows x 32 columns each; coordinates from per-CTA tables of the
 //     linspace base grid (the IEEE division of align_corners=False is paid once per CTA, not per
 //     thread), 16 LDS with immediate offsets per pixel, interpolation in the pinned order,
@@ -48,40 +50,54 @@ struct TileDesc {  // written by the producer, read by the consumers after the f
 };
 static_assert(sizeof(TileDesc) == 64, "TileDesc is read as four 16 B words");
 
+// developer timeline probe (MT_WARP_DBG bit 3): per CTA globaltimer stamps
+// [0] kernel entry, [1] after setup + griddepcontrol.wait, [2] first TMA issued,
+// [3] first full barrier passed (consumer warp 0), [4] consumer warp 0 done, [5] tiles of this CTA
+__device__ unsigned long long g_timeline[256 * 8];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct WarpStagedArgs {
     const float *x, *vis, *theta, *m_target;
     float *x_al, *v_al, *v_map;
     int x_sb, x_sc, x_sf, vis_sb, vis_sf, mt_sb, xa_sb, xa_sc, xa_sf;
     int F, P, tiles_x, tiles_per_frame, n_tiles;
-    int debug;  // MT_WARP_DBG (developer): bit 0 = never stage (every tile takes the direct path)
+    int debug;  // MT_WARP_DBG (developer): bit 0 = never stage (every tile takes the direct path); bit 3 = timeline probe
     Sampler sp;
 };
 
 template <int BOX, int STAGES>
 constexpr int staged_smem_bytes() {
-    return STAGES * 4 * BOX * BOX * 4 + 2 * kMaxTable * 4 + STAGES * (int)sizeof(TileDesc) + 2 * STAGES * 8 + 128;
+    return STAGES * (4 * BOX * BOX + kTile * kTile) * 4 + 2 * kMaxTable * 4 + STAGES * (int)sizeof(TileDesc) +
+           2 * STAGES * 8 + 128;
 }
 
 __device__ __forceinline__ float unnorm_t(float g, float sf, bool ac) { return unnormalize(g, sf, ac); }
 
 // AC: align_corners; FM: `vis` holds masks (v = 1 - m inside the frame, 0 outside)
-template <int BOX, int STAGES, bool AC, bool FM>
-__global__ void __launch_bounds__(kStagedThreads, 1)
+template <int BOX, int STAGES, int CPS, bool AC, bool FM>
+__global__ void __launch_bounds__(kStagedThreads, CPS)
 warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_v,
-                   const WarpStagedArgs a) {
+                   const __grid_constant__ CUtensorMap map_t, const WarpStagedArgs a) {
     constexpr int kPlane = BOX * BOX;
-    constexpr uint32_t kStageBytes = 4u * kPlane * 4u;
+    constexpr int kStageFloats = 4 * kPlane + kTile * kTile;  // RGB + mask boxes, target-mask tile
+    constexpr uint32_t kMtBytes = kTile * kTile * 4u;
     // 128 B alignment (TMA destination) comes from the declaration: a manual round-up through
     // uintptr_t makes the compiler lose the shared address space (generic LD/ST instead of LDS/STS)
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float *stage0 = reinterpret_cast<float *>(smem_raw);
-    float *s_bx = stage0 + STAGES * 4 * kPlane;
+    float *s_bx = stage0 + STAGES * kStageFloats;
     float *s_by = s_bx + kMaxTable;
     TileDesc *desc = reinterpret_cast<TileDesc *>(s_by + kMaxTable);
     uint64_t *full = reinterpret_cast<uint64_t *>(desc + STAGES), *empty = full + STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = a.sp.W, H = a.sp.H;
+    const bool probe = (a.debug & 8) && blockIdx.x < 256;
+    if (probe && threadIdx.x == 0) g_timeline[blockIdx.x * 8 + 0] = gtime();
 
     // ---- on-chip setup: overlaps the tail of the previous kernel (PDL) ----
     for (int i = threadIdx.x; i < W; i += kStagedThreads) s_bx[i] = base_coord(i, W, a.sp.stepx, AC);
@@ -89,6 +105,7 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_t) : "memory");
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(full + s), 1);
             mbar_init(smem_u32(empty + s), kConsWarps);
@@ -97,71 +114,77 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
     __syncthreads();
     pdl_sync();
+    if (probe && threadIdx.x == 0) g_timeline[blockIdx.x * 8 + 1] = gtime();
 
     const float wmax = a.sp.wmax, hmax = a.sp.hmax;
 
     if (warp == kConsWarps) {
         // ===================== producer =====================
         if (lane == 0) {
-        int cur_n = -1;
-        float th[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        int i = 0;
-        for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
-            const int s = i % STAGES;
-            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-            mbar_wait(smem_u32(empty + s), ph ^ 1u);
-            const int n = t / a.tiles_per_frame, r = t - n * a.tiles_per_frame;
-            const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-            if (n != cur_n) {
-                cur_n = n;
+            // The descriptor of a tile (theta load, two integer divisions, four corner evaluations) is
+            // prepared while its stage is still in use: between "stage released" and "TMA issued"
+            // there is only the descriptor store (ncu: consumers polled the full barrier 2.9 times
+            // per tile while this chain sat behind the empty wait).
+            auto prepare = [&](int t) {
+                TileDesc d;
+                const int n = t / a.tiles_per_frame, r = t - n * a.tiles_per_frame;
+                const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
 #pragma unroll
-                for (int j = 0; j < 6; ++j) th[j] = __ldg(a.theta + n * 6 + j);
-            }
-            const int b = n / a.F, f = n - b * a.F;
-            const int xs[2] = {tx * kTile, min(tx * kTile + kTile - 1, W - 1)};
-            const int ys[2] = {ty * kTile, min(ty * kTile + kTile - 1, H - 1)};
-            float xlo = 3.0e38f, xhi = -3.0e38f, ylo = 3.0e38f, yhi = -3.0e38f;
-            bool finite = true;
+                for (int j = 0; j < 6; ++j) d.th[j] = __ldg(a.theta + n * 6 + j);
+                const int b = n / a.F, f = n - b * a.F;
+                const int xs[2] = {tx * kTile, min(tx * kTile + kTile - 1, W - 1)};
+                const int ys[2] = {ty * kTile, min(ty * kTile + kTile - 1, H - 1)};
+                float xlo = 3.0e38f, xhi = -3.0e38f, ylo = 3.0e38f, yhi = -3.0e38f;
+                bool finite = true;
 #pragma unroll
-            for (int cy = 0; cy < 2; ++cy) {
+                for (int cy = 0; cy < 2; ++cy) {
 #pragma unroll
-                for (int cx = 0; cx < 2; ++cx) {
-                    const float bx = s_bx[xs[cx]], by = s_by[ys[cy]];
-                    // identical to the consumers' arithmetic below
-                    const float gx = __fadd_rn(__fmaf_rn(by, th[1], __fmul_rn(bx, th[0])), th[2]);
-                    const float gy = __fadd_rn(__fmaf_rn(by, th[4], __fmul_rn(bx, th[3])), th[5]);
-                    const float xw = floorf(unnorm_t(gx, a.sp.sfx, AC)), yn = floorf(unnorm_t(gy, a.sp.sfy, AC));
-                    finite = finite && (fabsf(xw) <= 1.0e6f) && (fabsf(yn) <= 1.0e6f);  // false for NaN / inf
-                    xlo = fminf(xlo, xw); xhi = fmaxf(xhi, xw);
-                    ylo = fminf(ylo, yn); yhi = fmaxf(yhi, yn);
+                    for (int cx = 0; cx < 2; ++cx) {
+                        const float bx = s_bx[xs[cx]], by = s_by[ys[cy]];
+                        // identical to the consumers' arithmetic below
+                        const float gx = __fadd_rn(__fmaf_rn(by, d.th[1], __fmul_rn(bx, d.th[0])), d.th[2]);
+                        const float gy = __fadd_rn(__fmaf_rn(by, d.th[4], __fmul_rn(bx, d.th[3])), d.th[5]);
+                        const float xw = floorf(unnorm_t(gx, a.sp.sfx, AC)), yn = floorf(unnorm_t(gy, a.sp.sfy, AC));
+                        finite = finite && (fabsf(xw) <= 1.0e6f) && (fabsf(yn) <= 1.0e6f);  // false for NaN / inf
+                        xlo = fminf(xlo, xw); xhi = fmaxf(xhi, xw);
+                        ylo = fminf(ylo, yn); yhi = fmaxf(yhi, yn);
+                    }
                 }
-            }
-            // taps span [xlo, xhi + 1] x [ylo, yhi + 1].  TMA needs the innermost start coordinate on a 16 B
-            // boundary (an unaligned one faults with "illegal instruction", tools/tma_probe.cu), so the box
-            // origin is xlo rounded down to a multiple of 4 pixels (two's complement: also for negatives)
-            const int bx0 = finite ? ((int)xlo & ~3) : 0, by0 = finite ? (int)ylo : 0;
-            const bool fits = finite && ((int)xhi + 2 - bx0 <= BOX) && ((int)yhi + 2 - by0 <= BOX) && !(a.debug & 1);
-            const bool inside = fits && xlo >= 0.0f && xhi + 1.0f <= wmax && ylo >= 0.0f && yhi + 1.0f <= hmax;
+                // taps span [xlo, xhi + 1] x [ylo, yhi + 1].  TMA needs the innermost start coordinate on a
+                // 16 B boundary (an unaligned one faults with "illegal instruction", tools/tma_probe.cu), so
+                // the box origin is xlo rounded down to a multiple of 4 pixels (two's complement: also for
+                // negative coordinates)
+                const int bx0 = finite ? ((int)xlo & ~3) : 0, by0 = finite ? (int)ylo : 0;
+                const bool fits = finite && ((int)xhi + 2 - bx0 <= BOX) && ((int)yhi + 2 - by0 <= BOX) && !(a.debug & 1);
+                const bool inside = fits && xlo >= 0.0f && xhi + 1.0f <= wmax && ylo >= 0.0f && yhi + 1.0f <= hmax;
+                d.flags = (fits ? 1 : 0) | (inside ? 2 : 0);
+                d.bx0 = bx0; d.by0 = by0;
+                d.b = b; d.f = f; d.n = n; d.tx = tx; d.ty = ty;
+                d.pad[0] = d.pad[1] = 0;
+                return d;
+            };
+            int t = blockIdx.x;
             TileDesc d;
-            d.flags = (fits ? 1 : 0) | (inside ? 2 : 0);
-            d.bx0 = bx0;
-            d.by0 = by0;
-            d.b = b; d.f = f; d.n = n; d.tx = tx; d.ty = ty;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) d.th[j] = th[j];
-            d.pad[0] = d.pad[1] = 0;
-            desc[s] = d;
-            if (fits) {
-                float *dst = stage0 + s * 4 * kPlane;
-                const uint32_t bytes = ((a.debug & 2) ? 0u : 3u * kPlane * 4u) + ((a.debug & 4) ? 0u : kPlane * 4u);
-                mbar_expect_tx(smem_u32(full + s), bytes);
-                // x as (W, H, C, F, B): box (BOX, BOX, 3, 1, 1); masks as (W, H, F, B): box (BOX, BOX, 1, 1)
-                if (!(a.debug & 2)) tma_load_5d(smem_u32(dst), &map_x, smem_u32(full + s), d.bx0, d.by0, 0, f, b);
-                if (!(a.debug & 4)) tma_load_4d(smem_u32(dst + 3 * kPlane), &map_v, smem_u32(full + s), d.bx0, d.by0, f, b);
-            } else {
-                mbar_arrive(smem_u32(full + s));
+            if (t < a.n_tiles) d = prepare(t);
+            for (int i = 0; t < a.n_tiles; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                mbar_wait(smem_u32(empty + s), ph ^ 1u);
+                desc[s] = d;
+                const bool fits = (d.flags & 1) != 0;
+                float *dst = stage0 + s * kStageFloats;
+                mbar_expect_tx(smem_u32(full + s), fits ? 4u * kPlane * 4u + kMtBytes : kMtBytes);
+                if (fits) {
+                    // x as (W, H, C, F, B): box (BOX, BOX, 3, 1, 1); masks as (W, H, F, B): box (BOX, BOX, 1, 1)
+                    tma_load_5d(smem_u32(dst), &map_x, smem_u32(full + s), d.bx0, d.by0, 0, d.f, d.b);
+                    tma_load_4d(smem_u32(dst + 3 * kPlane), &map_v, smem_u32(full + s), d.bx0, d.by0, d.f, d.b);
+                }
+                // target mask as (W, H, B): the tile itself
+                tma_load_3d(smem_u32(dst + 4 * kPlane), &map_t, smem_u32(full + s), d.tx * kTile, d.ty * kTile, d.b);
+                if (probe && i == 0) g_timeline[blockIdx.x * 8 + 2] = gtime();
+                t += gridDim.x;
+                if (t < a.n_tiles) d = prepare(t);
             }
-        }
         }
         return;
     }
@@ -173,6 +196,7 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         mbar_wait(smem_u32(full + s), ph);
+        if (probe && i == 0 && threadIdx.x == 0) g_timeline[blockIdx.x * 8 + 3] = gtime();
         const int4 d0 = reinterpret_cast<const int4 *>(desc + s)[0];      // flags, bx0, by0, b
         const int4 d1 = reinterpret_cast<const int4 *>(desc + s)[1];      // f, n, tx, ty
         const float4 d2 = reinterpret_cast<const float4 *>(desc + s)[2];  // th0..3
@@ -182,10 +206,10 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const bool live = xg < W;
         const int x = min(xg, W - 1);
         const int p0 = y0 * W + x;
-        // target-mask loads first: only needed by the stores at the end
+        const float *st = stage0 + s * kStageFloats;
         float mtv[2];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) mtv[k] = (live && y0 + k < H) ? __ldcs(a.m_target + (b * a.mt_sb + p0 + k * W)) : 0.0f;
+        for (int k = 0; k < 2; ++k) mtv[k] = st[4 * kPlane + (2 * warp + k) * kTile + lane];
         const float bx = s_bx[x];
         const float bxt0 = __fmul_rn(bx, d2.x), bxt3 = __fmul_rn(bx, d2.w);
         float ix[2], iy[2], xw[2], yn[2], wnw[2], wne[2], wsw[2], wse[2];
@@ -206,7 +230,6 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         float xa[3][2], va[2];
         if (flags & 1) {
             // ---------------- taps from the staged box ----------------
-            const float *st = stage0 + s * 4 * kPlane;
             float q[4][2][4];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
@@ -243,6 +266,7 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             }
         } else {
             // ---------------- direct gathers (footprint larger than the box) ----------------
+            __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(empty + s));
             const float *xp = a.x + (b * a.x_sb + f * a.x_sf);
             const float *vp = a.vis + (b * a.vis_sb + f * a.vis_sf);
@@ -275,6 +299,10 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             }
         }
     }
+    if (probe && threadIdx.x == 0) {
+        g_timeline[blockIdx.x * 8 + 4] = gtime();
+        g_timeline[blockIdx.x * 8 + 5] = (unsigned long long)i;
+    }
 }
 
 }  // namespace
@@ -290,7 +318,7 @@ int warp_staged_launch(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
     if (W > kMaxTable || H > kMaxTable) return 0;
     // TMA: 16 B aligned base, every stride a multiple of 16 B
     if ((W & 3) || (x_sb & 3) || (x_sc & 3) || (x_sf & 3) || (vis_sb & 3) || (vis_sf & 3)) return 0;
-    if (!aligned16(x) || !aligned16(vis)) return 0;
+    if (!aligned16(x) || !aligned16(vis) || !aligned16(m_target) || (mt_sb & 3)) return 0;
     const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile;
     const int64_t n_tiles = (int64_t)B * F * tiles_x * tiles_y;
     // tiny problems cannot fill a persistent grid of 148 CTAs x 16 warps: keep the strip kernel
@@ -298,7 +326,17 @@ int warp_staged_launch(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
     EncodeTiledFn enc = encode_fn();
     if (!enc) return 0;
     const int box = tuning("MT_WARP_BOX", 48) == 40 ? 40 : 48;
-    CUtensorMap map_x, map_v;
+    CUtensorMap map_x, map_v, map_t;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[2] = {(cuuint64_t)W * 4, mt_sb ? (cuuint64_t)mt_sb * 4 : 16};
+        cuuint32_t bx[3] = {(cuuint32_t)kTile, (cuuint32_t)kTile, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&map_t, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(m_target), dims, strides, bx,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 0;
+    }
     {
         cuuint64_t dims[5] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)F, (cuuint64_t)B};
         cuuint64_t strides[4] = {(cuuint64_t)W * 4, (cuuint64_t)x_sc * 4, (cuuint64_t)x_sf * 4, (cuuint64_t)x_sb * 4};
@@ -331,29 +369,38 @@ int warp_staged_launch(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
     a.F = F; a.P = H * W; a.tiles_x = tiles_x; a.tiles_per_frame = tiles_x * tiles_y; a.n_tiles = (int)n_tiles;
     a.sp = make_sampler(H, W, ac);
     a.debug = tuning("MT_WARP_DBG", 0);
-    int ctas = sm_count() * tuning("MT_WARP_CTAS_PER_SM", 1);
+    const int cps = tuning("MT_WARP_CTAS_PER_SM", 1) == 2 ? 2 : 1;
+    int ctas = sm_count() * cps;
     if (ctas > n_tiles) ctas = (int)n_tiles;
-#define MT_STAGED_GO(BOXV, STG, ACV, FMV)                                                            \
+#define MT_STAGED_GO(BOXV, STG, CPSV, ACV, FMV)                                                      \
     do {                                                                                             \
-        auto kern = warp_staged_kernel<BOXV, STG, ACV, FMV>;                                         \
+        auto kern = warp_staged_kernel<BOXV, STG, CPSV, ACV, FMV>;                                   \
         constexpr int smem = staged_smem_bytes<BOXV, STG>();                                         \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
         if (e != cudaSuccess) {                                                                      \
             set_error("mt_warp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));               \
             return MT_ERR_CUDA;                                                                      \
         }                                                                                            \
-        launch(kern, dim3(ctas), dim3(kStagedThreads), (size_t)smem, st, map_x, map_v, a);           \
+        launch(kern, dim3(ctas), dim3(kStagedThreads), (size_t)smem, st, map_x, map_v, map_t, a);           \
     } while (0)
-#define MT_STAGED_PICK(BOXV, STG)                                                 \
+#define MT_STAGED_PICK(BOXV, STG, CPSV)                                           \
     do {                                                                          \
-        if (ac) { if (from_mask) MT_STAGED_GO(BOXV, STG, true, true); else MT_STAGED_GO(BOXV, STG, true, false); }   \
-        else    { if (from_mask) MT_STAGED_GO(BOXV, STG, false, true); else MT_STAGED_GO(BOXV, STG, false, false); } \
+        if (ac) { if (from_mask) MT_STAGED_GO(BOXV, STG, CPSV, true, true); else MT_STAGED_GO(BOXV, STG, CPSV, true, false); }   \
+        else    { if (from_mask) MT_STAGED_GO(BOXV, STG, CPSV, false, true); else MT_STAGED_GO(BOXV, STG, CPSV, false, false); } \
     } while (0)
-    if (box == 40) MT_STAGED_PICK(40, 6);  // 6 x 25.6 KB
-    else MT_STAGED_PICK(48, 4);            // 4 x 36.9 KB
+    // shared memory per SM: 227 KB; stage = 4 boxes + the 4 KB target-mask tile
+    if (cps == 1) { if (box == 40) MT_STAGED_PICK(40, 7, 1); else MT_STAGED_PICK(48, 5, 1); }  // 7 x 29.0 / 5 x 40.0 KB
+    else          { if (box == 40) MT_STAGED_PICK(40, 3, 2); else MT_STAGED_PICK(48, 2, 2); }  // 2 x (3 x 29.0 / 2 x 40.0) KB
 #undef MT_STAGED_PICK
 #undef MT_STAGED_GO
     return 1;
 }
 
 }  // namespace mt
+
+// developer probe (not part of include/mt_b200.h): copies the timeline stamps to the host
+extern "C" __attribute__((visibility("default"))) int mt_debug_warp_timeline(unsigned long long *dst, int n) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(dst, mt::g_timeline, sizeof(unsigned long long) * (n < 2048 ? n : 2048)) == cudaSuccess
+               ? 0 : -2;
+}
