@@ -22,6 +22,7 @@
 #include <math.h>
 
 #include "mt_common.cuh"
+#include "mt_tma.cuh"
 
 namespace mt {
 namespace {
@@ -38,6 +39,12 @@ struct CmArgs {
     float *gs;        // workspace: (B, R)  (exported for tests)
     float *weights;   // workspace: (B, R, P) softmax weights over references
     int B, C, f, h, w, H, W, P, R, nparts, chunks, sim_ch, b_off;
+    // fused path: per-sample count of finished similarity items (zeroed by cm_masks), items per
+    // sample and pass, and the distance (in samples) between pass 1 and pass 2 of the same sample
+    unsigned int *count, *flag;  // (B) finished S items / table published
+    unsigned char *pmask;        // (B, P) bit 0: vt', bit r + 1: vr' of reference r
+    float *table;                // (B, 2^R, R + 1) softmax weights and c_mask per mask pattern
+    int n_items, lag;
 };
 
 // F.interpolate(bilinear, align_corners=False) source index (UpSample.h)
@@ -51,24 +58,37 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
     l0 = __fsub_rn(1.0f, l1);
 }
 
+// pass 0: grid (ceil(P / 256), B); thread = one low-resolution pixel, all f masks.
+// Also resets the per-sample state of the pipelined kernel (count, flag, table = NaN).
 __global__ void __launch_bounds__(256) cm_masks_kernel(const CmArgs a) {
     pdl_sync();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y, b = blockIdx.z;  // j = 0: target, j >= 1: reference j-1
+    const int b = blockIdx.y;
+    if (blockIdx.x == 0) {
+        const int tabf = (1 << a.R) * (a.R + 1);
+        for (int q = threadIdx.x; q < tabf; q += blockDim.x) a.table[(int64_t)b * tabf + q] = __int_as_float(0x7fc00000);
+        if (threadIdx.x == 0) { a.count[b] = 0u; a.flag[b] = 0u; }
+    }
     if (p >= a.P) return;
-    const float *src = (j == 0) ? a.v_t + (int64_t)b * a.H * a.W
-                                : a.v_al + ((int64_t)b * a.R + (j - 1)) * a.H * a.W;
     const int y = p / a.w, x = p - y * a.w;
     int y0, y1, x0, x1;
     float ly0, ly1, lx0, lx1;
     src_index(y, __fdiv_rn((float)a.H, (float)a.h), a.H, y0, y1, ly0, ly1);
     src_index(x, __fdiv_rn((float)a.W, (float)a.w), a.W, x0, x1, lx0, lx1);
-    const float v00 = __ldg(src + y0 * a.W + x0), v01 = __ldg(src + y0 * a.W + x1);
-    const float v10 = __ldg(src + y1 * a.W + x0), v11 = __ldg(src + y1 * a.W + x1);
-    const float top = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
-    const float bot = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
-    const float val = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
-    a.masks[((int64_t)b * a.f + j) * a.P + p] = val > 0.5f ? 1.0f : 0.0f;  // model_cpn.py:208-217
+    unsigned int bits = 0u;
+    for (int j = 0; j < a.f; ++j) {  // j = 0: target, j >= 1: reference j - 1
+        const float *src = (j == 0) ? a.v_t + (int64_t)b * a.H * a.W
+                                    : a.v_al + ((int64_t)b * a.R + (j - 1)) * a.H * a.W;
+        const float v00 = __ldg(src + y0 * a.W + x0), v01 = __ldg(src + y0 * a.W + x1);
+        const float v10 = __ldg(src + y1 * a.W + x0), v11 = __ldg(src + y1 * a.W + x1);
+        const float top = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
+        const float bot = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
+        const float val = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+        const bool on = val > 0.5f;                                            // model_cpn.py:208-217
+        a.masks[((int64_t)b * a.f + j) * a.P + p] = on ? 1.0f : 0.0f;
+        bits |= on ? (1u << j) : 0u;
+    }
+    a.pmask[(int64_t)b * a.P + p] = (unsigned char)bits;
 }
 
 // gs[b, :] from the partials of sample b (fixed order, double).  Result in smem gs[R].
@@ -265,11 +285,485 @@ __global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K3p: pass 1 + 1b + 2 as ONE persistent, software-pipelined launch; pass 2 reads c_feats from L2.
+//
+// The two passes over c_feats are inherent (the similarity is a global reduction over the sample),
+// but as separate launches over the whole batch the second pass misses L2 (ncu: 4.6 % hit rate at
+// B=8, 84 MB) and the op moves 84+10+84+34 MB through HBM for 128 MB algorithmic.  Here one CTA
+// per SM walks a static, ordered item list
+//     S(0) | S(1) C(0) interleaved | S(2) C(1) | ... | C(B-1)
+// (S = similarity partial of a 1024-pixel x CH-channel slab, C = weighted copy of such a slab), so
+// a sample (10.5 MB) is re-read one sample later, while it is L2-resident: HBM traffic =
+// algorithmic traffic.
+//   * Memory pipeline: the operands of item i+NST-1 are fetched with cp.async (16 B per thread and
+//     slot, thread-private slots => conflict-free LDS.128, no barrier for the data) into an NST-deep
+//     shared-memory ring while item i is computed.  A first version without the ring (loads into
+//     registers, 2-3 CTAs/SM) ran 60-77 us against 48 us for the three launches: every item
+//     exposed a DRAM round trip plus, for C items, the chain poll -> fold -> table.
+//   * Masks travel as one byte per pixel (bit 0 target, bit r+1 reference r; cm_masks_kernel):
+//     4 B per thread and item instead of 80 B.
+//   * vr' is 0/1, so the masked softmax over the references has only 2^R distinct results per
+//     sample.  The CTA that finishes the LAST S item of a sample (per-sample counter) folds the
+//     partials in fixed order in double, evaluates the softmax once per mask pattern (the same
+//     operations in the same order as cm_weights_kernel: same bits) and publishes that table; C
+//     items prefetch the table with their operands and look weights up per pixel - no weights array
+//     in HBM, no per-pixel expf / division, and normally no wait: the table was cleared to NaN by
+//     cm_masks_kernel, a prefetched copy without NaN is complete (every word is written once);
+//     otherwise the CTA waits for the sample's flag (acquire) and reloads.
+// Progress: items are taken in order (item i -> CTA i mod grid), S items never wait, a C item
+// waits only for S items that are earlier in the list, and the grid is one resident wave.  A wait
+// that does not end within 2 s traps (the launch fails loudly instead of hanging).
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// named barrier 1 = the 256 compute threads of cm_pipe_kernel (the publisher warp never joins)
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ bool bar_compute_or(bool p) {
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred pin, pout;\n\tsetp.ne.u32 pin, %1, 0;\n\tbar.red.or.pred pout, 1, 256, pin;\n\t"
+        "selp.u32 %0, 1, 0, pout;\n\t}"
+        : "=r"(r) : "r"((int)p) : "memory");
+    return r != 0;
+}
+// block_sum over the 8 compute warps (result valid in thread 0)
+template <int K>
+__device__ __forceinline__ void compute_sum(float (&v)[K], float *smem) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        v[k] = warp_sum(v[k]);
+        if (lane == 0) smem[k * 32 + wid] = v[k];
+    }
+    bar_compute();
+    if (wid == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float t = lane < 8 ? smem[k * 32 + lane] : 0.0f;
+            v[k] = warp_sum(t);
+        }
+    }
+}
+constexpr int kCmThreads = 320;  // 8 compute warps + publisher warp + producer warp
+constexpr int kMailbox = 16;
+
+template <int R>
+constexpr int cm_table_floats() { return (1 << R) * (R + 1); }  // per pattern: R weights, c_mask
+
+struct CmItem { int b, idx; bool copy, valid; };
+
+#ifdef MT_DEV_PROBES
+// developer probe (tools/dbg_cm.py): per CTA [0] kernel ns, [1] ns waiting for cp.async data, [2] ns in S
+// items, [3] ns in C items, [4] C items through the slow path, [5] items, [6] publisher busy ns, [7] publishes
+__device__ unsigned long long g_cm_probe[256 * 8];
+__device__ unsigned long long g_cm_probe2[256 * 8];  // [0] slow items whose flag was already set, [1] ns in the slow path, [2] ns in decode
+#define CM_PROBE(...) __VA_ARGS__
+#else
+#define CM_PROBE(...)
+#endif
+
+__device__ __forceinline__ CmItem cm_decode(const CmArgs &a, int it) {
+    const int nI = a.n_items, L = a.lag;
+    const int n_head = L * nI, n_mid = (a.B - L) * 2 * nI, total = 2 * a.B * nI;
+    CmItem d;
+    d.valid = it < total;
+    if (it < n_head) {
+        d.b = it / nI; d.idx = it - d.b * nI; d.copy = false;
+    } else if (it < n_head + n_mid) {
+        const int i2 = it - n_head, ph = i2 / (2 * nI), j = i2 - ph * 2 * nI;
+        // S and C alternate along the list; with an even grid a CTA would only ever see one parity
+        // (all copies on the odd CTAs: measured, 2x slower), so the order of a pair flips every
+        // grid / 2 pairs and every CTA alternates between S and C items
+        const int g = (int)gridDim.x, flip = (g & 1) ? 0 : (((j >> 1) / (g >> 1)) & 1);
+        d.copy = ((j & 1) ^ flip) != 0; d.idx = j >> 1;
+        d.b = d.copy ? ph : ph + L;
+    } else {
+        const int i2 = it - n_head - n_mid, ph = i2 / nI;
+        d.b = a.B - L + ph; d.idx = i2 - ph * nI; d.copy = true;
+    }
+    return d;
+}
+
+// executed by ONE warp: partials of sample b -> gs -> softmax table -> flag
+template <int R>
+__device__ __forceinline__ void cm_publish_table(const CmArgs &a, int b) {
+    constexpr int G2 = 2 * R, TABF = cm_table_floats<R>();
+    const int lane = threadIdx.x & 31;
+    // lane l adds rows l, l + 32, ... in increasing order (4 rows of loads in flight), then an xor tree
+    // over the lanes: fixed order, double
+    double v[G2];
+#pragma unroll
+    for (int r = 0; r < G2; ++r) v[r] = 0.0;
+    const float *rows = a.partials + (int64_t)b * a.nparts * G2;
+    for (int i0 = lane; i0 < a.nparts; i0 += 4 * 32) {
+        float t[4][G2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+#pragma unroll
+            for (int r = 0; r < G2; ++r) t[u][r] = i < a.nparts ? __ldcg(rows + (int64_t)i * G2 + r) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int r = 0; r < G2; ++r) v[r] += (double)t[u][r];
+    }
+#pragma unroll
+    for (int r = 0; r < G2; ++r) v[r] = warp_sum(v[r]);
+    float gs[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double d = v[r], vs = v[R + r];
+        const bool zero = vs < 1e-4;                                       // :222
+        const float v_sum = (float)vs + (zero ? 1.0f : 0.0f);              // :223
+        const float g0 = (float)d / (v_sum * (float)a.C);                  // :225-227
+        gs[r] = zero ? 0.0f : g0;                                          // :228
+        if (lane == 0) a.gs[(int64_t)b * R + r] = gs[r];
+    }
+    float *tab = a.table + (int64_t)b * TABF;
+    for (int t = lane; t < (1 << R); t += 32) {
+        // masked_softmax over the references for mask pattern t                 :245-254
+        float vr[R], wv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) vr[r] = ((t >> r) & 1) ? 1.0f : 0.0f;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < R; ++r) mx = fmaxf(mx, __fmul_rn(gs[r], vr[r]));
+        float sum = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            wv[r] = __fmul_rn(expf(__fsub_rn(__fmul_rn(gs[r], vr[r]), mx)), vr[r]);
+            sum = __fadd_rn(sum, wv[r]);
+        }
+        if (sum < 1e-4f) sum = __fadd_rn(sum, 1.0f);
+        float cm = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            wv[r] = __fdiv_rn(wv[r], sum);
+            cm = __fadd_rn(cm, __fmul_rn(wv[r], vr[r]));                          // :240
+            __stcg(tab + t * (R + 1) + r, wv[r]);
+        }
+        __stcg(tab + t * (R + 1) + R, __fsub_rn(1.0f, cm));                       // :241
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release(a.flag + b, 1u);
+}
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int R, int CH>
+constexpr int cm_stage_bytes() { return CH * (R + 1) * 4096 + 1024; }  // CH x f slabs of 1024 px + 1024 mask bytes
+
+template <int R, int CH, int NST>
+__global__ void __launch_bounds__(kCmThreads, 1) cm_pipe_kernel(const __grid_constant__ CmArgs a) {
+    constexpr int TABF = cm_table_floats<R>();
+    constexpr int kStageBytes = cm_stage_bytes<R, CH>();
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float *tabs = reinterpret_cast<float *>(smem_raw + NST * kStageBytes);  // 2 tables
+    __shared__ float red[2][2 * R * 32];
+    __shared__ uint64_t full[NST], empty[NST];
+    // S items hand their sums to the publisher warp through this mailbox: the global publication
+    // (store, fence, returning atomic: 2-3 us of latency) is off the compute warps' path.  With the
+    // publication done by warp 0 itself every S item cost 3-5 us (the next item's barrier waited).
+    __shared__ float mbox[kMailbox][2 * R];
+    __shared__ int mbox_b[kMailbox], mbox_idx[kMailbox];
+    __shared__ volatile int mb_ready, mb_done, mb_fin;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        mb_ready = 0; mb_done = 0; mb_fin = 0;
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(smem_u32(full + s), 1);
+            mbar_init(smem_u32(empty + s), 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_sync();
+    CM_PROBE(unsigned long long pr_t0 = global_ns(); unsigned long long pr_wait = 0, pr_s = 0, pr_c = 0, pr_slow = 0, pr_n = 0;)
+    if (wid == 9) {
+        // ===================== producer: bulk copies of the operands, NST items ahead =====================
+        if (lane == 0) {
+            for (int n = 0;; ++n) {
+                const CmItem d = cm_decode(a, blockIdx.x + n * gridDim.x);
+                if (!d.valid) break;
+                const int s = n % NST;
+                const uint32_t ph = (uint32_t)(n / NST) & 1u;
+                mbar_wait(smem_u32(empty + s), ph ^ 1u);
+                const int chunk = d.idx % a.chunks, slab = d.idx / a.chunks, c0 = slab * CH;
+                const int px = min(1024, a.P - chunk * 1024);
+                const int nch = min(CH, a.C - c0);
+                const uint32_t fb = smem_u32(full + s), dst = smem_u32(smem_raw + s * kStageBytes);
+                mbar_expect_tx(fb, (uint32_t)(nch * (R + 1) * px * 4 + px));
+                for (int k = 0; k < nch; ++k) {
+                    const float *base = a.c_feats + ((int64_t)d.b * a.C + c0 + k) * a.f * a.P + chunk * 1024;
+#pragma unroll
+                    for (int fr = 0; fr <= R; ++fr)
+                        bulk_load(dst + (k * (R + 1) + fr) * 4096, base + (int64_t)fr * a.P, (uint32_t)px * 4u, fb);
+                }
+                bulk_load(dst + CH * (R + 1) * 4096, a.pmask + (int64_t)d.b * a.P + chunk * 1024, (uint32_t)px, fb);
+            }
+        }
+        return;
+    }
+    if (wid == 8) {
+        // ===================== publisher warp =====================
+        int done = 0;
+        CM_PROBE(unsigned long long pb_busy = 0, pb_n = 0;)
+        for (;;) {
+            int ready = mb_ready;
+            if (ready == done) {
+                if (mb_fin && mb_ready == done) break;
+                __nanosleep(100);
+                continue;
+            }
+            __threadfence_block();
+            CM_PROBE(unsigned long long pb_t = global_ns();)
+            const int slot = done % kMailbox;
+            const int b = mbox_b[slot], idx = mbox_idx[slot];
+            if (lane < 2 * R) __stcg(a.partials + ((int64_t)b * a.nparts + idx) * (2 * R) + lane, mbox[slot][lane]);
+            __threadfence();  // release: the partials before the count
+            __syncwarp();
+            unsigned int old = 0;
+            if (lane == 0) {
+                mb_done = done + 1;
+                old = atomicAdd(a.count + b, 1u);
+            }
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == (unsigned int)a.n_items - 1u) {
+                __threadfence();  // acquire: every other item's partials
+                cm_publish_table<R>(a, b);
+            }
+            ++done;
+            CM_PROBE(pb_busy += global_ns() - pb_t; ++pb_n;)
+        }
+        CM_PROBE(if (lane == 0 && blockIdx.x < 256) { g_cm_probe[blockIdx.x * 8 + 6] = pb_busy; g_cm_probe[blockIdx.x * 8 + 7] = pb_n; })
+        return;
+    }
+
+    // ===================== compute warps =====================
+    // the softmax table of the NEXT item travels through a register (one 16 B chunk per thread)
+    float4 tnext = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const CmItem d0 = cm_decode(a, blockIdx.x);
+        if (d0.valid && d0.copy && tid < TABF / 4) {
+            tnext = __ldcg(reinterpret_cast<const float4 *>(a.table + (int64_t)d0.b * TABF) + tid);
+            reinterpret_cast<float4 *>(tabs)[tid] = tnext;
+        }
+    }
+    int n_sim = 0;
+    CM_PROBE(if (tid == 0 && blockIdx.x < 256) { g_cm_probe2[blockIdx.x * 8 + 0] = 0; g_cm_probe2[blockIdx.x * 8 + 1] = 0; g_cm_probe2[blockIdx.x * 8 + 2] = 0; })
+    for (int n = 0;; ++n) {
+        CM_PROBE(unsigned long long dc_t = global_ns();)
+        const CmItem d = cm_decode(a, blockIdx.x + n * gridDim.x);
+        if (!d.valid) break;
+        const CmItem dn = cm_decode(a, blockIdx.x + (n + 1) * gridDim.x);
+        CM_PROBE(if (tid == 0 && blockIdx.x < 256) g_cm_probe2[blockIdx.x * 8 + 2] += global_ns() - dc_t;)
+        const bool tn = dn.valid && dn.copy && tid < TABF / 4;
+        if (tn) tnext = __ldcg(reinterpret_cast<const float4 *>(a.table + (int64_t)dn.b * TABF) + tid);
+        const int s = n % NST;
+        CM_PROBE(unsigned long long pr_a = global_ns();)
+        mbar_wait(smem_u32(full + s), (uint32_t)(n / NST) & 1u);
+        CM_PROBE(unsigned long long pr_b = global_ns(); pr_wait += pr_b - pr_a; ++pr_n;)
+        const int chunk = d.idx % a.chunks, slab = d.idx / a.chunks;
+        const int p0 = (chunk * 256 + tid) * 4, c0 = slab * CH;
+        const bool live = p0 < a.P;
+        const uint8_t *stb = smem_raw + s * kStageBytes;
+        const float4 *st = reinterpret_cast<const float4 *>(stb);
+        const uint32_t mw = live ? reinterpret_cast<const uint32_t *>(stb + CH * (R + 1) * 4096)[tid] : 0u;
+        if (!d.copy) {
+            // ---------------- S item: partial similarity ----------------
+            float acc[2 * R];
+#pragma unroll
+            for (int r = 0; r < 2 * R; ++r) acc[r] = 0.0f;
+            if (live) {
+                float4 vm[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {  // vt' * vr'                  :220
+                    const uint32_t m = mw & (mw >> (r + 1)) & 0x01010101u;
+                    vm[r] = make_float4((float)(m & 1u), (float)((m >> 8) & 1u), (float)((m >> 16) & 1u),
+                                        (float)((m >> 24) & 1u));
+                    if (slab == 0) acc[R + r] = (vm[r].x + vm[r].y) + (vm[r].z + vm[r].w);  // :221
+                }
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    if (c0 + k < a.C) {
+                        const float4 ct = st[(k * (R + 1)) * 256 + tid];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {  // vmap * c_t * c_r            :226
+                            const float4 cr = st[(k * (R + 1) + r + 1) * 256 + tid];
+                            acc[r] += vm[r].x * ct.x * cr.x;
+                            acc[r] += vm[r].y * ct.y * cr.y;
+                            acc[r] += vm[r].z * ct.z * cr.z;
+                            acc[r] += vm[r].w * ct.w * cr.w;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(empty + s));  // the stage may be refilled
+            compute_sum<2 * R>(acc, red[n_sim & 1]);  // double-buffered: warp 0 reads while the others move on
+            if (tid == 0) {
+                while (n_sim - mb_done >= kMailbox) __nanosleep(100);
+                const int slot = n_sim % kMailbox;
+#pragma unroll
+                for (int r = 0; r < 2 * R; ++r) mbox[slot][r] = acc[r];
+                mbox_b[slot] = d.b;
+                mbox_idx[slot] = d.idx;
+                __threadfence_block();
+                mb_ready = n_sim + 1;
+            }
+            ++n_sim;
+        } else {
+            // ---------------- C item: cat[c_t, sum_r c_r * w_r] ----------------
+            float *tb = tabs + (n & 1) * TABF;
+            bool bad = false;
+            if (tid < TABF / 4) {  // the chunk this thread fetched one item ago
+                const float4 t4 = reinterpret_cast<const float4 *>(tb)[tid];
+                bad = isnan(t4.x) || isnan(t4.y) || isnan(t4.z) || isnan(t4.w);
+            }
+            if (bar_compute_or(bad)) {  // also: the table chunks of the other threads are visible
+                CM_PROBE(++pr_slow; unsigned long long sl_t = global_ns();)
+                if (tid == 0) {
+                    CM_PROBE(if (ld_acquire(a.flag + d.b) != 0u && blockIdx.x < 256) g_cm_probe2[blockIdx.x * 8 + 0] += 1;)
+                    if (ld_acquire(a.flag + d.b) == 0u) {
+                        const unsigned long long t0 = global_ns();
+                        while (ld_acquire(a.flag + d.b) == 0u) {
+                            __nanosleep(64);
+                            if (global_ns() - t0 > 2000000000ull) __trap();
+                        }
+                    }
+                }
+                bar_compute();
+                for (int q = tid; q < TABF; q += 256) tb[q] = __ldcg(a.table + (int64_t)d.b * TABF + q);
+                bar_compute();
+                CM_PROBE(if (tid == 0 && blockIdx.x < 256) g_cm_probe2[blockIdx.x * 8 + 1] += global_ns() - sl_t;)
+            }
+            if (live) {
+                int pat[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pat[j] = (int)((mw >> (8 * j + 1)) & ((1u << R) - 1u)) * (R + 1);
+                float *ob = a.out + (int64_t)d.b * (2 * a.C + 1) * a.P + p0;
+                if (slab == 0) {
+                    const float4 c4 = make_float4(tb[pat[0] + R], tb[pat[1] + R], tb[pat[2] + R], tb[pat[3] + R]);
+                    st_stream4(ob + (int64_t)(2 * a.C) * a.P, c4);
+                    st_stream4(a.c_mask + (int64_t)d.b * a.P + p0, c4);
+                }
+                float4 wg[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) wg[r] = make_float4(tb[pat[0] + r], tb[pat[1] + r], tb[pat[2] + r], tb[pat[3] + r]);
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    const int c = c0 + k;
+                    if (c >= a.C) break;
+                    float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {  // sum_r c_r * w_r, sequential over r    :238
+                        const float4 cr = st[(k * (R + 1) + r + 1) * 256 + tid];
+                        o.x = __fadd_rn(o.x, __fmul_rn(cr.x, wg[r].x));
+                        o.y = __fadd_rn(o.y, __fmul_rn(cr.y, wg[r].y));
+                        o.z = __fadd_rn(o.z, __fmul_rn(cr.z, wg[r].z));
+                        o.w = __fadd_rn(o.w, __fmul_rn(cr.w, wg[r].w));
+                    }
+                    st_stream4(ob + (int64_t)c * a.P, st[(k * (R + 1)) * 256 + tid]);  // cat[c_t, ...]  :243
+                    st_stream4(ob + (int64_t)(a.C + c) * a.P, o);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(empty + s));  // the stage may be refilled
+        }
+        // table of the next item: slot (n + 1) & 1 was last read by item n - 1, and every thread has
+        // passed the barrier of item n
+        if (tn) reinterpret_cast<float4 *>(tabs + ((n + 1) & 1) * TABF)[tid] = tnext;
+        CM_PROBE(if (d.copy) pr_c += global_ns() - pr_b; else pr_s += global_ns() - pr_b;)
+    }
+    CM_PROBE(if (tid == 0 && blockIdx.x < 256) {
+        unsigned long long *o = g_cm_probe + blockIdx.x * 8;
+        o[0] = global_ns() - pr_t0; o[1] = pr_wait; o[2] = pr_s; o[3] = pr_c; o[4] = pr_slow; o[5] = pr_n;
+    })
+    if (tid == 0) { __threadfence_block(); mb_fin = 1; }
+}
+
+template <int R, int CH>
+constexpr int cm_pipe_smem(int nst) {
+    return nst * cm_stage_bytes<R, CH>() + 2 * cm_table_floats<R>() * 4;
+}
+
+template <int R, int CH, int NST>
+int launch_cm_pipe_n(CmArgs a, cudaStream_t st) {
+    constexpr int smem = cm_pipe_smem<R, CH>(NST);
+    auto kern = cm_pipe_kernel<R, CH, NST>;
+    static bool ready = false;
+    if (!ready) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        ready = true;
+    }
+    a.n_items = a.chunks * ((a.C + CH - 1) / CH);
+    a.nparts = a.n_items;
+    a.lag = tuning("MT_CM_LAG", 2);
+    if (a.lag < 1) a.lag = 1;
+    if (a.lag > a.B) a.lag = a.B;
+    const int64_t total = 2ll * a.B * a.n_items;
+    if (total > (1ll << 30)) return -1;
+    int64_t grid = sm_count();  // one resident wave (1 CTA/SM): the CTAs wait on each other
+    if (grid > total) grid = total;
+    launch(cm_masks_kernel, dim3((a.P + 255) / 256, a.B), 256, 0, st, a);
+    launch(kern, dim3((unsigned)grid), kCmThreads, (size_t)smem, st, a);
+    return launch_status("mt_cm_match_fwd");
+}
+
+// deepest ring that fits 227 KB of shared memory (static smem of the kernel: < 3 KB)
+template <int R, int CH>
+int launch_cm_pipe(CmArgs a, cudaStream_t st) {
+    constexpr int kBudget = 224 * 1024;
+    const int want = tuning("MT_CM_STAGES", 5);
+    if ((a.P & 15) != 0) return -1;  // bulk copies: 16 B aligned rows of the byte masks
+    if constexpr (cm_pipe_smem<R, CH>(5) <= kBudget) { if (want >= 5) return launch_cm_pipe_n<R, CH, 5>(a, st); }
+    if constexpr (cm_pipe_smem<R, CH>(4) <= kBudget) { if (want >= 4) return launch_cm_pipe_n<R, CH, 4>(a, st); }
+    if constexpr (cm_pipe_smem<R, CH>(3) <= kBudget) { if (want >= 3) return launch_cm_pipe_n<R, CH, 3>(a, st); }
+    if constexpr (cm_pipe_smem<R, CH>(2) <= kBudget) return launch_cm_pipe_n<R, CH, 2>(a, st);
+    return -1;
+}
+
 template <int R>
 int launch_cm(CmArgs a, cudaStream_t st) {
+    // one persistent launch (pass 2 from L2); MT_CM_FUSED=0 keeps the three-launch path
+    if (R <= 7 && tuning("MT_CM_FUSED", 0)) {  // the mask byte holds the target and up to 7 references
+        const int ch = tuning("MT_CM_FUSED_CH", 2);
+        const int rc = ch == 4 ? launch_cm_pipe<R, 4>(a, st) : (ch == 1 ? launch_cm_pipe<R, 1>(a, st) : launch_cm_pipe<R, 2>(a, st));
+        if (rc >= 0) return rc;
+    }
     a.b_off = 0;
-    dim3 g0((a.P + 255) / 256, a.f, a.B);
-    launch(cm_masks_kernel, g0, 256, 0, st, a);
+    launch(cm_masks_kernel, dim3((a.P + 255) / 256, a.B), 256, 0, st, a);
     // MT_CM_CHUNK > 0 processes the samples in chunks (sim -> weights -> copy per chunk) so that
     // pass 2 could re-read c_feats from L2.  Swept on B200 at B=8 (profiles/r1_sweep_cm.sh):
     // 1/2/4/8 samples per chunk -> 111/72/55/48 us: the extra small launches cost more than the
@@ -310,7 +804,8 @@ extern "C" int64_t mt_cm_workspace_bytes(int B, int C, int f, int h, int w) {
     const int64_t P = (int64_t)h * w, R = f - 1;
     const int64_t chunks = (P + 1023) / 1024, nparts = chunks * ((C + 1) / 2);  // finest pass-1 split
     return align256(B * f * P * 4) + align256(B * nparts * 2 * R * 4) + align256(B * R * 4) +
-           align256(B * R * P * 4);
+           align256(B * R * P * 4) + 2 * align256((int64_t)B * 4) + align256(B * P) +
+           align256(B * (int64_t)(1 << R) * (R + 1) * 4);
 }
 
 extern "C" int mt_cm_match_fwd(const float *c_feats, const float *v_t, const float *v_aligned,
@@ -337,6 +832,15 @@ extern "C" int mt_cm_match_fwd(const float *c_feats, const float *v_t, const flo
     a.gs = reinterpret_cast<float *>(ws);
     ws += align256((int64_t)B * a.R * 4);
     a.weights = reinterpret_cast<float *>(ws);
+    ws += align256((int64_t)B * a.R * a.P * 4);
+    a.count = reinterpret_cast<unsigned int *>(ws);
+    ws += align256((int64_t)B * 4);
+    a.flag = reinterpret_cast<unsigned int *>(ws);
+    ws += align256((int64_t)B * 4);
+    a.pmask = reinterpret_cast<unsigned char *>(ws);
+    ws += align256((int64_t)B * a.P);
+    a.table = reinterpret_cast<float *>(ws);
+    a.n_items = 0; a.lag = 1;
     cudaStream_t st = (cudaStream_t)stream;
     switch (a.R) {
         case 1: return launch_cm<1>(a, st);
@@ -357,3 +861,12 @@ extern "C" const float *mt_cm_workspace_gs(const void *workspace, int B, int C, 
     return reinterpret_cast<const float *>(reinterpret_cast<const char *>(workspace) +
                                            align256(B * f * P * 4) + align256(B * nparts * 2 * R * 4));
 }
+
+#ifdef MT_DEV_PROBES
+extern "C" __attribute__((visibility("default"))) int mt_debug_cm_probe(unsigned long long *dst, int n) {
+    cudaDeviceSynchronize();
+    if (n < 0) return cudaMemcpyFromSymbol(dst, mt::g_cm_probe2, sizeof(unsigned long long) * 2048) == cudaSuccess ? 0 : -2;
+    return cudaMemcpyFromSymbol(dst, mt::g_cm_probe, sizeof(unsigned long long) * (n < 2048 ? n : 2048)) == cudaSuccess
+               ? 0 : -2;
+}
+#endif

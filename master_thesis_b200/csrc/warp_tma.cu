@@ -202,20 +202,32 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const float4 d2 = reinterpret_cast<const float4 *>(desc + s)[2];  // th0..3
         const float4 d3 = reinterpret_cast<const float4 *>(desc + s)[3];  // th4, th5
         const int flags = d0.x, bx0 = d0.y, by0 = d0.z, b = d0.w, f = d1.x, n = d1.y;
-        const int xg = d1.z * kTile + lane, y0 = d1.w * kTile + 2 * warp;
+        // lane -> pixel: a warp instruction covers 16 columns x 2 adjacent rows (and the thread's second
+        // pixel lies 2 rows below).  With the box pitch of 48 words a source row starts 16 banks after
+        // the previous one, so the two half-warps read disjoint bank ranges and a tap instruction is
+        // one shared-memory wavefront; the 32 x 1 mapping had 2-way conflicts wherever the footprint
+        // of the 32 lanes stepped to the next source row (ncu: 44 % of the LDS wavefronts).
+#ifdef MT_WARP_MAP_32X1
+        const int tcol = lane, trow = 2 * warp;
+        constexpr int kRowStep = 1;
+#else
+        const int tcol = (warp & 1) * 16 + (lane & 15), trow = (warp >> 1) * 4 + (lane >> 4);
+        constexpr int kRowStep = 2;
+#endif
+        const int xg = d1.z * kTile + tcol, y0 = d1.w * kTile + trow;
         const bool live = xg < W;
         const int x = min(xg, W - 1);
         const int p0 = y0 * W + x;
         const float *st = stage0 + s * kStageFloats;
         float mtv[2];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) mtv[k] = st[4 * kPlane + (2 * warp + k) * kTile + lane];
+        for (int k = 0; k < 2; ++k) mtv[k] = st[4 * kPlane + (trow + k * kRowStep) * kTile + tcol];
         const float bx = s_bx[x];
         const float bxt0 = __fmul_rn(bx, d2.x), bxt3 = __fmul_rn(bx, d2.w);
         float ix[2], iy[2], xw[2], yn[2], wnw[2], wne[2], wsw[2], wse[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const float by = s_by[min(y0 + k, H - 1)];
+            const float by = s_by[min(y0 + k * kRowStep, H - 1)];
             const float gx = __fadd_rn(__fmaf_rn(by, d2.y, bxt0), d2.z);  // fma(by, t1, bx*t0) + t2 (pinned order)
             const float gy = __fadd_rn(__fmaf_rn(by, d3.x, bxt3), d3.y);
             ix[k] = unnorm_t(gx, a.sp.sfx, AC);
@@ -291,11 +303,12 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             const int xao = b * a.xa_sb + f * a.xa_sf + p0, np0 = n * a.P + p0;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                if (y0 + k >= H) break;
+                if (y0 + k * kRowStep >= H) break;
+                const int ro = k * kRowStep * W;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) st_stream1(a.x_al + (xao + c * a.xa_sc + k * W), xa[c][k]);
-                st_stream1(a.v_al + (np0 + k * W), va[k]);
-                st_stream1(a.v_map + (np0 + k * W), clamp01(__fsub_rn(va[k], __fsub_rn(1.0f, mtv[k]))));
+                for (int c = 0; c < 3; ++c) st_stream1(a.x_al + (xao + c * a.xa_sc + ro), xa[c][k]);
+                st_stream1(a.v_al + (np0 + ro), va[k]);
+                st_stream1(a.v_map + (np0 + ro), clamp01(__fsub_rn(va[k], __fsub_rn(1.0f, mtv[k]))));
             }
         }
     }
@@ -398,9 +411,12 @@ int warp_staged_launch(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
 
 }  // namespace mt
 
-// developer probe (not part of include/mt_b200.h): copies the timeline stamps to the host
+// developer probe (not part of include/mt_b200.h; only in builds with -DMT_DEV_PROBES, see
+// tools/dbg_timeline.py): copies the timeline stamps to the host
+#ifdef MT_DEV_PROBES
 extern "C" __attribute__((visibility("default"))) int mt_debug_warp_timeline(unsigned long long *dst, int n) {
     cudaDeviceSynchronize();
     return cudaMemcpyFromSymbol(dst, mt::g_timeline, sizeof(unsigned long long) * (n < 2048 ? n : 2048)) == cudaSuccess
                ? 0 : -2;
 }
+#endif

@@ -4,6 +4,8 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["MT_WARP_DBG"] = "8"
+# needs a probe build: python -m master_thesis_b200.build -DMT_DEV_PROBES --out=tools/libmt_dev.so
+os.environ.setdefault("MT_B200_LIB", os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmt_dev.so"))
 import master_thesis_b200 as mtb
 from master_thesis_b200 import synth, _lib
 b, f, h, w = int(sys.argv[1]) if len(sys.argv) > 1 else 8, 4, 256, 256
