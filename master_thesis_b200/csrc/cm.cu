@@ -31,6 +31,23 @@ constexpr int kSimChannels = 2;   // default channels per CTA slab in pass 1 (sw
 constexpr int kCopyChannels = 4;  // default channels per CTA slab in pass 2 (template CC)
 constexpr int kMaxRefs = 8;
 
+// exact unsigned division by a runtime constant (round-up method): q = x / d for every 32-bit x
+struct FastDiv { uint32_t d, m, s1, s2; };
+static inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    f.d = d;
+    f.m = (uint32_t)((((1ull << l) - d) << 32) / d + 1);
+    f.s1 = l < 1 ? l : 1;
+    f.s2 = l > 0 ? l - 1 : 0;
+    return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, const FastDiv &f) {
+    const uint32_t t = __umulhi(f.m, x);
+    return (t + ((x - t) >> f.s1)) >> f.s2;
+}
+
 struct CmArgs {
     const float *c_feats, *v_t, *v_al;
     float *out, *c_mask;
@@ -44,7 +61,9 @@ struct CmArgs {
     unsigned int *count, *flag;  // (B) finished S items / table published
     unsigned char *pmask;        // (B, P) bit 0: vt', bit r + 1: vr' of reference r
     float *table;                // (B, 2^R, R + 1) softmax weights and c_mask per mask pattern
-    int n_items, lag;
+    int n_items, lag, copy_reverse;
+    int workers, rounds, head;  // schedule of the pipelined kernel (cm_decode)
+    FastDiv dv_items, dv_chunks;
 };
 
 // F.interpolate(bilinear, align_corners=False) source index (UpSample.h)
@@ -251,7 +270,10 @@ __global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
     pdl_sync();
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (p0 >= a.P) return;
-    const int slab = blockIdx.y, b = blockIdx.z + a.b_off;
+    // samples in REVERSE order: pass 1 streamed them 0 .. B-1, so the tail of the batch is what is
+    // still in L2 (126 MB); walking forwards again evicts it just before it is needed (LRU: ncu
+    // 4.6 % hit rate at B=8)
+    const int slab = blockIdx.y, b = (a.copy_reverse ? (int)gridDim.z - 1 - (int)blockIdx.z : (int)blockIdx.z) + a.b_off;
     const int c0 = slab * CC;
     float4 ct[CC], cr[CC][R];
 #pragma unroll
@@ -373,39 +395,49 @@ constexpr int kMailbox = 16;
 template <int R>
 constexpr int cm_table_floats() { return (1 << R) * (R + 1); }  // per pattern: R weights, c_mask
 
-struct CmItem { int b, idx; bool copy, valid; };
+struct CmItem { int b, idx, chunk, slab; bool copy, valid; };
 
 #ifdef MT_DEV_PROBES
 // developer probe (tools/dbg_cm.py): per CTA [0] kernel ns, [1] ns waiting for cp.async data, [2] ns in S
 // items, [3] ns in C items, [4] C items through the slow path, [5] items, [6] publisher busy ns, [7] publishes
 __device__ unsigned long long g_cm_probe[256 * 8];
-__device__ unsigned long long g_cm_probe2[256 * 8];  // [0] slow items whose flag was already set, [1] ns in the slow path, [2] ns in decode
+__device__ unsigned long long g_cm_probe2[2048];  // [0] slow items whose flag was already set, [1] ns in the slow path, [2] ns in decode
 #define CM_PROBE(...) __VA_ARGS__
 #else
 #define CM_PROBE(...)
 #endif
 
-__device__ __forceinline__ CmItem cm_decode(const CmArgs &a, int it) {
-    const int nI = a.n_items, L = a.lag;
-    const int n_head = L * nI, n_mid = (a.B - L) * 2 * nI, total = 2 * a.B * nI;
+// Schedule.  The S items of all samples form one stream (position u = b * n_items + idx), the C items
+// another.  Every worker (a compute group of a CTA; NW workers in all) runs the SAME sequence of
+// rounds and takes position round * NW + worker of the round's stream: `head` S rounds, then C and S
+// rounds alternating, then the remaining C rounds.  Every worker therefore alternates between reads
+// from HBM (S) and reads from L2 + writes (C) - a first version that interleaved the two streams in
+// one list gave the even CTAs only S items and the odd ones only C items (2x slower) - and every S
+// item of a sample is earlier in every worker's sequence than any C item of that sample (the host
+// picks `head` accordingly), which is what makes waiting inside a C item safe.
+__device__ __forceinline__ CmItem cm_decode(const CmArgs &a, int worker, int r) {
     CmItem d;
-    d.valid = it < total;
-    if (it < n_head) {
-        d.b = it / nI; d.idx = it - d.b * nI; d.copy = false;
-    } else if (it < n_head + n_mid) {
-        const int i2 = it - n_head, ph = i2 / (2 * nI), j = i2 - ph * 2 * nI;
-        // S and C alternate along the list; with an even grid a CTA would only ever see one parity
-        // (all copies on the odd CTAs: measured, 2x slower), so the order of a pair flips every
-        // grid / 2 pairs and every CTA alternates between S and C items
-        const int g = (int)gridDim.x, flip = (g & 1) ? 0 : (((j >> 1) / (g >> 1)) & 1);
-        d.copy = ((j & 1) ^ flip) != 0; d.idx = j >> 1;
-        d.b = d.copy ? ph : ph + L;
-    } else {
-        const int i2 = it - n_head - n_mid, ph = i2 / nI;
-        d.b = a.B - L + ph; d.idx = i2 - ph * nI; d.copy = true;
+    const int R1 = a.rounds;  // rounds per stream
+    int sr;                   // round within the stream
+    if (r < a.head) { d.copy = false; sr = r; }
+    else {
+        const int t = r - a.head, pairs = R1 - a.head;  // alternating part: C first
+        if (t < 2 * pairs) { d.copy = (t & 1) == 0; sr = d.copy ? (t >> 1) : a.head + (t >> 1); }
+        else { d.copy = true; sr = pairs + (t - 2 * pairs); }
+    }
+    const int u = sr * a.workers + worker;
+    d.valid = r < 2 * R1 && u < a.B * a.n_items;
+    d.b = 0; d.idx = 0; d.chunk = 0; d.slab = 0;
+    if (d.valid) {
+        d.b = (int)fast_div((uint32_t)u, a.dv_items);
+        d.idx = u - d.b * a.n_items;
+        d.slab = (int)fast_div((uint32_t)d.idx, a.dv_chunks);
+        d.chunk = d.idx - d.slab * a.chunks;
     }
     return d;
 }
+// a worker is done after round 2 * rounds - 1; rounds whose position is past the end of the stream are empty
+__device__ __forceinline__ bool cm_done(const CmArgs &a, int r) { return r >= 2 * a.rounds; }
 
 // executed by ONE warp: partials of sample b -> gs -> softmax table -> flag
 template <int R>
@@ -471,6 +503,7 @@ __device__ __forceinline__ void cm_publish_table(const CmArgs &a, int b) {
     __threadfence();
     __syncwarp();
     if (lane == 0) st_release(a.flag + b, 1u);
+    CM_PROBE(if (lane == 0 && b < 64) g_cm_probe2[1024 + b] = global_ns();)
 }
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -481,23 +514,57 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
 template <int R, int CH>
 constexpr int cm_stage_bytes() { return CH * (R + 1) * 4096 + 1024; }  // CH x f slabs of 1024 px + 1024 mask bytes
 
-template <int R, int CH, int NST>
-__global__ void __launch_bounds__(kCmThreads, 1) cm_pipe_kernel(const __grid_constant__ CmArgs a) {
+// 8 values per lane -> lane l holds the warp total of value (l >> 2) & 7: 9 shuffles instead of 40
+__device__ __forceinline__ float warp_sum8(const float (&v)[8]) {
+    const int lane = threadIdx.x & 31;
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+    float w[4], x[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h4 ? v[i] : v[i + 4], keep = h4 ? v[i + 4] : v[i];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h3 ? w[i] : w[i + 2], keep = h3 ? w[i + 2] : w[i];
+        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float send = h2 ? x[0] : x[1], keep = h2 ? x[1] : x[0];
+    float y = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    y += __shfl_xor_sync(0xffffffffu, y, 2);
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    return y;
+}
+__device__ __forceinline__ void bar_group(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ bool bar_group_or(int id, bool p) {
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred pin, pout;\n\tsetp.ne.u32 pin, %2, 0;\n\tbar.red.or.pred pout, %1, 256, pin;\n\t"
+        "selp.u32 %0, 1, 0, pout;\n\t}"
+        : "=r"(r) : "r"(id), "r"((int)p) : "memory");
+    return r != 0;
+}
+
+// NG groups of 8 compute warps (each group works on its own item: 4 warps per scheduler hide the
+// LDS / FP latencies that 2 could not), one publisher warp, one producer warp.
+template <int R, int CH, int NST, int NG>
+__global__ void __launch_bounds__(NG * 256 + 64, 1) cm_pipe_kernel(const __grid_constant__ CmArgs a) {
     constexpr int TABF = cm_table_floats<R>();
     constexpr int kStageBytes = cm_stage_bytes<R, CH>();
+    constexpr int G2 = 2 * R;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    float *tabs = reinterpret_cast<float *>(smem_raw + NST * kStageBytes);  // 2 tables
-    __shared__ float red[2][2 * R * 32];
+    float *tabs = reinterpret_cast<float *>(smem_raw + NST * kStageBytes);  // NG x 2 tables
+    __shared__ float red[NG][2][G2 * 8];
     __shared__ uint64_t full[NST], empty[NST];
-    // S items hand their sums to the publisher warp through this mailbox: the global publication
+    // S items hand their sums to the publisher warp through these mailboxes: the global publication
     // (store, fence, returning atomic: 2-3 us of latency) is off the compute warps' path.  With the
     // publication done by warp 0 itself every S item cost 3-5 us (the next item's barrier waited).
-    __shared__ float mbox[kMailbox][2 * R];
-    __shared__ int mbox_b[kMailbox], mbox_idx[kMailbox];
-    __shared__ volatile int mb_ready, mb_done, mb_fin;
+    __shared__ float mbox[NG][kMailbox][G2];
+    __shared__ int mbox_b[NG][kMailbox], mbox_idx[NG][kMailbox];
+    __shared__ volatile int mb_ready[NG], mb_done[NG], mb_fin[NG];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
-        mb_ready = 0; mb_done = 0; mb_fin = 0;
+        for (int g = 0; g < NG; ++g) { mb_ready[g] = 0; mb_done[g] = 0; mb_fin[g] = 0; }
         for (int s = 0; s < NST; ++s) {
             mbar_init(smem_u32(full + s), 1);
             mbar_init(smem_u32(empty + s), 8);
@@ -507,101 +574,121 @@ __global__ void __launch_bounds__(kCmThreads, 1) cm_pipe_kernel(const __grid_con
     __syncthreads();
     pdl_sync();
     CM_PROBE(unsigned long long pr_t0 = global_ns(); unsigned long long pr_wait = 0, pr_s = 0, pr_c = 0, pr_slow = 0, pr_n = 0;)
-    if (wid == 9) {
+    CM_PROBE(if (tid == 0 && blockIdx.x < 256) { g_cm_probe2[blockIdx.x * 8 + 0] = 0; g_cm_probe2[blockIdx.x * 8 + 1] = 0; })
+    CM_PROBE(if (tid == 0 && blockIdx.x == 0) g_cm_probe2[1200] = pr_t0;)
+    if (wid == 8 * NG + 1) {
         // ===================== producer: bulk copies of the operands, NST items ahead =====================
         if (lane == 0) {
-            for (int n = 0;; ++n) {
-                const CmItem d = cm_decode(a, blockIdx.x + n * gridDim.x);
-                if (!d.valid) break;
+            int n = 0;  // valid items of this CTA so far (stage ring position)
+            for (int r = 0; !cm_done(a, r); ++r)
+            for (int g = 0; g < NG; ++g) {
+                const CmItem d = cm_decode(a, blockIdx.x + g * gridDim.x, r);
+                if (!d.valid) continue;
                 const int s = n % NST;
                 const uint32_t ph = (uint32_t)(n / NST) & 1u;
+                ++n;
                 mbar_wait(smem_u32(empty + s), ph ^ 1u);
-                const int chunk = d.idx % a.chunks, slab = d.idx / a.chunks, c0 = slab * CH;
-                const int px = min(1024, a.P - chunk * 1024);
+                const int c0 = d.slab * CH;
+                const int px = min(1024, a.P - d.chunk * 1024);
                 const int nch = min(CH, a.C - c0);
                 const uint32_t fb = smem_u32(full + s), dst = smem_u32(smem_raw + s * kStageBytes);
                 mbar_expect_tx(fb, (uint32_t)(nch * (R + 1) * px * 4 + px));
                 for (int k = 0; k < nch; ++k) {
-                    const float *base = a.c_feats + ((int64_t)d.b * a.C + c0 + k) * a.f * a.P + chunk * 1024;
+                    const float *base = a.c_feats + ((int64_t)d.b * a.C + c0 + k) * a.f * a.P + d.chunk * 1024;
 #pragma unroll
                     for (int fr = 0; fr <= R; ++fr)
                         bulk_load(dst + (k * (R + 1) + fr) * 4096, base + (int64_t)fr * a.P, (uint32_t)px * 4u, fb);
                 }
-                bulk_load(dst + CH * (R + 1) * 4096, a.pmask + (int64_t)d.b * a.P + chunk * 1024, (uint32_t)px, fb);
+                bulk_load(dst + CH * (R + 1) * 4096, a.pmask + (int64_t)d.b * a.P + d.chunk * 1024, (uint32_t)px, fb);
             }
         }
         return;
     }
-    if (wid == 8) {
+    if (wid == 8 * NG) {
         // ===================== publisher warp =====================
-        int done = 0;
+        int done[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) done[g] = 0;
         CM_PROBE(unsigned long long pb_busy = 0, pb_n = 0;)
         for (;;) {
-            int ready = mb_ready;
-            if (ready == done) {
-                if (mb_fin && mb_ready == done) break;
+            bool any = false, fin = true;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                if (mb_ready[g] == done[g]) {
+                    fin = fin && mb_fin[g] && mb_ready[g] == done[g];
+                    continue;
+                }
+                any = true;
+                __threadfence_block();
+                CM_PROBE(unsigned long long pb_t = global_ns();)
+                const int slot = done[g] % kMailbox;
+                const int b = mbox_b[g][slot], idx = mbox_idx[g][slot];
+                if (lane < G2) __stcg(a.partials + ((int64_t)b * a.nparts + idx) * G2 + lane, mbox[g][slot][lane]);
+                __threadfence();  // release: the partials before the count
+                __syncwarp();
+                unsigned int old = 0;
+                if (lane == 0) {
+                    mb_done[g] = done[g] + 1;
+                    old = atomicAdd(a.count + b, 1u);
+                }
+                old = __shfl_sync(0xffffffffu, old, 0);
+                if (old == (unsigned int)a.n_items - 1u) {
+                    CM_PROBE(if (lane == 0 && b < 64) g_cm_probe2[1152 + b - 0] = global_ns();)
+                    __threadfence();  // acquire: every other item's partials
+                    cm_publish_table<R>(a, b);
+                }
+                ++done[g];
+                CM_PROBE(pb_busy += global_ns() - pb_t; ++pb_n;)
+            }
+            if (!any) {
+                if (fin) break;
                 __nanosleep(100);
-                continue;
             }
-            __threadfence_block();
-            CM_PROBE(unsigned long long pb_t = global_ns();)
-            const int slot = done % kMailbox;
-            const int b = mbox_b[slot], idx = mbox_idx[slot];
-            if (lane < 2 * R) __stcg(a.partials + ((int64_t)b * a.nparts + idx) * (2 * R) + lane, mbox[slot][lane]);
-            __threadfence();  // release: the partials before the count
-            __syncwarp();
-            unsigned int old = 0;
-            if (lane == 0) {
-                mb_done = done + 1;
-                old = atomicAdd(a.count + b, 1u);
-            }
-            old = __shfl_sync(0xffffffffu, old, 0);
-            if (old == (unsigned int)a.n_items - 1u) {
-                __threadfence();  // acquire: every other item's partials
-                cm_publish_table<R>(a, b);
-            }
-            ++done;
-            CM_PROBE(pb_busy += global_ns() - pb_t; ++pb_n;)
         }
         CM_PROBE(if (lane == 0 && blockIdx.x < 256) { g_cm_probe[blockIdx.x * 8 + 6] = pb_busy; g_cm_probe[blockIdx.x * 8 + 7] = pb_n; })
         return;
     }
 
     // ===================== compute warps =====================
-    // the softmax table of the NEXT item travels through a register (one 16 B chunk per thread)
+    const int grp = wid >> 3, lt = tid & 255, lw = wid & 7, bar_id = 1 + grp;
+    float *gtabs = tabs + grp * 2 * TABF;
+    // the softmax table of the group's NEXT item travels through a register (one 16 B chunk per thread)
     float4 tnext = make_float4(0.f, 0.f, 0.f, 0.f);
-    {
-        const CmItem d0 = cm_decode(a, blockIdx.x);
-        if (d0.valid && d0.copy && tid < TABF / 4) {
-            tnext = __ldcg(reinterpret_cast<const float4 *>(a.table + (int64_t)d0.b * TABF) + tid);
-            reinterpret_cast<float4 *>(tabs)[tid] = tnext;
+    const int me = blockIdx.x + grp * gridDim.x;
+    for (int r = 0; !cm_done(a, r); ++r) {  // table of the group's first C item, if that is its first item
+        const CmItem d0 = cm_decode(a, me, r);
+        if (!d0.valid) continue;
+        if (d0.copy && lt < TABF / 4) {
+            tnext = __ldcg(reinterpret_cast<const float4 *>(a.table + (int64_t)d0.b * TABF) + lt);
+            reinterpret_cast<float4 *>(gtabs)[lt] = tnext;
         }
+        break;
     }
-    int n_sim = 0;
-    CM_PROBE(if (tid == 0 && blockIdx.x < 256) { g_cm_probe2[blockIdx.x * 8 + 0] = 0; g_cm_probe2[blockIdx.x * 8 + 1] = 0; g_cm_probe2[blockIdx.x * 8 + 2] = 0; })
-    for (int n = 0;; ++n) {
-        CM_PROBE(unsigned long long dc_t = global_ns();)
-        const CmItem d = cm_decode(a, blockIdx.x + n * gridDim.x);
-        if (!d.valid) break;
-        const CmItem dn = cm_decode(a, blockIdx.x + (n + 1) * gridDim.x);
-        CM_PROBE(if (tid == 0 && blockIdx.x < 256) g_cm_probe2[blockIdx.x * 8 + 2] += global_ns() - dc_t;)
-        const bool tn = dn.valid && dn.copy && tid < TABF / 4;
-        if (tn) tnext = __ldcg(reinterpret_cast<const float4 *>(a.table + (int64_t)dn.b * TABF) + tid);
+    int n_sim = 0, i = 0, n = 0;  // S items / items of the group, valid items of the CTA (stage ring position)
+    for (int r = 0; !cm_done(a, r); ++r)
+    for (int g = 0; g < NG; ++g) {
+        const CmItem d = cm_decode(a, blockIdx.x + g * gridDim.x, r);
+        if (!d.valid) continue;
         const int s = n % NST;
+        const uint32_t full_ph = (uint32_t)(n / NST) & 1u;
+        ++n;
+        if (g != grp) continue;
+        const CmItem dn = cm_decode(a, me, r + 1);
+        const bool tn = dn.valid && dn.copy && lt < TABF / 4;
+        if (tn) tnext = __ldcg(reinterpret_cast<const float4 *>(a.table + (int64_t)dn.b * TABF) + lt);
         CM_PROBE(unsigned long long pr_a = global_ns();)
-        mbar_wait(smem_u32(full + s), (uint32_t)(n / NST) & 1u);
+        mbar_wait(smem_u32(full + s), full_ph);
         CM_PROBE(unsigned long long pr_b = global_ns(); pr_wait += pr_b - pr_a; ++pr_n;)
-        const int chunk = d.idx % a.chunks, slab = d.idx / a.chunks;
-        const int p0 = (chunk * 256 + tid) * 4, c0 = slab * CH;
+        const int p0 = (d.chunk * 256 + lt) * 4, c0 = d.slab * CH;
         const bool live = p0 < a.P;
         const uint8_t *stb = smem_raw + s * kStageBytes;
         const float4 *st = reinterpret_cast<const float4 *>(stb);
-        const uint32_t mw = live ? reinterpret_cast<const uint32_t *>(stb + CH * (R + 1) * 4096)[tid] : 0u;
+        const uint32_t mw = live ? reinterpret_cast<const uint32_t *>(stb + CH * (R + 1) * 4096)[lt] : 0u;
         if (!d.copy) {
             // ---------------- S item: partial similarity ----------------
-            float acc[2 * R];
+            float acc[G2];
 #pragma unroll
-            for (int r = 0; r < 2 * R; ++r) acc[r] = 0.0f;
+            for (int r = 0; r < G2; ++r) acc[r] = 0.0f;
             if (live) {
                 float4 vm[R];
 #pragma unroll
@@ -609,15 +696,15 @@ __global__ void __launch_bounds__(kCmThreads, 1) cm_pipe_kernel(const __grid_con
                     const uint32_t m = mw & (mw >> (r + 1)) & 0x01010101u;
                     vm[r] = make_float4((float)(m & 1u), (float)((m >> 8) & 1u), (float)((m >> 16) & 1u),
                                         (float)((m >> 24) & 1u));
-                    if (slab == 0) acc[R + r] = (vm[r].x + vm[r].y) + (vm[r].z + vm[r].w);  // :221
+                    if (d.slab == 0) acc[R + r] = (vm[r].x + vm[r].y) + (vm[r].z + vm[r].w);  // :221
                 }
 #pragma unroll
                 for (int k = 0; k < CH; ++k) {
                     if (c0 + k < a.C) {
-                        const float4 ct = st[(k * (R + 1)) * 256 + tid];
+                        const float4 ct = st[(k * (R + 1)) * 256 + lt];
 #pragma unroll
                         for (int r = 0; r < R; ++r) {  // vmap * c_t * c_r            :226
-                            const float4 cr = st[(k * (R + 1) + r + 1) * 256 + tid];
+                            const float4 cr = st[(k * (R + 1) + r + 1) * 256 + lt];
                             acc[r] += vm[r].x * ct.x * cr.x;
                             acc[r] += vm[r].y * ct.y * cr.y;
                             acc[r] += vm[r].z * ct.z * cr.z;
@@ -628,29 +715,62 @@ __global__ void __launch_bounds__(kCmThreads, 1) cm_pipe_kernel(const __grid_con
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(empty + s));  // the stage may be refilled
-            compute_sum<2 * R>(acc, red[n_sim & 1]);  // double-buffered: warp 0 reads while the others move on
-            if (tid == 0) {
-                while (n_sim - mb_done >= kMailbox) __nanosleep(100);
-                const int slot = n_sim % kMailbox;
+            // CTA-group sum of the 2R values, fixed order; double-buffered scratch: warp 0 of the group
+            // reads while the others move on to their next item
+            float *rd = red[grp][n_sim & 1];
+            const int slot = n_sim % kMailbox;
+            if constexpr (G2 == 8) {
+                const float y = warp_sum8(acc);
+                if ((lane & 3) == 0) rd[(lane >> 2) * 8 + lw] = y;
+                bar_group(bar_id);
+                if (lw == 0) {
+                    float t = rd[(lane >> 2) * 8 + 2 * (lane & 3)] + rd[(lane >> 2) * 8 + 2 * (lane & 3) + 1];
+                    t += __shfl_xor_sync(0xffffffffu, t, 1);
+                    t += __shfl_xor_sync(0xffffffffu, t, 2);
+                    if (lane == 0) while (n_sim - mb_done[grp] >= kMailbox) __nanosleep(100);
+                    __syncwarp();
+                    if ((lane & 3) == 0) mbox[grp][slot][lane >> 2] = t;
+                }
+            } else {
 #pragma unroll
-                for (int r = 0; r < 2 * R; ++r) mbox[slot][r] = acc[r];
-                mbox_b[slot] = d.b;
-                mbox_idx[slot] = d.idx;
-                __threadfence_block();
-                mb_ready = n_sim + 1;
+                for (int k = 0; k < G2; ++k) {
+                    acc[k] = warp_sum(acc[k]);
+                    if (lane == 0) rd[k * 8 + lw] = acc[k];
+                }
+                bar_group(bar_id);
+                if (lw == 0) {
+                    if (lane == 0) while (n_sim - mb_done[grp] >= kMailbox) __nanosleep(100);
+                    __syncwarp();
+                    if (lane < G2) {
+                        float t = 0.0f;
+#pragma unroll
+                        for (int w8 = 0; w8 < 8; ++w8) t += rd[lane * 8 + w8];
+                        mbox[grp][slot][lane] = t;
+                    }
+                }
+            }
+            if (lw == 0) {
+                __syncwarp();
+                if (lane == 0) {
+                    mbox_b[grp][slot] = d.b;
+                    mbox_idx[grp][slot] = d.idx;
+                    __threadfence_block();
+                    mb_ready[grp] = n_sim + 1;
+                }
             }
             ++n_sim;
         } else {
             // ---------------- C item: cat[c_t, sum_r c_r * w_r] ----------------
-            float *tb = tabs + (n & 1) * TABF;
+            float *tb = gtabs + (i & 1) * TABF;
             bool bad = false;
-            if (tid < TABF / 4) {  // the chunk this thread fetched one item ago
-                const float4 t4 = reinterpret_cast<const float4 *>(tb)[tid];
+            if (lt < TABF / 4) {  // the chunk this thread fetched one item ago
+                const float4 t4 = reinterpret_cast<const float4 *>(tb)[lt];
                 bad = isnan(t4.x) || isnan(t4.y) || isnan(t4.z) || isnan(t4.w);
             }
-            if (bar_compute_or(bad)) {  // also: the table chunks of the other threads are visible
-                CM_PROBE(++pr_slow; unsigned long long sl_t = global_ns();)
-                if (tid == 0) {
+            if (bar_group_or(bar_id, bad)) {  // also: the table chunks of the other threads are visible
+                CM_PROBE(++pr_slow; unsigned long long sl_t = global_ns();
+                         if (lt == 0 && d.b < 64) atomicMin(&g_cm_probe2[1088 + d.b], sl_t);)
+                if (lt == 0) {
                     CM_PROBE(if (ld_acquire(a.flag + d.b) != 0u && blockIdx.x < 256) g_cm_probe2[blockIdx.x * 8 + 0] += 1;)
                     if (ld_acquire(a.flag + d.b) == 0u) {
                         const unsigned long long t0 = global_ns();
@@ -660,9 +780,9 @@ __global__ void __launch_bounds__(kCmThreads, 1) cm_pipe_kernel(const __grid_con
                         }
                     }
                 }
-                bar_compute();
-                for (int q = tid; q < TABF; q += 256) tb[q] = __ldcg(a.table + (int64_t)d.b * TABF + q);
-                bar_compute();
+                bar_group(bar_id);
+                for (int q = lt; q < TABF; q += 256) tb[q] = __ldcg(a.table + (int64_t)d.b * TABF + q);
+                bar_group(bar_id);
                 CM_PROBE(if (tid == 0 && blockIdx.x < 256) g_cm_probe2[blockIdx.x * 8 + 1] += global_ns() - sl_t;)
             }
             if (live) {
@@ -670,7 +790,7 @@ __global__ void __launch_bounds__(kCmThreads, 1) cm_pipe_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 4; ++j) pat[j] = (int)((mw >> (8 * j + 1)) & ((1u << R) - 1u)) * (R + 1);
                 float *ob = a.out + (int64_t)d.b * (2 * a.C + 1) * a.P + p0;
-                if (slab == 0) {
+                if (d.slab == 0) {
                     const float4 c4 = make_float4(tb[pat[0] + R], tb[pat[1] + R], tb[pat[2] + R], tb[pat[3] + R]);
                     st_stream4(ob + (int64_t)(2 * a.C) * a.P, c4);
                     st_stream4(a.c_mask + (int64_t)d.b * a.P + p0, c4);
@@ -685,40 +805,42 @@ __global__ void __launch_bounds__(kCmThreads, 1) cm_pipe_kernel(const __grid_con
                     float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
                     for (int r = 0; r < R; ++r) {  // sum_r c_r * w_r, sequential over r    :238
-                        const float4 cr = st[(k * (R + 1) + r + 1) * 256 + tid];
+                        const float4 cr = st[(k * (R + 1) + r + 1) * 256 + lt];
                         o.x = __fadd_rn(o.x, __fmul_rn(cr.x, wg[r].x));
                         o.y = __fadd_rn(o.y, __fmul_rn(cr.y, wg[r].y));
                         o.z = __fadd_rn(o.z, __fmul_rn(cr.z, wg[r].z));
                         o.w = __fadd_rn(o.w, __fmul_rn(cr.w, wg[r].w));
                     }
-                    st_stream4(ob + (int64_t)c * a.P, st[(k * (R + 1)) * 256 + tid]);  // cat[c_t, ...]  :243
+                    st_stream4(ob + (int64_t)c * a.P, st[(k * (R + 1)) * 256 + lt]);  // cat[c_t, ...]  :243
                     st_stream4(ob + (int64_t)(a.C + c) * a.P, o);
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(empty + s));  // the stage may be refilled
         }
-        // table of the next item: slot (n + 1) & 1 was last read by item n - 1, and every thread has
-        // passed the barrier of item n
-        if (tn) reinterpret_cast<float4 *>(tabs + ((n + 1) & 1) * TABF)[tid] = tnext;
+        // table of the group's next item: slot (i + 1) & 1 was last read by item i - 1 of the group, and
+        // every thread of the group has passed the barrier of item i
+        if (tn) reinterpret_cast<float4 *>(gtabs + ((i + 1) & 1) * TABF)[lt] = tnext;
         CM_PROBE(if (d.copy) pr_c += global_ns() - pr_b; else pr_s += global_ns() - pr_b;)
+        ++i;
     }
-    CM_PROBE(if (tid == 0 && blockIdx.x < 256) {
+    CM_PROBE(if (lt == 0 && grp == 0 && blockIdx.x < 256) {
         unsigned long long *o = g_cm_probe + blockIdx.x * 8;
         o[0] = global_ns() - pr_t0; o[1] = pr_wait; o[2] = pr_s; o[3] = pr_c; o[4] = pr_slow; o[5] = pr_n;
     })
-    if (tid == 0) { __threadfence_block(); mb_fin = 1; }
+    if (lt == 0) { __threadfence_block(); mb_fin[grp] = 1; }
 }
 
+constexpr int kCmGroups = 2;
 template <int R, int CH>
 constexpr int cm_pipe_smem(int nst) {
-    return nst * cm_stage_bytes<R, CH>() + 2 * cm_table_floats<R>() * 4;
+    return nst * cm_stage_bytes<R, CH>() + kCmGroups * 2 * cm_table_floats<R>() * 4;
 }
 
 template <int R, int CH, int NST>
 int launch_cm_pipe_n(CmArgs a, cudaStream_t st) {
     constexpr int smem = cm_pipe_smem<R, CH>(NST);
-    auto kern = cm_pipe_kernel<R, CH, NST>;
+    auto kern = cm_pipe_kernel<R, CH, NST, kCmGroups>;
     static bool ready = false;
     if (!ready) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -729,15 +851,29 @@ int launch_cm_pipe_n(CmArgs a, cudaStream_t st) {
     }
     a.n_items = a.chunks * ((a.C + CH - 1) / CH);
     a.nparts = a.n_items;
-    a.lag = tuning("MT_CM_LAG", 2);
-    if (a.lag < 1) a.lag = 1;
-    if (a.lag > a.B) a.lag = a.B;
-    const int64_t total = 2ll * a.B * a.n_items;
-    if (total > (1ll << 30)) return -1;
+    const int64_t total = (int64_t)a.B * a.n_items;  // per stream
+    if (total > (1ll << 29)) return -1;
     int64_t grid = sm_count();  // one resident wave (1 CTA/SM): the CTAs wait on each other
-    if (grid > total) grid = total;
+    if (grid * kCmGroups > total) grid = (total + kCmGroups - 1) / kCmGroups;
+    a.workers = (int)grid * kCmGroups;
+    a.rounds = (int)((total + a.workers - 1) / a.workers);
+    // every S item of a sample before any C item of it in the common round sequence (cm_decode), plus
+    // MT_CM_LAG rounds so that the table of a sample is normally published before its first C item
+    int need = 1;
+    for (int b = 0; b < a.B; ++b) {
+        const int i_max = (int)((((int64_t)b + 1) * a.n_items - 1) / a.workers);
+        const int j_min = (int)(((int64_t)b * a.n_items) / a.workers);
+        if (i_max - j_min + 1 > need) need = i_max - j_min + 1;
+    }
+    a.lag = tuning("MT_CM_LAG", 2);
+    if (a.lag < 0) a.lag = 0;
+    if (a.lag > 4) a.lag = 4;
+    a.head = need + a.lag;
+    if (a.head > a.rounds) a.head = a.rounds;
+    a.dv_items = make_fastdiv((uint32_t)a.n_items);
+    a.dv_chunks = make_fastdiv((uint32_t)a.chunks);
     launch(cm_masks_kernel, dim3((a.P + 255) / 256, a.B), 256, 0, st, a);
-    launch(kern, dim3((unsigned)grid), kCmThreads, (size_t)smem, st, a);
+    launch(kern, dim3((unsigned)grid), kCmGroups * 256 + 64, (size_t)smem, st, a);
     return launch_status("mt_cm_match_fwd");
 }
 
@@ -757,9 +893,10 @@ int launch_cm_pipe(CmArgs a, cudaStream_t st) {
 template <int R>
 int launch_cm(CmArgs a, cudaStream_t st) {
     // one persistent launch (pass 2 from L2); MT_CM_FUSED=0 keeps the three-launch path
+    // MT_CM_FUSED=1 (experimental, off): the persistent pipelined kernel K3p.  Parity-green, but on B200
+    // it is 1.5-2x slower than the three launches at every batch size (profiles/r1_experiments.md).
     if (R <= 7 && tuning("MT_CM_FUSED", 0)) {  // the mask byte holds the target and up to 7 references
-        const int ch = tuning("MT_CM_FUSED_CH", 2);
-        const int rc = ch == 4 ? launch_cm_pipe<R, 4>(a, st) : (ch == 1 ? launch_cm_pipe<R, 1>(a, st) : launch_cm_pipe<R, 2>(a, st));
+        const int rc = launch_cm_pipe<R, 2>(a, st);
         if (rc >= 0) return rc;
     }
     a.b_off = 0;
@@ -841,6 +978,7 @@ extern "C" int mt_cm_match_fwd(const float *c_feats, const float *v_t, const flo
     ws += align256((int64_t)B * a.P);
     a.table = reinterpret_cast<float *>(ws);
     a.n_items = 0; a.lag = 1;
+    a.copy_reverse = tuning("MT_CM_COPY_REVERSE", 1);
     cudaStream_t st = (cudaStream_t)stream;
     switch (a.R) {
         case 1: return launch_cm<1>(a, st);
@@ -863,6 +1001,11 @@ extern "C" const float *mt_cm_workspace_gs(const void *workspace, int B, int C, 
 }
 
 #ifdef MT_DEV_PROBES
+extern "C" __attribute__((visibility("default"))) int mt_debug_cm_reset(void) {
+    static unsigned long long init[2048];
+    for (int i = 0; i < 2048; ++i) init[i] = (i >= 1088 && i < 1152) ? ~0ull : 0ull;
+    return cudaMemcpyToSymbol(mt::g_cm_probe2, init, sizeof(init)) == cudaSuccess ? 0 : -2;
+}
 extern "C" __attribute__((visibility("default"))) int mt_debug_cm_probe(unsigned long long *dst, int n) {
     cudaDeviceSynchronize();
     if (n < 0) return cudaMemcpyFromSymbol(dst, mt::g_cm_probe2, sizeof(unsigned long long) * 2048) == cudaSuccess ? 0 : -2;

@@ -35,9 +35,11 @@
 namespace mt {
 namespace {
 
-constexpr int kTile = 32;           // output tile: 32 x 32 pixels
-constexpr int kConsWarps = 16;      // 2 rows each
-constexpr int kStagedThreads = (kConsWarps + 1) * 32;
+constexpr int kTileH = 32;          // output tile: TW x 32 pixels, TW = 32 or 64
+// TW / 2 consumer warps (16 x 4 pixels each); TW = 32: + a dedicated producer warp; TW = 64: 32 consumer
+// warps are the 1024-thread limit, the consumer warps take turns as producer (one tile each)
+constexpr bool staged_own_producer(int tw) { return tw == 32; }
+constexpr int staged_threads(int tw) { return (tw / 2 + (staged_own_producer(tw) ? 1 : 0)) * 32; }
 constexpr int kMaxTable = 1024;     // W, H <= 1024 (tables of the base grid in shared memory)
 
 struct TileDesc {  // written by the producer, read by the consumers after the full barrier
@@ -69,22 +71,24 @@ struct WarpStagedArgs {
     Sampler sp;
 };
 
-template <int BOX, int STAGES>
+template <int TW, int BW, int BH, int STAGES>
 constexpr int staged_smem_bytes() {
-    return STAGES * (4 * BOX * BOX + kTile * kTile) * 4 + 2 * kMaxTable * 4 + STAGES * (int)sizeof(TileDesc) +
+    return STAGES * (4 * BW * BH + TW * kTileH) * 4 + 2 * kMaxTable * 4 + STAGES * (int)sizeof(TileDesc) +
            2 * STAGES * 8 + 128;
 }
 
 __device__ __forceinline__ float unnorm_t(float g, float sf, bool ac) { return unnormalize(g, sf, ac); }
 
 // AC: align_corners; FM: `vis` holds masks (v = 1 - m inside the frame, 0 outside)
-template <int BOX, int STAGES, int CPS, bool AC, bool FM>
-__global__ void __launch_bounds__(kStagedThreads, CPS)
+template <int TW, int BW, int BH, int STAGES, bool AC, bool FM>
+__global__ void __launch_bounds__(staged_threads(TW), 1)
 warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_v,
                    const __grid_constant__ CUtensorMap map_t, const WarpStagedArgs a) {
-    constexpr int kPlane = BOX * BOX;
-    constexpr int kStageFloats = 4 * kPlane + kTile * kTile;  // RGB + mask boxes, target-mask tile
-    constexpr uint32_t kMtBytes = kTile * kTile * 4u;
+    static_assert(BW % 32 == 16, "a source row must start 16 banks after the previous one (see the lane mapping)");
+    constexpr int kConsWarps = TW / 2, kStagedThreads = staged_threads(TW);
+    constexpr int kPlane = BW * BH;
+    constexpr int kStageFloats = 4 * kPlane + TW * kTileH;  // RGB + mask boxes, target-mask tile
+    constexpr uint32_t kMtBytes = TW * kTileH * 4u;
     // 128 B alignment (TMA destination) comes from the declaration: a manual round-up through
     // uintptr_t makes the compiler lose the shared address space (generic LD/ST instead of LDS/STS)
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -118,81 +122,105 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
     const float wmax = a.sp.wmax, hmax = a.sp.hmax;
 
-    if (warp == kConsWarps) {
-        // ===================== producer =====================
-        if (lane == 0) {
-            // The descriptor of a tile (theta load, two integer divisions, four corner evaluations) is
-            // prepared while its stage is still in use: between "stage released" and "TMA issued"
-            // there is only the descriptor store (ncu: consumers polled the full barrier 2.9 times
-            // per tile while this chain sat behind the empty wait).
-            auto prepare = [&](int t) {
-                TileDesc d;
-                const int n = t / a.tiles_per_frame, r = t - n * a.tiles_per_frame;
-                const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+    // ---- producer duty (one thread at a time) ----
+    // The descriptor of a tile: theta load, two integer divisions, four corner evaluations.
+    auto prepare = [&](int t) {
+        TileDesc d;
+        const int n = t / a.tiles_per_frame, r = t - n * a.tiles_per_frame;
+        const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
 #pragma unroll
-                for (int j = 0; j < 6; ++j) d.th[j] = __ldg(a.theta + n * 6 + j);
-                const int b = n / a.F, f = n - b * a.F;
-                const int xs[2] = {tx * kTile, min(tx * kTile + kTile - 1, W - 1)};
-                const int ys[2] = {ty * kTile, min(ty * kTile + kTile - 1, H - 1)};
-                float xlo = 3.0e38f, xhi = -3.0e38f, ylo = 3.0e38f, yhi = -3.0e38f;
-                bool finite = true;
+        for (int j = 0; j < 6; ++j) d.th[j] = __ldg(a.theta + n * 6 + j);
+        const int b = n / a.F, f = n - b * a.F;
+        const int xs[2] = {tx * TW, min(tx * TW + TW - 1, W - 1)};
+        const int ys[2] = {ty * kTileH, min(ty * kTileH + kTileH - 1, H - 1)};
+        float xlo = 3.0e38f, xhi = -3.0e38f, ylo = 3.0e38f, yhi = -3.0e38f;
+        bool finite = true;
 #pragma unroll
-                for (int cy = 0; cy < 2; ++cy) {
+        for (int cy = 0; cy < 2; ++cy) {
 #pragma unroll
-                    for (int cx = 0; cx < 2; ++cx) {
-                        const float bx = s_bx[xs[cx]], by = s_by[ys[cy]];
-                        // identical to the consumers' arithmetic below
-                        const float gx = __fadd_rn(__fmaf_rn(by, d.th[1], __fmul_rn(bx, d.th[0])), d.th[2]);
-                        const float gy = __fadd_rn(__fmaf_rn(by, d.th[4], __fmul_rn(bx, d.th[3])), d.th[5]);
-                        const float xw = floorf(unnorm_t(gx, a.sp.sfx, AC)), yn = floorf(unnorm_t(gy, a.sp.sfy, AC));
-                        finite = finite && (fabsf(xw) <= 1.0e6f) && (fabsf(yn) <= 1.0e6f);  // false for NaN / inf
-                        xlo = fminf(xlo, xw); xhi = fmaxf(xhi, xw);
-                        ylo = fminf(ylo, yn); yhi = fmaxf(yhi, yn);
-                    }
-                }
-                // taps span [xlo, xhi + 1] x [ylo, yhi + 1].  TMA needs the innermost start coordinate on a
-                // 16 B boundary (an unaligned one faults with "illegal instruction", tools/tma_probe.cu), so
-                // the box origin is xlo rounded down to a multiple of 4 pixels (two's complement: also for
-                // negative coordinates)
-                const int bx0 = finite ? ((int)xlo & ~3) : 0, by0 = finite ? (int)ylo : 0;
-                const bool fits = finite && ((int)xhi + 2 - bx0 <= BOX) && ((int)yhi + 2 - by0 <= BOX) && !(a.debug & 1);
-                const bool inside = fits && xlo >= 0.0f && xhi + 1.0f <= wmax && ylo >= 0.0f && yhi + 1.0f <= hmax;
-                d.flags = (fits ? 1 : 0) | (inside ? 2 : 0);
-                d.bx0 = bx0; d.by0 = by0;
-                d.b = b; d.f = f; d.n = n; d.tx = tx; d.ty = ty;
-                d.pad[0] = d.pad[1] = 0;
-                return d;
-            };
-            int t = blockIdx.x;
-            TileDesc d;
-            if (t < a.n_tiles) d = prepare(t);
-            for (int i = 0; t < a.n_tiles; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-                mbar_wait(smem_u32(empty + s), ph ^ 1u);
-                desc[s] = d;
-                const bool fits = (d.flags & 1) != 0;
-                float *dst = stage0 + s * kStageFloats;
-                mbar_expect_tx(smem_u32(full + s), fits ? 4u * kPlane * 4u + kMtBytes : kMtBytes);
-                if (fits) {
-                    // x as (W, H, C, F, B): box (BOX, BOX, 3, 1, 1); masks as (W, H, F, B): box (BOX, BOX, 1, 1)
-                    tma_load_5d(smem_u32(dst), &map_x, smem_u32(full + s), d.bx0, d.by0, 0, d.f, d.b);
-                    tma_load_4d(smem_u32(dst + 3 * kPlane), &map_v, smem_u32(full + s), d.bx0, d.by0, d.f, d.b);
-                }
-                // target mask as (W, H, B): the tile itself
-                tma_load_3d(smem_u32(dst + 4 * kPlane), &map_t, smem_u32(full + s), d.tx * kTile, d.ty * kTile, d.b);
-                if (probe && i == 0) g_timeline[blockIdx.x * 8 + 2] = gtime();
-                t += gridDim.x;
-                if (t < a.n_tiles) d = prepare(t);
+            for (int cx = 0; cx < 2; ++cx) {
+                const float bx = s_bx[xs[cx]], by = s_by[ys[cy]];
+                // identical to the consumers' arithmetic below
+                const float gx = __fadd_rn(__fmaf_rn(by, d.th[1], __fmul_rn(bx, d.th[0])), d.th[2]);
+                const float gy = __fadd_rn(__fmaf_rn(by, d.th[4], __fmul_rn(bx, d.th[3])), d.th[5]);
+                const float xw = floorf(unnorm_t(gx, a.sp.sfx, AC)), yn = floorf(unnorm_t(gy, a.sp.sfy, AC));
+                finite = finite && (fabsf(xw) <= 1.0e6f) && (fabsf(yn) <= 1.0e6f);  // false for NaN / inf
+                xlo = fminf(xlo, xw); xhi = fmaxf(xhi, xw);
+                ylo = fminf(ylo, yn); yhi = fmaxf(yhi, yn);
             }
         }
-        return;
+        // taps span [xlo, xhi + 1] x [ylo, yhi + 1].  TMA needs the innermost start coordinate on a
+        // 16 B boundary (an unaligned one faults with "illegal instruction", tools/tma_probe.cu), so
+        // the box origin is xlo rounded down to a multiple of 4 pixels (two's complement: also for
+        // negative coordinates)
+        const int bx0 = finite ? ((int)xlo & ~3) : 0, by0 = finite ? (int)ylo : 0;
+        const bool fits = finite && ((int)xhi + 2 - bx0 <= BW) && ((int)yhi + 2 - by0 <= BH) && !(a.debug & 1);
+        const bool inside = fits && xlo >= 0.0f && xhi + 1.0f <= wmax && ylo >= 0.0f && yhi + 1.0f <= hmax;
+        d.flags = (fits ? 1 : 0) | (inside ? 2 : 0);
+        d.bx0 = bx0; d.by0 = by0;
+        d.b = b; d.f = f; d.n = n; d.tx = tx; d.ty = ty;
+        d.pad[0] = d.pad[1] = 0;
+        return d;
+    };
+    // i-th tile of this CTA -> stage i % STAGES (waits until the consumers have released it)
+    auto issue = [&](int i, const TileDesc &d) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(smem_u32(empty + s), ph ^ 1u);
+        desc[s] = d;
+        const bool fits = (d.flags & 1) != 0;
+        float *dst = stage0 + s * kStageFloats;
+        mbar_expect_tx(smem_u32(full + s), fits ? 4u * kPlane * 4u + kMtBytes : kMtBytes);
+        if (fits) {
+            // x as (W, H, C, F, B): box (BW, BH, 3, 1, 1); masks as (W, H, F, B): box (BW, BH, 1, 1)
+            tma_load_5d(smem_u32(dst), &map_x, smem_u32(full + s), d.bx0, d.by0, 0, d.f, d.b);
+            tma_load_4d(smem_u32(dst + 3 * kPlane), &map_v, smem_u32(full + s), d.bx0, d.by0, d.f, d.b);
+        }
+        // target mask as (W, H, B): the tile itself
+        tma_load_3d(smem_u32(dst + 4 * kPlane), &map_t, smem_u32(full + s), d.tx * TW, d.ty * kTileH, d.b);
+        if (probe && i == 0) g_timeline[blockIdx.x * 8 + 2] = gtime();
+    };
+
+    if constexpr (staged_own_producer(TW)) {
+        if (warp == kConsWarps) {
+            // ===================== producer warp =====================
+            // The descriptor of the next tile is prepared while its stage is still in use: between
+            // "stage released" and "TMA issued" there is only the descriptor store (ncu: consumers
+            // polled the full barrier 2.9 times per tile while this chain sat behind the empty wait).
+            if (lane == 0) {
+                int t = blockIdx.x;
+                TileDesc d;
+                if (t < a.n_tiles) d = prepare(t);
+                for (int i = 0; t < a.n_tiles; ++i) {
+                    issue(i, d);
+                    t += gridDim.x;
+                    if (t < a.n_tiles) d = prepare(t);
+                }
+            }
+            return;
+        }
+    } else {
+        // no spare warp (32 consumer warps = 1024 threads): the first STAGES - 1 tiles are issued here,
+        // tile i + STAGES - 1 by consumer warp i % kConsWarps at the top of its iteration i
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < STAGES - 1; ++i) {
+                const int t = blockIdx.x + i * gridDim.x;
+                if (t < a.n_tiles) issue(i, prepare(t));
+            }
+        }
     }
 
     // ===================== consumers =====================
     const float wm2 = wmax - 1.0f, hm2 = hmax - 1.0f;
     int i = 0;
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
+        if constexpr (!staged_own_producer(TW)) {
+            if (lane == 0 && warp == i % kConsWarps) {
+                const int tj = t + (STAGES - 1) * gridDim.x;
+                if (tj < a.n_tiles) issue(i + STAGES - 1, prepare(tj));
+            }
+            __syncwarp();
+        }
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         mbar_wait(smem_u32(full + s), ph);
@@ -207,21 +235,16 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         // the previous one, so the two half-warps read disjoint bank ranges and a tap instruction is
         // one shared-memory wavefront; the 32 x 1 mapping had 2-way conflicts wherever the footprint
         // of the 32 lanes stepped to the next source row (ncu: 44 % of the LDS wavefronts).
-#ifdef MT_WARP_MAP_32X1
-        const int tcol = lane, trow = 2 * warp;
-        constexpr int kRowStep = 1;
-#else
-        const int tcol = (warp & 1) * 16 + (lane & 15), trow = (warp >> 1) * 4 + (lane >> 4);
-        constexpr int kRowStep = 2;
-#endif
-        const int xg = d1.z * kTile + tcol, y0 = d1.w * kTile + trow;
+        constexpr int kColGroups = TW / 16, kRowStep = 2;
+        const int tcol = (warp % kColGroups) * 16 + (lane & 15), trow = (warp / kColGroups) * 4 + (lane >> 4);
+        const int xg = d1.z * TW + tcol, y0 = d1.w * kTileH + trow;
         const bool live = xg < W;
         const int x = min(xg, W - 1);
         const int p0 = y0 * W + x;
         const float *st = stage0 + s * kStageFloats;
         float mtv[2];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) mtv[k] = st[4 * kPlane + (trow + k * kRowStep) * kTile + tcol];
+        for (int k = 0; k < 2; ++k) mtv[k] = st[4 * kPlane + (trow + k * kRowStep) * TW + tcol];
         const float bx = s_bx[x];
         const float bxt0 = __fmul_rn(bx, d2.x), bxt3 = __fmul_rn(bx, d2.w);
         float ix[2], iy[2], xw[2], yn[2], wnw[2], wne[2], wsw[2], wse[2];
@@ -245,11 +268,11 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             float q[4][2][4];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const float *p = st + (((int)yn[k] - by0) * BOX + ((int)xw[k] - bx0));
+                const float *p = st + (((int)yn[k] - by0) * BW + ((int)xw[k] - bx0));
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     q[c][k][0] = p[c * kPlane]; q[c][k][1] = p[c * kPlane + 1];
-                    q[c][k][2] = p[c * kPlane + BOX]; q[c][k][3] = p[c * kPlane + BOX + 1];
+                    q[c][k][2] = p[c * kPlane + BW]; q[c][k][3] = p[c * kPlane + BW + 1];
                 }
             }
             __syncwarp();
@@ -320,6 +343,89 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
 }  // namespace
 
+namespace {
+struct StagedHost {
+    const float *x, *vis, *theta, *m_target;
+    float *x_al, *v_al, *v_map;
+    int64_t x_sb, x_sc, x_sf, vis_sb, vis_sf, mt_sb, xa_sb, xa_sc, xa_sf;
+    int B, F, H, W;
+    bool ac, from_mask;
+    cudaStream_t st;
+    EncodeTiledFn enc;
+};
+
+template <int TW, int BW, int BH, int STAGES>
+int staged_go(const StagedHost &h) {
+    const int W = h.W, H = h.H;
+    const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + kTileH - 1) / kTileH;
+    const int64_t n_tiles = (int64_t)h.B * h.F * tiles_x * tiles_y;
+    // tiny problems cannot fill a persistent grid of one CTA per SM: keep the strip kernel
+    if (n_tiles < 2 * (int64_t)sm_count() || n_tiles > (1ll << 30)) return 0;
+    CUtensorMap map_x, map_v, map_t;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)h.B};
+        cuuint64_t strides[2] = {(cuuint64_t)W * 4, h.mt_sb ? (cuuint64_t)h.mt_sb * 4 : 16};
+        cuuint32_t bx[3] = {(cuuint32_t)TW, (cuuint32_t)kTileH, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = h.enc(&map_t, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(h.m_target), dims, strides,
+                           bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 0;
+    }
+    {
+        cuuint64_t dims[5] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)h.F, (cuuint64_t)h.B};
+        cuuint64_t strides[4] = {(cuuint64_t)W * 4, (cuuint64_t)h.x_sc * 4, (cuuint64_t)h.x_sf * 4,
+                                 (cuuint64_t)h.x_sb * 4};
+        // a stride of 0 bytes (B or F of extent 1 sliced out of a view) is not encodable: any multiple of 16 is fine there
+        for (int i = 1; i < 4; ++i) if (strides[i] == 0) strides[i] = 16;
+        cuuint32_t bx[5] = {(cuuint32_t)BW, (cuuint32_t)BH, 3, 1, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = h.enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(h.x), dims, strides, bx, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 0;  // e.g. strides beyond the encodable range: direct kernel
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)h.F, (cuuint64_t)h.B};
+        cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)h.vis_sf * 4, (cuuint64_t)h.vis_sb * 4};
+        for (int i = 1; i < 3; ++i) if (strides[i] == 0) strides[i] = 16;
+        cuuint32_t bx[4] = {(cuuint32_t)BW, (cuuint32_t)BH, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = h.enc(&map_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(h.vis), dims, strides, bx,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 0;
+    }
+    WarpStagedArgs a;
+    a.x = h.x; a.vis = h.vis; a.theta = h.theta; a.m_target = h.m_target;
+    a.x_al = h.x_al; a.v_al = h.v_al; a.v_map = h.v_map;
+    a.x_sb = (int)h.x_sb; a.x_sc = (int)h.x_sc; a.x_sf = (int)h.x_sf;
+    a.vis_sb = (int)h.vis_sb; a.vis_sf = (int)h.vis_sf; a.mt_sb = (int)h.mt_sb;
+    a.xa_sb = (int)h.xa_sb; a.xa_sc = (int)h.xa_sc; a.xa_sf = (int)h.xa_sf;
+    a.F = h.F; a.P = H * W; a.tiles_x = tiles_x; a.tiles_per_frame = tiles_x * tiles_y; a.n_tiles = (int)n_tiles;
+    a.sp = make_sampler(H, W, h.ac);
+    a.debug = tuning("MT_WARP_DBG", 0);
+    int ctas = sm_count();
+    if (ctas > n_tiles) ctas = (int)n_tiles;
+    constexpr int smem = staged_smem_bytes<TW, BW, BH, STAGES>();
+    static_assert(smem <= 227 * 1024, "stage ring exceeds the shared memory of an SM");
+#define MT_STAGED_GO(ACV, FMV)                                                                       \
+    do {                                                                                             \
+        auto kern = warp_staged_kernel<TW, BW, BH, STAGES, ACV, FMV>;                                \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e != cudaSuccess) {                                                                      \
+            set_error("mt_warp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));               \
+            return MT_ERR_CUDA;                                                                      \
+        }                                                                                            \
+        launch(kern, dim3(ctas), dim3(staged_threads(TW)), (size_t)smem, h.st, map_x, map_v, map_t, a); \
+    } while (0)
+    if (h.ac) { if (h.from_mask) MT_STAGED_GO(true, true); else MT_STAGED_GO(true, false); }
+    else      { if (h.from_mask) MT_STAGED_GO(false, true); else MT_STAGED_GO(false, false); }
+#undef MT_STAGED_GO
+    return 1;
+}
+}  // namespace
+
 // 1 = launched, 0 = not applicable (caller uses the direct-gather kernel), < 0 = error.
 int warp_staged_launch(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf, const float *vis,
                        int64_t vis_sb, int64_t vis_sf, const float *theta, const float *m_target,
@@ -332,81 +438,18 @@ int warp_staged_launch(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
     // TMA: 16 B aligned base, every stride a multiple of 16 B
     if ((W & 3) || (x_sb & 3) || (x_sc & 3) || (x_sf & 3) || (vis_sb & 3) || (vis_sf & 3)) return 0;
     if (!aligned16(x) || !aligned16(vis) || !aligned16(m_target) || (mt_sb & 3)) return 0;
-    const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile;
-    const int64_t n_tiles = (int64_t)B * F * tiles_x * tiles_y;
-    // tiny problems cannot fill a persistent grid of 148 CTAs x 16 warps: keep the strip kernel
-    if (n_tiles < 2 * (int64_t)sm_count() || n_tiles > (1ll << 30)) return 0;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return 0;
-    const int box = tuning("MT_WARP_BOX", 48) == 40 ? 40 : 48;
-    CUtensorMap map_x, map_v, map_t;
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[2] = {(cuuint64_t)W * 4, mt_sb ? (cuuint64_t)mt_sb * 4 : 16};
-        cuuint32_t bx[3] = {(cuuint32_t)kTile, (cuuint32_t)kTile, 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&map_t, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(m_target), dims, strides, bx,
-                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return 0;
-    }
-    {
-        cuuint64_t dims[5] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)F, (cuuint64_t)B};
-        cuuint64_t strides[4] = {(cuuint64_t)W * 4, (cuuint64_t)x_sc * 4, (cuuint64_t)x_sf * 4, (cuuint64_t)x_sb * 4};
-        // a stride of 0 bytes (B or F of extent 1 sliced out of a view) is not encodable: any multiple of 16 is fine there
-        for (int i = 1; i < 4; ++i) if (strides[i] == 0) strides[i] = 16;
-        cuuint32_t bx[5] = {(cuuint32_t)box, (cuuint32_t)box, 3, 1, 1};
-        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(x), dims, strides, bx, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return 0;  // e.g. strides beyond the encodable range: direct kernel
-    }
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)F, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)vis_sf * 4, (cuuint64_t)vis_sb * 4};
-        for (int i = 1; i < 3; ++i) if (strides[i] == 0) strides[i] = 16;
-        cuuint32_t bx[4] = {(cuuint32_t)box, (cuuint32_t)box, 1, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = enc(&map_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(vis), dims, strides, bx, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return 0;
-    }
-    WarpStagedArgs a;
-    a.x = x; a.vis = vis; a.theta = theta; a.m_target = m_target;
-    a.x_al = x_aligned; a.v_al = v_aligned; a.v_map = v_map;
-    a.x_sb = (int)x_sb; a.x_sc = (int)x_sc; a.x_sf = (int)x_sf;
-    a.vis_sb = (int)vis_sb; a.vis_sf = (int)vis_sf; a.mt_sb = (int)mt_sb;
-    a.xa_sb = (int)xa_sb; a.xa_sc = (int)xa_sc; a.xa_sf = (int)xa_sf;
-    a.F = F; a.P = H * W; a.tiles_x = tiles_x; a.tiles_per_frame = tiles_x * tiles_y; a.n_tiles = (int)n_tiles;
-    a.sp = make_sampler(H, W, ac);
-    a.debug = tuning("MT_WARP_DBG", 0);
-    const int cps = tuning("MT_WARP_CTAS_PER_SM", 1) == 2 ? 2 : 1;
-    int ctas = sm_count() * cps;
-    if (ctas > n_tiles) ctas = (int)n_tiles;
-#define MT_STAGED_GO(BOXV, STG, CPSV, ACV, FMV)                                                      \
-    do {                                                                                             \
-        auto kern = warp_staged_kernel<BOXV, STG, CPSV, ACV, FMV>;                                   \
-        constexpr int smem = staged_smem_bytes<BOXV, STG>();                                         \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-        if (e != cudaSuccess) {                                                                      \
-            set_error("mt_warp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));               \
-            return MT_ERR_CUDA;                                                                      \
-        }                                                                                            \
-        launch(kern, dim3(ctas), dim3(kStagedThreads), (size_t)smem, st, map_x, map_v, map_t, a);           \
-    } while (0)
-#define MT_STAGED_PICK(BOXV, STG, CPSV)                                           \
-    do {                                                                          \
-        if (ac) { if (from_mask) MT_STAGED_GO(BOXV, STG, CPSV, true, true); else MT_STAGED_GO(BOXV, STG, CPSV, true, false); }   \
-        else    { if (from_mask) MT_STAGED_GO(BOXV, STG, CPSV, false, true); else MT_STAGED_GO(BOXV, STG, CPSV, false, false); } \
-    } while (0)
-    // shared memory per SM: 227 KB; stage = 4 boxes + the 4 KB target-mask tile
-    if (cps == 1) { if (box == 40) MT_STAGED_PICK(40, 7, 1); else MT_STAGED_PICK(48, 5, 1); }  // 7 x 29.0 / 5 x 40.0 KB
-    else          { if (box == 40) MT_STAGED_PICK(40, 3, 2); else MT_STAGED_PICK(48, 2, 2); }  // 2 x (3 x 29.0 / 2 x 40.0) KB
-#undef MT_STAGED_PICK
-#undef MT_STAGED_GO
-    return 1;
+    StagedHost h;
+    h.x = x; h.vis = vis; h.theta = theta; h.m_target = m_target;
+    h.x_al = x_aligned; h.v_al = v_aligned; h.v_map = v_map;
+    h.x_sb = x_sb; h.x_sc = x_sc; h.x_sf = x_sf; h.vis_sb = vis_sb; h.vis_sf = vis_sf; h.mt_sb = mt_sb;
+    h.xa_sb = xa_sb; h.xa_sc = xa_sc; h.xa_sf = xa_sf;
+    h.B = B; h.F = F; h.H = H; h.W = W; h.ac = ac; h.from_mask = from_mask; h.st = st; h.enc = enc;
+    // tile 64 x 32 (32 consumer warps, box 80 x 48, 3 stages of 68 KB) or 32 x 32 (16 warps, box 48 x 48,
+    // 5 stages of 40 KB)
+    if (tuning("MT_WARP_TILE_W", 32) == 64 && W >= 64) return staged_go<64, 80, 48, 3>(h);
+    return staged_go<32, 48, 48, 5>(h);
 }
 
 }  // namespace mt

@@ -112,26 +112,30 @@ STAGED_CASES = {
 }
 
 
+DEFAULT_TILE_W = 32
+DEFAULT_CM_FUSED = 0
+
+
 def _set_tuning(name, value):
     from master_thesis_b200 import _lib
     _lib.call("mt_set_tuning", name.encode(), value)
 
 
-@pytest.mark.parametrize("box", [48, 40])
+@pytest.mark.parametrize("tile_w", [32, 64])
 @pytest.mark.parametrize("name", sorted(STAGED_CASES))
-def test_cpn_align_tail_staged(mtb, name, box):
+def test_cpn_align_tail_staged(mtb, name, tile_w):
     spec = STAGED_CASES[name]
     x, m, m_t, theta = cases.cpn_inputs(spec)
     oxa, ova, ovm = oracle.cpn_align_tail(x, m, m_t, theta=theta)
     try:
-        _set_tuning("MT_WARP_BOX", box)
+        _set_tuning("MT_WARP_TILE_W", tile_w)
         _set_tuning("MT_WARP_STAGED", 1)
         xa, va, vm = mtb.cpn_align_tail(dev(x), dev(m), dev(m_t), dev(theta))
         _set_tuning("MT_WARP_STAGED", 0)
         xd, vd, vmd = mtb.cpn_align_tail(dev(x), dev(m), dev(m_t), dev(theta))
     finally:
         _set_tuning("MT_WARP_STAGED", 1)
-        _set_tuning("MT_WARP_BOX", 48)
+        _set_tuning("MT_WARP_TILE_W", DEFAULT_TILE_W)
     for got, direct, orc in ((xa, xd, oxa), (va, vd, ova), (vm, vmd, ovm)):
         assert np.array_equal(host(got), orc)           # staged kernel == oracle, bit for bit
         assert np.array_equal(host(direct), orc)        # direct-gather kernel == oracle
@@ -251,15 +255,22 @@ def test_corr4d(mtb, name):
 
 
 # ---------------------------------------------------------------- a8
+@pytest.mark.parametrize("fused", [1, 0])
 @pytest.mark.parametrize("name", sorted(cases.CM_CASES))
-def test_cm_module(mtb, name):
+def test_cm_module(mtb, name, fused):
+    """fused=1: the persistent pipelined kernel (cm.cu K3p); fused=0: the three-launch path."""
     from master_thesis_b200 import ops
     cf, vt, va = cases.cm_inputs(cases.CM_CASES[name])
     g = load_golden("cm_" + name)
-    out, cmask = mtb.CM_Module()(dev(cf), dev(vt), dev(va))
-    out, cmask = host(out), host(cmask)
     oout, ocmask, ogs = oracle.cm_module(cf, vt, va, return_gs=True)
-    _, _, gs = ops.cm_match(dev(cf), dev(vt), dev(va), return_gs=True)
+    try:
+        _set_tuning("MT_CM_FUSED", fused)
+        out, cmask = mtb.CM_Module()(dev(cf), dev(vt), dev(va))
+        out, cmask = host(out), host(cmask)
+        _, _, gs = ops.cm_match(dev(cf), dev(vt), dev(va), return_gs=True)
+        gs = gs.clone()
+    finally:
+        _set_tuning("MT_CM_FUSED", DEFAULT_CM_FUSED)
     assert np.abs(host(gs) - ogs).max() <= 1e-6 * max(1.0, np.abs(ogs).max())
     assert np.abs(out - oout).max() <= 1e-5 and np.abs(cmask - ocmask).max() <= 2e-6
     assert np.abs(cmask - g["c_mask"]).max() <= 2e-6
@@ -267,6 +278,31 @@ def test_cm_module(mtb, name):
         assert np.abs(out - g["out"]).max() <= 1e-5
     else:
         assert np.abs(out.reshape(-1)[::53] - g["sample"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("shape", [(5, 4, 9, 24, 48), (3, 2, 5, 32, 32), (9, 5, 16, 16, 80), (1, 8, 6, 16, 16)])
+def test_cm_pipelined_ragged(mtb, shape):
+    """The persistent kernel against the oracle and the three-launch path on shapes that leave
+    partial 1024-pixel chunks, a channel count that is not a multiple of the slab, more samples
+    than the lag, one sample, and 1 / 3 / 4 / 7 references."""
+    from master_thesis_b200 import ops, synth
+    b, f, c, h, w = shape
+    cf, vt, va = synth.cm_inputs(61 + b, b, f, c, h, w, 4)
+    oout, ocm, ogs = oracle.cm_module(cf, vt, va, return_gs=True)
+    res = {}
+    try:
+        for fused in (1, 0):
+            _set_tuning("MT_CM_FUSED", fused)
+            out, cmask, gs = ops.cm_match(dev(cf), dev(vt), dev(va), return_gs=True)
+            res[fused] = (host(out), host(cmask), host(gs.clone()))
+    finally:
+        _set_tuning("MT_CM_FUSED", DEFAULT_CM_FUSED)
+    for fused in (1, 0):
+        out, cmask, gs = res[fused]
+        assert np.abs(gs - ogs).max() <= 1e-6 * max(1.0, np.abs(ogs).max())
+        assert np.abs(out - oout).max() <= 1e-5 and np.abs(cmask - ocm).max() <= 2e-6
+    # same partial sums folded in a different (fixed) order: the two paths agree to rounding
+    assert np.abs(res[1][0] - res[0][0]).max() <= 1e-5 and np.abs(res[1][1] - res[0][1]).max() <= 2e-6
 
 
 # ---------------------------------------------------------------- a9 .. a12

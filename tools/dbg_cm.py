@@ -18,6 +18,8 @@ lib = _lib.load()
 for it in range(5):
     cf, vt, va = sets[it % 3]
     torch.cuda.synchronize()
+    if hasattr(lib, "mt_debug_cm_reset"):
+        lib.mt_debug_cm_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     ops.cm_match(cf, vt, va)
@@ -29,6 +31,11 @@ for it in range(5):
     buf2 = (ctypes.c_ulonglong * 2048)()
     lib.mt_debug_cm_probe(buf2, -1)
     t2 = np.array(buf2[:148 * 8], dtype=np.float64).reshape(148, 8)
+    full = np.array(buf2[:2048], dtype=np.float64)
+    t00 = full[1200]
+    print("   per sample: last S arrival %s | published %s | first slow C poll %s (us after CTA 0 start)" % (
+        np.round((full[1152:1152 + b] - t00) / 1e3, 1), np.round((full[1024:1024 + b] - t00) / 1e3, 1),
+        np.round((full[1088:1088 + b] - t00) / 1e3, 1)))
     print("   slow items with flag already set %.1f | ns in slow path %.0f | ns in decode %.0f" % (t2[:, 0].mean(), np.median(t2[:, 1]), np.median(t2[:, 2])))
     print("run %d: event %.1f us | kernel ns med %.0f max %.0f | wait %.0f | S %.0f | C %.0f | slow C items %.1f of items %.1f | "
           "publisher busy %.0f ns over %.1f publishes" % (it, e0.elapsed_time(e1) * 1e3, np.median(t[:, 0]), t[:, 0].max(),

@@ -1,0 +1,16 @@
+set -x
+timeout 900 python -m pytest tests -m gpu -x -q -k "cm" 2>&1 | tail -15
+MT_CM_FUSED=1 python tools/dbg_cm.py 8 2>&1 | tail -4
+run() { env "$@" timeout 180 python bench.py --workload ${WL:-cfg2} --steps 300 --warmup 5 --no-cpu-baseline --e2e-steps 2 2>gpurun_out/err.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('${WL:-cfg2} $*  step=%.1f us  '%(d['ms_per_step']*1e3) + '  '.join('%s=%.1f'%(k['call'][3:],k['avg_us']) for k in d['kernels']))" || tail -5 gpurun_out/err.log; }
+run MT_CM_FUSED=0
+run MT_CM_FUSED=1
+run MT_CM_FUSED=1 MT_CM_LAG=0
+run MT_CM_FUSED=1 MT_CM_LAG=1
+run MT_CM_FUSED=1 MT_CM_LAG=3
+run MT_CM_FUSED=1 MT_CM_STAGES=3
+run MT_CM_FUSED=1 MT_CM_FUSED_CH=4
+run MT_CM_FUSED=1 MT_CM_FUSED_CH=4 MT_CM_LAG=1
+run MT_CM_FUSED=1 MT_CM_FUSED_CH=1
