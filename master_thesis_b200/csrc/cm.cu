@@ -27,7 +27,7 @@
 namespace mt {
 namespace {
 
-constexpr int kSimChannels = 2;   // default channels per CTA slab in pass 1 (swept on B200: profiles/)
+constexpr int kSimChannels = 4;   // default channels per CTA slab in pass 1 (swept on B200: profiles/)
 constexpr int kCopyChannels = 4;  // default channels per CTA slab in pass 2 (template CC)
 constexpr int kMaxRefs = 8;
 
@@ -63,6 +63,7 @@ struct CmArgs {
     float *table;                // (B, 2^R, R + 1) softmax weights and c_mask per mask pattern
     int n_items, lag, copy_reverse;
     int workers, rounds, head;  // schedule of the pipelined kernel (cm_decode)
+    int n_copy, b_sim, n_sim;   // cm_copy_sim_kernel: copies samples [b_off, +n_copy), similarities of [b_sim, +n_sim)
     FastDiv dv_items, dv_chunks;
 };
 
@@ -141,28 +142,16 @@ __device__ __forceinline__ void fold_gs(const CmArgs &a, int b, float *gs_smem) 
     __syncthreads();
 }
 
-// pass 1: grid (chunks, C / SC, B); thread = 4 pixels x SC channels
-template <int R, int SC>
-__global__ void __launch_bounds__(256) cm_sim_kernel(const CmArgs a) {
-    pdl_sync();
-    __shared__ float red[2 * R * 32];
+// pass 1 for one (1024-pixel chunk, SC-channel slab, sample): thread = 4 pixels x SC channels
+template <int R, int SC, bool WAIT>
+__device__ __forceinline__ void cm_sim_body(const CmArgs &a, int slab, int b, float *red) {
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int slab = blockIdx.y, b = blockIdx.z + a.b_off;
     float acc[2 * R];  // [0, R): dot products, [R, 2R): sum of vt'*vr' (slab 0 only)
 #pragma unroll
     for (int r = 0; r < 2 * R; ++r) acc[r] = 0.0f;
+    const int c0 = slab * SC;
+    float4 ct[SC], cr[SC][R];
     if (p0 < a.P) {
-        const float *mk = a.masks + (int64_t)b * a.f * a.P + p0;
-        const float4 vt = *reinterpret_cast<const float4 *>(mk);
-        float4 vm[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float4 vr = *reinterpret_cast<const float4 *>(mk + (int64_t)(r + 1) * a.P);
-            vm[r] = make_float4(vt.x * vr.x, vt.y * vr.y, vt.z * vr.z, vt.w * vr.w);  // :220
-            if (slab == 0) acc[R + r] = (vm[r].x + vm[r].y) + (vm[r].z + vm[r].w);     // :221
-        }
-        const int c0 = slab * SC;
-        float4 ct[SC], cr[SC][R];
 #pragma unroll
         for (int k = 0; k < SC; ++k) {
             const int c = c0 + k;
@@ -174,6 +163,20 @@ __global__ void __launch_bounds__(256) cm_sim_kernel(const CmArgs a) {
                 for (int r = 0; r < R; ++r)
                     cr[k][r] = __ldg(reinterpret_cast<const float4 *>(base + (int64_t)(r + 1) * a.P));
             }
+        }
+    }
+    // WAIT: the features above were requested while the previous kernel of the stream (cm_masks) was
+    // still running - they do not depend on it; the masks below do (pdl_wait)
+    if (WAIT) pdl_wait();
+    if (p0 < a.P) {
+        const float *mk = a.masks + (int64_t)b * a.f * a.P + p0;
+        const float4 vt = __ldcg(reinterpret_cast<const float4 *>(mk));
+        float4 vm[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float4 vr = __ldcg(reinterpret_cast<const float4 *>(mk + (int64_t)(r + 1) * a.P));
+            vm[r] = make_float4(vt.x * vr.x, vt.y * vr.y, vt.z * vr.z, vt.w * vr.w);  // :220
+            if (slab == 0) acc[R + r] = (vm[r].x + vm[r].y) + (vm[r].z + vm[r].w);     // :221
         }
 #pragma unroll
         for (int k = 0; k < SC; ++k) {
@@ -196,11 +199,25 @@ __global__ void __launch_bounds__(256) cm_sim_kernel(const CmArgs a) {
     }
 }
 
+// pass 1: grid (chunks, C / SC, B)
+template <int R, int SC>
+__global__ void __launch_bounds__(256) cm_sim_kernel(const CmArgs a) {
+    // Scheduled while cm_masks_kernel is still running (that kernel waited for ITS predecessor before it
+    // let this one start, so c_feats is complete): the feature loads overlap it, the wait sits in the body.
+    pdl_launch();
+    __shared__ float red[2 * R * 32];
+    cm_sim_body<R, SC, true>(a, (int)blockIdx.y, (int)blockIdx.z + a.b_off, red);
+}
+
 // pass 1b: similarities -> per-pixel softmax weights, computed ONCE per pixel.
 // grid (ceil(P / 1024), B), 256 threads, one 4-pixel group per thread.
 template <int R>
 __global__ void __launch_bounds__(256) cm_weights_kernel(const CmArgs a) {
-    pdl_sync();
+    // launch_dependents BEFORE the wait: the CTAs of cm_copy_kernel are scheduled into the slots that the
+    // last wave of pass 1 frees and request their features (old data: c_feats) while pass 1 drains and
+    // this kernel runs; they wait for this kernel before they touch the weights.
+    pdl_launch();
+    pdl_wait();
     __shared__ float gs_smem[R];
     const int b = blockIdx.y + a.b_off;
     fold_gs<R>(a, b, gs_smem);
@@ -264,16 +281,14 @@ __global__ void __launch_bounds__(256) cm_weights_kernel(const CmArgs a) {
     }
 }
 
-// pass 2: grid (chunks, ceil(C / CC), B); thread = 4 pixels x CC channels.
-template <int R, int CC>
-__global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
-    pdl_sync();
+// pass 2 for one (1024-pixel chunk, CC-channel slab, sample): thread = 4 pixels x CC channels
+template <int R, int CC, bool WAIT>
+__device__ __forceinline__ void cm_copy_body(const CmArgs &a, int slab, int b) {
     const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (p0 >= a.P) return;
-    // samples in REVERSE order: pass 1 streamed them 0 .. B-1, so the tail of the batch is what is
-    // still in L2 (126 MB); walking forwards again evicts it just before it is needed (LRU: ncu
-    // 4.6 % hit rate at B=8)
-    const int slab = blockIdx.y, b = (a.copy_reverse ? (int)gridDim.z - 1 - (int)blockIdx.z : (int)blockIdx.z) + a.b_off;
+    if (p0 >= a.P) {
+        if (WAIT) pdl_wait();
+        return;
+    }
     const int c0 = slab * CC;
     float4 ct[CC], cr[CC][R];
 #pragma unroll
@@ -285,10 +300,12 @@ __global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
             for (int r = 0; r < R; ++r) cr[k][r] = ld_stream4(base + (int64_t)(r + 1) * a.P);
         }
     }
+    // WAIT: the features above were requested while cm_weights_kernel was still running
+    if (WAIT) pdl_wait();
     float4 wg[R];
     const float *wp = a.weights + (int64_t)b * R * a.P + p0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) wg[r] = __ldg(reinterpret_cast<const float4 *>(wp + (int64_t)r * a.P));
+    for (int r = 0; r < R; ++r) wg[r] = __ldcg(reinterpret_cast<const float4 *>(wp + (int64_t)r * a.P));
     float *ob = a.out + (int64_t)b * (2 * a.C + 1) * a.P + p0;
 #pragma unroll
     for (int k = 0; k < CC; ++k) {
@@ -304,6 +321,33 @@ __global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
         }
         st_stream4(ob + (int64_t)c * a.P, ct[k]);                             // cat[c_t, ...]  :243
         st_stream4(ob + (int64_t)(a.C + c) * a.P, o);
+    }
+}
+
+// pass 2: grid (chunks, ceil(C / CC), B)
+template <int R, int CC>
+__global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
+    pdl_launch();
+    // samples in REVERSE order: pass 1 streamed them 0 .. B-1, so the tail of the batch is what is
+    // still in L2 (126 MB); walking forwards again evicts it just before it is needed (LRU: ncu
+    // 4.6 % hit rate at B=8)
+    const int b = (a.copy_reverse ? (int)gridDim.z - 1 - (int)blockIdx.z : (int)blockIdx.z) + a.b_off;
+    cm_copy_body<R, CC, true>(a, (int)blockIdx.y, b);
+}
+
+// pass 2 of one group of samples and pass 1 of the NEXT group in the same launch (slabs interleaved
+// along blockIdx.y): the copy re-reads its group from L2, where pass 1 left it one launch ago, while
+// the similarity of the next group streams from HBM - so c_feats crosses HBM once, without any
+// synchronisation inside a kernel.  grid (chunks, 2 * ceil(C / CH), max(n_copy, n_sim)).
+template <int R, int CH>
+__global__ void __launch_bounds__(256) cm_copy_sim_kernel(const CmArgs a) {
+    pdl_sync();
+    __shared__ float red[2 * R * 32];
+    const int slab = (int)blockIdx.y >> 1, z = (int)blockIdx.z;
+    if (blockIdx.y & 1) {
+        if (z < a.n_sim) cm_sim_body<R, CH, false>(a, slab, a.b_sim + z, red);
+    } else {
+        if (z < a.n_copy) cm_copy_body<R, CH, false>(a, slab, a.b_off + z);
     }
 }
 
@@ -901,22 +945,42 @@ int launch_cm(CmArgs a, cudaStream_t st) {
     }
     a.b_off = 0;
     launch(cm_masks_kernel, dim3((a.P + 255) / 256, a.B), 256, 0, st, a);
-    // MT_CM_CHUNK > 0 processes the samples in chunks (sim -> weights -> copy per chunk) so that
-    // pass 2 could re-read c_feats from L2.  Swept on B200 at B=8 (profiles/r1_sweep_cm.sh):
-    // 1/2/4/8 samples per chunk -> 111/72/55/48 us: the extra small launches cost more than the
-    // L2 reuse brings, so the default is the whole batch in one group.
+    // MT_CM_CHUNK > 0 (off): samples in groups, sim(g0) | weights(g0) | copy(g0) + sim(g1) | weights(g1) |
+    // copy(g1) + sim(g2) | ...  - pass 2 of a group shares a launch with pass 1 of the next one and
+    // re-reads its c_feats from L2 (a group of 4 samples is 42 MB of the 126 MB).  Measured on B200:
+    // 52.0 / 57.3 / 63.5 us for groups of 4 / 3 / 2 against 46.9 us for one group at B=8, 166.6 against
+    // 140.3 us at B=32: every additional launch costs 3-5 us of ramp and tail, more than the L2 hits
+    // return.  (Separate launches per pass and group were worse still: 111/72/55 us for 1/2/4.)
     int chunk = tuning("MT_CM_CHUNK", 0);
     if (chunk < 1 || chunk > a.B) chunk = a.B;
     const int cc = tuning("MT_CM_COPY_CH", kCopyChannels);
+    const bool merged = chunk < a.B;
+    if (merged) a.sim_ch = tuning("MT_CM_MERGE_CH", 4) == 2 ? 2 : 4;  // one slab width for both passes
+    a.nparts = a.chunks * ((a.C + a.sim_ch - 1) / a.sim_ch);
+    const int slabs = (a.C + a.sim_ch - 1) / a.sim_ch;
     for (int b0 = 0; b0 < a.B; b0 += chunk) {
         const int nb = a.B - b0 < chunk ? a.B - b0 : chunk;
         a.b_off = b0;
-        dim3 g1(a.chunks, (a.C + a.sim_ch - 1) / a.sim_ch, nb);
-        if (a.sim_ch == 2) launch(cm_sim_kernel<R, 2>, g1, 256, 0, st, a);
-        else launch(cm_sim_kernel<R, 4>, g1, 256, 0, st, a);
+        if (!merged || b0 == 0) {
+            dim3 g1(a.chunks, slabs, nb);
+            if (a.sim_ch == 2) launch(cm_sim_kernel<R, 2>, g1, 256, 0, st, a);
+            else launch(cm_sim_kernel<R, 4>, g1, 256, 0, st, a);
+        }
         dim3 gw(a.chunks, nb);
         launch(cm_weights_kernel<R>, gw, 256, 0, st, a);
-        if (cc == 2) {
+        if (merged && b0 + nb < a.B) {
+            a.n_copy = nb;
+            a.b_sim = b0 + nb;
+            a.n_sim = a.B - a.b_sim < chunk ? a.B - a.b_sim : chunk;
+            dim3 g2(a.chunks, 2 * slabs, a.n_copy > a.n_sim ? a.n_copy : a.n_sim);
+            if (a.sim_ch == 2) launch(cm_copy_sim_kernel<R, 2>, g2, 256, 0, st, a);
+            else launch(cm_copy_sim_kernel<R, 4>, g2, 256, 0, st, a);
+        } else if (merged) {
+            a.copy_reverse = 0;
+            dim3 g2(a.chunks, slabs, nb);
+            if (a.sim_ch == 2) launch(cm_copy_kernel<R, 2>, g2, 256, 0, st, a);
+            else launch(cm_copy_kernel<R, 4>, g2, 256, 0, st, a);
+        } else if (cc == 2) {
             dim3 g2(a.chunks, (a.C + 1) / 2, nb);
             launch(cm_copy_kernel<R, 2>, g2, 256, 0, st, a);
         } else {

@@ -71,6 +71,13 @@ __device__ __forceinline__ void pdl_sync() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// The two halves separately, for kernels whose first loads do not depend on the previous kernel of the
+// stream (see cm.cu): launch_dependents first, the wait where the dependent loads begin.  Safe only
+// when the previous kernel itself waited before it called launch_dependents (every kernel of this
+// library does): then everything older than it has completed.
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 constexpr float kMean0 = 0.485f, kMean1 = 0.456f, kMean2 = 0.406f;  // model_chn.py:32-37
 constexpr float kStd0 = 0.229f, kStd1 = 0.224f, kStd2 = 0.225f;
 
