@@ -335,6 +335,131 @@ __global__ void __launch_bounds__(256) cm_copy_kernel(const CmArgs a) {
     cm_copy_body<R, CC, true>(a, (int)blockIdx.y, b);
 }
 
+// pass 1b + 2 in one launch (the default): every CTA folds the partials of its sample itself (4 KB from
+// L2, one double per thread, fixed order) and evaluates the masked softmax once per MASK PATTERN - vr' is
+// 0/1, so a sample has only 2^R distinct weight vectors; same operations in the same order as
+// cm_weights_kernel, hence the same bits - while its feature loads, issued before the wait, are still in
+// flight.  Per pixel the weights are a table lookup by the mask byte.  This removes cm_weights_kernel
+// from the chain (7 us as a launch of 32 latency-bound CTAs), the weights array (B,R,P) and its reads.
+template <int R, int CC>
+__global__ void __launch_bounds__(256, 2) cm_copy2_kernel(const CmArgs a) {
+    constexpr int G2 = 2 * R, TABF = (1 << R) * (R + 1);
+    __shared__ double dred[256];
+    __shared__ float gs_smem[R];
+    __shared__ float tab[TABF];
+    pdl_launch();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int p0 = (blockIdx.x * blockDim.x + tid) * 4;
+    const bool live = p0 < a.P;
+    const int slab = blockIdx.y, b = (a.copy_reverse ? (int)gridDim.z - 1 - (int)blockIdx.z : (int)blockIdx.z) + a.b_off;
+    const int c0 = slab * CC;
+    float4 ct[CC], cr[CC][R];
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < CC; ++k) {
+            if (c0 + k < a.C) {
+                const float *base = a.c_feats + ((int64_t)b * a.C + c0 + k) * a.f * a.P + p0;
+                ct[k] = ld_stream4(base);
+#pragma unroll
+                for (int r = 0; r < R; ++r) cr[k][r] = ld_stream4(base + (int64_t)(r + 1) * a.P);
+            }
+        }
+    }
+    pdl_wait();  // pass 1 (and cm_masks before it) complete: partials and mask bytes are valid
+    const uint32_t mw = live ? __ldcg(reinterpret_cast<const uint32_t *>(a.pmask + (int64_t)b * a.P + p0)) : 0u;
+    // ---- gs[b, :]: thread t adds element t % 2R of rows t / 2R, t / 2R + kSlots, ... in increasing order ----
+    constexpr int kSlots = 256 / G2;
+    double v = 0.0;
+    if (tid < kSlots * G2) {
+        const int r = tid % G2, i0 = tid / G2;
+        const float *o = a.partials + (int64_t)b * a.nparts * G2 + r;
+#pragma unroll 4
+        for (int i = i0; i < a.nparts; i += kSlots) v += (double)__ldcg(o + (int64_t)i * G2);
+    }
+    if constexpr ((G2 & (G2 - 1)) == 0 && G2 <= 16) {
+        // the lanes l, l + 2R, l + 4R, ... of a warp hold the same element: xor tree, then 8 warps
+#pragma unroll
+        for (int o = G2; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane < G2) dred[wid * G2 + lane] = v;
+        __syncthreads();
+        if (tid < R) {
+            double d = 0.0, vs = 0.0;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) { d += dred[w8 * G2 + tid]; vs += dred[w8 * G2 + R + tid]; }
+            const bool zero = vs < 1e-4;                                       // :222
+            const float v_sum = (float)vs + (zero ? 1.0f : 0.0f);              // :223
+            const float g = (float)d / (v_sum * (float)a.C);                   // :225-227
+            gs_smem[tid] = zero ? 0.0f : g;                                    // :228
+        }
+    } else {
+        dred[tid] = v;
+        __syncthreads();
+        if (tid < R) {
+            double d = 0.0, vs = 0.0;
+            for (int sl = 0; sl < kSlots; ++sl) { d += dred[sl * G2 + tid]; vs += dred[sl * G2 + R + tid]; }
+            const bool zero = vs < 1e-4;
+            const float v_sum = (float)vs + (zero ? 1.0f : 0.0f);
+            const float g = (float)d / (v_sum * (float)a.C);
+            gs_smem[tid] = zero ? 0.0f : g;
+        }
+    }
+    __syncthreads();
+    // ---- masked_softmax over the references, once per mask pattern t                :245-254 ----
+    for (int t = tid; t < (1 << R); t += 256) {
+        float vr[R], wv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) vr[r] = ((t >> r) & 1) ? 1.0f : 0.0f;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < R; ++r) mx = fmaxf(mx, __fmul_rn(gs_smem[r], vr[r]));
+        float sum = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            wv[r] = __fmul_rn(expf(__fsub_rn(__fmul_rn(gs_smem[r], vr[r]), mx)), vr[r]);
+            sum = __fadd_rn(sum, wv[r]);
+        }
+        if (sum < 1e-4f) sum = __fadd_rn(sum, 1.0f);
+        float cm = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            wv[r] = __fdiv_rn(wv[r], sum);
+            cm = __fadd_rn(cm, __fmul_rn(wv[r], vr[r]));                          // :240
+            tab[t * (R + 1) + r] = wv[r];
+        }
+        tab[t * (R + 1) + R] = __fsub_rn(1.0f, cm);                               // :241
+    }
+    __syncthreads();
+    if (slab == 0 && blockIdx.x == 0 && tid < R) a.gs[(int64_t)b * R + tid] = gs_smem[tid];
+    if (!live) return;
+    int pat[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pat[j] = (int)((mw >> (8 * j + 1)) & ((1u << R) - 1u)) * (R + 1);
+    float *ob = a.out + (int64_t)b * (2 * a.C + 1) * a.P + p0;
+    if (slab == 0) {
+        const float4 c4 = make_float4(tab[pat[0] + R], tab[pat[1] + R], tab[pat[2] + R], tab[pat[3] + R]);
+        st_stream4(ob + (int64_t)(2 * a.C) * a.P, c4);
+        st_stream4(a.c_mask + (int64_t)b * a.P + p0, c4);
+    }
+    float4 wg[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) wg[r] = make_float4(tab[pat[0] + r], tab[pat[1] + r], tab[pat[2] + r], tab[pat[3] + r]);
+#pragma unroll
+    for (int k = 0; k < CC; ++k) {
+        const int c = c0 + k;
+        if (c >= a.C) break;
+        float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {  // sum_r c_r * w_r, sequential over r    :238
+            o.x = __fadd_rn(o.x, __fmul_rn(cr[k][r].x, wg[r].x));
+            o.y = __fadd_rn(o.y, __fmul_rn(cr[k][r].y, wg[r].y));
+            o.z = __fadd_rn(o.z, __fmul_rn(cr[k][r].z, wg[r].z));
+            o.w = __fadd_rn(o.w, __fmul_rn(cr[k][r].w, wg[r].w));
+        }
+        st_stream4(ob + (int64_t)c * a.P, ct[k]);                             // cat[c_t, ...]  :243
+        st_stream4(ob + (int64_t)(a.C + c) * a.P, o);
+    }
+}
+
 // pass 2 of one group of samples and pass 1 of the NEXT group in the same launch (slabs interleaved
 // along blockIdx.y): the copy re-reads its group from L2, where pass 1 left it one launch ago, while
 // the similarity of the next group streams from HBM - so c_feats crosses HBM once, without any
@@ -965,6 +1090,11 @@ int launch_cm(CmArgs a, cudaStream_t st) {
             dim3 g1(a.chunks, slabs, nb);
             if (a.sim_ch == 2) launch(cm_sim_kernel<R, 2>, g1, 256, 0, st, a);
             else launch(cm_sim_kernel<R, 4>, g1, 256, 0, st, a);
+        }
+        if (!merged && R <= 7 && tuning("MT_CM_TABLE", 1)) {  // pass 1b folded into pass 2 (the mask byte holds <= 7 references)
+            if (cc == 2) launch(cm_copy2_kernel<R, 2>, dim3(a.chunks, (a.C + 1) / 2, nb), 256, 0, st, a);
+            else launch(cm_copy2_kernel<R, 4>, dim3(a.chunks, (a.C + 3) / 4, nb), 256, 0, st, a);
+            continue;
         }
         dim3 gw(a.chunks, nb);
         launch(cm_weights_kernel<R>, gw, 256, 0, st, a);
