@@ -147,6 +147,30 @@ MT_API int mt_masked_l1_bwd(const float *y_hat, int64_t a_sb, int64_t a_sc, int6
                      int B, int C, int F, int64_t P, int mask_c, int reduction, float weight,
                      mt_stream_t stream);
 
+/* The three masked-L1 terms of CHN.compute_loss in one pass          model_chn.py:347-362  (a5)
+ *   loss_nh  = masked_l1(y_hat,      target, v_target repeated over F, 'sum', w_nh)
+ *   loss_vh  = masked_l1(y_hat,      target, v_map,                    'sum', w_vh)
+ *   loss_nvh = masked_l1(y_hat_comp, target, (1 - nh_mask) - vh_mask,  'sum', w_nvh)
+ * y_hat, y_comp (B,3,F,P) strided; y_target (B,3,P), v_target (B,1,P), v_map (B,1,F,P) strided.
+ * out9 = [loss, sum|.|, sum(mask)+1e-9] x {nh, vh, nvh} on the device.
+ * workspace: mt_workspace_bytes() bytes, zero-initialised once (self-resetting ticket). */
+MT_API int mt_chn_l1x3_fwd(const float *y_hat, int64_t yh_sb, int64_t yh_sc, int64_t yh_sf,
+                    const float *y_comp, int64_t yc_sb, int64_t yc_sc, int64_t yc_sf,
+                    const float *y_target, int64_t yt_sb, int64_t yt_sc,
+                    const float *v_target, int64_t vt_sb,
+                    const float *v_map, int64_t vm_sb, int64_t vm_sf,
+                    float *out9, void *workspace, int B, int F, int64_t P,
+                    float w_nh, float w_vh, float w_nvh, mt_stream_t stream);
+/* grads (contiguous (B,3,F,P)) w.r.t. y_hat (terms nh + vh) and y_hat_comp (term nvh); either may be
+ * NULL.  grad_out3: the three upstream scalars on the device. */
+MT_API int mt_chn_l1x3_bwd(const float *y_hat, int64_t yh_sb, int64_t yh_sc, int64_t yh_sf,
+                    const float *y_comp, int64_t yc_sb, int64_t yc_sc, int64_t yc_sf,
+                    const float *y_target, int64_t yt_sb, int64_t yt_sc,
+                    const float *v_target, int64_t vt_sb,
+                    const float *v_map, int64_t vm_sb, int64_t vm_sf,
+                    const float *out9, const float *grad_out3, float *grad_y_hat, float *grad_y_comp,
+                    int B, int F, int64_t P, float w_nh, float w_vh, float w_nvh, mt_stream_t stream);
+
 /* ---- K2  masked cosine correlation on tcgen05 ----------------------------
  * replaces CorrelationVGG.correlation_masked_4d  model_dfpn.py:534-565  (a7)
  * feats_t (B,C,P) contiguous, v_t (B,P) or NULL, feats_r (B,C,F,P) contiguous,

@@ -13,7 +13,7 @@ call does, and raises if libmt_b200.so is missing (no CPU fallback).
 """
 from . import ops, synth  # noqa: F401
 from .plug import (CM_Module, CorrelationVGG, FlowsUtils, LossesUtils,  # noqa: F401
-                   chn_forward, chn_inpaint_cp, chn_inpaint_ff, chn_inpaint_ip,
+                   chn_compute_loss, chn_forward, chn_inpaint_cp, chn_inpaint_ff, chn_inpaint_ip,
                    cpn_align, cpn_align_tail, dfpn_align, dfpn_align_tail, patch,
                    trivial_copy, unpatch)
 

@@ -301,6 +301,109 @@ __global__ void __launch_bounds__(256) masked_l1_bwd_kernel(const L1Args a) {
     }
 }
 
+// ---- the three masked-L1 terms of CHN.compute_loss in one pass ------------------------------
+// model_chn.py:347-362: loss_nh  = masked_l1(y_hat,      target, v_target (repeated over F), 'sum', w_nh)
+//                       loss_vh  = masked_l1(y_hat,      target, v_map,                       'sum', w_vh)
+//                       loss_nvh = masked_l1(y_hat_comp, target, (1 - nh_mask) - vh_mask,     'sum', w_nvh)
+// As three calls every term re-reads y_hat / y_hat_comp / target / its mask (3 x 28 px B per frame,
+// plus the materialised (1 - nh) - vh mask); here each input crosses HBM once (28 px + 16 px / F).
+// Arithmetic per element and the reductions are those of masked_l1_fwd_kernel / _bwd_kernel.
+struct L1x3Args {
+    const float *yh; int64_t yh_sb, yh_sc, yh_sf;
+    const float *yc; int64_t yc_sb, yc_sc, yc_sf;
+    const float *yt; int64_t yt_sb, yt_sc;
+    const float *vt; int64_t vt_sb;
+    const float *vm; int64_t vm_sb, vm_sf;
+    float *out9; void *ws;
+    const float *out9_in; const float *grad_out3; float *g_yh, *g_yc;
+    int B, F; int64_t P; float w[3];
+    int chunks; int64_t total_chunks;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) chn_l1x3_fwd_kernel(const L1x3Args a) {
+    pdl_sync();
+    __shared__ float red[6 * 32];
+    float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // sum |.| of the three terms, sum(mask) of the three
+    for (int64_t ch = blockIdx.x; ch < a.total_chunks; ch += gridDim.x) {
+        const int64_t bf = ch / a.chunks;
+        const int b = (int)(bf / a.F), f = (int)(bf - (int64_t)b * a.F);
+        const int64_t p0 = ((ch - bf * a.chunks) * blockDim.x + threadIdx.x) * VEC;
+        if (p0 >= a.P) continue;
+        Vec<VEC> m1, m2, m3;
+        m1.load_cached(a.vt + b * a.vt_sb + p0);
+        m2.load_stream(a.vm + b * a.vm_sb + f * a.vm_sf + p0);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            m3.v[i] = __fsub_rn(__fsub_rn(1.0f, m1.v[i]), m2.v[i]);  // (1 - nh_mask) - vh_mask   :359
+            acc[3] += m1.v[i]; acc[4] += m2.v[i]; acc[5] += m3.v[i];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Vec<VEC> yh, yc, yt;
+            yh.load_stream(a.yh + b * a.yh_sb + c * a.yh_sc + f * a.yh_sf + p0);
+            yc.load_stream(a.yc + b * a.yc_sb + c * a.yc_sc + f * a.yc_sf + p0);
+            yt.load_cached(a.yt + b * a.yt_sb + c * a.yt_sc + p0);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {  // |y_hat*mask - y*mask|   utils.py:166
+                acc[0] += fabsf(__fsub_rn(__fmul_rn(yh.v[i], m1.v[i]), __fmul_rn(yt.v[i], m1.v[i])));
+                acc[1] += fabsf(__fsub_rn(__fmul_rn(yh.v[i], m2.v[i]), __fmul_rn(yt.v[i], m2.v[i])));
+                acc[2] += fabsf(__fsub_rn(__fmul_rn(yc.v[i], m3.v[i]), __fmul_rn(yt.v[i], m3.v[i])));
+            }
+        }
+    }
+    float *out9 = a.out9;
+    const float w0 = a.w[0], w1 = a.w[1], w2 = a.w[2];
+    grid_reduce_finish<6>(acc, a.ws, red, [out9, w0, w1, w2](const double *tot) {
+        const float w[3] = {w0, w1, w2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {  // 'sum': / (sum(mask) + 1e-9)   utils.py:167-169
+            const float num = (float)tot[k], den = (float)tot[3 + k] + 1e-9f;
+            out9[3 * k + 0] = w[k] * (num / den);
+            out9[3 * k + 1] = num;
+            out9[3 * k + 2] = den;
+        }
+    });
+}
+
+// grads w.r.t. y_hat (terms nh + vh, added as autograd accumulates them) and y_hat_comp (term nvh)
+template <int VEC>
+__global__ void __launch_bounds__(256) chn_l1x3_bwd_kernel(const L1x3Args a) {
+    pdl_sync();
+    const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (p0 >= a.P) return;
+    const int bf = blockIdx.y, b = bf / a.F, f = bf - b * a.F;
+    float sc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sc[k] = a.w[k] * __ldg(a.grad_out3 + k) / __ldg(a.out9_in + 3 * k + 2);
+    Vec<VEC> m1, m2, m3;
+    m1.load_cached(a.vt + b * a.vt_sb + p0);
+    m2.load_stream(a.vm + b * a.vm_sb + f * a.vm_sf + p0);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) m3.v[i] = __fsub_rn(__fsub_rn(1.0f, m1.v[i]), m2.v[i]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        Vec<VEC> yh, yc, yt, gh, gc;
+        yh.load_stream(a.yh + b * a.yh_sb + c * a.yh_sc + f * a.yh_sf + p0);
+        yc.load_stream(a.yc + b * a.yc_sb + c * a.yc_sc + f * a.yc_sf + p0);
+        yt.load_cached(a.yt + b * a.yt_sb + c * a.yt_sc + p0);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float d1 = __fsub_rn(__fmul_rn(yh.v[i], m1.v[i]), __fmul_rn(yt.v[i], m1.v[i]));
+            const float d2 = __fsub_rn(__fmul_rn(yh.v[i], m2.v[i]), __fmul_rn(yt.v[i], m2.v[i]));
+            const float d3 = __fsub_rn(__fmul_rn(yc.v[i], m3.v[i]), __fmul_rn(yt.v[i], m3.v[i]));
+            const float s1 = (d1 > 0.0f) ? 1.0f : ((d1 < 0.0f) ? -1.0f : 0.0f);
+            const float s2 = (d2 > 0.0f) ? 1.0f : ((d2 < 0.0f) ? -1.0f : 0.0f);
+            const float s3 = (d3 > 0.0f) ? 1.0f : ((d3 < 0.0f) ? -1.0f : 0.0f);
+            gh.v[i] = __fadd_rn(s1 * m1.v[i] * sc[0], s2 * m2.v[i] * sc[1]);
+            gc.v[i] = s3 * m3.v[i] * sc[2];
+        }
+        const int64_t o = (((int64_t)b * 3 + c) * a.F + f) * a.P + p0;
+        if (a.g_yh) gh.store_stream(a.g_yh + o);
+        if (a.g_yc) gc.store_stream(a.g_yc + o);
+    }
+}
+
 int reduce_blocks(int64_t total) {
     int64_t want = (int64_t)sm_count() * 8;
     int64_t n = total < want ? total : want;
@@ -470,4 +573,70 @@ extern "C" int mt_masked_l1_bwd(const float *y_hat, int64_t a_sb, int64_t a_sc, 
     if (v4) launch(masked_l1_bwd_kernel<4>, grid, 256, 0, (cudaStream_t)stream, a);
     else launch(masked_l1_bwd_kernel<1>, grid, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_masked_l1_bwd");
+}
+
+static int fill_l1x3(L1x3Args &a, const float *y_hat, int64_t yh_sb, int64_t yh_sc, int64_t yh_sf,
+                     const float *y_comp, int64_t yc_sb, int64_t yc_sc, int64_t yc_sf, const float *y_target,
+                     int64_t yt_sb, int64_t yt_sc, const float *v_target, int64_t vt_sb, const float *v_map,
+                     int64_t vm_sb, int64_t vm_sf, int B, int F, int64_t P, float w_nh, float w_vh, float w_nvh,
+                     const char *who) {
+    MT_REQUIRE(y_hat && y_comp && y_target && v_target && v_map, "%s: NULL tensor", who);
+    MT_REQUIRE(B > 0 && F > 0 && P > 0, "%s: empty shape", who);
+    a.yh = y_hat; a.yh_sb = yh_sb; a.yh_sc = yh_sc; a.yh_sf = yh_sf;
+    a.yc = y_comp; a.yc_sb = yc_sb; a.yc_sc = yc_sc; a.yc_sf = yc_sf;
+    a.yt = y_target; a.yt_sb = yt_sb; a.yt_sc = yt_sc;
+    a.vt = v_target; a.vt_sb = vt_sb;
+    a.vm = v_map; a.vm_sb = vm_sb; a.vm_sf = vm_sf;
+    a.B = B; a.F = F; a.P = P; a.w[0] = w_nh; a.w[1] = w_vh; a.w[2] = w_nvh;
+    a.out9 = nullptr; a.ws = nullptr; a.out9_in = nullptr; a.grad_out3 = nullptr; a.g_yh = a.g_yc = nullptr;
+    return MT_OK;
+}
+
+static bool l1x3_vec4(const L1x3Args &a) {
+    return mult4(a.P) && aligned16(a.yh) && aligned16(a.yc) && aligned16(a.yt) && aligned16(a.vt) &&
+           aligned16(a.vm) && mult4(a.yh_sb) && mult4(a.yh_sc) && mult4(a.yh_sf) && mult4(a.yc_sb) &&
+           mult4(a.yc_sc) && mult4(a.yc_sf) && mult4(a.yt_sb) && mult4(a.yt_sc) && mult4(a.vt_sb) &&
+           mult4(a.vm_sb) && mult4(a.vm_sf);
+}
+
+extern "C" int mt_chn_l1x3_fwd(const float *y_hat, int64_t yh_sb, int64_t yh_sc, int64_t yh_sf,
+                               const float *y_comp, int64_t yc_sb, int64_t yc_sc, int64_t yc_sf,
+                               const float *y_target, int64_t yt_sb, int64_t yt_sc, const float *v_target,
+                               int64_t vt_sb, const float *v_map, int64_t vm_sb, int64_t vm_sf, float *out9,
+                               void *workspace, int B, int F, int64_t P, float w_nh, float w_vh, float w_nvh,
+                               mt_stream_t stream) {
+    L1x3Args a;
+    int rc = fill_l1x3(a, y_hat, yh_sb, yh_sc, yh_sf, y_comp, yc_sb, yc_sc, yc_sf, y_target, yt_sb, yt_sc,
+                       v_target, vt_sb, v_map, vm_sb, vm_sf, B, F, P, w_nh, w_vh, w_nvh, "mt_chn_l1x3_fwd");
+    if (rc) return rc;
+    MT_REQUIRE(out9 && workspace, "mt_chn_l1x3_fwd: NULL out9 / workspace");
+    a.out9 = out9; a.ws = workspace;
+    const bool v4 = l1x3_vec4(a);
+    a.chunks = (int)((P + (v4 ? 1024 : 256) - 1) / (v4 ? 1024 : 256));
+    a.total_chunks = (int64_t)B * F * a.chunks;
+    const int nblk = reduce_blocks(a.total_chunks);
+    if (v4) launch(chn_l1x3_fwd_kernel<4>, nblk, 256, 0, (cudaStream_t)stream, a);
+    else launch(chn_l1x3_fwd_kernel<1>, nblk, 256, 0, (cudaStream_t)stream, a);
+    return launch_status("mt_chn_l1x3_fwd");
+}
+
+extern "C" int mt_chn_l1x3_bwd(const float *y_hat, int64_t yh_sb, int64_t yh_sc, int64_t yh_sf,
+                               const float *y_comp, int64_t yc_sb, int64_t yc_sc, int64_t yc_sf,
+                               const float *y_target, int64_t yt_sb, int64_t yt_sc, const float *v_target,
+                               int64_t vt_sb, const float *v_map, int64_t vm_sb, int64_t vm_sf,
+                               const float *out9, const float *grad_out3, float *grad_y_hat,
+                               float *grad_y_comp, int B, int F, int64_t P, float w_nh, float w_vh,
+                               float w_nvh, mt_stream_t stream) {
+    L1x3Args a;
+    int rc = fill_l1x3(a, y_hat, yh_sb, yh_sc, yh_sf, y_comp, yc_sb, yc_sc, yc_sf, y_target, yt_sb, yt_sc,
+                       v_target, vt_sb, v_map, vm_sb, vm_sf, B, F, P, w_nh, w_vh, w_nvh, "mt_chn_l1x3_bwd");
+    if (rc) return rc;
+    MT_REQUIRE(out9 && grad_out3 && (grad_y_hat || grad_y_comp), "mt_chn_l1x3_bwd: NULL argument");
+    MT_REQUIRE((int64_t)B * F <= 65535, "mt_chn_l1x3_bwd: B*F > 65535");
+    a.out9_in = out9; a.grad_out3 = grad_out3; a.g_yh = grad_y_hat; a.g_yc = grad_y_comp;
+    const bool v4 = l1x3_vec4(a) && aligned16(grad_y_hat) && aligned16(grad_y_comp);
+    dim3 grid((unsigned)((P + (v4 ? 1024 : 256) - 1) / (v4 ? 1024 : 256)), (unsigned)(B * F));
+    if (v4) launch(chn_l1x3_bwd_kernel<4>, grid, 256, 0, (cudaStream_t)stream, a);
+    else launch(chn_l1x3_bwd_kernel<1>, grid, 256, 0, (cudaStream_t)stream, a);
+    return launch_status("mt_chn_l1x3_bwd");
 }

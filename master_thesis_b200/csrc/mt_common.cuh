@@ -55,7 +55,7 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 
 // workspace layout used by the reducing kernels
 constexpr int kMaxReduceBlocks = 16384;
-constexpr int kPartialsPerBlock = 4;  // one float4 row per CTA
+constexpr int kPartialsPerBlock = 8;  // up to two float4 rows per CTA
 constexpr int64_t kWsTicketBytes = 256;
 constexpr int64_t kWorkspaceBytes = kWsTicketBytes + int64_t(kMaxReduceBlocks) * kPartialsPerBlock * 4;
 
@@ -163,13 +163,19 @@ __device__ __forceinline__ void grid_reduce_finish(float (&v)[K], void *workspac
     __shared__ bool is_last;
     const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
     const unsigned int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    constexpr int ROWS = (K + 3) / 4;  // float4 rows per CTA (stride kPartialsPerBlock / 4 rows)
+    constexpr int RSTRIDE = kPartialsPerBlock / 4;
     block_sum<K>(v, smem);
     if (threadIdx.x == 0) {
-        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
-        float *mp = &mine.x;
 #pragma unroll
-        for (int k = 0; k < K; ++k) mp[k] = v[k];
-        reinterpret_cast<float4 *>(partials)[bid] = mine;
+        for (int j = 0; j < ROWS; ++j) {
+            float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+            float *mp = &mine.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (4 * j + k < K) mp[k] = v[4 * j + k];
+            reinterpret_cast<float4 *>(partials)[bid * RSTRIDE + j] = mine;
+        }
         __threadfence();
         unsigned int t = atomicAdd(ticket, 1u);
         is_last = (t == nblocks - 1);
@@ -182,19 +188,26 @@ __device__ __forceinline__ void grid_reduce_finish(float (&v)[K], void *workspac
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
     // 8 rows of partials in flight per thread: a plain loop here is a chain of exposed
     // L2 latencies (measured: 90 us for 16 K partials)
-    for (unsigned int i0 = threadIdx.x; i0 < nblocks; i0 += 8 * blockDim.x) {
-        float4 row[8];
+    constexpr int U = 8 / ROWS;
+    for (unsigned int i0 = threadIdx.x; i0 < nblocks; i0 += U * blockDim.x) {
+        float4 row[U][ROWS];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < U; ++u) {
             const unsigned int i = i0 + u * blockDim.x;
-            row[u] = i < nblocks ? __ldcg(reinterpret_cast<const float4 *>(partials) + i)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j)
+                row[u][j] = i < nblocks ? __ldcg(reinterpret_cast<const float4 *>(partials) + i * RSTRIDE + j)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float r4[4] = {row[u].x, row[u].y, row[u].z, row[u].w};
+        for (int u = 0; u < U; ++u) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] += (double)r4[k];
+            for (int j = 0; j < ROWS; ++j) {
+                const float r4[4] = {row[u][j].x, row[u][j].y, row[u][j].z, row[u][j].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (4 * j + k < K) acc[4 * j + k] += (double)r4[k];
+            }
         }
     }
     __shared__ double dsm[K * 32];

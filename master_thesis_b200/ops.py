@@ -268,6 +268,68 @@ def masked_l1(y_hat, y, mask, batch_mask=None, reduction="mean", weight=1):
 
 
 # --------------------------------------------------------------------------
+# fused CHN L1 terms (the three masked_l1 calls of CHN.compute_loss, model_chn.py:347-362)
+# --------------------------------------------------------------------------
+def chn_l1x3_fwd_raw(y_hat, y_hat_comp, y_target, v_target, v_map, weights=(0.5, 2.0, 1.0)):
+    """mt_chn_l1x3_fwd without autograd.  Returns (out9, saved): out9 = [loss, sum|.|, den] for the terms
+    nh, vh, nvh on the device; ``saved`` feeds chn_l1x3_bwd_raw."""
+    _need_cuda(y_hat, y_hat_comp, y_target, v_target, v_map)
+    b, c, f, h, w = y_hat.shape
+    if c != 3:
+        raise RuntimeError("chn_l1_terms: C must be 3")
+    yh, *yh_s = _s5(y_hat)
+    yc, *yc_s = _s5(y_hat_comp)
+    vm, vm_sb, _, vm_sf = _s5(v_map)
+    yt, vt = _planes(y_target), _planes(v_target)
+    out9 = _empty(9, dtype=torch.float32, device=yh.device)
+    wts = tuple(float(x) for x in weights)
+    _lib.call("mt_chn_l1x3_fwd", _ptr(yh), *yh_s, _ptr(yc), *yc_s, _ptr(yt), yt.stride(0), yt.stride(1),
+              _ptr(vt), vt.stride(0), _ptr(vm), vm_sb, vm_sf, _ptr(out9), _ptr(reduce_workspace(yh)),
+              b, f, h * w, wts[0], wts[1], wts[2], _stream(yh))
+    meta = (tuple(yh_s), tuple(yc_s), (yt.stride(0), yt.stride(1)), vt.stride(0), (vm_sb, vm_sf), b, f, h, w, wts)
+    return out9, (yh, yc, yt, vt, vm, out9, meta)
+
+
+def chn_l1x3_bwd_raw(saved, grad_out3, need_y_hat=True, need_y_comp=True):
+    """mt_chn_l1x3_bwd: gradients w.r.t. y_hat (terms nh + vh) and y_hat_comp (term nvh)."""
+    yh, yc, yt, vt, vm, out9, (yh_s, yc_s, yt_s, vt_sb, vm_s, b, f, h, w, wts) = saved
+    g_yh = _empty((b, 3, f, h, w), dtype=torch.float32, device=yh.device) if need_y_hat else None
+    g_yc = _empty((b, 3, f, h, w), dtype=torch.float32, device=yh.device) if need_y_comp else None
+    _lib.call("mt_chn_l1x3_bwd", _ptr(yh), *yh_s, _ptr(yc), *yc_s, _ptr(yt), *yt_s, _ptr(vt), vt_sb,
+              _ptr(vm), *vm_s, _ptr(out9), _ptr(grad_out3), _ptr(g_yh), _ptr(g_yc), b, f, h * w,
+              wts[0], wts[1], wts[2], _stream(yh))
+    return g_yh, g_yc
+
+
+class ChnL1x3Fn(torch.autograd.Function):
+    """The L1 terms of CHN.compute_loss + autograd w.r.t. y_hat and y_hat_comp (the ground-truth frame
+    and the masks take no gradient in the reference)."""
+
+    @staticmethod
+    def forward(ctx, y_hat, y_hat_comp, y_target, v_target, v_map, weights):
+        out9, saved = chn_l1x3_fwd_raw(y_hat, y_hat_comp, y_target, v_target, v_map, weights)
+        ctx.save_for_backward(*saved[:6])
+        ctx.meta = saved[6]
+        return out9[0], out9[3], out9[6]
+
+    @staticmethod
+    def backward(ctx, g_nh, g_vh, g_nvh):
+        if any(ctx.needs_input_grad[2:5]):
+            raise RuntimeError("chn_l1_terms: gradients w.r.t. y_target / v_target / v_map are not provided")
+        need_h, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_h or need_c):
+            return (None,) * 6
+        g3 = torch.stack([g_nh, g_vh, g_nvh]).to(torch.float32).contiguous()
+        g_yh, g_yc = chn_l1x3_bwd_raw(tuple(ctx.saved_tensors) + (ctx.meta,), g3, need_h, need_c)
+        return g_yh, g_yc, None, None, None, None
+
+
+def chn_l1_terms(y_target, v_target, y_hat, y_hat_comp, v_map, weights=(0.5, 2.0, 1.0)):
+    """(loss_nh, loss_vh, loss_nvh) of CHN.compute_loss (model_chn.py:347-362) in one pass."""
+    return ChnL1x3Fn.apply(y_hat, y_hat_comp, y_target, v_target, v_map, tuple(weights))
+
+
+# --------------------------------------------------------------------------
 # K1c fused warp + mask_out + masked L1
 # --------------------------------------------------------------------------
 def warp_l1_fwd_raw(x_refs, vis, flow, x_target, v_target, weight=1.0, materialize=False,

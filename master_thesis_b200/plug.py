@@ -122,6 +122,28 @@ def chn_forward(self, x_target, v_target, x_refs_aligned, v_refs_aligned, v_maps
     return ops.chn_composite(nn_output, x_target, v_target, b, f)
 
 
+def chn_compute_loss(self, y_target, v_target, y_hat, y_hat_comp, v_map):
+    """Replaces CHN.compute_loss (model_chn.py:324-375): the three masked-L1 terms come from ONE
+    kernel pass (ops.chn_l1_terms); the perceptual (VGG, cuDNN) and gradient terms are the
+    reference's own functions, looked up on the patched package exactly as the reference does."""
+    import master_thesis as mt
+    b, c, h, w = y_target.size()
+    target_img = y_target.unsqueeze(2).repeat(1, 1, y_hat.size(2), 1, 1)
+    loss_nh, loss_vh, loss_nvh = ops.chn_l1_terms(y_target, v_target, y_hat, y_hat_comp, v_map,
+                                                  (0.50, 2, 1))
+    loss_perceptual, *_ = mt.LossesUtils.perceptual(
+        y_hat.transpose(1, 2).reshape(-1, c, h, w),
+        target_img.transpose(1, 2).reshape(-1, c, h, w),
+        model_vgg=self.model_vgg,
+        weight=0.50,
+    )
+    loss_grad = mt.LossesUtils.grad(
+        y_hat.squeeze(2), target_img.squeeze(2), reduction='mean', weight=1
+    )
+    loss = loss_nh + loss_vh + loss_nvh + loss_perceptual + loss_grad
+    return loss, [loss_nh, loss_vh, loss_nvh, loss_perceptual, loss_grad]
+
+
 def _fill_step(chn, aligner, x_t, m_t, x_ref, m_ref):
     """One align -> hallucinate -> hole-update step shared by the three inpainting
     algorithms (model_chn.py:114-131, 165-186, 225-248).  All tensors carry a batch dim."""
@@ -206,6 +228,7 @@ _PATCHES = (
     ("model_cpn", "CPN", "align", cpn_align, False),
     ("model_cpn", "CM_Module", "forward", CM_Module.forward, False),
     ("model_chn", "CHN", "forward", chn_forward, False),
+    ("model_chn", "CHN", "compute_loss", chn_compute_loss, False),
     ("model_chn", "CHN", "inpaint_ff", chn_inpaint_ff, False),
     ("model_chn", "CHN", "inpaint_ip", chn_inpaint_ip, False),
     ("model_chn", "CHN", "inpaint_cp", chn_inpaint_cp, False),

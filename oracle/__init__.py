@@ -251,3 +251,23 @@ def trivial_copy(x_t, x_al, v_map):
     y = np.empty_like(x_al)
     lib().mto_trivial_copy(_p(x_t), _p(x_al), _p(v_map), _i(b), _i(f), _l(h * w), _p(y))
     return y
+
+
+def chn_l1_terms(y_target, v_target, y_hat, y_hat_comp, v_map, weights=(0.5, 2.0, 1.0), grads=False):
+    """The three masked-L1 terms of CHN.compute_loss, model_chn.py:347-362, as three a5 calls.
+    Returns [loss_nh, loss_vh, loss_nvh] (+ grads w.r.t. y_hat and y_hat_comp for upstream grads of 1)."""
+    f = y_hat.shape[2]
+    target_img = np.repeat(y_target[:, :, None], f, axis=2)
+    nh = np.repeat(v_target[:, :, None], f, axis=2).astype(np.float32)
+    vh = np.ascontiguousarray(v_map, dtype=np.float32)
+    nvh = ((1 - nh) - vh).astype(np.float32)
+    losses = [masked_l1(y_hat, target_img, nh, reduction="sum", weight=weights[0]),
+              masked_l1(y_hat, target_img, vh, reduction="sum", weight=weights[1]),
+              masked_l1(y_hat_comp, target_img, nvh, reduction="sum", weight=weights[2])]
+    if not grads:
+        return losses
+    # masked_l1_bwd returns the gradient w.r.t. y; the one w.r.t. y_hat is its negation
+    g_yh = -(masked_l1_bwd(y_hat, target_img, nh, reduction="sum", weight=weights[0]) +
+             masked_l1_bwd(y_hat, target_img, vh, reduction="sum", weight=weights[1]))
+    g_yc = -masked_l1_bwd(y_hat_comp, target_img, nvh, reduction="sum", weight=weights[2])
+    return losses, g_yh, g_yc

@@ -135,3 +135,24 @@ def chn_inputs(spec):
     nn_out.reshape(-1)[::97] = ((0.0 - 0.485) / 0.229)
     del flow
     return x_t, (1 - m_t).astype(np.float32), x_al, v_al, v_map, nn_out
+
+
+# a5 in CHN.compute_loss --------------------------------------------------------
+CHNLOSS_CASES = {
+    "f4": dict(seed=81, b=2, f=4, h=16, w=24),
+    "f1_odd": dict(seed=82, b=3, f=1, h=15, w=21),
+}
+
+
+def chnloss_inputs(spec):
+    """y_target (b,3,h,w), v_target (b,1,h,w), y_hat, y_hat_comp (b,3,f,h,w), v_map (b,1,f,h,w)."""
+    b, f, h, w = spec["b"], spec["f"], spec["h"], spec["w"]
+    r = synth.rng(spec["seed"])
+    y_target = r.random_sample((b, 3, h, w)).astype(np.float32)
+    v_target = (r.random_sample((b, 1, h, w)) < 0.85).astype(np.float32)
+    y_hat = r.random_sample((b, 3, f, h, w)).astype(np.float32)
+    v_al = (r.random_sample((b, 1, f, h, w)) < 0.8).astype(np.float32)
+    v_map = np.clip(v_al - v_target[:, :, None], 0, 1).astype(np.float32)
+    y_hat_comp = (v_target[:, :, None] * y_target[:, :, None] + (1 - v_target[:, :, None]) * y_hat).astype(np.float32)
+    y_hat.reshape(-1)[::89] = np.repeat(y_target[:, :, None], f, axis=2).reshape(-1)[::89]   # exact ties: sign 0
+    return y_target, v_target, y_hat, y_hat_comp, v_map

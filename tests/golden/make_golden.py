@@ -42,7 +42,8 @@ def save(name, **arrays):
 # case tables (shared with the tests through cases.py)
 # --------------------------------------------------------------------------
 from cases import WARP_CASES, CPN_CASES, CORR_CASES, CM_CASES, CHN_CASES, LOSS_CASES  # noqa: E402
-from cases import warp_inputs, cpn_inputs, corr_inputs, cm_inputs, chn_inputs, loss_inputs  # noqa: E402
+from cases import (warp_inputs, cpn_inputs, corr_inputs, cm_inputs, chn_inputs, loss_inputs,  # noqa: E402
+                   chnloss_inputs, CHNLOSS_CASES)
 
 
 def main():
@@ -175,6 +176,28 @@ def main():
              y_hat_comp=y_comp.detach().contiguous().numpy(), g_nn_out=seen['nn_out'].grad.numpy(),
              m_new=m_new.numpy(), x_new=x_new.detach().numpy(), inp_per=inp_per.numpy(),
              trivial=triv.numpy())
+
+    # ---- a5 inside CHN.compute_loss (model_chn.py:324-375), unmodified; only the two terms outside
+    # the hot path are replaced by zeros: perceptual (VGG) and the image-gradient loss.
+    zero = lambda *a, **k: (torch.zeros(()), None, None)  # noqa: E731
+    orig_p, orig_g = mt.LossesUtils.perceptual, mt.LossesUtils.grad
+    mt.LossesUtils.perceptual = staticmethod(zero)
+    mt.LossesUtils.grad = staticmethod(lambda *a, **k: torch.zeros(()))
+    try:
+        for name, spec in CHNLOSS_CASES.items():
+            y_target, v_target, y_hat, y_comp, v_map = chnloss_inputs(spec)
+
+            class FakeCHN2(object):
+                model_vgg = None
+
+            yh = T(y_hat).clone().requires_grad_(True)
+            yc = T(y_comp).clone().requires_grad_(True)
+            loss, items = CHN.compute_loss(FakeCHN2(), T(y_target), T(v_target), yh, yc, T(v_map))
+            loss.backward()
+            save("chnloss_" + name, losses=np.array([float(items[0]), float(items[1]), float(items[2])], np.float32),
+                 g_y_hat=yh.grad.numpy(), g_y_hat_comp=yc.grad.numpy())
+    finally:
+        mt.LossesUtils.perceptual, mt.LossesUtils.grad = orig_p, orig_g
 
 
 if __name__ == "__main__":

@@ -344,6 +344,55 @@ def test_chn(mtb, name):
                           g["nn_input"])
 
 
+@pytest.mark.parametrize("name", sorted(cases.CHNLOSS_CASES))
+def test_chn_l1_terms(mtb, name):
+    """One-pass L1 terms of CHN.compute_loss against the reference's golden outputs, the oracle, the
+    three separate masked_l1 launches, and through the patched CHN.compute_loss."""
+    import sys
+    import types
+    from master_thesis_b200 import ops
+    y_target, v_target, y_hat, y_comp, v_map = cases.chnloss_inputs(cases.CHNLOSS_CASES[name])
+    g = load_golden("chnloss_" + name)
+    yh, yc = dev(y_hat).requires_grad_(True), dev(y_comp).requires_grad_(True)
+    l_nh, l_vh, l_nvh = ops.chn_l1_terms(dev(y_target), dev(v_target), yh, yc, dev(v_map))
+    (l_nh + l_vh + l_nvh).backward()
+    got = np.array([float(l_nh), float(l_vh), float(l_nvh)], np.float32)
+    assert np.allclose(got, g["losses"], rtol=1e-5, atol=0)
+    ol, og_yh, og_yc = oracle.chn_l1_terms(y_target, v_target, y_hat, y_comp, v_map, grads=True)
+    assert np.allclose(got, ol, rtol=1e-5, atol=0)
+    for t, ref, orc in ((yh.grad, g["g_y_hat"], og_yh), (yc.grad, g["g_y_hat_comp"], og_yc)):
+        scale = max(1e-12, np.abs(ref).max())
+        assert np.abs(host(t) - ref).max() <= 1e-6 * scale and np.abs(host(t) - orc).max() <= 1e-6 * scale
+    # the three separate launches (LossesUtils.masked_l1 mirror) give the same numbers
+    f = y_hat.shape[2]
+    tgt = dev(y_target).unsqueeze(2).expand(-1, -1, f, -1, -1)
+    nh = dev(v_target).unsqueeze(2).expand(-1, -1, f, -1, -1)
+    sep = [mtb.LossesUtils.masked_l1(dev(y_hat), tgt, nh, reduction='sum', weight=0.5),
+           mtb.LossesUtils.masked_l1(dev(y_hat), tgt, dev(v_map), reduction='sum', weight=2),
+           mtb.LossesUtils.masked_l1(dev(y_comp), tgt, (1 - nh) - dev(v_map), reduction='sum', weight=1)]
+    assert np.allclose(got, [float(x) for x in sep], rtol=1e-6, atol=0)
+    # through the plug point: CHN.compute_loss with the reference's other two terms stubbed
+    stub = types.ModuleType("master_thesis")
+
+    class _LU(object):
+        perceptual = staticmethod(lambda *a, **k: (torch.zeros((), device="cuda"), None, None))
+        grad = staticmethod(lambda *a, **k: torch.zeros((), device="cuda"))
+
+    stub.LossesUtils = _LU
+    saved = sys.modules.get("master_thesis")
+    sys.modules["master_thesis"] = stub
+    try:
+        fake = types.SimpleNamespace(model_vgg=None)
+        loss, items = mtb.plug.chn_compute_loss(fake, dev(y_target), dev(v_target), dev(y_hat), dev(y_comp),
+                                                dev(v_map))
+    finally:
+        if saved is None:
+            del sys.modules["master_thesis"]
+        else:
+            sys.modules["master_thesis"] = saved
+    assert len(items) == 5 and float(loss) == pytest.approx(float(g["losses"].sum()), rel=1e-5)
+
+
 # ---------------------------------------------------------------- full-size properties
 def test_full_size_properties(mtb):
     """BASELINE cfg2 sizes (B=8, F=4, 256x256): size-independent properties."""

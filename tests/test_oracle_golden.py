@@ -77,6 +77,17 @@ def test_losses_and_backward(name):
     assert np.abs(-gfl1 - g["g_flow_l1"]).max() <= 1e-6 * np.abs(g["g_flow_l1"]).max() + 1e-12
 
 
+@pytest.mark.parametrize("name", sorted(cases.CHNLOSS_CASES))
+def test_chn_l1_terms(name):
+    """The L1 terms of the unmodified CHN.compute_loss (model_chn.py:347-362) and their autograd."""
+    y_target, v_target, y_hat, y_comp, v_map = cases.chnloss_inputs(cases.CHNLOSS_CASES[name])
+    g = load_golden("chnloss_" + name)
+    losses, g_yh, g_yc = oracle.chn_l1_terms(y_target, v_target, y_hat, y_comp, v_map, grads=True)
+    assert np.allclose(losses, g["losses"], rtol=1e-5, atol=0)
+    for got, ref in ((g_yh, g["g_y_hat"]), (g_yc, g["g_y_hat_comp"])):
+        assert np.abs(got - ref).max() <= 1e-6 * max(1e-12, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("name", sorted(cases.CORR_CASES))
 def test_corr4d(name):
     ft, vt, fr, vr = cases.corr_inputs(cases.CORR_CASES[name])
