@@ -190,6 +190,9 @@ MT_API int mt_corr4d_uses_tensor_cores(int C, int P);
  * c_feats (B,C,f,h,w) contiguous (index 0 of f = target), v_t (B,1,H,W),
  * v_aligned (B,1,f-1,H,W) contiguous.  out (B,2C+1,h,w) = cat[c_t,c_out,c_mask],
  * c_mask (B,1,h,w).  1 <= f-1 <= 8, h*w % 4 == 0.
+ * Launches: masks (bilinear down-sample > 0.5, one byte per pixel), similarity partials, then the
+ * weighted copy, which folds the partials and looks the softmax weights up per mask pattern
+ * (f-1 <= 7; with 8 references a separate weights kernel runs).
  * workspace: mt_cm_workspace_bytes(B, C, f, h, w) bytes (no zeroing needed). */
 MT_API int mt_cm_match_fwd(const float *c_feats, const float *v_t, const float *v_aligned,
                     float *out, float *c_mask, void *workspace,
