@@ -177,8 +177,8 @@ class Cfg4(Workload):
     def __init__(self, b=1, f=1, h=480, w=854):
         self.b, self.f, self.h, self.w = b, f, h, w
         self.frames_per_step = b * f
-        self.describe = ("cfg4: CHN inference hot path, DFPN aligner (warp + pack + composite + "
-                         "hole update), batch_size=%d F=%d %dx%d per GPU" % (b, f, h, w))
+        self.describe = ("cfg4: CHN inference hot path, DFPN aligner (warp + pack | composite + "
+                         "hole update: two kernels), batch_size=%d F=%d %dx%d per GPU" % (b, f, h, w))
 
     def host_inputs(self, seed):
         import numpy as np
@@ -198,11 +198,13 @@ class Cfg4(Workload):
     inputs_h2d = ("x_target", "x_refs", "m_refs", "m_target", "v_target", "flow", "nn_out")
 
     def gpu_step(self, mtb, d):
+        # the step of CHN.inpaint_* as the patched loop runs it (plug._fill_step): warp + CNN-input pack in
+        # one kernel, [RRDBNet: cuDNN, outside the hot path], composite + hole update in one kernel
         ops = mtb.ops
-        xa, va, vm = mtb.dfpn_align_tail(d["x_refs"], d["m_refs"], d["m_target"], d["flow"])
-        nn_in = ops.chn_pack(d["x_target"], d["v_target"], xa, va, vm)
-        y_hat, y_comp = ops.chn_composite(d["nn_out"], d["x_target"], d["v_target"], self.b, self.f)
-        m_new, x_new, per = ops.hole_update(d["m_target"], vm[:, :, 0], y_comp[:, :, 0])
+        nn_in, vm, _, _ = ops.warp_pack_fwd(d["x_refs"], d["m_refs"], d["flow"], d["m_target"], d["x_target"],
+                                            d["v_target"], ops.ALIGN_CORNERS | ops.VIS_FROM_MASK)
+        y_comp, m_new, x_new, per = ops.chn_fill(d["nn_out"], d["x_target"], d["v_target"], d["m_target"],
+                                                 vm[:, :, 0])
         return {"nn_in": nn_in, "y_comp": y_comp, "m_new": m_new, "x_new": x_new, "inp_per": per}
 
     def cpu_step(self, tp, d):
@@ -214,10 +216,10 @@ class Cfg4(Workload):
     def calls(self):
         px = self.h * self.w
         n = self.b * self.f
-        return [("mt_warp_fwd", 1, n * 44 * px + self.b * 4 * px, "hbm"),
-                ("mt_chn_pack", 1, n * 56 * px + self.b * 16 * px, "hbm"),
-                ("mt_chn_composite_fwd", 1, n * 36 * px + self.b * 16 * px, "hbm"),
-                ("mt_hole_update", 1, self.b * 36 * px, "hbm")]
+        # warp + pack: x_ref 12, m_ref 4, flow 8 in; nn_in 36, v_map 4 out; per sample x_t 12, v_t 4, m_t 4 in
+        # composite + hole update (F = 1): nn_out 12, x_t 12, v_t 4, m_t 4, v_map 4 in; y_comp 12, m_new 4, x_new 12 out
+        return [("mt_warp_pack_fwd", 1, n * 64 * px + self.b * 20 * px, "hbm"),
+                ("mt_chn_fill_step", 1, self.b * 64 * px, "hbm")]
 
     def sub(self, b):
         return Cfg4(b, self.f, self.h, self.w)
@@ -592,8 +594,8 @@ def run_gpu(args):
     single = [c for c in per_call if c["launches"] == 1] or per_call
     dom = max(single, key=lambda c: c["avg_us"] / c["launches"])
     call = dom["call"].split("#")[0]
-    kname = {"mt_warp_fwd": "warp_fwd_kernel", "mt_warp_l1_fwd": "warp_l1_fwd_kernel",
-             "mt_warp_l1_bwd": "warp_l1_bwd_kernel"}.get(call, call)
+    kname = {"mt_warp_fwd": "warp_fwd_kernel", "mt_warp_pack_fwd": "warp_fwd_kernel<PACK>",
+             "mt_warp_l1_fwd": "warp_l1_fwd_kernel", "mt_warp_l1_bwd": "warp_l1_bwd_kernel"}.get(call, call)
     roofline = {"bound": "hbm", "kernel": kname, "call": dom["call"], "launches_in_call": dom["launches"],
                 "achieved": dom["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": dom["frac_hbm"], "traffic": None, "peak_source": peak_src,

@@ -87,6 +87,19 @@ MT_API int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
                 float *v_aligned, float *v_map,
                 int B, int C, int F, int H, int W, int flags, mt_stream_t stream);
 
+/* mt_warp_fwd that also writes the CNN input of CHN.forward (model_chn.py:68-80):
+ * nn_in (B*F, 9, H, W) = [(x_t - mean)/std, (x_aligned - mean)/std, v_t, v_aligned, v_map], exactly
+ * what mt_chn_pack produces from this call's outputs.  x_t (B,3,H,W) strided, v_t (B,1,H,W);
+ * x_aligned / v_aligned / v_map may be NULL (the inference loop only needs v_map).  C = 3. */
+MT_API int mt_warp_pack_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
+                     const float *vis, int64_t vis_sb, int64_t vis_sf,
+                     const float *grid, const float *m_target, int64_t mt_sb,
+                     const float *x_t, int64_t xt_sb, int64_t xt_sc, const float *v_t, int64_t vt_sb,
+                     float *nn_in,
+                     float *x_aligned, int64_t xa_sb, int64_t xa_sc, int64_t xa_sf,
+                     float *v_aligned, float *v_map,
+                     int B, int F, int H, int W, int flags, mt_stream_t stream);
+
 /* ---- K1b  backward of the bilinear warp w.r.t. the dense grid ------------
  * replaces autograd of F.grid_sample in align_set (utils.py:93-97)       (a6)
  * gout (B,C,F,H,W) strided (plane contiguous) -> ggrid (B,F,H,W,2) contiguous.
@@ -170,6 +183,15 @@ MT_API int mt_chn_l1x3_bwd(const float *y_hat, int64_t yh_sb, int64_t yh_sc, int
                     const float *v_map, int64_t vm_sb, int64_t vm_sf,
                     const float *out9, const float *grad_out3, float *grad_y_hat, float *grad_y_comp,
                     int B, int F, int64_t P, float w_nh, float w_vh, float w_nvh, mt_stream_t stream);
+
+/* composite (model_chn.py:80-85) + hole update (model_chn.py:128-131) of one inference step in one pass
+ * (F = 1): y_comp0 (B,3,P), m_new (B,1,P), x_new (B,3,P), inp_per (1) - what mt_chn_composite_fwd
+ * followed by mt_hole_update produce.  nn_out (B,3,P); x_t strided; v_t, m_t, v_map0 (B,1,P) strided.
+ * workspace: mt_workspace_bytes() bytes, zero-initialised once. */
+MT_API int mt_chn_fill_step(const float *nn_out, const float *x_t, int64_t xt_sb, int64_t xt_sc,
+                     const float *v_t, int64_t vt_sb, const float *m_t, int64_t mt_sb,
+                     const float *v_map0, int64_t vm_sb, float *y_comp0, float *m_new, float *x_new,
+                     float *inp_per, void *workspace, int B, int64_t P, mt_stream_t stream);
 
 /* ---- K2  masked cosine correlation on tcgen05 ----------------------------
  * replaces CorrelationVGG.correlation_masked_4d  model_dfpn.py:534-565  (a7)

@@ -172,6 +172,64 @@ __global__ void __launch_bounds__(256) hole_update_kernel(const HoleArgs a) {
     });
 }
 
+// ---- a10 + a11: composite and hole update of one inference step (F = 1) in one pass ------------
+struct FillArgs {
+    const float *nn_out;
+    const float *x_t; int64_t xt_sb, xt_sc;
+    const float *v_t; int64_t vt_sb;
+    const float *m_t; int64_t mt_sb;
+    const float *v_map0; int64_t vm_sb;
+    float *y_comp0, *m_new, *x_new, *inp_per;
+    void *ws;
+    int B; int64_t P; int chunks; int64_t total_chunks;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) chn_fill_kernel(const FillArgs a) {
+    pdl_sync();
+    __shared__ float red[32];
+    float acc[1] = {0.0f};
+    for (int64_t ch = blockIdx.x; ch < a.total_chunks; ch += gridDim.x) {
+        const int b = (int)(ch / a.chunks);
+        const int64_t p0 = ((ch - (int64_t)b * a.chunks) * blockDim.x + threadIdx.x) * VEC;
+        if (p0 >= a.P) continue;
+        Vec<VEC> vt, m, vm, o[3], xt[3];
+        vt.load_stream(a.v_t + b * a.vt_sb + p0);
+        m.load_stream(a.m_t + b * a.mt_sb + p0);
+        vm.load_stream(a.v_map0 + b * a.vm_sb + p0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            o[c].load_stream(a.nn_out + ((int64_t)b * 3 + c) * a.P + p0);
+            xt[c].load_stream(a.x_t + b * a.xt_sb + c * a.xt_sc + p0);
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            m.v[i] = __fsub_rn(m.v[i], vm.v[i]);  // m_t - v_map[:, :, 0]       :128
+            acc[0] += m.v[i];
+        }
+        m.store_stream(a.m_new + (int64_t)b * a.P + p0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float mean = chan_mean(c), s = chan_std(c);  // fill colour == mean, model_chn.py:102-104
+            Vec<VEC> yc, xn;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float yh = clamp01(__fadd_rn(__fmul_rn(o[c].v[i], s), mean));            // :83
+                yc.v[i] = __fadd_rn(__fmul_rn(vt.v[i], xt[c].v[i]),                             // :84
+                                    __fmul_rn(__fsub_rn(1.0f, vt.v[i]), yh));
+                xn.v[i] = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, m.v[i]), yc.v[i]), __fmul_rn(m.v[i], mean));  // :129-130
+            }
+            yc.store_stream(a.y_comp0 + ((int64_t)b * 3 + c) * a.P + p0);
+            xn.store_stream(a.x_new + ((int64_t)b * 3 + c) * a.P + p0);
+        }
+    }
+    float *out = a.inp_per;
+    const float numel = (float)((double)a.B * (double)a.P);
+    grid_reduce_finish<1>(acc, a.ws, red, [out, numel](const double *tot) {
+        out[0] = (float)tot[0] * 100.0f / numel;  // sum(m)*100/numel               :131
+    });
+}
+
 // ---- a12 trivial copy ------------------------------------------------------------
 struct TrivArgs {
     const float *x_t; int64_t xt_sb, xt_sc;
@@ -333,6 +391,14 @@ __global__ void __launch_bounds__(256) chn_l1x3_fwd_kernel(const L1x3Args a) {
         Vec<VEC> m1, m2, m3;
         m1.load_cached(a.vt + b * a.vt_sb + p0);
         m2.load_stream(a.vm + b * a.vm_sb + f * a.vm_sf + p0);
+        // all nine operand loads of the chunk in flight before the first use
+        Vec<VEC> yh[3], yc[3], yt[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            yh[c].load_stream(a.yh + b * a.yh_sb + c * a.yh_sc + f * a.yh_sf + p0);
+            yc[c].load_stream(a.yc + b * a.yc_sb + c * a.yc_sc + f * a.yc_sf + p0);
+            yt[c].load_cached(a.yt + b * a.yt_sb + c * a.yt_sc + p0);
+        }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             m3.v[i] = __fsub_rn(__fsub_rn(1.0f, m1.v[i]), m2.v[i]);  // (1 - nh_mask) - vh_mask   :359
@@ -340,15 +406,11 @@ __global__ void __launch_bounds__(256) chn_l1x3_fwd_kernel(const L1x3Args a) {
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            Vec<VEC> yh, yc, yt;
-            yh.load_stream(a.yh + b * a.yh_sb + c * a.yh_sc + f * a.yh_sf + p0);
-            yc.load_stream(a.yc + b * a.yc_sb + c * a.yc_sc + f * a.yc_sf + p0);
-            yt.load_cached(a.yt + b * a.yt_sb + c * a.yt_sc + p0);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {  // |y_hat*mask - y*mask|   utils.py:166
-                acc[0] += fabsf(__fsub_rn(__fmul_rn(yh.v[i], m1.v[i]), __fmul_rn(yt.v[i], m1.v[i])));
-                acc[1] += fabsf(__fsub_rn(__fmul_rn(yh.v[i], m2.v[i]), __fmul_rn(yt.v[i], m2.v[i])));
-                acc[2] += fabsf(__fsub_rn(__fmul_rn(yc.v[i], m3.v[i]), __fmul_rn(yt.v[i], m3.v[i])));
+                acc[0] += fabsf(__fsub_rn(__fmul_rn(yh[c].v[i], m1.v[i]), __fmul_rn(yt[c].v[i], m1.v[i])));
+                acc[1] += fabsf(__fsub_rn(__fmul_rn(yh[c].v[i], m2.v[i]), __fmul_rn(yt[c].v[i], m2.v[i])));
+                acc[2] += fabsf(__fsub_rn(__fmul_rn(yc[c].v[i], m3.v[i]), __fmul_rn(yt[c].v[i], m3.v[i])));
             }
         }
     }
@@ -639,4 +701,26 @@ extern "C" int mt_chn_l1x3_bwd(const float *y_hat, int64_t yh_sb, int64_t yh_sc,
     if (v4) launch(chn_l1x3_bwd_kernel<4>, grid, 256, 0, (cudaStream_t)stream, a);
     else launch(chn_l1x3_bwd_kernel<1>, grid, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_chn_l1x3_bwd");
+}
+
+extern "C" int mt_chn_fill_step(const float *nn_out, const float *x_t, int64_t xt_sb, int64_t xt_sc,
+                                const float *v_t, int64_t vt_sb, const float *m_t, int64_t mt_sb,
+                                const float *v_map0, int64_t vm_sb, float *y_comp0, float *m_new,
+                                float *x_new, float *inp_per, void *workspace, int B, int64_t P,
+                                mt_stream_t stream) {
+    MT_REQUIRE(nn_out && x_t && v_t && m_t && v_map0 && y_comp0 && m_new && x_new && inp_per && workspace,
+               "mt_chn_fill_step: NULL argument");
+    MT_REQUIRE(B > 0 && P > 0, "mt_chn_fill_step: bad shape");
+    FillArgs a{nn_out, x_t, xt_sb, xt_sc, v_t, vt_sb, m_t, mt_sb, v_map0, vm_sb, y_comp0, m_new, x_new, inp_per,
+               workspace, B, P, 0, 0};
+    bool v4 = mult4(P) && aligned16(nn_out) && aligned16(x_t) && aligned16(v_t) && aligned16(m_t) &&
+              aligned16(v_map0) && aligned16(y_comp0) && aligned16(m_new) && aligned16(x_new) && mult4(xt_sb) &&
+              mult4(xt_sc) && mult4(vt_sb) && mult4(mt_sb) && mult4(vm_sb);
+    const int vec = v4 ? 4 : 1;
+    a.chunks = (int)((P + 256 * vec - 1) / (256 * vec));
+    a.total_chunks = (int64_t)B * a.chunks;
+    const int nblk = reduce_blocks(a.total_chunks);
+    if (v4) launch(chn_fill_kernel<4>, nblk, 256, 0, (cudaStream_t)stream, a);
+    else launch(chn_fill_kernel<1>, nblk, 256, 0, (cudaStream_t)stream, a);
+    return launch_status("mt_chn_fill_step");
 }

@@ -52,6 +52,10 @@ struct WarpFwdArgs {
     unsigned f_magic;  // ceil(2^32 / F): b = umulhi(n, f_magic) for n < 2^16; 0 when F == 1 (b = n)
     Sampler sp;
     bool from_mask;
+    // PACK: the CNN input of CHN.forward is written by this launch as well (model_chn.py:68-80)
+    const float *x_t, *v_t;
+    float *nn_in;
+    int xt_sb, xt_sc, vt_sb;
 };
 constexpr int kMaxRowsPerCta = 32;
 
@@ -66,7 +70,10 @@ constexpr int kMaxRowsPerCta = 32;
 // uniform branches, the affine row term computed once per CTA, 32-bit offsets.
 // VIS: 1 = nearest (DFPN), 2 = bilinear > 0.5 (CPN).  FULL: x_al, v_al and v_map
 // are all requested (no NULL checks).
-template <int C, int U, int VIS, bool AFFINE, bool FULL>
+// PACK (C == 3): additionally writes nn_in (B*F, 9, H, W) = [(x_t - mean) / std, (x_aligned - mean) / std,
+// v_t, v_aligned, v_map] - the chn_pack kernel's output - so that the inference loop of CHN.inpaint_*
+// needs no second pass over the aligned frame.
+template <int C, int U, int VIS, bool AFFINE, bool FULL, bool PACK = false>
 __global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const WarpFwdArgs a) {
     pdl_sync();
     __shared__ float s_by[kMaxRowsPerCta];
@@ -112,6 +119,16 @@ __global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const War
         if (FULL || a.v_map) {
 #pragma unroll
             for (int k = 0; k < U; ++k) mtv[k] = (y0 + k < H) ? __ldcs(a.m_target + (mto + p0 + k * W)) : 0.0f;
+        }
+        float xtv[PACK ? 3 : 1][U], vtv[U];
+        if (PACK) {
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const bool in = y0 + k < H;
+                vtv[k] = in ? __ldg(a.v_t + (b * a.vt_sb + p0 + k * W)) : 0.0f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) xtv[c][k] = in ? __ldg(a.x_t + (b * a.xt_sb + c * a.xt_sc + p0 + k * W)) : 0.0f;
+            }
         }
         float ix[U], iy[U], xw[U], yn[U];
         float wnw[U], wne[U], wsw[U], wse[U];
@@ -214,8 +231,21 @@ __global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const War
                     for (int c = 0; c < C; ++c) st_stream1(a.x_al + (xao + p0 + c * a.xa_sc + k * W), xa[c][k]);
                 }
                 if (FULL || a.v_al) st_stream1(a.v_al + (np0 + k * W), va[k]);
+                const float vmap = (FULL || PACK || a.v_map) ? clamp01(__fsub_rn(va[k], __fsub_rn(1.0f, mtv[k]))) : 0.0f;
                 if (FULL || a.v_map)  // clamp(v_al - (1 - m_t), 0, 1)
-                    st_stream1(a.v_map + (np0 + k * W), clamp01(__fsub_rn(va[k], __fsub_rn(1.0f, mtv[k]))));
+                    st_stream1(a.v_map + (np0 + k * W), vmap);
+                if (PACK) {
+                    float *o = a.nn_in + ((int)n * 9 * a.P + p0 + k * W);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {  // (x - mean) / std   model_chn.py:73-74
+                        const float m = chan_mean(c), sd = chan_std(c);
+                        st_stream1(o + c * a.P, __fdiv_rn(__fsub_rn(xtv[c][k], m), sd));
+                        st_stream1(o + (3 + c) * a.P, __fdiv_rn(__fsub_rn(xa[c][k], m), sd));
+                    }
+                    st_stream1(o + 6 * a.P, vtv[k]);
+                    st_stream1(o + 7 * a.P, va[k]);
+                    st_stream1(o + 8 * a.P, vmap);
+                }
             }
         }
     }
@@ -479,11 +509,17 @@ static unsigned frame_magic(int F) {
     return F == 1 ? 0u : (unsigned)(((1ull << 32) + (unsigned)F - 1) / (unsigned)F);
 }
 
-extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
-                           const float *vis, int64_t vis_sb, int64_t vis_sf, const float *grid,
-                           const float *m_target, int64_t mt_sb, float *x_aligned, int64_t xa_sb,
-                           int64_t xa_sc, int64_t xa_sf, float *v_aligned, float *v_map, int B,
-                           int C, int F, int H, int W, int flags, mt_stream_t stream) {
+struct PackOut {
+    const float *x_t; int64_t xt_sb, xt_sc;
+    const float *v_t; int64_t vt_sb;
+    float *nn_in;
+};
+
+static int warp_fwd_impl(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
+                         const float *vis, int64_t vis_sb, int64_t vis_sf, const float *grid,
+                         const float *m_target, int64_t mt_sb, float *x_aligned, int64_t xa_sb,
+                         int64_t xa_sc, int64_t xa_sf, float *v_aligned, float *v_map, int B,
+                         int C, int F, int H, int W, int flags, mt_stream_t stream, const PackOut *pack) {
     MT_REQUIRE(x && vis && grid, "mt_warp_fwd: NULL input");
     MT_REQUIRE(B > 0 && F > 0 && H > 0 && W > 0, "mt_warp_fwd: empty shape B=%d F=%d H=%d W=%d", B, F, H, W);
     MT_REQUIRE(C == 1 || C == 3, "mt_warp_fwd: C must be 1 or 3 (reference hard-codes 3, utils.py:97), got %d", C);
@@ -510,6 +546,15 @@ extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x
     a.f_magic = frame_magic(F);
     a.sp = make_sampler(H, W, (flags & MT_ALIGN_CORNERS) != 0);
     a.from_mask = (flags & MT_VIS_FROM_MASK) != 0;
+    a.x_t = a.v_t = nullptr; a.nn_in = nullptr; a.xt_sb = a.xt_sc = a.vt_sb = 0;
+    if (pack) {
+        MT_REQUIRE(C == 3 && m_target && pack->x_t && pack->v_t && pack->nn_in, "mt_warp_pack_fwd: C must be 3, no NULL input");
+        MT_REQUIRE(pack->xt_sb >= 0 && pack->xt_sc >= 0 && pack->vt_sb >= 0 &&
+                   (B - 1) * pack->xt_sb + 2 * pack->xt_sc + P < lim && (B - 1) * pack->vt_sb + P < lim &&
+                   (int64_t)B * F * 9 * P < lim, "mt_warp_pack_fwd: tensors beyond 2^31 elements are not supported");
+        a.x_t = pack->x_t; a.v_t = pack->v_t; a.nn_in = pack->nn_in;
+        a.xt_sb = (int)pack->xt_sb; a.xt_sc = (int)pack->xt_sc; a.vt_sb = (int)pack->vt_sb;
+    }
     const bool affine = (flags & MT_GRID_AFFINE) != 0;
     const bool vis_bil = (flags & MT_VIS_BILINEAR) != 0;
     const int rows = tuning("MT_WARP_ROWS", kRows) == 2 ? 2 : 4;
@@ -520,6 +565,17 @@ extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x
     dim3 block(kCols), gridd((W + kCols - 1) / kCols, (H + rows * iters - 1) / (rows * iters), B * F);
     cudaStream_t st = (cudaStream_t)stream;
     const bool full = x_aligned && v_aligned && v_map;
+    if (pack) {
+#define MT_WARP_PACK_GO(VV, AA)                                                                       \
+    do {                                                                                              \
+        if (rows == 2) launch(warp_fwd_kernel<3, 2, VV, AA, false, true>, gridd, block, 0, st, a);    \
+        else launch(warp_fwd_kernel<3, 4, VV, AA, false, true>, gridd, block, 0, st, a);              \
+    } while (0)
+        if (vis_bil) { if (affine) MT_WARP_PACK_GO(2, true); else MT_WARP_PACK_GO(2, false); }
+        else         { if (affine) MT_WARP_PACK_GO(1, true); else MT_WARP_PACK_GO(1, false); }
+#undef MT_WARP_PACK_GO
+        return launch_status("mt_warp_pack_fwd");
+    }
     if (affine && vis_bil && C == 3 && full) {
         // CPN.align tail: persistent kernel with TMA-staged reference tiles (warp_tma.cu) when it applies
         const int rc = warp_staged_launch(x, x_sb, x_sc, x_sf, vis, vis_sb, vis_sf, grid, m_target, mt_sb, x_aligned,
@@ -546,6 +602,27 @@ extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x
 #undef MT_WARP_PICK
 #undef MT_WARP_GO
     return launch_status("mt_warp_fwd");
+}
+
+extern "C" int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
+                           const float *vis, int64_t vis_sb, int64_t vis_sf, const float *grid,
+                           const float *m_target, int64_t mt_sb, float *x_aligned, int64_t xa_sb,
+                           int64_t xa_sc, int64_t xa_sf, float *v_aligned, float *v_map, int B,
+                           int C, int F, int H, int W, int flags, mt_stream_t stream) {
+    return warp_fwd_impl(x, x_sb, x_sc, x_sf, vis, vis_sb, vis_sf, grid, m_target, mt_sb, x_aligned, xa_sb, xa_sc,
+                         xa_sf, v_aligned, v_map, B, C, F, H, W, flags, stream, nullptr);
+}
+
+extern "C" int mt_warp_pack_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
+                                const float *vis, int64_t vis_sb, int64_t vis_sf, const float *grid,
+                                const float *m_target, int64_t mt_sb, const float *x_t, int64_t xt_sb,
+                                int64_t xt_sc, const float *v_t, int64_t vt_sb, float *nn_in,
+                                float *x_aligned, int64_t xa_sb, int64_t xa_sc, int64_t xa_sf,
+                                float *v_aligned, float *v_map, int B, int F, int H, int W, int flags,
+                                mt_stream_t stream) {
+    PackOut pk{x_t, xt_sb, xt_sc, v_t, vt_sb, nn_in};
+    return warp_fwd_impl(x, x_sb, x_sc, x_sf, vis, vis_sb, vis_sf, grid, m_target, mt_sb, x_aligned, xa_sb, xa_sc,
+                         xa_sf, v_aligned, v_map, B, 3, F, H, W, flags, stream, &pk);
 }
 
 extern "C" int mt_warp_bwd_grid(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,

@@ -132,6 +132,36 @@ def warp_fwd(x, vis, grid, m_target=None, flags=ALIGN_CORNERS, want_x=True, want
     return xa, va, vm
 
 
+def warp_pack_fwd(x, vis, grid, m_target, x_t, v_t, flags=ALIGN_CORNERS, want_aligned=False):
+    """mt_warp_pack_fwd: the warp of mt_warp_fwd that also writes the CNN input of CHN.forward.
+
+    Returns (nn_in (B*F,9,H,W), v_map (B,1,F,H,W), x_aligned | None, v_aligned | None)."""
+    _need_cuda(x, vis, grid, m_target, x_t, v_t)
+    b, c, f, h, w = x.shape
+    if c != 3:
+        raise RuntimeError("warp_pack_fwd: C must be 3")
+    x, x_sb, x_sc, x_sf = _s5(x)
+    vis, v_sb, _, v_sf = _s5(vis)
+    grid = _contig(grid)
+    if flags & GRID_AFFINE:
+        if grid.numel() != b * f * 6:
+            raise RuntimeError("theta must have shape (B*F,2,3)")
+    elif tuple(grid.shape) != (b, f, h, w, 2):
+        raise RuntimeError("flow must have shape (B,F,H,W,2), got %s" % (tuple(grid.shape),))
+    m_target, xt, vt = _planes(m_target), _planes(x_t), _planes(v_t)
+    p = h * w
+    xa_mem = xa = va = None
+    if want_aligned:
+        xa_mem, xa = _frame_major(b, c, f, h, w, x)
+        va = _empty((b, 1, f, h, w), dtype=torch.float32, device=x.device)
+    vm = _empty((b, 1, f, h, w), dtype=torch.float32, device=x.device)
+    nn_in = _empty((b * f, 9, h, w), dtype=torch.float32, device=x.device)
+    _lib.call("mt_warp_pack_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis), v_sb, v_sf, _ptr(grid),
+              _ptr(m_target), m_target.stride(0), _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0),
+              _ptr(nn_in), _ptr(xa_mem), f * c * p, p, c * p, _ptr(va), _ptr(vm), b, f, h, w, flags, _stream(x))
+    return nn_in, vm, xa, va
+
+
 def warp_bwd_grid(x, grid, gout, flags=ALIGN_CORNERS):
     _need_cuda(x, grid, gout)
     b, c, f, h, w = x.shape
@@ -522,6 +552,23 @@ def hole_update(m_t, v_map0, y_comp0):
               yc.stride(1), _ptr(m_new), _ptr(x_new), _ptr(per), _ptr(reduce_workspace(mt)), b, h * w,
               _stream(mt))
     return m_new, x_new, per[0]
+
+
+def chn_fill(nn_out, x_t, v_t, m_t, v_map0):
+    """mt_chn_fill_step: composite (model_chn.py:80-85) + hole update (:128-131) of one inference step
+    with a single reference frame.  nn_out (B,3,H,W).  Returns (y_comp0 (B,3,H,W), m_new, x_new, inp_per)."""
+    _need_cuda(nn_out, x_t, v_t, m_t, v_map0)
+    b = x_t.shape[0]
+    h, w = x_t.shape[-2:]
+    no, xt, vt, mt, vm = _contig(nn_out), _planes(x_t), _planes(v_t), _planes(m_t), _planes(v_map0)
+    yc = _empty((b, 3, h, w), dtype=torch.float32, device=no.device)
+    m_new = _empty((b, 1, h, w), dtype=torch.float32, device=no.device)
+    x_new = _empty((b, 3, h, w), dtype=torch.float32, device=no.device)
+    per = _empty(1, dtype=torch.float32, device=no.device)
+    _lib.call("mt_chn_fill_step", _ptr(no), _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0),
+              _ptr(mt), mt.stride(0), _ptr(vm), vm.stride(0), _ptr(yc), _ptr(m_new), _ptr(x_new), _ptr(per),
+              _ptr(reduce_workspace(no)), b, h * w, _stream(no))
+    return yc, m_new, x_new, per[0]
 
 
 def trivial_copy(x_t, x_al, v_map):

@@ -70,20 +70,16 @@ class CM_Module(nn.Module):
 # aligner protocol: .align(x_target, m_target, x_refs, m_refs)
 #                   -> (x_aligned, v_aligned, v_maps)
 # ---------------------------------------------------------------------------
-def dfpn_align(self, x_target, m_target, x_refs, m_refs):
-    """Replaces DFPN.align (model_dfpn.py:103-133).  ``self`` is the DFPN module: its
-    forward (VGG, 4-D conv, flow estimators: cuDNN) still produces the flow; the warp of
-    the frames, of the visibility 1 - m_refs and the v_map are one kernel."""
+def _dfpn_grid(self, x_target, m_target, x_refs, m_refs):
+    """The flow of DFPN.align (model_dfpn.py:103-127): the DFPN forward (VGG, 4-D conv, flow
+    estimators: cuDNN), untouched."""
     with torch.no_grad():
         *_, flow_256 = self(x_target, m_target, x_refs, m_refs)
-    return ops.warp_fwd(x_refs, m_refs, flow_256, m_target,
-                        ops.ALIGN_CORNERS | ops.VIS_FROM_MASK)
+    return flow_256, ops.ALIGN_CORNERS | ops.VIS_FROM_MASK
 
 
-def cpn_align(self, x_target, m_target, x_refs, m_refs):
-    """Replaces CPN.align (model_cpn.py:31-91).  ``self`` is the CPN module: A_Encoder and
-    A_Regressor (cuDNN) still produce theta; affine_grid, both grid_samples, the > 0.5
-    threshold and v_maps (model_cpn.py:75-89) are one kernel."""
+def _cpn_grid(self, x_target, m_target, x_refs, m_refs):
+    """theta of CPN.align (model_cpn.py:31-74): A_Encoder and A_Regressor (cuDNN), untouched."""
     b, c, ref_n, h, w = x_refs.size()
     x_target_feats = self.A_Encoder(x_target, m_target)
     x_refs_feats = self.A_Encoder(
@@ -95,8 +91,23 @@ def cpn_align(self, x_target, m_target, x_refs, m_refs):
         x_target_feats.unsqueeze(1).expand(b, ref_n, fc, fh, fw).reshape(-1, fc, fh, fw),
         x_refs_feats,
     )
-    return ops.warp_fwd(x_refs, m_refs, theta_rt.float(), m_target,
-                        ops.GRID_AFFINE | ops.VIS_BILINEAR | ops.VIS_FROM_MASK)
+    return theta_rt.float(), ops.GRID_AFFINE | ops.VIS_BILINEAR | ops.VIS_FROM_MASK
+
+
+def dfpn_align(self, x_target, m_target, x_refs, m_refs):
+    """Replaces DFPN.align (model_dfpn.py:103-133).  ``self`` is the DFPN module: its
+    forward still produces the flow; the warp of the frames, of the visibility 1 - m_refs and
+    the v_map are one kernel."""
+    grid, flags = _dfpn_grid(self, x_target, m_target, x_refs, m_refs)
+    return ops.warp_fwd(x_refs, m_refs, grid, m_target, flags)
+
+
+def cpn_align(self, x_target, m_target, x_refs, m_refs):
+    """Replaces CPN.align (model_cpn.py:31-91).  ``self`` is the CPN module: A_Encoder and
+    A_Regressor (cuDNN) still produce theta; affine_grid, both grid_samples, the > 0.5
+    threshold and v_maps (model_cpn.py:75-89) are one kernel."""
+    grid, flags = _cpn_grid(self, x_target, m_target, x_refs, m_refs)
+    return ops.warp_fwd(x_refs, m_refs, grid, m_target, flags)
 
 
 def dfpn_align_tail(x_refs, m_refs, m_target, flow):
@@ -146,7 +157,20 @@ def chn_compute_loss(self, y_target, v_target, y_hat, y_hat_comp, v_map):
 
 def _fill_step(chn, aligner, x_t, m_t, x_ref, m_ref):
     """One align -> hallucinate -> hole-update step shared by the three inpainting
-    algorithms (model_chn.py:114-131, 165-186, 225-248).  All tensors carry a batch dim."""
+    algorithms (model_chn.py:114-131, 165-186, 225-248).  All tensors carry a batch dim.
+
+    With a patched aligner (DFPN or CPN) the step is two kernels around the hallucination CNN:
+    warp + CNN-input pack, then composite + hole update; the aligned frame itself is
+    never materialised.  Any other aligner object takes the four-kernel route through its own
+    ``align`` and ``chn.forward``."""
+    fn = getattr(type(aligner), "align", None)
+    grid_fn = _dfpn_grid if fn is dfpn_align else (_cpn_grid if fn is cpn_align else None)
+    if grid_fn is not None and x_ref.size(2) == 1:
+        grid, flags = grid_fn(aligner, x_t, m_t, x_ref, m_ref)
+        v_t = 1 - m_t
+        nn_in, v_map, _, _ = ops.warp_pack_fwd(x_ref, m_ref, grid, m_t, x_t, v_t, flags)
+        y_comp, m_new, x_new, per = ops.chn_fill(chn.nn(nn_in), x_t, v_t, m_t, v_map[:, :, 0])
+        return y_comp, m_new, x_new, per
     x_al, v_al, v_map = aligner.align(x_t, m_t, x_ref, m_ref)
     _, y_comp = chn(x_t, 1 - m_t, x_al, v_al, v_map)
     m_new, x_new, per = ops.hole_update(m_t, v_map[:, :, 0], y_comp[:, :, 0])

@@ -393,6 +393,64 @@ def test_chn_l1_terms(mtb, name):
     assert len(items) == 5 and float(loss) == pytest.approx(float(g["losses"].sum()), rel=1e-5)
 
 
+def test_inference_step_fusions(mtb):
+    """warp + CNN-input pack in one kernel and composite + hole update in one kernel are
+    bit-identical to the four-kernel route, to the golden vectors of the reference, and are what the
+    inpainting loop's step uses when the aligner is a patched DFPN / CPN."""
+    from master_thesis_b200 import ops, plug
+    # (1) warp + pack == pack(warp), dense flow (DFPN) and theta (CPN)
+    x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES["f1_odd"])
+    _, _, theta = cases.cpn_inputs(cases.CPN_CASES["rand_f4"])[1:]
+    r = cases.synth.rng(5)
+    x_t = r.random_sample((x.shape[0], 3) + x.shape[-2:]).astype(np.float32)
+    for grid, flags, xx, mm, mt_ in (
+            (flow, ops.ALIGN_CORNERS | ops.VIS_FROM_MASK, x, m, m_t),
+            (theta, ops.GRID_AFFINE | ops.VIS_BILINEAR | ops.VIS_FROM_MASK) + cases.cpn_inputs(cases.CPN_CASES["rand_f4"])[:3]):
+        xt = dev(r.random_sample((xx.shape[0], 3) + xx.shape[-2:]).astype(np.float32))
+        vt = 1 - dev(mt_)
+        xa, va, vm = ops.warp_fwd(dev(xx), dev(mm), dev(grid), dev(mt_), flags)
+        want = ops.chn_pack(xt, vt, xa, va, vm)
+        nn_in, vm2, xa2, va2 = ops.warp_pack_fwd(dev(xx), dev(mm), dev(grid), dev(mt_), xt, vt, flags, want_aligned=True)
+        assert torch.equal(nn_in, want) and torch.equal(vm2, vm) and torch.equal(xa2, xa) and torch.equal(va2, va)
+        nn_in3, vm3, xa3, va3 = ops.warp_pack_fwd(dev(xx), dev(mm), dev(grid), dev(mt_), xt, vt, flags)
+        assert torch.equal(nn_in3, want) and torch.equal(vm3, vm) and xa3 is None and va3 is None
+    # (2) composite + hole update == the two kernels == golden (F = 1 case of the reference run)
+    x_t, v_t, x_al, v_al, v_map, nn_out = cases.chn_inputs(cases.CHN_CASES["f1_odd"])
+    g = load_golden("chn_f1_odd")
+    b = x_t.shape[0]
+    yc, m_new, x_new, per = ops.chn_fill(dev(nn_out), dev(x_t), dev(v_t), dev(1 - v_t), dev(v_map)[:, :, 0])
+    assert np.array_equal(host(yc), g["y_hat_comp"][:, :, 0]) and np.array_equal(host(m_new), g["m_new"])
+    assert np.array_equal(host(x_new), g["x_new"]) and float(per) == pytest.approx(float(g["inp_per"]), rel=1e-5)
+    # (3) the inpainting step: fused route (patched aligner class) == generic route (foreign aligner)
+    x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES["f1_odd"])
+    nn_o = dev(cases.synth.nn_output(9, x.shape[0], x.shape[-2], x.shape[-1]))
+
+    class _DFPNLike(object):
+        align = plug.dfpn_align
+
+        def __call__(self, *a):
+            return None, None, None, dev(flow)
+
+    class _Foreign(object):
+        def align(self, x_target, m_target, x_refs, m_refs):
+            return plug.dfpn_align_tail(x_refs, m_refs, m_target, dev(flow))
+
+    class _CHNLike(object):
+        forward = plug.chn_forward
+
+        def nn(self, inp):
+            return nn_o
+
+        def __call__(self, *a):
+            return self.forward(*a)
+
+    xt = dev(r.random_sample((x.shape[0], 3) + x.shape[-2:]).astype(np.float32))
+    fused = plug._fill_step(_CHNLike(), _DFPNLike(), xt, dev(m_t), dev(x), dev(m))
+    plain = plug._fill_step(_CHNLike(), _Foreign(), xt, dev(m_t), dev(x), dev(m))
+    for a_, b_ in zip(fused, plain):
+        assert torch.equal(a_, b_)
+
+
 # ---------------------------------------------------------------- full-size properties
 def test_full_size_properties(mtb):
     """BASELINE cfg2 sizes (B=8, F=4, 256x256): size-independent properties."""
