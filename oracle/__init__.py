@@ -271,3 +271,29 @@ def chn_l1_terms(y_target, v_target, y_hat, y_hat_comp, v_map, weights=(0.5, 2.0
              masked_l1_bwd(y_hat, target_img, vh, reduction="sum", weight=weights[1]))
     g_yc = -masked_l1_bwd(y_hat_comp, target_img, nvh, reduction="sum", weight=weights[2])
     return losses, g_yh, g_yc
+
+
+def inpaint_ff(x, m, flows, nn_outs, s=1, D=20, e=1):
+    """CHN.inpaint_ff (model_chn.py:87-133) with the DFPN aligner, as a loop over the oracle's a2, a9-a11;
+    the DFPN forward and the RRDBNet are the preset tensors ``flows`` / ``nn_outs`` in call order.
+    x (3,n,h,w), m (1,n,h,w).  Returns (y_inpainted (3,n,h,w), number of steps)."""
+    n = x.shape[1]
+    y = np.zeros_like(x)
+    k = 0
+    for t in range(n):
+        x_t, m_t = x[None, :, t].copy(), m[None, :, t].copy()
+        cand = [r for r in range(n) if r != t]
+        cand = [r for _, r in sorted((abs(r - t), r) for r in cand)]
+        cand = [r for r in cand if abs(r - t) <= D and abs(r - t) % s == 0]      # :460-482
+        y_comp, per = None, 0.0
+        while y_comp is None or (len(cand) > 0 and per > e):                     # :111-112
+            r = cand.pop(0)
+            x_al, v_al, v_map = dfpn_align_tail(x[None, :, r:r + 1], m[None, :, r:r + 1], m_t, flows[k % len(flows)])
+            nn_in = chn_pack(x_t, 1 - m_t, x_al, v_al, v_map)
+            assert nn_in.shape[1] == 9
+            _, yc = chn_composite(nn_outs[k % len(nn_outs)], x_t, 1 - m_t, 1, 1)
+            k += 1
+            m_t, x_t, per = hole_update(m_t, v_map[:, :, 0], yc[:, :, 0])         # :128-131
+            y_comp = yc[:, :, 0]
+        y[:, t] = y_comp[0]
+    return y, k

@@ -156,3 +156,26 @@ def chnloss_inputs(spec):
     y_hat_comp = (v_target[:, :, None] * y_target[:, :, None] + (1 - v_target[:, :, None]) * y_hat).astype(np.float32)
     y_hat.reshape(-1)[::89] = np.repeat(y_target[:, :, None], f, axis=2).reshape(-1)[::89]   # exact ties: sign 0
     return y_target, v_target, y_hat, y_hat_comp, v_map
+
+
+# a9-a11 in context: CHN.inpaint_ff --------------------------------------------
+INPAINT_CASES = {
+    "ff_n4": dict(seed=91, n=4, h=15, w=21, k=8),
+}
+
+
+def inpaint_inputs(spec):
+    """x (3,n,h,w), m (1,n,h,w), k dense flows (1,1,h,w,2) and k CNN outputs (1,3,h,w) handed out in
+    call order by the stand-ins for the DFPN forward and the RRDBNet."""
+    n, h, w, k = spec["n"], spec["h"], spec["w"], spec["k"]
+    x, m, _ = synth.frames(spec["seed"], 1, n, h, w)
+    flows = [synth.dense_flow(spec["seed"] + 10 + i, 1, 1, h, w, 0.05, True) for i in range(k)]
+    nn_outs = [synth.nn_output(spec["seed"] + 40 + i, 1, h, w) for i in range(k)]
+    return x[0].copy(), m[0].copy(), flows, nn_outs
+
+
+def get_indexes_ff(t, max_t, s, D):
+    """Reference-frame order of the frame-by-frame algorithm (model_chn.py:460-482)."""
+    cand = [r for r in range(max_t) if r != t]
+    cand = [r for _, r in sorted((abs(r - t), r) for r in cand)]
+    return [r for r in cand if abs(r - t) <= D and abs(r - t) % s == 0]

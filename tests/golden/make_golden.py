@@ -43,7 +43,7 @@ def save(name, **arrays):
 # --------------------------------------------------------------------------
 from cases import WARP_CASES, CPN_CASES, CORR_CASES, CM_CASES, CHN_CASES, LOSS_CASES  # noqa: E402
 from cases import (warp_inputs, cpn_inputs, corr_inputs, cm_inputs, chn_inputs, loss_inputs,  # noqa: E402
-                   chnloss_inputs, CHNLOSS_CASES)
+                   chnloss_inputs, CHNLOSS_CASES, inpaint_inputs, INPAINT_CASES)
 
 
 def main():
@@ -198,6 +198,43 @@ def main():
                  g_y_hat=yh.grad.numpy(), g_y_hat_comp=yc.grad.numpy())
     finally:
         mt.LossesUtils.perceptual, mt.LossesUtils.grad = orig_p, orig_g
+
+    # ---- a9-a11 in context: the unmodified CHN.inpaint_ff (model_chn.py:87-133) with the unmodified
+    # DFPN.align on a short clip; the DFPN forward and the RRDBNet hand out preset tensors in call order.
+    for name, spec in INPAINT_CASES.items():
+        x, m, flows, nn_outs = inpaint_inputs(spec)
+
+        class FakeDFPN2(object):
+            align = DFPN.align
+
+            def __init__(self):
+                self.n = 0
+
+            def __call__(self, *a):
+                i = self.n
+                self.n += 1
+                return None, None, None, T(flows[i % len(flows)])
+
+        class FakeCHN3(object):
+            mean = torch.as_tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1, 1)
+            std = torch.as_tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1, 1)
+            forward = CHN.forward
+
+            def __init__(self):
+                self.model_aligner = FakeDFPN2()
+                self.k = 0
+
+            def nn(self, inp):
+                i = self.k
+                self.k += 1
+                return T(nn_outs[i % len(nn_outs)])
+
+            def __call__(self, *a):
+                return self.forward(*a)
+
+        fake = FakeCHN3()
+        y = CHN.inpaint_ff(fake, T(x), T(m), s=1, D=20, e=1)
+        save("inpaint_" + name, y=y.numpy(), steps=np.array([fake.k], np.int32))
 
 
 if __name__ == "__main__":

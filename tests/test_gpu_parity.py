@@ -451,6 +451,52 @@ def test_inference_step_fusions(mtb):
         assert torch.equal(a_, b_)
 
 
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", sorted(cases.INPAINT_CASES))
+def test_inpaint_ff_mirror(mtb, name, fused):
+    """The patched CHN.inpaint_ff (two fused kernels per step, or the four-kernel route for a foreign
+    aligner) against the output of the unmodified reference loop, bit for bit."""
+    from master_thesis_b200 import plug
+    x, m, flows, nn_outs = cases.inpaint_inputs(cases.INPAINT_CASES[name])
+    g = load_golden("inpaint_" + name)
+
+    class _DFPNLike(object):
+        def __init__(self):
+            self.n = 0
+
+        def __call__(self, *a):
+            i = self.n
+            self.n += 1
+            return None, None, None, dev(flows[i % len(flows)])
+
+    if fused:
+        _DFPNLike.align = plug.dfpn_align
+    else:
+        _DFPNLike.align = lambda self, xt, mt_, xr, mr: plug.dfpn_align_tail(xr, mr, mt_, self(xt, mt_, xr, mr)[3])
+
+    class _CHNLike(object):
+        forward = plug.chn_forward
+        inpaint_ff = plug.chn_inpaint_ff
+        get_indexes_ff = staticmethod(cases.get_indexes_ff)
+
+        def __init__(self):
+            self.model_aligner = _DFPNLike()
+            self.k = 0
+
+        def nn(self, inp):
+            i = self.k
+            self.k += 1
+            return dev(nn_outs[i % len(nn_outs)])
+
+        def __call__(self, *a):
+            return self.forward(*a)
+
+    chn = _CHNLike()
+    y = chn.inpaint_ff(dev(x), dev(m), s=1, D=20, e=1)
+    assert chn.k == int(g["steps"][0])
+    assert np.array_equal(host(y), g["y"])
+
+
 # ---------------------------------------------------------------- full-size properties
 def test_full_size_properties(mtb):
     """BASELINE cfg2 sizes (B=8, F=4, 256x256): size-independent properties."""

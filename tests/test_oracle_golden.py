@@ -88,6 +88,16 @@ def test_chn_l1_terms(name):
         assert np.abs(got - ref).max() <= 1e-6 * max(1e-12, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("name", sorted(cases.INPAINT_CASES))
+def test_inpaint_ff(name):
+    """a2 + a9-a11 chained as the unmodified CHN.inpaint_ff chains them (model_chn.py:87-133)."""
+    x, m, flows, nn_outs = cases.inpaint_inputs(cases.INPAINT_CASES[name])
+    g = load_golden("inpaint_" + name)
+    y, steps = oracle.inpaint_ff(x, m, flows, nn_outs)
+    assert steps == int(g["steps"][0])
+    assert np.array_equal(y, g["y"])
+
+
 @pytest.mark.parametrize("name", sorted(cases.CORR_CASES))
 def test_corr4d(name):
     ft, vt, fr, vr = cases.corr_inputs(cases.CORR_CASES[name])
