@@ -703,7 +703,10 @@ extern "C" int mt_warp_l1_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_
                "mt_warp_l1_fwd: B*F*ceil(W/128) = %lld exceeds %d CTAs (split the batch)",
                (long long)colb * B * F, kMaxReduceBlocks);
     // about 16 CTAs per SM in total; each CTA strides over the remaining row blocks
-    int64_t cap = ((int64_t)sm_count() * 16) / ((int64_t)colb * B * F);
+    int64_t per_sm = tuning("MT_WARPL1_CTAS_PER_SM", 16);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * sm_count() > kMaxReduceBlocks) per_sm = kMaxReduceBlocks / sm_count();
+    int64_t cap = ((int64_t)sm_count() * per_sm) / ((int64_t)colb * B * F);
     if (cap < 1) cap = 1;
     if (gy > cap) gy = (int)cap;
     dim3 block(kCols), gridd(colb, gy, B * F);
