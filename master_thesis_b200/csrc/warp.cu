@@ -264,18 +264,20 @@ struct Taps {
 
 // flow of pixel (y0 + k, x) of frame n for k < U; rows past H get a centred dummy
 template <int U>
-__device__ __forceinline__ void dense_taps(const float *__restrict__ flow, int np0, int y0, const Sampler &sp,
-                                           Taps<U> &t) {
+__device__ __forceinline__ void dense_flow_load(const float *__restrict__ flow, int np0, int y0, const Sampler &sp,
+                                                float2 (&g)[U]) {
+#pragma unroll
+    for (int k = 0; k < U; ++k)
+        g[k] = (y0 + k < sp.H) ? __ldcs(reinterpret_cast<const float2 *>(flow) + (np0 + k * sp.W)) : make_float2(0.0f, 0.0f);
+}
+
+template <int U>
+__device__ __forceinline__ void dense_taps_from(const float2 (&g)[U], const Sampler &sp, Taps<U> &t) {
     const float wm2 = sp.wmax - 1.0f, hm2 = sp.hmax - 1.0f;
     t.interior = true;
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-        if (y0 + k < sp.H) {
-            const float2 g = __ldcs(reinterpret_cast<const float2 *>(flow) + (np0 + k * sp.W));
-            t.gx[k] = g.x; t.gy[k] = g.y;
-        } else {
-            t.gx[k] = t.gy[k] = 0.0f;
-        }
+        t.gx[k] = g[k].x; t.gy[k] = g[k].y;
         t.ix[k] = unnormalize(t.gx[k], sp.sfx, sp.ac);
         t.iy[k] = unnormalize(t.gy[k], sp.sfy, sp.ac);
         t.xw[k] = floorf(t.ix[k]);
@@ -284,6 +286,14 @@ __device__ __forceinline__ void dense_taps(const float *__restrict__ flow, int n
         t.n[k] = __fsub_rn(t.iy[k], t.yn[k]); t.s[k] = __fsub_rn(1.0f, t.n[k]);
         t.interior = t.interior && (t.xw[k] >= 0.0f) && (t.xw[k] <= wm2) && (t.yn[k] >= 0.0f) && (t.yn[k] <= hm2);
     }
+}
+
+template <int U>
+__device__ __forceinline__ void dense_taps(const float *__restrict__ flow, int np0, int y0, const Sampler &sp,
+                                           Taps<U> &t) {
+    float2 g[U];
+    dense_flow_load<U>(flow, np0, y0, sp, g);
+    dense_taps_from<U>(g, sp, t);
 }
 
 // the four taps of C planes for every row slot: fast path when the whole warp is interior
@@ -396,6 +406,11 @@ __global__ void __launch_bounds__(kCols, MT_WARPB_MINB) warp_l1_fwd_kernel(const
     const unsigned n = blockIdx.z;
     const int b = a.f_magic ? (int)__umulhi(n, a.f_magic) : (int)n, f = (int)n - b * a.F;
     const int xo = b * a.x_sb + f * a.x_sf;
+    // the flow of the NEXT row block is requested before the gathers of this one: a CTA walks several
+    // row blocks, and "flow -> taps -> gathers" would otherwise be two dependent round trips per block
+    float2 g_next[U];
+    if ((int)blockIdx.y < a.row_blocks)
+        dense_flow_load<U>(a.flow, (int)n * a.P + (int)blockIdx.y * U * W + x, (int)blockIdx.y * U, a.sp, g_next);
     for (int rb = blockIdx.y; rb < a.row_blocks; rb += gridDim.y) {
         const int y0 = rb * U;
         const int p0 = y0 * W + x, np0 = (int)n * a.P + p0;
@@ -408,7 +423,11 @@ __global__ void __launch_bounds__(kCols, MT_WARPB_MINB) warp_l1_fwd_kernel(const
             for (int c = 0; c < 3; ++c) xt[c][k] = in ? __ldg(a.xt + (b * a.xt_sb + c * a.xt_sc + p0 + k * W)) : 0.0f;
         }
         Taps<U> t;
-        dense_taps<U>(a.flow, np0, y0, a.sp, t);
+        dense_taps_from<U>(g_next, a.sp, t);
+        {
+            const int rn = rb + (int)gridDim.y;
+            if (rn < a.row_blocks) dense_flow_load<U>(a.flow, (int)n * a.P + rn * U * W + x, rn * U, a.sp, g_next);
+        }
         Corners q[3][U];
         gather_taps<3, U>(a.x, xo, a.x_sc, a.sp, t, q);
 #pragma unroll
