@@ -6,19 +6,23 @@
 // The reference's "correlation" here is ONE masked global dot product per
 // (sample, reference) - K = C*h*w = 524 288 terms, M = N = 1 - followed by a
 // per-pixel softmax over the references and a weighted copy.  It is HBM-bound
-// (AI ~ 0.6 flop/B), not a GEMM, so it stays on the SIMT pipes:
-//   pass 0  cm_masks:  v' = bilinear_resize(v, (h,w)) > 0.5 for target + refs
+// (AI ~ 0.6 flop/B), not a GEMM, so it stays on the SIMT pipes.  Three launches:
+//   pass 0  cm_masks:  v' = bilinear_resize(v, (h,w)) > 0.5 for target + refs, as floats and as
+//                      one byte per pixel (bit 0 target, bit r+1 reference r)
 //   pass 1  cm_sim:    partial sums of vt'*vr'*c_t*c_r (and of vt'*vr') per (b, r);
-//                      reads c_feats exactly once from HBM (16 B loads)
-//   pass 1b cm_weights: folds the partials into gs (fixed order, double) and
-//                      computes the masked softmax over references ONCE per
-//                      pixel -> weights (B,R,P), c_mask, c_mask channel of out
-//   pass 2  cm_copy:   streams c_feats again (L2 where it still is: a sample is
-//                      10.5 MB) and writes cat[c_t, sum_r c_r * w_r].
+//                      reads c_feats exactly once from HBM (16 B loads); its feature loads are
+//                      issued before griddepcontrol.wait, i.e. while cm_masks is still running
+//   pass 2  cm_copy2:  streams c_feats again (reverse sample order: the tail of the batch is what
+//                      pass 1 left in L2) and writes cat[c_t, sum_r c_r * w_r, c_mask]; every CTA
+//                      folds the partials of its sample into gs (fixed order, double) and evaluates
+//                      the masked softmax once per MASK PATTERN (2^R entries), weights per pixel are
+//                      a lookup by the mask byte.  (With 8 references, or MT_CM_TABLE=0: the separate
+//                      cm_weights kernel - softmax once per pixel -> weights (B,R,P) - and cm_copy.)
 // Reductions are two-level and fixed-order (deterministic).  History (profiles/):
-// a single-CTA-per-sample reduction kernel cost 14 us (latency chain); recomputing the
-// softmax in every pass-2 CTA cost ~10 channels' worth of instructions per CTA; a
-// per-sample ticket tail in pass 1 doubled pass 1 (fence + atomic + barrier per CTA).
+// a single-CTA-per-sample reduction kernel cost 14 us (latency chain); recomputing the per-PIXEL
+// softmax in every pass-2 CTA cost ~10 channels' worth of instructions per CTA; a per-sample
+// ticket tail in pass 1 doubled pass 1 (fence + atomic + barrier per CTA); per-group launches
+// (MT_CM_CHUNK) and a persistent pipelined single launch (K3p below) are slower than this.
 #include <math.h>
 
 #include "mt_common.cuh"
@@ -478,34 +482,34 @@ __global__ void __launch_bounds__(256) cm_copy_sim_kernel(const CmArgs a) {
 
 
 // ---------------------------------------------------------------------------------------------
-// K3p: pass 1 + 1b + 2 as ONE persistent, software-pipelined launch; pass 2 reads c_feats from L2.
+// K3p (EXPERIMENTAL, MT_CM_FUSED=1, off by default): pass 1 + 1b + 2 as ONE persistent,
+// software-pipelined launch in which pass 2 reads c_feats from L2.  Parity-green, but 1.5-2x slower
+// than the three launches on B200 at every batch size; kept as the record of that design
+// (measurements and the reasons: profiles/r1_experiments.md).
 //
 // The two passes over c_feats are inherent (the similarity is a global reduction over the sample),
 // but as separate launches over the whole batch the second pass misses L2 (ncu: 4.6 % hit rate at
-// B=8, 84 MB) and the op moves 84+10+84+34 MB through HBM for 128 MB algorithmic.  Here one CTA
-// per SM walks a static, ordered item list
-//     S(0) | S(1) C(0) interleaved | S(2) C(1) | ... | C(B-1)
-// (S = similarity partial of a 1024-pixel x CH-channel slab, C = weighted copy of such a slab), so
-// a sample (10.5 MB) is re-read one sample later, while it is L2-resident: HBM traffic =
-// algorithmic traffic.
-//   * Memory pipeline: the operands of item i+NST-1 are fetched with cp.async (16 B per thread and
-//     slot, thread-private slots => conflict-free LDS.128, no barrier for the data) into an NST-deep
-//     shared-memory ring while item i is computed.  A first version without the ring (loads into
-//     registers, 2-3 CTAs/SM) ran 60-77 us against 48 us for the three launches: every item
-//     exposed a DRAM round trip plus, for C items, the chain poll -> fold -> table.
-//   * Masks travel as one byte per pixel (bit 0 target, bit r+1 reference r; cm_masks_kernel):
-//     4 B per thread and item instead of 80 B.
-//   * vr' is 0/1, so the masked softmax over the references has only 2^R distinct results per
-//     sample.  The CTA that finishes the LAST S item of a sample (per-sample counter) folds the
-//     partials in fixed order in double, evaluates the softmax once per mask pattern (the same
-//     operations in the same order as cm_weights_kernel: same bits) and publishes that table; C
-//     items prefetch the table with their operands and look weights up per pixel - no weights array
-//     in HBM, no per-pixel expf / division, and normally no wait: the table was cleared to NaN by
-//     cm_masks_kernel, a prefetched copy without NaN is complete (every word is written once);
-//     otherwise the CTA waits for the sample's flag (acquire) and reloads.
-// Progress: items are taken in order (item i -> CTA i mod grid), S items never wait, a C item
-// waits only for S items that are earlier in the list, and the grid is one resident wave.  A wait
-// that does not end within 2 s traps (the launch fails loudly instead of hanging).
+// B=8, 84 MB) and the op moves 84+10+84+34 MB through HBM for 128 MB algorithmic.  Here one CTA per SM
+// (two groups of 8 compute warps = two workers, a publisher warp, a producer warp) walks a common
+// round schedule (cm_decode): S rounds (similarity partial of a 1024-pixel x CH-channel slab) run
+// `head` rounds ahead of the C rounds (weighted copy of such a slab), so a sample (10.5 MB) is
+// re-read from L2 a few rounds after it was streamed from HBM.
+//   * Memory pipeline: the producer warp fetches the operands of the next NST items with
+//     cp.async.bulk (4 KB per slab and frame) into a shared-memory ring; slot layout = 16 B per
+//     thread, so the compute warps read conflict-free LDS.128; full / empty mbarriers per stage.
+//   * Masks travel as one byte per pixel (bit 0 target, bit r+1 reference r; cm_masks_kernel).
+//   * S items hand their 2R sums to the publisher warp through a shared-memory mailbox; the
+//     publisher stores the partial, fences and bumps the per-sample counter (off the compute warps'
+//     path: with warp 0 publishing, every item cost 3-5 us).  The publisher that finishes the LAST
+//     partial of a sample folds them in fixed order in double, evaluates the masked softmax once per
+//     MASK PATTERN (vr' is 0/1: 2^R distinct weight vectors per sample; the same operations in the
+//     same order as cm_weights_kernel: same bits) and publishes that table + a flag.
+//   * C items read the table one item ahead through a register; cm_masks_kernel cleared it to NaN, so
+//     a copy without NaN is complete (every word is written once); otherwise the group waits for the
+//     sample's flag (acquire) and reloads.  Weights per pixel are a lookup by the mask byte.
+// Progress: every S item of a sample precedes every C item of it in the common round sequence (the
+// host picks `head` accordingly), S items never wait, and the grid is one resident wave.  A wait that
+// does not end within 2 s traps (the launch fails loudly instead of hanging).
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -519,46 +523,6 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// named barrier 1 = the 256 compute threads of cm_pipe_kernel (the publisher warp never joins)
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ bool bar_compute_or(bool p) {
-    int r;
-    asm volatile(
-        "{\n\t.reg .pred pin, pout;\n\tsetp.ne.u32 pin, %1, 0;\n\tbar.red.or.pred pout, 1, 256, pin;\n\t"
-        "selp.u32 %0, 1, 0, pout;\n\t}"
-        : "=r"(r) : "r"((int)p) : "memory");
-    return r != 0;
-}
-// block_sum over the 8 compute warps (result valid in thread 0)
-template <int K>
-__device__ __forceinline__ void compute_sum(float (&v)[K], float *smem) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        v[k] = warp_sum(v[k]);
-        if (lane == 0) smem[k * 32 + wid] = v[k];
-    }
-    bar_compute();
-    if (wid == 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            float t = lane < 8 ? smem[k * 32 + lane] : 0.0f;
-            v[k] = warp_sum(t);
-        }
-    }
-}
-constexpr int kCmThreads = 320;  // 8 compute warps + publisher warp + producer warp
 constexpr int kMailbox = 16;
 
 template <int R>
