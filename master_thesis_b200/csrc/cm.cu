@@ -173,15 +173,28 @@ __device__ __forceinline__ void cm_sim_body(const CmArgs &a, int slab, int b, fl
     // still running - they do not depend on it; the masks below do (pdl_wait)
     if (WAIT) pdl_wait();
     if (p0 < a.P) {
-        const float *mk = a.masks + (int64_t)b * a.f * a.P + p0;
-        const float4 vt = __ldcg(reinterpret_cast<const float4 *>(mk));
         float4 vm[R];
+        if (R <= 7) {
+            // the masks of 4 pixels as 4 bytes (bit 0 target, bit r + 1 reference r) instead of R + 1 float4
+            const uint32_t mw = __ldcg(reinterpret_cast<const uint32_t *>(a.pmask + (int64_t)b * a.P + p0));
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float4 vr = __ldcg(reinterpret_cast<const float4 *>(mk + (int64_t)(r + 1) * a.P));
-            vm[r] = make_float4(vt.x * vr.x, vt.y * vr.y, vt.z * vr.z, vt.w * vr.w);  // :220
-            if (slab == 0) acc[R + r] = (vm[r].x + vm[r].y) + (vm[r].z + vm[r].w);     // :221
+            for (int r = 0; r < R; ++r) {  // vt' * vr'                  :220
+                const uint32_t m = mw & (mw >> (r + 1)) & 0x01010101u;
+                vm[r] = make_float4((float)(m & 1u), (float)((m >> 8) & 1u), (float)((m >> 16) & 1u),
+                                    (float)((m >> 24) & 1u));
+            }
+        } else {
+            const float *mk = a.masks + (int64_t)b * a.f * a.P + p0;
+            const float4 vt = __ldcg(reinterpret_cast<const float4 *>(mk));
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 vr = __ldcg(reinterpret_cast<const float4 *>(mk + (int64_t)(r + 1) * a.P));
+                vm[r] = make_float4(vt.x * vr.x, vt.y * vr.y, vt.z * vr.z, vt.w * vr.w);  // :220
+            }
         }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (slab == 0) acc[R + r] = (vm[r].x + vm[r].y) + (vm[r].z + vm[r].w);     // :221
 #pragma unroll
         for (int k = 0; k < SC; ++k) {
             if (c0 + k < a.C) {
