@@ -426,7 +426,7 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------
 # CPU arms
 # ---------------------------------------------------------------------------
-def cpu_time_workload(wl, seconds, threads=None, min_reps=2, max_reps=50):
+def cpu_time_workload(wl, seconds, threads=None, min_reps=2, max_reps=100000):
     """Times the torch-CPU port of the path (oracle/torch_port.py) on a bounded sample."""
     import torch
     from oracle import torch_port as tp
@@ -629,7 +629,7 @@ def run_gpu(args):
         "roofline": roofline, "kernels": per_call,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = wl.sub(max(1, wl.b // 4)) if wl.b >= 4 else wl
+        sample = wl   # the full workload, repeated for about --cpu-seconds of CPU work
         v, mean, reps, cores = cpu_time_workload(sample, args.cpu_seconds)
         line["cpu_baseline"] = {
             "value": v, "unit": "frames/s", "cores": cores, "kind": "port",
