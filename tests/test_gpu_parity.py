@@ -497,6 +497,85 @@ def test_inpaint_ff_mirror(mtb, name, fused):
     assert np.array_equal(host(y), g["y"])
 
 
+def test_no_out_of_bounds_writes(mtb):
+    """Every output and workspace the ops allocate is carved out of a larger sentinel-filled buffer; after
+    the calls the guard bands before and after each allocation must be untouched (compute-sanitizer is not
+    available on this pool).  Shapes are ragged on purpose: partial tiles, partial 1024-pixel chunks,
+    channel counts that are not multiples of the slabs, widths that are not multiples of 4."""
+    import contextlib
+    from master_thesis_b200 import _lib, ops, plug
+    G = 256  # guard elements on both sides (keeps 16 B alignment for every dtype)
+    made = []
+
+    def guarded_empty(*a, **k):
+        probe = torch.empty(*a, **{**k, "device": "meta"})
+        n = probe.numel()
+        buf = torch.empty(n + 2 * G, dtype=probe.dtype, device=k.get("device", "cuda"))
+        sentinel = 0xA5 if probe.dtype == torch.uint8 else -12345.0
+        buf.fill_(sentinel)
+        made.append((buf, n, sentinel))
+        return _lib.keep(buf[G:G + n].view(probe.shape))
+
+    @contextlib.contextmanager
+    def guards():
+        orig, orig_like = ops._empty, ops._empty_like
+        saved_ws = dict(ops._workspaces)
+        ops._workspaces.clear()
+        ops._empty = guarded_empty
+        ops._empty_like = lambda t, **k: guarded_empty(t.shape, dtype=t.dtype, device=t.device)
+        try:
+            yield
+        finally:
+            ops._empty, ops._empty_like = orig, orig_like
+            ops._workspaces.clear()
+            ops._workspaces.update(saved_ws)
+
+    r = cases.synth.rng(123)
+    with guards():
+        # staged CPN warp with partial tiles (both tile shapes), direct-gather warp with W % 4 != 0
+        x, m, m_t, theta = cases.cpn_inputs(STAGED_CASES["rand"])
+        for tw in (32, 64):
+            try:
+                _set_tuning("MT_WARP_TILE_W", tw)
+                mtb.cpn_align_tail(dev(x), dev(m), dev(m_t), dev(theta))
+            finally:
+                _set_tuning("MT_WARP_TILE_W", DEFAULT_TILE_W)
+        xw, mw, mtw, flow = cases.warp_inputs(cases.WARP_CASES["f1_odd"])
+        mtb.dfpn_align_tail(dev(xw), dev(mw), dev(mtw), dev(flow))
+        # warp + pack, composite + hole update (odd sizes)
+        xt = dev(r.random_sample((xw.shape[0], 3) + xw.shape[-2:]).astype(np.float32))
+        nn_in, vm, _, _ = ops.warp_pack_fwd(dev(xw), dev(mw), dev(flow), dev(mtw), xt, 1 - dev(mtw),
+                                            ops.ALIGN_CORNERS | ops.VIS_FROM_MASK, want_aligned=True)
+        nn_o = dev(cases.synth.nn_output(9, xw.shape[0], xw.shape[-2], xw.shape[-1]))
+        ops.chn_fill(nn_o, xt, 1 - dev(mtw), dev(mtw), vm[:, :, 0])
+        # CHN pack / composite / the three L1 terms forward + backward
+        x_t, v_t, x_al, v_al, v_map, nn_out = cases.chn_inputs(cases.CHN_CASES["f1_odd"])
+        ops.chn_pack(dev(x_t), dev(v_t), dev(x_al), dev(v_al), dev(v_map))
+        no = dev(nn_out).requires_grad_(True)
+        yh, yc = ops.chn_composite(no, dev(x_t), dev(v_t), x_t.shape[0], x_al.shape[2])
+        y_target, v_target, y_hat, y_comp, v_map2 = cases.chnloss_inputs(cases.CHNLOSS_CASES["f1_odd"])
+        yh2, yc2 = dev(y_hat).requires_grad_(True), dev(y_comp).requires_grad_(True)
+        sum(ops.chn_l1_terms(dev(y_target), dev(v_target), yh2, yc2, dev(v_map2))).backward()
+        # CM: three-launch path and the experimental pipelined kernel, ragged shapes
+        for shape in ((5, 4, 9, 24, 48), (3, 2, 5, 32, 32)):
+            b, f, c, h, w = shape
+            cf, vt, va = cases.synth.cm_inputs(61 + b, b, f, c, h, w, 4)
+            for fused in (0, 1):
+                try:
+                    _set_tuning("MT_CM_FUSED", fused)
+                    ops.cm_match(dev(cf), dev(vt), dev(va))
+                finally:
+                    _set_tuning("MT_CM_FUSED", DEFAULT_CM_FUSED)
+        # correlation and the fused DFPN loss
+        ft, vtt, fr, vr = cases.synth.vgg_feats(5, 1, 2)
+        ops.corr4d(dev(ft), dev(vtt), dev(fr), dev(vr))
+        torch.cuda.synchronize()
+    assert len(made) > 30
+    for buf, n, sentinel in made:
+        lo, hi = buf[:G], buf[G + n:]
+        assert bool((lo == sentinel).all()) and bool((hi == sentinel).all()), "guard band overwritten (n=%d)" % n
+
+
 # ---------------------------------------------------------------- full-size properties
 def test_full_size_properties(mtb):
     """BASELINE cfg2 sizes (B=8, F=4, 256x256): size-independent properties."""
