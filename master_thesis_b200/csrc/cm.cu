@@ -496,8 +496,8 @@ __global__ void __launch_bounds__(256) cm_copy_sim_kernel(const CmArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 // K3p (EXPERIMENTAL, MT_CM_FUSED=1, off by default): pass 1 + 1b + 2 as ONE persistent,
-// software-pipelined launch in which pass 2 reads c_feats from L2.  Parity-green, but 1.5-2x slower
-// than the three launches on B200 at every batch size; kept as the record of that design
+// software-pipelined launch in which pass 2 reads c_feats from L2.  Parity-green, but 1.3-1.4x slower
+// than the three launches on B200 (55 vs 40 us at B=8, 175 vs 132 us at B=32); kept as the record of that design
 // (measurements and the reasons: profiles/r1_experiments.md).
 //
 // The two passes over c_feats are inherent (the similarity is a global reduction over the sample),
@@ -694,7 +694,8 @@ __device__ __forceinline__ bool bar_group_or(int id, bool p) {
 // NG groups of 8 compute warps (each group works on its own item: 4 warps per scheduler hide the
 // LDS / FP latencies that 2 could not), one publisher warp, one producer warp.
 template <int R, int CH, int NST, int NG>
-__global__ void __launch_bounds__(NG * 256 + 64, 1) cm_pipe_kernel(const __grid_constant__ CmArgs a) {
+__global__ void __launch_bounds__(NG * 256 + 64, 1) cm_pipe_kernel(const __grid_constant__ CUtensorMap map_c,
+                                                                   const __grid_constant__ CmArgs a) {
     constexpr int TABF = cm_table_floats<R>();
     constexpr int kStageBytes = cm_stage_bytes<R, CH>();
     constexpr int G2 = 2 * R;
@@ -736,15 +737,13 @@ __global__ void __launch_bounds__(NG * 256 + 64, 1) cm_pipe_kernel(const __grid_
                 mbar_wait(smem_u32(empty + s), ph ^ 1u);
                 const int c0 = d.slab * CH;
                 const int px = min(1024, a.P - d.chunk * 1024);
-                const int nch = min(CH, a.C - c0);
                 const uint32_t fb = smem_u32(full + s), dst = smem_u32(smem_raw + s * kStageBytes);
-                mbar_expect_tx(fb, (uint32_t)(nch * (R + 1) * px * 4 + px));
-                for (int k = 0; k < nch; ++k) {
-                    const float *base = a.c_feats + ((int64_t)d.b * a.C + c0 + k) * a.f * a.P + d.chunk * 1024;
-#pragma unroll
-                    for (int fr = 0; fr <= R; ++fr)
-                        bulk_load(dst + (k * (R + 1) + fr) * 4096, base + (int64_t)fr * a.P, (uint32_t)px * 4u, fb);
-                }
+                // ONE tensor load for the CH x (R + 1) slabs of 1024 pixels: c_feats as (256 px, P / 256, B*C*f
+                // rows), box (256, 4, CH * (R + 1)).  As 4 KB bulk copies (one per slab and frame) an item took
+                // ~3 us to arrive: ~0.3 us per copy, issued one after the other.  Rows past the tensor and
+                // pixels past P are zero-filled and count towards the transaction bytes.
+                mbar_expect_tx(fb, (uint32_t)(CH * (R + 1) * 4096 + px));
+                tma_load_3d(dst, &map_c, fb, 0, d.chunk * 4, (d.b * a.C + c0) * a.f);
                 bulk_load(dst + CH * (R + 1) * 4096, a.pmask + (int64_t)d.b * a.P + d.chunk * 1024, (uint32_t)px, fb);
             }
         }
@@ -752,44 +751,65 @@ __global__ void __launch_bounds__(NG * 256 + 64, 1) cm_pipe_kernel(const __grid_
     }
     if (wid == 8 * NG) {
         // ===================== publisher warp =====================
+        // Batched: every ready mailbox entry of both groups is taken by its own lane - partial rows
+        // stored, ONE fence, then the counter atomics side by side.  One entry at a time cost 1.4 us each
+        // (fence + returning atomic), more than the compute warps need to produce one: the mailboxes ran
+        // full and a sample's table appeared 20+ us after its last item.
+        static_assert(NG * kMailbox <= 32, "one lane per mailbox entry");
         int done[NG];
 #pragma unroll
         for (int g = 0; g < NG; ++g) done[g] = 0;
         CM_PROBE(unsigned long long pb_busy = 0, pb_n = 0;)
         for (;;) {
-            bool any = false, fin = true;
+            int rdy[NG], total = 0;
+            bool fin = true;
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
-                if (mb_ready[g] == done[g]) {
-                    fin = fin && mb_fin[g] && mb_ready[g] == done[g];
-                    continue;
-                }
-                any = true;
-                __threadfence_block();
-                CM_PROBE(unsigned long long pb_t = global_ns();)
-                const int slot = done[g] % kMailbox;
-                const int b = mbox_b[g][slot], idx = mbox_idx[g][slot];
-                if (lane < G2) __stcg(a.partials + ((int64_t)b * a.nparts + idx) * G2 + lane, mbox[g][slot][lane]);
-                __threadfence();  // release: the partials before the count
-                __syncwarp();
-                unsigned int old = 0;
-                if (lane == 0) {
-                    mb_done[g] = done[g] + 1;
-                    old = atomicAdd(a.count + b, 1u);
-                }
-                old = __shfl_sync(0xffffffffu, old, 0);
-                if (old == (unsigned int)a.n_items - 1u) {
-                    CM_PROBE(if (lane == 0 && b < 64) g_cm_probe2[1152 + b - 0] = global_ns();)
-                    __threadfence();  // acquire: every other item's partials
-                    cm_publish_table<R>(a, b);
-                }
-                ++done[g];
-                CM_PROBE(pb_busy += global_ns() - pb_t; ++pb_n;)
+                rdy[g] = mb_ready[g];
+                total += rdy[g] - done[g];
+                fin = fin && mb_fin[g] && mb_ready[g] == done[g];
             }
-            if (!any) {
+            if (total == 0) {
                 if (fin) break;
                 __nanosleep(100);
+                continue;
             }
+            __threadfence_block();
+            CM_PROBE(unsigned long long pb_t = global_ns();)
+            // lane e < total: entry e, group by group
+            int eg = -1, eslot = 0, e = lane;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const int cnt = rdy[g] - done[g];
+                if (eg < 0 && e < cnt) { eg = g; eslot = (done[g] + e) % kMailbox; }
+                if (eg < 0) e -= cnt;
+            }
+            int b = 0;
+            if (eg >= 0) {
+                b = mbox_b[eg][eslot];
+                float *o = a.partials + ((int64_t)b * a.nparts + mbox_idx[eg][eslot]) * G2;
+#pragma unroll
+                for (int r = 0; r < G2; ++r) __stcg(o + r, mbox[eg][eslot][r]);
+            }
+            __threadfence();  // release: the partials before the counts
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) mb_done[g] = rdy[g];  // the mailbox slots are free again
+            }
+            bool last = false;
+            if (eg >= 0) last = atomicAdd(a.count + b, 1u) == (unsigned int)a.n_items - 1u;
+            unsigned int lm = __ballot_sync(0xffffffffu, last);
+            while (lm) {
+                const int src = __ffs(lm) - 1;
+                lm &= lm - 1;
+                const int bl = __shfl_sync(0xffffffffu, b, src);
+                __threadfence();  // acquire: every other item's partials
+                cm_publish_table<R>(a, bl);
+            }
+#pragma unroll
+            for (int g = 0; g < NG; ++g) done[g] = rdy[g];
+            CM_PROBE(pb_busy += global_ns() - pb_t; pb_n += total;)
         }
         CM_PROBE(if (lane == 0 && blockIdx.x < 256) { g_cm_probe[blockIdx.x * 8 + 6] = pb_busy; g_cm_probe[blockIdx.x * 8 + 7] = pb_n; })
         return;
@@ -1018,8 +1038,21 @@ int launch_cm_pipe_n(CmArgs a, cudaStream_t st) {
     if (a.head > a.rounds) a.head = a.rounds;
     a.dv_items = make_fastdiv((uint32_t)a.n_items);
     a.dv_chunks = make_fastdiv((uint32_t)a.chunks);
+    EncodeTiledFn enc = encode_fn();
+    if (!enc || (a.P & 255) != 0 || (int64_t)a.B * a.C * a.f > (1ll << 31) - 1) return -1;
+    CUtensorMap map_c;
+    {
+        cuuint64_t dims[3] = {256, (cuuint64_t)(a.P / 256), (cuuint64_t)a.B * a.C * a.f};
+        cuuint64_t strides[2] = {1024, (cuuint64_t)a.P * 4};
+        cuuint32_t box[3] = {256, 4, (cuuint32_t)(CH * (R + 1))};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (enc(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(a.c_feats), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -1;
+    }
     launch(cm_masks_kernel, dim3((a.P + 255) / 256, a.B), 256, 0, st, a);
-    launch(kern, dim3((unsigned)grid), kCmGroups * 256 + 64, (size_t)smem, st, a);
+    launch(kern, dim3((unsigned)grid), kCmGroups * 256 + 64, (size_t)smem, st, map_c, a);
     return launch_status("mt_cm_match_fwd");
 }
 
@@ -1040,7 +1073,7 @@ template <int R>
 int launch_cm(CmArgs a, cudaStream_t st) {
     // one persistent launch (pass 2 from L2); MT_CM_FUSED=0 keeps the three-launch path
     // MT_CM_FUSED=1 (experimental, off): the persistent pipelined kernel K3p.  Parity-green, but on B200
-    // it is 1.5-2x slower than the three launches at every batch size (profiles/r1_experiments.md).
+    // it is 1.3-1.4x slower than the three launches (profiles/r1_experiments.md).
     if (R <= 7 && tuning("MT_CM_FUSED", 0)) {  // the mask byte holds the target and up to 7 references
         const int rc = launch_cm_pipe<R, 2>(a, st);
         if (rc >= 0) return rc;
