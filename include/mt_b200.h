@@ -90,7 +90,8 @@ MT_API int mt_warp_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
 /* mt_warp_fwd that also writes the CNN input of CHN.forward (model_chn.py:68-80):
  * nn_in (B*F, 9, H, W) = [(x_t - mean)/std, (x_aligned - mean)/std, v_t, v_aligned, v_map], exactly
  * what mt_chn_pack produces from this call's outputs.  x_t (B,3,H,W) strided, v_t (B,1,H,W);
- * x_aligned / v_aligned / v_map may be NULL (the inference loop only needs v_map).  C = 3. */
+ * x_aligned / v_aligned / v_map may each be NULL (the inference loop only needs v_map; m_target is
+ * always required because channel 8 of nn_in is the v_map).  C = 3. */
 MT_API int mt_warp_pack_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
                      const float *vis, int64_t vis_sb, int64_t vis_sf,
                      const float *grid, const float *m_target, int64_t mt_sb,
@@ -99,6 +100,28 @@ MT_API int mt_warp_pack_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t 
                      float *x_aligned, int64_t xa_sb, int64_t xa_sc, int64_t xa_sf,
                      float *v_aligned, float *v_map,
                      int B, int F, int H, int W, int flags, mt_stream_t stream);
+
+/* mt_warp_fwd / mt_warp_pack_fwd for a dense flow predicted at another resolution: the DFPN
+ * predicts its last flow at 256 x 256 and resizes it to the frame size with
+ * FlowsUtils.resize_flow(flow_256, (H, W), mode='bilinear') (model_dfpn.py:100-101, utils.py:107-126) before
+ * DFPN.align warps with it (model_dfpn.py:128-133).  Here flow is (B,F,gh,gw,2) and the bilinear resize
+ * (F.interpolate, align_corners=False, ATen's CPU operation order) happens in the warp kernel: the H x W flow
+ * is never written or read.  Results are bit-identical to resizing first.  Nearest visibility (DFPN) only:
+ * flags = MT_ALIGN_CORNERS [| MT_VIS_FROM_MASK].  gh == H and gw == W degenerates to mt_warp_fwd. */
+MT_API int mt_warp_lowres_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
+                       const float *vis, int64_t vis_sb, int64_t vis_sf,
+                       const float *flow, int gh, int gw, const float *m_target, int64_t mt_sb,
+                       float *x_aligned, int64_t xa_sb, int64_t xa_sc, int64_t xa_sf,
+                       float *v_aligned, float *v_map,
+                       int B, int F, int H, int W, int flags, mt_stream_t stream);
+MT_API int mt_warp_pack_lowres_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
+                            const float *vis, int64_t vis_sb, int64_t vis_sf,
+                            const float *flow, int gh, int gw, const float *m_target, int64_t mt_sb,
+                            const float *x_t, int64_t xt_sb, int64_t xt_sc, const float *v_t, int64_t vt_sb,
+                            float *nn_in,
+                            float *x_aligned, int64_t xa_sb, int64_t xa_sc, int64_t xa_sf,
+                            float *v_aligned, float *v_map,
+                            int B, int F, int H, int W, int flags, mt_stream_t stream);
 
 /* ---- K1b  backward of the bilinear warp w.r.t. the dense grid ------------
  * replaces autograd of F.grid_sample in align_set (utils.py:93-97)       (a6)
@@ -144,13 +167,17 @@ MT_API int mt_mask_out(const float *flow, int64_t n, float *out, mt_stream_t str
  * {1,C}.  batch_mask: B device bytes or NULL (selection without the
  * reference's host sync, utils.py:158-165).  out3[0] = weight * l1 / den with
  * den = sum(mask)+1e-9 ('sum') or numel ('mean'); out3[1] = sum|.|;
- * out3[2] = den.  0 if nothing is selected. */
+ * out3[2] = den.  0 if nothing is selected.
+ * A mask smaller than y_hat is passed with stride 0 on the broadcast axes (m_sb, m_sf; a
+ * channel broadcast is mask_c = 1 and needs nothing else); mask_repeat = how many times every
+ * element of the mask AS GIVEN is visited that way (1 for a full-size mask): the reference's
+ * denominator is torch.sum(mask) of the un-broadcast mask (utils.py:167-169). */
 MT_API int mt_masked_l1_fwd(const float *y_hat, int64_t a_sb, int64_t a_sc, int64_t a_sf,
                      const float *y, int64_t b_sb, int64_t b_sc, int64_t b_sf,
                      const float *mask, int64_t m_sb, int64_t m_sc, int64_t m_sf,
                      const uint8_t *batch_mask, float *out3, void *workspace,
-                     int B, int C, int F, int64_t P, int mask_c, int reduction, float weight,
-                     mt_stream_t stream);
+                     int B, int C, int F, int64_t P, int mask_c, int64_t mask_repeat, int reduction,
+                     float weight, mt_stream_t stream);
 /* grads (contiguous (B,C,F,P)); either may be NULL. grad_y = -grad_y_hat. */
 MT_API int mt_masked_l1_bwd(const float *y_hat, int64_t a_sb, int64_t a_sc, int64_t a_sf,
                      const float *y, int64_t b_sb, int64_t b_sc, int64_t b_sf,

@@ -124,6 +124,12 @@ class Plan(object):
     def names(self):
         return [e[0] for e in self.entries]
 
+    def args(self, i):
+        """Arguments of entry ``i`` by the parameter names of the header (pointers as integers or None)."""
+        name, _, cargs = self.entries[i]
+        return {pname: (a.value if isinstance(a, ctypes._SimpleCData) else a)
+                for (_, pname), a in zip(_protos[name][1], cargs)}
+
     def run_entry(self, i):
         name, fn, cargs = self.entries[i]
         rc = fn(*cargs)

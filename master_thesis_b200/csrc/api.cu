@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "mt_common.cuh"
 
 namespace mt {
@@ -48,9 +50,11 @@ namespace {
 struct TuningEntry { char name[32]; int value; };
 TuningEntry g_tuning[32];
 int g_tuning_used = 0;
+std::mutex g_tuning_mu;  // launches may come from several host threads (one per GPU): the table is shared
 }  // namespace
 
 int tuning(const char *name, int dflt) {
+    std::lock_guard<std::mutex> lock(g_tuning_mu);
     for (int i = 0; i < g_tuning_used; ++i)
         if (strcmp(g_tuning[i].name, name) == 0) return g_tuning[i].value;
     const char *e = getenv(name);
@@ -63,6 +67,7 @@ int tuning(const char *name, int dflt) {
 }
 
 int set_tuning(const char *name, int value) {
+    std::lock_guard<std::mutex> lock(g_tuning_mu);
     for (int i = 0; i < g_tuning_used; ++i)
         if (strcmp(g_tuning[i].name, name) == 0) { g_tuning[i].value = value; return MT_OK; }
     if (g_tuning_used >= 32 || strlen(name) >= sizeof(g_tuning[0].name)) return MT_ERR_INVALID;

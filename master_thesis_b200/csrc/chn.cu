@@ -269,6 +269,7 @@ struct L1Args {
     const float *out3_in; const float *grad_out; float *ga, *gb;
     int B, C, F; int64_t P; int mask_c, reduction; float weight;
     int chunks; int64_t total_chunks;  // over (B, F, chunk)
+    double mask_repeat;                // times every mask element is visited through stride-0 broadcasting
 };
 
 template <int VEC>
@@ -311,13 +312,16 @@ __global__ void __launch_bounds__(256) masked_l1_fwd_kernel(const L1Args a) {
     const float weight = a.weight;
     const int reduction = a.reduction;
     const double per_item = (double)a.C * (double)a.F * (double)a.P;
-    grid_reduce_finish<3>(acc, a.ws, red, [out3, weight, reduction, per_item](const double *tot) {
+    const double mask_repeat = a.mask_repeat;
+    grid_reduce_finish<3>(acc, a.ws, red, [out3, weight, reduction, per_item, mask_repeat](const double *tot) {
         const float num = (float)tot[0];
         if (tot[2] == 0.0) {  // nothing selected: zeros(1)   utils.py:158-159
             out3[0] = 0.0f; out3[1] = 0.0f; out3[2] = 1.0f;
             return;
         }
-        const float den = reduction == MT_REDUCE_SUM ? (float)tot[1] + 1e-9f : (float)(tot[2] * per_item);
+        // utils.py:167-169 divides by torch.sum(mask) of the mask AS GIVEN: a mask that reaches the kernel
+        // through stride-0 broadcasting (over b, f or the plane) was summed mask_repeat times
+        const float den = reduction == MT_REDUCE_SUM ? (float)(tot[1] / mask_repeat) + 1e-9f : (float)(tot[2] * per_item);
         out3[0] = weight * (reduction == MT_REDUCE_SUM ? num / den : (float)(tot[0] / (tot[2] * per_item)));
         out3[1] = num;
         out3[2] = den;
@@ -598,14 +602,15 @@ extern "C" int mt_masked_l1_fwd(const float *y_hat, int64_t a_sb, int64_t a_sc, 
                                 const float *y, int64_t b_sb, int64_t b_sc, int64_t b_sf,
                                 const float *mask, int64_t m_sb, int64_t m_sc, int64_t m_sf,
                                 const uint8_t *batch_mask, float *out3, void *workspace, int B,
-                                int C, int F, int64_t P, int mask_c, int reduction, float weight,
-                                mt_stream_t stream) {
+                                int C, int F, int64_t P, int mask_c, int64_t mask_repeat, int reduction,
+                                float weight, mt_stream_t stream) {
     L1Args a;
     int rc = fill_l1(a, y_hat, a_sb, a_sc, a_sf, y, b_sb, b_sc, b_sf, mask, m_sb, m_sc, m_sf,
                      batch_mask, B, C, F, P, mask_c, reduction, weight, "mt_masked_l1_fwd");
     if (rc) return rc;
     MT_REQUIRE(out3 && workspace, "mt_masked_l1_fwd: NULL out3 / workspace");
-    a.out3 = out3; a.ws = workspace;
+    MT_REQUIRE(mask_repeat >= 1, "mt_masked_l1_fwd: mask_repeat must be >= 1");
+    a.out3 = out3; a.ws = workspace; a.mask_repeat = (double)mask_repeat;
     const bool v4 = l1_vec4(a);
     const int vec = v4 ? 4 : 1;
     a.chunks = (int)((P + 256 * vec - 1) / (256 * vec));

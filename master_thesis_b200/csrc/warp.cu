@@ -56,6 +56,10 @@ struct WarpFwdArgs {
     const float *x_t, *v_t;
     float *nn_in;
     int xt_sb, xt_sc, vt_sb;
+    // LOWRES: `grid` is a flow of gh x gw points per frame, resized to H x W on the fly
+    // (FlowsUtils.resize_flow(mode='bilinear'), utils.py:107-126 as called at model_dfpn.py:100-101)
+    int gh, gw;
+    float gsy, gsx;  // gh / H, gw / W in fp32
 };
 constexpr int kMaxRowsPerCta = 32;
 
@@ -73,10 +77,14 @@ constexpr int kMaxRowsPerCta = 32;
 // PACK (C == 3): additionally writes nn_in (B*F, 9, H, W) = [(x_t - mean) / std, (x_aligned - mean) / std,
 // v_t, v_aligned, v_map] - the chn_pack kernel's output - so that the inference loop of CHN.inpaint_*
 // needs no second pass over the aligned frame.
-template <int C, int U, int VIS, bool AFFINE, bool FULL, bool PACK = false>
+// LOWRES (dense flow only): the flow is given at gh x gw and bilinearly resized to H x W in the kernel - the
+// resized flow is never written or read back; bit-identical to resizing first.
+template <int C, int U, int VIS, bool AFFINE, bool FULL, bool PACK = false, bool LOWRES = false>
 __global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const WarpFwdArgs a) {
+    static_assert(!(AFFINE && LOWRES), "a theta needs no resize");
     pdl_sync();
     __shared__ float s_by[kMaxRowsPerCta];
+    __shared__ Lin s_ly[LOWRES ? kMaxRowsPerCta : 1];
     const int W = a.sp.W, H = a.sp.H;
     // lanes past the last column stay alive (the warp vote below needs every lane)
     // on a clamped column and are masked at the stores
@@ -90,6 +98,12 @@ __global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const War
     if (AFFINE) {  // row term of the affine grid: rows_cta values per CTA
         if ((int)threadIdx.x < rows_cta)
             s_by[threadIdx.x] = base_coord(min(yb + (int)threadIdx.x, H - 1), H, a.sp.stepy, ac);
+        __syncthreads();
+    }
+    Lin lx;
+    if (LOWRES) {  // row terms of the flow resize once per CTA, the column term once per thread
+        if ((int)threadIdx.x < rows_cta) s_ly[threadIdx.x] = lin_index(min(yb + (int)threadIdx.x, H - 1), a.gh, H, a.gsy);
+        lx = lin_index(x, a.gw, W, a.gsx);
         __syncthreads();
     }
     const int xo = b * a.x_sb + f * a.x_sf;
@@ -116,7 +130,7 @@ __global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const War
         const int np0 = (int)n * a.P + p0;
         // issue the target-mask loads first: they are only needed by the stores at the end
         float mtv[U];
-        if (FULL || a.v_map) {
+        if (FULL || PACK || a.v_map) {  // PACK needs v_map for channel 8 of nn_in also when v_map itself is not requested
 #pragma unroll
             for (int k = 0; k < U; ++k) mtv[k] = (y0 + k < H) ? __ldcs(a.m_target + (mto + p0 + k * W)) : 0.0f;
         }
@@ -140,6 +154,11 @@ __global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const War
                 const float by = s_by[it * U + k];
                 gx = __fadd_rn(__fmaf_rn(by, t1, bxt0), t2);  // fma(by, t1, bx*t0) + t2 (pinned order)
                 gy = __fadd_rn(__fmaf_rn(by, t4, bxt3), t5);
+            } else if (LOWRES) {
+                const Lin ly = s_ly[it * U + k];
+                const float2 *fl = reinterpret_cast<const float2 *>(a.grid) + (int)n * (a.gh * a.gw);
+                const float2 g = lin_flow(fl + ly.i0 * a.gw, fl + ly.i1 * a.gw, lx, ly.l0, ly.l1);
+                gx = g.x; gy = g.y;
             } else if (y0 + k < H) {
                 const float2 g = __ldcs(reinterpret_cast<const float2 *>(a.grid) + (np0 + k * W));
                 gx = g.x; gy = g.y;
@@ -538,8 +557,13 @@ static int warp_fwd_impl(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_s
                          const float *vis, int64_t vis_sb, int64_t vis_sf, const float *grid,
                          const float *m_target, int64_t mt_sb, float *x_aligned, int64_t xa_sb,
                          int64_t xa_sc, int64_t xa_sf, float *v_aligned, float *v_map, int B,
-                         int C, int F, int H, int W, int flags, mt_stream_t stream, const PackOut *pack) {
+                         int C, int F, int H, int W, int flags, mt_stream_t stream, const PackOut *pack,
+                         int gh = 0, int gw = 0) {
     MT_REQUIRE(x && vis && grid, "mt_warp_fwd: NULL input");
+    const bool lowres = gh > 0 && gw > 0 && !(gh == H && gw == W);
+    MT_REQUIRE(!lowres || (!(flags & MT_GRID_AFFINE) && !(flags & MT_VIS_BILINEAR) && C == 3 &&
+                           (int64_t)B * F * gh * gw * 2 < (1ll << 31) - 1),
+               "mt_warp_lowres_fwd: needs a dense flow, nearest visibility, C = 3 and B*F*gh*gw*2 < 2^31");
     MT_REQUIRE(B > 0 && F > 0 && H > 0 && W > 0, "mt_warp_fwd: empty shape B=%d F=%d H=%d W=%d", B, F, H, W);
     MT_REQUIRE(C == 1 || C == 3, "mt_warp_fwd: C must be 1 or 3 (reference hard-codes 3, utils.py:97), got %d", C);
     MT_REQUIRE((int64_t)B * F <= 65535, "mt_warp_fwd: B*F > 65535");
@@ -566,6 +590,8 @@ static int warp_fwd_impl(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_s
     a.sp = make_sampler(H, W, (flags & MT_ALIGN_CORNERS) != 0);
     a.from_mask = (flags & MT_VIS_FROM_MASK) != 0;
     a.x_t = a.v_t = nullptr; a.nn_in = nullptr; a.xt_sb = a.xt_sc = a.vt_sb = 0;
+    a.gh = lowres ? gh : H; a.gw = lowres ? gw : W;
+    a.gsy = (float)a.gh / (float)H; a.gsx = (float)a.gw / (float)W;
     if (pack) {
         MT_REQUIRE(C == 3 && m_target && pack->x_t && pack->v_t && pack->nn_in, "mt_warp_pack_fwd: C must be 3, no NULL input");
         MT_REQUIRE(pack->xt_sb >= 0 && pack->xt_sc >= 0 && pack->vt_sb >= 0 &&
@@ -584,6 +610,21 @@ static int warp_fwd_impl(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_s
     dim3 block(kCols), gridd((W + kCols - 1) / kCols, (H + rows * iters - 1) / (rows * iters), B * F);
     cudaStream_t st = (cudaStream_t)stream;
     const bool full = x_aligned && v_aligned && v_map;
+    if (pack && lowres) {  // DFPN inference step at a frame size other than the flow's 256 x 256
+        if (rows == 2) launch(warp_fwd_kernel<3, 2, 1, false, false, true, true>, gridd, block, 0, st, a);
+        else launch(warp_fwd_kernel<3, 4, 1, false, false, true, true>, gridd, block, 0, st, a);
+        return launch_status("mt_warp_pack_lowres_fwd");
+    }
+    if (lowres) {
+        if (rows == 2) {
+            if (full) launch(warp_fwd_kernel<3, 2, 1, false, true, false, true>, gridd, block, 0, st, a);
+            else launch(warp_fwd_kernel<3, 2, 1, false, false, false, true>, gridd, block, 0, st, a);
+        } else {
+            if (full) launch(warp_fwd_kernel<3, 4, 1, false, true, false, true>, gridd, block, 0, st, a);
+            else launch(warp_fwd_kernel<3, 4, 1, false, false, false, true>, gridd, block, 0, st, a);
+        }
+        return launch_status("mt_warp_lowres_fwd");
+    }
     if (pack) {
 #define MT_WARP_PACK_GO(VV, AA)                                                                       \
     do {                                                                                              \
@@ -642,6 +683,29 @@ extern "C" int mt_warp_pack_fwd(const float *x, int64_t x_sb, int64_t x_sc, int6
     PackOut pk{x_t, xt_sb, xt_sc, v_t, vt_sb, nn_in};
     return warp_fwd_impl(x, x_sb, x_sc, x_sf, vis, vis_sb, vis_sf, grid, m_target, mt_sb, x_aligned, xa_sb, xa_sc,
                          xa_sf, v_aligned, v_map, B, 3, F, H, W, flags, stream, &pk);
+}
+
+extern "C" int mt_warp_lowres_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
+                                  const float *vis, int64_t vis_sb, int64_t vis_sf, const float *flow, int gh,
+                                  int gw, const float *m_target, int64_t mt_sb, float *x_aligned, int64_t xa_sb,
+                                  int64_t xa_sc, int64_t xa_sf, float *v_aligned, float *v_map, int B, int F,
+                                  int H, int W, int flags, mt_stream_t stream) {
+    MT_REQUIRE(gh > 0 && gw > 0, "mt_warp_lowres_fwd: empty flow");
+    return warp_fwd_impl(x, x_sb, x_sc, x_sf, vis, vis_sb, vis_sf, flow, m_target, mt_sb, x_aligned, xa_sb, xa_sc,
+                         xa_sf, v_aligned, v_map, B, 3, F, H, W, flags, stream, nullptr, gh, gw);
+}
+
+extern "C" int mt_warp_pack_lowres_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
+                                       const float *vis, int64_t vis_sb, int64_t vis_sf, const float *flow,
+                                       int gh, int gw, const float *m_target, int64_t mt_sb, const float *x_t,
+                                       int64_t xt_sb, int64_t xt_sc, const float *v_t, int64_t vt_sb,
+                                       float *nn_in, float *x_aligned, int64_t xa_sb, int64_t xa_sc,
+                                       int64_t xa_sf, float *v_aligned, float *v_map, int B, int F, int H,
+                                       int W, int flags, mt_stream_t stream) {
+    MT_REQUIRE(gh > 0 && gw > 0, "mt_warp_pack_lowres_fwd: empty flow");
+    PackOut pk{x_t, xt_sb, xt_sc, v_t, vt_sb, nn_in};
+    return warp_fwd_impl(x, x_sb, x_sc, x_sf, vis, vis_sb, vis_sf, flow, m_target, mt_sb, x_aligned, xa_sb, xa_sc,
+                         xa_sf, v_aligned, v_map, B, 3, F, H, W, flags, stream, &pk, gh, gw);
 }
 
 extern "C" int mt_warp_bwd_grid(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,

@@ -96,6 +96,39 @@ __device__ __forceinline__ float base_coord(int idx, int size, float step, bool 
     return v;
 }
 
+// F.interpolate(mode='bilinear', align_corners=False) source index + weights of one output coordinate
+// (ATen UpSample.h:442-476 compute_source_index_and_lambda), in the CPU build's operation order:
+// src = fma(scale, dst + 0.5, -0.5) clamped at 0, scale = in / out in fp32 (host-computed, same IEEE
+// division); in == out is the identity.  Used by the flow resize fused into the DFPN warp
+// (FlowsUtils.resize_flow, utils.py:107-126, called at model_dfpn.py:100-101).
+struct Lin {
+    int i0, i1;
+    float l0, l1;
+};
+__device__ __forceinline__ Lin lin_index(int dst, int in, int out, float scale) {
+    Lin r;
+    if (in == out) {
+        r.i0 = r.i1 = dst; r.l0 = 1.0f; r.l1 = 0.0f;
+        return r;
+    }
+    float s = __fmaf_rn(scale, __fadd_rn((float)dst, 0.5f), -0.5f);
+    s = s < 0.0f ? 0.0f : s;
+    r.i0 = min((int)floorf(s), in - 1);
+    r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+    r.l1 = fminf(fmaxf(__fsub_rn(s, (float)r.i0), 0.0f), 1.0f);
+    r.l0 = __fsub_rn(1.0f, r.l1);
+    return r;
+}
+// the resized flow at one output pixel: rows r0 / r1 of the low-resolution flow (float2 = (gx, gy)),
+// row(y) = fma(v[x0], lx0, v[x1] * lx1); out = fma(row(y0), ly0, row(y1) * ly1)   (the CPU build's order: DESIGN.md "bit-exactness")
+__device__ __forceinline__ float2 lin_flow(const float2 *__restrict__ r0, const float2 *__restrict__ r1, const Lin &lx,
+                                           float ly0, float ly1) {
+    const float2 a = __ldg(r0 + lx.i0), b = __ldg(r0 + lx.i1), c = __ldg(r1 + lx.i0), d = __ldg(r1 + lx.i1);
+    const float tx = __fmaf_rn(a.x, lx.l0, __fmul_rn(b.x, lx.l1)), ty = __fmaf_rn(a.y, lx.l0, __fmul_rn(b.y, lx.l1));
+    const float bx = __fmaf_rn(c.x, lx.l0, __fmul_rn(d.x, lx.l1)), by = __fmaf_rn(c.y, lx.l0, __fmul_rn(d.y, lx.l1));
+    return make_float2(__fmaf_rn(tx, ly0, __fmul_rn(bx, ly1)), __fmaf_rn(ty, ly0, __fmul_rn(by, ly1)));
+}
+
 static inline Sampler make_sampler(int H, int W, bool ac) {
     Sampler s;
     s.sfx = ac ? (float)(W - 1) / 2.0f : (float)W / 2.0f;

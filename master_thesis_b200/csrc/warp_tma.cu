@@ -438,6 +438,10 @@ int warp_staged_launch(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
     // TMA: 16 B aligned base, every stride a multiple of 16 B
     if ((W & 3) || (x_sb & 3) || (x_sc & 3) || (x_sf & 3) || (vis_sb & 3) || (vis_sf & 3)) return 0;
     if (!aligned16(x) || !aligned16(vis) || !aligned16(m_target) || (mt_sb & 3)) return 0;
+    // a stride of 0 with an extent > 1 (expanded views such as m_target.expand(B, ...)) cannot be encoded in a
+    // tensor map (the encoders below substitute 16 B, which is only harmless for extent 1): direct-gather kernel
+    if ((B > 1 && (x_sb == 0 || vis_sb == 0 || mt_sb == 0)) || (F > 1 && (x_sf == 0 || vis_sf == 0)) || x_sc == 0)
+        return 0;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return 0;
     StagedHost h;

@@ -30,9 +30,9 @@ def _empty_like(*a, **k):
 
 
 def _contig(t):
-    """contiguous() whose copy (if one is made) is owned by the active recording."""
-    c = t.contiguous()
-    return c if c is t else _lib.keep(c)
+    """contiguous(); the tensor handed to the kernel is owned by the active recording either way (a
+    recorded plan replays raw pointers: an autograd-made gradient must not be freed under it)."""
+    return _lib.keep(t.contiguous())
 
 
 def _stream(t):
@@ -43,7 +43,21 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+_device = [None]     # device index of the operator call in progress (set by _need_cuda)
+
+
+def _call(name, *args):
+    """_lib.call on the device of the call's tensors: the launch, the SM count the launcher reads and the
+    stream handle all belong to that device even when it is not the process's current one."""
+    dev = _device[0]
+    if dev is not None and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return _lib.call(name, *args)
+    return _lib.call(name, *args)
+
+
 def _need_cuda(*ts):
+    first = None
     for t in ts:
         if t is None:
             continue
@@ -52,6 +66,22 @@ def _need_cuda(*ts):
                                "fallback); got %s" % (t.device if isinstance(t, torch.Tensor) else type(t)))
         if t.dtype != torch.float32:
             raise RuntimeError("master_thesis_b200: fp32 tensors required, got %s" % t.dtype)
+        if first is None:
+            first = t.device
+        elif t.device != first:
+            raise RuntimeError("master_thesis_b200: tensors on different devices (%s, %s)" % (first, t.device))
+    if first is not None:
+        _device[0] = first.index
+
+
+def _no_grad_inputs(who, *ts):
+    """The kernels behind ``who`` have no backward: fail loudly instead of cutting the autograd graph
+    (the reference's frozen-aligner and no_grad flows never get here with a differentiable input)."""
+    if torch.is_grad_enabled():
+        for t in ts:
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                raise RuntimeError("master_thesis_b200.%s: an input requires grad but this operator provides no "
+                                   "backward pass (run it under torch.no_grad(), or detach the input)" % who)
 
 
 def reduce_workspace(t):
@@ -100,21 +130,36 @@ def _frame_major(b, c, f, h, w, like):
 # --------------------------------------------------------------------------
 # K1 warp
 # --------------------------------------------------------------------------
-def warp_fwd(x, vis, grid, m_target=None, flags=ALIGN_CORNERS, want_x=True, want_v=True):
-    """x (B,C,F,H,W), vis (B,1,F,H,W), grid dense (B,F,H,W,2) or theta (B*F,2,3).
-
-    Returns (x_aligned (B,C,F,H,W) view, v_aligned (B,1,F,H,W), v_map (B,1,F,H,W) | None).
-    """
-    _need_cuda(x, vis, grid, m_target)
-    b, c, f, h, w = x.shape
-    x, x_sb, x_sc, x_sf = _s5(x)
-    vis, v_sb, _, v_sf = _s5(vis)
+def _grid_kind(grid, flags, b, f, h, w):
+    """Validates ``grid`` and returns (contiguous grid, gh, gw): a theta (B*F,2,3) [gh = gw = 0], a dense flow
+    (B,F,H,W,2) [gh, gw = H, W] or a dense flow at another resolution (B,F,gh,gw,2), which the DFPN kernels
+    resize bilinearly on the fly."""
     grid = _contig(grid)
     if flags & GRID_AFFINE:
         if grid.numel() != b * f * 6:
             raise RuntimeError("theta must have shape (B*F,2,3)")
-    elif tuple(grid.shape) != (b, f, h, w, 2):
+        return grid, 0, 0
+    if grid.dim() != 5 or grid.shape[0] != b or grid.shape[1] != f or grid.shape[4] != 2:
         raise RuntimeError("flow must have shape (B,F,H,W,2), got %s" % (tuple(grid.shape),))
+    gh, gw = int(grid.shape[2]), int(grid.shape[3])
+    if (gh, gw) != (h, w) and (flags & VIS_BILINEAR):
+        raise RuntimeError("a flow at another resolution (%dx%d for %dx%d frames) needs the nearest-visibility "
+                           "(DFPN) flavour" % (gh, gw, h, w))
+    return grid, gh, gw
+
+
+def warp_fwd(x, vis, grid, m_target=None, flags=ALIGN_CORNERS, want_x=True, want_v=True):
+    """x (B,C,F,H,W), vis (B,1,F,H,W), grid dense (B,F,H,W,2) or theta (B*F,2,3); a dense flow
+    (B,F,gh,gw,2) of another resolution is resized to (H,W) inside the kernel (resize_flow, utils.py:107-126).
+
+    Returns (x_aligned (B,C,F,H,W) view, v_aligned (B,1,F,H,W), v_map (B,1,F,H,W) | None).
+    """
+    _need_cuda(x, vis, grid, m_target)
+    _no_grad_inputs("warp_fwd", x, vis, grid, m_target)
+    b, c, f, h, w = x.shape
+    x, x_sb, x_sc, x_sf = _s5(x)
+    vis, v_sb, _, v_sf = _s5(vis)
+    grid, gh, gw = _grid_kind(grid, flags, b, f, h, w)
     mt_sb = 0
     if m_target is not None:
         m_target = _planes(m_target)
@@ -126,37 +171,45 @@ def warp_fwd(x, vis, grid, m_target=None, flags=ALIGN_CORNERS, want_x=True, want
     vm = _empty((b, 1, f, h, w), dtype=torch.float32, device=x.device) \
         if m_target is not None else None
     p = h * w
-    _lib.call("mt_warp_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis), v_sb, v_sf, _ptr(grid),
+    if gh and (gh, gw) != (h, w):
+        if c != 3:
+            raise RuntimeError("warp_fwd: a flow at another resolution needs C = 3")
+        _call("mt_warp_lowres_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis), v_sb, v_sf, _ptr(grid), gh, gw,
+                  _ptr(m_target), mt_sb, _ptr(xa_mem), f * c * p, p, c * p, _ptr(va), _ptr(vm),
+                  b, f, h, w, flags, _stream(x))
+        return xa, va, vm
+    _call("mt_warp_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis), v_sb, v_sf, _ptr(grid),
               _ptr(m_target), mt_sb, _ptr(xa_mem), f * c * p, p, c * p, _ptr(va), _ptr(vm),
               b, c, f, h, w, flags, _stream(x))
     return xa, va, vm
 
 
-def warp_pack_fwd(x, vis, grid, m_target, x_t, v_t, flags=ALIGN_CORNERS, want_aligned=False):
+def warp_pack_fwd(x, vis, grid, m_target, x_t, v_t, flags=ALIGN_CORNERS, want_aligned=False, want_v_map=True):
     """mt_warp_pack_fwd: the warp of mt_warp_fwd that also writes the CNN input of CHN.forward.
 
-    Returns (nn_in (B*F,9,H,W), v_map (B,1,F,H,W), x_aligned | None, v_aligned | None)."""
+    Returns (nn_in (B*F,9,H,W), v_map (B,1,F,H,W) | None, x_aligned | None, v_aligned | None)."""
     _need_cuda(x, vis, grid, m_target, x_t, v_t)
+    _no_grad_inputs("warp_pack_fwd", x, vis, grid, m_target, x_t, v_t)
     b, c, f, h, w = x.shape
     if c != 3:
         raise RuntimeError("warp_pack_fwd: C must be 3")
     x, x_sb, x_sc, x_sf = _s5(x)
     vis, v_sb, _, v_sf = _s5(vis)
-    grid = _contig(grid)
-    if flags & GRID_AFFINE:
-        if grid.numel() != b * f * 6:
-            raise RuntimeError("theta must have shape (B*F,2,3)")
-    elif tuple(grid.shape) != (b, f, h, w, 2):
-        raise RuntimeError("flow must have shape (B,F,H,W,2), got %s" % (tuple(grid.shape),))
+    grid, gh, gw = _grid_kind(grid, flags, b, f, h, w)
     m_target, xt, vt = _planes(m_target), _planes(x_t), _planes(v_t)
     p = h * w
     xa_mem = xa = va = None
     if want_aligned:
         xa_mem, xa = _frame_major(b, c, f, h, w, x)
         va = _empty((b, 1, f, h, w), dtype=torch.float32, device=x.device)
-    vm = _empty((b, 1, f, h, w), dtype=torch.float32, device=x.device)
+    vm = _empty((b, 1, f, h, w), dtype=torch.float32, device=x.device) if want_v_map else None
     nn_in = _empty((b * f, 9, h, w), dtype=torch.float32, device=x.device)
-    _lib.call("mt_warp_pack_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis), v_sb, v_sf, _ptr(grid),
+    if gh and (gh, gw) != (h, w):
+        _call("mt_warp_pack_lowres_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis), v_sb, v_sf, _ptr(grid), gh, gw,
+                  _ptr(m_target), m_target.stride(0), _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0),
+                  _ptr(nn_in), _ptr(xa_mem), f * c * p, p, c * p, _ptr(va), _ptr(vm), b, f, h, w, flags, _stream(x))
+        return nn_in, vm, xa, va
+    _call("mt_warp_pack_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis), v_sb, v_sf, _ptr(grid),
               _ptr(m_target), m_target.stride(0), _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0),
               _ptr(nn_in), _ptr(xa_mem), f * c * p, p, c * p, _ptr(va), _ptr(vm), b, f, h, w, flags, _stream(x))
     return nn_in, vm, xa, va
@@ -169,7 +222,7 @@ def warp_bwd_grid(x, grid, gout, flags=ALIGN_CORNERS):
     gout, g_sb, g_sc, g_sf = _s5(gout)
     grid = _contig(grid)
     gg = _empty_like(grid)
-    _lib.call("mt_warp_bwd_grid", _ptr(x), x_sb, x_sc, x_sf, _ptr(grid), _ptr(gout), g_sb, g_sc,
+    _call("mt_warp_bwd_grid", _ptr(x), x_sb, x_sc, x_sf, _ptr(grid), _ptr(gout), g_sb, g_sc,
               g_sf, _ptr(gg), b, c, f, h, w, flags, _stream(x))
     return gg
 
@@ -205,30 +258,77 @@ def mask_out(flow):
     flow = _contig(flow.detach())
     b, f, h, w, _ = flow.shape
     out = _empty((b, 1, f, h, w), dtype=torch.float32, device=flow.device)
-    _lib.call("mt_mask_out", _ptr(flow), flow.numel() // 2, _ptr(out), _stream(flow))
+    _call("mt_mask_out", _ptr(flow), flow.numel() // 2, _ptr(out), _stream(flow))
     return out
 
 
 # --------------------------------------------------------------------------
 # masked L1
 # --------------------------------------------------------------------------
+def _lead3(t, nlead, plane_dims):
+    """(tensor with one contiguous trailing plane, stride_b, stride_c, stride_f) of a tensor whose first
+    ``nlead`` (<= 3) dims are the (b, c, f) axes; missing axes and axes of extent 1 get stride 0."""
+    t = _planes(t, plane_dims) if plane_dims else t
+    st = [t.stride(d) if d < nlead and t.size(d) != 1 else 0 for d in range(3)]
+    return t, st[0], st[1], st[2]
+
+
+def _ones_plane(like, p):
+    """A cached plane of ones (the all-ones mask of the flow losses, model_dfpn.py:259-267)."""
+    key = ("ones", like.device.index)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < p:
+        buf = torch.ones(max(int(p), 1024), dtype=torch.float32, device=like.device)
+        _workspaces[key] = buf
+    return buf
+
+
 def _l1_layout(y_hat, y, mask):
-    """Common (B,C,F,P) decomposition + strides for the three operands."""
+    """(B, C, F, P) decomposition + strides of the three operands of masked_l1 (utils.py:139-169).
+
+    dim 0 = B, dim 1 = C, dim 2 = F for tensors of >= 5 dims (F = 1 otherwise), P = the remaining dims.
+    ``mask`` may be None (all ones) or anything that broadcasts against ``y_hat``: axes of extent 1 become
+    stride 0 (the channel axis natively: mask_c = 1), and ``repeat`` says how often every element of the
+    mask as given is visited, because the reference divides by torch.sum(mask) of the un-broadcast mask
+    (utils.py:167-169)."""
     if y_hat.shape != y.shape:
         raise RuntimeError("masked_l1: y_hat %s vs y %s" % (tuple(y_hat.shape), tuple(y.shape)))
-    if y_hat.dim() == 5 and mask.dim() == 5 and mask.shape[0] == y_hat.shape[0] \
-            and mask.shape[2:] == y_hat.shape[2:] and mask.shape[1] in (1, y_hat.shape[1]):
-        b, c, f, h, w = y_hat.shape
-        ts = [_s5(t) for t in (y_hat, y, mask)]
-        return ts, b, c, f, h * w, mask.shape[1]
-    if mask.shape != y_hat.shape:
-        mask = mask.expand_as(y_hat)
-    b = y_hat.shape[0]
-    ts = []
-    for t in (y_hat, y, mask):
-        t = _contig(t).view(b, 1, 1, -1)
-        ts.append((t, t.stride(0), 0, 0))
-    return ts, b, 1, 1, ts[0][0].shape[-1], 1
+    while y_hat.dim() < 3:
+        y_hat, y = y_hat.unsqueeze(-1), y.unsqueeze(-1)
+        if mask is not None and mask.dim() == y_hat.dim() - 1:
+            mask = mask.unsqueeze(-1)
+    nd = y_hat.dim()
+    nlead = 3 if nd >= 5 else 2
+    shape = tuple(y_hat.shape)
+    B, C = shape[0], shape[1]
+    F = shape[2] if nlead == 3 else 1
+    P = 1
+    for d in shape[nlead:]:
+        P *= d
+    pd = nd - nlead
+    a = _lead3(y_hat, nlead, pd)
+    b_ = _lead3(y, nlead, pd)
+    if mask is None:     # torch.ones_like(y_hat): one cached plane of ones, visited per channel (mask_c = C)
+        return (a, b_, (_ones_plane(y_hat, P), 0, 0, 0)), B, C, F, P, C, B * F
+    if mask.dim() > nd:
+        raise RuntimeError("masked_l1: mask %s does not broadcast against %s" % (tuple(mask.shape), shape))
+    mask = mask.reshape((1,) * (nd - mask.dim()) + tuple(mask.shape))
+    for d in range(nd):
+        if mask.size(d) not in (1, shape[d]):
+            raise RuntimeError("masked_l1: mask %s does not broadcast against %s" % (tuple(mask.shape), shape))
+    repeat = 1
+    if tuple(mask.shape[nlead:]) != shape[nlead:]:       # broadcast inside the plane: materialise the plane
+        for d in range(nlead, nd):
+            if mask.size(d) != shape[d]:
+                repeat *= shape[d]
+        mask = _contig(mask.expand(tuple(mask.shape[:nlead]) + shape[nlead:]))
+    if mask.size(0) == 1 and B > 1:
+        repeat *= B
+    if nlead == 3 and mask.size(2) == 1 and F > 1:
+        repeat *= F
+    mask_c = C if (mask.size(1) == C and C > 1) else 1
+    m = _lead3(mask, nlead, pd)
+    return (a, b_, m), B, C, F, P, mask_c, repeat
 
 
 def _bm(batch_mask, like):
@@ -242,12 +342,14 @@ def masked_l1_fwd_raw(y_hat, y, mask, batch_mask=None, reduction="mean", weight=
     """mt_masked_l1_fwd without autograd.  Returns (out3, saved): out3 = [loss, sum|.|, den] on the
     device, ``saved`` feeds masked_l1_bwd_raw."""
     _need_cuda(y_hat, y, mask)
-    (a, b_, m), B, C, F, P, mask_c = _l1_layout(y_hat, y, mask)
+    if y_hat.numel() == 0:
+        raise RuntimeError("masked_l1: empty input")
+    (a, b_, m), B, C, F, P, mask_c, repeat = _l1_layout(y_hat, y, mask)
     bm = _bm(batch_mask, y_hat)
     out3 = _empty(3, dtype=torch.float32, device=y_hat.device)
-    _lib.call("mt_masked_l1_fwd", _ptr(a[0]), a[1], a[2], a[3], _ptr(b_[0]), b_[1], b_[2], b_[3],
+    _call("mt_masked_l1_fwd", _ptr(a[0]), a[1], a[2], a[3], _ptr(b_[0]), b_[1], b_[2], b_[3],
               _ptr(m[0]), m[1], m[2], m[3], _ptr(bm), _ptr(out3), _ptr(reduce_workspace(y_hat)),
-              B, C, F, P, mask_c, REDUCE[reduction], float(weight), _stream(y_hat))
+              B, C, F, P, mask_c, repeat, REDUCE[reduction], float(weight), _stream(y_hat))
     meta = (a[1:], b_[1:], m[1:], B, C, F, P, mask_c, REDUCE[reduction], float(weight), tuple(y_hat.shape))
     return out3, (a[0], b_[0], m[0], out3, bm, meta)
 
@@ -255,9 +357,10 @@ def masked_l1_fwd_raw(y_hat, y, mask, batch_mask=None, reduction="mean", weight=
 def masked_l1_bwd_raw(saved, grad_out, need_y_hat=True, need_y=False):
     """mt_masked_l1_bwd: gradients w.r.t. y_hat and / or y (grad_y = -grad_y_hat)."""
     a, b_, m, out3, bm, (sa, sb, sm, B, C, F, P, mask_c, red, weight, shape) = saved
+    _device[0] = a.device.index
     ga = _empty((B, C, F, P), dtype=torch.float32, device=a.device) if need_y_hat else None
     gb = _empty((B, C, F, P), dtype=torch.float32, device=a.device) if need_y else None
-    _lib.call("mt_masked_l1_bwd", _ptr(a), sa[0], sa[1], sa[2], _ptr(b_), sb[0], sb[1], sb[2],
+    _call("mt_masked_l1_bwd", _ptr(a), sa[0], sa[1], sa[2], _ptr(b_), sb[0], sb[1], sb[2],
               _ptr(m), sm[0], sm[1], sm[2], _ptr(bm), _ptr(out3), _ptr(grad_out),
               _ptr(ga), _ptr(gb), B, C, F, P, mask_c, red, weight, _stream(a))
     ga = ga.view(shape) if ga is not None else None
@@ -313,7 +416,7 @@ def chn_l1x3_fwd_raw(y_hat, y_hat_comp, y_target, v_target, v_map, weights=(0.5,
     yt, vt = _planes(y_target), _planes(v_target)
     out9 = _empty(9, dtype=torch.float32, device=yh.device)
     wts = tuple(float(x) for x in weights)
-    _lib.call("mt_chn_l1x3_fwd", _ptr(yh), *yh_s, _ptr(yc), *yc_s, _ptr(yt), yt.stride(0), yt.stride(1),
+    _call("mt_chn_l1x3_fwd", _ptr(yh), *yh_s, _ptr(yc), *yc_s, _ptr(yt), yt.stride(0), yt.stride(1),
               _ptr(vt), vt.stride(0), _ptr(vm), vm_sb, vm_sf, _ptr(out9), _ptr(reduce_workspace(yh)),
               b, f, h * w, wts[0], wts[1], wts[2], _stream(yh))
     meta = (tuple(yh_s), tuple(yc_s), (yt.stride(0), yt.stride(1)), vt.stride(0), (vm_sb, vm_sf), b, f, h, w, wts)
@@ -323,9 +426,10 @@ def chn_l1x3_fwd_raw(y_hat, y_hat_comp, y_target, v_target, v_map, weights=(0.5,
 def chn_l1x3_bwd_raw(saved, grad_out3, need_y_hat=True, need_y_comp=True):
     """mt_chn_l1x3_bwd: gradients w.r.t. y_hat (terms nh + vh) and y_hat_comp (term nvh)."""
     yh, yc, yt, vt, vm, out9, (yh_s, yc_s, yt_s, vt_sb, vm_s, b, f, h, w, wts) = saved
+    _device[0] = yh.device.index
     g_yh = _empty((b, 3, f, h, w), dtype=torch.float32, device=yh.device) if need_y_hat else None
     g_yc = _empty((b, 3, f, h, w), dtype=torch.float32, device=yh.device) if need_y_comp else None
-    _lib.call("mt_chn_l1x3_bwd", _ptr(yh), *yh_s, _ptr(yc), *yc_s, _ptr(yt), *yt_s, _ptr(vt), vt_sb,
+    _call("mt_chn_l1x3_bwd", _ptr(yh), *yh_s, _ptr(yc), *yc_s, _ptr(yt), *yt_s, _ptr(vt), vt_sb,
               _ptr(vm), *vm_s, _ptr(out9), _ptr(grad_out3), _ptr(g_yh), _ptr(g_yc), b, f, h * w,
               wts[0], wts[1], wts[2], _stream(yh))
     return g_yh, g_yc
@@ -381,7 +485,7 @@ def warp_l1_fwd_raw(x_refs, vis, flow, x_target, v_target, weight=1.0, materiali
         xa_mem, xa = _frame_major(b, 3, f, h, w, x)
         va = _empty((b, 1, f, h, w), dtype=torch.float32, device=x.device)
         vis_t, v_sb, _, v_sf = _s5(vis)
-    _lib.call("mt_warp_l1_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis_t), v_sb, v_sf, _ptr(flow_c),
+    _call("mt_warp_l1_fwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(vis_t), v_sb, v_sf, _ptr(flow_c),
               _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0), _ptr(xa_mem),
               _ptr(va), _ptr(out3), _ptr(reduce_workspace(x)), b, f, h, w, float(weight),
               flags, _stream(x))
@@ -392,8 +496,9 @@ def warp_l1_fwd_raw(x_refs, vis, flow, x_target, v_target, weight=1.0, materiali
 def warp_l1_bwd_raw(saved, grad_out):
     """mt_warp_l1_bwd: d loss / d flow (B,F,H,W,2); grad_out is a 1-element device tensor."""
     x, flow, xt, vt, out3, (x_sb, x_sc, x_sf, b, f, h, w, weight, flags) = saved
+    _device[0] = x.device.index
     gflow = _empty_like(flow)
-    _lib.call("mt_warp_l1_bwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(flow), _ptr(xt), xt.stride(0),
+    _call("mt_warp_l1_bwd", _ptr(x), x_sb, x_sc, x_sf, _ptr(flow), _ptr(xt), xt.stride(0),
               xt.stride(1), _ptr(vt), vt.stride(0), _ptr(out3), _ptr(grad_out), _ptr(gflow), b, f, h, w,
               weight, flags, _stream(x))
     return gflow
@@ -435,6 +540,7 @@ def warp_masked_l1(x_refs, vis, flow, x_target, v_target, weight=1.0, materializ
 def corr4d(feats_t, v_t, feats_r, v_r):
     """CorrelationVGG.correlation_masked_4d (model_dfpn.py:534-565)."""
     _need_cuda(feats_t, v_t, feats_r, v_r)
+    _no_grad_inputs("corr4d", feats_t, v_t, feats_r, v_r)
     b, c, f, h, w = feats_r.shape
     p = h * w
     ft = _contig(feats_t)
@@ -445,7 +551,7 @@ def corr4d(feats_t, v_t, feats_r, v_r):
     lib = _lib.load()
     nbytes = int(lib.mt_corr4d_workspace_bytes(b, c, f, p))
     ws = scratch(fr, "corr", nbytes)
-    _lib.call("mt_corr4d_fwd", _ptr(ft), _ptr(vt), _ptr(fr), _ptr(vr), _ptr(out), _ptr(ws),
+    _call("mt_corr4d_fwd", _ptr(ft), _ptr(vt), _ptr(fr), _ptr(vr), _ptr(out), _ptr(ws),
               ws.numel(), b, c, f, p, _stream(fr))
     return out
 
@@ -456,6 +562,7 @@ def corr4d(feats_t, v_t, feats_r, v_r):
 def cm_match(c_feats, v_t, v_aligned, return_gs=False):
     """CM_Module.forward (model_cpn.py:206-243)."""
     _need_cuda(c_feats, v_t, v_aligned)
+    _no_grad_inputs("cm_match", c_feats, v_t, v_aligned)
     b, c, f, h, w = c_feats.shape
     H, W = v_t.shape[-2:]
     cf = _contig(c_feats)
@@ -465,7 +572,7 @@ def cm_match(c_feats, v_t, v_aligned, return_gs=False):
     cmask = _empty((b, 1, h, w), dtype=torch.float32, device=cf.device)
     lib = _lib.load()
     ws = scratch(cf, "cm", int(lib.mt_cm_workspace_bytes(b, c, f, h, w)))
-    _lib.call("mt_cm_match_fwd", _ptr(cf), _ptr(vt), _ptr(va), _ptr(out), _ptr(cmask), _ptr(ws),
+    _call("mt_cm_match_fwd", _ptr(cf), _ptr(vt), _ptr(va), _ptr(out), _ptr(cmask), _ptr(ws),
               b, c, f, h, w, H, W, _stream(cf))
     if return_gs:
         addr = lib.mt_cm_workspace_gs(_ptr(ws), b, c, f, h, w)
@@ -481,13 +588,14 @@ def cm_match(c_feats, v_t, v_aligned, return_gs=False):
 def chn_pack(x_t, v_t, x_al, v_al, v_map):
     """model_chn.py:68-80 -> nn_input (B*F,9,H,W) NCHW."""
     _need_cuda(x_t, v_t, x_al, v_al, v_map)
+    _no_grad_inputs("chn_pack", x_t, v_t, x_al, v_al, v_map)
     b, _, f, h, w = x_al.shape
     xt, vt = _planes(x_t), _planes(v_t)
     xa, xa_sb, xa_sc, xa_sf = _s5(x_al)
     va, va_sb, _, va_sf = _s5(v_al)
     vm, vm_sb, _, vm_sf = _s5(v_map)
     out = _empty((b * f, 9, h, w), dtype=torch.float32, device=xa.device)
-    _lib.call("mt_chn_pack", _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0), _ptr(xa),
+    _call("mt_chn_pack", _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0), _ptr(xa),
               xa_sb, xa_sc, xa_sf, _ptr(va), va_sb, va_sf, _ptr(vm), vm_sb, vm_sf, _ptr(out), b, f,
               h * w, _stream(xa))
     return out
@@ -504,7 +612,7 @@ class ChnCompositeFn(torch.autograd.Function):
         xt, vt = _planes(x_t), _planes(v_t)
         yh_mem, yh = _frame_major(b, 3, f, h, w, no)
         yc_mem, yc = _frame_major(b, 3, f, h, w, no)
-        _lib.call("mt_chn_composite_fwd", _ptr(no), _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt),
+        _call("mt_chn_composite_fwd", _ptr(no), _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt),
                   vt.stride(0), _ptr(yh_mem), _ptr(yc_mem), b, f, h * w, _stream(no))
         ctx.save_for_backward(no, vt)
         ctx.meta = (b, f, h, w)
@@ -522,6 +630,7 @@ class ChnCompositeFn(torch.autograd.Function):
 def chn_composite_bwd_raw(nn_out, v_t, g_yh, g_yc, b, f):
     """mt_chn_composite_bwd: gradient w.r.t. the CNN output from the grads of both outputs."""
     h, w = nn_out.shape[-2:]
+    _device[0] = nn_out.device.index
     no, vt = _contig(nn_out), _planes(v_t)
     gy = gc = None
     gy_s = gc_s = (0, 0, 0)
@@ -530,7 +639,7 @@ def chn_composite_bwd_raw(nn_out, v_t, g_yh, g_yc, b, f):
     if g_yc is not None:
         gc, *gc_s = _s5(g_yc)
     g = _empty_like(no)
-    _lib.call("mt_chn_composite_bwd", _ptr(no), _ptr(vt), vt.stride(0), _ptr(gy), *gy_s, _ptr(gc),
+    _call("mt_chn_composite_bwd", _ptr(no), _ptr(vt), vt.stride(0), _ptr(gy), *gy_s, _ptr(gc),
               *gc_s, _ptr(g), b, f, h * w, _stream(no))
     return g
 
@@ -542,13 +651,14 @@ def chn_composite(nn_out, x_t, v_t, b, f):
 def hole_update(m_t, v_map0, y_comp0):
     """model_chn.py:128-131: returns (m_new (B,1,H,W), x_new (B,3,H,W), inp_per 0-d device tensor)."""
     _need_cuda(m_t, v_map0, y_comp0)
+    _no_grad_inputs("hole_update", m_t, v_map0, y_comp0)
     b = m_t.shape[0]
     h, w = m_t.shape[-2:]
     mt, vm, yc = _planes(m_t), _planes(v_map0), _planes(y_comp0)
     m_new = _empty((b, 1, h, w), dtype=torch.float32, device=mt.device)
     x_new = _empty((b, 3, h, w), dtype=torch.float32, device=mt.device)
     per = _empty(1, dtype=torch.float32, device=mt.device)
-    _lib.call("mt_hole_update", _ptr(mt), mt.stride(0), _ptr(vm), vm.stride(0), _ptr(yc), yc.stride(0),
+    _call("mt_hole_update", _ptr(mt), mt.stride(0), _ptr(vm), vm.stride(0), _ptr(yc), yc.stride(0),
               yc.stride(1), _ptr(m_new), _ptr(x_new), _ptr(per), _ptr(reduce_workspace(mt)), b, h * w,
               _stream(mt))
     return m_new, x_new, per[0]
@@ -558,6 +668,7 @@ def chn_fill(nn_out, x_t, v_t, m_t, v_map0):
     """mt_chn_fill_step: composite (model_chn.py:80-85) + hole update (:128-131) of one inference step
     with a single reference frame.  nn_out (B,3,H,W).  Returns (y_comp0 (B,3,H,W), m_new, x_new, inp_per)."""
     _need_cuda(nn_out, x_t, v_t, m_t, v_map0)
+    _no_grad_inputs("chn_fill", nn_out, x_t, v_t, m_t, v_map0)
     b = x_t.shape[0]
     h, w = x_t.shape[-2:]
     no, xt, vt, mt, vm = _contig(nn_out), _planes(x_t), _planes(v_t), _planes(m_t), _planes(v_map0)
@@ -565,7 +676,7 @@ def chn_fill(nn_out, x_t, v_t, m_t, v_map0):
     m_new = _empty((b, 1, h, w), dtype=torch.float32, device=no.device)
     x_new = _empty((b, 3, h, w), dtype=torch.float32, device=no.device)
     per = _empty(1, dtype=torch.float32, device=no.device)
-    _lib.call("mt_chn_fill_step", _ptr(no), _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0),
+    _call("mt_chn_fill_step", _ptr(no), _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0),
               _ptr(mt), mt.stride(0), _ptr(vm), vm.stride(0), _ptr(yc), _ptr(m_new), _ptr(x_new), _ptr(per),
               _ptr(reduce_workspace(no)), b, h * w, _stream(no))
     return yc, m_new, x_new, per[0]
@@ -574,11 +685,12 @@ def chn_fill(nn_out, x_t, v_t, m_t, v_map0):
 def trivial_copy(x_t, x_al, v_map):
     """model_dfpn.py:427-429."""
     _need_cuda(x_t, x_al, v_map)
+    _no_grad_inputs("trivial_copy", x_t, x_al, v_map)
     b, _, f, h, w = x_al.shape
     xt = _planes(x_t)
     xa, xa_sb, xa_sc, xa_sf = _s5(x_al)
     vm, vm_sb, _, vm_sf = _s5(v_map)
     y = _empty((b, 3, f, h, w), dtype=torch.float32, device=xa.device)
-    _lib.call("mt_trivial_copy", _ptr(xt), xt.stride(0), xt.stride(1), _ptr(xa), xa_sb, xa_sc, xa_sf,
+    _call("mt_trivial_copy", _ptr(xt), xt.stride(0), xt.stride(1), _ptr(xa), xa_sb, xa_sc, xa_sf,
               _ptr(vm), vm_sb, vm_sf, _ptr(y), b, f, h * w, _stream(xa))
     return y

@@ -70,12 +70,33 @@ class CM_Module(nn.Module):
 # aligner protocol: .align(x_target, m_target, x_refs, m_refs)
 #                   -> (x_aligned, v_aligned, v_maps)
 # ---------------------------------------------------------------------------
+def dfpn_forward_256(self, x_target, m_target, x_refs, m_refs):
+    """DFPN.forward (model_dfpn.py:46-101) up to its last line: the same calls into the same sub-networks
+    (VGG, 4-D conv, mixer, flow estimators: cuDNN), returning the flow at the DFPN's internal 256 x 256
+    resolution.  The reference's closing ``resize_flow(flow_256, (h, w), mode='bilinear')`` (:100-101) is what
+    the warp kernel then does on the fly.  Installed by ``patch()`` as ``DFPN._mt_b200_flow_256``."""
+    import master_thesis as mt
+    x_target = (x_target - self.mean.squeeze(2)) / self.std.squeeze(2)                      # :71
+    x_refs = (x_refs - self.mean) / self.std                                                # :72
+    sq = mt.TransformsUtils.resize_set_bis(x_target, m_target, x_refs, m_refs, (256, 256))   # :74-77
+    s64 = mt.TransformsUtils.resize_set_bis(x_target, m_target, x_refs, m_refs, (64, 64))    # :78-81
+    flow_16 = self.corr_mixer(self.corr(*sq))                                               # :83-84
+    flow_64 = self.flow_64(*s64, mt.FlowsUtils.resize_flow(flow_16, (64, 64), mode='bilinear'))      # :86-91
+    return self.flow_256(*sq, mt.FlowsUtils.resize_flow(flow_64, (256, 256), mode='bilinear'))       # :93-98
+
+
 def _dfpn_grid(self, x_target, m_target, x_refs, m_refs):
     """The flow of DFPN.align (model_dfpn.py:103-127): the DFPN forward (VGG, 4-D conv, flow
-    estimators: cuDNN), untouched."""
+    estimators: cuDNN), untouched.  For frames that are not 256 x 256 a patched DFPN hands out the flow
+    at 256 x 256 (``_mt_b200_flow_256``) and the kernel resizes it while it warps."""
+    h, w = x_refs.shape[-2:]
+    lowres = getattr(self, "_mt_b200_flow_256", None)
     with torch.no_grad():
-        *_, flow_256 = self(x_target, m_target, x_refs, m_refs)
-    return flow_256, ops.ALIGN_CORNERS | ops.VIS_FROM_MASK
+        if lowres is not None and (h, w) != (256, 256):
+            flow = lowres(x_target, m_target, x_refs, m_refs)
+        else:
+            *_, flow = self(x_target, m_target, x_refs, m_refs)
+    return flow, ops.ALIGN_CORNERS | ops.VIS_FROM_MASK
 
 
 def _cpn_grid(self, x_target, m_target, x_refs, m_refs):
@@ -100,6 +121,93 @@ def dfpn_align(self, x_target, m_target, x_refs, m_refs):
     the v_map are one kernel."""
     grid, flags = _dfpn_grid(self, x_target, m_target, x_refs, m_refs)
     return ops.warp_fwd(x_refs, m_refs, grid, m_target, flags)
+
+
+class DeferredAlign(object):
+    """An ``xs_aligned`` entry of the patched ``DFPN._train_val_wrapper``: the arguments of
+    ``FlowsUtils.align_set(x_refs, v_refs, flow)`` (model_dfpn.py:377-385) whose result has not been computed.
+    The patched ``DFPN.compute_loss`` feeds them to the fused warp + mask_out + masked-L1 kernel, so the
+    aligned frames of the training step are never written to HBM.  Anything else that touches the object
+    (attribute access, torch functions) gets the materialised ``x_aligned`` tensor."""
+
+    def __init__(self, x_refs, v_refs, flow):
+        self.x_refs, self.v_refs, self.flow = x_refs, v_refs, flow
+        self._done = None
+
+    def materialize(self):
+        """(x_aligned, v_aligned) = FlowsUtils.align_set(x_refs, v_refs, flow), differentiable w.r.t. flow."""
+        if self._done is None:
+            self._done = ops.align_set(self.x_refs, self.v_refs, self.flow)
+        return self._done
+
+    def __getattr__(self, name):          # only reached for names that are not set in __init__
+        return getattr(self.materialize()[0], name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def conv(a):
+            if isinstance(a, DeferredAlign):
+                return a.materialize()[0]
+            if isinstance(a, (list, tuple)):
+                return type(a)(conv(i) for i in a)
+            return a
+        return func(*conv(tuple(args)), **{k: conv(v) for k, v in (kwargs or {}).items()})
+
+
+def dfpn_train_val_wrapper(self, x, m, y, flow_gt, flows_use, t, r_list):
+    """Replaces DFPN._train_val_wrapper (model_dfpn.py:310-394).  Same forward pass, same resized sets and
+    ground-truth flows, same 8-tuple; two differences, neither visible in what the reference does with the
+    result: (i) ``xs_aligned`` holds ``DeferredAlign`` handles instead of warped tensors - the patched
+    ``compute_loss`` turns the 64 and 256 scales into ONE fused kernel each (warp + mask_out + masked L1),
+    the 16 scale is never used by the loss (:274-287); (ii) the two ``align_set`` calls with the ground-truth
+    flows (:358-363) are skipped: their results only feed ``v_map_64_gt`` / ``v_map_256_gt`` (:365-375),
+    which the reference computes and never reads."""
+    import master_thesis as mt
+    corr, flow_16, flow_64, flow_256 = self(x[:, :, t], m[:, :, t], x[:, :, r_list], m[:, :, r_list])
+    x_16, v_16, y_16 = mt.TransformsUtils.resize_set(x, 1 - m, y, 16)
+    x_64, v_64, y_64 = mt.TransformsUtils.resize_set(x, 1 - m, y, 64)
+    x_256, v_256, y_256 = x, 1 - m, y
+    flow_16_gt = mt.FlowsUtils.resize_flow(flow_gt[:, r_list], (16, 16))
+    flow_64_gt = mt.FlowsUtils.resize_flow(flow_gt[:, r_list], (64, 64))
+    flow_256_gt = flow_gt[:, r_list]
+    xs_aligned = tuple(DeferredAlign(xx[:, :, r_list], vv[:, :, r_list], fl)
+                       for xx, vv, fl in ((x_16, v_16, flow_16), (x_64, v_64, flow_64), (x_256, v_256, flow_256)))
+    return corr, (x_16, x_64, x_256), (v_16, v_64, v_256), (y_16, y_64, y_256), xs_aligned, \
+        (flow_16, flow_64, flow_256), (flow_16_gt, flow_64_gt, flow_256_gt), flows_use
+
+
+def _alignment_recons(x, v, x_aligned, flow, t, n_refs):
+    """One reconstruction term of DFPN.compute_loss (model_dfpn.py:269-287)."""
+    if isinstance(x_aligned, DeferredAlign) and x_aligned._done is None and x_aligned.flow is flow:
+        # warp + mask_out + masked L1 ('sum') in one pass; backward = one pass writing only d loss / d flow
+        return ops.warp_masked_l1(x_aligned.x_refs, x_aligned.v_refs, flow, x[:, :, t], v[:, :, t])[0]
+    if isinstance(x_aligned, DeferredAlign):
+        x_aligned = x_aligned.materialize()[0]
+    mask = v[:, :, t].unsqueeze(2) * (1 - ops.mask_out(flow))             # (B,1,F,h,w), :269-272 + :277-278
+    return ops.masked_l1(x[:, :, t].unsqueeze(2).expand(-1, -1, n_refs, -1, -1), x_aligned, mask, reduction='sum')
+
+
+def dfpn_compute_loss(self, corr, xs, vs, ys, xs_aligned, flows, flows_gt, flows_use, t, r_list):
+    """Replaces DFPN.compute_loss (model_dfpn.py:210-293).  The VGG features of the ground truth (cuDNN) and
+    the L1 against the filled correlation volume are the reference's own calls; the unmasked correlation of
+    the ground truth (:254), the three flow losses (:259-267, all-ones mask never materialised, no host sync
+    for ``flows_use``) and the two reconstruction terms (:269-287) are kernels of this library."""
+    import torch.nn.functional as F
+    b, c, f, h, w = ys[2].size()
+    with torch.no_grad():
+        y_vgg_input = ys[2].transpose(1, 2).reshape(b * f, c, h, w)
+        if not (h == 256 and w == 256):
+            y_vgg_input = F.interpolate(y_vgg_input, (256, 256), mode='bilinear')
+        y_vgg_feats = self.model_vgg(y_vgg_input)
+    y_vgg_feats = y_vgg_feats[3].reshape(b, f, -1, 16, 16).transpose(1, 2)
+    corr_y = ops.corr4d(y_vgg_feats[:, :, t], None, y_vgg_feats[:, :, r_list], None)
+    corr_loss = F.l1_loss(corr, corr_y)
+    flow_losses = [ops.masked_l1(flows[i], flows_gt[i], None, flows_use) for i in range(3)]
+    recons_64 = _alignment_recons(xs[1], vs[1], xs_aligned[1], flows[1], t, len(r_list))
+    recons_256 = _alignment_recons(xs[2], vs[2], xs_aligned[2], flows[2], t, len(r_list))
+    total_loss = corr_loss + flow_losses[0] + flow_losses[1] + flow_losses[2]
+    total_loss = total_loss + recons_64 + recons_256
+    return total_loss, [corr_loss] + flow_losses + [recons_64, recons_256]
 
 
 def cpn_align(self, x_target, m_target, x_refs, m_refs):
@@ -242,6 +350,8 @@ def trivial_copy(x_target, x_ref_aligned, v_map):
 # ---------------------------------------------------------------------------
 # rebinding
 # ---------------------------------------------------------------------------
+_ABSENT = object()      # marker: the attribute did not exist before patch() (helpers such as _mt_b200_flow_256)
+
 _PATCHES = (
     # (module path, class, attribute, replacement, static?)
     ("utils", "FlowsUtils", "align_set", FlowsUtils.align_set, True),
@@ -249,6 +359,9 @@ _PATCHES = (
     ("model_dfpn", "CorrelationVGG", "correlation_masked_4d",
      CorrelationVGG.correlation_masked_4d, True),
     ("model_dfpn", "DFPN", "align", dfpn_align, False),
+    ("model_dfpn", "DFPN", "_train_val_wrapper", dfpn_train_val_wrapper, False),
+    ("model_dfpn", "DFPN", "compute_loss", dfpn_compute_loss, False),
+    ("model_dfpn", "DFPN", "_mt_b200_flow_256", dfpn_forward_256, False),
     ("model_cpn", "CPN", "align", cpn_align, False),
     ("model_cpn", "CM_Module", "forward", CM_Module.forward, False),
     ("model_chn", "CHN", "forward", chn_forward, False),
@@ -271,7 +384,7 @@ def patch(mt):
         klass = getattr(getattr(mt, mod), cls)
         key = "_mt_b200_orig_" + attr
         if key not in klass.__dict__:
-            setattr(klass, key, klass.__dict__[attr])
+            setattr(klass, key, klass.__dict__.get(attr, _ABSENT))
         setattr(klass, attr, staticmethod(repl) if static else repl)
         done.append("%s.%s.%s" % (mod, cls, attr))
     return done
@@ -282,5 +395,8 @@ def unpatch(mt):
         klass = getattr(getattr(mt, mod), cls)
         key = "_mt_b200_orig_" + attr
         if key in klass.__dict__:
-            setattr(klass, attr, klass.__dict__[key])
+            if klass.__dict__[key] is _ABSENT:
+                delattr(klass, attr)
+            else:
+                setattr(klass, attr, klass.__dict__[key])
             delattr(klass, key)

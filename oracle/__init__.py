@@ -156,6 +156,28 @@ def masked_l1(y_hat, y, mask, batch_mask=None, reduction="mean", weight=1.0):
         ctypes.c_float(weight), None))
 
 
+def masked_l1_bcast(y_hat, y, mask, reduction="mean", weight=1.0, grad=False):
+    """a5 with a mask that broadcasts against y_hat (utils.py:166-169): the numerator runs over the broadcast
+    product, the 'sum' denominator is sum(mask) of the mask AS GIVEN.  Returns the loss (and d loss / d y_hat)."""
+    y_hat, y, mask = _c(y_hat), _c(y), _c(mask)
+    full = np.ascontiguousarray(np.broadcast_to(mask, y_hat.shape))
+    b = y_hat.shape[0]
+    sums = (ctypes.c_double * 3)()
+    inner = int(np.prod(y_hat.shape[1:]))
+    lib().mto_masked_l1(_p(y_hat), _p(y), _p(full), _i(b), _i(1), _l(inner), _i(1), None, _i(1),
+                        ctypes.c_float(1.0), sums)
+    num = np.float32(sums[0])
+    if reduction == "sum":
+        den = np.float32(np.float32(mask.astype(np.float64).sum()) + np.float32(1e-9))
+        loss, scale = np.float32(weight) * num / den, np.float32(weight) / den
+    else:
+        loss, scale = np.float32(weight) * np.float32(sums[0] / y_hat.size), np.float32(weight) / np.float32(y_hat.size)
+    if not grad:
+        return float(loss)
+    d = y_hat * full - y * full
+    return float(loss), (np.sign(d) * full * scale).astype(np.float32)
+
+
 def masked_l1_bwd(y_hat, y, mask, batch_mask=None, reduction="mean", weight=1.0, grad_out=1.0):
     """Gradient of a5 w.r.t. ``y`` (grad w.r.t. ``y_hat`` is its negation)."""
     y_hat, y, mask, b, c, inner, mask_c, bm = _l1_args(y_hat, y, mask, batch_mask)
@@ -251,6 +273,26 @@ def trivial_copy(x_t, x_al, v_map):
     y = np.empty_like(x_al)
     lib().mto_trivial_copy(_p(x_t), _p(x_al), _p(v_map), _i(b), _i(f), _l(h * w), _p(y))
     return y
+
+
+def resize_flow(flow, size):
+    """f1 - FlowsUtils.resize_flow(flow, size, mode='bilinear') (utils.py:107-126); flow (b,f,h,w,2)."""
+    flow = _c(flow)
+    b, f, h, w, _ = flow.shape
+    H, W = size
+    out = np.empty((b, f, H, W, 2), np.float32)
+    lib().mto_resize_flow(_p(flow), _i(b * f), _i(h), _i(w), _i(H), _i(W), _p(out))
+    return out
+
+
+def vis_nearest(m, size):
+    """f3 - F.interpolate(1 - m, size, mode='nearest') (model_dfpn.py:521-526); m (..., H, W)."""
+    m = _c(m)
+    H, W = m.shape[-2:]
+    h, w = size
+    out = np.empty(m.shape[:-2] + (h, w), np.float32)
+    lib().mto_vis_nearest(_p(m), _i(int(np.prod(m.shape[:-2]))), _i(H), _i(W), _i(h), _i(w), _p(out))
+    return out
 
 
 def chn_l1_terms(y_target, v_target, y_hat, y_hat_comp, v_map, weights=(0.5, 2.0, 1.0), grads=False):

@@ -647,3 +647,84 @@ MTO_API void mto_trivial_copy(const float *x_t, const float *x_al, const float *
                     y[d] = x_t[((int64_t)bi * 3 + k) * P + p] * (1.0f - vm) + x_al[d] * vm;
                 }
 }
+
+/* ------------------------------------------------------------------------ */
+/* f1: FlowsUtils.resize_flow(flow, (H, W), mode='bilinear')                  */
+/*     master_thesis/utils.py:107-126, called at model_dfpn.py:100-101        */
+/* ------------------------------------------------------------------------ */
+/* F.interpolate(bilinear, align_corners=False) of the two flow components
+   (ATen UpSample.h:442-476 compute_source_index_and_lambda +
+   UpSampleKernel.cpp cpu_upsample_generic).  Operation order and FMA
+   contraction of the CPU build, pinned by probing torch 2.11 CPU with a
+   256 x 256 source (the only source size the reference uses here) and
+   outputs from 100 x 180 to 1080 x 1920:
+       src = fma(scale, dst + 0.5, -0.5), clamped at 0; scale = in / out (fp32)
+       i0 = min(floor(src), in - 1); i1 = i0 + (i0 < in - 1)
+       l1 = clamp(src - i0, 0, 1); l0 = 1 - l1      (in == out: identity)
+       row(y) = fma(v[y][x0], lx0, v[y][x1] * lx1)
+       out    = fma(row(y0), ly0, row(y1) * ly1)
+   (outputs of a few dozen pixels take another ATen code path whose last ulp
+   differs: <= 2.4e-7.)                                                       */
+typedef struct { int i0, i1; float l0, l1; } mto_lin_t;
+
+static inline mto_lin_t lin_index(int dst, int in, int out) {
+    mto_lin_t r;
+    if (in == out) {
+        r.i0 = r.i1 = dst; r.l0 = 1.0f; r.l1 = 0.0f;
+        return r;
+    }
+    const float scale = (float)in / (float)out;
+    float s = fmaf(scale, (float)dst + 0.5f, -0.5f);
+    if (s < 0.0f) s = 0.0f;
+    int i0 = (int)floorf(s);
+    if (i0 > in - 1) i0 = in - 1;
+    r.i0 = i0;
+    r.i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    float l1 = s - (float)i0;
+    l1 = l1 < 0.0f ? 0.0f : (l1 > 1.0f ? 1.0f : l1);
+    r.l1 = l1;
+    r.l0 = 1.0f - l1;
+    return r;
+}
+
+/* flow (n, h, w, 2) -> out (n, H, W, 2) */
+MTO_API void mto_resize_flow(const float *flow, int n, int h, int w, int H, int W, float *out) {
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int i = 0; i < n; ++i) {
+        for (int y = 0; y < H; ++y) {
+            const mto_lin_t ly = lin_index(y, h, H);
+            const float *r0 = flow + ((int64_t)i * h + ly.i0) * w * 2;
+            const float *r1 = flow + ((int64_t)i * h + ly.i1) * w * 2;
+            float *o = out + ((int64_t)i * H + y) * W * 2;
+            for (int x = 0; x < W; ++x) {
+                const mto_lin_t lx = lin_index(x, w, W);
+                for (int k = 0; k < 2; ++k) {
+                    const float top = fmaf(r0[lx.i0 * 2 + k], lx.l0, r0[lx.i1 * 2 + k] * lx.l1);
+                    const float bot = fmaf(r1[lx.i0 * 2 + k], lx.l0, r1[lx.i1 * 2 + k] * lx.l1);
+                    o[x * 2 + k] = fmaf(top, ly.l0, bot * ly.l1);
+                }
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* f3: nearest down-sample of the visibility maps in CorrelationVGG.forward  */
+/*     master_thesis/model_dfpn.py:521-526:  v = F.interpolate(1 - m, (h, w),  */
+/*     mode='nearest'); ATen UpSample.h nearest_neighbor_compute_source_index: */
+/*     src = min(floor(dst * (in / out)), in - 1), scale in fp32.              */
+/* ------------------------------------------------------------------------ */
+/* m (n, H, W) -> v (n, h, w) = 1 - m[nearest] */
+MTO_API void mto_vis_nearest(const float *m, int n, int H, int W, int h, int w, float *v) {
+    const float sy = (float)H / (float)h, sx = (float)W / (float)w;
+    for (int i = 0; i < n; ++i)
+        for (int y = 0; y < h; ++y) {
+            int ys = (int)floorf((float)y * sy);
+            if (ys > H - 1) ys = H - 1;
+            for (int x = 0; x < w; ++x) {
+                int xs = (int)floorf((float)x * sx);
+                if (xs > W - 1) xs = W - 1;
+                v[((int64_t)i * h + y) * w + x] = 1.0f - m[((int64_t)i * H + ys) * W + xs];
+            }
+        }
+}

@@ -147,3 +147,56 @@ def hole_update(m_t, v_map0, y_comp0):
     m_new = m_t - v_map0
     x_new = (1 - m_new) * y_comp0 + m_new.repeat(1, 3, 1, 1) * fill
     return m_new, x_new, torch.sum(m_new) * 100 / m_new.numel()
+
+
+# --------------------------------------------------------------------------------------------------
+# DFPN training step around the hot path (model_dfpn.py:310-394, 210-293): needed to pin the patched
+# DFPN._train_val_wrapper / DFPN.compute_loss on the GPU box, where the reference is absent.
+# --------------------------------------------------------------------------------------------------
+def resize_set(x, v, y, size):
+    """TransformsUtils.resize_set, utils.py:522-560."""
+    b, c, f, h, w = x.size()
+
+    def rs(t, ch, **kw):
+        return F.interpolate(t.transpose(1, 2).reshape(-1, ch, h, w), (size, size), **kw) \
+            .reshape(b, f, ch, size, size).transpose(1, 2)
+    return rs(x, c, mode='bilinear'), rs(v, 1), rs(y, c, mode='bilinear')
+
+
+def resize_flow(flow, size, mode='nearest'):
+    """FlowsUtils.resize_flow, utils.py:107-126."""
+    b, f, h, w, _ = flow.size()
+    r = F.interpolate(flow.reshape(b * f, h, w, 2).permute(0, 3, 1, 2), size, mode=mode)
+    return r.reshape(b, f, 2, size[0], size[1]).permute(0, 1, 3, 4, 2)
+
+
+def dfpn_train_val_wrapper(forward, x, m, y, flow_gt, flows_use, t, r_list):
+    """model_dfpn.py:346-394 (the ground-truth alignments :358-375 feed nothing and are omitted)."""
+    corr, flow_16, flow_64, flow_256 = forward(x[:, :, t], m[:, :, t], x[:, :, r_list], m[:, :, r_list])
+    x_16, v_16, y_16 = resize_set(x, 1 - m, y, 16)
+    x_64, v_64, y_64 = resize_set(x, 1 - m, y, 64)
+    x_256, v_256, y_256 = x, 1 - m, y
+    flows_gt = (resize_flow(flow_gt[:, r_list], (16, 16)), resize_flow(flow_gt[:, r_list], (64, 64)), flow_gt[:, r_list])
+    xs_aligned = tuple(align_set(xx[:, :, r_list], vv[:, :, r_list], fl)[0]
+                       for xx, vv, fl in ((x_16, v_16, flow_16), (x_64, v_64, flow_64), (x_256, v_256, flow_256)))
+    return corr, (x_16, x_64, x_256), (v_16, v_64, v_256), (y_16, y_64, y_256), xs_aligned, \
+        (flow_16, flow_64, flow_256), flows_gt, flows_use
+
+
+def dfpn_compute_loss(model_vgg, corr, xs, vs, ys, xs_aligned, flows, flows_gt, flows_use, t, r_list):
+    """model_dfpn.py:210-293."""
+    b, c, f, h, w = ys[2].size()
+    with torch.no_grad():
+        y_in = ys[2].transpose(1, 2).reshape(b * f, c, h, w)
+        if not (h == 256 and w == 256):
+            y_in = F.interpolate(y_in, (256, 256), mode='bilinear')
+        feats = model_vgg(y_in)
+    feats = feats[3].reshape(b, f, -1, 16, 16).transpose(1, 2)
+    corr_loss = F.l1_loss(corr, corr4d(feats[:, :, t], None, feats[:, :, r_list], None))
+    items = [corr_loss] + [masked_l1(flows[i], flows_gt[i], torch.ones_like(flows[i]), flows_use) for i in range(3)]
+    for i in (1, 2):
+        n = len(r_list)
+        items.append(masked_l1(xs[i][:, :, t].unsqueeze(2).repeat(1, 1, n, 1, 1), xs_aligned[i],
+                               vs[i][:, :, t].unsqueeze(2).repeat(1, 1, n, 1, 1) * (1 - mask_out(flows[i])),
+                               reduction='sum'))
+    return sum(items[1:], items[0]), items

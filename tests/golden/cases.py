@@ -84,6 +84,10 @@ CORR_CASES = {
     "small_nomask": dict(seed=42, b=1, f=3, c=16, h=4, w=4, masked=False),
     "real_masked": dict(seed=43, b=1, f=2, c=512, h=16, w=16, masked=True),
     "real_nomask": dict(seed=44, b=2, f=1, c=512, h=16, w=16, masked=False),
+    # batch sizes at which mt_corr4d_fwd picks its wider tiles by itself (corr_tc.cu: TN = 128 from 37 frames,
+    # TN = 256 from 74 frames on a 148-SM part); the fixtures hold a strided sample + checksums
+    "mid_masked": dict(seed=45, b=10, f=4, c=512, h=16, w=16, masked=True, stride=211),
+    "big_masked": dict(seed=46, b=32, f=4, c=512, h=16, w=16, masked=True, stride=997),
 }
 
 
@@ -94,6 +98,21 @@ def corr_inputs(spec):
         return ft, None, fr, None
     vt[0, 0, 0, :] = 0.0          # a fully masked row of target pixels
     return ft, vt, fr, vr
+
+
+def corr_check(c, g, spec, tol):
+    """Compares a correlation volume with its golden file: the whole volume, or - for the large cases - the
+    strided sample and the two checksums the fixture holds."""
+    if "corr" in g:
+        assert c.shape == g["corr"].shape
+        assert np.abs(c - g["corr"]).max() <= tol
+        return
+    sample = c.reshape(-1)[::spec.get("stride", 37)]
+    assert sample.shape == g["sample"].shape
+    assert np.abs(sample - g["sample"]).max() <= tol
+    total, abs_total = c.astype(np.float64).sum(), np.abs(c).astype(np.float64).sum()
+    assert abs(total - float(g["total"])) <= tol * c.size * 0.05 + 1e-6 * abs(float(g["total"]))
+    assert abs(abs_total - float(g["abs_total"])) <= tol * c.size * 0.05 + 1e-6 * abs(float(g["abs_total"]))
 
 
 # a8 ----------------------------------------------------------------------
@@ -179,3 +198,67 @@ def get_indexes_ff(t, max_t, s, D):
     cand = [r for r in range(max_t) if r != t]
     cand = [r for _, r in sorted((abs(r - t), r) for r in cand)]
     return [r for r in cand if abs(r - t) <= D and abs(r - t) % s == 0]
+
+
+# a5, broadcast masks (the denominator is torch.sum(mask) of the mask as given) -------------
+def l1_broadcast_inputs(seed=35, b=3, c=3, f=4, h=12, w=20):
+    """y_hat, y (b,c,h,w) with a (b,1,h,w) mask - the shapes LossesUtils.masked_l1 documents (utils.py:139-157) -
+    and 5-D y_hat, y (b,c,f,h,w) with masks broadcast over F, over B, and inside the plane."""
+    r = synth.rng(seed)
+    y4a = r.random_sample((b, c, h, w)).astype(np.float32)
+    y4b = r.random_sample((b, c, h, w)).astype(np.float32)
+    m4 = (r.random_sample((b, 1, h, w)) < 0.7).astype(np.float32)
+    y5a = r.random_sample((b, c, f, h, w)).astype(np.float32)
+    y5b = r.random_sample((b, c, f, h, w)).astype(np.float32)
+    m5f = (r.random_sample((b, 1, 1, h, w)) < 0.7).astype(np.float32)       # broadcast over C and F
+    m5b = (r.random_sample((1, c, f, h, w)) < 0.7).astype(np.float32)       # broadcast over B
+    m5p = (r.random_sample((b, 1, f, 1, 1)) < 0.7).astype(np.float32)       # broadcast inside the plane
+    return y4a, y4b, m4, y5a, y5b, m5f, m5b, m5p
+
+
+# f1: resize_flow fused into the DFPN.align tail ---------------------------------------------------------
+LOWRES_CASES = {
+    # the DFPN predicts its last flow at 256 x 256 and resizes it to the frame size (model_dfpn.py:100-101)
+    "davis4": dict(seed=95, b=1, f=2, h=120, w=214, sigma=0.04),
+    "tall": dict(seed=96, b=2, f=1, h=181, w=104, sigma=0.3),
+}
+
+
+def lowres_inputs(spec):
+    """x_refs (b,3,f,h,w), m_refs (b,1,f,h,w), m_target (b,1,h,w), flow_256 (b,f,256,256,2)."""
+    b, f, h, w = spec["b"], spec["f"], spec["h"], spec["w"]
+    x, m, _ = synth.frames(spec["seed"], b, f + 1, h, w)
+    flow = synth.dense_flow(spec["seed"] + 1, b, f, 256, 256, spec["sigma"], True)
+    return x[:, :, 1:].copy(), m[:, :, 1:].copy(), m[:, :, 0].copy(), flow
+
+
+def lowres_check(xa, va, vm, g):
+    """Bit-exact comparison with a lowres_* golden file (strided sample of x_aligned + its sum, full masks)."""
+    assert np.array_equal(va, g["v_aligned"].astype(np.float32))
+    assert np.array_equal(vm, g["v_map"].astype(np.float32))
+    assert np.array_equal(xa.reshape(-1)[::5], g["x_sample"])
+    assert xa.astype(np.float64).sum() == float(g["x_total"])
+
+
+# a1 + a4 + a5 + a6 in context: DFPN._train_val_wrapper + DFPN.compute_loss ------------------------------
+DFPNLOSS_CASES = {
+    "n5": dict(seed=101, b=2, n=5, h=40, w=56, sigma=0.3, use=[1, 0]),
+    "n2": dict(seed=102, b=3, n=2, h=24, w=36, sigma=0.1, use=[1, 1, 1]),
+}
+
+
+def dfpnloss_inputs(spec):
+    """Inputs of DFPN._train_val_wrapper (model_dfpn.py:310-394) and the preset outputs of the networks it
+    calls: x, m, y (b,·,n,h,w), flow_gt (b,n,h,w,2), flows_use (b) bool, the DFPN forward's
+    (corr (b,f,16,16,16,16), flow_16, flow_64, flow_hw) and the VGG pool-4 features of y (b*n,512,16,16)."""
+    b, n, h, w = spec["b"], spec["n"], spec["h"], spec["w"]
+    x, m, y = synth.frames(spec["seed"], b, n, h, w)
+    f = n - 1
+    r = synth.rng(spec["seed"] + 1)
+    flow_gt = synth.dense_flow(spec["seed"] + 2, b, n, h, w, 0.05, True)
+    corr = r.random_sample((b, f, 16, 16, 16, 16)).astype(np.float32)
+    flow_16 = synth.dense_flow(spec["seed"] + 3, b, f, 16, 16, spec["sigma"], True)
+    flow_64 = synth.dense_flow(spec["seed"] + 4, b, f, 64, 64, spec["sigma"], True)
+    flow_hw = synth.dense_flow(spec["seed"] + 5, b, f, h, w, spec["sigma"], True)
+    feats = np.maximum(r.standard_normal((b * n, 512, 16, 16)), 0).astype(np.float32)
+    return x, m, y, flow_gt, np.array(spec["use"], dtype=bool), corr, flow_16, flow_64, flow_hw, feats

@@ -43,7 +43,8 @@ def save(name, **arrays):
 # --------------------------------------------------------------------------
 from cases import WARP_CASES, CPN_CASES, CORR_CASES, CM_CASES, CHN_CASES, LOSS_CASES  # noqa: E402
 from cases import (warp_inputs, cpn_inputs, corr_inputs, cm_inputs, chn_inputs, loss_inputs,  # noqa: E402
-                   chnloss_inputs, CHNLOSS_CASES, inpaint_inputs, INPAINT_CASES)
+                   chnloss_inputs, CHNLOSS_CASES, inpaint_inputs, INPAINT_CASES, l1_broadcast_inputs,
+                   LOWRES_CASES, lowres_inputs, DFPNLOSS_CASES, dfpnloss_inputs)
 
 
 def main():
@@ -119,6 +120,65 @@ def main():
              flow_l1=flow_l1.detach().numpy(), g_flow_l1=g_flow_l1.numpy(),
              none_selected=none_sel.numpy(), mean_l1=mean_l1.detach().numpy())
 
+    # ---- a5 with masks smaller than y_hat (utils.py:139-169: the denominator is torch.sum(mask) of the
+    # mask as given, the numerator runs over the broadcast product)
+    y4a, y4b, m4, y5a, y5b, m5f, m5b, m5p = l1_broadcast_inputs()
+    out = {}
+    for key, (ya, yb, mk) in dict(l4=(y4a, y4b, m4), l5f=(y5a, y5b, m5f), l5b=(y5a, y5b, m5b),
+                                  l5p=(y5a, y5b, m5p)).items():
+        a = T(ya).clone().requires_grad_(True)
+        l = mt.LossesUtils.masked_l1(a, T(yb), T(mk), reduction='sum', weight=1.5)
+        l.backward()
+        out[key] = l.detach().numpy()
+        out["g_" + key] = a.grad.numpy()
+        out[key + "_mean"] = mt.LossesUtils.masked_l1(T(ya), T(yb), T(mk), reduction='mean').numpy()
+    save("l1_broadcast", **out)
+
+    # ---- f1: the DFPN.align tail on the flow the DFPN forward returns for a frame size other than 256 x 256:
+    # FlowsUtils.resize_flow(flow_256, (h, w), mode='bilinear') (model_dfpn.py:100-101, utils.py:107-126), then
+    # DFPN.align (model_dfpn.py:125-133), both unmodified.
+    for name, spec in LOWRES_CASES.items():
+        x, m, mt_, flow256 = lowres_inputs(spec)
+        h, w = x.shape[-2:]
+        flow_hw = mt.FlowsUtils.resize_flow(T(flow256), (h, w), mode='bilinear')
+
+        class FakeDFPN4(object):
+            def __call__(self, *a):
+                return None, None, None, flow_hw
+
+        xa, va, vm = DFPN.align(FakeDFPN4(), T(x[:, :, 0] * 0), T(mt_), T(x), T(m))
+        xa = xa.contiguous().numpy()
+        save("lowres_" + name, x_sample=xa.reshape(-1)[::5].copy(), x_total=np.float64(xa.astype(np.float64).sum()),
+             v_aligned=va.contiguous().numpy().astype(np.uint8), v_map=vm.contiguous().numpy().astype(np.uint8),
+             flow_sample=flow_hw.contiguous().numpy().reshape(-1)[::3].copy())
+
+    # ---- a1 + a4 + a5 + a6 in context: the unmodified DFPN._train_val_wrapper (model_dfpn.py:310-394) and
+    # DFPN.compute_loss (:210-293); the DFPN forward and the VGG hand out preset tensors.
+    for name, spec in DFPNLOSS_CASES.items():
+        x, m, y, flow_gt, use, corr, f16, f64, fhw, feats = dfpnloss_inputs(spec)
+        t, r_list = DFPN.get_indexes(x.shape[2])
+        leaves = [T(a).clone().requires_grad_(True) for a in (corr, f16, f64, fhw)]
+
+        class FakeDFPN5(object):
+            def __call__(self, *a):
+                return tuple(leaves)
+
+            def model_vgg(self, inp):
+                return [None, None, None, T(feats)]
+
+        fake = FakeDFPN5()
+        res = DFPN._train_val_wrapper(fake, T(x), T(m), T(y), T(flow_gt), T(use), t, r_list)
+        loss, items = DFPN.compute_loss(fake, *res, t, r_list)
+        grads = torch.autograd.grad(loss, leaves)
+        xs_al = res[4]
+        save("dfpnloss_" + name, loss=loss.detach().numpy(), items=np.array([float(i) for i in items], np.float32),
+             g_corr_sample=grads[0].numpy().reshape(-1)[::101].copy(),
+             g_corr_abs=np.float64(grads[0].abs().double().sum()),
+             g_flow16_abs=np.float64(grads[1].abs().double().sum()),
+             g_flow64=grads[2].numpy(), g_flowhw=grads[3].numpy(),
+             x16_al_sum=np.float64(xs_al[0].double().sum()), x64_al_sum=np.float64(xs_al[1].double().sum()),
+             xhw_al_sum=np.float64(xs_al[2].double().sum()))
+
     # ---- a7: CorrelationVGG.correlation_masked_4d (model_dfpn.py:534-565)
     for name, spec in CORR_CASES.items():
         ft, vt, fr, vr = corr_inputs(spec)
@@ -126,7 +186,8 @@ def main():
             T(ft), None if vt is None else T(vt), T(fr), None if vr is None else T(vr))
         c = c.numpy()
         if c.size > 300000:   # keep the fixture small: strided sample + checksum
-            save("corr_" + name, sample=c.reshape(-1)[::37].copy(), total=np.float64(c.astype(np.float64).sum()),
+            save("corr_" + name, sample=c.reshape(-1)[::spec.get("stride", 37)].copy(),
+                 total=np.float64(c.astype(np.float64).sum()),
                  abs_total=np.float64(np.abs(c).astype(np.float64).sum()))
         else:
             save("corr_" + name, corr=c)

@@ -236,6 +236,13 @@ def test_losses_and_backward(mtb, name):
 
 
 # ---------------------------------------------------------------- a7
+def _corr_tol_check(c, g, spec, tc):
+    if tc:   # TF32 operands, fp32 accumulate: north_star tolerance <= 1e-2 relative; cosine values are <= 1
+        cases.corr_check(c, g, spec, 2e-3)
+    else:
+        cases.corr_check(c, g, spec, 2e-6)
+
+
 @pytest.mark.parametrize("name", sorted(cases.CORR_CASES))
 def test_corr4d(mtb, name):
     from master_thesis_b200 import _lib
@@ -243,15 +250,32 @@ def test_corr4d(mtb, name):
     ft, vt, fr, vr = cases.corr_inputs(spec)
     g = load_golden("corr_" + name)
     c = host(mtb.CorrelationVGG.correlation_masked_4d(dev(ft), dev(vt), dev(fr), dev(vr)))
-    assert c.shape == g["corr"].shape
     tc = _lib.load().mt_corr4d_uses_tensor_cores(spec["c"], spec["h"] * spec["w"])
-    if tc:   # TF32 operands, fp32 accumulate: north_star tolerance <= 1e-2 relative
-        assert np.abs(c - g["corr"]).max() <= 1e-2 * max(np.abs(g["corr"]).max(), 1e-6)
-        assert np.abs(c - g["corr"]).max() <= 2e-3
-    else:
-        assert np.abs(c - g["corr"]).max() <= 2e-6
+    _corr_tol_check(c, g, spec, tc)
     if vt is not None:       # masked rows are exactly zero
         assert np.all(c[0, :, 0, :] == 0.0)
+
+
+@pytest.mark.parametrize("tn", [64, 128, 256])
+@pytest.mark.parametrize("name", ["real_masked", "real_nomask", "mid_masked", "big_masked"])
+def test_corr4d_every_tile_variant(mtb, name, tn):
+    """Every corr_tc_kernel instantiation (64 / 128 / 256 output columns per CTA: different epilogue column
+    offsets, scale tables, stage counts and grids) on small, medium (40 frames) and cfg3-size (128 frames)
+    batches, against the golden vectors of the reference AND the whole volume of the CPU oracle."""
+    spec = cases.CORR_CASES[name]
+    ft, vt, fr, vr = cases.corr_inputs(spec)
+    g = load_golden("corr_" + name)
+    try:
+        _set_tuning("MT_CORR_TN", tn)
+        c = host(mtb.CorrelationVGG.correlation_masked_4d(dev(ft), dev(vt), dev(fr), dev(vr)))
+    finally:
+        _set_tuning("MT_CORR_TN", 0)
+    _corr_tol_check(c, g, spec, True)
+    o = oracle.corr4d(ft, vt, fr, vr)
+    err = np.abs(c - o)
+    assert err.max() <= 2e-3 and err.max() <= 1e-2 * np.abs(o).max()
+    if vt is not None:       # masked rows / columns are exactly zero in every frame
+        assert np.array_equal(c == 0.0, o == 0.0)
 
 
 # ---------------------------------------------------------------- a8
@@ -631,3 +655,233 @@ def test_480x854_davis_shape(mtb):
     xa, va, vm = mtb.dfpn_align_tail(dev(x[:, :, 1:]), dev(m[:, :, 1:]), dev(m[:, :, 0]), dev(flow))
     oxa, ova, ovm = oracle.dfpn_align_tail(x[:, :, 1:], m[:, :, 1:], m[:, :, 0], flow)
     assert np.array_equal(host(xa), oxa) and np.array_equal(host(va), ova) and np.array_equal(host(vm), ovm)
+
+
+# ---------------------------------------------------------------- host-buffer C ABI
+def test_host_buffer_entry_points(mtb):
+    """mt_cpn_align_host / mt_dfpn_align_host: plain host pointers in, host pointers out (H2D, kernel, D2H and
+    the synchronisation inside the call) - what a non-torch caller of the C ABI uses."""
+    import ctypes
+    from master_thesis_b200 import _lib
+    lib = _lib.load()
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)   # noqa: E731
+    for spec, staged in ((cases.CPN_CASES["rand_f4"], False), (STAGED_CASES["rand"], True)):
+        x, m, m_t, theta = cases.cpn_inputs(spec)
+        b, _, f, h, w = x.shape
+        xa, va, vm = np.full_like(x, -7.0), np.full_like(m, -7.0), np.full_like(m, -7.0)
+        rc = lib.mt_cpn_align_host(p(x), p(m), p(m_t), p(theta), p(xa), p(va), p(vm), b, f, h, w)
+        assert rc == 0, _lib.last_error()
+        oxa, ova, ovm = oracle.cpn_align_tail(x, m, m_t, theta=theta)
+        assert np.array_equal(xa, oxa) and np.array_equal(va, ova) and np.array_equal(vm, ovm)
+    for name in ("smooth_f4", "noisy_oob", "f1_odd"):
+        x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES[name])
+        g = load_golden("warp_" + name)
+        b, _, f, h, w = x.shape
+        xa, va, vm = np.full_like(x, -7.0), np.full_like(m, -7.0), np.full_like(m, -7.0)
+        rc = lib.mt_dfpn_align_host(p(x), p(m), p(m_t), p(flow), p(xa), p(va), p(vm), b, f, h, w)
+        assert rc == 0, _lib.last_error()
+        assert np.array_equal(xa, g["x_aligned"]) and np.array_equal(va, g["v_aligned"]) and np.array_equal(vm, g["v_map"])
+    # errors are codes + messages, never exceptions or crashes
+    assert lib.mt_dfpn_align_host(None, p(m), p(m_t), p(flow), p(xa), p(va), p(vm), b, f, h, w) == -1
+    assert "NULL" in _lib.last_error()
+    assert lib.mt_cpn_align_host(p(x), p(m), p(m_t), p(flow), p(xa), p(va), p(vm), 0, f, h, w) == -1
+
+
+# ---------------------------------------------------------------- reductions at the full batch sizes
+def test_fused_losses_at_cfg3_and_cfg5_sizes(mtb):
+    """warp_l1_fwd / bwd at the cfg3 batch (B=32, F=4, 256 x 256: 8.4 M pixels x 3 channels through the
+    per-CTA partials + last-CTA double sum) and chn_l1x3 at the same pixel count, against the CPU oracle."""
+    from master_thesis_b200 import ops, synth
+    b, f, h, w = 32, 4, 256, 256
+    x, m, _ = synth.frames(201, b, f + 1, h, w)
+    xr, vr = np.ascontiguousarray(x[:, :, 1:]), np.ascontiguousarray(1 - m[:, :, 1:])
+    xt, vt = np.ascontiguousarray(x[:, :, 0]), np.ascontiguousarray(1 - m[:, :, 0])
+    flow = synth.dense_flow(202, b, f, h, w, 0.3, True)          # a few percent of the samples out of frame
+    fl = dev(flow).requires_grad_(True)
+    loss = mtb.LossesUtils.alignment_recons(dev(xt), dev(vt), dev(xr), dev(vr), fl)
+    loss.backward()
+    oxa, _ = oracle.align_set(xr, vr, flow)
+    y_hat = np.repeat(xt[:, :, None], f, axis=2)
+    mask = np.repeat(vt[:, :, None], f, axis=2) * (1 - oracle.mask_out(flow))
+    oloss = oracle.masked_l1(y_hat, oxa, mask, reduction="sum")
+    assert float(loss) == pytest.approx(oloss, rel=1e-5)
+    og = oracle.align_set_bwd_flow(xr, flow, oracle.masked_l1_bwd(y_hat, oxa, mask, reduction="sum"))
+    assert np.abs(host(fl.grad) - og).max() <= 2e-5 * np.abs(og).max()
+    del oxa, y_hat, mask, og, fl
+    # the three L1 terms of CHN.compute_loss at the same size
+    r = synth.rng(203)
+    y_target = r.random_sample((b, 3, h, w)).astype(np.float32)
+    v_target = (r.random_sample((b, 1, h, w)) < 0.85).astype(np.float32)
+    y_hat = r.random_sample((b, 3, f, h, w)).astype(np.float32)
+    v_al = (r.random_sample((b, 1, f, h, w)) < 0.8).astype(np.float32)
+    v_map = np.clip(v_al - v_target[:, :, None], 0, 1).astype(np.float32)
+    y_comp = (v_target[:, :, None] * y_target[:, :, None] + (1 - v_target[:, :, None]) * y_hat).astype(np.float32)
+    yh, yc = dev(y_hat).requires_grad_(True), dev(y_comp).requires_grad_(True)
+    terms = ops.chn_l1_terms(dev(y_target), dev(v_target), yh, yc, dev(v_map))
+    sum(terms).backward()
+    ol, og_yh, og_yc = oracle.chn_l1_terms(y_target, v_target, y_hat, y_comp, v_map, grads=True)
+    assert np.allclose([float(t) for t in terms], ol, rtol=1e-5, atol=0)
+    assert np.abs(host(yh.grad) - og_yh).max() <= 1e-6 * np.abs(og_yh).max()
+    assert np.abs(host(yc.grad) - og_yc).max() <= 1e-6 * max(1e-12, np.abs(og_yc).max())
+
+
+# ---------------------------------------------------------------- ADVICE r1
+def test_masked_l1_broadcast_masks(mtb):
+    """masked_l1 with masks smaller than y_hat (the shapes utils.py:139-157 documents): the 'sum' denominator is
+    torch.sum(mask) of the mask as given.  Forward and backward against the unmodified reference's outputs."""
+    y4a, y4b, m4, y5a, y5b, m5f, m5b, m5p = cases.l1_broadcast_inputs()
+    g = load_golden("l1_broadcast")
+    for key, (ya, yb, mk) in dict(l4=(y4a, y4b, m4), l5f=(y5a, y5b, m5f), l5b=(y5a, y5b, m5b),
+                                  l5p=(y5a, y5b, m5p)).items():
+        a = dev(ya).requires_grad_(True)
+        loss = mtb.LossesUtils.masked_l1(a, dev(yb), dev(mk), reduction='sum', weight=1.5)
+        loss.backward()
+        assert float(loss) == pytest.approx(float(g[key]), rel=1e-5), key
+        assert np.abs(host(a.grad) - g["g_" + key]).max() <= 1e-6 * np.abs(g["g_" + key]).max(), key
+        mean = mtb.LossesUtils.masked_l1(dev(ya), dev(yb), dev(mk), reduction='mean')
+        assert float(mean) == pytest.approx(float(g[key + "_mean"]), rel=1e-5), key
+    # mask=None is torch.ones_like(y_hat) (the flow losses of DFPN.compute_loss) without the tensor
+    from master_thesis_b200 import ops
+    ones = ops.masked_l1(dev(y5a), dev(y5b), torch.ones_like(dev(y5a)), reduction='sum')
+    none = ops.masked_l1(dev(y5a), dev(y5b), None, reduction='sum')
+    assert float(ones) == pytest.approx(float(none), rel=1e-6)
+
+
+def test_warp_pack_without_v_map_output(mtb):
+    """mt_warp_pack_fwd with v_map = NULL (allowed by the header): channel 8 of nn_in is still the v_map."""
+    from master_thesis_b200 import ops
+    x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES["f1_odd"])
+    r = cases.synth.rng(6)
+    xt = dev(r.random_sample((x.shape[0], 3) + x.shape[-2:]).astype(np.float32))
+    flags = ops.ALIGN_CORNERS | ops.VIS_FROM_MASK
+    want, vm, _, _ = ops.warp_pack_fwd(dev(x), dev(m), dev(flow), dev(m_t), xt, 1 - dev(m_t), flags)
+    got, none, _, _ = ops.warp_pack_fwd(dev(x), dev(m), dev(flow), dev(m_t), xt, 1 - dev(m_t), flags, want_v_map=False)
+    assert none is None and torch.equal(got, want) and torch.equal(got[:, 8], vm[:, 0].reshape(got[:, 8].shape))
+
+
+def test_staged_warp_with_expanded_inputs(mtb):
+    """Stride-0 (expanded) inputs cannot be encoded in a tensor map: the CPN tail must take the direct kernel
+    and still match the oracle (one target mask / one reference clip shared by the whole batch)."""
+    spec = STAGED_CASES["rand"]
+    x, m, m_t, theta = cases.cpn_inputs(spec)
+    b = x.shape[0]
+    m_t1 = np.ascontiguousarray(m_t[:1])
+    xa, va, vm = mtb.cpn_align_tail(dev(x), dev(m), dev(m_t1).expand(b, -1, -1, -1), dev(theta))
+    oxa, ova, ovm = oracle.cpn_align_tail(x, m, np.repeat(m_t1, b, axis=0), theta=theta)
+    assert np.array_equal(host(xa), oxa) and np.array_equal(host(va), ova) and np.array_equal(host(vm), ovm)
+    x1, m1 = np.ascontiguousarray(x[:1]), np.ascontiguousarray(m[:1])
+    xa, va, vm = mtb.cpn_align_tail(dev(x1).expand(b, -1, -1, -1, -1), dev(m1).expand(b, -1, -1, -1, -1), dev(m_t), dev(theta))
+    oxa, ova, ovm = oracle.cpn_align_tail(np.repeat(x1, b, axis=0), np.repeat(m1, b, axis=0), m_t, theta=theta)
+    assert np.array_equal(host(xa), oxa) and np.array_equal(host(va), ova) and np.array_equal(host(vm), ovm)
+
+
+def test_operators_without_backward_refuse_differentiable_inputs(mtb):
+    from master_thesis_b200 import ops
+    cf, vt, va = cases.cm_inputs(cases.CM_CASES["small"])
+    with pytest.raises(RuntimeError, match="no backward"):
+        ops.cm_match(dev(cf).requires_grad_(True), dev(vt), dev(va))
+    ft, vt_, fr, vr = cases.corr_inputs(cases.CORR_CASES["small_masked"])
+    with pytest.raises(RuntimeError, match="no backward"):
+        ops.corr4d(dev(ft).requires_grad_(True), dev(vt_), dev(fr), dev(vr))
+    x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES["f1_odd"])
+    with pytest.raises(RuntimeError, match="no backward"):
+        mtb.dfpn_align_tail(dev(x), dev(m), dev(m_t), dev(flow).requires_grad_(True))
+    with torch.no_grad():      # the reference's own flows (frozen aligner, no_grad) are unaffected
+        mtb.dfpn_align_tail(dev(x), dev(m), dev(m_t), dev(flow).requires_grad_(True))
+
+
+# ---------------------------------------------------------------- f1: flow resize fused into the warp
+@pytest.mark.parametrize("name", sorted(cases.LOWRES_CASES))
+def test_lowres_flow_align(mtb, name):
+    """The DFPN.align tail fed with the 256 x 256 flow: resize_flow (model_dfpn.py:100-101) happens inside the
+    warp kernel; bit-identical to the unmodified reference (resize, then align) and to the two-step route."""
+    from master_thesis_b200 import ops, plug
+    x, m, m_t, flow256 = cases.lowres_inputs(cases.LOWRES_CASES[name])
+    g = load_golden("lowres_" + name)
+    xa, va, vm = mtb.dfpn_align_tail(dev(x), dev(m), dev(m_t), dev(flow256))
+    cases.lowres_check(host(xa), host(va), host(vm), g)
+    flow_hw = oracle.resize_flow(flow256, x.shape[-2:])
+    xa2, va2, vm2 = mtb.dfpn_align_tail(dev(x), dev(m), dev(m_t), dev(flow_hw))
+    assert torch.equal(xa, xa2) and torch.equal(va, va2) and torch.equal(vm, vm2)
+    # warp + CNN-input pack with the low-resolution flow == pack(warp)
+    r = cases.synth.rng(8)
+    xt = dev(r.random_sample((x.shape[0], 3) + x.shape[-2:]).astype(np.float32))
+    flags = ops.ALIGN_CORNERS | ops.VIS_FROM_MASK
+    nn_in, vm3, xa3, va3 = ops.warp_pack_fwd(dev(x), dev(m), dev(flow256), dev(m_t), xt, 1 - dev(m_t), flags, want_aligned=True)
+    assert torch.equal(nn_in, ops.chn_pack(xt, 1 - dev(m_t), xa, va, vm)) and torch.equal(vm3, vm) and torch.equal(xa3, xa)
+
+    # through the aligner protocol: a patched DFPN hands the kernel its 256 x 256 flow
+    class _DFPNLike(object):
+        align = plug.dfpn_align
+
+        def _mt_b200_flow_256(self, *a):
+            return dev(flow256)
+
+        def __call__(self, *a):
+            raise AssertionError("the full-resolution forward must not be used for frames that are not 256 x 256")
+
+    xa4, va4, vm4 = _DFPNLike().align(dev(x[:, :, 0]), dev(m_t), dev(x), dev(m))
+    assert torch.equal(xa4, xa) and torch.equal(vm4, vm)
+
+
+# ---------------------------------------------------------------- a1 + a4 + a5 + a6 in context
+def _stub_reference_package():
+    """A stand-in ``master_thesis`` package for the GPU box (the reference is absent there): the two helpers the
+    DFPN mirrors look up on it, restated in oracle/torch_port.py (pinned to the reference on the CPU)."""
+    import types
+    from oracle import torch_port as tp
+    stub = types.ModuleType("master_thesis")
+    stub.TransformsUtils = types.SimpleNamespace(resize_set=tp.resize_set)
+    stub.FlowsUtils = types.SimpleNamespace(resize_flow=tp.resize_flow)
+    return stub
+
+
+@pytest.mark.parametrize("name", sorted(cases.DFPNLOSS_CASES))
+def test_dfpn_training_step_mirrors(mtb, name):
+    """The patched DFPN._train_val_wrapper + DFPN.compute_loss (fused warp + mask_out + masked-L1 kernels, no
+    aligned frames in HBM) against the golden outputs of the unmodified reference methods: loss items, and
+    the gradients that reach the flows and the correlation volume."""
+    import sys
+    from master_thesis_b200 import _lib, plug
+    spec = cases.DFPNLOSS_CASES[name]
+    x, m, y, flow_gt, use, corr, f16, f64, fhw, feats = cases.dfpnloss_inputs(spec)
+    g = load_golden("dfpnloss_" + name)
+    n = x.shape[2]
+    t, r_list = n // 2, [i for i in range(n) if i != n // 2]
+    leaves = [dev(a).requires_grad_(True) for a in (corr, f16, f64, fhw)]
+
+    class _DFPNLike(object):
+        def __call__(self, *a):
+            return tuple(leaves)
+
+        def model_vgg(self, inp):
+            return [None, None, None, dev(feats)]
+
+    saved = sys.modules.get("master_thesis")
+    sys.modules["master_thesis"] = _stub_reference_package()
+    try:
+        fake = _DFPNLike()
+        with _lib.record() as plan:
+            res = plug.dfpn_train_val_wrapper(fake, dev(x), dev(m), dev(y), dev(flow_gt), dev(use), t, r_list)
+            loss, items = plug.dfpn_compute_loss(fake, *res, t, r_list)
+            grads = torch.autograd.grad(loss, leaves)
+    finally:
+        if saved is None:
+            del sys.modules["master_thesis"]
+        else:
+            sys.modules["master_thesis"] = saved
+    assert len(res) == 8 and all(isinstance(a, plug.DeferredAlign) for a in res[4])
+    # the hot path of the step is exactly these launches: no align_set, no mask_out, no x_aligned in HBM
+    assert sorted(plan.names()) == sorted(["mt_corr4d_fwd"] + ["mt_masked_l1_fwd"] * 3 + ["mt_warp_l1_fwd"] * 2 +
+                                          ["mt_warp_l1_bwd"] * 2 + ["mt_masked_l1_bwd"] * 3)
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-5)
+    # corr_loss compares a TF32 correlation of the ground truth with the given volume: |d| <= 7e-4 per element
+    assert abs(float(items[0]) - float(g["items"][0])) <= 1e-3
+    assert np.allclose([float(i) for i in items[1:]], g["items"][1:], rtol=1e-5, atol=0)
+    assert np.abs(host(grads[2]) - g["g_flow64"]).max() <= 2e-5 * np.abs(g["g_flow64"]).max()
+    assert np.abs(host(grads[3]) - g["g_flowhw"]).max() <= 2e-5 * np.abs(g["g_flowhw"]).max()
+    assert float(grads[1].abs().double().sum()) == pytest.approx(float(g["g_flow16_abs"]), rel=1e-5)
+    assert float(grads[0].abs().double().sum()) == pytest.approx(float(g["g_corr_abs"]), rel=1e-3)
+    # a consumer that treats an xs_aligned entry as a tensor gets the aligned frames
+    assert float(res[4][2].double().sum()) == pytest.approx(float(g["xhw_al_sum"]), rel=1e-6)
+    assert float(torch.sum(res[4][1]).double()) == pytest.approx(float(g["x64_al_sum"]), rel=1e-5)

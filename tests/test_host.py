@@ -188,10 +188,42 @@ def test_recorded_plan_owns_its_buffers():
     with _lib.record() as plan:
         a = ops._empty(8)
         b = ops._contig(torch.zeros(4, 4).t())    # non-contiguous: a copy is made and kept
-        c = ops._contig(torch.zeros(4))           # already contiguous: nothing to keep
-    refs = [weakref.ref(a), weakref.ref(b)]
-    assert len(plan.keep) == 2 and plan.keep[0] is a and plan.keep[1] is b and c is not None
-    del a, b
+        c = ops._contig(torch.zeros(4))           # already contiguous: kept as it is (a replay reads its pointer)
+    refs = [weakref.ref(a), weakref.ref(b), weakref.ref(c)]
+    assert len(plan.keep) == 3 and plan.keep[0] is a and plan.keep[1] is b and plan.keep[2] is c
+    del a, b, c
     assert all(r() is not None for r in refs)     # the plan keeps them alive
     del plan
     assert all(r() is None for r in refs)
+
+
+def test_masked_l1_layout_of_broadcast_masks():
+    """the (B, C, F, P) decomposition never expands a mask into the 'sum' denominator: broadcast axes
+    become stride 0 and `repeat` counts how often every element of the mask as given is visited."""
+    y4 = torch.zeros(3, 4, 6, 8)
+    (a, b_, m), B, C, F, P, mask_c, repeat = ops._l1_layout(y4, y4, torch.zeros(3, 1, 6, 8))
+    assert (B, C, F, P, mask_c, repeat) == (3, 4, 1, 48, 1, 1) and m[1:] == (48, 0, 0) and a[1:] == (192, 48, 0)
+    y5 = torch.zeros(3, 4, 5, 6, 8)
+    (_, _, m), B, C, F, P, mask_c, repeat = ops._l1_layout(y5, y5, torch.zeros(3, 1, 1, 6, 8))
+    assert (B, C, F, P, mask_c, repeat) == (3, 4, 5, 48, 1, 5) and m[1:] == (48, 0, 0)
+    (_, _, m), *_, mask_c, repeat = ops._l1_layout(y5, y5, torch.zeros(1, 4, 5, 6, 8))
+    assert (mask_c, repeat) == (4, 3) and m[1:] == (0, 240, 48)
+    (_, _, m), *_, mask_c, repeat = ops._l1_layout(y5, y5, torch.zeros(3, 1, 5, 1, 1))
+    assert (mask_c, repeat) == (1, 48) and m[0].shape == (3, 1, 5, 6, 8) and m[1:] == (240, 0, 48)
+    (_, _, m), *_, mask_c, repeat = ops._l1_layout(y5, y5, torch.zeros(3, 4, 5, 6, 8))
+    assert (mask_c, repeat) == (4, 1)
+    # the flows of DFPN.compute_loss: (B, F, h, w, 2) against a mask of ones of the same shape
+    fl = torch.zeros(2, 4, 16, 16, 2)
+    (a, _, m), B, C, F, P, mask_c, repeat = ops._l1_layout(fl, fl, torch.ones_like(fl))
+    assert (B, C, F, P, mask_c, repeat) == (2, 4, 16, 32, 4, 1)
+    with pytest.raises(RuntimeError, match="broadcast"):
+        ops._l1_layout(y5, y5, torch.zeros(3, 2, 5, 6, 8))
+
+
+def test_deferred_align_is_transparent():
+    """An xs_aligned handle of the patched DFPN._train_val_wrapper behaves like the aligned tensor for anyone
+    who touches it (here: materialisation is stubbed, no GPU involved)."""
+    d = plug.DeferredAlign("x", "v", "flow")
+    d._done = (torch.arange(6.0).reshape(2, 3), None)
+    assert d.size() == (2, 3) and float(torch.sum(d)) == 15.0 and float(d.double().sum()) == 15.0
+    assert torch.equal(torch.cat([d, d]), torch.cat([d._done[0], d._done[0]]))

@@ -103,11 +103,76 @@ def test_corr4d(name):
     ft, vt, fr, vr = cases.corr_inputs(cases.CORR_CASES[name])
     g = load_golden("corr_" + name)
     c = oracle.corr4d(ft, vt, fr, vr)
-    ref = g["corr"]
-    assert c.shape == ref.shape
-    assert np.abs(c - ref).max() <= 2e-6          # cosine values are <= 1
+    cases.corr_check(c, g, cases.CORR_CASES[name], 2e-6)      # cosine values are <= 1
     if vt is not None:                            # masked rows / cols are exactly 0
         assert np.all(c[0, :, 0, :] == 0.0)
+
+
+def test_masked_l1_broadcast_masks():
+    """utils.py:166-169 with masks smaller than y_hat: (B,1,H,W) against (B,C,H,W) - the documented shapes -
+    and 5-D masks broadcast over F, over B, and inside the plane."""
+    y4a, y4b, m4, y5a, y5b, m5f, m5b, m5p = cases.l1_broadcast_inputs()
+    g = load_golden("l1_broadcast")
+    for key, (ya, yb, mk) in dict(l4=(y4a, y4b, m4), l5f=(y5a, y5b, m5f), l5b=(y5a, y5b, m5b),
+                                  l5p=(y5a, y5b, m5p)).items():
+        loss, grad = oracle.masked_l1_bcast(ya, yb, mk, "sum", 1.5, grad=True)
+        assert loss == pytest.approx(float(g[key]), rel=1e-5)
+        assert np.abs(grad - g["g_" + key]).max() <= 1e-6 * np.abs(g["g_" + key]).max()
+        assert oracle.masked_l1_bcast(ya, yb, mk, "mean") == pytest.approx(float(g[key + "_mean"]), rel=1e-5)
+
+
+@pytest.mark.parametrize("name", sorted(cases.LOWRES_CASES))
+def test_lowres_flow_align(name):
+    """f1: resize_flow(flow_256, (h, w), 'bilinear') + DFPN.align (model_dfpn.py:100-101, 125-133): the
+    oracle's resize restates ATen's CPU operation order bit for bit, so everything downstream is exact."""
+    x, m, m_t, flow256 = cases.lowres_inputs(cases.LOWRES_CASES[name])
+    g = load_golden("lowres_" + name)
+    flow = oracle.resize_flow(flow256, x.shape[-2:])
+    assert np.array_equal(flow.reshape(-1)[::3], g["flow_sample"])
+    xa, va, vm = oracle.dfpn_align_tail(x, m, m_t, flow)
+    cases.lowres_check(xa, va, vm, g)
+
+
+@pytest.mark.parametrize("name", sorted(cases.DFPNLOSS_CASES))
+def test_dfpn_training_step(name):
+    """DFPN._train_val_wrapper + DFPN.compute_loss (model_dfpn.py:310-394, 210-293): the torch port of the
+    call sequence reproduces the unmodified reference, and the C oracle's a1 / a4 / a5 / a6 chained the same
+    way reproduce the two reconstruction terms and their flow gradients."""
+    import torch
+    from oracle import torch_port as tp
+    T = torch.from_numpy
+    torch.set_num_threads(2)
+    spec = cases.DFPNLOSS_CASES[name]
+    x, m, y, flow_gt, use, corr, f16, f64, fhw, feats = cases.dfpnloss_inputs(spec)
+    g = load_golden("dfpnloss_" + name)
+    n = x.shape[2]
+    t, r_list = n // 2, [i for i in range(n) if i != n // 2]
+    leaves = [T(a).clone().requires_grad_(True) for a in (corr, f16, f64, fhw)]
+    res = tp.dfpn_train_val_wrapper(lambda *a: tuple(leaves), T(x), T(m), T(y), T(flow_gt), T(use), t, r_list)
+    loss, items = tp.dfpn_compute_loss(lambda inp: [None, None, None, T(feats)], *res, t, r_list)
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-6)
+    assert np.allclose([float(i) for i in items], g["items"], rtol=1e-6, atol=0)
+    grads = torch.autograd.grad(loss, leaves)
+    assert np.abs(grads[2].numpy() - g["g_flow64"]).max() <= 1e-6 * np.abs(g["g_flow64"]).max()
+    assert np.abs(grads[3].numpy() - g["g_flowhw"]).max() <= 1e-6 * np.abs(g["g_flowhw"]).max()
+    assert float(grads[0].abs().double().sum()) == pytest.approx(float(g["g_corr_abs"]), rel=1e-6)
+    # the C oracle on the same resized sets
+    xs, vs = res[1], res[2]
+    for i, (fl, gkey) in ((1, (f64, "g_flow64")), (2, (fhw, "g_flowhw"))):
+        xr = xs[i][:, :, r_list].contiguous().numpy()
+        vr = vs[i][:, :, r_list].contiguous().numpy()
+        xa, _ = oracle.align_set(xr, vr, fl)
+        f = len(r_list)
+        y_hat = np.repeat(xs[i][:, :, t].numpy()[:, :, None], f, axis=2)
+        mask = np.repeat(vs[i][:, :, t].numpy()[:, :, None], f, axis=2) * (1 - oracle.mask_out(fl))
+        rec = oracle.masked_l1(y_hat, xa, mask, reduction="sum")
+        assert rec == pytest.approx(float(g["items"][3 + i]), rel=1e-5)
+        gfl = oracle.align_set_bwd_flow(xr, fl, oracle.masked_l1_bwd(y_hat, xa, mask, reduction="sum"))
+        # the golden gradient of this flow also carries its flow-L1 term: remove it (sign / numel per selected item)
+        sel = np.asarray(spec["use"], bool)
+        fgt = res[6][i].contiguous().numpy()
+        gl1 = np.sign(fl - fgt) / (sel.sum() * fl[0].size) * sel[:, None, None, None, None]
+        assert np.abs(gfl + gl1.astype(np.float32) - g[gkey]).max() <= 2e-5 * np.abs(g[gkey]).max()
 
 
 @pytest.mark.parametrize("name", sorted(cases.CM_CASES))
