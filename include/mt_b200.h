@@ -220,6 +220,19 @@ MT_API int mt_chn_fill_step(const float *nn_out, const float *x_t, int64_t xt_sb
                      const float *v_map0, int64_t vm_sb, float *y_comp0, float *m_new, float *x_new,
                      float *inp_per, void *workspace, int B, int64_t P, mt_stream_t stream);
 
+/* mt_chn_fill_step under device-side loop control.  The reference's inpainting loops run
+ * `while ... and inp_per > e` (model_chn.py:112, 163) and therefore read inp_per back to the host after
+ * every step.  Here the step takes the PREVIOUS step's inp_per as a device scalar: while *gate_per > gate_e it
+ * is mt_chn_fill_step; once the loop condition has failed on the device it hands the state through unchanged
+ * (y_comp0 = y_prev, m_new = m_t, x_new = x_t, inp_per = *gate_per), so a host that checks the condition only
+ * every k steps gets bit-identical results.  gate_per == NULL: ungated (the first step of a loop). */
+MT_API int mt_chn_fill_step_gated(const float *nn_out, const float *x_t, int64_t xt_sb, int64_t xt_sc,
+                           const float *v_t, int64_t vt_sb, const float *m_t, int64_t mt_sb,
+                           const float *v_map0, int64_t vm_sb, const float *y_prev,
+                           const float *gate_per, float gate_e,
+                           float *y_comp0, float *m_new, float *x_new,
+                           float *inp_per, void *workspace, int B, int64_t P, mt_stream_t stream);
+
 /* ---- K2  masked cosine correlation on tcgen05 ----------------------------
  * replaces CorrelationVGG.correlation_masked_4d  model_dfpn.py:534-565  (a7)
  * feats_t (B,C,P) contiguous, v_t (B,P) or NULL, feats_r (B,C,F,P) contiguous,
@@ -233,6 +246,19 @@ MT_API int mt_corr4d_fwd(const float *feats_t, const float *v_t, const float *fe
 MT_API int64_t mt_corr4d_workspace_bytes(int B, int C, int F, int P);
 /* 1 if the tcgen05 path serves this shape, 0 if the SIMT fallback does */
 MT_API int mt_corr4d_uses_tensor_cores(int C, int P);
+
+/* The correlation as CorrelationVGG.forward calls it, with its neighbours fused (SURVEY 8f-3,
+ * model_dfpn.py:516-528): the features are taken where the VGG left them - feats_t (B,C,h,w) and
+ * feats_r (B,C,F,h,w) with arbitrary b / c / f strides (the reference's `.reshape(b, ref_n, -1, 16, 16)
+ * .transpose(1, 2)` view of the (B*F, C, h, w) VGG output needs no copy) - and the visibilities come from
+ * the FULL-RESOLUTION masks: v = 1 - m[nearest], F.interpolate(1 - m, (h, w), mode='nearest')
+ * (:521-526), evaluated in the kernel.  m_target (B,1,MH,MW), m_refs (B,1,F,MH,MW) strided with contiguous
+ * planes, or both NULL (no masking, :254).  Tensor-core shapes only (mt_corr4d_uses_tensor_cores). */
+MT_API int mt_corr4d_vgg_fwd(const float *feats_t, int64_t ft_sb, int64_t ft_sc,
+                      const float *m_target, int64_t mt_sb,
+                      const float *feats_r, int64_t fr_sb, int64_t fr_sc, int64_t fr_sf,
+                      const float *m_refs, int64_t mr_sb, int64_t mr_sf, int MH, int MW,
+                      float *out, int B, int C, int F, int h, int w, mt_stream_t stream);
 
 /* ---- K3  CPN context matching --------------------------------------------
  * replaces CM_Module.forward + masked_softmax   model_cpn.py:206-254    (a8)

@@ -182,6 +182,9 @@ struct FillArgs {
     float *y_comp0, *m_new, *x_new, *inp_per;
     void *ws;
     int B; int64_t P; int chunks; int64_t total_chunks;
+    // device-side loop control: the step only happens while the previous step's inp_per > gate_e,
+    // the reference's `while ... and inp_per > e` (model_chn.py:112); otherwise the state passes through
+    const float *gate_per, *y_prev; float gate_e;
 };
 
 template <int VEC>
@@ -189,6 +192,26 @@ __global__ void __launch_bounds__(256) chn_fill_kernel(const FillArgs a) {
     pdl_sync();
     __shared__ float red[32];
     float acc[1] = {0.0f};
+    if (a.gate_per && !(__ldg(a.gate_per) > a.gate_e)) {
+        // the loop has ended on the device: hand the state through unchanged (no reduction, no ticket)
+        for (int64_t ch = blockIdx.x; ch < a.total_chunks; ch += gridDim.x) {
+            const int b = (int)(ch / a.chunks);
+            const int64_t p0 = ((ch - (int64_t)b * a.chunks) * blockDim.x + threadIdx.x) * VEC;
+            if (p0 >= a.P) continue;
+            Vec<VEC> t;
+            t.load_stream(a.m_t + b * a.mt_sb + p0);
+            t.store_stream(a.m_new + (int64_t)b * a.P + p0);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                t.load_stream(a.x_t + b * a.xt_sb + c * a.xt_sc + p0);
+                t.store_stream(a.x_new + ((int64_t)b * 3 + c) * a.P + p0);
+                t.load_stream(a.y_prev + ((int64_t)b * 3 + c) * a.P + p0);
+                t.store_stream(a.y_comp0 + ((int64_t)b * 3 + c) * a.P + p0);
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.inp_per[0] = __ldg(a.gate_per);
+        return;
+    }
     for (int64_t ch = blockIdx.x; ch < a.total_chunks; ch += gridDim.x) {
         const int b = (int)(ch / a.chunks);
         const int64_t p0 = ((ch - (int64_t)b * a.chunks) * blockDim.x + threadIdx.x) * VEC;
@@ -708,19 +731,21 @@ extern "C" int mt_chn_l1x3_bwd(const float *y_hat, int64_t yh_sb, int64_t yh_sc,
     return launch_status("mt_chn_l1x3_bwd");
 }
 
-extern "C" int mt_chn_fill_step(const float *nn_out, const float *x_t, int64_t xt_sb, int64_t xt_sc,
-                                const float *v_t, int64_t vt_sb, const float *m_t, int64_t mt_sb,
-                                const float *v_map0, int64_t vm_sb, float *y_comp0, float *m_new,
-                                float *x_new, float *inp_per, void *workspace, int B, int64_t P,
-                                mt_stream_t stream) {
+static int chn_fill_impl(const float *nn_out, const float *x_t, int64_t xt_sb, int64_t xt_sc,
+                         const float *v_t, int64_t vt_sb, const float *m_t, int64_t mt_sb,
+                         const float *v_map0, int64_t vm_sb, const float *y_prev, const float *gate_per,
+                         float gate_e, float *y_comp0, float *m_new, float *x_new, float *inp_per,
+                         void *workspace, int B, int64_t P, mt_stream_t stream) {
     MT_REQUIRE(nn_out && x_t && v_t && m_t && v_map0 && y_comp0 && m_new && x_new && inp_per && workspace,
                "mt_chn_fill_step: NULL argument");
     MT_REQUIRE(B > 0 && P > 0, "mt_chn_fill_step: bad shape");
+    MT_REQUIRE(!gate_per || y_prev, "mt_chn_fill_step_gated: a gate needs the previous step's y_comp0");
+    MT_REQUIRE(inp_per != gate_per && y_prev != y_comp0, "mt_chn_fill_step_gated: outputs must not alias the gate inputs");
     FillArgs a{nn_out, x_t, xt_sb, xt_sc, v_t, vt_sb, m_t, mt_sb, v_map0, vm_sb, y_comp0, m_new, x_new, inp_per,
-               workspace, B, P, 0, 0};
+               workspace, B, P, 0, 0, gate_per, y_prev, gate_e};
     bool v4 = mult4(P) && aligned16(nn_out) && aligned16(x_t) && aligned16(v_t) && aligned16(m_t) &&
               aligned16(v_map0) && aligned16(y_comp0) && aligned16(m_new) && aligned16(x_new) && mult4(xt_sb) &&
-              mult4(xt_sc) && mult4(vt_sb) && mult4(mt_sb) && mult4(vm_sb);
+              mult4(xt_sc) && mult4(vt_sb) && mult4(mt_sb) && mult4(vm_sb) && aligned16(y_prev);
     const int vec = v4 ? 4 : 1;
     a.chunks = (int)((P + 256 * vec - 1) / (256 * vec));
     a.total_chunks = (int64_t)B * a.chunks;
@@ -728,4 +753,23 @@ extern "C" int mt_chn_fill_step(const float *nn_out, const float *x_t, int64_t x
     if (v4) launch(chn_fill_kernel<4>, nblk, 256, 0, (cudaStream_t)stream, a);
     else launch(chn_fill_kernel<1>, nblk, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_chn_fill_step");
+}
+
+extern "C" int mt_chn_fill_step(const float *nn_out, const float *x_t, int64_t xt_sb, int64_t xt_sc,
+                                const float *v_t, int64_t vt_sb, const float *m_t, int64_t mt_sb,
+                                const float *v_map0, int64_t vm_sb, float *y_comp0, float *m_new,
+                                float *x_new, float *inp_per, void *workspace, int B, int64_t P,
+                                mt_stream_t stream) {
+    return chn_fill_impl(nn_out, x_t, xt_sb, xt_sc, v_t, vt_sb, m_t, mt_sb, v_map0, vm_sb, nullptr, nullptr, 0.0f,
+                         y_comp0, m_new, x_new, inp_per, workspace, B, P, stream);
+}
+
+extern "C" int mt_chn_fill_step_gated(const float *nn_out, const float *x_t, int64_t xt_sb, int64_t xt_sc,
+                                      const float *v_t, int64_t vt_sb, const float *m_t, int64_t mt_sb,
+                                      const float *v_map0, int64_t vm_sb, const float *y_prev,
+                                      const float *gate_per, float gate_e, float *y_comp0, float *m_new,
+                                      float *x_new, float *inp_per, void *workspace, int B, int64_t P,
+                                      mt_stream_t stream) {
+    return chn_fill_impl(nn_out, x_t, xt_sb, xt_sc, v_t, vt_sb, m_t, mt_sb, v_map0, vm_sb, y_prev, gate_per, gate_e,
+                         y_comp0, m_new, x_new, inp_per, workspace, B, P, stream);
 }

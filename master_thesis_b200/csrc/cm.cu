@@ -21,12 +21,15 @@
 // Reductions are two-level and fixed-order (deterministic).  History (profiles/):
 // a single-CTA-per-sample reduction kernel cost 14 us (latency chain); recomputing the per-PIXEL
 // softmax in every pass-2 CTA cost ~10 channels' worth of instructions per CTA; a per-sample
-// ticket tail in pass 1 doubled pass 1 (fence + atomic + barrier per CTA); per-group launches
-// (MT_CM_CHUNK) and a persistent pipelined single launch (K3p below) are slower than this.
+// ticket tail in pass 1 doubled pass 1 (fence + atomic + barrier per CTA); per-group launches and a
+// persistent software-pipelined single launch that re-read c_feats from L2 ("K3p", round 1: parity-green,
+// 1.3-1.4x slower; removed in round 2, design and measurements in profiles/r1_experiments.md) lost to this.
+// The second DRAM read of c_feats is what L2 capacity allows: at B = 8 the features are 84 MB, a streamed
+// buffer keeps ~45-60 MB resident in the 126 MB L2 (tools/l2_probe.py), and pass 2 already walks the samples
+// in reverse to take exactly that tail from L2.
 #include <math.h>
 
 #include "mt_common.cuh"
-#include "mt_tma.cuh"
 
 namespace mt {
 namespace {
@@ -34,23 +37,6 @@ namespace {
 constexpr int kSimChannels = 4;   // default channels per CTA slab in pass 1 (swept on B200: profiles/)
 constexpr int kCopyChannels = 4;  // default channels per CTA slab in pass 2 (template CC)
 constexpr int kMaxRefs = 8;
-
-// exact unsigned division by a runtime constant (round-up method): q = x / d for every 32-bit x
-struct FastDiv { uint32_t d, m, s1, s2; };
-static inline FastDiv make_fastdiv(uint32_t d) {
-    FastDiv f;
-    uint32_t l = 0;
-    while ((1ull << l) < d) ++l;
-    f.d = d;
-    f.m = (uint32_t)((((1ull << l) - d) << 32) / d + 1);
-    f.s1 = l < 1 ? l : 1;
-    f.s2 = l > 0 ? l - 1 : 0;
-    return f;
-}
-__device__ __forceinline__ uint32_t fast_div(uint32_t x, const FastDiv &f) {
-    const uint32_t t = __umulhi(f.m, x);
-    return (t + ((x - t) >> f.s1)) >> f.s2;
-}
 
 struct CmArgs {
     const float *c_feats, *v_t, *v_al;
@@ -60,15 +46,8 @@ struct CmArgs {
     float *gs;        // workspace: (B, R)  (exported for tests)
     float *weights;   // workspace: (B, R, P) softmax weights over references
     int B, C, f, h, w, H, W, P, R, nparts, chunks, sim_ch, b_off;
-    // fused path: per-sample count of finished similarity items (zeroed by cm_masks), items per
-    // sample and pass, and the distance (in samples) between pass 1 and pass 2 of the same sample
-    unsigned int *count, *flag;  // (B) finished S items / table published
     unsigned char *pmask;        // (B, P) bit 0: vt', bit r + 1: vr' of reference r
-    float *table;                // (B, 2^R, R + 1) softmax weights and c_mask per mask pattern
-    int n_items, lag, copy_reverse;
-    int workers, rounds, head;  // schedule of the pipelined kernel (cm_decode)
-    int n_copy, b_sim, n_sim;   // cm_copy_sim_kernel: copies samples [b_off, +n_copy), similarities of [b_sim, +n_sim)
-    FastDiv dv_items, dv_chunks;
+    int copy_reverse;
 };
 
 // F.interpolate(bilinear, align_corners=False) source index (UpSample.h)
@@ -83,16 +62,10 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
 }
 
 // pass 0: grid (ceil(P / 256), B); thread = one low-resolution pixel, all f masks.
-// Also resets the per-sample state of the pipelined kernel (count, flag, table = NaN).
 __global__ void __launch_bounds__(256) cm_masks_kernel(const CmArgs a) {
     pdl_sync();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
-    if (blockIdx.x == 0) {
-        const int tabf = (1 << a.R) * (a.R + 1);
-        for (int q = threadIdx.x; q < tabf; q += blockDim.x) a.table[(int64_t)b * tabf + q] = __int_as_float(0x7fc00000);
-        if (threadIdx.x == 0) { a.count[b] = 0u; a.flag[b] = 0u; }
-    }
     if (p >= a.P) return;
     const int y = p / a.w, x = p - y * a.w;
     int y0, y1, x0, x1;
@@ -477,657 +450,24 @@ __global__ void __launch_bounds__(256, 2) cm_copy2_kernel(const CmArgs a) {
     }
 }
 
-// pass 2 of one group of samples and pass 1 of the NEXT group in the same launch (slabs interleaved
-// along blockIdx.y): the copy re-reads its group from L2, where pass 1 left it one launch ago, while
-// the similarity of the next group streams from HBM - so c_feats crosses HBM once, without any
-// synchronisation inside a kernel.  grid (chunks, 2 * ceil(C / CH), max(n_copy, n_sim)).
-template <int R, int CH>
-__global__ void __launch_bounds__(256) cm_copy_sim_kernel(const CmArgs a) {
-    pdl_sync();
-    __shared__ float red[2 * R * 32];
-    const int slab = (int)blockIdx.y >> 1, z = (int)blockIdx.z;
-    if (blockIdx.y & 1) {
-        if (z < a.n_sim) cm_sim_body<R, CH, false>(a, slab, a.b_sim + z, red);
-    } else {
-        if (z < a.n_copy) cm_copy_body<R, CH, false>(a, slab, a.b_off + z);
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// K3p (EXPERIMENTAL, MT_CM_FUSED=1, off by default): pass 1 + 1b + 2 as ONE persistent,
-// software-pipelined launch in which pass 2 reads c_feats from L2.  Parity-green, but 1.3-1.4x slower
-// than the three launches on B200 (55 vs 40 us at B=8, 175 vs 132 us at B=32); kept as the record of that design
-// (measurements and the reasons: profiles/r1_experiments.md).
-//
-// The two passes over c_feats are inherent (the similarity is a global reduction over the sample),
-// but as separate launches over the whole batch the second pass misses L2 (ncu: 4.6 % hit rate at
-// B=8, 84 MB) and the op moves 84+10+84+34 MB through HBM for 128 MB algorithmic.  Here one CTA per SM
-// (two groups of 8 compute warps = two workers, a publisher warp, a producer warp) walks a common
-// round schedule (cm_decode): S rounds (similarity partial of a 1024-pixel x CH-channel slab) run
-// `head` rounds ahead of the C rounds (weighted copy of such a slab), so a sample (10.5 MB) is
-// re-read from L2 a few rounds after it was streamed from HBM.
-//   * Memory pipeline: the producer warp fetches the operands of the next NST items with
-//     cp.async.bulk (4 KB per slab and frame) into a shared-memory ring; slot layout = 16 B per
-//     thread, so the compute warps read conflict-free LDS.128; full / empty mbarriers per stage.
-//   * Masks travel as one byte per pixel (bit 0 target, bit r+1 reference r; cm_masks_kernel).
-//   * S items hand their 2R sums to the publisher warp through a shared-memory mailbox; the
-//     publisher stores the partial, fences and bumps the per-sample counter (off the compute warps'
-//     path: with warp 0 publishing, every item cost 3-5 us).  The publisher that finishes the LAST
-//     partial of a sample folds them in fixed order in double, evaluates the masked softmax once per
-//     MASK PATTERN (vr' is 0/1: 2^R distinct weight vectors per sample; the same operations in the
-//     same order as cm_weights_kernel: same bits) and publishes that table + a flag.
-//   * C items read the table one item ahead through a register; cm_masks_kernel cleared it to NaN, so
-//     a copy without NaN is complete (every word is written once); otherwise the group waits for the
-//     sample's flag (acquire) and reloads.  Weights per pixel are a lookup by the mask byte.
-// Progress: every S item of a sample precedes every C item of it in the common round sequence (the
-// host picks `head` accordingly), S items never wait, and the grid is one resident wave.  A wait that
-// does not end within 2 s traps (the launch fails loudly instead of hanging).
-__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(unsigned int *p, unsigned int v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-constexpr int kMailbox = 16;
-
-template <int R>
-constexpr int cm_table_floats() { return (1 << R) * (R + 1); }  // per pattern: R weights, c_mask
-
-struct CmItem { int b, idx, chunk, slab; bool copy, valid; };
-
-#ifdef MT_DEV_PROBES
-// developer probe (tools/dbg_cm.py): per CTA [0] kernel ns, [1] ns waiting for cp.async data, [2] ns in S
-// items, [3] ns in C items, [4] C items through the slow path, [5] items, [6] publisher busy ns, [7] publishes
-__device__ unsigned long long g_cm_probe[256 * 8];
-__device__ unsigned long long g_cm_probe2[2048];  // [0] slow items whose flag was already set, [1] ns in the slow path, [2] ns in decode
-#define CM_PROBE(...) __VA_ARGS__
-#else
-#define CM_PROBE(...)
-#endif
-
-// Schedule.  The S items of all samples form one stream (position u = b * n_items + idx), the C items
-// another.  Every worker (a compute group of a CTA; NW workers in all) runs the SAME sequence of
-// rounds and takes position round * NW + worker of the round's stream: `head` S rounds, then C and S
-// rounds alternating, then the remaining C rounds.  Every worker therefore alternates between reads
-// from HBM (S) and reads from L2 + writes (C) - a first version that interleaved the two streams in
-// one list gave the even CTAs only S items and the odd ones only C items (2x slower) - and every S
-// item of a sample is earlier in every worker's sequence than any C item of that sample (the host
-// picks `head` accordingly), which is what makes waiting inside a C item safe.
-__device__ __forceinline__ CmItem cm_decode(const CmArgs &a, int worker, int r) {
-    CmItem d;
-    const int R1 = a.rounds;  // rounds per stream
-    int sr;                   // round within the stream
-    if (r < a.head) { d.copy = false; sr = r; }
-    else {
-        const int t = r - a.head, pairs = R1 - a.head;  // alternating part: C first
-        if (t < 2 * pairs) { d.copy = (t & 1) == 0; sr = d.copy ? (t >> 1) : a.head + (t >> 1); }
-        else { d.copy = true; sr = pairs + (t - 2 * pairs); }
-    }
-    const int u = sr * a.workers + worker;
-    d.valid = r < 2 * R1 && u < a.B * a.n_items;
-    d.b = 0; d.idx = 0; d.chunk = 0; d.slab = 0;
-    if (d.valid) {
-        d.b = (int)fast_div((uint32_t)u, a.dv_items);
-        d.idx = u - d.b * a.n_items;
-        d.slab = (int)fast_div((uint32_t)d.idx, a.dv_chunks);
-        d.chunk = d.idx - d.slab * a.chunks;
-    }
-    return d;
-}
-// a worker is done after round 2 * rounds - 1; rounds whose position is past the end of the stream are empty
-__device__ __forceinline__ bool cm_done(const CmArgs &a, int r) { return r >= 2 * a.rounds; }
-
-// executed by ONE warp: partials of sample b -> gs -> softmax table -> flag
-template <int R>
-__device__ __forceinline__ void cm_publish_table(const CmArgs &a, int b) {
-    constexpr int G2 = 2 * R, TABF = cm_table_floats<R>();
-    const int lane = threadIdx.x & 31;
-    // lane l adds rows l, l + 32, ... in increasing order (4 rows of loads in flight), then an xor tree
-    // over the lanes: fixed order, double
-    double v[G2];
-#pragma unroll
-    for (int r = 0; r < G2; ++r) v[r] = 0.0;
-    const float *rows = a.partials + (int64_t)b * a.nparts * G2;
-    for (int i0 = lane; i0 < a.nparts; i0 += 4 * 32) {
-        float t[4][G2];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + 32 * u;
-#pragma unroll
-            for (int r = 0; r < G2; ++r) t[u][r] = i < a.nparts ? __ldcg(rows + (int64_t)i * G2 + r) : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int r = 0; r < G2; ++r) v[r] += (double)t[u][r];
-    }
-#pragma unroll
-    for (int r = 0; r < G2; ++r) v[r] = warp_sum(v[r]);
-    float gs[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const double d = v[r], vs = v[R + r];
-        const bool zero = vs < 1e-4;                                       // :222
-        const float v_sum = (float)vs + (zero ? 1.0f : 0.0f);              // :223
-        const float g0 = (float)d / (v_sum * (float)a.C);                  // :225-227
-        gs[r] = zero ? 0.0f : g0;                                          // :228
-        if (lane == 0) a.gs[(int64_t)b * R + r] = gs[r];
-    }
-    float *tab = a.table + (int64_t)b * TABF;
-    for (int t = lane; t < (1 << R); t += 32) {
-        // masked_softmax over the references for mask pattern t                 :245-254
-        float vr[R], wv[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) vr[r] = ((t >> r) & 1) ? 1.0f : 0.0f;
-        float mx = -INFINITY;
-#pragma unroll
-        for (int r = 0; r < R; ++r) mx = fmaxf(mx, __fmul_rn(gs[r], vr[r]));
-        float sum = 0.0f;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            wv[r] = __fmul_rn(expf(__fsub_rn(__fmul_rn(gs[r], vr[r]), mx)), vr[r]);
-            sum = __fadd_rn(sum, wv[r]);
-        }
-        if (sum < 1e-4f) sum = __fadd_rn(sum, 1.0f);
-        float cm = 0.0f;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            wv[r] = __fdiv_rn(wv[r], sum);
-            cm = __fadd_rn(cm, __fmul_rn(wv[r], vr[r]));                          // :240
-            __stcg(tab + t * (R + 1) + r, wv[r]);
-        }
-        __stcg(tab + t * (R + 1) + R, __fsub_rn(1.0f, cm));                       // :241
-    }
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) st_release(a.flag + b, 1u);
-    CM_PROBE(if (lane == 0 && b < 64) g_cm_probe2[1024 + b] = global_ns();)
-}
-
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-template <int R, int CH>
-constexpr int cm_stage_bytes() { return CH * (R + 1) * 4096 + 1024; }  // CH x f slabs of 1024 px + 1024 mask bytes
-
-// 8 values per lane -> lane l holds the warp total of value (l >> 2) & 7: 9 shuffles instead of 40
-__device__ __forceinline__ float warp_sum8(const float (&v)[8]) {
-    const int lane = threadIdx.x & 31;
-    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
-    float w[4], x[2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = h4 ? v[i] : v[i + 4], keep = h4 ? v[i + 4] : v[i];
-        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = h3 ? w[i] : w[i + 2], keep = h3 ? w[i + 2] : w[i];
-        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    const float send = h2 ? x[0] : x[1], keep = h2 ? x[1] : x[0];
-    float y = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    y += __shfl_xor_sync(0xffffffffu, y, 2);
-    y += __shfl_xor_sync(0xffffffffu, y, 1);
-    return y;
-}
-__device__ __forceinline__ void bar_group(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ bool bar_group_or(int id, bool p) {
-    int r;
-    asm volatile(
-        "{\n\t.reg .pred pin, pout;\n\tsetp.ne.u32 pin, %2, 0;\n\tbar.red.or.pred pout, %1, 256, pin;\n\t"
-        "selp.u32 %0, 1, 0, pout;\n\t}"
-        : "=r"(r) : "r"(id), "r"((int)p) : "memory");
-    return r != 0;
-}
-
-// NG groups of 8 compute warps (each group works on its own item: 4 warps per scheduler hide the
-// LDS / FP latencies that 2 could not), one publisher warp, one producer warp.
-template <int R, int CH, int NST, int NG>
-__global__ void __launch_bounds__(NG * 256 + 64, 1) cm_pipe_kernel(const __grid_constant__ CUtensorMap map_c,
-                                                                   const __grid_constant__ CmArgs a) {
-    constexpr int TABF = cm_table_floats<R>();
-    constexpr int kStageBytes = cm_stage_bytes<R, CH>();
-    constexpr int G2 = 2 * R;
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    float *tabs = reinterpret_cast<float *>(smem_raw + NST * kStageBytes);  // NG x 2 tables
-    __shared__ float red[NG][2][G2 * 8];
-    __shared__ uint64_t full[NST], empty[NST];
-    // S items hand their sums to the publisher warp through these mailboxes: the global publication
-    // (store, fence, returning atomic: 2-3 us of latency) is off the compute warps' path.  With the
-    // publication done by warp 0 itself every S item cost 3-5 us (the next item's barrier waited).
-    __shared__ float mbox[NG][kMailbox][G2];
-    __shared__ int mbox_b[NG][kMailbox], mbox_idx[NG][kMailbox];
-    __shared__ volatile int mb_ready[NG], mb_done[NG], mb_fin[NG];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) {
-        for (int g = 0; g < NG; ++g) { mb_ready[g] = 0; mb_done[g] = 0; mb_fin[g] = 0; }
-        for (int s = 0; s < NST; ++s) {
-            mbar_init(smem_u32(full + s), 1);
-            mbar_init(smem_u32(empty + s), 8);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    pdl_sync();
-    CM_PROBE(unsigned long long pr_t0 = global_ns(); unsigned long long pr_wait = 0, pr_s = 0, pr_c = 0, pr_slow = 0, pr_n = 0;)
-    CM_PROBE(if (tid == 0 && blockIdx.x < 256) { g_cm_probe2[blockIdx.x * 8 + 0] = 0; g_cm_probe2[blockIdx.x * 8 + 1] = 0; })
-    CM_PROBE(if (tid == 0 && blockIdx.x == 0) g_cm_probe2[1200] = pr_t0;)
-    if (wid == 8 * NG + 1) {
-        // ===================== producer: bulk copies of the operands, NST items ahead =====================
-        if (lane == 0) {
-            int n = 0;  // valid items of this CTA so far (stage ring position)
-            for (int r = 0; !cm_done(a, r); ++r)
-            for (int g = 0; g < NG; ++g) {
-                const CmItem d = cm_decode(a, blockIdx.x + g * gridDim.x, r);
-                if (!d.valid) continue;
-                const int s = n % NST;
-                const uint32_t ph = (uint32_t)(n / NST) & 1u;
-                ++n;
-                mbar_wait(smem_u32(empty + s), ph ^ 1u);
-                const int c0 = d.slab * CH;
-                const int px = min(1024, a.P - d.chunk * 1024);
-                const uint32_t fb = smem_u32(full + s), dst = smem_u32(smem_raw + s * kStageBytes);
-                // ONE tensor load for the CH x (R + 1) slabs of 1024 pixels: c_feats as (256 px, P / 256, B*C*f
-                // rows), box (256, 4, CH * (R + 1)).  As 4 KB bulk copies (one per slab and frame) an item took
-                // ~3 us to arrive: ~0.3 us per copy, issued one after the other.  Rows past the tensor and
-                // pixels past P are zero-filled and count towards the transaction bytes.
-                mbar_expect_tx(fb, (uint32_t)(CH * (R + 1) * 4096 + px));
-                tma_load_3d(dst, &map_c, fb, 0, d.chunk * 4, (d.b * a.C + c0) * a.f);
-                bulk_load(dst + CH * (R + 1) * 4096, a.pmask + (int64_t)d.b * a.P + d.chunk * 1024, (uint32_t)px, fb);
-            }
-        }
-        return;
-    }
-    if (wid == 8 * NG) {
-        // ===================== publisher warp =====================
-        // Batched: every ready mailbox entry of both groups is taken by its own lane - partial rows
-        // stored, ONE fence, then the counter atomics side by side.  One entry at a time cost 1.4 us each
-        // (fence + returning atomic), more than the compute warps need to produce one: the mailboxes ran
-        // full and a sample's table appeared 20+ us after its last item.
-        static_assert(NG * kMailbox <= 32, "one lane per mailbox entry");
-        int done[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) done[g] = 0;
-        CM_PROBE(unsigned long long pb_busy = 0, pb_n = 0;)
-        for (;;) {
-            int rdy[NG], total = 0;
-            bool fin = true;
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                rdy[g] = mb_ready[g];
-                total += rdy[g] - done[g];
-                fin = fin && mb_fin[g] && mb_ready[g] == done[g];
-            }
-            if (total == 0) {
-                if (fin) break;
-                __nanosleep(100);
-                continue;
-            }
-            __threadfence_block();
-            CM_PROBE(unsigned long long pb_t = global_ns();)
-            // lane e < total: entry e, group by group
-            int eg = -1, eslot = 0, e = lane;
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const int cnt = rdy[g] - done[g];
-                if (eg < 0 && e < cnt) { eg = g; eslot = (done[g] + e) % kMailbox; }
-                if (eg < 0) e -= cnt;
-            }
-            int b = 0;
-            if (eg >= 0) {
-                b = mbox_b[eg][eslot];
-                float *o = a.partials + ((int64_t)b * a.nparts + mbox_idx[eg][eslot]) * G2;
-#pragma unroll
-                for (int r = 0; r < G2; ++r) __stcg(o + r, mbox[eg][eslot][r]);
-            }
-            __threadfence();  // release: the partials before the counts
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-                for (int g = 0; g < NG; ++g) mb_done[g] = rdy[g];  // the mailbox slots are free again
-            }
-            bool last = false;
-            if (eg >= 0) last = atomicAdd(a.count + b, 1u) == (unsigned int)a.n_items - 1u;
-            unsigned int lm = __ballot_sync(0xffffffffu, last);
-            while (lm) {
-                const int src = __ffs(lm) - 1;
-                lm &= lm - 1;
-                const int bl = __shfl_sync(0xffffffffu, b, src);
-                __threadfence();  // acquire: every other item's partials
-                cm_publish_table<R>(a, bl);
-            }
-#pragma unroll
-            for (int g = 0; g < NG; ++g) done[g] = rdy[g];
-            CM_PROBE(pb_busy += global_ns() - pb_t; pb_n += total;)
-        }
-        CM_PROBE(if (lane == 0 && blockIdx.x < 256) { g_cm_probe[blockIdx.x * 8 + 6] = pb_busy; g_cm_probe[blockIdx.x * 8 + 7] = pb_n; })
-        return;
-    }
-
-    // ===================== compute warps =====================
-    const int grp = wid >> 3, lt = tid & 255, lw = wid & 7, bar_id = 1 + grp;
-    float *gtabs = tabs + grp * 2 * TABF;
-    // the softmax table of the group's NEXT item travels through a register (one 16 B chunk per thread)
-    float4 tnext = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int me = blockIdx.x + grp * gridDim.x;
-    for (int r = 0; !cm_done(a, r); ++r) {  // table of the group's first C item, if that is its first item
-        const CmItem d0 = cm_decode(a, me, r);
-        if (!d0.valid) continue;
-        if (d0.copy && lt < TABF / 4) {
-            tnext = __ldcg(reinterpret_cast<const float4 *>(a.table + (int64_t)d0.b * TABF) + lt);
-            reinterpret_cast<float4 *>(gtabs)[lt] = tnext;
-        }
-        break;
-    }
-    int n_sim = 0, i = 0, n = 0;  // S items / items of the group, valid items of the CTA (stage ring position)
-    for (int r = 0; !cm_done(a, r); ++r)
-    for (int g = 0; g < NG; ++g) {
-        const CmItem d = cm_decode(a, blockIdx.x + g * gridDim.x, r);
-        if (!d.valid) continue;
-        const int s = n % NST;
-        const uint32_t full_ph = (uint32_t)(n / NST) & 1u;
-        ++n;
-        if (g != grp) continue;
-        const CmItem dn = cm_decode(a, me, r + 1);
-        const bool tn = dn.valid && dn.copy && lt < TABF / 4;
-        if (tn) tnext = __ldcg(reinterpret_cast<const float4 *>(a.table + (int64_t)dn.b * TABF) + lt);
-        CM_PROBE(unsigned long long pr_a = global_ns();)
-        mbar_wait(smem_u32(full + s), full_ph);
-        CM_PROBE(unsigned long long pr_b = global_ns(); pr_wait += pr_b - pr_a; ++pr_n;)
-        const int p0 = (d.chunk * 256 + lt) * 4, c0 = d.slab * CH;
-        const bool live = p0 < a.P;
-        const uint8_t *stb = smem_raw + s * kStageBytes;
-        const float4 *st = reinterpret_cast<const float4 *>(stb);
-        const uint32_t mw = live ? reinterpret_cast<const uint32_t *>(stb + CH * (R + 1) * 4096)[lt] : 0u;
-        if (!d.copy) {
-            // ---------------- S item: partial similarity ----------------
-            float acc[G2];
-#pragma unroll
-            for (int r = 0; r < G2; ++r) acc[r] = 0.0f;
-            if (live) {
-                float4 vm[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {  // vt' * vr'                  :220
-                    const uint32_t m = mw & (mw >> (r + 1)) & 0x01010101u;
-                    vm[r] = make_float4((float)(m & 1u), (float)((m >> 8) & 1u), (float)((m >> 16) & 1u),
-                                        (float)((m >> 24) & 1u));
-                    if (d.slab == 0) acc[R + r] = (vm[r].x + vm[r].y) + (vm[r].z + vm[r].w);  // :221
-                }
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    if (c0 + k < a.C) {
-                        const float4 ct = st[(k * (R + 1)) * 256 + lt];
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {  // vmap * c_t * c_r            :226
-                            const float4 cr = st[(k * (R + 1) + r + 1) * 256 + lt];
-                            acc[r] += vm[r].x * ct.x * cr.x;
-                            acc[r] += vm[r].y * ct.y * cr.y;
-                            acc[r] += vm[r].z * ct.z * cr.z;
-                            acc[r] += vm[r].w * ct.w * cr.w;
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(empty + s));  // the stage may be refilled
-            // CTA-group sum of the 2R values, fixed order; double-buffered scratch: warp 0 of the group
-            // reads while the others move on to their next item
-            float *rd = red[grp][n_sim & 1];
-            const int slot = n_sim % kMailbox;
-            if constexpr (G2 == 8) {
-                const float y = warp_sum8(acc);
-                if ((lane & 3) == 0) rd[(lane >> 2) * 8 + lw] = y;
-                bar_group(bar_id);
-                if (lw == 0) {
-                    float t = rd[(lane >> 2) * 8 + 2 * (lane & 3)] + rd[(lane >> 2) * 8 + 2 * (lane & 3) + 1];
-                    t += __shfl_xor_sync(0xffffffffu, t, 1);
-                    t += __shfl_xor_sync(0xffffffffu, t, 2);
-                    if (lane == 0) while (n_sim - mb_done[grp] >= kMailbox) __nanosleep(100);
-                    __syncwarp();
-                    if ((lane & 3) == 0) mbox[grp][slot][lane >> 2] = t;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < G2; ++k) {
-                    acc[k] = warp_sum(acc[k]);
-                    if (lane == 0) rd[k * 8 + lw] = acc[k];
-                }
-                bar_group(bar_id);
-                if (lw == 0) {
-                    if (lane == 0) while (n_sim - mb_done[grp] >= kMailbox) __nanosleep(100);
-                    __syncwarp();
-                    if (lane < G2) {
-                        float t = 0.0f;
-#pragma unroll
-                        for (int w8 = 0; w8 < 8; ++w8) t += rd[lane * 8 + w8];
-                        mbox[grp][slot][lane] = t;
-                    }
-                }
-            }
-            if (lw == 0) {
-                __syncwarp();
-                if (lane == 0) {
-                    mbox_b[grp][slot] = d.b;
-                    mbox_idx[grp][slot] = d.idx;
-                    __threadfence_block();
-                    mb_ready[grp] = n_sim + 1;
-                }
-            }
-            ++n_sim;
-        } else {
-            // ---------------- C item: cat[c_t, sum_r c_r * w_r] ----------------
-            float *tb = gtabs + (i & 1) * TABF;
-            bool bad = false;
-            if (lt < TABF / 4) {  // the chunk this thread fetched one item ago
-                const float4 t4 = reinterpret_cast<const float4 *>(tb)[lt];
-                bad = isnan(t4.x) || isnan(t4.y) || isnan(t4.z) || isnan(t4.w);
-            }
-            if (bar_group_or(bar_id, bad)) {  // also: the table chunks of the other threads are visible
-                CM_PROBE(++pr_slow; unsigned long long sl_t = global_ns();
-                         if (lt == 0 && d.b < 64) atomicMin(&g_cm_probe2[1088 + d.b], sl_t);)
-                if (lt == 0) {
-                    CM_PROBE(if (ld_acquire(a.flag + d.b) != 0u && blockIdx.x < 256) g_cm_probe2[blockIdx.x * 8 + 0] += 1;)
-                    if (ld_acquire(a.flag + d.b) == 0u) {
-                        const unsigned long long t0 = global_ns();
-                        while (ld_acquire(a.flag + d.b) == 0u) {
-                            __nanosleep(64);
-                            if (global_ns() - t0 > 2000000000ull) __trap();
-                        }
-                    }
-                }
-                bar_group(bar_id);
-                for (int q = lt; q < TABF; q += 256) tb[q] = __ldcg(a.table + (int64_t)d.b * TABF + q);
-                bar_group(bar_id);
-                CM_PROBE(if (tid == 0 && blockIdx.x < 256) g_cm_probe2[blockIdx.x * 8 + 1] += global_ns() - sl_t;)
-            }
-            if (live) {
-                int pat[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pat[j] = (int)((mw >> (8 * j + 1)) & ((1u << R) - 1u)) * (R + 1);
-                float *ob = a.out + (int64_t)d.b * (2 * a.C + 1) * a.P + p0;
-                if (d.slab == 0) {
-                    const float4 c4 = make_float4(tb[pat[0] + R], tb[pat[1] + R], tb[pat[2] + R], tb[pat[3] + R]);
-                    st_stream4(ob + (int64_t)(2 * a.C) * a.P, c4);
-                    st_stream4(a.c_mask + (int64_t)d.b * a.P + p0, c4);
-                }
-                float4 wg[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) wg[r] = make_float4(tb[pat[0] + r], tb[pat[1] + r], tb[pat[2] + r], tb[pat[3] + r]);
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const int c = c0 + k;
-                    if (c >= a.C) break;
-                    float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {  // sum_r c_r * w_r, sequential over r    :238
-                        const float4 cr = st[(k * (R + 1) + r + 1) * 256 + lt];
-                        o.x = __fadd_rn(o.x, __fmul_rn(cr.x, wg[r].x));
-                        o.y = __fadd_rn(o.y, __fmul_rn(cr.y, wg[r].y));
-                        o.z = __fadd_rn(o.z, __fmul_rn(cr.z, wg[r].z));
-                        o.w = __fadd_rn(o.w, __fmul_rn(cr.w, wg[r].w));
-                    }
-                    st_stream4(ob + (int64_t)c * a.P, st[(k * (R + 1)) * 256 + lt]);  // cat[c_t, ...]  :243
-                    st_stream4(ob + (int64_t)(a.C + c) * a.P, o);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(empty + s));  // the stage may be refilled
-        }
-        // table of the group's next item: slot (i + 1) & 1 was last read by item i - 1 of the group, and
-        // every thread of the group has passed the barrier of item i
-        if (tn) reinterpret_cast<float4 *>(gtabs + ((i + 1) & 1) * TABF)[lt] = tnext;
-        CM_PROBE(if (d.copy) pr_c += global_ns() - pr_b; else pr_s += global_ns() - pr_b;)
-        ++i;
-    }
-    CM_PROBE(if (lt == 0 && grp == 0 && blockIdx.x < 256) {
-        unsigned long long *o = g_cm_probe + blockIdx.x * 8;
-        o[0] = global_ns() - pr_t0; o[1] = pr_wait; o[2] = pr_s; o[3] = pr_c; o[4] = pr_slow; o[5] = pr_n;
-    })
-    if (lt == 0) { __threadfence_block(); mb_fin[grp] = 1; }
-}
-
-constexpr int kCmGroups = 2;
-template <int R, int CH>
-constexpr int cm_pipe_smem(int nst) {
-    return nst * cm_stage_bytes<R, CH>() + kCmGroups * 2 * cm_table_floats<R>() * 4;
-}
-
-template <int R, int CH, int NST>
-int launch_cm_pipe_n(CmArgs a, cudaStream_t st) {
-    constexpr int smem = cm_pipe_smem<R, CH>(NST);
-    auto kern = cm_pipe_kernel<R, CH, NST, kCmGroups>;
-    static bool ready = false;
-    if (!ready) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-            cudaGetLastError();
-            return -1;
-        }
-        ready = true;
-    }
-    a.n_items = a.chunks * ((a.C + CH - 1) / CH);
-    a.nparts = a.n_items;
-    const int64_t total = (int64_t)a.B * a.n_items;  // per stream
-    if (total > (1ll << 29)) return -1;
-    int64_t grid = sm_count();  // one resident wave (1 CTA/SM): the CTAs wait on each other
-    if (grid * kCmGroups > total) grid = (total + kCmGroups - 1) / kCmGroups;
-    a.workers = (int)grid * kCmGroups;
-    a.rounds = (int)((total + a.workers - 1) / a.workers);
-    // every S item of a sample before any C item of it in the common round sequence (cm_decode), plus
-    // MT_CM_LAG rounds so that the table of a sample is normally published before its first C item
-    int need = 1;
-    for (int b = 0; b < a.B; ++b) {
-        const int i_max = (int)((((int64_t)b + 1) * a.n_items - 1) / a.workers);
-        const int j_min = (int)(((int64_t)b * a.n_items) / a.workers);
-        if (i_max - j_min + 1 > need) need = i_max - j_min + 1;
-    }
-    a.lag = tuning("MT_CM_LAG", 2);
-    if (a.lag < 0) a.lag = 0;
-    if (a.lag > 4) a.lag = 4;
-    a.head = need + a.lag;
-    if (a.head > a.rounds) a.head = a.rounds;
-    a.dv_items = make_fastdiv((uint32_t)a.n_items);
-    a.dv_chunks = make_fastdiv((uint32_t)a.chunks);
-    EncodeTiledFn enc = encode_fn();
-    if (!enc || (a.P & 255) != 0 || (int64_t)a.B * a.C * a.f > (1ll << 31) - 1) return -1;
-    CUtensorMap map_c;
-    {
-        cuuint64_t dims[3] = {256, (cuuint64_t)(a.P / 256), (cuuint64_t)a.B * a.C * a.f};
-        cuuint64_t strides[2] = {1024, (cuuint64_t)a.P * 4};
-        cuuint32_t box[3] = {256, 4, (cuuint32_t)(CH * (R + 1))};
-        cuuint32_t estr[3] = {1, 1, 1};
-        if (enc(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(a.c_feats), dims, strides, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return -1;
-    }
-    launch(cm_masks_kernel, dim3((a.P + 255) / 256, a.B), 256, 0, st, a);
-    launch(kern, dim3((unsigned)grid), kCmGroups * 256 + 64, (size_t)smem, st, map_c, a);
-    return launch_status("mt_cm_match_fwd");
-}
-
-// deepest ring that fits 227 KB of shared memory (static smem of the kernel: < 3 KB)
-template <int R, int CH>
-int launch_cm_pipe(CmArgs a, cudaStream_t st) {
-    constexpr int kBudget = 224 * 1024;
-    const int want = tuning("MT_CM_STAGES", 5);
-    if ((a.P & 15) != 0) return -1;  // bulk copies: 16 B aligned rows of the byte masks
-    if constexpr (cm_pipe_smem<R, CH>(5) <= kBudget) { if (want >= 5) return launch_cm_pipe_n<R, CH, 5>(a, st); }
-    if constexpr (cm_pipe_smem<R, CH>(4) <= kBudget) { if (want >= 4) return launch_cm_pipe_n<R, CH, 4>(a, st); }
-    if constexpr (cm_pipe_smem<R, CH>(3) <= kBudget) { if (want >= 3) return launch_cm_pipe_n<R, CH, 3>(a, st); }
-    if constexpr (cm_pipe_smem<R, CH>(2) <= kBudget) return launch_cm_pipe_n<R, CH, 2>(a, st);
-    return -1;
-}
-
 template <int R>
 int launch_cm(CmArgs a, cudaStream_t st) {
-    // one persistent launch (pass 2 from L2); MT_CM_FUSED=0 keeps the three-launch path
-    // MT_CM_FUSED=1 (experimental, off): the persistent pipelined kernel K3p.  Parity-green, but on B200
-    // it is 1.3-1.4x slower than the three launches (profiles/r1_experiments.md).
-    if (R <= 7 && tuning("MT_CM_FUSED", 0)) {  // the mask byte holds the target and up to 7 references
-        const int rc = launch_cm_pipe<R, 2>(a, st);
-        if (rc >= 0) return rc;
-    }
     a.b_off = 0;
     launch(cm_masks_kernel, dim3((a.P + 255) / 256, a.B), 256, 0, st, a);
-    // MT_CM_CHUNK > 0 (off): samples in groups, sim(g0) | weights(g0) | copy(g0) + sim(g1) | weights(g1) |
-    // copy(g1) + sim(g2) | ...  - pass 2 of a group shares a launch with pass 1 of the next one and
-    // re-reads its c_feats from L2 (a group of 4 samples is 42 MB of the 126 MB).  Measured on B200:
-    // 52.0 / 57.3 / 63.5 us for groups of 4 / 3 / 2 against 46.9 us for one group at B=8, 166.6 against
-    // 140.3 us at B=32: every additional launch costs 3-5 us of ramp and tail, more than the L2 hits
-    // return.  (Separate launches per pass and group were worse still: 111/72/55 us for 1/2/4.)
-    int chunk = tuning("MT_CM_CHUNK", 0);
-    if (chunk < 1 || chunk > a.B) chunk = a.B;
     const int cc = tuning("MT_CM_COPY_CH", kCopyChannels);
-    const bool merged = chunk < a.B;
-    if (merged) a.sim_ch = tuning("MT_CM_MERGE_CH", 4) == 2 ? 2 : 4;  // one slab width for both passes
     a.nparts = a.chunks * ((a.C + a.sim_ch - 1) / a.sim_ch);
     const int slabs = (a.C + a.sim_ch - 1) / a.sim_ch;
-    for (int b0 = 0; b0 < a.B; b0 += chunk) {
-        const int nb = a.B - b0 < chunk ? a.B - b0 : chunk;
-        a.b_off = b0;
-        if (!merged || b0 == 0) {
-            dim3 g1(a.chunks, slabs, nb);
-            if (a.sim_ch == 2) launch(cm_sim_kernel<R, 2>, g1, 256, 0, st, a);
-            else launch(cm_sim_kernel<R, 4>, g1, 256, 0, st, a);
-        }
-        if (!merged && R <= 7 && tuning("MT_CM_TABLE", 1)) {  // pass 1b folded into pass 2 (the mask byte holds <= 7 references)
-            if (cc == 2) launch(cm_copy2_kernel<R, 2>, dim3(a.chunks, (a.C + 1) / 2, nb), 256, 0, st, a);
-            else launch(cm_copy2_kernel<R, 4>, dim3(a.chunks, (a.C + 3) / 4, nb), 256, 0, st, a);
-            continue;
-        }
-        dim3 gw(a.chunks, nb);
-        launch(cm_weights_kernel<R>, gw, 256, 0, st, a);
-        if (merged && b0 + nb < a.B) {
-            a.n_copy = nb;
-            a.b_sim = b0 + nb;
-            a.n_sim = a.B - a.b_sim < chunk ? a.B - a.b_sim : chunk;
-            dim3 g2(a.chunks, 2 * slabs, a.n_copy > a.n_sim ? a.n_copy : a.n_sim);
-            if (a.sim_ch == 2) launch(cm_copy_sim_kernel<R, 2>, g2, 256, 0, st, a);
-            else launch(cm_copy_sim_kernel<R, 4>, g2, 256, 0, st, a);
-        } else if (merged) {
-            a.copy_reverse = 0;
-            dim3 g2(a.chunks, slabs, nb);
-            if (a.sim_ch == 2) launch(cm_copy_kernel<R, 2>, g2, 256, 0, st, a);
-            else launch(cm_copy_kernel<R, 4>, g2, 256, 0, st, a);
-        } else if (cc == 2) {
-            dim3 g2(a.chunks, (a.C + 1) / 2, nb);
-            launch(cm_copy_kernel<R, 2>, g2, 256, 0, st, a);
-        } else {
-            dim3 g2(a.chunks, (a.C + 3) / 4, nb);
-            launch(cm_copy_kernel<R, 4>, g2, 256, 0, st, a);
-        }
+    dim3 g1(a.chunks, slabs, a.B);
+    if (a.sim_ch == 2) launch(cm_sim_kernel<R, 2>, g1, 256, 0, st, a);
+    else launch(cm_sim_kernel<R, 4>, g1, 256, 0, st, a);
+    if (R <= 7 && tuning("MT_CM_TABLE", 1)) {  // pass 1b folded into pass 2 (the mask byte holds <= 7 references)
+        if (cc == 2) launch(cm_copy2_kernel<R, 2>, dim3(a.chunks, (a.C + 1) / 2, a.B), 256, 0, st, a);
+        else launch(cm_copy2_kernel<R, 4>, dim3(a.chunks, (a.C + 3) / 4, a.B), 256, 0, st, a);
+        return launch_status("mt_cm_match_fwd");
     }
+    launch(cm_weights_kernel<R>, dim3(a.chunks, a.B), 256, 0, st, a);
+    if (cc == 2) launch(cm_copy_kernel<R, 2>, dim3(a.chunks, (a.C + 1) / 2, a.B), 256, 0, st, a);
+    else launch(cm_copy_kernel<R, 4>, dim3(a.chunks, (a.C + 3) / 4, a.B), 256, 0, st, a);
     return launch_status("mt_cm_match_fwd");
 }
 
@@ -1145,8 +485,7 @@ extern "C" int64_t mt_cm_workspace_bytes(int B, int C, int f, int h, int w) {
     const int64_t P = (int64_t)h * w, R = f - 1;
     const int64_t chunks = (P + 1023) / 1024, nparts = chunks * ((C + 1) / 2);  // finest pass-1 split
     return align256(B * f * P * 4) + align256(B * nparts * 2 * R * 4) + align256(B * R * 4) +
-           align256(B * R * P * 4) + 2 * align256((int64_t)B * 4) + align256(B * P) +
-           align256(B * (int64_t)(1 << R) * (R + 1) * 4);
+           align256(B * R * P * 4) + align256(B * P);
 }
 
 extern "C" int mt_cm_match_fwd(const float *c_feats, const float *v_t, const float *v_aligned,
@@ -1174,14 +513,7 @@ extern "C" int mt_cm_match_fwd(const float *c_feats, const float *v_t, const flo
     ws += align256((int64_t)B * a.R * 4);
     a.weights = reinterpret_cast<float *>(ws);
     ws += align256((int64_t)B * a.R * a.P * 4);
-    a.count = reinterpret_cast<unsigned int *>(ws);
-    ws += align256((int64_t)B * 4);
-    a.flag = reinterpret_cast<unsigned int *>(ws);
-    ws += align256((int64_t)B * 4);
     a.pmask = reinterpret_cast<unsigned char *>(ws);
-    ws += align256((int64_t)B * a.P);
-    a.table = reinterpret_cast<float *>(ws);
-    a.n_items = 0; a.lag = 1;
     a.copy_reverse = tuning("MT_CM_COPY_REVERSE", 1);
     cudaStream_t st = (cudaStream_t)stream;
     switch (a.R) {
@@ -1203,17 +535,3 @@ extern "C" const float *mt_cm_workspace_gs(const void *workspace, int B, int C, 
     return reinterpret_cast<const float *>(reinterpret_cast<const char *>(workspace) +
                                            align256(B * f * P * 4) + align256(B * nparts * 2 * R * 4));
 }
-
-#ifdef MT_DEV_PROBES
-extern "C" __attribute__((visibility("default"))) int mt_debug_cm_reset(void) {
-    static unsigned long long init[2048];
-    for (int i = 0; i < 2048; ++i) init[i] = (i >= 1088 && i < 1152) ? ~0ull : 0ull;
-    return cudaMemcpyToSymbol(mt::g_cm_probe2, init, sizeof(init)) == cudaSuccess ? 0 : -2;
-}
-extern "C" __attribute__((visibility("default"))) int mt_debug_cm_probe(unsigned long long *dst, int n) {
-    cudaDeviceSynchronize();
-    if (n < 0) return cudaMemcpyFromSymbol(dst, mt::g_cm_probe2, sizeof(unsigned long long) * 2048) == cudaSuccess ? 0 : -2;
-    return cudaMemcpyFromSymbol(dst, mt::g_cm_probe, sizeof(unsigned long long) * (n < 2048 ? n : 2048)) == cudaSuccess
-               ? 0 : -2;
-}
-#endif

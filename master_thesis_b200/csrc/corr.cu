@@ -22,6 +22,10 @@ int corr4d_tc_supported(int C, int P);
 int corr4d_tc_launch(const float *ft, const float *vt, const float *fr, const float *vr, float *out,
                      void *ws, int64_t ws_bytes, int B, int C, int F, int P, cudaStream_t st);
 int64_t corr4d_tc_workspace_bytes(int B, int C, int F, int P);
+int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const float *fr, int64_t fr_sb, int64_t fr_sc,
+                        int64_t fr_sf, const float *vt, int64_t vt_sb, const float *vr, int64_t vr_sb, int64_t vr_sf,
+                        int mask_mode, int MH, int MW, int fh, int fw, float *out, int B, int C, int F, int P,
+                        cudaStream_t st);
 
 namespace {
 
@@ -138,4 +142,20 @@ extern "C" int mt_corr4d_fwd(const float *feats_t, const float *v_t, const float
     dim3 gg((P + 63) / 64, (P + 63) / 64, B * F);
     launch(corr_gemm_simt_kernel, gg, 256, 0, st, an, bn, out, C, P, F);
     return launch_status("mt_corr4d_fwd");
+}
+
+extern "C" int mt_corr4d_vgg_fwd(const float *feats_t, int64_t ft_sb, int64_t ft_sc, const float *m_target,
+                                 int64_t mt_sb, const float *feats_r, int64_t fr_sb, int64_t fr_sc, int64_t fr_sf,
+                                 const float *m_refs, int64_t mr_sb, int64_t mr_sf, int MH, int MW, float *out,
+                                 int B, int C, int F, int h, int w, mt_stream_t stream) {
+    MT_REQUIRE(feats_t && feats_r && out, "mt_corr4d_vgg_fwd: NULL argument");
+    MT_REQUIRE(B > 0 && C > 0 && F > 0 && h > 0 && w > 0, "mt_corr4d_vgg_fwd: empty shape");
+    MT_REQUIRE((m_target == nullptr) == (m_refs == nullptr), "mt_corr4d_vgg_fwd: both masks or none");
+    MT_REQUIRE(!m_target || (MH > 0 && MW > 0 && mt_sb >= 0 && mr_sb >= 0 && mr_sf >= 0), "mt_corr4d_vgg_fwd: bad mask shape");
+    MT_REQUIRE((int64_t)B * F <= 65535, "mt_corr4d_vgg_fwd: B*F > 65535");
+    MT_REQUIRE(corr4d_tc_supported(C, h * w),
+               "mt_corr4d_vgg_fwd: only shapes served by the tensor-core kernel (h*w %% 256 == 0, C %% 32 == 0); use "
+               "mt_corr4d_fwd on contiguous, pre-masked inputs otherwise");
+    return corr4d_tc_launch_ex(feats_t, ft_sb, ft_sc, feats_r, fr_sb, fr_sc, fr_sf, m_target, mt_sb, m_refs, mr_sb,
+                               mr_sf, m_target ? 1 : 0, MH, MW, h, w, out, B, C, F, h * w, (cudaStream_t)stream);
 }

@@ -44,13 +44,6 @@ constexpr int kTile = 256;        // output tile rows (two UMMA M = 128 halves);
 constexpr int kBK = 32;
 constexpr int kUmmaK = 8;         // tf32: 32 B of K per instruction
 constexpr int kStageBytesA = kTile * kBK * 4;  // 32 KB
-constexpr int kWorkerWarps = 8;   // norm + epilogue warps (one per TMEM lane quarter and M half)
-constexpr int kThreadsTc = (2 + kWorkerWarps) * 32;
-// TN columns per CTA: 256 = every operand byte loaded once, 1 CTA/SM (large batches);
-// 128 / 64 = 2 / 4 CTAs per frame (A re-read from L2) with deeper TMA rings, for small batches
-// (swept on B200, profiles/r1_sweep_corr.sh: 8 frames 35/31/25 us, 128 frames 40/52/70 us).
-template <int TN, int STAGES>
-constexpr int smem_bytes() { return STAGES * (kStageBytesA + TN * kBK * 4) + 1024 /*align*/ + 4096 /*barriers, scales*/; }
 
 // MN-major, SWIZZLE_128B_BASE32B shared-memory matrix descriptor (sm_100 "version 1").
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -101,31 +94,73 @@ __device__ __forceinline__ uint32_t staged_offset(int p, int k) {
 }
 
 struct CorrTcArgs {
-    const float *vt;  // (B, P) target visibility or NULL
-    const float *vr;  // (B, F, P) reference visibility or NULL
-    float *out;       // (B, F, P, P)
-    int C, F, P;
+    // visibilities at feature resolution (mask_mode 0; NULL = all ones), or full-resolution masks m
+    // (mask_mode 1): v = 1 - m[nearest source pixel], CorrelationVGG.forward model_dfpn.py:521-526
+    const float *vt; int64_t vt_sb;                // (B, P) | (B, MH, MW)
+    const float *vr; int64_t vr_sb, vr_sf;         // (B, F, P) | (B, F, MH, MW)
+    int mask_mode, MH, MW, fw;
+    float msy, msx;                                // MH / fh, MW / fw in fp32 (ATen nearest: floor(dst * scale))
+    float *out;                                    // (B, F, P, P)
+    int C, F, P, tiles_m, tiles_n, n_tiles;
 };
 
+// visibility of feature pixel p of plane `base` (see CorrTcArgs)
+__device__ __forceinline__ float corr_vis(const float *base, int p, const CorrTcArgs &a) {
+    if (!base) return 1.0f;
+    if (!a.mask_mode) return __ldg(base + p);
+    const int y = p / a.fw, x = p - y * a.fw;
+    const int ys = min((int)floorf(__fmul_rn((float)y, a.msy)), a.MH - 1);
+    const int xs = min((int)floorf(__fmul_rn((float)x, a.msx)), a.MW - 1);
+    return __fsub_rn(1.0f, __ldg(base + (int64_t)ys * a.MW + xs));
+}
+
+constexpr int kNormWarps = 8;     // one thread per row of the A tile / column of the B tile
+constexpr int kEpiWarps = 4;      // one per TMEM lane quarter
+constexpr int kThreadsP = (2 + kNormWarps + kEpiWarps) * 32;
+constexpr int kEpiPitch = 36;     // floats per staged row: 144 B keeps float4 alignment, conflict-free both ways
+constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch * 4;
+
+template <int TN, int STAGES>
+constexpr int smem_bytes_p() {
+    return STAGES * (kStageBytesA + TN * kBK * 4) + kEpiBytes + 2 * (kTile + kTile) * 4 /*scales*/ + 256 /*barriers*/ +
+           1024 /*alignment*/;
+}
+
+// Persistent kernel: one CTA per SM walks the output tiles (256 rows x TN columns of one (b, f) frame) in a
+// static round-robin.  Warp roles (14 warps):
+//   warp 0      TMA producer: runs ahead over tile boundaries, bounded only by the smem ring
+//   warp 1      TMEM owner + single-thread tcgen05.mma issuer; accumulator buffers of 2 x TN fp32 columns
+//               (two M = 128 halves): two buffers for TN <= 128, so the MMAs of tile i + 1 start while the
+//               epilogue of tile i is still draining its buffer
+//   warps 2-9   norms: thread t accumulates sum x^2 of row t of the A tile and column t of the B tile from the
+//               staged (swizzled) operands while the tensor cores consume the same stage, then publishes the
+//               row / column scales of the tile (double-buffered)
+//   warps 10-13 epilogue: tcgen05.ld 32 lanes x 32 columns -> * sa[m] * sb[n] -> transposed through a private
+//               4.5 KB staging tile -> 128 B-per-row coalesced streaming stores (4 full lines per instruction; the
+//               first version stored 16 B per lane straight from the TMEM layout: 32 half-used sectors per
+//               instruction, which made the epilogue as long as the main loop)
+// Barriers: full/empty per smem stage (empty = MMA commit + one arrival per norm warp), tmem_full / tmem_empty and
+// scales_ready per accumulator buffer.
 template <int TN, int kStages>
-__global__ void __launch_bounds__(kThreadsTc, 1)
+__global__ void __launch_bounds__(kThreadsP, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const CorrTcArgs a) {
     constexpr int kStageBytesB = TN * kBK * 4;
-    constexpr int kTmemCols = 2 * TN;  // two accumulators (M halves) of TN fp32 columns
+    constexpr int kBufs = TN <= 128 ? 2 : 1;          // accumulator buffers
+    constexpr int kBufCols = 2 * TN;                  // two M halves
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + kStages * kStageBytesA;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * (kStageBytesA + kStageBytesB));
-    uint64_t *full = bars, *empty = bars + kStages, *tmem_full = bars + 2 * kStages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 1);
-    float *s_sb = reinterpret_cast<float *>(bars + 2 * kStages + 2);  // TN column scales
-    float *s_sa = s_sb + kTile;                                         // kTile row scales
+    float *epi = reinterpret_cast<float *>(smem + kStages * (kStageBytesA + kStageBytesB));
+    float *s_sa = epi + kEpiWarps * 32 * kEpiPitch;   // [2][kTile] row scales
+    float *s_sb = s_sa + 2 * kTile;                   // [2][kTile] column scales (TN used)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_sb + 2 * kTile);
+    uint64_t *full = bars, *empty = bars + kStages, *tmem_full = bars + 2 * kStages, *tmem_empty = tmem_full + 2,
+             *scales_ready = tmem_empty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(scales_ready + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, n_tile = blockIdx.y, frame = blockIdx.z;
-    const int b = frame / a.F, f = frame - b * a.F;
     const int num_k = a.C / kBK;
 
     if (warp == 0 && lane == 0) {
@@ -133,14 +168,18 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         for (int s = 0; s < kStages; ++s) {
             mbar_init(smem_u32(full + s), 1);
-            mbar_init(smem_u32(empty + s), 1 + kWorkerWarps);  // MMA commit + one arrival per worker warp
+            mbar_init(smem_u32(empty + s), 1 + kNormWarps);  // MMA commit + one arrival per norm warp
         }
-        mbar_init(smem_u32(tmem_full), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(tmem_full + i), 1);
+            mbar_init(smem_u32(tmem_empty + i), kEpiWarps);
+            mbar_init(smem_u32(scales_ready + i), kNormWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: two 128-lane x TN-column fp32 accumulators (all 512 columns at TN = 256)
+    if (warp == 1) {  // TMEM: all 512 columns (1 CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+                     ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -150,48 +189,64 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // everything above is on-chip setup and overlaps the tail of the previous kernel (PDL)
     pdl_sync();
 
+    const int tiles_per_frame = a.tiles_m * a.tiles_n;
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(smem_u32(empty + s), ph ^ 1);
-                mbar_expect_tx(smem_u32(full + s), kStageBytesA + kStageBytesB);
-                // A: (pixel-in-group 32, channel C, pixel group P/32, batch B)
-                tma_load_4d(smem_u32(smem_a + s * kStageBytesA), &map_a, smem_u32(full + s), 0, kb * kBK,
-                            m_tile * (kTile / 32), b);
-                // B: (pixel-in-group 32, channel C, pixel group P/32, frame F, batch B)
-                tma_load_5d(smem_u32(smem_b + s * kStageBytesB), &map_b, smem_u32(full + s), 0, kb * kBK,
-                            n_tile * (TN / 32), f, b);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                const int frame = tile / tiles_per_frame, r = tile - frame * tiles_per_frame;
+                const int m_tile = r / a.tiles_n, n_tile = r - m_tile * a.tiles_n;
+                const int b = frame / a.F, f = frame - b * a.F;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1;
+                    mbar_wait(smem_u32(empty + s), ph ^ 1);
+                    mbar_expect_tx(smem_u32(full + s), kStageBytesA + kStageBytesB);
+                    // A: (pixel-in-group 32, channel C, pixel group P/32, batch B)
+                    tma_load_4d(smem_u32(smem_a + s * kStageBytesA), &map_a, smem_u32(full + s), 0, kb * kBK,
+                                m_tile * (kTile / 32), b);
+                    // B: (pixel-in-group 32, channel C, pixel group P/32, frame F, batch B)
+                    tma_load_5d(smem_u32(smem_b + s * kStageBytesB), &map_b, smem_u32(full + s), 0, kb * kBK,
+                                n_tile * (TN / 32), f, b);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected lane) =====
         if (lane == 0) {
             constexpr uint32_t idesc = instr_desc(128, TN);
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(smem_u32(full + s), ph);
+            uint32_t it = 0;
+            int ti = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++ti) {
+                const int buf = ti % kBufs;
+                const uint32_t use = (uint32_t)(ti / kBufs);
+                mbar_wait(smem_u32(tmem_empty + buf), (use & 1) ^ 1);  // the epilogue has drained this buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a0 = smem_u32(smem_a + s * kStageBytesA), b0 = smem_u32(smem_b + s * kStageBytesB);
+                const uint32_t acc = tmem_base + buf * kBufCols;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1;
+                    mbar_wait(smem_u32(full + s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = smem_u32(smem_a + s * kStageBytesA), b0 = smem_u32(smem_b + s * kStageBytesB);
 #pragma unroll
-                for (int j = 0; j < kBK / kUmmaK; ++j) {
-                    // K advance inside the stage: next 8 channels = two 512 B atoms = +1024 B
-                    const uint64_t bd = umma_desc(b0 + j * 1024, kBK * 128, 512);
+                    for (int j = 0; j < kBK / kUmmaK; ++j) {
+                        // K advance inside the stage: next 8 channels = two 512 B atoms = +1024 B
+                        const uint64_t bd = umma_desc(b0 + j * 1024, kBK * 128, 512);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {  // M halves: pixel groups 0..3 and 4..7 of the A stage
-                        const uint64_t ad = umma_desc(a0 + h * (4 * kBK * 128) + j * 1024, kBK * 128, 512);
-                        umma_tf32(tmem_base + h * TN, ad, bd, idesc, (kb | j) != 0 ? 1u : 0u);
+                        for (int h = 0; h < 2; ++h) {  // M halves: pixel groups 0..3 and 4..7 of the A stage
+                            const uint64_t ad = umma_desc(a0 + h * (4 * kBK * 128) + j * 1024, kBK * 128, 512);
+                            umma_tf32(acc + h * TN, ad, bd, idesc, (kb | j) != 0 ? 1u : 0u);
+                        }
                     }
+                    umma_commit(smem_u32(empty + s));  // frees the smem slot when these MMAs retire
                 }
-                umma_commit(smem_u32(empty + s));  // frees the smem slot when these MMAs retire
+                umma_commit(smem_u32(tmem_full + buf));  // accumulators of this tile complete
             }
-            umma_commit(smem_u32(tmem_full));      // accumulators complete
         }
-    } else {
-        // ===== workers: norms during the main loop, then the epilogue =====
+    } else if (warp < 2 + kNormWarps) {
+        // ===== norm warps =====
         const int t = threadIdx.x - 64;  // 0..255: row t of A, column t of B (if t < TN)
         const int tb = t < TN ? t : 0;
         // the swizzle phase repeats every 4 channels: channel k = 4 j + r lives at base[r] + 512 j,
@@ -199,59 +254,99 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t base_a[4], base_b[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) { base_a[r] = staged_offset(t, r); base_b[r] = staged_offset(tb, r); }
-        float qa[4] = {0.f, 0.f, 0.f, 0.f}, qb[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int kb = 0; kb < num_k; ++kb) {
-            const int s = kb % kStages;
-            const uint32_t ph = (kb / kStages) & 1;
-            mbar_wait(smem_u32(full + s), ph);
-            const uint8_t *pa = smem_a + s * kStageBytesA, *pb = smem_b + s * kStageBytesB;
+        uint32_t it = 0;
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++ti) {
+            const int frame = tile / tiles_per_frame, r0 = tile - frame * tiles_per_frame;
+            const int m_tile = r0 / a.tiles_n, n_tile = r0 - m_tile * a.tiles_n;
+            const int b = frame / a.F, f = frame - b * a.F;
+            // the visibilities are needed at the end of the main loop only: request them first
+            const float vt = corr_vis(a.vt ? a.vt + (int64_t)b * a.vt_sb : nullptr, m_tile * kTile + t, a);
+            const float vr = corr_vis(a.vr ? a.vr + (int64_t)b * a.vr_sb + (int64_t)f * a.vr_sf : nullptr,
+                                      n_tile * TN + tb, a);
+            float qa[4] = {0.f, 0.f, 0.f, 0.f}, qb[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int kb = 0; kb < num_k; ++kb, ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(smem_u32(full + s), ph);
+                const uint8_t *pa = smem_a + s * kStageBytesA, *pb = smem_b + s * kStageBytesB;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+                for (int r = 0; r < 4; ++r) {
 #pragma unroll
-                for (int j = 0; j < kBK / 4; ++j) {
-                    const float va = *reinterpret_cast<const float *>(pa + base_a[r] + j * 512);
-                    const float vb = *reinterpret_cast<const float *>(pb + base_b[r] + j * 512);
-                    qa[r] = __fmaf_rn(va, va, qa[r]);
-                    qb[r] = __fmaf_rn(vb, vb, qb[r]);
+                    for (int j = 0; j < kBK / 4; ++j) {
+                        const float va = *reinterpret_cast<const float *>(pa + base_a[r] + j * 512);
+                        const float vb = *reinterpret_cast<const float *>(pb + base_b[r] + j * 512);
+                        qa[r] = __fmaf_rn(va, va, qa[r]);
+                        qb[r] = __fmaf_rn(vb, vb, qb[r]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(empty + s));
+            }
+            const float ssa = (qa[0] + qa[1]) + (qa[2] + qa[3]), ssb = (qb[0] + qb[1]) + (qb[2] + qb[3]);
+            const int buf = ti % kBufs;
+            const uint32_t use = (uint32_t)(ti / kBufs);
+            // the scale tables of this buffer are free once the epilogue of its previous tile has finished
+            mbar_wait(smem_u32(tmem_empty + buf), (use & 1) ^ 1);
+            // scales: v / (|v| * ||f|| + 1e-9)   (||f * v|| = |v| * ||f||)
+            s_sa[buf * kTile + t] = __fdiv_rn(vt, __fadd_rn(__fmul_rn(fabsf(vt), sqrtf(ssa)), 1e-9f));
+            if (t < TN) s_sb[buf * kTile + t] = __fdiv_rn(vr, __fadd_rn(__fmul_rn(fabsf(vr), sqrtf(ssb)), 1e-9f));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(scales_ready + buf));
+        }
+    } else {
+        // ===== epilogue warps =====
+        // TMEM lane-quarter rule: warp w may touch lanes 32*(w%4)..32*(w%4)+31; warps 10..13 cover all four
+        const int lq = warp & 3, ew = warp - (2 + kNormWarps);
+        float *st = epi + ew * 32 * kEpiPitch;
+        const int rr = lane >> 3, c4 = (lane & 7) * 4;  // read-back: 4 rows x 8 float4 per instruction
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++ti) {
+            const int frame = tile / tiles_per_frame, r0 = tile - frame * tiles_per_frame;
+            const int m_tile = r0 / a.tiles_n, n_tile = r0 - m_tile * a.tiles_n;
+            const int buf = ti % kBufs;
+            const uint32_t use = (uint32_t)(ti / kBufs);
+            mbar_wait(smem_u32(scales_ready + buf), use & 1);
+            mbar_wait(smem_u32(tmem_full + buf), use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float *sbv = s_sb + buf * kTile;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int row0 = h * 128 + lq * 32;  // first row of this warp's 32-row block
+                const float sa = s_sa[buf * kTile + row0 + lane];
+                float *oblk = a.out + (((int64_t)frame * a.P + m_tile * kTile + row0) * a.P + n_tile * TN);
+#pragma unroll 1
+                for (int c0 = 0; c0 < TN; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * kBufCols + h * TN + c0), v);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 o;
+                        o.x = v[i] * sa * sbv[c0 + i];
+                        o.y = v[i + 1] * sa * sbv[c0 + i + 1];
+                        o.z = v[i + 2] * sa * sbv[c0 + i + 2];
+                        o.w = v[i + 3] * sa * sbv[c0 + i + 3];
+                        *reinterpret_cast<float4 *>(st + lane * kEpiPitch + i) = o;  // row = lane
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int row = j * 4 + rr;
+                        const float4 o = *reinterpret_cast<const float4 *>(st + row * kEpiPitch + c4);
+                        __stcs(reinterpret_cast<float4 *>(oblk + (int64_t)row * a.P + c0 + c4), o);
+                    }
+                    __syncwarp();
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(empty + s));
-        }
-        const float ssa = (qa[0] + qa[1]) + (qa[2] + qa[3]), ssb = (qb[0] + qb[1]) + (qb[2] + qb[3]);
-        // scales: v / (|v| * ||f|| + 1e-9)   (||f * v|| = |v| * ||f||)
-        const float vt = a.vt ? __ldg(a.vt + ((int64_t)b * a.P + m_tile * kTile + t)) : 1.0f;
-        const float vr = a.vr ? __ldg(a.vr + ((int64_t)frame * a.P + n_tile * TN + tb)) : 1.0f;
-        s_sa[t] = __fdiv_rn(vt, __fadd_rn(__fmul_rn(fabsf(vt), sqrtf(ssa)), 1e-9f));
-        if (t < TN) s_sb[t] = __fdiv_rn(vr, __fadd_rn(__fmul_rn(fabsf(vr), sqrtf(ssb)), 1e-9f));
-        asm volatile("bar.sync 1, %0;" ::"n"(kWorkerWarps * 32) : "memory");  // workers only
-        // TMEM lane-quarter rule: warp w may touch lanes 32*(w%4)..32*(w%4)+31.  Warps 2..9 have
-        // (w%4) = 2,3,0,1,2,3,0,1; warps 2..5 drain the first M half, 6..9 the second.
-        const int lq = warp & 3, wh = (warp - 2) >> 2;
-        const int row = wh * 128 + lq * 32 + lane;
-        const float sa = s_sa[row];
-        float *orow = a.out + (((int64_t)frame * a.P + m_tile * kTile + row) * a.P + n_tile * TN);
-        mbar_wait(smem_u32(tmem_full), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(wh * TN + c0), v);
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                float4 o;
-                o.x = v[i] * sa * s_sb[c0 + i];
-                o.y = v[i + 1] * sa * s_sb[c0 + i + 1];
-                o.z = v[i + 2] * sa * s_sb[c0 + i + 2];
-                o.w = v[i + 3] * sa * s_sb[c0 + i + 3];
-                __stcs(reinterpret_cast<float4 *>(orow + c0 + i), o);
-            }
+            if (lane == 0) mbar_arrive(smem_u32(tmem_empty + buf));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
     }
 }
 
@@ -267,24 +362,34 @@ int64_t corr4d_tc_workspace_bytes(int B, int C, int F, int P) {
     return 0;  // norms are fused into the GEMM: no scratch
 }
 
-int corr4d_tc_launch(const float *ft, const float *vt, const float *fr, const float *vr, float *out, void *ws,
-                     int64_t ws_bytes, int B, int C, int F, int P, cudaStream_t st) {
-    (void)ws; (void)ws_bytes;
+// Strided form.  ft (B, C, P): strides ft_sb, ft_sc; fr (B, C, F, P): fr_sb, fr_sc, fr_sf (elements; the pixel index
+// is contiguous).  Masks: see CorrTcArgs.
+int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const float *fr, int64_t fr_sb, int64_t fr_sc,
+                        int64_t fr_sf, const float *vt, int64_t vt_sb, const float *vr, int64_t vr_sb, int64_t vr_sf,
+                        int mask_mode, int MH, int MW, int fh, int fw, float *out, int B, int C, int F, int P,
+                        cudaStream_t st) {
     MT_REQUIRE(aligned16(ft) && aligned16(fr) && aligned16(out), "mt_corr4d_fwd: pointers must be 16 B aligned");
+    MT_REQUIRE(!((ft_sb | ft_sc | fr_sb | fr_sc | fr_sf) & 3) && ft_sc > 0 && fr_sc > 0 && (B == 1 || (ft_sb > 0 && fr_sb > 0)) &&
+               (F == 1 || fr_sf > 0) && ft_sb >= 0 && fr_sb >= 0 && fr_sf >= 0,
+               "mt_corr4d_fwd: feature strides must be positive multiples of 4 elements");
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
         set_error("mt_corr4d_fwd: cuTensorMapEncodeTiled is not available from the driver");
         return MT_ERR_NO_DEVICE;
     }
-    // columns per CTA: split a frame across more CTAs when the batch alone cannot fill the GPU
+    // columns per tile: 256 = every operand byte loaded once but a single accumulator buffer; 128 = two buffers
+    // (epilogue of a tile under the main loop of the next), the target tile re-read from L2 once per frame
     const int frames = B * F * (P / kTile);
     int tn = tuning("MT_CORR_TN", 0);
-    if (tn != 256 && tn != 128 && tn != 64) tn = frames >= sm_count() / 2 ? 256 : (frames * 2 >= sm_count() / 2 ? 128 : 64);
+    // swept on B200 (profiles/r2_corr_sweep.md): 8 frames 22.8 / 24.1 / 31.3 us, 40 frames 32.9 / 25.9 / 32.1 us,
+    // 128 frames 55.4 / 39.8 / 35.4 us for TN = 64 / 128 / 256
+    if (tn != 256 && tn != 128 && tn != 64) tn = frames * 2 >= sm_count() ? 256 : (frames * 8 >= sm_count() ? 128 : 64);
+    if (P % tn) tn = 64;
     CUtensorMap map_a, map_b;
     {
         // ft (B, C, P) viewed as (32, C, P/32, B): strides in bytes for dims 1..3
         cuuint64_t dims[4] = {32, (cuuint64_t)C, (cuuint64_t)(P / 32), (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)P * 4, 128, (cuuint64_t)C * P * 4};
+        cuuint64_t strides[3] = {(cuuint64_t)ft_sc * 4, 128, (cuuint64_t)(B > 1 ? ft_sb : (int64_t)C * P) * 4};
         cuuint32_t box[4] = {32, (cuuint32_t)kBK, (cuuint32_t)(kTile / 32), 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(ft), dims, strides, box,
@@ -298,7 +403,8 @@ int corr4d_tc_launch(const float *ft, const float *vt, const float *fr, const fl
     {
         // fr (B, C, F, P) viewed as (32, C, P/32, F, B)
         cuuint64_t dims[5] = {32, (cuuint64_t)C, (cuuint64_t)(P / 32), (cuuint64_t)F, (cuuint64_t)B};
-        cuuint64_t strides[4] = {(cuuint64_t)F * P * 4, 128, (cuuint64_t)P * 4, (cuuint64_t)C * F * P * 4};
+        cuuint64_t strides[4] = {(cuuint64_t)fr_sc * 4, 128, (cuuint64_t)(F > 1 ? fr_sf : (int64_t)P) * 4,
+                                 (cuuint64_t)(B > 1 ? fr_sb : (int64_t)C * F * P) * 4};
         cuuint32_t box[5] = {32, (cuuint32_t)kBK, (cuuint32_t)(tn / 32), 1, 1};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(fr), dims, strides, box,
@@ -309,24 +415,43 @@ int corr4d_tc_launch(const float *ft, const float *vt, const float *fr, const fl
             return MT_ERR_CUDA;
         }
     }
-    CorrTcArgs a{vt, vr, out, C, F, P};
-    dim3 grid(P / kTile, P / tn, B * F);
+    CorrTcArgs a;
+    a.vt = vt; a.vt_sb = vt_sb; a.vr = vr; a.vr_sb = vr_sb; a.vr_sf = vr_sf;
+    a.mask_mode = mask_mode; a.MH = MH; a.MW = MW; a.fw = fw > 0 ? fw : 1;
+    a.msy = mask_mode ? (float)MH / (float)fh : 1.0f;
+    a.msx = mask_mode ? (float)MW / (float)fw : 1.0f;
+    a.out = out; a.C = C; a.F = F; a.P = P;
+    a.tiles_m = P / kTile; a.tiles_n = P / tn;
+    const int64_t n_tiles = (int64_t)B * F * a.tiles_m * a.tiles_n;
+    MT_REQUIRE(n_tiles < (1ll << 30), "mt_corr4d_fwd: too many tiles");
+    a.n_tiles = (int)n_tiles;
+    int ctas = sm_count();
+    if (ctas > a.n_tiles) ctas = a.n_tiles;
+    dim3 grid(ctas);
 #define MT_CORR_GO(TNV, STG)                                                                         \
     do {                                                                                             \
         cudaError_t e = cudaFuncSetAttribute(corr_tc_kernel<TNV, STG>,                               \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<TNV, STG>()); \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_p<TNV, STG>()); \
         if (e != cudaSuccess) {                                                                      \
             set_error("mt_corr4d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));             \
             return MT_ERR_CUDA;                                                                      \
         }                                                                                            \
-        launch(corr_tc_kernel<TNV, STG>, grid, dim3(kThreadsTc), (size_t)smem_bytes<TNV, STG>(), st, map_a, map_b, a); \
+        launch(corr_tc_kernel<TNV, STG>, grid, dim3(kThreadsP), (size_t)smem_bytes_p<TNV, STG>(), st, map_a, map_b, a); \
     } while (0)
-    // narrower tiles run with fewer CTAs than SMs: spend the shared memory on pipeline depth
+    static_assert(smem_bytes_p<256, 3>() <= 227 * 1024 && smem_bytes_p<128, 4>() <= 227 * 1024 &&
+                  smem_bytes_p<64, 5>() <= 227 * 1024, "stage ring exceeds the shared memory of an SM");
     if (tn == 256) MT_CORR_GO(256, 3);       // 3 x 64 KB
     else if (tn == 128) MT_CORR_GO(128, 4);  // 4 x 48 KB
     else MT_CORR_GO(64, 5);                  // 5 x 40 KB
 #undef MT_CORR_GO
     return launch_status("mt_corr4d_fwd");
+}
+
+int corr4d_tc_launch(const float *ft, const float *vt, const float *fr, const float *vr, float *out, void *ws,
+                     int64_t ws_bytes, int B, int C, int F, int P, cudaStream_t st) {
+    (void)ws; (void)ws_bytes;
+    return corr4d_tc_launch_ex(ft, (int64_t)C * P, P, fr, (int64_t)C * F * P, (int64_t)F * P, P, vt, P, vr,
+                               (int64_t)F * P, P, 0, 0, 0, 0, 0, out, B, C, F, P, st);
 }
 
 }  // namespace mt

@@ -309,7 +309,7 @@ def _l1_layout(y_hat, y, mask):
     a = _lead3(y_hat, nlead, pd)
     b_ = _lead3(y, nlead, pd)
     if mask is None:     # torch.ones_like(y_hat): one cached plane of ones, visited per channel (mask_c = C)
-        return (a, b_, (_ones_plane(y_hat, P), 0, 0, 0)), B, C, F, P, C, B * F
+        return (a, b_, (_ones_plane(y_hat, P), 0, 0, 0)), B, C, F, P, C, 1
     if mask.dim() > nd:
         raise RuntimeError("masked_l1: mask %s does not broadcast against %s" % (tuple(mask.shape), shape))
     mask = mask.reshape((1,) * (nd - mask.dim()) + tuple(mask.shape))
@@ -556,6 +556,41 @@ def corr4d(feats_t, v_t, feats_r, v_r):
     return out
 
 
+def corr4d_vgg_supported(c, p):
+    """True if mt_corr4d_vgg_fwd (tensor-core kernel, strided features, masks down-sampled in the kernel)
+    serves (C, h*w)."""
+    return bool(_lib.load().mt_corr4d_uses_tensor_cores(int(c), int(p)))
+
+
+def corr4d_vgg(feats_t, m_target, feats_r, m_refs):
+    """The correlation of CorrelationVGG.forward with its neighbours (model_dfpn.py:516-528):
+    feats_t (B,C,h,w), feats_r (B,C,F,h,w) with ANY b / c / f strides (the transposed view of the VGG output is
+    read in place), m_target (B,1,H,W) / m_refs (B,1,F,H,W) FULL-RESOLUTION masks or both None; the visibilities
+    v = F.interpolate(1 - m, (h, w), mode='nearest') are evaluated inside the kernel.  -> (B,F,h,w,h,w)."""
+    _need_cuda(feats_t, m_target, feats_r, m_refs)
+    _no_grad_inputs("corr4d_vgg", feats_t, m_target, feats_r, m_refs)
+    b, c, f, h, w = feats_r.shape
+    if not corr4d_vgg_supported(c, h * w):
+        raise RuntimeError("corr4d_vgg: (C=%d, h*w=%d) is not served by the tensor-core kernel" % (c, h * w))
+
+    def ok(t, lead):       # strides the tensor map can encode: positive multiples of 4 elements, plane contiguous
+        return all(t.size(d) == 1 or (t.stride(d) > 0 and t.stride(d) % 4 == 0) for d in range(lead)) and \
+            t.stride(-1) == 1 and t.stride(-2) == w and t.data_ptr() % 16 == 0
+    ft = feats_t if ok(feats_t, 2) else _contig(feats_t)
+    fr = feats_r if ok(feats_r, 3) else _contig(feats_r)
+    _lib.keep(ft), _lib.keep(fr)
+    mt = mr = None
+    mt_sb = mr_sb = mr_sf = MH = MW = 0
+    if m_target is not None:
+        mt, mr = _planes(m_target), _planes(m_refs)
+        MH, MW = mt.shape[-2:]
+        mt_sb, mr_sb, mr_sf = mt.stride(0), mr.stride(0), mr.stride(2)
+    out = _empty((b, f, h, w, h, w), dtype=torch.float32, device=fr.device)
+    _call("mt_corr4d_vgg_fwd", _ptr(ft), ft.stride(0), ft.stride(1), _ptr(mt), mt_sb, _ptr(fr), fr.stride(0),
+          fr.stride(1), fr.stride(2), _ptr(mr), mr_sb, mr_sf, MH, MW, _ptr(out), b, c, f, h, w, _stream(fr))
+    return out
+
+
 # --------------------------------------------------------------------------
 # K3 context matching
 # --------------------------------------------------------------------------
@@ -664,9 +699,12 @@ def hole_update(m_t, v_map0, y_comp0):
     return m_new, x_new, per[0]
 
 
-def chn_fill(nn_out, x_t, v_t, m_t, v_map0):
+def chn_fill(nn_out, x_t, v_t, m_t, v_map0, gate=None):
     """mt_chn_fill_step: composite (model_chn.py:80-85) + hole update (:128-131) of one inference step
-    with a single reference frame.  nn_out (B,3,H,W).  Returns (y_comp0 (B,3,H,W), m_new, x_new, inp_per)."""
+    with a single reference frame.  nn_out (B,3,H,W).  Returns (y_comp0 (B,3,H,W), m_new, x_new, inp_per).
+
+    ``gate = (prev_inp_per (1-element device tensor), e, y_prev)``: device-side loop control - the step only
+    happens while prev_inp_per > e, otherwise the state passes through unchanged (mt_chn_fill_step_gated)."""
     _need_cuda(nn_out, x_t, v_t, m_t, v_map0)
     _no_grad_inputs("chn_fill", nn_out, x_t, v_t, m_t, v_map0)
     b = x_t.shape[0]
@@ -676,9 +714,17 @@ def chn_fill(nn_out, x_t, v_t, m_t, v_map0):
     m_new = _empty((b, 1, h, w), dtype=torch.float32, device=no.device)
     x_new = _empty((b, 3, h, w), dtype=torch.float32, device=no.device)
     per = _empty(1, dtype=torch.float32, device=no.device)
-    _call("mt_chn_fill_step", _ptr(no), _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0),
+    if gate is None:
+        _call("mt_chn_fill_step", _ptr(no), _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0),
               _ptr(mt), mt.stride(0), _ptr(vm), vm.stride(0), _ptr(yc), _ptr(m_new), _ptr(x_new), _ptr(per),
               _ptr(reduce_workspace(no)), b, h * w, _stream(no))
+    else:
+        prev_per, e, y_prev = gate
+        _need_cuda(prev_per, y_prev)
+        y_prev = _contig(y_prev)
+        _call("mt_chn_fill_step_gated", _ptr(no), _ptr(xt), xt.stride(0), xt.stride(1), _ptr(vt), vt.stride(0),
+              _ptr(mt), mt.stride(0), _ptr(vm), vm.stride(0), _ptr(y_prev), _ptr(prev_per.reshape(1)), float(e),
+              _ptr(yc), _ptr(m_new), _ptr(x_new), _ptr(per), _ptr(reduce_workspace(no)), b, h * w, _stream(no))
     return yc, m_new, x_new, per[0]
 
 

@@ -59,6 +59,30 @@ class CorrelationVGG:
         return ops.corr4d(x_target_feats, v_target, x_ref_feats, v_ref)
 
 
+def corr_vgg_forward(self, x_target, m_target, x_refs, m_refs):
+    """Replaces CorrelationVGG.forward (model_dfpn.py:491-532).  The two VGG passes and the 4-D convolution
+    (cuDNN) are the module's own; what lies between them (:516-528) is ONE kernel: the transposed view of the
+    reference features is read in place (no permute copy), the nearest down-sample of the two visibility
+    maps (:521-526) is evaluated inside the correlation kernel from the full-resolution masks, and the
+    masking / normalisation / contraction (:534-565) run on tcgen05."""
+    b, c, ref_n, h, w = x_refs.size()
+    with torch.no_grad():
+        x_target_feats = self.model_vgg(x_target, normalize_input=False)[3]
+        x_ref_feats = self.model_vgg(x_refs.transpose(1, 2).reshape(b * ref_n, c, h, w), normalize_input=False)[3]
+    x_ref_feats = x_ref_feats.reshape(b, ref_n, -1, 16, 16).transpose(1, 2)
+    fc, fh, fw = x_ref_feats.shape[1], x_ref_feats.shape[3], x_ref_feats.shape[4]
+    if ops.corr4d_vgg_supported(fc, fh * fw):
+        corr = ops.corr4d_vgg(x_target_feats, m_target, x_ref_feats, m_refs)
+    else:   # shapes the tensor-core kernel does not serve: the reference's own lines around the patched op
+        import torch.nn.functional as F
+        v_target = F.interpolate(1 - m_target, size=(fh, fw), mode='nearest')
+        v_ref = F.interpolate(1 - m_refs.transpose(1, 2).reshape(b * ref_n, 1, m_refs.size(3), m_refs.size(4)),
+                              size=(fh, fw), mode='nearest').reshape(b, ref_n, 1, fh, fw).transpose(1, 2)
+        corr = ops.corr4d(x_target_feats, v_target, x_ref_feats, v_ref)
+    corr = self.conv(corr)
+    return type(self).softmax_3d(corr) if self.use_softmax else corr
+
+
 class CM_Module(nn.Module):
     """Mirror of master_thesis.model_cpn.CM_Module (model_cpn.py:202-254)."""
 
@@ -263,21 +287,28 @@ def chn_compute_loss(self, y_target, v_target, y_hat, y_hat_comp, v_map):
     return loss, [loss_nh, loss_vh, loss_nvh, loss_perceptual, loss_grad]
 
 
-def _fill_step(chn, aligner, x_t, m_t, x_ref, m_ref):
+def _fused_step(aligner, x_ref):
+    """The grid function of a patched aligner if the two-kernel step applies (one reference frame)."""
+    fn = getattr(type(aligner), "align", None)
+    grid_fn = _dfpn_grid if fn is dfpn_align else (_cpn_grid if fn is cpn_align else None)
+    return grid_fn if (grid_fn is not None and x_ref.size(2) == 1) else None
+
+
+def _fill_step(chn, aligner, x_t, m_t, x_ref, m_ref, gate=None):
     """One align -> hallucinate -> hole-update step shared by the three inpainting
     algorithms (model_chn.py:114-131, 165-186, 225-248).  All tensors carry a batch dim.
 
     With a patched aligner (DFPN or CPN) the step is two kernels around the hallucination CNN:
     warp + CNN-input pack, then composite + hole update; the aligned frame itself is
     never materialised.  Any other aligner object takes the four-kernel route through its own
-    ``align`` and ``chn.forward``."""
-    fn = getattr(type(aligner), "align", None)
-    grid_fn = _dfpn_grid if fn is dfpn_align else (_cpn_grid if fn is cpn_align else None)
-    if grid_fn is not None and x_ref.size(2) == 1:
+    ``align`` and ``chn.forward``.  ``gate = (prev_inp_per, e, prev_y_comp)``: device-side loop control,
+    see ops.chn_fill (two-kernel route only)."""
+    grid_fn = _fused_step(aligner, x_ref)
+    if grid_fn is not None:
         grid, flags = grid_fn(aligner, x_t, m_t, x_ref, m_ref)
         v_t = 1 - m_t
         nn_in, v_map, _, _ = ops.warp_pack_fwd(x_ref, m_ref, grid, m_t, x_t, v_t, flags)
-        y_comp, m_new, x_new, per = ops.chn_fill(chn.nn(nn_in), x_t, v_t, m_t, v_map[:, :, 0])
+        y_comp, m_new, x_new, per = ops.chn_fill(chn.nn(nn_in), x_t, v_t, m_t, v_map[:, :, 0], gate)
         return y_comp, m_new, x_new, per
     x_al, v_al, v_map = aligner.align(x_t, m_t, x_ref, m_ref)
     _, y_comp = chn(x_t, 1 - m_t, x_al, v_al, v_map)
@@ -285,36 +316,55 @@ def _fill_step(chn, aligner, x_t, m_t, x_ref, m_ref):
     return y_comp[:, :, 0], m_new, x_new, per
 
 
+def _sync_every(chn):
+    """Steps between two host reads of inp_per in the patched inpaint_ff / inpaint_ip loops: attribute
+    ``mt_b200_sync_every`` of the CHN module, else $MT_INPAINT_SYNC_EVERY, else 1 (the reference's behaviour:
+    one device->host sync per step, model_chn.py:112).  With k > 1 the loop condition is evaluated on the
+    device by the step itself (gated fill step) and the host looks every k steps; results are bit-identical,
+    at most k - 1 steps per target frame run as no-ops after the condition has failed."""
+    import os
+    return max(1, int(getattr(chn, "mt_b200_sync_every", os.environ.get("MT_INPAINT_SYNC_EVERY", "1"))))
+
+
+def _fill_loop(chn, cands, x_t, m_t, ref_of, e):
+    """`while inp_per > e and candidates remain` of model_chn.py:111-131 / 162-186 around _fill_step.
+    ``ref_of(r)`` -> (x_ref, m_ref) of candidate r.  Returns the final (y_comp, m_t, x_t)."""
+    k = _sync_every(chn)
+    y_comp, per, n, go = None, None, 0, True
+    while y_comp is None or (len(cands) > 0 and go):
+        x_ref, m_ref = ref_of([cands.pop(0)])
+        gated = k > 1 and y_comp is not None and _fused_step(chn.model_aligner, x_ref) is not None
+        y_comp, m_t, x_t, per = _fill_step(chn, chn.model_aligner, x_t, m_t, x_ref, m_ref,
+                                           (per, e, y_comp) if gated else None)
+        n += 1
+        if not gated or n % k == 0 or len(cands) == 0:
+            go = float(per) > e            # the only device->host synchronisation of the loop
+    return y_comp, m_t, x_t
+
+
 def chn_inpaint_ff(self, x, m, s=1, D=20, e=1):
     """Replaces CHN.inpaint_ff (model_chn.py:87-133).  x (C,F,H,W), m (1,F,H,W)."""
     n = x.size(1)
     y_inpainted = torch.zeros_like(x)
     for t in range(n):
-        x_t, m_t = x[:, t].unsqueeze(0), m[:, t].unsqueeze(0)
         cands = type(self).get_indexes_ff(t, n, s=s, D=D)
-        y_comp, per = None, 0
-        while y_comp is None or (len(cands) > 0 and float(per) > e):
-            r = [cands.pop(0)]
-            y_comp, m_t, x_t, per = _fill_step(self, self.model_aligner, x_t, m_t,
-                                               x[:, r].unsqueeze(0), m[:, r].unsqueeze(0))
+        y_comp, _, _ = _fill_loop(self, cands, x[:, t].unsqueeze(0), m[:, t].unsqueeze(0),
+                                  lambda r: (x[:, r].unsqueeze(0), m[:, r].unsqueeze(0)), e)
         y_inpainted[:, t] = y_comp[0]
     return y_inpainted
 
 
 def chn_inpaint_ip(self, x, m, s=1, D=20, e=1):
-    """Replaces CHN.inpaint_ip (model_chn.py:135-189)."""
+    """Replaces CHN.inpaint_ip (model_chn.py:135-189).  The reference writes the intermediate state of frame t
+    back into the sequence after every step (:181-186); only frame t reads it, and the lines after the loop
+    (:188-189) overwrite it, so the state is carried by the loop and written once."""
     y_inp, m_inp = x.unsqueeze(0), m.unsqueeze(0)
     n = x.size(1)
     order = sorted(range(n), key=lambda i: abs(i - n // 2))
     for t in order:
         cands = type(self).get_indexes_ip(t, order, s, D)
-        y_comp, per = None, 0
-        while y_comp is None or (len(cands) > 0 and float(per) > e):
-            r = [cands.pop(0)]
-            y_comp, m_new, x_new, per = _fill_step(self, self.model_aligner, y_inp[:, :, t],
-                                                   m_inp[:, :, t], y_inp[:, :, r], m_inp[:, :, r])
-            m_inp[:, :, t] = m_new
-            y_inp[:, :, t] = x_new
+        y_comp, _, _ = _fill_loop(self, cands, y_inp[:, :, t], m_inp[:, :, t],
+                                  lambda r: (y_inp[:, :, r], m_inp[:, :, r]), e)
         m_inp[:, :, t] = 0
         y_inp[:, :, t] = y_comp
     return y_inp[0]
@@ -358,6 +408,7 @@ _PATCHES = (
     ("utils", "LossesUtils", "masked_l1", LossesUtils.masked_l1, True),
     ("model_dfpn", "CorrelationVGG", "correlation_masked_4d",
      CorrelationVGG.correlation_masked_4d, True),
+    ("model_dfpn", "CorrelationVGG", "forward", corr_vgg_forward, False),
     ("model_dfpn", "DFPN", "align", dfpn_align, False),
     ("model_dfpn", "DFPN", "_train_val_wrapper", dfpn_train_val_wrapper, False),
     ("model_dfpn", "DFPN", "compute_loss", dfpn_compute_loss, False),

@@ -339,3 +339,31 @@ def inpaint_ff(x, m, flows, nn_outs, s=1, D=20, e=1):
             y_comp = yc[:, :, 0]
         y[:, t] = y_comp[0]
     return y, k
+
+
+def inpaint_ip(x, m, flows, nn_outs, s=1, D=20, e=1):
+    """CHN.inpaint_ip (model_chn.py:135-189) with the DFPN aligner as a loop over the oracle's a2, a9-a11 (see
+    inpaint_ff).  x (3,n,h,w), m (1,n,h,w) are not modified.  Returns (y (3,n,h,w), number of steps)."""
+    y_inp, m_inp = x.copy(), m.copy()
+    n = x.shape[1]
+    order = sorted(range(n), key=lambda i: abs(i - n // 2))
+    k = 0
+    for t in order:
+        done = list(reversed(order[:order.index(t)]))
+        cand = [r for r in range(n) if r != t]
+        cand = [r for _, r in sorted((abs(r - t), r) for r in cand)]
+        cand = done + [r for r in cand if abs(r - t) <= D and abs(r - t) % s == 0 and r not in done]   # :484-503
+        y_comp, per = None, 0.0
+        while y_comp is None or (len(cand) > 0 and per > e):
+            r = cand.pop(0)
+            x_t, m_t = y_inp[None, :, t].copy(), m_inp[None, :, t].copy()
+            x_al, v_al, v_map = dfpn_align_tail(y_inp[None, :, r:r + 1], m_inp[None, :, r:r + 1], m_t, flows[k % len(flows)])
+            chn_pack(x_t, 1 - m_t, x_al, v_al, v_map)
+            _, yc = chn_composite(nn_outs[k % len(nn_outs)], x_t, 1 - m_t, 1, 1)
+            k += 1
+            m_new, x_new, per = hole_update(m_t, v_map[:, :, 0], yc[:, :, 0])                           # :181-186
+            m_inp[:, t], y_inp[:, t] = m_new[0], x_new[0]
+            y_comp = yc[:, :, 0]
+        m_inp[:, t] = 0
+        y_inp[:, t] = y_comp[0]
+    return y_inp, k

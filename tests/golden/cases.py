@@ -111,8 +111,8 @@ def corr_check(c, g, spec, tol):
     assert sample.shape == g["sample"].shape
     assert np.abs(sample - g["sample"]).max() <= tol
     total, abs_total = c.astype(np.float64).sum(), np.abs(c).astype(np.float64).sum()
-    assert abs(total - float(g["total"])) <= tol * c.size * 0.05 + 1e-6 * abs(float(g["total"]))
-    assert abs(abs_total - float(g["abs_total"])) <= tol * c.size * 0.05 + 1e-6 * abs(float(g["abs_total"]))
+    assert abs(total - float(g["total"])) <= tol * c.size * 0.5 + 1e-6 * abs(float(g["total"]))
+    assert abs(abs_total - float(g["abs_total"])) <= tol * c.size * 0.5 + 1e-6 * abs(float(g["abs_total"]))
 
 
 # a8 ----------------------------------------------------------------------
@@ -180,6 +180,10 @@ def chnloss_inputs(spec):
 # a9-a11 in context: CHN.inpaint_ff --------------------------------------------
 INPAINT_CASES = {
     "ff_n4": dict(seed=91, n=4, h=15, w=21, k=8),
+    "ip_n5": dict(seed=92, n=5, h=18, w=22, k=11, algo="ip"),
+    # a threshold that the sprinkled single-pixel holes keep the loops from reaching: several steps per frame
+    "ff_n6_long": dict(seed=93, n=6, h=16, w=20, k=13, e=0.05),
+    "ip_n6_long": dict(seed=94, n=6, h=16, w=20, k=13, e=0.05, algo="ip"),
 }
 
 
@@ -198,6 +202,12 @@ def get_indexes_ff(t, max_t, s, D):
     cand = [r for r in range(max_t) if r != t]
     cand = [r for _, r in sorted((abs(r - t), r) for r in cand)]
     return [r for r in cand if abs(r - t) <= D and abs(r - t) % s == 0]
+
+
+def get_indexes_ip(t, t_list, s, D):
+    """Reference-frame order of the inpaint-and-propagate algorithm (model_chn.py:484-503)."""
+    done = list(reversed(t_list[:t_list.index(t)]))
+    return done + [r for r in get_indexes_ff(t, len(t_list), s, D) if r not in done]
 
 
 # a5, broadcast masks (ADVICE r1: the denominator is torch.sum(mask) of the mask as given) -------------
@@ -262,3 +272,21 @@ def dfpnloss_inputs(spec):
     flow_hw = synth.dense_flow(spec["seed"] + 5, b, f, h, w, spec["sigma"], True)
     feats = np.maximum(r.standard_normal((b * n, 512, 16, 16)), 0).astype(np.float32)
     return x, m, y, flow_gt, np.array(spec["use"], dtype=bool), corr, flow_16, flow_64, flow_hw, feats
+
+
+# f3: CorrelationVGG.forward around the correlation (model_dfpn.py:491-532) ---------------------------
+CORRVGG_CASES = {
+    "f3": dict(seed=111, b=2, f=3, h=64, w=96, stride=53),
+    "f1_odd": dict(seed=112, b=1, f=1, h=50, w=70, stride=17),
+}
+
+
+def corrvgg_inputs(spec):
+    """x_target (b,3,h,w), m_target (b,1,h,w), x_refs (b,3,f,h,w), m_refs (b,1,f,h,w) and the VGG pool-4
+    features the stand-in network hands out: target (b,512,16,16), references (b*f,512,16,16)."""
+    b, f, h, w = spec["b"], spec["f"], spec["h"], spec["w"]
+    x, m, _ = synth.frames(spec["seed"], b, f + 1, h, w)
+    r = synth.rng(spec["seed"] + 1)
+    ft = np.maximum(r.standard_normal((b, 512, 16, 16)), 0).astype(np.float32)
+    fr = np.maximum(r.standard_normal((b * f, 512, 16, 16)), 0).astype(np.float32)
+    return x[:, :, 0].copy(), m[:, :, 0].copy(), x[:, :, 1:].copy(), m[:, :, 1:].copy(), ft, fr

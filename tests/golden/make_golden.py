@@ -44,7 +44,7 @@ def save(name, **arrays):
 from cases import WARP_CASES, CPN_CASES, CORR_CASES, CM_CASES, CHN_CASES, LOSS_CASES  # noqa: E402
 from cases import (warp_inputs, cpn_inputs, corr_inputs, cm_inputs, chn_inputs, loss_inputs,  # noqa: E402
                    chnloss_inputs, CHNLOSS_CASES, inpaint_inputs, INPAINT_CASES, l1_broadcast_inputs,
-                   LOWRES_CASES, lowres_inputs, DFPNLOSS_CASES, dfpnloss_inputs)
+                   LOWRES_CASES, lowres_inputs, DFPNLOSS_CASES, dfpnloss_inputs, CORRVGG_CASES, corrvgg_inputs)
 
 
 def main():
@@ -192,6 +192,26 @@ def main():
         else:
             save("corr_" + name, corr=c)
 
+    # ---- f3: the unmodified CorrelationVGG.forward (model_dfpn.py:491-532) with the VGG and the 4-D
+    # convolution replaced (preset features, identity): feature permute, nearest mask down-sample, correlation.
+    for name, spec in CORRVGG_CASES.items():
+        x_t, m_t, x_r, m_r, ft, fr = corrvgg_inputs(spec)
+        b = x_t.shape[0]
+
+        class FakeCorrVGG(object):
+            use_softmax = False
+            conv = staticmethod(lambda c: c)
+
+            def model_vgg(self, inp, normalize_input=True):     # first call: the target, second: the references
+                assert normalize_input is False
+                self.n = getattr(self, "n", 0) + 1
+                return [None, None, None, T(ft) if self.n == 1 else T(fr)]
+
+        c = CorrelationVGG.forward(FakeCorrVGG(), T(x_t), T(m_t), T(x_r), T(m_r)).numpy()
+        save("corrvgg_" + name, sample=c.reshape(-1)[::spec["stride"]].copy(),
+             total=np.float64(c.astype(np.float64).sum()), abs_total=np.float64(np.abs(c).astype(np.float64).sum()),
+             zero_rows=np.array([(c.reshape(c.shape[0], c.shape[1], 256, 256) == 0).all(-1).sum()], np.int64))
+
     # ---- a8: CM_Module.forward (model_cpn.py:206-254)
     for name, spec in CM_CASES.items():
         cf, vt, va = cm_inputs(spec)
@@ -294,7 +314,10 @@ def main():
                 return self.forward(*a)
 
         fake = FakeCHN3()
-        y = CHN.inpaint_ff(fake, T(x), T(m), s=1, D=20, e=1)
+        if spec.get("algo") == "ip":
+            y = CHN.inpaint_ip(fake, T(x).clone(), T(m).clone(), s=1, D=20, e=spec.get("e", 1))
+        else:
+            y = CHN.inpaint_ff(fake, T(x), T(m), s=1, D=20, e=spec.get("e", 1))
         save("inpaint_" + name, y=y.numpy(), steps=np.array([fake.k], np.int32))
 
 

@@ -113,7 +113,6 @@ STAGED_CASES = {
 
 
 DEFAULT_TILE_W = 32
-DEFAULT_CM_FUSED = 0
 
 
 def _set_tuning(name, value):
@@ -279,22 +278,23 @@ def test_corr4d_every_tile_variant(mtb, name, tn):
 
 
 # ---------------------------------------------------------------- a8
-@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("table", [1, 0])
 @pytest.mark.parametrize("name", sorted(cases.CM_CASES))
-def test_cm_module(mtb, name, fused):
-    """fused=1: the persistent pipelined kernel (cm.cu K3p); fused=0: the three-launch path."""
+def test_cm_module(mtb, name, table):
+    """table=1: masks | similarity | copy with the softmax looked up per mask pattern (default);
+    table=0: the separate per-pixel weights kernel (the path 8 references take)."""
     from master_thesis_b200 import ops
     cf, vt, va = cases.cm_inputs(cases.CM_CASES[name])
     g = load_golden("cm_" + name)
     oout, ocmask, ogs = oracle.cm_module(cf, vt, va, return_gs=True)
     try:
-        _set_tuning("MT_CM_FUSED", fused)
+        _set_tuning("MT_CM_TABLE", table)
         out, cmask = mtb.CM_Module()(dev(cf), dev(vt), dev(va))
         out, cmask = host(out), host(cmask)
         _, _, gs = ops.cm_match(dev(cf), dev(vt), dev(va), return_gs=True)
         gs = gs.clone()
     finally:
-        _set_tuning("MT_CM_FUSED", DEFAULT_CM_FUSED)
+        _set_tuning("MT_CM_TABLE", 1)
     assert np.abs(host(gs) - ogs).max() <= 1e-6 * max(1.0, np.abs(ogs).max())
     assert np.abs(out - oout).max() <= 1e-5 and np.abs(cmask - ocmask).max() <= 2e-6
     assert np.abs(cmask - g["c_mask"]).max() <= 2e-6
@@ -304,25 +304,25 @@ def test_cm_module(mtb, name, fused):
         assert np.abs(out.reshape(-1)[::53] - g["sample"]).max() <= 1e-5
 
 
-@pytest.mark.parametrize("shape", [(5, 4, 9, 24, 48), (3, 2, 5, 32, 32), (9, 5, 16, 16, 80), (1, 8, 6, 16, 16)])
-def test_cm_pipelined_ragged(mtb, shape):
-    """The persistent kernel against the oracle and the three-launch path on shapes that leave
-    partial 1024-pixel chunks, a channel count that is not a multiple of the slab, more samples
-    than the lag, one sample, and 1 / 3 / 4 / 7 references."""
+@pytest.mark.parametrize("shape", [(5, 4, 9, 24, 48), (3, 2, 5, 32, 32), (9, 5, 16, 16, 80), (1, 8, 6, 16, 16),
+                                   (2, 9, 7, 16, 24)])
+def test_cm_ragged(mtb, shape):
+    """Both weight paths against the oracle on shapes that leave partial 1024-pixel chunks, a channel count
+    that is not a multiple of the slab, one sample, and 1 / 3 / 4 / 7 / 8 references."""
     from master_thesis_b200 import ops, synth
     b, f, c, h, w = shape
     cf, vt, va = synth.cm_inputs(61 + b, b, f, c, h, w, 4)
     oout, ocm, ogs = oracle.cm_module(cf, vt, va, return_gs=True)
     res = {}
     try:
-        for fused in (1, 0):
-            _set_tuning("MT_CM_FUSED", fused)
+        for table in (1, 0):
+            _set_tuning("MT_CM_TABLE", table)
             out, cmask, gs = ops.cm_match(dev(cf), dev(vt), dev(va), return_gs=True)
-            res[fused] = (host(out), host(cmask), host(gs.clone()))
+            res[table] = (host(out), host(cmask), host(gs.clone()))
     finally:
-        _set_tuning("MT_CM_FUSED", DEFAULT_CM_FUSED)
-    for fused in (1, 0):
-        out, cmask, gs = res[fused]
+        _set_tuning("MT_CM_TABLE", 1)
+    for table in (1, 0):
+        out, cmask, gs = res[table]
         assert np.abs(gs - ogs).max() <= 1e-6 * max(1.0, np.abs(ogs).max())
         assert np.abs(out - oout).max() <= 1e-5 and np.abs(cmask - ocm).max() <= 2e-6
     # same partial sums folded in a different (fixed) order: the two paths agree to rounding
@@ -475,23 +475,24 @@ def test_inference_step_fusions(mtb):
         assert torch.equal(a_, b_)
 
 
-@pytest.mark.parametrize("fused", [True, False])
-@pytest.mark.parametrize("name", sorted(cases.INPAINT_CASES))
-def test_inpaint_ff_mirror(mtb, name, fused):
-    """The patched CHN.inpaint_ff (two fused kernels per step, or the four-kernel route for a foreign
-    aligner) against the output of the unmodified reference loop, bit for bit."""
+def _inpaint_harness(spec, x, m, flows, nn_outs, fused, sync_every=1, by_content=False):
+    """Stand-ins for the CHN module and its DFPN aligner around the patched loops: the DFPN forward and the
+    RRDBNet hand out preset tensors - in call order (as make_golden.py's stand-ins do), or chosen by the content
+    of their inputs (``by_content``: a step that is repeated on the same state gets the same tensors)."""
     from master_thesis_b200 import plug
-    x, m, flows, nn_outs = cases.inpaint_inputs(cases.INPAINT_CASES[name])
-    g = load_golden("inpaint_" + name)
+
+    def pick(presets, counter, t):
+        if by_content:
+            return dev(presets[int(float(t.double().abs().sum()) * 1000.0) % len(presets)])
+        return dev(presets[counter % len(presets)])
 
     class _DFPNLike(object):
         def __init__(self):
             self.n = 0
 
-        def __call__(self, *a):
-            i = self.n
+        def __call__(self, x_target, m_target, x_refs, m_refs):
             self.n += 1
-            return None, None, None, dev(flows[i % len(flows)])
+            return None, None, None, pick(flows, self.n - 1, m_target + x_refs[:, :1, 0])
 
     if fused:
         _DFPNLike.align = plug.dfpn_align
@@ -501,24 +502,54 @@ def test_inpaint_ff_mirror(mtb, name, fused):
     class _CHNLike(object):
         forward = plug.chn_forward
         inpaint_ff = plug.chn_inpaint_ff
+        inpaint_ip = plug.chn_inpaint_ip
         get_indexes_ff = staticmethod(cases.get_indexes_ff)
+        get_indexes_ip = staticmethod(cases.get_indexes_ip)
+        mt_b200_sync_every = sync_every
 
         def __init__(self):
             self.model_aligner = _DFPNLike()
             self.k = 0
 
         def nn(self, inp):
-            i = self.k
             self.k += 1
-            return dev(nn_outs[i % len(nn_outs)])
+            return pick(nn_outs, self.k - 1, inp[:, 6:])      # the three visibility channels of the CNN input
 
         def __call__(self, *a):
             return self.forward(*a)
 
     chn = _CHNLike()
-    y = chn.inpaint_ff(dev(x), dev(m), s=1, D=20, e=1)
-    assert chn.k == int(g["steps"][0])
-    assert np.array_equal(host(y), g["y"])
+    algo = chn.inpaint_ip if spec.get("algo") == "ip" else chn.inpaint_ff
+    y = algo(dev(x).clone(), dev(m).clone(), s=1, D=20, e=spec.get("e", 1))
+    return host(y), chn.k
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", sorted(cases.INPAINT_CASES))
+def test_inpaint_mirrors(mtb, name, fused):
+    """The patched CHN.inpaint_ff / inpaint_ip (two fused kernels per step, or the four-kernel route a foreign
+    aligner takes) against the output of the unmodified reference loops, bit for bit."""
+    spec = cases.INPAINT_CASES[name]
+    x, m, flows, nn_outs = cases.inpaint_inputs(spec)
+    g = load_golden("inpaint_" + name)
+    y, k = _inpaint_harness(spec, x, m, flows, nn_outs, fused)
+    assert k == int(g["steps"][0])
+    assert np.array_equal(y, g["y"])
+
+
+@pytest.mark.parametrize("sync_every", [2, 3, 8])
+@pytest.mark.parametrize("name", sorted(cases.INPAINT_CASES))
+def test_inpaint_device_side_loop_control(mtb, name, sync_every):
+    """with the loop condition evaluated on the device (gated fill step) and the host looking only
+    every k steps, the inpainted frames are bit-identical to the one-sync-per-step loop; the surplus steps (at
+    most k - 1 per target frame) run as no-ops."""
+    spec = cases.INPAINT_CASES[name]
+    x, m, flows, nn_outs = cases.inpaint_inputs(spec)
+    y1, k1 = _inpaint_harness(spec, x, m, flows, nn_outs, True, 1, by_content=True)
+    yk, kk = _inpaint_harness(spec, x, m, flows, nn_outs, True, sync_every, by_content=True)
+    assert np.array_equal(yk, y1)
+    assert k1 <= kk <= k1 + (sync_every - 1) * x.shape[1]
+    assert k1 > x.shape[1] or "long" not in name      # the long cases really iterate
 
 
 def test_no_out_of_bounds_writes(mtb):
@@ -580,16 +611,16 @@ def test_no_out_of_bounds_writes(mtb):
         y_target, v_target, y_hat, y_comp, v_map2 = cases.chnloss_inputs(cases.CHNLOSS_CASES["f1_odd"])
         yh2, yc2 = dev(y_hat).requires_grad_(True), dev(y_comp).requires_grad_(True)
         sum(ops.chn_l1_terms(dev(y_target), dev(v_target), yh2, yc2, dev(v_map2))).backward()
-        # CM: three-launch path and the experimental pipelined kernel, ragged shapes
+        # CM: both weight paths, ragged shapes
         for shape in ((5, 4, 9, 24, 48), (3, 2, 5, 32, 32)):
             b, f, c, h, w = shape
             cf, vt, va = cases.synth.cm_inputs(61 + b, b, f, c, h, w, 4)
-            for fused in (0, 1):
+            for table in (1, 0):
                 try:
-                    _set_tuning("MT_CM_FUSED", fused)
+                    _set_tuning("MT_CM_TABLE", table)
                     ops.cm_match(dev(cf), dev(vt), dev(va))
                 finally:
-                    _set_tuning("MT_CM_FUSED", DEFAULT_CM_FUSED)
+                    _set_tuning("MT_CM_TABLE", 1)
         # correlation and the fused DFPN loss
         ft, vtt, fr, vr = cases.synth.vgg_feats(5, 1, 2)
         ops.corr4d(dev(ft), dev(vtt), dev(fr), dev(vr))
@@ -874,9 +905,9 @@ def test_dfpn_training_step_mirrors(mtb, name):
     # the hot path of the step is exactly these launches: no align_set, no mask_out, no x_aligned in HBM
     assert sorted(plan.names()) == sorted(["mt_corr4d_fwd"] + ["mt_masked_l1_fwd"] * 3 + ["mt_warp_l1_fwd"] * 2 +
                                           ["mt_warp_l1_bwd"] * 2 + ["mt_masked_l1_bwd"] * 3)
-    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-5)
     # corr_loss compares a TF32 correlation of the ground truth with the given volume: |d| <= 7e-4 per element
     assert abs(float(items[0]) - float(g["items"][0])) <= 1e-3
+    assert float(loss) - float(items[0]) == pytest.approx(float(g["loss"]) - float(g["items"][0]), rel=1e-5)
     assert np.allclose([float(i) for i in items[1:]], g["items"][1:], rtol=1e-5, atol=0)
     assert np.abs(host(grads[2]) - g["g_flow64"]).max() <= 2e-5 * np.abs(g["g_flow64"]).max()
     assert np.abs(host(grads[3]) - g["g_flowhw"]).max() <= 2e-5 * np.abs(g["g_flowhw"]).max()
@@ -885,3 +916,40 @@ def test_dfpn_training_step_mirrors(mtb, name):
     # a consumer that treats an xs_aligned entry as a tensor gets the aligned frames
     assert float(res[4][2].double().sum()) == pytest.approx(float(g["xhw_al_sum"]), rel=1e-6)
     assert float(torch.sum(res[4][1]).double()) == pytest.approx(float(g["x64_al_sum"]), rel=1e-5)
+
+
+# ---------------------------------------------------------------- f3: CorrelationVGG.forward neighbours
+@pytest.mark.parametrize("tn", [0, 64, 128, 256])
+@pytest.mark.parametrize("name", sorted(cases.CORRVGG_CASES))
+def test_corr_vgg_forward_mirror(mtb, name, tn):
+    """The patched CorrelationVGG.forward: strided (un-permuted) VGG features and full-resolution masks go
+    straight into the tensor-core kernel; against the unmodified reference's output and the CPU oracle."""
+    from master_thesis_b200 import _lib, plug
+    spec = cases.CORRVGG_CASES[name]
+    x_t, m_t, x_r, m_r, ft, fr = cases.corrvgg_inputs(spec)
+    g = load_golden("corrvgg_" + name)
+    b, f = spec["b"], spec["f"]
+
+    class _CorrLike(object):
+        use_softmax = False
+        conv = staticmethod(lambda c: c)
+
+        def __init__(self):
+            self.n = 0
+
+        def model_vgg(self, inp, normalize_input=True):
+            self.n += 1
+            return [None, None, None, dev(ft) if self.n == 1 else dev(fr)]
+
+    try:
+        _set_tuning("MT_CORR_TN", tn)
+        with _lib.record() as plan:
+            c = host(plug.corr_vgg_forward(_CorrLike(), dev(x_t), dev(m_t), dev(x_r), dev(m_r)))
+    finally:
+        _set_tuning("MT_CORR_TN", 0)
+    assert plan.names() == ["mt_corr4d_vgg_fwd"]      # no permute copy, no mask kernels
+    cases.corr_check(c, g, spec, 2e-3)
+    feats_r = fr.reshape(b, f, 512, 16, 16).transpose(0, 2, 1, 3, 4)
+    o = oracle.corr4d(ft, oracle.vis_nearest(m_t, (16, 16)), feats_r, oracle.vis_nearest(m_r, (16, 16)))
+    assert np.abs(c - o).max() <= 2e-3 and np.array_equal(c == 0.0, o == 0.0)
+    assert int((c.reshape(b, f, 256, 256) == 0).all(-1).sum()) == int(g["zero_rows"][0])

@@ -93,7 +93,8 @@ def test_inpaint_ff(name):
     """a2 + a9-a11 chained as the unmodified CHN.inpaint_ff chains them (model_chn.py:87-133)."""
     x, m, flows, nn_outs = cases.inpaint_inputs(cases.INPAINT_CASES[name])
     g = load_golden("inpaint_" + name)
-    y, steps = oracle.inpaint_ff(x, m, flows, nn_outs)
+    algo = oracle.inpaint_ip if cases.INPAINT_CASES[name].get("algo") == "ip" else oracle.inpaint_ff
+    y, steps = algo(x, m, flows, nn_outs, e=cases.INPAINT_CASES[name].get("e", 1))
     assert steps == int(g["steps"][0])
     assert np.array_equal(y, g["y"])
 
@@ -238,3 +239,17 @@ def test_torch_port_matches_golden():
     x, m, flow, flow_gt, use, t, r_list = cases.loss_inputs(cases.LOSS_CASES["f4"])
     rec = tp.alignment_recons(T(x)[:, :, t], T(1 - m)[:, :, t], T(x)[:, :, r_list], T(1 - m)[:, :, r_list], T(flow))
     assert float(rec) == float(load_golden("loss_f4")["recons"])
+
+
+@pytest.mark.parametrize("name", sorted(cases.CORRVGG_CASES))
+def test_corr_vgg_forward_neighbours(name):
+    """f3: CorrelationVGG.forward between its two networks (model_dfpn.py:516-528): feature permute, nearest
+    down-sample of 1 - m to the feature resolution, masked correlation."""
+    spec = cases.CORRVGG_CASES[name]
+    x_t, m_t, x_r, m_r, ft, fr = cases.corrvgg_inputs(spec)
+    g = load_golden("corrvgg_" + name)
+    b, f = spec["b"], spec["f"]
+    feats_r = fr.reshape(b, f, 512, 16, 16).transpose(0, 2, 1, 3, 4)
+    c = oracle.corr4d(ft, oracle.vis_nearest(m_t, (16, 16)), feats_r, oracle.vis_nearest(m_r, (16, 16)))
+    cases.corr_check(c, g, spec, 2e-6)
+    assert int((c.reshape(b, f, 256, 256) == 0).all(-1).sum()) == int(g["zero_rows"][0])

@@ -1,0 +1,36 @@
+"""Launches the three headline kernels a few times on rotating inputs (for ncu -k captures):
+corr_tc_kernel at 128 frames, the DFPN direct-gather warp and the staged CPN warp at 32 frames."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import master_thesis_b200 as mtb                     # noqa: E402
+from master_thesis_b200 import ops, synth            # noqa: E402
+
+dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()   # noqa: E731
+which = sys.argv[1:] or ["corr", "dfpn", "cpn"]
+sets = []
+for i in range(3):
+    d = {}
+    if "corr" in which:
+        ft, vt, fr, vr = synth.vgg_feats(10 + i, 32, 4)
+        d["corr"] = tuple(dev(a) for a in (ft, vt, fr, vr))
+    x, m, _ = synth.frames(20 + i, 8, 5, 256, 256)
+    d["x"], d["m"], d["mt"] = dev(x[:, :, 1:]), dev(m[:, :, 1:]), dev(m[:, :, 0])
+    d["flow"] = dev(synth.dense_flow(30 + i, 8, 4, 256, 256, 0.05, True))
+    d["theta"] = dev(synth.thetas(40 + i, 32, 0.1))
+    sets.append(d)
+torch.cuda.synchronize()
+for rep in range(3):
+    for d in sets:
+        if "corr" in which:
+            ops.corr4d(*d["corr"])
+        if "dfpn" in which:
+            mtb.dfpn_align_tail(d["x"], d["m"], d["mt"], d["flow"])
+        if "cpn" in which:
+            mtb.cpn_align_tail(d["x"], d["m"], d["mt"], d["theta"])
+torch.cuda.synchronize()
+print("ok")
