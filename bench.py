@@ -498,6 +498,46 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+
+def bind_to_gpu_numa(device_index):
+    """Pins this rank to the CPUs NVML reports as local to its GPU BEFORE any pinned host buffer is allocated, so
+    that first-touch places the staging buffers on the GPU's NUMA node (N ranks on one node otherwise share
+    whatever node the launcher started them on).  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(cpus & allowed)
+        if not cpus:
+            return {"bound": False, "why": "NVML reports no local CPU inside this process's cpuset"}
+        os.sched_setaffinity(0, cpus)
+        node = None
+        try:
+            for n in sorted(os.listdir("/sys/devices/system/node")):
+                if n.startswith("node") and n[4:].isdigit():
+                    lst = open("/sys/devices/system/node/%s/cpulist" % n).read().strip()
+                    ids = set()
+                    for part in lst.split(","):
+                        if part:
+                            lo, _, hi = part.partition("-")
+                            ids.update(range(int(lo), int(hi or lo) + 1))
+                    if cpus[0] in ids:
+                        node = int(n[4:])
+        except Exception:
+            pass
+        return {"bound": True, "cpus": "%d-%d (%d)" % (cpus[0], cpus[-1], len(cpus)), "numa_node": node}
+    except Exception as e:      # noqa: BLE001
+        return {"bound": False, "why": str(e)[:80]}
+
 # ---------------------------------------------------------------------------
 # CPU arms
 # ---------------------------------------------------------------------------
@@ -575,6 +615,7 @@ def run_gpu(args):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL_DEBUG is left as the caller set it: fd 1 is redirected to stderr for the whole run (_RealStdout),
@@ -778,7 +819,7 @@ def run_gpu(args):
                                    "the median repetition" % (len(rounds), K)},
         "rounds_ms": {"n": len(rounds), "min": min(rounds), "median": ms, "max": max(rounds),
                       "integrated_ms": sum(rounds), "instrumented": ms_instr},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K,
+        "clocks": clocks, "e2e": e2e, "host_affinity": affinity, "gpu_launches": launches_per_step * K,
         "roofline": roofline, "kernels": per_call,
     }
     line.update(line_extra)
@@ -855,9 +896,42 @@ def run_e2e(args, wl, mtb, ops, host, dev, world):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # the platform's ceiling for this step: the same pinned copies on the same two streams, no kernels
+    # (all ranks at once: at N > 1 they share the host's memory bandwidth and PCIe root ports)
+    def copies_only(i):
+        st, pin_in, d_in, plan, out, pin_out = slots[i % 2]
+        with torch.cuda.stream(st):
+            for k in pin_in:
+                d_in[k].copy_(pin_in[k], non_blocking=True)
+            for k in out:
+                pin_out[k].copy_(out[k], non_blocking=True)
+
+    Kc = max(2, min(K, 20))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(main)
+    for st, *_ in slots:
+        st.wait_stream(main)
+    for i in range(Kc):
+        copies_only(i)
+    for st, *_ in slots:
+        main.wait_stream(st)
+    c1.record(main)
+    torch.cuda.synchronize()
+    ms_copy = c0.elapsed_time(c1)
+    if world > 1:
+        t = torch.tensor([ms_copy], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_copy = float(t.item())
     return {"value": wl.frames_per_step * world * K / (ms * 1e-3), "unit": "frames/s",
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": K,
             "ms_per_step": ms / K,
+            "copies_only_ms_per_step": ms_copy / Kc,
+            "copies_only_gbs_per_rank": (h2d + d2h) / (ms_copy / Kc * 1e-3) / 1e9,
+            "fraction_of_copy_ceiling": (ms_copy / Kc) / (ms / K),
             "api": "master_thesis_b200 plug-point mirrors on pinned host tensors, 2 pipelined streams"}
 
 

@@ -265,9 +265,11 @@ MT_API int mt_corr4d_vgg_fwd(const float *feats_t, int64_t ft_sb, int64_t ft_sc,
  * c_feats (B,C,f,h,w) contiguous (index 0 of f = target), v_t (B,1,H,W),
  * v_aligned (B,1,f-1,H,W) contiguous.  out (B,2C+1,h,w) = cat[c_t,c_out,c_mask],
  * c_mask (B,1,h,w).  1 <= f-1 <= 8, h*w % 4 == 0.
- * Launches: masks (bilinear down-sample > 0.5, one byte per pixel), similarity partials, then the
- * weighted copy, which folds the partials and looks the softmax weights up per mask pattern
- * (f-1 <= 7; with 8 references a separate weights kernel runs).
+ * Launches: masks (bilinear down-sample > 0.5, one byte per pixel), then ONE grouped launch: the resident
+ * grid is split into groups of CTAs, a group streams the features of its sample once from HBM for the
+ * similarities, synchronises among its own CTAs only, builds the softmax table per mask pattern and walks
+ * the same features again from L2 for the weighted copy (f-1 <= 7; tuning MT_CM_TABLE=1: similarity and copy as
+ * two launches; with 8 references, or MT_CM_TABLE=0: a separate per-pixel weights kernel).
  * workspace: mt_cm_workspace_bytes(B, C, f, h, w) bytes (no zeroing needed). */
 MT_API int mt_cm_match_fwd(const float *c_feats, const float *v_t, const float *v_aligned,
                     float *out, float *c_mask, void *workspace,

@@ -37,6 +37,7 @@ namespace {
 constexpr int kSimChannels = 4;   // default channels per CTA slab in pass 1 (swept on B200: profiles/)
 constexpr int kCopyChannels = 4;  // default channels per CTA slab in pass 2 (template CC)
 constexpr int kMaxRefs = 8;
+constexpr int kMaxGroupCtas = 512;  // CTAs per group of cm_group_kernel (rows of per-CTA partials per sample)
 
 struct CmArgs {
     const float *c_feats, *v_t, *v_al;
@@ -48,6 +49,10 @@ struct CmArgs {
     int B, C, f, h, w, H, W, P, R, nparts, chunks, sim_ch, b_off;
     unsigned char *pmask;        // (B, P) bit 0: vt', bit r + 1: vr' of reference r
     int copy_reverse;
+    // grouped single-launch variant (cm_group_kernel)
+    unsigned int *counters;      // (B) arrivals per sample, zeroed by cm_masks
+    float *gpart;                // (B, S, 2R) per-CTA partials
+    int G, S;                    // samples in flight (groups of S CTAs)
 };
 
 // F.interpolate(bilinear, align_corners=False) source index (UpSample.h)
@@ -66,6 +71,7 @@ __global__ void __launch_bounds__(256) cm_masks_kernel(const CmArgs a) {
     pdl_sync();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
+    if (p == 0) a.counters[b] = 0u;  // arrival counter of cm_group_kernel (this kernel precedes it in the stream)
     if (p >= a.P) return;
     const int y = p / a.w, x = p - y * a.w;
     int y0, y1, x0, x1;
@@ -73,19 +79,58 @@ __global__ void __launch_bounds__(256) cm_masks_kernel(const CmArgs a) {
     src_index(y, __fdiv_rn((float)a.H, (float)a.h), a.H, y0, y1, ly0, ly1);
     src_index(x, __fdiv_rn((float)a.W, (float)a.w), a.W, x0, x1, lx0, lx1);
     unsigned int bits = 0u;
-    for (int j = 0; j < a.f; ++j) {  // j = 0: target, j >= 1: reference j - 1
-        const float *src = (j == 0) ? a.v_t + (int64_t)b * a.H * a.W
-                                    : a.v_al + ((int64_t)b * a.R + (j - 1)) * a.H * a.W;
-        const float v00 = __ldg(src + y0 * a.W + x0), v01 = __ldg(src + y0 * a.W + x1);
-        const float v10 = __ldg(src + y1 * a.W + x0), v11 = __ldg(src + y1 * a.W + x1);
-        const float top = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
-        const float bot = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
-        const float val = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
-        const bool on = val > 0.5f;                                            // model_cpn.py:208-217
-        a.masks[((int64_t)b * a.f + j) * a.P + p] = on ? 1.0f : 0.0f;
-        bits |= on ? (1u << j) : 0u;
+    // all 4 * f taps are requested before the first use: one DRAM round trip instead of f
+    float v00[kMaxRefs + 1], v01[kMaxRefs + 1], v10[kMaxRefs + 1], v11[kMaxRefs + 1];
+#pragma unroll
+    for (int j = 0; j <= kMaxRefs; ++j) {  // j = 0: target, j >= 1: reference j - 1
+        if (j < a.f) {
+            const float *src = (j == 0) ? a.v_t + (int64_t)b * a.H * a.W
+                                        : a.v_al + ((int64_t)b * a.R + (j - 1)) * a.H * a.W;
+            v00[j] = __ldg(src + y0 * a.W + x0); v01[j] = __ldg(src + y0 * a.W + x1);
+            v10[j] = __ldg(src + y1 * a.W + x0); v11[j] = __ldg(src + y1 * a.W + x1);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j <= kMaxRefs; ++j) {
+        if (j < a.f) {
+            const float top = __fadd_rn(__fmul_rn(lx0, v00[j]), __fmul_rn(lx1, v01[j]));
+            const float bot = __fadd_rn(__fmul_rn(lx0, v10[j]), __fmul_rn(lx1, v11[j]));
+            const float val = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+            const bool on = val > 0.5f;                                            // model_cpn.py:208-217
+            a.masks[((int64_t)b * a.f + j) * a.P + p] = on ? 1.0f : 0.0f;
+            bits |= on ? (1u << j) : 0u;
+        }
     }
     a.pmask[(int64_t)b * a.P + p] = (unsigned char)bits;
+}
+
+// masked_softmax over the references, once per mask pattern t                         :245-254
+// (same operations in the same order as the per-pixel code of cm_weights_kernel)
+template <int R>
+__device__ __forceinline__ void softmax_table(const float *gs_smem, float *tab) {
+    for (int t = threadIdx.x; t < (1 << R); t += blockDim.x) {
+        float vr[R], wv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) vr[r] = ((t >> r) & 1) ? 1.0f : 0.0f;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < R; ++r) mx = fmaxf(mx, __fmul_rn(gs_smem[r], vr[r]));
+        float sum = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            wv[r] = __fmul_rn(expf(__fsub_rn(__fmul_rn(gs_smem[r], vr[r]), mx)), vr[r]);
+            sum = __fadd_rn(sum, wv[r]);
+        }
+        if (sum < 1e-4f) sum = __fadd_rn(sum, 1.0f);
+        float cm = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            wv[r] = __fdiv_rn(wv[r], sum);
+            cm = __fadd_rn(cm, __fmul_rn(wv[r], vr[r]));                          // :240
+            tab[t * (R + 1) + r] = wv[r];
+        }
+        tab[t * (R + 1) + R] = __fsub_rn(1.0f, cm);                               // :241
+    }
 }
 
 // gs[b, :] from the partials of sample b (fixed order, double).  Result in smem gs[R].
@@ -394,30 +439,7 @@ __global__ void __launch_bounds__(256, 2) cm_copy2_kernel(const CmArgs a) {
         }
     }
     __syncthreads();
-    // ---- masked_softmax over the references, once per mask pattern t                :245-254 ----
-    for (int t = tid; t < (1 << R); t += 256) {
-        float vr[R], wv[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) vr[r] = ((t >> r) & 1) ? 1.0f : 0.0f;
-        float mx = -INFINITY;
-#pragma unroll
-        for (int r = 0; r < R; ++r) mx = fmaxf(mx, __fmul_rn(gs_smem[r], vr[r]));
-        float sum = 0.0f;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            wv[r] = __fmul_rn(expf(__fsub_rn(__fmul_rn(gs_smem[r], vr[r]), mx)), vr[r]);
-            sum = __fadd_rn(sum, wv[r]);
-        }
-        if (sum < 1e-4f) sum = __fadd_rn(sum, 1.0f);
-        float cm = 0.0f;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            wv[r] = __fdiv_rn(wv[r], sum);
-            cm = __fadd_rn(cm, __fmul_rn(wv[r], vr[r]));                          // :240
-            tab[t * (R + 1) + r] = wv[r];
-        }
-        tab[t * (R + 1) + R] = __fsub_rn(1.0f, cm);                               // :241
-    }
+    softmax_table<R>(gs_smem, tab);  // masked_softmax once per mask pattern        :245-254
     __syncthreads();
     if (slab == 0 && blockIdx.x == 0 && tid < R) a.gs[(int64_t)b * R + tid] = gs_smem[tid];
     if (!live) return;
@@ -450,9 +472,262 @@ __global__ void __launch_bounds__(256, 2) cm_copy2_kernel(const CmArgs a) {
     }
 }
 
+
+// ---- single launch for pass 1 + 1b + 2: c_feats crosses HBM ONCE -------------------------------------
+// The resident grid (2 CTAs per SM) is split into G groups of S CTAs; group g owns samples g, g + G, ...
+// For its sample every CTA of the group
+//   1. streams its share of the (channel, 1024-pixel chunk) items from HBM in batches of UN items, accumulates
+//      the R masked dot products (pass 1) and already writes the c_t half of cat[c_t, ...] (it does not depend
+//      on the similarities); then stores its partials and arrives on the sample's counter;
+//   2. waits until the S CTAs of the group have arrived (one thread spins on an acquire load; the other groups
+//      are not involved - K3p's post-mortem: the hand-off must be per group of SMs, not global), folds the S
+//      partials in fixed order in double and builds the softmax table per mask pattern;
+//   3. walks its batches again in REVERSE order for sum_r w_r c_r and c_mask: the last batch is still in
+//      registers, the `keep` batches before it were parked in shared memory, the rest is what this CTA left
+//      in L2 microseconds ago (G samples in flight are G * C * f * P * 4 B = 84 MB at B = 8, 128 x 5 x 64 x 64,
+//      of the 126 MB; read with evict-first loads).  ncu at cfg2: 87 MB read from DRAM (the 3-launch form: 179 MB).
+// Every CTA of the grid is resident (grid <= SMs x occupancy), so the spin cannot deadlock.
+template <int R>
+struct CmGroupCfg {
+    static constexpr int UN = R <= 3 ? 4 : (R == 4 ? 3 : 2);  // items per batch: UN * (R + 1) 16 B loads in flight per thread
+    static constexpr int kBatchBytes = UN * R * 256 * 16;     // reference features of one batch parked in shared memory
+};
+
+template <int R>
+__global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const int keep) {
+    constexpr int G2 = 2 * R, TABF = (1 << R) * (R + 1), UN = CmGroupCfg<R>::UN;
+    constexpr int kMw = 4;  // mask words cached per thread (one per 1024-pixel chunk) when the sample has <= kMw chunks
+    __shared__ float red[G2 * 32];
+    __shared__ double dred[256];
+    __shared__ float gs_smem[R];
+    __shared__ float tab[TABF];
+    extern __shared__ __align__(16) uint8_t cm_dyn[];
+    float4 *park = reinterpret_cast<float4 *>(cm_dyn);  // [keep][UN][R][256]
+    pdl_launch();
+    const int tid = threadIdx.x;
+    const int g = (int)blockIdx.x % a.G, s = (int)blockIdx.x / a.G;
+    if (s >= a.S) return;
+    const int NI = a.C * a.chunks;
+    const int lo = (int)((int64_t)s * NI / a.S), hi = (int)((int64_t)(s + 1) * NI / a.S);
+    const int nb = (hi - lo + UN - 1) / UN;  // batches of this CTA
+    // pass 2 takes batch nb - 1 from registers, batches 0 .. np - 1 (the oldest in L2) from shared memory, the rest from L2
+    const int np = min(keep, nb - 1);
+    const int fP = a.f * a.P;  // 32-bit offsets within a sample (the launcher checks (2C + 1) * f * P < 2^31)
+    const bool mw_cached = a.chunks <= kMw;
+    bool waited = false;  // griddepcontrol.wait (cm_masks complete) once, after the first feature loads are in flight
+#pragma unroll 1
+    for (int b = g; b < a.B; b += a.G) {
+        const float *fb = a.c_feats + (int64_t)b * a.C * fP;
+        const unsigned char *pm = a.pmask + (int64_t)b * a.P;
+        float *ob = a.out + (int64_t)b * (2 * a.C + 1) * a.P;
+        uint32_t mwq[kMw] = {0u, 0u, 0u, 0u};
+        auto mask_word = [&](int q, int p) -> uint32_t {
+            if (mw_cached) {
+                uint32_t w = mwq[0];
+#pragma unroll
+                for (int j = 1; j < kMw; ++j) w = q == j ? mwq[j] : w;
+                return w;
+            }
+            return __ldcg(reinterpret_cast<const uint32_t *>(pm + p));
+        };
+        auto load_cr = [&](int bi, float4 (&cr)[UN][R], bool stream) {
+            const int it = lo + bi * UN;
+#pragma unroll
+            for (int k = 0; k < UN; ++k) {
+                // slots past the CTA's range / the chunk's end load a valid (clamped) address and are skipped by the
+                // consumers: unconditional loads keep the register live ranges apart (ptxas spilled otherwise)
+                const int i = min(it + k, hi - 1), c = i / a.chunks, p = (i - c * a.chunks) * 1024 + tid * 4;
+                const float *base = fb + (c * fP + min(p, a.P - 4));
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    cr[k][r] = stream ? ld_stream4(base + (r + 1) * a.P)
+                                      : __ldg(reinterpret_cast<const float4 *>(base + (r + 1) * a.P));
+            }
+        };
+        // ---------------- pass 1: partial dot products of this CTA's items, c_t copied through ----------------
+        float acc[G2];
+#pragma unroll
+        for (int r = 0; r < G2; ++r) acc[r] = 0.0f;
+        float4 cr[UN][R];  // the last batch stays here for pass 2
+#pragma unroll 1
+        for (int bi = 0; bi < nb; ++bi) {
+            const int it = lo + bi * UN;
+            float4 ct[UN];
+#pragma unroll
+            for (int k = 0; k < UN; ++k) {
+                const int i = min(it + k, hi - 1), c = i / a.chunks, p = (i - c * a.chunks) * 1024 + tid * 4;
+                ct[k] = __ldg(reinterpret_cast<const float4 *>(fb + (c * fP + min(p, a.P - 4))));
+            }
+            load_cr(bi, cr, false);  // default L2 policy: part of it is read again in pass 2
+            if (!waited) { pdl_wait(); waited = true; }
+            if (bi == 0 && mw_cached) {
+#pragma unroll
+                for (int j = 0; j < kMw; ++j)
+                    mwq[j] = (j < a.chunks && j * 1024 + tid * 4 < a.P) ? __ldcg(reinterpret_cast<const uint32_t *>(pm + j * 1024 + tid * 4)) : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < UN; ++k) {
+                const int i = it + k, c = i / a.chunks, q = i - c * a.chunks, p = q * 1024 + tid * 4;
+                if (i >= hi || p >= a.P) continue;
+                const uint32_t mw = mask_word(q, p);
+                st_stream4(ob + (c * a.P + p), ct[k]);                             // cat[c_t, ...]  :243
+#pragma unroll
+                for (int r = 0; r < R; ++r) {  // vt' * vr'                  :220
+                    const uint32_t m = mw & (mw >> (r + 1)) & 0x01010101u;
+                    const float4 vm = make_float4((float)(m & 1u), (float)((m >> 8) & 1u), (float)((m >> 16) & 1u),
+                                                  (float)((m >> 24) & 1u));
+                    if (c == 0) acc[R + r] += (vm.x + vm.y) + (vm.z + vm.w);       // :221 (once per pixel)
+                    acc[r] += vm.x * ct[k].x * cr[k][r].x;                         // :226
+                    acc[r] += vm.y * ct[k].y * cr[k][r].y;
+                    acc[r] += vm.z * ct[k].z * cr[k][r].z;
+                    acc[r] += vm.w * ct[k].w * cr[k][r].w;
+                    if (bi < np) park[((bi * UN + k) * R + r) * 256 + tid] = cr[k][r];
+                }
+            }
+        }
+        if (!waited) { pdl_wait(); waited = true; }
+        block_sum<G2>(acc, red);
+        if (tid == 0) {
+            float *o = a.gpart + ((int64_t)b * a.S + s) * G2;
+#pragma unroll
+            for (int r = 0; r < G2; ++r) o[r] = acc[r];
+            __threadfence();
+            atomicAdd(a.counters + b, 1u);
+            unsigned int seen;
+            do {  // the S CTAs of this group only
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.counters + b) : "memory");
+                if (seen < (unsigned int)a.S) __nanosleep(40);
+            } while (seen < (unsigned int)a.S);
+        }
+        __syncthreads();
+        // ---------------- pass 1b: gs[b, :] (fixed order, double) and the softmax table ----------------
+        {
+            constexpr int kSlots = 256 / G2;
+            double v = 0.0;
+            if (tid < kSlots * G2) {
+                const int r = tid % G2, i0 = tid / G2;
+                const float *o = a.gpart + (int64_t)b * a.S * G2 + r;
+#pragma unroll 4
+                for (int i = i0; i < a.S; i += kSlots) v += (double)__ldcg(o + (int64_t)i * G2);
+            }
+            dred[tid] = v;
+            __syncthreads();
+            if (tid < R) {
+                double d = 0.0, vs = 0.0;
+                for (int sl = 0; sl < kSlots; ++sl) { d += dred[sl * G2 + tid]; vs += dred[sl * G2 + R + tid]; }
+                const bool zero = vs < 1e-4;                                       // :222
+                const float v_sum = (float)vs + (zero ? 1.0f : 0.0f);              // :223
+                const float gg = (float)d / (v_sum * (float)a.C);                  // :225-227
+                gs_smem[tid] = zero ? 0.0f : gg;                                   // :228
+                if (s == 0) a.gs[(int64_t)b * R + tid] = gs_smem[tid];
+            }
+            __syncthreads();
+            softmax_table<R>(gs_smem, tab);
+            __syncthreads();
+        }
+        // ---------------- pass 2: sum_r w_r c_r and c_mask ----------------
+        // one item: the weights of its 4 pixels are table rows selected by the mask bytes
+        auto emit = [&](int i, auto &&ref) {
+            const int c = i / a.chunks, q = i - c * a.chunks, p = q * 1024 + tid * 4;
+            if (i >= hi || p >= a.P) return;
+            const uint32_t mw = mask_word(q, p);
+            int pat[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pat[j] = (int)((mw >> (8 * j + 1)) & ((1u << R) - 1u)) * (R + 1);
+            if (c == 0) {
+                const float4 c4 = make_float4(tab[pat[0] + R], tab[pat[1] + R], tab[pat[2] + R], tab[pat[3] + R]);
+                st_stream4(ob + (2 * a.C * a.P + p), c4);
+                st_stream4(a.c_mask + ((int64_t)b * a.P + p), c4);
+            }
+            float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {  // sum_r c_r * w_r, sequential over r    :238
+                const float4 v = ref(r);
+                o.x = __fadd_rn(o.x, __fmul_rn(v.x, tab[pat[0] + r]));
+                o.y = __fadd_rn(o.y, __fmul_rn(v.y, tab[pat[1] + r]));
+                o.z = __fadd_rn(o.z, __fmul_rn(v.z, tab[pat[2] + r]));
+                o.w = __fadd_rn(o.w, __fmul_rn(v.w, tab[pat[3] + r]));
+            }
+            st_stream4(ob + ((a.C + c) * a.P + p), o);
+        };
+        auto emit_regs = [&](int bi) {
+#pragma unroll
+            for (int k = 0; k < UN; ++k) emit(lo + bi * UN + k, [&](int r) { return cr[k][r]; });
+        };
+        auto emit_parked = [&](int bi) {  // straight from shared memory, 4 registers at a time
+#pragma unroll
+            for (int k = 0; k < UN; ++k) emit(lo + bi * UN + k, [&](int r) { return park[((bi * UN + k) * R + r) * 256 + tid]; });
+        };
+        // order: registers (batch nb - 1), then the L2 batches nb - 2 ... np (most recently read first), each requested
+        // one step ahead and a parked batch processed while it is in flight
+        if (nb > 0) {
+            emit_regs(nb - 1);
+            int q = 0;             // next parked batch
+            int j = nb - 2;        // next L2 batch
+            if (j >= np) load_cr(j, cr, true);
+#pragma unroll 1
+            while (j >= np || q < np) {
+                if (q < np) { emit_parked(q); ++q; }
+                if (j >= np) {
+                    emit_regs(j);
+                    --j;
+                    if (j >= np) load_cr(j, cr, true);
+                }
+            }
+        }
+        __syncthreads();  // red / tab / park are reused by the next sample of this group
+    }
+}
+
+// resident CTAs of cm_group_kernel<R> on this device (<= 2 per SM) and the batches each may park in shared memory
+template <int R>
+int cm_group_ctas(int *keep_out) {
+    static int n = 0, keep = 0;
+    if (n == 0) {
+        cudaFuncAttributes fa;
+        int dev = 0, smem_sm = 0, occ = 0;
+        if (cudaFuncGetAttributes(&fa, cm_group_kernel<R>) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess)
+            return 0;
+        // two CTAs per SM: each gets half of the SM's shared memory minus its static part and the 1 KB the system reserves
+        int dyn = smem_sm / 2 - (int)fa.sharedSizeBytes - 1024;
+        int kp = dyn / CmGroupCfg<R>::kBatchBytes;
+        if (kp > 8) kp = 8;
+        if (kp < 0) kp = 0;
+        const int bytes = kp * CmGroupCfg<R>::kBatchBytes;
+        if (cudaFuncSetAttribute(cm_group_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cm_group_kernel<R>, 256, bytes) != cudaSuccess || occ < 1) return 0;
+        keep = kp;
+        n = sm_count() * (occ > 2 ? 2 : occ);
+    }
+    *keep_out = keep;
+    return n;
+}
+
 template <int R>
 int launch_cm(CmArgs a, cudaStream_t st) {
     a.b_off = 0;
+    const int mode = tuning("MT_CM_TABLE", 2);  // 2: grouped single launch, 1: sim | copy2 (table), 0: sim | weights | copy
+    if constexpr (R <= 7) {
+        int keep = 0;
+        const int ctas = (mode == 2 && (int64_t)(2 * a.C + 1) * a.f * a.P < (1ll << 31)) ? cm_group_ctas<R>(&keep) : 0;
+        keep = max(0, min(keep, tuning("MT_CM_KEEP", 8)));  // batches parked in shared memory between the passes
+        if (ctas > 0) {
+            // samples in flight: as many as keep their features (C * f * P * 4 B each) within ~90 MB of L2
+            const int64_t sample_bytes = (int64_t)a.C * a.f * a.P * 4;
+            int64_t g = tuning("MT_CM_GROUPS", 0);
+            if (g <= 0) g = (int64_t)tuning("MT_CM_L2_MB", 90) * 1000000 / sample_bytes;
+            if (g > a.B) g = a.B;
+            if (g > ctas) g = ctas;
+            if (g < 1) g = 1;
+            a.G = (int)g;
+            a.S = ctas / a.G;
+            if (a.S > kMaxGroupCtas) a.S = kMaxGroupCtas;
+            launch(cm_masks_kernel, dim3((a.P + 255) / 256, a.B), 256, 0, st, a);
+            launch(cm_group_kernel<R>, dim3(a.G * a.S), 256, (size_t)keep * CmGroupCfg<R>::kBatchBytes, st, a, keep);
+            return launch_status("mt_cm_match_fwd");
+        }
+    }
     launch(cm_masks_kernel, dim3((a.P + 255) / 256, a.B), 256, 0, st, a);
     const int cc = tuning("MT_CM_COPY_CH", kCopyChannels);
     a.nparts = a.chunks * ((a.C + a.sim_ch - 1) / a.sim_ch);
@@ -460,7 +735,7 @@ int launch_cm(CmArgs a, cudaStream_t st) {
     dim3 g1(a.chunks, slabs, a.B);
     if (a.sim_ch == 2) launch(cm_sim_kernel<R, 2>, g1, 256, 0, st, a);
     else launch(cm_sim_kernel<R, 4>, g1, 256, 0, st, a);
-    if (R <= 7 && tuning("MT_CM_TABLE", 1)) {  // pass 1b folded into pass 2 (the mask byte holds <= 7 references)
+    if (R <= 7 && mode) {  // pass 1b folded into pass 2 (the mask byte holds <= 7 references)
         if (cc == 2) launch(cm_copy2_kernel<R, 2>, dim3(a.chunks, (a.C + 1) / 2, a.B), 256, 0, st, a);
         else launch(cm_copy2_kernel<R, 4>, dim3(a.chunks, (a.C + 3) / 4, a.B), 256, 0, st, a);
         return launch_status("mt_cm_match_fwd");
@@ -485,7 +760,8 @@ extern "C" int64_t mt_cm_workspace_bytes(int B, int C, int f, int h, int w) {
     const int64_t P = (int64_t)h * w, R = f - 1;
     const int64_t chunks = (P + 1023) / 1024, nparts = chunks * ((C + 1) / 2);  // finest pass-1 split
     return align256(B * f * P * 4) + align256(B * nparts * 2 * R * 4) + align256(B * R * 4) +
-           align256(B * R * P * 4) + align256(B * P);
+           align256(B * R * P * 4) + align256(B * P) + align256((int64_t)B * 4) +
+           align256((int64_t)B * kMaxGroupCtas * 2 * R * 4);
 }
 
 extern "C" int mt_cm_match_fwd(const float *c_feats, const float *v_t, const float *v_aligned,
@@ -514,6 +790,11 @@ extern "C" int mt_cm_match_fwd(const float *c_feats, const float *v_t, const flo
     a.weights = reinterpret_cast<float *>(ws);
     ws += align256((int64_t)B * a.R * a.P * 4);
     a.pmask = reinterpret_cast<unsigned char *>(ws);
+    ws += align256((int64_t)B * a.P);
+    a.counters = reinterpret_cast<unsigned int *>(ws);
+    ws += align256((int64_t)B * 4);
+    a.gpart = reinterpret_cast<float *>(ws);
+    a.G = a.S = 0;
     a.copy_reverse = tuning("MT_CM_COPY_REVERSE", 1);
     cudaStream_t st = (cudaStream_t)stream;
     switch (a.R) {

@@ -40,10 +40,9 @@
 namespace mt {
 namespace {
 
-constexpr int kTile = 256;        // output tile rows (two UMMA M = 128 halves); columns TN <= 256
+constexpr int kTile = 256;        // largest output tile: TM rows (one or two UMMA M = 128 halves) x TN <= 256 columns
 constexpr int kBK = 32;
 constexpr int kUmmaK = 8;         // tf32: 32 B of K per instruction
-constexpr int kStageBytesA = kTile * kBK * 4;  // 32 KB
 
 // MN-major, SWIZZLE_128B_BASE32B shared-memory matrix descriptor (sm_100 "version 1").
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -120,14 +119,16 @@ constexpr int kThreadsP = (2 + kNormWarps + kEpiWarps) * 32;
 constexpr int kEpiPitch = 36;     // floats per staged row: 144 B keeps float4 alignment, conflict-free both ways
 constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch * 4;
 
-template <int TN, int STAGES>
+template <int TM, int TN, int STAGES>
 constexpr int smem_bytes_p() {
-    return STAGES * (kStageBytesA + TN * kBK * 4) + kEpiBytes + 2 * (kTile + kTile) * 4 /*scales*/ + 256 /*barriers*/ +
+    return STAGES * ((TM + TN) * kBK * 4) + kEpiBytes + 2 * (kTile + kTile) * 4 /*scales*/ + 256 /*barriers*/ +
            1024 /*alignment*/;
 }
 
-// Persistent kernel: one CTA per SM walks the output tiles (256 rows x TN columns of one (b, f) frame) in a
-// static round-robin.  Warp roles (14 warps):
+// Persistent kernel: one CTA per SM walks the output tiles (TM rows x TN columns of one (b, f) frame) in a
+// static round-robin.  TM = 256, TN = 256 loads every operand byte once (large batches); smaller tiles split a
+// frame over 2 .. 8 CTAs so that small batches still occupy the machine (the operands are then re-read from L2).
+// Warp roles (14 warps):
 //   warp 0      TMA producer: runs ahead over tile boundaries, bounded only by the smem ring
 //   warp 1      TMEM owner + single-thread tcgen05.mma issuer; accumulator buffers of 2 x TN fp32 columns
 //               (two M = 128 halves): two buffers for TN <= 128, so the MMAs of tile i + 1 start while the
@@ -141,15 +142,19 @@ constexpr int smem_bytes_p() {
 //               instruction, which made the epilogue as long as the main loop)
 // Barriers: full/empty per smem stage (empty = MMA commit + one arrival per norm warp), tmem_full / tmem_empty and
 // scales_ready per accumulator buffer.
-template <int TN, int kStages>
+template <int TM, int TN, int kStages>
 __global__ void __launch_bounds__(kThreadsP, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const CorrTcArgs a) {
-    constexpr int kStageBytesB = TN * kBK * 4;
-    constexpr int kBufs = TN <= 128 ? 2 : 1;          // accumulator buffers
-    constexpr int kBufCols = 2 * TN;                  // two M halves
+    constexpr int kHalves = TM / 128;                 // UMMA M = 128 accumulators per tile
+    constexpr int kStageBytesA = TM * kBK * 4, kStageBytesB = TN * kBK * 4;
+    constexpr int kBufCols = kHalves * TN;            // TMEM columns per accumulator buffer
+    constexpr int kBufs = 2 * kBufCols <= 512 ? 2 : 1;  // accumulator buffers
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024 B alignment (swizzle atoms) as an OFFSET from the declared array: a round trip through uintptr_t loses
+    // the shared address space and every access below became a generic LD.E / ST.E (ncu r2e: the norm warps'
+    // 64 loads per stage and the epilogue staging were all generic; stall reason "lg")
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + kStages * kStageBytesA;
     float *epi = reinterpret_cast<float *>(smem + kStages * (kStageBytesA + kStageBytesB));
@@ -205,7 +210,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mbar_expect_tx(smem_u32(full + s), kStageBytesA + kStageBytesB);
                     // A: (pixel-in-group 32, channel C, pixel group P/32, batch B)
                     tma_load_4d(smem_u32(smem_a + s * kStageBytesA), &map_a, smem_u32(full + s), 0, kb * kBK,
-                                m_tile * (kTile / 32), b);
+                                m_tile * (TM / 32), b);
                     // B: (pixel-in-group 32, channel C, pixel group P/32, frame F, batch B)
                     tma_load_5d(smem_u32(smem_b + s * kStageBytesB), &map_b, smem_u32(full + s), 0, kb * kBK,
                                 n_tile * (TN / 32), f, b);
@@ -235,7 +240,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         // K advance inside the stage: next 8 channels = two 512 B atoms = +1024 B
                         const uint64_t bd = umma_desc(b0 + j * 1024, kBK * 128, 512);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {  // M halves: pixel groups 0..3 and 4..7 of the A stage
+                        for (int h = 0; h < kHalves; ++h) {  // M halves: pixel groups 0..3 and 4..7 of the A stage
                             const uint64_t ad = umma_desc(a0 + h * (4 * kBK * 128) + j * 1024, kBK * 128, 512);
                             umma_tf32(acc + h * TN, ad, bd, idesc, (kb | j) != 0 ? 1u : 0u);
                         }
@@ -247,13 +252,17 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp < 2 + kNormWarps) {
         // ===== norm warps =====
-        const int t = threadIdx.x - 64;  // 0..255: row t of A, column t of B (if t < TN)
-        const int tb = t < TN ? t : 0;
+        // thread -> row ra of the A tile and / or column cb of the B tile (warp-uniform: TM, TN are multiples of 64).
+        // Small tiles give the two operands to different warps, large ones give every thread one of each.
+        const int t = threadIdx.x - 64;  // 0..255
+        constexpr bool kSplit = TM + TN <= 256;
+        const bool has_a = t < TM, has_b = kSplit ? (t >= TM && t < TM + TN) : (t < TN);
+        const int ta = has_a ? t : 0, tb = has_b ? (kSplit ? t - TM : t) : 0;
         // the swizzle phase repeats every 4 channels: channel k = 4 j + r lives at base[r] + 512 j,
         // so the loop below is 32 LDS with immediate offsets + 32 FFMA per operand, no address math
         uint32_t base_a[4], base_b[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) { base_a[r] = staged_offset(t, r); base_b[r] = staged_offset(tb, r); }
+        for (int r = 0; r < 4; ++r) { base_a[r] = staged_offset(ta, r); base_b[r] = staged_offset(tb, r); }
         uint32_t it = 0;
         int ti = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++ti) {
@@ -261,7 +270,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int m_tile = r0 / a.tiles_n, n_tile = r0 - m_tile * a.tiles_n;
             const int b = frame / a.F, f = frame - b * a.F;
             // the visibilities are needed at the end of the main loop only: request them first
-            const float vt = corr_vis(a.vt ? a.vt + (int64_t)b * a.vt_sb : nullptr, m_tile * kTile + t, a);
+            const float vt = corr_vis(a.vt ? a.vt + (int64_t)b * a.vt_sb : nullptr, m_tile * TM + ta, a);
             const float vr = corr_vis(a.vr ? a.vr + (int64_t)b * a.vr_sb + (int64_t)f * a.vr_sf : nullptr,
                                       n_tile * TN + tb, a);
             float qa[4] = {0.f, 0.f, 0.f, 0.f}, qb[4] = {0.f, 0.f, 0.f, 0.f};
@@ -270,14 +279,24 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t ph = (it / kStages) & 1;
                 mbar_wait(smem_u32(full + s), ph);
                 const uint8_t *pa = smem_a + s * kStageBytesA, *pb = smem_b + s * kStageBytesB;
+                if (has_a) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                    for (int r = 0; r < 4; ++r) {
 #pragma unroll
-                    for (int j = 0; j < kBK / 4; ++j) {
-                        const float va = *reinterpret_cast<const float *>(pa + base_a[r] + j * 512);
-                        const float vb = *reinterpret_cast<const float *>(pb + base_b[r] + j * 512);
-                        qa[r] = __fmaf_rn(va, va, qa[r]);
-                        qb[r] = __fmaf_rn(vb, vb, qb[r]);
+                        for (int j = 0; j < kBK / 4; ++j) {
+                            const float va = *reinterpret_cast<const float *>(pa + base_a[r] + j * 512);
+                            qa[r] = __fmaf_rn(va, va, qa[r]);
+                        }
+                    }
+                }
+                if (has_b) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                        for (int j = 0; j < kBK / 4; ++j) {
+                            const float vb = *reinterpret_cast<const float *>(pb + base_b[r] + j * 512);
+                            qb[r] = __fmaf_rn(vb, vb, qb[r]);
+                        }
                     }
                 }
                 __syncwarp();
@@ -289,8 +308,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // the scale tables of this buffer are free once the epilogue of its previous tile has finished
             mbar_wait(smem_u32(tmem_empty + buf), (use & 1) ^ 1);
             // scales: v / (|v| * ||f|| + 1e-9)   (||f * v|| = |v| * ||f||)
-            s_sa[buf * kTile + t] = __fdiv_rn(vt, __fadd_rn(__fmul_rn(fabsf(vt), sqrtf(ssa)), 1e-9f));
-            if (t < TN) s_sb[buf * kTile + t] = __fdiv_rn(vr, __fadd_rn(__fmul_rn(fabsf(vr), sqrtf(ssb)), 1e-9f));
+            if (has_a) s_sa[buf * kTile + ta] = __fdiv_rn(vt, __fadd_rn(__fmul_rn(fabsf(vt), sqrtf(ssa)), 1e-9f));
+            if (has_b) s_sb[buf * kTile + tb] = __fdiv_rn(vr, __fadd_rn(__fmul_rn(fabsf(vr), sqrtf(ssb)), 1e-9f));
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(scales_ready + buf));
         }
@@ -311,10 +330,10 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const float *sbv = s_sb + buf * kTile;
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < kHalves; ++h) {
                 const int row0 = h * 128 + lq * 32;  // first row of this warp's 32-row block
                 const float sa = s_sa[buf * kTile + row0 + lane];
-                float *oblk = a.out + (((int64_t)frame * a.P + m_tile * kTile + row0) * a.P + n_tile * TN);
+                float *oblk = a.out + (((int64_t)frame * a.P + m_tile * TM + row0) * a.P + n_tile * TN);
 #pragma unroll 1
                 for (int c0 = 0; c0 < TN; c0 += 32) {
                     float v[32];
@@ -377,20 +396,32 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
         set_error("mt_corr4d_fwd: cuTensorMapEncodeTiled is not available from the driver");
         return MT_ERR_NO_DEVICE;
     }
-    // columns per tile: 256 = every operand byte loaded once but a single accumulator buffer; 128 = two buffers
-    // (epilogue of a tile under the main loop of the next), the target tile re-read from L2 once per frame
+    // Tile shape TM x TN.  256 x 256 = a whole frame per CTA: every operand byte loaded once, but one tile per (b, f)
+    // frame; smaller tiles split a frame over 2 / 4 / 8 CTAs (operands re-read from L2) so that a small batch still
+    // fills the 148 SMs, and leave room for two TMEM accumulator buffers (epilogue under the next main loop).
+    // Swept on B200 (profiles/r2_experiments.md).  MT_CORR_TM / MT_CORR_TN override.
     const int frames = B * F * (P / kTile);
-    int tn = tuning("MT_CORR_TN", 0);
-    // swept on B200 (profiles/r2_corr_sweep.md): 8 frames 22.8 / 24.1 / 31.3 us, 40 frames 32.9 / 25.9 / 32.1 us,
-    // 128 frames 55.4 / 39.8 / 35.4 us for TN = 64 / 128 / 256
-    if (tn != 256 && tn != 128 && tn != 64) tn = frames * 2 >= sm_count() ? 256 : (frames * 8 >= sm_count() ? 128 : 64);
+    int tm = tuning("MT_CORR_TM", 0), tn = tuning("MT_CORR_TN", 0);
+    const bool tn_given = tn == 256 || tn == 128 || tn == 64, tm_given = tm == 256 || tm == 128;
+    if (!tn_given || !tm_given) {
+        // graph-replayed step, cfg1 at 8 / 32 / 128 frames (profiles/r2_experiments.md): 20.5 us (128 x 64),
+        // 46.2 us (256 x 128), 168.0 us (256 x 256); the runners-up cost 2 - 25 % more
+        const int sms = sm_count();
+        int atm, atn;
+        if (frames * 2 >= sms) { atm = 256; atn = 256; }
+        else if (frames * 5 >= sms) { atm = 256; atn = 128; }
+        else if (frames * 10 >= sms) { atm = 128; atn = 128; }
+        else { atm = 128; atn = 64; }
+        if (!tm_given) tm = tn_given ? 256 : atm;
+        if (!tn_given) tn = atn;
+    }
     if (P % tn) tn = 64;
     CUtensorMap map_a, map_b;
     {
         // ft (B, C, P) viewed as (32, C, P/32, B): strides in bytes for dims 1..3
         cuuint64_t dims[4] = {32, (cuuint64_t)C, (cuuint64_t)(P / 32), (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)ft_sc * 4, 128, (cuuint64_t)(B > 1 ? ft_sb : (int64_t)C * P) * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)kBK, (cuuint32_t)(kTile / 32), 1};
+        cuuint32_t box[4] = {32, (cuuint32_t)kBK, (cuuint32_t)(tm / 32), 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(ft), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
@@ -421,28 +452,33 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
     a.msy = mask_mode ? (float)MH / (float)fh : 1.0f;
     a.msx = mask_mode ? (float)MW / (float)fw : 1.0f;
     a.out = out; a.C = C; a.F = F; a.P = P;
-    a.tiles_m = P / kTile; a.tiles_n = P / tn;
+    a.tiles_m = P / tm; a.tiles_n = P / tn;
     const int64_t n_tiles = (int64_t)B * F * a.tiles_m * a.tiles_n;
     MT_REQUIRE(n_tiles < (1ll << 30), "mt_corr4d_fwd: too many tiles");
     a.n_tiles = (int)n_tiles;
     int ctas = sm_count();
     if (ctas > a.n_tiles) ctas = a.n_tiles;
     dim3 grid(ctas);
-#define MT_CORR_GO(TNV, STG)                                                                         \
+#define MT_CORR_GO(TMV, TNV, STG)                                                                    \
     do {                                                                                             \
-        cudaError_t e = cudaFuncSetAttribute(corr_tc_kernel<TNV, STG>,                               \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_p<TNV, STG>()); \
+        static_assert(smem_bytes_p<TMV, TNV, STG>() <= 227 * 1024, "stage ring exceeds the shared memory of an SM"); \
+        cudaError_t e = cudaFuncSetAttribute(corr_tc_kernel<TMV, TNV, STG>,                          \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_p<TMV, TNV, STG>()); \
         if (e != cudaSuccess) {                                                                      \
             set_error("mt_corr4d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));             \
             return MT_ERR_CUDA;                                                                      \
         }                                                                                            \
-        launch(corr_tc_kernel<TNV, STG>, grid, dim3(kThreadsP), (size_t)smem_bytes_p<TNV, STG>(), st, map_a, map_b, a); \
+        launch(corr_tc_kernel<TMV, TNV, STG>, grid, dim3(kThreadsP), (size_t)smem_bytes_p<TMV, TNV, STG>(), st, map_a, map_b, a); \
     } while (0)
-    static_assert(smem_bytes_p<256, 3>() <= 227 * 1024 && smem_bytes_p<128, 4>() <= 227 * 1024 &&
-                  smem_bytes_p<64, 5>() <= 227 * 1024, "stage ring exceeds the shared memory of an SM");
-    if (tn == 256) MT_CORR_GO(256, 3);       // 3 x 64 KB
-    else if (tn == 128) MT_CORR_GO(128, 4);  // 4 x 48 KB
-    else MT_CORR_GO(64, 5);                  // 5 x 40 KB
+    if (tm == 256) {
+        if (tn == 256) MT_CORR_GO(256, 256, 3);       // 3 x 64 KB
+        else if (tn == 128) MT_CORR_GO(256, 128, 4);  // 4 x 48 KB
+        else MT_CORR_GO(256, 64, 5);                  // 5 x 40 KB
+    } else {
+        if (tn == 256) MT_CORR_GO(128, 256, 4);       // 4 x 48 KB
+        else if (tn == 128) MT_CORR_GO(128, 128, 6);  // 6 x 32 KB
+        else MT_CORR_GO(128, 64, 8);                  // 8 x 24 KB
+    }
 #undef MT_CORR_GO
     return launch_status("mt_corr4d_fwd");
 }

@@ -121,6 +121,16 @@ __global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const War
     }
     const float wm2 = a.sp.wmax - 1.0f, hm2 = a.sp.hmax - 1.0f;
 
+    // dense flow: the grid values of the NEXT row group are requested before the gathers of the current one, so a
+    // CTA that walks several row groups (iters > 1) has one dependent DRAM round trip per group instead of two
+    constexpr bool kDense = !AFFINE && !LOWRES;
+    float2 g_next[U];
+    if (kDense) {
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+            g_next[k] = (yb + k < H) ? __ldcs(reinterpret_cast<const float2 *>(a.grid) + ((int)n * a.P + (yb + k) * W + x))
+                                     : make_float2(0.0f, 0.0f);
+    }
     // the per-thread setup above is paid once for U * iters pixels
 #pragma unroll 1
     for (int it = 0; it < a.iters; ++it) {
@@ -159,11 +169,8 @@ __global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const War
                 const float2 *fl = reinterpret_cast<const float2 *>(a.grid) + (int)n * (a.gh * a.gw);
                 const float2 g = lin_flow(fl + ly.i0 * a.gw, fl + ly.i1 * a.gw, lx, ly.l0, ly.l1);
                 gx = g.x; gy = g.y;
-            } else if (y0 + k < H) {
-                const float2 g = __ldcs(reinterpret_cast<const float2 *>(a.grid) + (np0 + k * W));
-                gx = g.x; gy = g.y;
             } else {
-                gx = gy = 0.0f;
+                gx = g_next[k].x; gy = g_next[k].y;  // rows past H hold (0, 0)
             }
             ix[k] = unnormalize(gx, a.sp.sfx, ac);
             iy[k] = unnormalize(gy, a.sp.sfy, ac);
@@ -175,6 +182,12 @@ __global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const War
             wsw[k] = __fmul_rn(nn, e); wse[k] = __fmul_rn(nn, w);
             // rows past the end of the frame are computed (harmlessly) and never stored
             interior = interior && (xw[k] >= 0.0f) && (xw[k] <= wm2) && (yn[k] >= 0.0f) && (yn[k] <= hm2);
+        }
+        if (kDense && it + 1 < a.iters) {
+#pragma unroll
+            for (int k = 0; k < U; ++k)
+                g_next[k] = (y0 + U + k < H) ? __ldcs(reinterpret_cast<const float2 *>(a.grid) + (np0 + (U + k) * W))
+                                             : make_float2(0.0f, 0.0f);
         }
         float xa[C][U], va[U];
         if (__all_sync(0xffffffffu, interior)) {

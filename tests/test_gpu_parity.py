@@ -255,20 +255,24 @@ def test_corr4d(mtb, name):
         assert np.all(c[0, :, 0, :] == 0.0)
 
 
+@pytest.mark.parametrize("tm", [256, 128])
 @pytest.mark.parametrize("tn", [64, 128, 256])
 @pytest.mark.parametrize("name", ["real_masked", "real_nomask", "mid_masked", "big_masked"])
-def test_corr4d_every_tile_variant(mtb, name, tn):
-    """Every corr_tc_kernel instantiation (64 / 128 / 256 output columns per CTA: different epilogue column
-    offsets, scale tables, stage counts and grids) on small, medium (40 frames) and cfg3-size (128 frames)
-    batches, against the golden vectors of the reference AND the whole volume of the CPU oracle."""
+def test_corr4d_every_tile_variant(mtb, name, tn, tm):
+    """Every corr_tc_kernel instantiation (128 / 256 output rows x 64 / 128 / 256 output columns per CTA: different
+    accumulator halves, epilogue offsets, scale tables, norm-warp mappings, stage counts and grids) on small, medium
+    (40 frames) and cfg3-size (128 frames) batches, against the golden vectors of the reference AND the whole
+    volume of the CPU oracle."""
     spec = cases.CORR_CASES[name]
     ft, vt, fr, vr = cases.corr_inputs(spec)
     g = load_golden("corr_" + name)
     try:
         _set_tuning("MT_CORR_TN", tn)
+        _set_tuning("MT_CORR_TM", tm)
         c = host(mtb.CorrelationVGG.correlation_masked_4d(dev(ft), dev(vt), dev(fr), dev(vr)))
     finally:
         _set_tuning("MT_CORR_TN", 0)
+        _set_tuning("MT_CORR_TM", 0)
     _corr_tol_check(c, g, spec, True)
     o = oracle.corr4d(ft, vt, fr, vr)
     err = np.abs(c - o)
@@ -278,10 +282,11 @@ def test_corr4d_every_tile_variant(mtb, name, tn):
 
 
 # ---------------------------------------------------------------- a8
-@pytest.mark.parametrize("table", [1, 0])
+@pytest.mark.parametrize("table", [2, 1, 0])
 @pytest.mark.parametrize("name", sorted(cases.CM_CASES))
 def test_cm_module(mtb, name, table):
-    """table=1: masks | similarity | copy with the softmax looked up per mask pattern (default);
+    """table=2: masks | one grouped launch for similarity + softmax table + copy (default: c_feats crosses HBM once);
+    table=1: masks | similarity | copy with the softmax looked up per mask pattern;
     table=0: the separate per-pixel weights kernel (the path 8 references take)."""
     from master_thesis_b200 import ops
     cf, vt, va = cases.cm_inputs(cases.CM_CASES[name])
@@ -294,7 +299,7 @@ def test_cm_module(mtb, name, table):
         _, _, gs = ops.cm_match(dev(cf), dev(vt), dev(va), return_gs=True)
         gs = gs.clone()
     finally:
-        _set_tuning("MT_CM_TABLE", 1)
+        _set_tuning("MT_CM_TABLE", 2)
     assert np.abs(host(gs) - ogs).max() <= 1e-6 * max(1.0, np.abs(ogs).max())
     assert np.abs(out - oout).max() <= 1e-5 and np.abs(cmask - ocmask).max() <= 2e-6
     assert np.abs(cmask - g["c_mask"]).max() <= 2e-6
@@ -307,26 +312,74 @@ def test_cm_module(mtb, name, table):
 @pytest.mark.parametrize("shape", [(5, 4, 9, 24, 48), (3, 2, 5, 32, 32), (9, 5, 16, 16, 80), (1, 8, 6, 16, 16),
                                    (2, 9, 7, 16, 24)])
 def test_cm_ragged(mtb, shape):
-    """Both weight paths against the oracle on shapes that leave partial 1024-pixel chunks, a channel count
-    that is not a multiple of the slab, one sample, and 1 / 3 / 4 / 7 / 8 references."""
+    """All three launch structures against the oracle on shapes that leave partial 1024-pixel chunks, a channel
+    count that is not a multiple of the slab, one sample, and 1 / 3 / 4 / 7 / 8 references (8: the grouped and the
+    table variants fall back to the weights kernel)."""
     from master_thesis_b200 import ops, synth
     b, f, c, h, w = shape
     cf, vt, va = synth.cm_inputs(61 + b, b, f, c, h, w, 4)
     oout, ocm, ogs = oracle.cm_module(cf, vt, va, return_gs=True)
     res = {}
     try:
-        for table in (1, 0):
+        for table in (2, 1, 0):
             _set_tuning("MT_CM_TABLE", table)
             out, cmask, gs = ops.cm_match(dev(cf), dev(vt), dev(va), return_gs=True)
             res[table] = (host(out), host(cmask), host(gs.clone()))
     finally:
-        _set_tuning("MT_CM_TABLE", 1)
-    for table in (1, 0):
+        _set_tuning("MT_CM_TABLE", 2)
+    for table in (2, 1, 0):
         out, cmask, gs = res[table]
         assert np.abs(gs - ogs).max() <= 1e-6 * max(1.0, np.abs(ogs).max())
         assert np.abs(out - oout).max() <= 1e-5 and np.abs(cmask - ocm).max() <= 2e-6
     # same partial sums folded in a different (fixed) order: the two paths agree to rounding
     assert np.abs(res[1][0] - res[0][0]).max() <= 1e-5 and np.abs(res[1][1] - res[0][1]).max() <= 2e-6
+    assert np.abs(res[2][0] - res[1][0]).max() <= 1e-5 and np.abs(res[2][1] - res[1][1]).max() <= 2e-6
+
+
+@pytest.mark.parametrize("groups", [1, 2, 3, 64])
+def test_cm_grouped_rounds(mtb, groups):
+    """The grouped single-launch kernel with fewer groups than samples (a group then walks several samples:
+    B = 5 in rounds of 1 / 2 / 3) and with more groups requested than samples (clamped to B)."""
+    from master_thesis_b200 import ops, synth
+    b, f, c, h, w = 5, 5, 24, 32, 40
+    cf, vt, va = synth.cm_inputs(77, b, f, c, h, w, 4)
+    va[1] = 0.0                      # one sample without any visible reference pixel (v_sum guard)
+    oout, ocm, ogs = oracle.cm_module(cf, vt, va, return_gs=True)
+    try:
+        _set_tuning("MT_CM_TABLE", 2)
+        _set_tuning("MT_CM_GROUPS", groups)
+        for rep in range(2):          # twice: the arrival counters are re-armed by the masks kernel of every call
+            out, cmask, gs = ops.cm_match(dev(cf), dev(vt), dev(va), return_gs=True)
+            out, cmask, gs = host(out), host(cmask), host(gs.clone())
+            assert np.abs(gs - ogs).max() <= 1e-6 * max(1.0, np.abs(ogs).max())
+            assert np.abs(out - oout).max() <= 1e-5 and np.abs(cmask - ocm).max() <= 2e-6
+    finally:
+        _set_tuning("MT_CM_GROUPS", 0)
+
+
+@pytest.mark.parametrize("keep", [8, 1, 0])
+def test_cm_grouped_full_size(mtb, keep):
+    """cfg2 size (B = 8, 128 x 5 x 64 x 64: 14 items per CTA) so that pass 2 of the grouped kernel takes its
+    operands from all three places: the last batch from registers, `keep` batches from shared memory, the rest
+    from L2.  Checked against the oracle and against the three-launch form."""
+    from master_thesis_b200 import ops, synth
+    cf, vt, va = synth.cm_inputs(91, 8, 5, 128, 64, 64)
+    oout, ocm, ogs = oracle.cm_module(cf, vt, va, return_gs=True)
+    dcf, dvt, dva = dev(cf), dev(vt), dev(va)
+    try:
+        _set_tuning("MT_CM_KEEP", keep)
+        out, cmask, gs = ops.cm_match(dcf, dvt, dva, return_gs=True)
+        out, cmask, gs = host(out), host(cmask), host(gs.clone())
+        _set_tuning("MT_CM_TABLE", 1)
+        out1, cmask1 = ops.cm_match(dcf, dvt, dva)
+        out1, cmask1 = host(out1), host(cmask1)
+    finally:
+        _set_tuning("MT_CM_KEEP", 8)
+        _set_tuning("MT_CM_TABLE", 2)
+    assert np.abs(gs - ogs).max() <= 1e-6 * max(1.0, np.abs(ogs).max())
+    assert np.abs(out - oout).max() <= 1e-5 and np.abs(cmask - ocm).max() <= 2e-6
+    assert np.array_equal(out[:, :128], cf[:, :, 0].reshape(8, 128, 64, 64))      # cat[c_t, ...]: a plain copy
+    assert np.abs(out - out1).max() <= 1e-5 and np.abs(cmask - cmask1).max() <= 2e-6
 
 
 # ---------------------------------------------------------------- a9 .. a12
@@ -615,12 +668,12 @@ def test_no_out_of_bounds_writes(mtb):
         for shape in ((5, 4, 9, 24, 48), (3, 2, 5, 32, 32)):
             b, f, c, h, w = shape
             cf, vt, va = cases.synth.cm_inputs(61 + b, b, f, c, h, w, 4)
-            for table in (1, 0):
+            for table in (2, 1, 0):
                 try:
                     _set_tuning("MT_CM_TABLE", table)
                     ops.cm_match(dev(cf), dev(vt), dev(va))
                 finally:
-                    _set_tuning("MT_CM_TABLE", 1)
+                    _set_tuning("MT_CM_TABLE", 2)
         # correlation and the fused DFPN loss
         ft, vtt, fr, vr = cases.synth.vgg_feats(5, 1, 2)
         ops.corr4d(dev(ft), dev(vtt), dev(fr), dev(vr))

@@ -1,5 +1,5 @@
 """Launches the three headline kernels a few times on rotating inputs (for ncu -k captures):
-corr_tc_kernel at 128 frames, the DFPN direct-gather warp and the staged CPN warp at 32 frames."""
+corr_tc_kernel at 128 frames, the DFPN direct-gather warp and the staged CPN warp at 32 frames, CM_Module at B = 8."""
 import os
 import sys
 
@@ -11,7 +11,7 @@ import master_thesis_b200 as mtb                     # noqa: E402
 from master_thesis_b200 import ops, synth            # noqa: E402
 
 dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()   # noqa: E731
-which = sys.argv[1:] or ["corr", "dfpn", "cpn"]
+which = sys.argv[1:] or ["corr", "dfpn", "cpn", "cm"]
 sets = []
 for i in range(3):
     d = {}
@@ -22,6 +22,9 @@ for i in range(3):
     d["x"], d["m"], d["mt"] = dev(x[:, :, 1:]), dev(m[:, :, 1:]), dev(m[:, :, 0])
     d["flow"] = dev(synth.dense_flow(30 + i, 8, 4, 256, 256, 0.05, True))
     d["theta"] = dev(synth.thetas(40 + i, 32, 0.1))
+    if "cm" in which:
+        cf, vt, va = synth.cm_inputs(50 + i, 8, 5, 128, 64, 64)
+        d["cm"] = (dev(cf), dev(vt), dev(va))
     sets.append(d)
 torch.cuda.synchronize()
 for rep in range(3):
@@ -32,5 +35,7 @@ for rep in range(3):
             mtb.dfpn_align_tail(d["x"], d["m"], d["mt"], d["flow"])
         if "cpn" in which:
             mtb.cpn_align_tail(d["x"], d["m"], d["mt"], d["theta"])
+        if "cm" in which:
+            ops.cm_match(*d["cm"])
 torch.cuda.synchronize()
 print("ok")
