@@ -628,9 +628,15 @@ def run_gpu(args):
     wl = WORKLOADS[args.workload](args.batch) if args.batch > 0 else WORKLOADS[args.workload]()
     hbm_peak, tf_peak, peak_src = measured_peaks()
 
-    # input sets rotate so that every step reads inputs last touched >= 2 steps ago
+    # The job is world x (per-GPU batch) samples; rank r owns the contiguous block shard.batch_shard gives it
+    # (samples / (b, f) frames are independent, no data-path collective).  The synthetic samples of a
+    # block are generated from its first global sample index, so the job's data does not depend on how many
+    # ranks run it.  Input sets rotate so that every step reads inputs last touched >= 2 steps ago.
+    from master_thesis_b200 import shard
+    s_lo, s_hi = shard.batch_shard(wl.b * world, rank, world)
+    assert s_hi - s_lo == wl.b
     nsets = args.sets
-    host_sets = [wl.host_inputs(1000 * rank + 17 * i) for i in range(nsets)]
+    host_sets = [wl.host_inputs(1000 * (s_lo // wl.b) + 17 * i) for i in range(nsets)]
     dsets = [{k: torch.from_numpy(v).to(dev) for k, v in hs.items()} for hs in host_sets]
     plans, outs, graphs = [], [], []
     for d in dsets:
@@ -813,7 +819,8 @@ def run_gpu(args):
                    "l2": "inputs rotate over %d buffer sets; %.0f MB algorithmic traffic per step, "
                          ">= %.0f MB between reuses of a set (L2 = 126 MB)"
                          % (nsets, step_bytes / 1e6, (nsets - 1) * step_bytes / 1e6),
-                   "sharding": "by sample, %d ranks, no data-path collective" % world,
+                   "sharding": "shard.batch_shard: contiguous blocks of %d of the job's %d samples per rank, %d ranks, "
+                               "no data-path collective" % (wl.b, wl.b * world, world),
                    "launch": "CUDA graph replay per step" if graphs else "one C-ABI call per kernel group",
                    "timed_region": "%d repetitions of exactly %d steps (barrier + sync around each); value = "
                                    "the median repetition" % (len(rounds), K)},

@@ -43,6 +43,7 @@ namespace {
 constexpr int kTile = 256;        // largest output tile: TM rows (one or two UMMA M = 128 halves) x TN <= 256 columns
 constexpr int kBK = 32;
 constexpr int kUmmaK = 8;         // tf32: 32 B of K per instruction
+constexpr bool kPairDefault = false;  // CTA-pair kernel on by default (set after the B200 sweep)
 
 // MN-major, SWIZZLE_128B_BASE32B shared-memory matrix descriptor (sm_100 "version 1").
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -369,6 +370,301 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
+
+// ======================================================================================================
+// CTA-PAIR variant (tcgen05 cta_group::2).  ncu on the single-CTA kernel above: the 128 B/clk of shared-memory
+// bandwidth per SM - TMA writes + UMMA operand reads + the norm warps' reads - bound it, not HBM or the tensor
+// pipe.  Two CTAs of a cluster on the two SMs of a TPC compute one 256 x TN tile with M = 256 instructions: each
+// CTA stages ITS 128 rows of A and ITS TN / 2 columns of B (half the TMA writes and half the operand reads per
+// SM), the leader's single thread issues the MMAs for both tensor cores, each CTA's TMEM receives its 128
+// rows x TN columns, so two accumulator buffers fit even for whole-frame tiles (TN = 256).
+// Hand-offs that cross the pair:
+//   * peer_full[s]  (leader): the peer's relay thread (its otherwise idle warp 1) forwards "my stage s has landed";
+//   * empty[s], tmem_full[b]: tcgen05.commit ... multicast::cluster arrives in both CTAs;
+//   * tmem_empty[b] (both): every epilogue warp arrives locally and on the peer - the leader may overwrite the
+//     accumulators, and either CTA's norm warps the scale tables, only when BOTH epilogues have drained them;
+//   * column scales: a CTA only sees its own TN / 2 columns of B, so its B-norm warps write sb into both CTAs'
+//     tables (st.shared::cluster) and arrive on both scales_ready[b].
+// ======================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t d;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(saddr), "r"(rank));
+    return d;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_remote_f32(uint32_t cluster_addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// wait with acquire at cluster scope: the phase may have been completed by the other CTA of the pair
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    do {
+#ifdef MT_PAIR_TESTWAIT
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
+        if (!ok && ++spins > (1u << 28)) __trap();
+    } while (!ok);
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    const uint32_t z = 0u;  // disable-output-lane mask: none
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+
+template <int TN, int STAGES>
+constexpr int smem_bytes_pair() {
+    return STAGES * ((128 + TN / 2) * kBK * 4) + kEpiBytes + 2 * (128 + kTile) * 4 /*scales*/ + 512 /*barriers*/ +
+           1024 /*alignment*/;
+}
+
+template <int TN, int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP, 1)
+corr_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const CorrTcArgs a) {
+    constexpr int TNH = TN / 2;                        // B columns staged by each CTA
+    constexpr int kStageBytesA = 128 * kBK * 4, kStageBytesB = TNH * kBK * 4;
+    constexpr int kBufs = 2;                           // accumulator buffers of TN columns (128 lanes per CTA)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + kStages * kStageBytesA;
+    float *epi = reinterpret_cast<float *>(smem + kStages * (kStageBytesA + kStageBytesB));
+    float *s_sa = epi + kEpiWarps * 32 * kEpiPitch;   // [2][128] row scales of this CTA's rows
+    float *s_sb = s_sa + 2 * 128;                     // [2][kTile] column scales of the whole tile
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_sb + 2 * kTile);
+    uint64_t *full = bars, *empty = bars + kStages, *peer_full = bars + 2 * kStages, *tmem_full = bars + 3 * kStages,
+             *tmem_empty = tmem_full + 2, *scales_ready = tmem_empty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(scales_ready + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank(), other = rank ^ 1u;
+    const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
+    const int num_k = a.C / kBK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(full + s), 1);
+            mbar_init(smem_u32(empty + s), 1 + kNormWarps);  // MMA commit (multicast) + one arrival per local norm warp
+            mbar_init(smem_u32(peer_full + s), 1);           // leader only: the peer's relay
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(tmem_full + i), 1);
+            mbar_init(smem_u32(tmem_empty + i), 2 * kEpiWarps);               // the epilogue warps of both CTAs
+            mbar_init(smem_u32(scales_ready + i), kNormWarps + kNormWarps / 2);  // local norm warps + the peer's B-norm warps
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: all 512 columns in both CTAs of the pair (the same warp id in both issues the alloc)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();  // barriers of both CTAs initialised before anyone arrives remotely
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
+
+    const int tiles_per_frame = a.tiles_m * a.tiles_n;
+    if (warp == 0) {
+        // ===== TMA producer: this CTA's 128 rows of A and TN / 2 columns of B =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = pair; tile < a.n_tiles; tile += npairs) {
+                const int frame = tile / tiles_per_frame, r = tile - frame * tiles_per_frame;
+                const int m_tile = r / a.tiles_n, n_tile = r - m_tile * a.tiles_n;
+                const int b = frame / a.F, f = frame - b * a.F;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1;
+                    mbar_wait(smem_u32(empty + s), ph ^ 1);
+                    mbar_expect_tx(smem_u32(full + s), kStageBytesA + kStageBytesB);
+                    tma_load_4d(smem_u32(smem_a + s * kStageBytesA), &map_a, smem_u32(full + s), 0, kb * kBK,
+                                m_tile * (kTile / 32) + (int)rank * 4, b);
+                    tma_load_5d(smem_u32(smem_b + s * kStageBytesB), &map_b, smem_u32(full + s), 0, kb * kBK,
+                                n_tile * (TN / 32) + (int)rank * (TNH / 32), f, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ===== MMA issuer (leader CTA, one thread): M = 256 over the pair =====
+            constexpr uint32_t idesc = instr_desc(256, TN);
+            uint32_t it = 0;
+            int ti = 0;
+            for (int tile = pair; tile < a.n_tiles; tile += npairs, ++ti) {
+                const int buf = ti % kBufs;
+                const uint32_t use = (uint32_t)(ti / kBufs);
+                mbar_wait_cluster(smem_u32(tmem_empty + buf), (use & 1) ^ 1);  // both epilogues have drained this buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_base + buf * TN;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1;
+                    mbar_wait(smem_u32(full + s), ph);
+                    mbar_wait_cluster(smem_u32(peer_full + s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = smem_u32(smem_a + s * kStageBytesA), b0 = smem_u32(smem_b + s * kStageBytesB);
+#pragma unroll
+                    for (int j = 0; j < kBK / kUmmaK; ++j)
+                        umma2_tf32(acc, umma_desc(a0 + j * 1024, kBK * 128, 512), umma_desc(b0 + j * 1024, kBK * 128, 512),
+                                   idesc, (kb | j) != 0 ? 1u : 0u);
+                    umma2_commit(smem_u32(empty + s));  // frees stage s in both CTAs when these MMAs retire
+                }
+                umma2_commit(smem_u32(tmem_full + buf));
+            }
+        } else if (lane == 0) {
+            // ===== relay (peer CTA): tell the leader that this CTA's stage has landed =====
+            uint32_t it = 0;
+            for (int tile = pair; tile < a.n_tiles; tile += npairs) {
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(smem_u32(full + s), (it / kStages) & 1);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive_remote(mapa_u32(smem_u32(peer_full + s), 0));
+                }
+            }
+        }
+    } else if (warp < 2 + kNormWarps) {
+        // ===== norm warps: threads 0..127 one row of this CTA's A half, threads 128..128+TNH-1 one of its B columns =====
+        const int t = threadIdx.x - 64;
+        const bool has_a = t < 128, has_b = t >= 128 && t < 128 + TNH;
+        const int ta = has_a ? t : 0, tb = has_b ? t - 128 : 0;
+        uint32_t base[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) base[r] = staged_offset(has_a ? ta : tb, r);
+        uint32_t it = 0;
+        int ti = 0;
+        for (int tile = pair; tile < a.n_tiles; tile += npairs, ++ti) {
+            const int frame = tile / tiles_per_frame, r0 = tile - frame * tiles_per_frame;
+            const int m_tile = r0 / a.tiles_n, n_tile = r0 - m_tile * a.tiles_n;
+            const int b = frame / a.F, f = frame - b * a.F;
+            const float vis = has_a ? corr_vis(a.vt ? a.vt + (int64_t)b * a.vt_sb : nullptr, m_tile * kTile + (int)rank * 128 + ta, a)
+                                    : corr_vis(a.vr ? a.vr + (int64_t)b * a.vr_sb + (int64_t)f * a.vr_sf : nullptr,
+                                               n_tile * TN + (int)rank * TNH + tb, a);
+            float q[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int kb = 0; kb < num_k; ++kb, ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(smem_u32(full + s), ph);
+                const uint8_t *ps = has_a ? smem_a + s * kStageBytesA : smem_b + s * kStageBytesB;
+                if (has_a || has_b) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                        for (int j = 0; j < kBK / 4; ++j) {
+                            const float v = *reinterpret_cast<const float *>(ps + base[r] + j * 512);
+                            q[r] = __fmaf_rn(v, v, q[r]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(empty + s));
+            }
+            const float ss = (q[0] + q[1]) + (q[2] + q[3]);
+            const int buf = ti % kBufs;
+            const uint32_t use = (uint32_t)(ti / kBufs);
+            // the scale tables of this buffer (here and in the peer) are free once both epilogues are done with them
+            mbar_wait_cluster(smem_u32(tmem_empty + buf), (use & 1) ^ 1);
+            const float sc = __fdiv_rn(vis, __fadd_rn(__fmul_rn(fabsf(vis), sqrtf(ss)), 1e-9f));
+            if (has_a) s_sa[buf * 128 + ta] = sc;
+            if (has_b) {
+                float *dst = s_sb + buf * kTile + (int)rank * TNH + tb;
+                *dst = sc;
+                st_remote_f32(mapa_u32(smem_u32(dst), other), sc);
+            }
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(scales_ready + buf));
+                if (t >= 128) mbar_arrive_remote(mapa_u32(smem_u32(scales_ready + buf), other));
+            }
+        }
+    } else {
+        // ===== epilogue warps: this CTA's 128 rows x TN columns =====
+        const int lq = warp & 3, ew = warp - (2 + kNormWarps);
+        float *st = epi + ew * 32 * kEpiPitch;
+        const int rr = lane >> 3, c4 = (lane & 7) * 4;
+        int ti = 0;
+        for (int tile = pair; tile < a.n_tiles; tile += npairs, ++ti) {
+            const int frame = tile / tiles_per_frame, r0 = tile - frame * tiles_per_frame;
+            const int m_tile = r0 / a.tiles_n, n_tile = r0 - m_tile * a.tiles_n;
+            const int buf = ti % kBufs;
+            const uint32_t use = (uint32_t)(ti / kBufs);
+            mbar_wait_cluster(smem_u32(scales_ready + buf), use & 1);
+            mbar_wait(smem_u32(tmem_full + buf), use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float *sbv = s_sb + buf * kTile;
+            const int row0 = lq * 32;
+            const float sa = s_sa[buf * 128 + row0 + lane];
+            float *oblk = a.out + (((int64_t)frame * a.P + m_tile * kTile + (int)rank * 128 + row0) * a.P + n_tile * TN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < TN; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TN + c0), v);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    float4 o;
+                    o.x = v[i] * sa * sbv[c0 + i];
+                    o.y = v[i + 1] * sa * sbv[c0 + i + 1];
+                    o.z = v[i + 2] * sa * sbv[c0 + i + 2];
+                    o.w = v[i + 3] * sa * sbv[c0 + i + 3];
+                    *reinterpret_cast<float4 *>(st + lane * kEpiPitch + i) = o;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int row = j * 4 + rr;
+                    const float4 o = *reinterpret_cast<const float4 *>(st + row * kEpiPitch + c4);
+                    __stcs(reinterpret_cast<float4 *>(oblk + (int64_t)row * a.P + c0 + c4), o);
+                }
+                __syncwarp();
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(tmem_empty + buf));
+                mbar_arrive_remote(mapa_u32(smem_u32(tmem_empty + buf), other));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal it
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
 }  // namespace
 
 int corr4d_tc_supported(int C, int P) {
@@ -416,12 +712,17 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
         if (!tn_given) tn = atn;
     }
     if (P % tn) tn = 64;
+    // CTA pairs (cta_group::2): whole-frame tiles on two SMs.  MT_CORR_2CTA = 1 forces, 0 disables; default: when the
+    // batch fills the pairs (see profiles/r2_experiments.md)
+    int pair = tuning("MT_CORR_2CTA", -1);
+    if (pair < 0) pair = kPairDefault && !tm_given && !tn_given && frames * 4 >= sm_count() ? 1 : 0;
+    if (pair && tn == 64) tn = 128;
     CUtensorMap map_a, map_b;
     {
         // ft (B, C, P) viewed as (32, C, P/32, B): strides in bytes for dims 1..3
         cuuint64_t dims[4] = {32, (cuuint64_t)C, (cuuint64_t)(P / 32), (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)ft_sc * 4, 128, (cuuint64_t)(B > 1 ? ft_sb : (int64_t)C * P) * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)kBK, (cuuint32_t)(tm / 32), 1};
+        cuuint32_t box[4] = {32, (cuuint32_t)kBK, (cuuint32_t)((pair ? 128 : tm) / 32), 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(ft), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
@@ -436,7 +737,7 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
         cuuint64_t dims[5] = {32, (cuuint64_t)C, (cuuint64_t)(P / 32), (cuuint64_t)F, (cuuint64_t)B};
         cuuint64_t strides[4] = {(cuuint64_t)fr_sc * 4, 128, (cuuint64_t)(F > 1 ? fr_sf : (int64_t)P) * 4,
                                  (cuuint64_t)(B > 1 ? fr_sb : (int64_t)C * F * P) * 4};
-        cuuint32_t box[5] = {32, (cuuint32_t)kBK, (cuuint32_t)(tn / 32), 1, 1};
+        cuuint32_t box[5] = {32, (cuuint32_t)kBK, (cuuint32_t)((pair ? tn / 2 : tn) / 32), 1, 1};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(fr), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
@@ -452,10 +753,40 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
     a.msy = mask_mode ? (float)MH / (float)fh : 1.0f;
     a.msx = mask_mode ? (float)MW / (float)fw : 1.0f;
     a.out = out; a.C = C; a.F = F; a.P = P;
-    a.tiles_m = P / tm; a.tiles_n = P / tn;
+    a.tiles_m = P / (pair ? kTile : tm); a.tiles_n = P / tn;
     const int64_t n_tiles = (int64_t)B * F * a.tiles_m * a.tiles_n;
     MT_REQUIRE(n_tiles < (1ll << 30), "mt_corr4d_fwd: too many tiles");
     a.n_tiles = (int)n_tiles;
+    if (pair) {
+        int npairs = sm_count() / 2;
+        if (npairs > a.n_tiles) npairs = a.n_tiles;
+        // cluster of two CTAs (compile-time __cluster_dims__) + programmatic dependent launch
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * npairs);
+        cfg.blockDim = dim3(kThreadsP);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 1 : 0;
+#define MT_CORR_PAIR_GO(TNV, STG)                                                                    \
+    do {                                                                                             \
+        static_assert(smem_bytes_pair<TNV, STG>() <= 227 * 1024, "stage ring exceeds the shared memory of an SM"); \
+        cudaError_t e = cudaFuncSetAttribute(corr_tc2_kernel<TNV, STG>,                              \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_pair<TNV, STG>()); \
+        if (e != cudaSuccess) {                                                                      \
+            set_error("mt_corr4d_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));             \
+            return MT_ERR_CUDA;                                                                      \
+        }                                                                                            \
+        cfg.dynamicSmemBytes = (size_t)smem_bytes_pair<TNV, STG>();                                  \
+        (void)cudaLaunchKernelEx(&cfg, corr_tc2_kernel<TNV, STG>, map_a, map_b, a);                  \
+    } while (0)
+        if (tn == 256) MT_CORR_PAIR_GO(256, 6);  // 6 x 32 KB per CTA
+        else MT_CORR_PAIR_GO(128, 8);            // 8 x 24 KB per CTA
+#undef MT_CORR_PAIR_GO
+        return launch_status("mt_corr4d_fwd");
+    }
     int ctas = sm_count();
     if (ctas > a.n_tiles) ctas = a.n_tiles;
     dim3 grid(ctas);

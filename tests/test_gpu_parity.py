@@ -281,6 +281,30 @@ def test_corr4d_every_tile_variant(mtb, name, tn, tm):
         assert np.array_equal(c == 0.0, o == 0.0)
 
 
+@pytest.mark.parametrize("tn", [128, 256])
+@pytest.mark.parametrize("name", ["real_masked", "real_nomask", "mid_masked", "big_masked"])
+def test_corr4d_cta_pairs(mtb, name, tn):
+    """The CTA-pair kernel (tcgen05 cta_group::2: M = 256 over two SMs, each CTA stages its half of A and of B,
+    column scales exchanged through distributed shared memory) on 2 / 40 / 128 frames: more tiles than pairs, fewer
+    tiles than pairs, masked and unmasked - against the reference's golden vectors and the whole oracle volume."""
+    spec = cases.CORR_CASES[name]
+    ft, vt, fr, vr = cases.corr_inputs(spec)
+    g = load_golden("corr_" + name)
+    try:
+        _set_tuning("MT_CORR_2CTA", 1)
+        _set_tuning("MT_CORR_TN", tn)
+        c = host(mtb.CorrelationVGG.correlation_masked_4d(dev(ft), dev(vt), dev(fr), dev(vr)))
+    finally:
+        _set_tuning("MT_CORR_TN", 0)
+        _set_tuning("MT_CORR_2CTA", -1)
+    _corr_tol_check(c, g, spec, True)
+    o = oracle.corr4d(ft, vt, fr, vr)
+    err = np.abs(c - o)
+    assert err.max() <= 2e-3 and err.max() <= 1e-2 * np.abs(o).max()
+    if vt is not None:
+        assert np.array_equal(c == 0.0, o == 0.0)
+
+
 # ---------------------------------------------------------------- a8
 @pytest.mark.parametrize("table", [2, 1, 0])
 @pytest.mark.parametrize("name", sorted(cases.CM_CASES))
@@ -380,6 +404,45 @@ def test_cm_grouped_full_size(mtb, keep):
     assert np.abs(out - oout).max() <= 1e-5 and np.abs(cmask - ocm).max() <= 2e-6
     assert np.array_equal(out[:, :128], cf[:, :, 0].reshape(8, 128, 64, 64))      # cat[c_t, ...]: a plain copy
     assert np.abs(out - out1).max() <= 1e-5 and np.abs(cmask - cmask1).max() <= 2e-6
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_launches_equal_unsharded(mtb, world):
+    """SURVEY 8(e) on the GPU: the (b, f) blocks of shard.frame_shard_groups (strided views of the full tensors,
+    one launch per group) and the per-sample CM shards of shard.batch_shard reproduce the unsharded launch bit
+    for bit - every emulated rank runs in turn on this GPU; there is no data-path collective to test."""
+    from master_thesis_b200 import ops, shard, synth
+    x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES["smooth_f4"])
+    b, c, f, h, w = x.shape
+    dx, dm, dmt, dfl = dev(x), dev(m), dev(m_t), dev(flow)
+    theta = dev(synth.thetas(5, b * f, 0.1))
+    full_d = [host(t) for t in mtb.dfpn_align_tail(dx, dm, dmt, dfl)]
+    full_c = [host(t) for t in mtb.cpn_align_tail(dx, dm, dmt, theta)]
+    got_d = [np.zeros_like(t) for t in full_d]
+    got_c = [np.zeros_like(t) for t in full_c]
+    owned = np.zeros((b, f), np.int32)
+    for rank in range(world):
+        for bi, (f0, f1) in shard.frame_shard_groups(b, f, rank, world).items():
+            owned[bi, f0:f1] += 1
+            part = mtb.dfpn_align_tail(dx[bi:bi + 1, :, f0:f1], dm[bi:bi + 1, :, f0:f1], dmt[bi:bi + 1], dfl[bi:bi + 1, f0:f1])
+            for dst, src in zip(got_d, part):
+                dst[bi, :, f0:f1] = host(src)[0]
+            th = theta.view(b, f, 2, 3)[bi, f0:f1].reshape(-1, 2, 3)
+            part = mtb.cpn_align_tail(dx[bi:bi + 1, :, f0:f1], dm[bi:bi + 1, :, f0:f1], dmt[bi:bi + 1], th)
+            for dst, src in zip(got_c, part):
+                dst[bi, :, f0:f1] = host(src)[0]
+    assert np.all(owned == 1)                        # the shards tile the B x F range exactly once
+    for a_, b_ in zip(got_d + got_c, full_d + full_c):
+        assert np.array_equal(a_, b_)
+    cf, vt, va = cases.cm_inputs(cases.CM_CASES["edge"])
+    dcf, dvt, dva = dev(cf), dev(vt), dev(va)
+    out, cmask = [host(t) for t in ops.cm_match(dcf, dvt, dva)]
+    for rank in range(world):
+        lo, hi = shard.batch_shard(cf.shape[0], rank, world)
+        if hi > lo:
+            o, cm = ops.cm_match(dcf[lo:hi], dvt[lo:hi], dva[lo:hi])
+            # a sample's result depends on its batch only through the number of CTAs that share its partial sums
+            assert np.abs(host(o) - out[lo:hi]).max() <= 1e-6 and np.abs(host(cm) - cmask[lo:hi]).max() <= 2e-6
 
 
 # ---------------------------------------------------------------- a9 .. a12
