@@ -148,6 +148,9 @@ class Align(Workload):
         return d
 
     def gpu_step(self, mtb, d):
+        # one stream: capturing the two aligners' paths as parallel graph branches was measured (r2, call M: 104.5 vs
+        # 102.0 us) - every kernel here is a persistent one-CTA-per-SM kernel with ~200 KB of shared memory, so two
+        # of them never share an SM and the branches only interleave
         out = self.dfpn.gpu_step(mtb, d)
         out.update({"cpn_" + k: v for k, v in self.cpn.gpu_step(mtb, d).items()})
         return out

@@ -399,6 +399,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// relaxed: for a thread that only forwards a signal.  A release arrive waits for the thread's previous remote
+// operation to be performed, which serialised the relay at one remote round trip (~1.2 us) per pipeline stage.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void st_remote_f32(uint32_t cluster_addr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
 }
@@ -532,7 +537,7 @@ corr_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const int s = it % kStages;
                     const uint32_t ph = (it / kStages) & 1;
                     mbar_wait(smem_u32(full + s), ph);
-                    mbar_wait_cluster(smem_u32(peer_full + s), ph);
+                    mbar_wait(smem_u32(peer_full + s), ph);  // remote arrival; the operands are read by the async proxy only
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a0 = smem_u32(smem_a + s * kStageBytesA), b0 = smem_u32(smem_b + s * kStageBytesB);
 #pragma unroll
@@ -545,13 +550,13 @@ corr_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         } else if (lane == 0) {
             // ===== relay (peer CTA): tell the leader that this CTA's stage has landed =====
+            const uint32_t leader_bar = mapa_u32(smem_u32(peer_full), 0);
             uint32_t it = 0;
             for (int tile = pair; tile < a.n_tiles; tile += npairs) {
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     const int s = it % kStages;
                     mbar_wait(smem_u32(full + s), (it / kStages) & 1);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive_remote(mapa_u32(smem_u32(peer_full + s), 0));
+                    mbar_arrive_remote_relaxed(leader_bar + (uint32_t)s * 8u);
                 }
             }
         }
