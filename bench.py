@@ -834,7 +834,35 @@ def run_gpu(args):
     }
     line.update(line_extra)
     if ddp:
+        # the collective alone and the kernels alone, for reading the overlap: step ~ max(kernels, all-reduce) when they overlap
+        def ar_only():
+            g = ddp["grads"]
+            for o in range(0, g.numel(), ddp["bucket"]):
+                dist.all_reduce(g[o:o + ddp["bucket"]])
+        for _ in range(3):
+            ar_only()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            ar_only()
+        a1.record()
+        barrier()
+        ar_ms = a0.elapsed_time(a1) / 10
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for i in range(K):
+            (graphs[i % nsets].replay() if graphs else plans[i % nsets]())
+        k1.record()
+        barrier()
+        kern_ms = k0.elapsed_time(k1) / K
+        t = torch.tensor([ar_ms, kern_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_ms, kern_ms = float(t[0]), float(t[1])
         line["ddp"] = {"allreduce_bytes_per_step": ddp["bytes"], "bucket_bytes": ddp["bucket"] * 4,
+                       "allreduce_alone_ms": ar_ms, "kernels_alone_ms_per_step": kern_ms,
+                       "value_without_allreduce": wl.frames_per_step * world / (kern_ms * 1e-3),
+                       "allreduce_busbw_gbs": 2.0 * (world - 1) / world * ddp["bytes"] / (ar_ms * 1e-3) / 1e9,
                        "note": "NCCL all-reduce of a gradient-sized fp32 buffer (DFPN 13.92 M / CHN 14.69 M parameters, "
                                "SURVEY section 5) on its own stream inside every timed step, overlapped with the kernels"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

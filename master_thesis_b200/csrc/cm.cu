@@ -493,7 +493,11 @@ struct CmGroupCfg {
     static constexpr int kBatchBytes = UN * R * 256 * 16;     // reference features of one batch parked in shared memory
 };
 
-template <int R>
+// PIPE (a group owns >= 2 samples): pass 1 of the group's NEXT sample is issued before pass 2 of the current one.
+// The hand-off then never stalls (the other CTAs of the group finish their pass 1 of sample i while this one streams
+// sample i + 1) and the DRAM-bound and the L2-bound phases of different CTAs overlap.  The batches parked in shared
+// memory belong to one sample at a time (every other sample); nothing is kept in registers across the next pass 1.
+template <int R, bool PIPE>
 __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const int keep) {
     constexpr int G2 = 2 * R, TABF = (1 << R) * (R + 1), UN = CmGroupCfg<R>::UN;
     constexpr int kMw = 4;  // mask words cached per thread (one per 1024-pixel chunk) when the sample has <= kMw chunks
@@ -510,45 +514,42 @@ __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const 
     const int NI = a.C * a.chunks;
     const int lo = (int)((int64_t)s * NI / a.S), hi = (int)((int64_t)(s + 1) * NI / a.S);
     const int nb = (hi - lo + UN - 1) / UN;  // batches of this CTA
-    // pass 2 takes batch nb - 1 from registers, batches 0 .. np - 1 (the oldest in L2) from shared memory, the rest from L2
-    const int np = min(keep, nb - 1);
     const int fP = a.f * a.P;  // 32-bit offsets within a sample (the launcher checks (2C + 1) * f * P < 2^31)
     const bool mw_cached = a.chunks <= kMw;
     bool waited = false;  // griddepcontrol.wait (cm_masks complete) once, after the first feature loads are in flight
-#pragma unroll 1
-    for (int b = g; b < a.B; b += a.G) {
+    float4 cr[UN][R];     // reference features of the batch in flight; !PIPE: the last batch of pass 1 stays here for pass 2
+
+    auto mask_word = [&](const uint32_t (&mwq)[kMw], const unsigned char *pm, int q, int p) -> uint32_t {
+        if (mw_cached) {
+            uint32_t w = mwq[0];
+#pragma unroll
+            for (int j = 1; j < kMw; ++j) w = q == j ? mwq[j] : w;
+            return w;
+        }
+        return __ldcg(reinterpret_cast<const uint32_t *>(pm + p));
+    };
+    auto load_cr = [&](const float *fb, int bi, bool stream) {
+        const int it = lo + bi * UN;
+#pragma unroll
+        for (int k = 0; k < UN; ++k) {
+            // slots past the CTA's range / the chunk's end load a valid (clamped) address and are skipped by the
+            // consumers: unconditional loads keep the register live ranges apart (ptxas spilled otherwise)
+            const int i = min(it + k, hi - 1), c = i / a.chunks, p = (i - c * a.chunks) * 1024 + tid * 4;
+            const float *base = fb + (c * fP + min(p, a.P - 4));
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                cr[k][r] = stream ? ld_stream4(base + (r + 1) * a.P)
+                                  : __ldg(reinterpret_cast<const float4 *>(base + (r + 1) * a.P));
+        }
+    };
+    // ---------------- pass 1: partial dot products of this CTA's items, c_t copied through; arrives, does not wait ----------------
+    auto pass1 = [&](int b, uint32_t (&mwq)[kMw], int np) {
         const float *fb = a.c_feats + (int64_t)b * a.C * fP;
         const unsigned char *pm = a.pmask + (int64_t)b * a.P;
         float *ob = a.out + (int64_t)b * (2 * a.C + 1) * a.P;
-        uint32_t mwq[kMw] = {0u, 0u, 0u, 0u};
-        auto mask_word = [&](int q, int p) -> uint32_t {
-            if (mw_cached) {
-                uint32_t w = mwq[0];
-#pragma unroll
-                for (int j = 1; j < kMw; ++j) w = q == j ? mwq[j] : w;
-                return w;
-            }
-            return __ldcg(reinterpret_cast<const uint32_t *>(pm + p));
-        };
-        auto load_cr = [&](int bi, float4 (&cr)[UN][R], bool stream) {
-            const int it = lo + bi * UN;
-#pragma unroll
-            for (int k = 0; k < UN; ++k) {
-                // slots past the CTA's range / the chunk's end load a valid (clamped) address and are skipped by the
-                // consumers: unconditional loads keep the register live ranges apart (ptxas spilled otherwise)
-                const int i = min(it + k, hi - 1), c = i / a.chunks, p = (i - c * a.chunks) * 1024 + tid * 4;
-                const float *base = fb + (c * fP + min(p, a.P - 4));
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    cr[k][r] = stream ? ld_stream4(base + (r + 1) * a.P)
-                                      : __ldg(reinterpret_cast<const float4 *>(base + (r + 1) * a.P));
-            }
-        };
-        // ---------------- pass 1: partial dot products of this CTA's items, c_t copied through ----------------
         float acc[G2];
 #pragma unroll
         for (int r = 0; r < G2; ++r) acc[r] = 0.0f;
-        float4 cr[UN][R];  // the last batch stays here for pass 2
 #pragma unroll 1
         for (int bi = 0; bi < nb; ++bi) {
             const int it = lo + bi * UN;
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const 
                 const int i = min(it + k, hi - 1), c = i / a.chunks, p = (i - c * a.chunks) * 1024 + tid * 4;
                 ct[k] = __ldg(reinterpret_cast<const float4 *>(fb + (c * fP + min(p, a.P - 4))));
             }
-            load_cr(bi, cr, false);  // default L2 policy: part of it is read again in pass 2
+            load_cr(fb, bi, false);  // default L2 policy: part of it is read again in pass 2
             if (!waited) { pdl_wait(); waited = true; }
             if (bi == 0 && mw_cached) {
 #pragma unroll
@@ -569,7 +570,7 @@ __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const 
             for (int k = 0; k < UN; ++k) {
                 const int i = it + k, c = i / a.chunks, q = i - c * a.chunks, p = q * 1024 + tid * 4;
                 if (i >= hi || p >= a.P) continue;
-                const uint32_t mw = mask_word(q, p);
+                const uint32_t mw = mask_word(mwq, pm, q, p);
                 st_stream4(ob + (c * a.P + p), ct[k]);                             // cat[c_t, ...]  :243
 #pragma unroll
                 for (int r = 0; r < R; ++r) {  // vt' * vr'                  :220
@@ -593,6 +594,11 @@ __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const 
             for (int r = 0; r < G2; ++r) o[r] = acc[r];
             __threadfence();
             atomicAdd(a.counters + b, 1u);
+        }
+    };
+    // ---------------- hand-off inside the group, gs[b, :] (fixed order, double), softmax table ----------------
+    auto handoff = [&](int b) {
+        if (tid == 0) {
             unsigned int seen;
             do {  // the S CTAs of this group only
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.counters + b) : "memory");
@@ -600,37 +606,41 @@ __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const 
             } while (seen < (unsigned int)a.S);
         }
         __syncthreads();
-        // ---------------- pass 1b: gs[b, :] (fixed order, double) and the softmax table ----------------
-        {
-            constexpr int kSlots = 256 / G2;
-            double v = 0.0;
-            if (tid < kSlots * G2) {
-                const int r = tid % G2, i0 = tid / G2;
-                const float *o = a.gpart + (int64_t)b * a.S * G2 + r;
+        constexpr int kSlots = 256 / G2;
+        double v = 0.0;
+        if (tid < kSlots * G2) {
+            const int r = tid % G2, i0 = tid / G2;
+            const float *o = a.gpart + (int64_t)b * a.S * G2 + r;
 #pragma unroll 4
-                for (int i = i0; i < a.S; i += kSlots) v += (double)__ldcg(o + (int64_t)i * G2);
-            }
-            dred[tid] = v;
-            __syncthreads();
-            if (tid < R) {
-                double d = 0.0, vs = 0.0;
-                for (int sl = 0; sl < kSlots; ++sl) { d += dred[sl * G2 + tid]; vs += dred[sl * G2 + R + tid]; }
-                const bool zero = vs < 1e-4;                                       // :222
-                const float v_sum = (float)vs + (zero ? 1.0f : 0.0f);              // :223
-                const float gg = (float)d / (v_sum * (float)a.C);                  // :225-227
-                gs_smem[tid] = zero ? 0.0f : gg;                                   // :228
-                if (s == 0) a.gs[(int64_t)b * R + tid] = gs_smem[tid];
-            }
-            __syncthreads();
-            softmax_table<R>(gs_smem, tab);
-            __syncthreads();
+            for (int i = i0; i < a.S; i += kSlots) v += (double)__ldcg(o + (int64_t)i * G2);
         }
-        // ---------------- pass 2: sum_r w_r c_r and c_mask ----------------
+        dred[tid] = v;
+        __syncthreads();
+        if (tid < R) {
+            double d = 0.0, vs = 0.0;
+            for (int sl = 0; sl < kSlots; ++sl) { d += dred[sl * G2 + tid]; vs += dred[sl * G2 + R + tid]; }
+            const bool zero = vs < 1e-4;                                       // :222
+            const float v_sum = (float)vs + (zero ? 1.0f : 0.0f);              // :223
+            const float gg = (float)d / (v_sum * (float)a.C);                  // :225-227
+            gs_smem[tid] = zero ? 0.0f : gg;                                   // :228
+            if (s == 0) a.gs[(int64_t)b * R + tid] = gs_smem[tid];
+        }
+        __syncthreads();
+        softmax_table<R>(gs_smem, tab);
+        __syncthreads();
+    };
+    // ---------------- pass 2: sum_r w_r c_r and c_mask ----------------
+    // operands: batch nb - 1 from registers if `last_in_regs`, batches 0 .. np - 1 (the oldest in L2) from shared memory,
+    // the rest from L2, most recently read first, each requested one step ahead while a parked batch is processed
+    auto pass2 = [&](int b, const uint32_t (&mwq)[kMw], int np, bool last_in_regs) {
+        const float *fb = a.c_feats + (int64_t)b * a.C * fP;
+        const unsigned char *pm = a.pmask + (int64_t)b * a.P;
+        float *ob = a.out + (int64_t)b * (2 * a.C + 1) * a.P;
         // one item: the weights of its 4 pixels are table rows selected by the mask bytes
         auto emit = [&](int i, auto &&ref) {
             const int c = i / a.chunks, q = i - c * a.chunks, p = q * 1024 + tid * 4;
             if (i >= hi || p >= a.P) return;
-            const uint32_t mw = mask_word(q, p);
+            const uint32_t mw = mask_word(mwq, pm, q, p);
             int pat[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) pat[j] = (int)((mw >> (8 * j + 1)) & ((1u << R) - 1u)) * (R + 1);
@@ -658,24 +668,50 @@ __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const 
 #pragma unroll
             for (int k = 0; k < UN; ++k) emit(lo + bi * UN + k, [&](int r) { return park[((bi * UN + k) * R + r) * 256 + tid]; });
         };
-        // order: registers (batch nb - 1), then the L2 batches nb - 2 ... np (most recently read first), each requested
-        // one step ahead and a parked batch processed while it is in flight
         if (nb > 0) {
-            emit_regs(nb - 1);
+            int j = nb - 1;        // next register / L2 batch
             int q = 0;             // next parked batch
-            int j = nb - 2;        // next L2 batch
-            if (j >= np) load_cr(j, cr, true);
+            if (last_in_regs) { emit_regs(j); --j; }
+            if (j >= np) load_cr(fb, j, true);
 #pragma unroll 1
             while (j >= np || q < np) {
                 if (q < np) { emit_parked(q); ++q; }
                 if (j >= np) {
                     emit_regs(j);
                     --j;
-                    if (j >= np) load_cr(j, cr, true);
+                    if (j >= np) load_cr(fb, j, true);
                 }
             }
         }
-        __syncthreads();  // red / tab / park are reused by the next sample of this group
+    };
+
+    uint32_t mw_a[kMw] = {0u, 0u, 0u, 0u};
+    if constexpr (!PIPE) {
+        const int np = min(keep, nb - 1);
+#pragma unroll 1
+        for (int b = g; b < a.B; b += a.G) {
+            pass1(b, mw_a, np);
+            handoff(b);
+            pass2(b, mw_a, np, true);
+            __syncthreads();  // red / tab / park are reused by the next sample of this group
+        }
+    } else {
+        uint32_t mw_b[kMw] = {0u, 0u, 0u, 0u};
+        const int npk = min(keep, nb);
+        bool parked = true;   // the sample whose pass 1 runs next may park (the slots are free)
+        if (g < a.B) pass1(g, mw_a, npk);
+#pragma unroll 1
+        for (int b = g; b < a.B; b += a.G) {
+            const int bn = b + a.G;
+            const bool cur_parked = parked;
+            if (bn < a.B) pass1(bn, mw_b, cur_parked ? 0 : npk);  // the slots hold sample b's batches iff cur_parked
+            handoff(b);
+            pass2(b, mw_a, cur_parked ? npk : 0, false);
+            parked = !cur_parked;
+#pragma unroll
+            for (int j = 0; j < kMw; ++j) mw_a[j] = mw_b[j];
+            __syncthreads();
+        }
     }
 }
 
@@ -686,7 +722,7 @@ int cm_group_ctas(int *keep_out) {
     if (n == 0) {
         cudaFuncAttributes fa;
         int dev = 0, smem_sm = 0, occ = 0;
-        if (cudaFuncGetAttributes(&fa, cm_group_kernel<R>) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess ||
+        if (cudaFuncGetAttributes(&fa, cm_group_kernel<R, false>) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess ||
             cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess)
             return 0;
         // two CTAs per SM: each gets half of the SM's shared memory minus its static part and the 1 KB the system reserves
@@ -695,8 +731,12 @@ int cm_group_ctas(int *keep_out) {
         if (kp > 8) kp = 8;
         if (kp < 0) kp = 0;
         const int bytes = kp * CmGroupCfg<R>::kBatchBytes;
-        if (cudaFuncSetAttribute(cm_group_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cm_group_kernel<R>, 256, bytes) != cudaSuccess || occ < 1) return 0;
+        if (cudaFuncSetAttribute(cm_group_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+            cudaFuncSetAttribute(cm_group_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 0;
+        int occ2 = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cm_group_kernel<R, false>, 256, bytes) != cudaSuccess || occ < 1 ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, cm_group_kernel<R, true>, 256, bytes) != cudaSuccess || occ2 < 1) return 0;
+        if (occ2 < occ) occ = occ2;
         keep = kp;
         n = sm_count() * (occ > 2 ? 2 : occ);
     }
@@ -713,18 +753,29 @@ int launch_cm(CmArgs a, cudaStream_t st) {
         const int ctas = (mode == 2 && (int64_t)(2 * a.C + 1) * a.f * a.P < (1ll << 31)) ? cm_group_ctas<R>(&keep) : 0;
         keep = max(0, min(keep, tuning("MT_CM_KEEP", 8)));  // batches parked in shared memory between the passes
         if (ctas > 0) {
-            // samples in flight: as many as keep their features (C * f * P * 4 B each) within ~90 MB of L2
+            // samples in flight: as many as keep their features (C * f * P * 4 B each) within ~90 MB of L2.  Pipelined
+            // form (default when B >= 2): a group streams its next sample before it finishes the current one, so
+            // two samples per group are in flight and G is half as large.
             const int64_t sample_bytes = (int64_t)a.C * a.f * a.P * 4;
+            const int64_t fit = (int64_t)tuning("MT_CM_L2_MB", 90) * 1000000 / sample_bytes;
+            int pipe = tuning("MT_CM_PIPE", -1);
             int64_t g = tuning("MT_CM_GROUPS", 0);
-            if (g <= 0) g = (int64_t)tuning("MT_CM_L2_MB", 90) * 1000000 / sample_bytes;
+            if (g <= 0) {
+                if (pipe != 0 && a.B >= 2) { g = fit / 2 < a.B / 2 ? fit / 2 : a.B / 2; pipe = 1; }
+                else { g = fit; pipe = 0; }
+            }
             if (g > a.B) g = a.B;
             if (g > ctas) g = ctas;
             if (g < 1) g = 1;
+            if (pipe < 0) pipe = a.B > g ? 1 : 0;
+            if (a.B <= g) pipe = 0;  // one sample per group: nothing to overlap
             a.G = (int)g;
             a.S = ctas / a.G;
             if (a.S > kMaxGroupCtas) a.S = kMaxGroupCtas;
             launch(cm_masks_kernel, dim3((a.P + 255) / 256, a.B), 256, 0, st, a);
-            launch(cm_group_kernel<R>, dim3(a.G * a.S), 256, (size_t)keep * CmGroupCfg<R>::kBatchBytes, st, a, keep);
+            const size_t dyn = (size_t)keep * CmGroupCfg<R>::kBatchBytes;
+            if (pipe) launch(cm_group_kernel<R, true>, dim3(a.G * a.S), 256, dyn, st, a, keep);
+            else launch(cm_group_kernel<R, false>, dim3(a.G * a.S), 256, dyn, st, a, keep);
             return launch_status("mt_cm_match_fwd");
         }
     }
