@@ -493,11 +493,7 @@ struct CmGroupCfg {
     static constexpr int kBatchBytes = UN * R * 256 * 16;     // reference features of one batch parked in shared memory
 };
 
-// PIPE (a group owns >= 2 samples): pass 1 of the group's NEXT sample is issued before pass 2 of the current one.
-// The hand-off then never stalls (the other CTAs of the group finish their pass 1 of sample i while this one streams
-// sample i + 1) and the DRAM-bound and the L2-bound phases of different CTAs overlap.  The batches parked in shared
-// memory belong to one sample at a time (every other sample); nothing is kept in registers across the next pass 1.
-template <int R, bool PIPE>
+template <int R>
 __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const int keep) {
     constexpr int G2 = 2 * R, TABF = (1 << R) * (R + 1), UN = CmGroupCfg<R>::UN;
     constexpr int kMw = 4;  // mask words cached per thread (one per 1024-pixel chunk) when the sample has <= kMw chunks
@@ -517,7 +513,7 @@ __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const 
     const int fP = a.f * a.P;  // 32-bit offsets within a sample (the launcher checks (2C + 1) * f * P < 2^31)
     const bool mw_cached = a.chunks <= kMw;
     bool waited = false;  // griddepcontrol.wait (cm_masks complete) once, after the first feature loads are in flight
-    float4 cr[UN][R];     // reference features of the batch in flight; !PIPE: the last batch of pass 1 stays here for pass 2
+    float4 cr[UN][R];     // reference features of the batch in flight; the last batch of pass 1 stays here for pass 2
 
     auto mask_word = [&](const uint32_t (&mwq)[kMw], const unsigned char *pm, int q, int p) -> uint32_t {
         if (mw_cached) {
@@ -685,33 +681,18 @@ __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const 
         }
     };
 
-    uint32_t mw_a[kMw] = {0u, 0u, 0u, 0u};
-    if constexpr (!PIPE) {
-        const int np = min(keep, nb - 1);
+    // A software-pipelined form (pass 1 of the group's next sample before pass 2 of the current one, two samples per
+    // group in flight, G = 4) hid the hand-off but was 5 - 10 % slower in the step (profiles/r2_experiments.md): with
+    // half as many items per CTA and sample the batches are short (3 + 3 + 1 items) and every other sample has no parked
+    // batches.  Not kept.
+    uint32_t mwq[kMw] = {0u, 0u, 0u, 0u};
+    const int np = min(keep, nb - 1);
 #pragma unroll 1
-        for (int b = g; b < a.B; b += a.G) {
-            pass1(b, mw_a, np);
-            handoff(b);
-            pass2(b, mw_a, np, true);
-            __syncthreads();  // red / tab / park are reused by the next sample of this group
-        }
-    } else {
-        uint32_t mw_b[kMw] = {0u, 0u, 0u, 0u};
-        const int npk = min(keep, nb);
-        bool parked = true;   // the sample whose pass 1 runs next may park (the slots are free)
-        if (g < a.B) pass1(g, mw_a, npk);
-#pragma unroll 1
-        for (int b = g; b < a.B; b += a.G) {
-            const int bn = b + a.G;
-            const bool cur_parked = parked;
-            if (bn < a.B) pass1(bn, mw_b, cur_parked ? 0 : npk);  // the slots hold sample b's batches iff cur_parked
-            handoff(b);
-            pass2(b, mw_a, cur_parked ? npk : 0, false);
-            parked = !cur_parked;
-#pragma unroll
-            for (int j = 0; j < kMw; ++j) mw_a[j] = mw_b[j];
-            __syncthreads();
-        }
+    for (int b = g; b < a.B; b += a.G) {
+        pass1(b, mwq, np);
+        handoff(b);
+        pass2(b, mwq, np, true);
+        __syncthreads();  // red / tab / park are reused by the next sample of this group
     }
 }
 
@@ -722,7 +703,7 @@ int cm_group_ctas(int *keep_out) {
     if (n == 0) {
         cudaFuncAttributes fa;
         int dev = 0, smem_sm = 0, occ = 0;
-        if (cudaFuncGetAttributes(&fa, cm_group_kernel<R, false>) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess ||
+        if (cudaFuncGetAttributes(&fa, cm_group_kernel<R>) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess ||
             cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess)
             return 0;
         // two CTAs per SM: each gets half of the SM's shared memory minus its static part and the 1 KB the system reserves
@@ -731,12 +712,8 @@ int cm_group_ctas(int *keep_out) {
         if (kp > 8) kp = 8;
         if (kp < 0) kp = 0;
         const int bytes = kp * CmGroupCfg<R>::kBatchBytes;
-        if (cudaFuncSetAttribute(cm_group_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
-            cudaFuncSetAttribute(cm_group_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 0;
-        int occ2 = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cm_group_kernel<R, false>, 256, bytes) != cudaSuccess || occ < 1 ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, cm_group_kernel<R, true>, 256, bytes) != cudaSuccess || occ2 < 1) return 0;
-        if (occ2 < occ) occ = occ2;
+        if (cudaFuncSetAttribute(cm_group_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cm_group_kernel<R>, 256, bytes) != cudaSuccess || occ < 1) return 0;
         keep = kp;
         n = sm_count() * (occ > 2 ? 2 : occ);
     }
@@ -753,29 +730,18 @@ int launch_cm(CmArgs a, cudaStream_t st) {
         const int ctas = (mode == 2 && (int64_t)(2 * a.C + 1) * a.f * a.P < (1ll << 31)) ? cm_group_ctas<R>(&keep) : 0;
         keep = max(0, min(keep, tuning("MT_CM_KEEP", 8)));  // batches parked in shared memory between the passes
         if (ctas > 0) {
-            // samples in flight: as many as keep their features (C * f * P * 4 B each) within ~90 MB of L2.  Pipelined
-            // form (default when B >= 2): a group streams its next sample before it finishes the current one, so
-            // two samples per group are in flight and G is half as large.
+            // samples in flight: as many as keep their features (C * f * P * 4 B each) within ~90 MB of L2
             const int64_t sample_bytes = (int64_t)a.C * a.f * a.P * 4;
-            const int64_t fit = (int64_t)tuning("MT_CM_L2_MB", 90) * 1000000 / sample_bytes;
-            int pipe = tuning("MT_CM_PIPE", -1);
             int64_t g = tuning("MT_CM_GROUPS", 0);
-            if (g <= 0) {
-                if (pipe != 0 && a.B >= 2) { g = fit / 2 < a.B / 2 ? fit / 2 : a.B / 2; pipe = 1; }
-                else { g = fit; pipe = 0; }
-            }
+            if (g <= 0) g = (int64_t)tuning("MT_CM_L2_MB", 90) * 1000000 / sample_bytes;
             if (g > a.B) g = a.B;
             if (g > ctas) g = ctas;
             if (g < 1) g = 1;
-            if (pipe < 0) pipe = a.B > g ? 1 : 0;
-            if (a.B <= g) pipe = 0;  // one sample per group: nothing to overlap
             a.G = (int)g;
             a.S = ctas / a.G;
             if (a.S > kMaxGroupCtas) a.S = kMaxGroupCtas;
             launch(cm_masks_kernel, dim3((a.P + 255) / 256, a.B), 256, 0, st, a);
-            const size_t dyn = (size_t)keep * CmGroupCfg<R>::kBatchBytes;
-            if (pipe) launch(cm_group_kernel<R, true>, dim3(a.G * a.S), 256, dyn, st, a, keep);
-            else launch(cm_group_kernel<R, false>, dim3(a.G * a.S), 256, dyn, st, a, keep);
+            launch(cm_group_kernel<R>, dim3(a.G * a.S), 256, (size_t)keep * CmGroupCfg<R>::kBatchBytes, st, a, keep);
             return launch_status("mt_cm_match_fwd");
         }
     }

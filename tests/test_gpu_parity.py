@@ -381,20 +381,17 @@ def test_cm_grouped_rounds(mtb, groups):
         _set_tuning("MT_CM_GROUPS", 0)
 
 
-@pytest.mark.parametrize("keep,pipe", [(8, -1), (1, -1), (0, -1), (8, 0), (1, 0), (0, 0)])
-def test_cm_grouped_full_size(mtb, keep, pipe):
-    """cfg2 size (B = 8, 128 x 5 x 64 x 64) so that pass 2 of the grouped kernel takes its operands from all three
-    places.  pipe = 0: one sample per group (14 items per CTA): the last batch from registers, `keep` batches from
-    shared memory, the rest from L2.  pipe = -1 (default: pipelined, two samples per group, 7 items per CTA): pass 1
-    of the next sample runs before pass 2 of the current one, parked batches belong to every other sample, the rest
-    comes from L2.  Checked against the oracle and against the two-launch form."""
+@pytest.mark.parametrize("keep", [8, 1, 0])
+def test_cm_grouped_full_size(mtb, keep):
+    """cfg2 size (B = 8, 128 x 5 x 64 x 64: 14 items per CTA) so that pass 2 of the grouped kernel takes its
+    operands from all three places: the last batch from registers, `keep` batches from shared memory, the rest
+    from L2.  Checked against the oracle and against the two-launch form."""
     from master_thesis_b200 import ops, synth
     cf, vt, va = synth.cm_inputs(91, 8, 5, 128, 64, 64)
     oout, ocm, ogs = oracle.cm_module(cf, vt, va, return_gs=True)
     dcf, dvt, dva = dev(cf), dev(vt), dev(va)
     try:
         _set_tuning("MT_CM_KEEP", keep)
-        _set_tuning("MT_CM_PIPE", pipe)
         out, cmask, gs = ops.cm_match(dcf, dvt, dva, return_gs=True)
         out, cmask, gs = host(out), host(cmask), host(gs.clone())
         _set_tuning("MT_CM_TABLE", 1)
@@ -402,7 +399,6 @@ def test_cm_grouped_full_size(mtb, keep, pipe):
         out1, cmask1 = host(out1), host(cmask1)
     finally:
         _set_tuning("MT_CM_KEEP", 8)
-        _set_tuning("MT_CM_PIPE", -1)
         _set_tuning("MT_CM_TABLE", 2)
     assert np.abs(gs - ogs).max() <= 1e-6 * max(1.0, np.abs(ogs).max())
     assert np.abs(out - oout).max() <= 1e-5 and np.abs(cmask - ocm).max() <= 2e-6

@@ -1,5 +1,5 @@
 """Small invocations of the kernels that changed in round 2, for `compute-sanitizer --tool memcheck|racecheck`:
-grouped CM (pipelined and one-sample-per-group, ragged shapes), correlation (single-CTA tiles and CTA pairs),
+grouped CM (one and several samples per group, ragged shapes), correlation (single-CTA tiles and CTA pairs),
 dense / low-resolution / staged warp, fused loss forward + backward."""
 import os
 import sys
@@ -21,10 +21,10 @@ def tune(name, v):
 for shape in ((5, 4, 9, 24, 48), (3, 5, 16, 32, 32), (1, 8, 6, 16, 16)):
     b, f, c, h, w = shape
     cf, vt, va = synth.cm_inputs(61 + b, b, f, c, h, w, 4)
-    for pipe in (-1, 0):
-        tune("MT_CM_PIPE", pipe)
+    for groups in (0, 1):
+        tune("MT_CM_GROUPS", groups)
         ops.cm_match(dev(cf), dev(vt), dev(va))
-tune("MT_CM_PIPE", -1)
+tune("MT_CM_GROUPS", 0)
 ft, vt, fr, vr = synth.vgg_feats(5, 1, 2)
 for pair, tm, tn in ((0, 0, 0), (0, 256, 256), (0, 128, 64), (1, 0, 256), (1, 0, 128)):
     tune("MT_CORR_2CTA", pair); tune("MT_CORR_TM", tm); tune("MT_CORR_TN", tn)
