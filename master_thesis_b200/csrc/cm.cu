@@ -6,27 +6,20 @@
 // The reference's "correlation" here is ONE masked global dot product per
 // (sample, reference) - K = C*h*w = 524 288 terms, M = N = 1 - followed by a
 // per-pixel softmax over the references and a weighted copy.  It is HBM-bound
-// (AI ~ 0.6 flop/B), not a GEMM, so it stays on the SIMT pipes.  Three launches:
+// (AI ~ 0.6 flop/B), not a GEMM, so it stays on the SIMT pipes.  Default: two launches
 //   pass 0  cm_masks:  v' = bilinear_resize(v, (h,w)) > 0.5 for target + refs, as floats and as
-//                      one byte per pixel (bit 0 target, bit r+1 reference r)
-//   pass 1  cm_sim:    partial sums of vt'*vr'*c_t*c_r (and of vt'*vr') per (b, r);
-//                      reads c_feats exactly once from HBM (16 B loads); its feature loads are
-//                      issued before griddepcontrol.wait, i.e. while cm_masks is still running
-//   pass 2  cm_copy2:  streams c_feats again (reverse sample order: the tail of the batch is what
-//                      pass 1 left in L2) and writes cat[c_t, sum_r c_r * w_r, c_mask]; every CTA
-//                      folds the partials of its sample into gs (fixed order, double) and evaluates
-//                      the masked softmax once per MASK PATTERN (2^R entries), weights per pixel are
-//                      a lookup by the mask byte.  (With 8 references, or MT_CM_TABLE=0: the separate
-//                      cm_weights kernel - softmax once per pixel -> weights (B,R,P) - and cm_copy.)
-// Reductions are two-level and fixed-order (deterministic).  History (profiles/):
-// a single-CTA-per-sample reduction kernel cost 14 us (latency chain); recomputing the per-PIXEL
-// softmax in every pass-2 CTA cost ~10 channels' worth of instructions per CTA; a per-sample
-// ticket tail in pass 1 doubled pass 1 (fence + atomic + barrier per CTA); per-group launches and a
-// persistent software-pipelined single launch that re-read c_feats from L2 ("K3p", round 1: parity-green,
-// 1.3-1.4x slower; removed in round 2, design and measurements in profiles/r1_experiments.md) lost to this.
-// The second DRAM read of c_feats is what L2 capacity allows: at B = 8 the features are 84 MB, a streamed
-// buffer keeps ~45-60 MB resident in the 126 MB L2 (tools/l2_probe.py), and pass 2 already walks the samples
-// in reverse to take exactly that tail from L2.
+//                      one byte per pixel (bit 0 target, bit r+1 reference r); re-arms the counters of pass 1+2
+//   pass 1+2 cm_group: the resident grid is split into groups of CTAs, one sample per group at a time;
+//                      a group streams c_feats ONCE from HBM for the R similarities (and copies c_t through),
+//                      hands off among its own CTAs only, folds the per-CTA partials into gs (fixed
+//                      order, double), evaluates the masked softmax once per MASK PATTERN (2^R entries) and
+//                      produces sum_r w_r c_r and c_mask from registers / shared memory / L2 (see the kernel).
+// Kept for comparison and for 8 references (the mask byte holds 7): cm_sim | cm_copy2 (MT_CM_TABLE=1: two
+// passes over c_feats from HBM, 1.64x the algorithmic traffic) and cm_sim | cm_weights | cm_copy (MT_CM_TABLE=0).
+// Reductions are fixed-order (deterministic).  History (profiles/r1_experiments.md, r2_experiments.md):
+// a single-CTA-per-sample reduction kernel cost 14 us (latency chain); a per-sample ticket tail in pass 1
+// doubled pass 1; per-group launches and a persistent software-pipelined single launch with GLOBAL hand-offs
+// ("K3p", round 1, removed) were 1.3-2x slower; the grouped form synchronises per group of CTAs instead.
 #include <math.h>
 
 #include "mt_common.cuh"
@@ -493,6 +486,22 @@ struct CmGroupCfg {
     static constexpr int kBatchBytes = UN * R * 256 * 16;     // reference features of one batch parked in shared memory
 };
 
+#ifdef MT_DEV_PROBES
+// developer timeline probe (probe builds only, tools/dbg_cm_timeline.py): per CTA globaltimer stamps of the first sample
+// [0] entry, [1] pass 1 done (arrived), [2] hand-off passed (all CTAs of the group arrived), [3] table built, [4] pass 2 done
+__device__ unsigned long long g_cm_timeline[1024 * 8];
+__device__ __forceinline__ void cm_stamp(int slot) {
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_cm_timeline[blockIdx.x * 8 + slot] = t;
+    }
+}
+#define MT_CM_STAMP(slot) cm_stamp(slot)
+#else
+#define MT_CM_STAMP(slot)
+#endif
+
 template <int R>
 __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const int keep) {
     constexpr int G2 = 2 * R, TABF = (1 << R) * (R + 1), UN = CmGroupCfg<R>::UN;
@@ -504,6 +513,7 @@ __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const 
     extern __shared__ __align__(16) uint8_t cm_dyn[];
     float4 *park = reinterpret_cast<float4 *>(cm_dyn);  // [keep][UN][R][256]
     pdl_launch();
+    MT_CM_STAMP(0);
     const int tid = threadIdx.x;
     const int g = (int)blockIdx.x % a.G, s = (int)blockIdx.x / a.G;
     if (s >= a.S) return;
@@ -602,6 +612,7 @@ __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const 
             } while (seen < (unsigned int)a.S);
         }
         __syncthreads();
+        if (b == g) MT_CM_STAMP(2);
         constexpr int kSlots = 256 / G2;
         double v = 0.0;
         if (tid < kSlots * G2) {
@@ -681,6 +692,8 @@ __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const 
         }
     };
 
+    // Handing the batches out dynamically inside the group (tickets, per-batch partial rows) narrowed the spread of the
+    // pass-1 finish times from 6.4 to 4 us (one batch is ~4 us) but cost as much per batch: step 61.9 vs 61.5 us.  Not kept.
     // A software-pipelined form (pass 1 of the group's next sample before pass 2 of the current one, two samples per
     // group in flight, G = 4) hid the hand-off but was 5 - 10 % slower in the step (profiles/r2_experiments.md): with
     // half as many items per CTA and sample the batches are short (3 + 3 + 1 items) and every other sample has no parked
@@ -690,8 +703,11 @@ __global__ void __launch_bounds__(256, 2) cm_group_kernel(const CmArgs a, const 
 #pragma unroll 1
     for (int b = g; b < a.B; b += a.G) {
         pass1(b, mwq, np);
+        if (b == g) MT_CM_STAMP(1);
         handoff(b);
+        if (b == g) MT_CM_STAMP(3);
         pass2(b, mwq, np, true);
+        if (b == g) MT_CM_STAMP(4);
         __syncthreads();  // red / tab / park are reused by the next sample of this group
     }
 }
@@ -833,3 +849,10 @@ extern "C" const float *mt_cm_workspace_gs(const void *workspace, int B, int C, 
     return reinterpret_cast<const float *>(reinterpret_cast<const char *>(workspace) +
                                            align256(B * f * P * 4) + align256(B * nparts * 2 * R * 4));
 }
+
+#ifdef MT_DEV_PROBES
+extern "C" __attribute__((visibility("default"))) int mt_debug_cm_timeline(unsigned long long *dst, int n) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(dst, mt::g_cm_timeline, sizeof(unsigned long long) * (n < 8192 ? n : 8192)) == cudaSuccess ? 0 : -2;
+}
+#endif
