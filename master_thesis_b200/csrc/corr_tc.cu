@@ -43,7 +43,7 @@ namespace {
 constexpr int kTile = 256;        // largest output tile: TM rows (one or two UMMA M = 128 halves) x TN <= 256 columns
 constexpr int kBK = 32;
 constexpr int kUmmaK = 8;         // tf32: 32 B of K per instruction
-constexpr bool kPairDefault = false;  // CTA-pair kernel on by default (set after the B200 sweep)
+constexpr bool kPairDefault = true;   // CTA-pair kernel for large batches (see the heuristic in corr4d_tc_launch_ex)
 
 // MN-major, SWIZZLE_128B_BASE32B shared-memory matrix descriptor (sm_100 "version 1").
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -719,8 +719,13 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
     if (P % tn) tn = 64;
     // CTA pairs (cta_group::2): whole-frame tiles on two SMs.  MT_CORR_2CTA = 1 forces, 0 disables; default: when the
     // batch fills the pairs (see profiles/r2_experiments.md)
+    // ncu (profiles/r2_experiments.md): 128 frames 29.8 vs 28.5 us, 256 frames 49.3 vs 51.4 us, 512 frames 84.4 vs 98.6 us
+    // (pairs vs single CTAs); graph-replayed cfg3 step at 256 / 512 frames: +1.2 % / -1.2 %.  The pairs win once every
+    // pair has ~5 whole-frame tiles; at 512 frames they run at 85 % of the HBM roofline (5.6 TB/s), where the op -
+    // bandwidth-bound from cold DRAM at 73 flop/B - cannot go much faster
     int pair = tuning("MT_CORR_2CTA", -1);
-    if (pair < 0) pair = kPairDefault && !tm_given && !tn_given && frames * 4 >= sm_count() ? 1 : 0;
+    if (pair < 0) pair = kPairDefault && !tm_given && !tn_given && frames * 2 >= sm_count() * 5 ? 1 : 0;
+    if (pair && !tn_given) tn = 256;
     if (pair && tn == 64) tn = 128;
     CUtensorMap map_a, map_b;
     {

@@ -305,6 +305,26 @@ def test_corr4d_cta_pairs(mtb, name, tn):
         assert np.array_equal(c == 0.0, o == 0.0)
 
 
+def test_corr4d_large_batch_takes_cta_pairs(mtb):
+    """384 frames (B = 96, F = 4): the default heuristic hands the batch to the CTA-pair kernel (5.2 whole-frame tiles
+    per pair).  Compared with the single-CTA kernel on the whole volume and with the CPU oracle on the first and the
+    last two samples."""
+    from master_thesis_b200 import ops, synth
+    ft, vt, fr, vr = synth.vgg_feats(23, 96, 4)
+    dft, dvt, dfr, dvr = dev(ft), dev(vt), dev(fr), dev(vr)
+    c_pair = host(ops.corr4d(dft, dvt, dfr, dvr))
+    try:
+        _set_tuning("MT_CORR_2CTA", 0)
+        c_one = host(ops.corr4d(dft, dvt, dfr, dvr))
+    finally:
+        _set_tuning("MT_CORR_2CTA", -1)
+    assert np.abs(c_pair - c_one).max() <= 1e-4          # same TF32 products, different accumulation order
+    assert np.array_equal(c_pair == 0.0, c_one == 0.0)
+    for sl in (slice(0, 2), slice(94, 96)):
+        o = oracle.corr4d(ft[sl], vt[sl], fr[sl], vr[sl])
+        assert np.abs(c_pair[sl] - o).max() <= 2e-3 and np.array_equal(c_pair[sl] == 0.0, o == 0.0)
+
+
 # ---------------------------------------------------------------- a8
 @pytest.mark.parametrize("table", [2, 1, 0])
 @pytest.mark.parametrize("name", sorted(cases.CM_CASES))
