@@ -267,6 +267,62 @@ class Cfg4(Workload):
     def sub(self, b):
         return Cfg4(b, self.f, self.h, self.w)
 
+    def loop_stats(self, mtb, dev, n=8, reps=3):
+        """Loop level: the patched CHN.inpaint_ff over an n-frame 480x854 clip with stand-ins for the two
+        CNNs (the DFPN forward hands out a 256x256 flow, the RRDBNet a preset tensor - both outside the hot path), timed
+        with one device->host sync per step (the reference's loop control, model_chn.py:112) and with the loop condition
+        evaluated on the device and the host looking every 8 steps."""
+        import time
+        import numpy as np
+        import torch
+        from master_thesis_b200 import plug, synth
+        h, w = self.h, self.w
+        x, m, _ = synth.frames(77, 1, n, h, w)
+        x, m = torch.from_numpy(x[0]).to(dev), torch.from_numpy(m[0]).to(dev)          # (3, n, H, W), (1, n, H, W)
+        flow = torch.from_numpy(synth.dense_flow(78, 1, 1, 256, 256, 0.03, True)).to(dev)
+        nn_o = torch.from_numpy(synth.nn_output(79, 1, h, w)).to(dev)
+        steps = [0]
+
+        class _DFPN(object):
+            align = plug.dfpn_align
+
+            def __call__(self, *a):
+                return None, None, None, flow
+
+        class _CHN(object):
+            forward = plug.chn_forward
+            inpaint_ff = plug.chn_inpaint_ff
+            model_aligner = _DFPN()
+
+            @staticmethod
+            def get_indexes_ff(t, n_frames, s=1, D=20):
+                return sorted((i for i in range(n_frames) if i != t), key=lambda i: abs(i - t))[:D]
+
+            def nn(self, inp):
+                steps[0] += 1
+                return nn_o
+
+            def __call__(self, *a):
+                return self.forward(*a)
+
+        out = {}
+        for k in (1, 8):
+            chn = _CHN()
+            chn.mt_b200_sync_every = k
+            chn.inpaint_ff(x, m)                      # warm-up
+            torch.cuda.synchronize()
+            steps[0] = 0
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                y = chn.inpaint_ff(x, m)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out["sync_every_%d" % k] = {"target_frames_per_sec": reps * n / dt, "fill_steps_per_target": steps[0] / (reps * n),
+                                        "us_per_fill_step": 1e6 * dt / max(steps[0], 1)}
+        out["note"] = ("patched CHN.inpaint_ff on an %d-frame %dx%d clip, host-driven loop (Python + 2 C-ABI calls per fill step), "
+                       "CNN stand-ins; the kernel-level step above is %s" % (n, h, w, "the two kernels alone"))
+        return out
+
 
 class Cfg3(Workload):
     """DFPN training-step hot path as the patched reference runs it: the masked correlation of the forward
@@ -865,6 +921,8 @@ def run_gpu(args):
                        "allreduce_busbw_gbs": 2.0 * (world - 1) / world * ddp["bytes"] / (ar_ms * 1e-3) / 1e9,
                        "note": "NCCL all-reduce of a gradient-sized fp32 buffer (DFPN 13.92 M / CHN 14.69 M parameters, "
                                "SURVEY section 5) on its own stream inside every timed step, overlapped with the kernels"}
+    if rank == 0 and world == 1 and hasattr(wl, "loop_stats"):
+        line["loop"] = wl.loop_stats(mtb, dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = wl   # the full workload, repeated for about --cpu-seconds of CPU work
         v, mean, reps, cores = cpu_time_workload(sample, args.cpu_seconds)
