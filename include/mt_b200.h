@@ -312,6 +312,21 @@ MT_API int mt_trivial_copy(const float *x_t, int64_t xt_sb, int64_t xt_sc,
                     const float *v_map, int64_t vm_sb, int64_t vm_sf,
                     float *y, int B, int F, int64_t P, mt_stream_t stream);
 
+/* ---- K5  FlowEstimator input pack -------------------------------------------
+ * mt_flow_pack        replaces FlowEstimator.forward model_dfpn.py:733-741   
+ *   x_refs (B,3,F,H,W) strided, x_t (B,3,H,W) strided, m_refs (B,1,F,H,W) strided, m_t (B,1,H,W),
+ *   flow (B,F,H,W,2) with ALL five strides (element units; FlowsUtils.resize_flow hands over a
+ *   permuted view of a (B,F,2,H,W) tensor) -> nn_in (B*F,10,H,W) contiguous NCHW for cuDNN:
+ *   channels [x_refs 0-2, x_t 3-5, m_refs 6, m_t 7, flow x 8, flow y 9].  Planes of x / m must be
+ *   contiguous (stride W, 1).  Pure data movement; the gradient of flow is the view
+ *   g_nn_in[:, 8:10] -> (B,F,H,W,2) (no kernel needed).
+ */
+MT_API int mt_flow_pack(const float *x_refs, int64_t xr_sb, int64_t xr_sc, int64_t xr_sf,
+                 const float *x_t, int64_t xt_sb, int64_t xt_sc,
+                 const float *m_refs, int64_t mr_sb, int64_t mr_sf, const float *m_t, int64_t mt_sb,
+                 const float *flow, int64_t fl_sb, int64_t fl_sf, int64_t fl_sy, int64_t fl_sx, int64_t fl_sc,
+                 float *nn_in, int B, int F, int H, int W, mt_stream_t stream);
+
 /* ---- host-buffer entry points (end-to-end: H2D + kernels + D2H inside) ----
  * The reference-facing calls with HOST memory, used for the e2e metric.
  * All pointers are host pointers (pinned memory recommended); tensors are

@@ -200,14 +200,14 @@ __global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const War
                 for (int c = 0; c < C; ++c) {
                     const float *r0 = a.x + (xo + c * a.x_sc + o);
                     const float *r1 = a.x + (xo + c * a.x_sc + o + W);
-                    c00[c][k] = __ldg(r0); c01[c][k] = __ldg(r0 + 1);
-                    c10[c][k] = __ldg(r1); c11[c][k] = __ldg(r1 + 1);
+                    tap_pair(r0, c00[c][k], c01[c][k]);
+                    tap_pair(r1, c10[c][k], c11[c][k]);
                 }
                 if (VIS == 2) {
                     const float *r0 = vp + o;
                     const float *r1 = vp + (o + W);
-                    c00[C][k] = __ldg(r0); c01[C][k] = __ldg(r0 + 1);
-                    c10[C][k] = __ldg(r1); c11[C][k] = __ldg(r1 + 1);
+                    tap_pair(r0, c00[C][k], c01[C][k]);
+                    tap_pair(r1, c10[C][k], c11[C][k]);
                 } else {
                     // nearest: rint (half-to-even) lands on one of the 4 interior taps: in bounds
                     c00[C][k] = __ldg(vp + ((int)rintf(iy[k]) * W + (int)rintf(ix[k])));
@@ -340,8 +340,8 @@ __device__ __forceinline__ void gather_taps(const float *__restrict__ x, int xo,
             for (int c = 0; c < C; ++c) {
                 const float *r0 = x + (xo + c * x_sc + o);
                 const float *r1 = x + (xo + c * x_sc + o + sp.W);
-                q[c][k].nw = __ldg(r0); q[c][k].ne = __ldg(r0 + 1);
-                q[c][k].sw = __ldg(r1); q[c][k].se = __ldg(r1 + 1);
+                tap_pair(r0, q[c][k].nw, q[c][k].ne);
+                tap_pair(r1, q[c][k].sw, q[c][k].se);
             }
         }
     } else {

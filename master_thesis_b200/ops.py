@@ -740,3 +740,46 @@ def trivial_copy(x_t, x_al, v_map):
     _call("mt_trivial_copy", _ptr(xt), xt.stride(0), xt.stride(1), _ptr(xa), xa_sb, xa_sc, xa_sf,
               _ptr(vm), vm_sb, vm_sf, _ptr(y), b, f, h * w, _stream(xa))
     return y
+
+
+# --------------------------------------------------------------------------
+# K5 FlowEstimator input pack
+# --------------------------------------------------------------------------
+def flow_pack_raw(x_target, m_target, x_refs, m_refs, flow_pre):
+    """model_dfpn.py:733-741 -> nn_input (B*F,10,H,W) NCHW; the flow is read through its own strides."""
+    _need_cuda(x_target, m_target, x_refs, m_refs, flow_pre)
+    b, c, f, h, w = x_refs.shape
+    if c != 3 or tuple(flow_pre.shape) != (b, f, h, w, 2) or tuple(m_refs.shape) != (b, 1, f, h, w):
+        raise ValueError("flow_pack: x_refs (B,3,F,H,W), m_refs (B,1,F,H,W), flow_pre (B,F,H,W,2) expected")
+    xt, mt = _planes(x_target), _planes(m_target)
+    xr, xr_sb, xr_sc, xr_sf = _s5(x_refs)
+    mr, mr_sb, _, mr_sf = _s5(m_refs)
+    out = _empty((b * f, 10, h, w), dtype=torch.float32, device=xr.device)
+    fs = flow_pre.stride()
+    _call("mt_flow_pack", _ptr(xr), xr_sb, xr_sc, xr_sf, _ptr(xt), xt.stride(0), xt.stride(1), _ptr(mr), mr_sb,
+          mr_sf, _ptr(mt), mt.stride(0), _ptr(flow_pre), fs[0], fs[1], fs[2], fs[3], fs[4], _ptr(out), b, f, h, w,
+          _stream(xr))
+    return out
+
+
+class FlowPackFn(torch.autograd.Function):
+    """The pack with the only gradient the reference's `cat` carries in DFPN training: the one of ``flow_pre``
+    (frames and masks are data).  It is a view of the gradient of channels 8-9 - no kernel."""
+
+    @staticmethod
+    def forward(ctx, flow_pre, x_target, m_target, x_refs, m_refs):
+        ctx.meta = x_refs.shape
+        return flow_pack_raw(x_target, m_target, x_refs, m_refs, flow_pre.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        b, _, f, h, w = ctx.meta
+        return g[:, 8:10].reshape(b, f, 2, h, w).permute(0, 1, 3, 4, 2), None, None, None, None
+
+
+def flow_pack(x_target, m_target, x_refs, m_refs, flow_pre):
+    """FlowEstimator.forward's `nn_input` (model_dfpn.py:733-741); differentiable w.r.t. ``flow_pre``."""
+    _no_grad_inputs("flow_pack", x_target, m_target, x_refs, m_refs)
+    if torch.is_grad_enabled() and flow_pre.requires_grad:
+        return FlowPackFn.apply(flow_pre, x_target, m_target, x_refs, m_refs)
+    return flow_pack_raw(x_target, m_target, x_refs, m_refs, flow_pre)

@@ -109,6 +109,16 @@ def dfpn_forward_256(self, x_target, m_target, x_refs, m_refs):
     return self.flow_256(*sq, mt.FlowsUtils.resize_flow(flow_64, (256, 256), mode='bilinear'))       # :93-98
 
 
+def flow_estimator_forward(self, x_target, m_target, x_refs, m_refs, flow_pre):
+    """FlowEstimator.forward (model_dfpn.py:714-744): the 10-channel input of the estimator's conv stack is
+    written by one kernel (``ops.flow_pack``: the reference builds it from two transposes, two repeats, a permute
+    and a `cat`, :733-741); the conv stack (``self.nn``, cuDNN) and the closing reshape / permute (:743-744)
+    are the reference's.  The gradient reaches ``flow_pre`` as it does through the reference's `cat`."""
+    b, _, ref_n, h, w = x_refs.size()
+    nn_input = ops.flow_pack(x_target, m_target, x_refs, m_refs, flow_pre)
+    return self.nn(nn_input).reshape(b, ref_n, 2, h, w).permute(0, 1, 3, 4, 2)
+
+
 def _dfpn_grid(self, x_target, m_target, x_refs, m_refs):
     """The flow of DFPN.align (model_dfpn.py:103-127): the DFPN forward (VGG, 4-D conv, flow
     estimators: cuDNN), untouched.  For frames that are not 256 x 256 a patched DFPN hands out the flow
@@ -413,6 +423,7 @@ _PATCHES = (
     ("model_dfpn", "DFPN", "_train_val_wrapper", dfpn_train_val_wrapper, False),
     ("model_dfpn", "DFPN", "compute_loss", dfpn_compute_loss, False),
     ("model_dfpn", "DFPN", "_mt_b200_flow_256", dfpn_forward_256, False),
+    ("model_dfpn", "FlowEstimator", "forward", flow_estimator_forward, False),
     ("model_cpn", "CPN", "align", cpn_align, False),
     ("model_cpn", "CM_Module", "forward", CM_Module.forward, False),
     ("model_chn", "CHN", "forward", chn_forward, False),

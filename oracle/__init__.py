@@ -233,6 +233,16 @@ def chn_pack(x_t, v_t, x_al, v_al, v_map):
     return out
 
 
+def flow_pack(x_target, m_target, x_refs, m_refs, flow_pre):
+    """8f-4 - FlowEstimator.forward's nn_input, model_dfpn.py:733-741."""
+    x_target, m_target, x_refs, m_refs, flow_pre = _c(x_target), _c(m_target), _c(x_refs), _c(m_refs), _c(flow_pre)
+    b, _, f, h, w = x_refs.shape
+    out = np.empty((b * f, 10, h, w), np.float32)
+    lib().mto_flow_pack(_p(x_refs), _p(x_target), _p(m_refs), _p(m_target), _p(flow_pre), _i(b), _i(f), _l(h * w),
+                        _p(out))
+    return out
+
+
 def chn_composite(nn_out, x_t, v_t, b, f):
     """a10 - model_chn.py:80-85."""
     nn_out, x_t, v_t = _c(nn_out), _c(x_t), _c(v_t)

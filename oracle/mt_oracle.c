@@ -571,6 +571,31 @@ MTO_API void mto_chn_pack(const float *x_t, const float *v_t, const float *x_al,
 }
 
 /* ------------------------------------------------------------------------ */
+/* 8f-4: FlowEstimator.forward input pack  master_thesis/model_dfpn.py:733-741 */
+/* ------------------------------------------------------------------------ */
+/* x_refs (b,3,f,P), x_t (b,3,P), m_refs (b,1,f,P), m_t (b,1,P), flow_pre (b,f,P,2) ->
+   nn_input (b*f, 10, P) = cat[x_refs (:734), x_t repeated over f (:735-736), m_refs (:737),
+   m_t repeated (:738-739), flow_pre as (2, P) planes (:740)] */
+MTO_API void mto_flow_pack(const float *x_refs, const float *x_t, const float *m_refs, const float *m_t,
+                           const float *flow, int b, int f, int64_t P, float *nn_in) {
+    for (int bi = 0; bi < b; ++bi)
+        for (int fi = 0; fi < f; ++fi) {
+            float *o = nn_in + ((int64_t)bi * f + fi) * 10 * P;
+            for (int k = 0; k < 3; ++k)
+                for (int64_t p = 0; p < P; ++p) {
+                    o[(int64_t)k * P + p] = x_refs[(((int64_t)bi * 3 + k) * f + fi) * P + p];
+                    o[(int64_t)(3 + k) * P + p] = x_t[((int64_t)bi * 3 + k) * P + p];
+                }
+            for (int64_t p = 0; p < P; ++p) {
+                o[6 * P + p] = m_refs[((int64_t)bi * f + fi) * P + p];
+                o[7 * P + p] = m_t[(int64_t)bi * P + p];
+                o[8 * P + p] = flow[(((int64_t)bi * f + fi) * P + p) * 2];
+                o[9 * P + p] = flow[(((int64_t)bi * f + fi) * P + p) * 2 + 1];
+            }
+        }
+}
+
+/* ------------------------------------------------------------------------ */
 /* a10: CHN.forward composite                master_thesis/model_chn.py:80-85 */
 /* ------------------------------------------------------------------------ */
 /* nn_out (b*f,3,P) -> y_hat (b,3,f,P) = clamp(nn_out*std + mean, 0, 1)   :83

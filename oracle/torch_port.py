@@ -131,6 +131,18 @@ def chn_pack(x_t, v_t, x_al, v_al, v_map):
     return nn_in.transpose(1, 2).reshape(b * f, 9, h, w)
 
 
+def flow_pack(x_target, m_target, x_refs, m_refs, flow_pre):
+    """model_dfpn.py:733-741 (FlowEstimator.forward's nn_input)."""
+    b, c, f, h, w = x_refs.shape
+    return torch.cat([
+        x_refs.transpose(1, 2).reshape(b * f, c, h, w),
+        x_target.unsqueeze(1).repeat(1, f, 1, 1, 1).reshape(b * f, c, h, w),
+        m_refs.transpose(1, 2).reshape(b * f, 1, h, w),
+        m_target.unsqueeze(1).repeat(1, f, 1, 1, 1).reshape(b * f, 1, h, w),
+        flow_pre.reshape(b * f, h, w, 2).permute(0, 3, 1, 2),
+    ], dim=1)
+
+
 def chn_composite(nn_out, x_t, v_t, b, f):
     """model_chn.py:80-85."""
     _, c, h, w = nn_out.shape

@@ -290,3 +290,41 @@ def corrvgg_inputs(spec):
     ft = np.maximum(r.standard_normal((b, 512, 16, 16)), 0).astype(np.float32)
     fr = np.maximum(r.standard_normal((b * f, 512, 16, 16)), 0).astype(np.float32)
     return x[:, :, 0].copy(), m[:, :, 0].copy(), x[:, :, 1:].copy(), m[:, :, 1:].copy(), ft, fr
+
+
+# 8f-4: FlowEstimator.forward input pack (model_dfpn.py:714-744) ------------------------------------------
+FLOWPACK_CASES = {
+    # layout of flow_pre: "planar" = what FlowsUtils.resize_flow returns (a permuted view of (b,f,2,h,w)),
+    # "interleaved" = contiguous (b,f,h,w,2), "sliced" = a window of a wider interleaved tensor (generic strides)
+    "planar_f4": dict(seed=121, b=2, f=4, h=16, w=24, layout="planar"),
+    "inter_f2": dict(seed=122, b=3, f=2, h=12, w=20, layout="interleaved"),
+    "odd_f1": dict(seed=123, b=1, f=1, h=15, w=21, layout="planar"),
+    "sliced_f3": dict(seed=124, b=2, f=3, h=8, w=12, layout="sliced"),
+}
+
+
+def flowpack_inputs(spec):
+    """x_target (b,3,h,w), m_target (b,1,h,w), x_refs (b,3,f,h,w), m_refs (b,1,f,h,w), flow_pre (b,f,h,w,2) in the
+    case's memory layout (a numpy view; `flowpack_torch_flow` rebuilds the same view on a torch tensor), and the
+    two tensors of the conv-stack stand-in: gain (b*f,2,h,w) and the upstream gradient (b,f,h,w,2)."""
+    b, f, h, w = spec["b"], spec["f"], spec["h"], spec["w"]
+    x, m, _ = synth.frames(spec["seed"], b, f + 1, h, w)
+    r = synth.rng(spec["seed"] + 1)
+    if spec["layout"] == "planar":
+        base = r.standard_normal((b, f, 2, h, w)).astype(np.float32)
+    elif spec["layout"] == "interleaved":
+        base = r.standard_normal((b, f, h, w, 2)).astype(np.float32)
+    else:
+        base = r.standard_normal((b, f, h + 1, w + 3, 2)).astype(np.float32)
+    gain = r.standard_normal((b * f, 2, h, w)).astype(np.float32)
+    up = r.standard_normal((b, f, h, w, 2)).astype(np.float32)
+    return x[:, :, 0].copy(), m[:, :, 0].copy(), x[:, :, 1:].copy(), m[:, :, 1:].copy(), base, gain, up
+
+
+def flowpack_view(base, spec):
+    """The (b,f,h,w,2) view of ``base`` (numpy array or torch tensor) the case hands to FlowEstimator.forward."""
+    if spec["layout"] == "planar":
+        return base.transpose(0, 1, 3, 4, 2) if isinstance(base, np.ndarray) else base.permute(0, 1, 3, 4, 2)
+    if spec["layout"] == "interleaved":
+        return base
+    return base[:, :, 1:, 2:2 + spec["w"]]

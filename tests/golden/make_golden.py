@@ -44,12 +44,37 @@ def save(name, **arrays):
 from cases import WARP_CASES, CPN_CASES, CORR_CASES, CM_CASES, CHN_CASES, LOSS_CASES  # noqa: E402
 from cases import (warp_inputs, cpn_inputs, corr_inputs, cm_inputs, chn_inputs, loss_inputs,  # noqa: E402
                    chnloss_inputs, CHNLOSS_CASES, inpaint_inputs, INPAINT_CASES, l1_broadcast_inputs,
-                   LOWRES_CASES, lowres_inputs, DFPNLOSS_CASES, dfpnloss_inputs, CORRVGG_CASES, corrvgg_inputs)
+                   LOWRES_CASES, lowres_inputs, DFPNLOSS_CASES, dfpnloss_inputs, CORRVGG_CASES, corrvgg_inputs,
+                   FLOWPACK_CASES, flowpack_inputs, flowpack_view)
+
+
+def flowpack_goldens(mt):
+    """8f-4: the unmodified FlowEstimator.forward (model_dfpn.py:714-744) with its conv stack replaced by a stand-in
+    that records the 10-channel input and returns a differentiable function of it (so that the gradient the
+    reference's `cat` sends to flow_pre is pinned as well)."""
+    FlowEstimator = mt.model_dfpn.FlowEstimator
+    for name, spec in FLOWPACK_CASES.items():
+        x_t, m_t, x_r, m_r, base, gain, up = flowpack_inputs(spec)
+        seen = {}
+
+        class FakeEstimator(object):
+            def nn(self, inp):
+                seen['nn_input'] = inp.detach().clone()
+                return inp[:, 0:2] * 0.5 + inp[:, 8:10] * T(gain)
+
+        tb = T(base).clone().requires_grad_(True)
+        out = FlowEstimator.forward(FakeEstimator(), T(x_t), T(m_t), T(x_r), T(m_r), flowpack_view(tb, spec))
+        (out * T(up)).sum().backward()
+        save("flowpack_" + name, nn_input=seen['nn_input'].numpy(), flow_out=out.detach().contiguous().numpy(),
+             g_base=tb.grad.numpy())
 
 
 def main():
     torch.set_num_threads(1)
     mt = import_reference()
+    if "--only-flowpack" in sys.argv:
+        return flowpack_goldens(mt)
+    flowpack_goldens(mt)
     DFPN = mt.model_dfpn.DFPN
     CorrelationVGG = mt.model_dfpn.CorrelationVGG
     CPN = mt.model_cpn.CPN

@@ -120,14 +120,18 @@ def _set_tuning(name, value):
     _lib.call("mt_set_tuning", name.encode(), value)
 
 
-@pytest.mark.parametrize("tile_w", [32, 64])
+@pytest.mark.parametrize("tile", [(32, 32, 0), (64, 32, 0), (64, 16, 80), (64, 16, 112)])
 @pytest.mark.parametrize("name", sorted(STAGED_CASES))
-def test_cpn_align_tail_staged(mtb, name, tile_w):
+def test_cpn_align_tail_staged(mtb, name, tile):
+    """Every tile shape of the staged kernel (tile width x height, box width) against the oracle and the direct kernel."""
     spec = STAGED_CASES[name]
     x, m, m_t, theta = cases.cpn_inputs(spec)
     oxa, ova, ovm = oracle.cpn_align_tail(x, m, m_t, theta=theta)
+    tile_w, tile_h, box_w = tile
     try:
         _set_tuning("MT_WARP_TILE_W", tile_w)
+        _set_tuning("MT_WARP_TILE_H", tile_h)
+        _set_tuning("MT_WARP_BOX_W", box_w or 80)
         _set_tuning("MT_WARP_STAGED", 1)
         xa, va, vm = mtb.cpn_align_tail(dev(x), dev(m), dev(m_t), dev(theta))
         _set_tuning("MT_WARP_STAGED", 0)
@@ -135,6 +139,8 @@ def test_cpn_align_tail_staged(mtb, name, tile_w):
     finally:
         _set_tuning("MT_WARP_STAGED", 1)
         _set_tuning("MT_WARP_TILE_W", DEFAULT_TILE_W)
+        _set_tuning("MT_WARP_TILE_H", 32)
+        _set_tuning("MT_WARP_BOX_W", 80)
     for got, direct, orc in ((xa, xd, oxa), (va, vd, ova), (vm, vmd, ovm)):
         assert np.array_equal(host(got), orc)           # staged kernel == oracle, bit for bit
         assert np.array_equal(host(direct), orc)        # direct-gather kernel == oracle
@@ -1089,3 +1095,56 @@ def test_corr_vgg_forward_mirror(mtb, name, tn):
     o = oracle.corr4d(ft, oracle.vis_nearest(m_t, (16, 16)), feats_r, oracle.vis_nearest(m_r, (16, 16)))
     assert np.abs(c - o).max() <= 2e-3 and np.array_equal(c == 0.0, o == 0.0)
     assert int((c.reshape(b, f, 256, 256) == 0).all(-1).sum()) == int(g["zero_rows"][0])
+
+
+# ---------------------------------------------------------------- 8f-4 FlowEstimator input pack
+@pytest.mark.parametrize("name", sorted(cases.FLOWPACK_CASES))
+def test_flow_estimator_input_pack(mtb, name):
+    """mt_flow_pack and the patched FlowEstimator.forward against the unmodified reference method
+    (model_dfpn.py:714-744): CNN input, output and the gradient that reaches flow_pre, bit for bit, for every
+    memory layout of flow_pre (vector paths: planar / interleaved; scalar path: odd sizes, sliced window)."""
+    from master_thesis_b200 import ops, plug
+    spec = cases.FLOWPACK_CASES[name]
+    x_t, m_t, x_r, m_r, base, gain, up = cases.flowpack_inputs(spec)
+    g = load_golden("flowpack_" + name)
+    tb = dev(base).requires_grad_(True)
+    flow = cases.flowpack_view(tb, spec)
+    want = oracle.flow_pack(x_t, m_t, x_r, m_r, cases.flowpack_view(base, spec))
+    with torch.no_grad():
+        got = ops.flow_pack(dev(x_t), dev(m_t), dev(x_r), dev(m_r), flow)
+    assert np.array_equal(host(got), want) and np.array_equal(host(got), g["nn_input"])
+    # strided frame views (x[:, :, r_list] / x[:, :, t] of one clip tensor, as DFPN.align receives them)
+    clip = dev(np.concatenate([x_t[:, :, None], x_r], axis=2))
+    mclip = dev(np.concatenate([m_t[:, :, None], m_r], axis=2))
+    with torch.no_grad():
+        got2 = ops.flow_pack(clip[:, :, 0], mclip[:, :, 0], clip[:, :, 1:], mclip[:, :, 1:], flow)
+    assert torch.equal(got2, got)
+    seen = {}
+
+    class Estimator(object):
+        def nn(self, inp):
+            seen["nn_input"] = inp.detach().clone()
+            return inp[:, 0:2] * 0.5 + inp[:, 8:10] * dev(gain)
+
+    out = plug.flow_estimator_forward(Estimator(), dev(x_t), dev(m_t), dev(x_r), dev(m_r), flow)
+    assert tuple(out.shape) == tuple(up.shape)
+    (out * dev(up)).sum().backward()
+    assert np.array_equal(host(seen["nn_input"]), g["nn_input"])
+    assert np.array_equal(host(out), g["flow_out"])
+    assert np.array_equal(host(tb.grad), g["g_base"])
+
+
+def test_flow_estimator_input_pack_full_size(mtb):
+    """cfg3's 256 x 256 estimator input (32 frames here) against the oracle; the guard band past the output and
+    the inputs stay untouched."""
+    from master_thesis_b200 import ops, synth
+    b, f, h, w = 8, 4, 256, 256
+    x, m, _ = synth.frames(77, b, f + 1, h, w)
+    flow = synth.dense_flow(78, b, f, h, w, 0.05, True)
+    t = f // 2
+    r_list = [i for i in range(f + 1) if i != t]
+    xd, md = dev(x), dev(m)
+    got = ops.flow_pack(xd[:, :, t], md[:, :, t], xd[:, :, r_list], md[:, :, r_list], dev(flow))
+    want = oracle.flow_pack(x[:, :, t], m[:, :, t], x[:, :, r_list], m[:, :, r_list], flow)
+    assert np.array_equal(host(got), want)
+    assert torch.equal(xd, dev(x)) and torch.equal(md, dev(m))

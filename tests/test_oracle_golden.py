@@ -253,3 +253,19 @@ def test_corr_vgg_forward_neighbours(name):
     c = oracle.corr4d(ft, oracle.vis_nearest(m_t, (16, 16)), feats_r, oracle.vis_nearest(m_r, (16, 16)))
     cases.corr_check(c, g, spec, 2e-6)
     assert int((c.reshape(b, f, 256, 256) == 0).all(-1).sum()) == int(g["zero_rows"][0])
+
+
+@pytest.mark.parametrize("name", sorted(cases.FLOWPACK_CASES))
+def test_flow_estimator_input_pack(name):
+    """8f-4: FlowEstimator.forward's 10-channel `cat` (model_dfpn.py:733-741), C oracle and torch port, every
+    flow layout the reference hands over (resize_flow's permuted view, contiguous, a strided window)."""
+    import torch
+    from oracle import torch_port as tp
+    spec = cases.FLOWPACK_CASES[name]
+    x_t, m_t, x_r, m_r, base, gain, up = cases.flowpack_inputs(spec)
+    g = load_golden("flowpack_" + name)
+    flow = cases.flowpack_view(base, spec)
+    assert np.array_equal(oracle.flow_pack(x_t, m_t, x_r, m_r, flow), g["nn_input"])
+    T = torch.from_numpy
+    got = tp.flow_pack(T(x_t), T(m_t), T(x_r), T(m_r), cases.flowpack_view(T(base), spec))
+    assert np.array_equal(got.numpy(), g["nn_input"])
