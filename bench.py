@@ -337,7 +337,7 @@ class Cfg3(Workload):
         self.b, self.f, self.h, self.w = b, f, h, w
         self.frames_per_step = b * f
         self.describe = ("cfg3: DFPN training hot path through the patched DFPN.compute_loss (2x "
-                         "correlation_masked_4d 512x16x16, 3 flow-L1 fwd/bwd, fused warp+mask_out+masked-L1 fwd/bwd "
+                         "correlation_masked_4d 512x16x16 - the second with F.l1_loss(corr, corr_y) in its epilogue, fwd/bwd -, 3 flow-L1 fwd/bwd, fused warp+mask_out+masked-L1 fwd/bwd "
                          "at %dx%d and %dx%d), batch_size=%d frames_n=%d per GPU" % (h, w, h // 4, w // 4, b, f + 1))
 
     def host_inputs(self, seed):
@@ -412,6 +412,12 @@ class Cfg3(Workload):
                 n = a["B"] * a["F"]
                 masks = (n + a["B"]) * 1024 if a["v_t"] else 0
                 out.append((name, 1, n * (524288 + 262144) + a["B"] * 524288 + masks, "tensor", n * CORR_FLOP))
+            elif name == "mt_corr4d_vgg_l1_fwd":
+                # features once, the prediction read (4 B) and the signs written (1 B) per volume element; no volume
+                n, pp = a["B"] * a["F"], (a["h"] * a["w"]) ** 2
+                out.append((name, 2, n * 524288 + a["B"] * 524288 + n * pp * 5, "tensor", n * CORR_FLOP))
+            elif name == "mt_corr4d_l1_bwd":
+                out.append((name, 1, a["n"] * 5, "hbm"))             # signs read, gradient written
             elif name in ("mt_warp_l1_fwd", "mt_warp_l1_bwd"):
                 n, px = a["B"] * a["F"], a["H"] * a["W"]
                 # loss-only fused forward: x_ref 12 + flow 8 per frame, target 12 + v 4 per sample; backward + 8 written

@@ -260,6 +260,22 @@ MT_API int mt_corr4d_vgg_fwd(const float *feats_t, int64_t ft_sb, int64_t ft_sc,
                       const float *m_refs, int64_t mr_sb, int64_t mr_sf, int MH, int MW,
                       float *out, int B, int C, int F, int h, int w, mt_stream_t stream);
 
+/* mt_corr4d_vgg_l1_fwd: the correlation above with F.l1_loss(corr, corr_y) (model_dfpn.py:254-257)
+ * folded into its epilogue: the volume of the ground-truth features is never written.  pred (B,F,P,P)
+ * contiguous = the network's filled volume `corr`; loss[0] (device) = mean |pred - corr_y|; sign (B*F*P*P int8,
+ * may be NULL when no gradient is needed) = sign(pred - corr_y), which is all the backward pass reads.
+ * workspace: mt_corr4d_l1_workspace_bytes() bytes.  Tensor-core shapes only.  Launches the volume kernel and a
+ * one-CTA fold of its partial sums (fixed order: deterministic for a given shape).
+ * mt_corr4d_l1_bwd: g_pred[i] = sign[i] * grad_loss[0] / n   (n = B*F*P*P, a multiple of 16). */
+MT_API int mt_corr4d_vgg_l1_fwd(const float *feats_t, int64_t ft_sb, int64_t ft_sc,
+                         const float *m_target, int64_t mt_sb,
+                         const float *feats_r, int64_t fr_sb, int64_t fr_sc, int64_t fr_sf,
+                         const float *m_refs, int64_t mr_sb, int64_t mr_sf, int MH, int MW,
+                         const float *pred, float *loss, void *sign, void *workspace, int64_t workspace_bytes,
+                         int B, int C, int F, int h, int w, mt_stream_t stream);
+MT_API int64_t mt_corr4d_l1_workspace_bytes(void);
+MT_API int mt_corr4d_l1_bwd(const void *sign, const float *grad_loss, float *g_pred, int64_t n, mt_stream_t stream);
+
 /* ---- K3  CPN context matching --------------------------------------------
  * replaces CM_Module.forward + masked_softmax   model_cpn.py:206-254    (a8)
  * c_feats (B,C,f,h,w) contiguous (index 0 of f = target), v_t (B,1,H,W),

@@ -18,6 +18,13 @@
 
 namespace mt {
 
+// L1 mode of the tensor-core launcher (corr_tc.cu): prediction, loss scalar, optional int8 signs, partial sums
+struct CorrL1 {
+    const float *pred;
+    float *loss;
+    signed char *sign;
+    float *partials;
+};
 int corr4d_tc_supported(int C, int P);
 int corr4d_tc_launch(const float *ft, const float *vt, const float *fr, const float *vr, float *out,
                      void *ws, int64_t ws_bytes, int B, int C, int F, int P, cudaStream_t st);
@@ -25,7 +32,9 @@ int64_t corr4d_tc_workspace_bytes(int B, int C, int F, int P);
 int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const float *fr, int64_t fr_sb, int64_t fr_sc,
                         int64_t fr_sf, const float *vt, int64_t vt_sb, const float *vr, int64_t vr_sb, int64_t vr_sf,
                         int mask_mode, int MH, int MW, int fh, int fw, float *out, int B, int C, int F, int P,
-                        cudaStream_t st);
+                        cudaStream_t st, const CorrL1 *l1);
+int64_t corr4d_l1_workspace_bytes();
+int corr4d_l1_bwd_launch(const signed char *sign, const float *grad_loss, float *g_pred, int64_t n, cudaStream_t st);
 
 namespace {
 
@@ -157,5 +166,30 @@ extern "C" int mt_corr4d_vgg_fwd(const float *feats_t, int64_t ft_sb, int64_t ft
                "mt_corr4d_vgg_fwd: only shapes served by the tensor-core kernel (h*w %% 256 == 0, C %% 32 == 0); use "
                "mt_corr4d_fwd on contiguous, pre-masked inputs otherwise");
     return corr4d_tc_launch_ex(feats_t, ft_sb, ft_sc, feats_r, fr_sb, fr_sc, fr_sf, m_target, mt_sb, m_refs, mr_sb,
-                               mr_sf, m_target ? 1 : 0, MH, MW, h, w, out, B, C, F, h * w, (cudaStream_t)stream);
+                               mr_sf, m_target ? 1 : 0, MH, MW, h, w, out, B, C, F, h * w, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int64_t mt_corr4d_l1_workspace_bytes(void) { return corr4d_l1_workspace_bytes(); }
+
+extern "C" int mt_corr4d_vgg_l1_fwd(const float *feats_t, int64_t ft_sb, int64_t ft_sc, const float *m_target,
+                                    int64_t mt_sb, const float *feats_r, int64_t fr_sb, int64_t fr_sc, int64_t fr_sf,
+                                    const float *m_refs, int64_t mr_sb, int64_t mr_sf, int MH, int MW,
+                                    const float *pred, float *loss, void *sign, void *workspace,
+                                    int64_t workspace_bytes, int B, int C, int F, int h, int w, mt_stream_t stream) {
+    MT_REQUIRE(feats_t && feats_r && pred && loss && workspace, "mt_corr4d_vgg_l1_fwd: NULL argument");
+    MT_REQUIRE(B > 0 && C > 0 && F > 0 && h > 0 && w > 0, "mt_corr4d_vgg_l1_fwd: empty shape");
+    MT_REQUIRE((m_target == nullptr) == (m_refs == nullptr), "mt_corr4d_vgg_l1_fwd: both masks or none");
+    MT_REQUIRE(!m_target || (MH > 0 && MW > 0 && mt_sb >= 0 && mr_sb >= 0 && mr_sf >= 0), "mt_corr4d_vgg_l1_fwd: bad mask shape");
+    MT_REQUIRE((int64_t)B * F <= 65535, "mt_corr4d_vgg_l1_fwd: B*F > 65535");
+    MT_REQUIRE(workspace_bytes >= corr4d_l1_workspace_bytes(), "mt_corr4d_vgg_l1_fwd: workspace too small");
+    MT_REQUIRE(corr4d_tc_supported(C, h * w),
+               "mt_corr4d_vgg_l1_fwd: only shapes served by the tensor-core kernel (h*w %% 256 == 0, C %% 32 == 0)");
+    CorrL1 l1{pred, loss, reinterpret_cast<signed char *>(sign), reinterpret_cast<float *>(workspace)};
+    return corr4d_tc_launch_ex(feats_t, ft_sb, ft_sc, feats_r, fr_sb, fr_sc, fr_sf, m_target, mt_sb, m_refs, mr_sb,
+                               mr_sf, m_target ? 1 : 0, MH, MW, h, w, nullptr, B, C, F, h * w, (cudaStream_t)stream, &l1);
+}
+
+extern "C" int mt_corr4d_l1_bwd(const void *sign, const float *grad_loss, float *g_pred, int64_t n, mt_stream_t stream) {
+    MT_REQUIRE(sign && grad_loss && g_pred, "mt_corr4d_l1_bwd: NULL argument");
+    return corr4d_l1_bwd_launch(reinterpret_cast<const signed char *>(sign), grad_loss, g_pred, n, (cudaStream_t)stream);
 }

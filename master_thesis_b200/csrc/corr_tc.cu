@@ -38,6 +38,15 @@
 #include "mt_tma.cuh"
 
 namespace mt {
+
+// L1 mode of the launchers (see CorrTcArgs): prediction to compare with, loss scalar, optional int8 signs, partial sums
+struct CorrL1 {
+    const float *pred;
+    float *loss;
+    signed char *sign;
+    float *partials;
+};
+
 namespace {
 
 constexpr int kTile = 256;        // largest output tile: TM rows (one or two UMMA M = 128 halves) x TN <= 256 columns
@@ -100,7 +109,13 @@ struct CorrTcArgs {
     const float *vr; int64_t vr_sb, vr_sf;         // (B, F, P) | (B, F, MH, MW)
     int mask_mode, MH, MW, fw;
     float msy, msx;                                // MH / fh, MW / fw in fp32 (ATen nearest: floor(dst * scale))
-    float *out;                                    // (B, F, P, P)
+    float *out;                                    // (B, F, P, P); unused in L1 mode
+    // L1 mode (pred != NULL): the volume is not written; the epilogue compares it with `pred` (B, F, P, P) instead and
+    // accumulates sum |pred - corr| (F.l1_loss(corr, corr_y), model_dfpn.py:254-257).  sign (optional):
+    // sign(pred - corr) as int8, all the backward pass needs.  partials: one float per (CTA, epilogue warp).
+    const float *pred;
+    signed char *sign;
+    float *partials;
     int C, F, P, tiles_m, tiles_n, n_tiles;
 };
 
@@ -114,10 +129,82 @@ __device__ __forceinline__ float corr_vis(const float *base, int p, const CorrTc
     return __fsub_rn(1.0f, __ldg(base + (int64_t)ys * a.MW + xs));
 }
 
+constexpr int kEpiPitch = 36;     // floats per staged row: 144 B keeps float4 alignment, conflict-free both ways
+
+__device__ __forceinline__ signed char sign_i8(float d) { return d > 0.0f ? 1 : (d < 0.0f ? -1 : 0); }
+
+// Epilogue of one 32-row x TN-column block of a tile (one warp = one TMEM lane quarter): tcgen05.ld 32 lanes x 32
+// columns -> * sa[row] * sb[col] -> transposed through the warp's private staging tile `st` -> 128 B-per-row
+// coalesced streaming stores of the volume, or (L1) the same rows of `pred` loaded instead (requested before the
+// TMEM read so that their latency hides under it) and |pred - corr| accumulated into `acc`.
+// `off0`: element offset of (first row of the block, first column of the tile) in the (B, F, P, P) volume.
+template <int TN, bool L1>
+__device__ __forceinline__ void corr_epi_block(const CorrTcArgs &a, uint32_t taddr, float sa, const float *sbv, float *st,
+                                               int64_t off0, int lane, float &acc) {
+    const int rr = lane >> 3, c4 = (lane & 7) * 4;  // read-back: 4 rows x 8 float4 per instruction
+#pragma unroll 1
+    for (int c0 = 0; c0 < TN; c0 += 32) {
+        // pred rows: the first half is requested before the TMEM read, the second once the accumulator registers
+        // are free again (the lines were brought into L2 while the main loop ran, see corr_epi_prefetch)
+        float4 p[2][4];
+        if (L1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                p[0][j] = __ldcs(reinterpret_cast<const float4 *>(a.pred + off0 + (int64_t)(j * 4 + rr) * a.P + c0 + c4));
+        }
+        {
+            float v[32];
+            tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                float4 o;
+                o.x = v[i] * sa * sbv[c0 + i];
+                o.y = v[i + 1] * sa * sbv[c0 + i + 1];
+                o.z = v[i + 2] * sa * sbv[c0 + i + 2];
+                o.w = v[i + 3] * sa * sbv[c0 + i + 3];
+                *reinterpret_cast<float4 *>(st + lane * kEpiPitch + i) = o;  // row = lane
+            }
+        }
+        if (L1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                p[1][j] = __ldcs(reinterpret_cast<const float4 *>(a.pred + off0 + (int64_t)((4 + j) * 4 + rr) * a.P + c0 + c4));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int row = j * 4 + rr;
+            const float4 o = *reinterpret_cast<const float4 *>(st + row * kEpiPitch + c4);
+            const int64_t off = off0 + (int64_t)row * a.P + c0 + c4;
+            if (L1) {
+                const float4 pj = p[j >> 2][j & 3];
+                const float dx = pj.x - o.x, dy = pj.y - o.y, dz = pj.z - o.z, dw = pj.w - o.w;
+                acc += (fabsf(dx) + fabsf(dy)) + (fabsf(dz) + fabsf(dw));
+                if (a.sign) {
+                    char4 sg;
+                    sg.x = sign_i8(dx); sg.y = sign_i8(dy); sg.z = sign_i8(dz); sg.w = sign_i8(dw);
+                    *reinterpret_cast<char4 *>(a.sign + off) = sg;
+                }
+            } else {
+                __stcs(reinterpret_cast<float4 *>(a.out + off), o);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// L1 mode: lane = row of a 32-row block; asks the L2 for the TN columns of that row of `pred`.  Issued by the epilogue
+// warps before they wait for the accumulators, so the lines arrive while the main loop of the tile runs.
+template <int TN>
+__device__ __forceinline__ void corr_epi_prefetch(const CorrTcArgs &a, int64_t off0, int lane) {
+    const float *row = a.pred + off0 + (int64_t)lane * a.P;
+#pragma unroll
+    for (int c = 0; c < TN; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + c));
+}
+
 constexpr int kNormWarps = 8;     // one thread per row of the A tile / column of the B tile
 constexpr int kEpiWarps = 4;      // one per TMEM lane quarter
 constexpr int kThreadsP = (2 + kNormWarps + kEpiWarps) * 32;
-constexpr int kEpiPitch = 36;     // floats per staged row: 144 B keeps float4 alignment, conflict-free both ways
 constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch * 4;
 
 template <int TM, int TN, int STAGES>
@@ -319,13 +406,18 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // TMEM lane-quarter rule: warp w may touch lanes 32*(w%4)..32*(w%4)+31; warps 10..13 cover all four
         const int lq = warp & 3, ew = warp - (2 + kNormWarps);
         float *st = epi + ew * 32 * kEpiPitch;
-        const int rr = lane >> 3, c4 = (lane & 7) * 4;  // read-back: 4 rows x 8 float4 per instruction
+        float l1_acc = 0.0f;
         int ti = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++ti) {
             const int frame = tile / tiles_per_frame, r0 = tile - frame * tiles_per_frame;
             const int m_tile = r0 / a.tiles_n, n_tile = r0 - m_tile * a.tiles_n;
             const int buf = ti % kBufs;
             const uint32_t use = (uint32_t)(ti / kBufs);
+            if (a.pred) {
+#pragma unroll
+                for (int h = 0; h < kHalves; ++h)
+                    corr_epi_prefetch<TN>(a, ((int64_t)frame * a.P + m_tile * TM + h * 128 + lq * 32) * a.P + n_tile * TN, lane);
+            }
             mbar_wait(smem_u32(scales_ready + buf), use & 1);
             mbar_wait(smem_u32(tmem_full + buf), use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -334,33 +426,18 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int h = 0; h < kHalves; ++h) {
                 const int row0 = h * 128 + lq * 32;  // first row of this warp's 32-row block
                 const float sa = s_sa[buf * kTile + row0 + lane];
-                float *oblk = a.out + (((int64_t)frame * a.P + m_tile * TM + row0) * a.P + n_tile * TN);
-#pragma unroll 1
-                for (int c0 = 0; c0 < TN; c0 += 32) {
-                    float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * kBufCols + h * TN + c0), v);
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        float4 o;
-                        o.x = v[i] * sa * sbv[c0 + i];
-                        o.y = v[i + 1] * sa * sbv[c0 + i + 1];
-                        o.z = v[i + 2] * sa * sbv[c0 + i + 2];
-                        o.w = v[i + 3] * sa * sbv[c0 + i + 3];
-                        *reinterpret_cast<float4 *>(st + lane * kEpiPitch + i) = o;  // row = lane
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int row = j * 4 + rr;
-                        const float4 o = *reinterpret_cast<const float4 *>(st + row * kEpiPitch + c4);
-                        __stcs(reinterpret_cast<float4 *>(oblk + (int64_t)row * a.P + c0 + c4), o);
-                    }
-                    __syncwarp();
-                }
+                const int64_t off0 = ((int64_t)frame * a.P + m_tile * TM + row0) * a.P + n_tile * TN;
+                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * kBufCols + h * TN);
+                if (a.pred) corr_epi_block<TN, true>(a, taddr, sa, sbv, st, off0, lane, l1_acc);
+                else corr_epi_block<TN, false>(a, taddr, sa, sbv, st, off0, lane, l1_acc);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(tmem_empty + buf));
+        }
+        if (a.pred) {  // one partial per (CTA, epilogue warp); summed in a fixed order by corr_l1_finish_kernel
+            l1_acc = warp_sum(l1_acc);
+            if (lane == 0) a.partials[blockIdx.x * kEpiWarps + ew] = l1_acc;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -619,48 +696,34 @@ corr_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ===== epilogue warps: this CTA's 128 rows x TN columns =====
         const int lq = warp & 3, ew = warp - (2 + kNormWarps);
         float *st = epi + ew * 32 * kEpiPitch;
-        const int rr = lane >> 3, c4 = (lane & 7) * 4;
+        float l1_acc = 0.0f;
         int ti = 0;
         for (int tile = pair; tile < a.n_tiles; tile += npairs, ++ti) {
             const int frame = tile / tiles_per_frame, r0 = tile - frame * tiles_per_frame;
             const int m_tile = r0 / a.tiles_n, n_tile = r0 - m_tile * a.tiles_n;
             const int buf = ti % kBufs;
             const uint32_t use = (uint32_t)(ti / kBufs);
+            const int row0 = lq * 32;
+            const int64_t off0 = ((int64_t)frame * a.P + m_tile * kTile + (int)rank * 128 + row0) * a.P + n_tile * TN;
+            if (a.pred) corr_epi_prefetch<TN>(a, off0, lane);
             mbar_wait_cluster(smem_u32(scales_ready + buf), use & 1);
             mbar_wait(smem_u32(tmem_full + buf), use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const float *sbv = s_sb + buf * kTile;
-            const int row0 = lq * 32;
             const float sa = s_sa[buf * 128 + row0 + lane];
-            float *oblk = a.out + (((int64_t)frame * a.P + m_tile * kTile + (int)rank * 128 + row0) * a.P + n_tile * TN);
-#pragma unroll 1
-            for (int c0 = 0; c0 < TN; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TN + c0), v);
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    float4 o;
-                    o.x = v[i] * sa * sbv[c0 + i];
-                    o.y = v[i + 1] * sa * sbv[c0 + i + 1];
-                    o.z = v[i + 2] * sa * sbv[c0 + i + 2];
-                    o.w = v[i + 3] * sa * sbv[c0 + i + 3];
-                    *reinterpret_cast<float4 *>(st + lane * kEpiPitch + i) = o;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int row = j * 4 + rr;
-                    const float4 o = *reinterpret_cast<const float4 *>(st + row * kEpiPitch + c4);
-                    __stcs(reinterpret_cast<float4 *>(oblk + (int64_t)row * a.P + c0 + c4), o);
-                }
-                __syncwarp();
-            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TN);
+            if (a.pred) corr_epi_block<TN, true>(a, taddr, sa, sbv, st, off0, lane, l1_acc);
+            else corr_epi_block<TN, false>(a, taddr, sa, sbv, st, off0, lane, l1_acc);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(smem_u32(tmem_empty + buf));
                 mbar_arrive_remote(mapa_u32(smem_u32(tmem_empty + buf), other));
             }
+        }
+        if (a.pred) {
+            l1_acc = warp_sum(l1_acc);
+            if (lane == 0) a.partials[blockIdx.x * kEpiWarps + ew] = l1_acc;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -670,7 +733,55 @@ corr_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
+// L1 mode, last step: the per-(CTA, epilogue warp) partial sums in a fixed order (double) -> mean
+__global__ void __launch_bounds__(256) corr_l1_finish_kernel(const float *__restrict__ partials, int n, double inv_count,
+                                                             float *__restrict__ loss) {
+    pdl_sync();
+    __shared__ double s[256];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) t += (double)partials[i];
+    s[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = (float)(s[0] * inv_count);
+}
+
+// backward of mean |pred - corr| w.r.t. pred: sign * grad / count; 16 elements per thread
+__global__ void __launch_bounds__(256) corr_l1_bwd_kernel(const signed char *__restrict__ sign,
+                                                          const float *__restrict__ grad_loss, float inv_count,
+                                                          float *__restrict__ g_pred, int64_t n16) {
+    pdl_sync();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    const float g = __fmul_rn(__ldg(grad_loss), inv_count);
+    const int4 w = __ldcs(reinterpret_cast<const int4 *>(sign) + i);
+    const int ws[4] = {w.x, w.y, w.z, w.w};
+    float4 *o = reinterpret_cast<float4 *>(g_pred) + i * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float4 r;
+        r.x = (float)(signed char)(ws[k] & 0xff) * g;
+        r.y = (float)(signed char)((ws[k] >> 8) & 0xff) * g;
+        r.z = (float)(signed char)((ws[k] >> 16) & 0xff) * g;
+        r.w = (float)(signed char)((ws[k] >> 24) & 0xff) * g;
+        __stcs(o + k, r);
+    }
+}
+
 }  // namespace
+
+int64_t corr4d_l1_workspace_bytes() { return 2 * 148 * kEpiWarps * 4 * 2; }  // partials of up to 296 CTAs, with slack
+
+int corr4d_l1_bwd_launch(const signed char *sign, const float *grad_loss, float *g_pred, int64_t n, cudaStream_t st) {
+    MT_REQUIRE(n > 0 && n % 16 == 0 && aligned16(sign) && aligned16(g_pred), "mt_corr4d_l1_bwd: n must be a multiple of 16, pointers 16 B aligned");
+    const int64_t n16 = n / 16;
+    launch(corr_l1_bwd_kernel, dim3((unsigned)((n16 + 255) / 256)), dim3(256), 0, st, sign, grad_loss,
+           (float)(1.0 / (double)n), g_pred, n16);
+    return launch_status("mt_corr4d_l1_bwd");
+}
 
 int corr4d_tc_supported(int C, int P) {
     if (tuning("MT_CORR_SIMT", 0)) return 0;
@@ -687,8 +798,10 @@ int64_t corr4d_tc_workspace_bytes(int B, int C, int F, int P) {
 int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const float *fr, int64_t fr_sb, int64_t fr_sc,
                         int64_t fr_sf, const float *vt, int64_t vt_sb, const float *vr, int64_t vr_sb, int64_t vr_sf,
                         int mask_mode, int MH, int MW, int fh, int fw, float *out, int B, int C, int F, int P,
-                        cudaStream_t st) {
-    MT_REQUIRE(aligned16(ft) && aligned16(fr) && aligned16(out), "mt_corr4d_fwd: pointers must be 16 B aligned");
+                        cudaStream_t st, const CorrL1 *l1) {
+    MT_REQUIRE(aligned16(ft) && aligned16(fr) && (l1 || aligned16(out)), "mt_corr4d_fwd: pointers must be 16 B aligned");
+    MT_REQUIRE(!l1 || (l1->pred && l1->loss && l1->partials && aligned16(l1->pred) && aligned16(l1->sign)),
+               "mt_corr4d_vgg_l1_fwd: pred, loss and workspace are required, pred / sign 16 B aligned");
     MT_REQUIRE(!((ft_sb | ft_sc | fr_sb | fr_sc | fr_sf) & 3) && ft_sc > 0 && fr_sc > 0 && (B == 1 || (ft_sb > 0 && fr_sb > 0)) &&
                (F == 1 || fr_sf > 0) && ft_sb >= 0 && fr_sb >= 0 && fr_sf >= 0,
                "mt_corr4d_fwd: feature strides must be positive multiples of 4 elements");
@@ -763,6 +876,13 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
     a.msy = mask_mode ? (float)MH / (float)fh : 1.0f;
     a.msx = mask_mode ? (float)MW / (float)fw : 1.0f;
     a.out = out; a.C = C; a.F = F; a.P = P;
+    a.pred = l1 ? l1->pred : nullptr; a.sign = l1 ? l1->sign : nullptr; a.partials = l1 ? l1->partials : nullptr;
+    // L1 mode: after the volume kernel, the partial sums of its n_parts (CTA, epilogue warp) pairs are folded
+    auto finish = [&](int n_parts) {
+        if (!l1) return;
+        launch(corr_l1_finish_kernel, dim3(1), dim3(256), 0, st, (const float *)l1->partials, n_parts,
+               1.0 / ((double)B * F * P * P), l1->loss);
+    };
     a.tiles_m = P / (pair ? kTile : tm); a.tiles_n = P / tn;
     const int64_t n_tiles = (int64_t)B * F * a.tiles_m * a.tiles_n;
     MT_REQUIRE(n_tiles < (1ll << 30), "mt_corr4d_fwd: too many tiles");
@@ -795,6 +915,7 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
         if (tn == 256) MT_CORR_PAIR_GO(256, 6);  // 6 x 32 KB per CTA
         else MT_CORR_PAIR_GO(128, 8);            // 8 x 24 KB per CTA
 #undef MT_CORR_PAIR_GO
+        finish(2 * npairs * kEpiWarps);
         return launch_status("mt_corr4d_fwd");
     }
     int ctas = sm_count();
@@ -821,6 +942,7 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
         else MT_CORR_GO(128, 64, 8);                  // 8 x 24 KB
     }
 #undef MT_CORR_GO
+    finish(ctas * kEpiWarps);
     return launch_status("mt_corr4d_fwd");
 }
 
@@ -828,7 +950,7 @@ int corr4d_tc_launch(const float *ft, const float *vt, const float *fr, const fl
                      int64_t ws_bytes, int B, int C, int F, int P, cudaStream_t st) {
     (void)ws; (void)ws_bytes;
     return corr4d_tc_launch_ex(ft, (int64_t)C * P, P, fr, (int64_t)C * F * P, (int64_t)F * P, P, vt, P, vr,
-                               (int64_t)F * P, P, 0, 0, 0, 0, 0, out, B, C, F, P, st);
+                               (int64_t)F * P, P, 0, 0, 0, 0, 0, out, B, C, F, P, st, nullptr);
 }
 
 }  // namespace mt

@@ -26,7 +26,14 @@ namespace mt {
 namespace {
 
 constexpr int kCols = 128;     // forward kernel: threads per CTA = columns per CTA
-constexpr int kRows = 2;       // forward kernel: rows per thread and iteration (swept on B200: 2 beats 4)
+#ifndef MT_WARP_ROWS
+#define MT_WARP_ROWS 2
+#endif
+#ifndef MT_TAP_REUSE
+#define MT_TAP_REUSE 1
+#endif
+constexpr int kRows = MT_WARP_ROWS;  // forward kernel: rows per thread and iteration (swept on B200: 2 beats 4)
+constexpr bool kTapReuse = MT_TAP_REUSE != 0;  // vertically adjacent pixels of a thread share a source row of taps
 constexpr int kIters = 1;      // forward kernel: row groups per thread (swept: more groups per thread is slower)
 // Minimum resident CTAs per SM given to ptxas.  This is a SCHEDULING knob, not an occupancy one:
 // with a bare __launch_bounds__(128) ptxas minimises registers (32-40) and does so by sinking the
@@ -35,6 +42,9 @@ constexpr int kIters = 1;      // forward kernel: row groups per thread (swept: 
 // budget stated, all gathers of a thread are issued before the first use.
 #ifndef MT_WARP_MINB
 #define MT_WARP_MINB 6
+#endif
+#ifndef MT_WARP_MINB4
+#define MT_WARP_MINB4 4  // 4 rows per thread: 40 taps in flight need the registers
 #endif
 #ifndef MT_WARPB_MINB
 #define MT_WARPB_MINB 6
@@ -80,7 +90,7 @@ constexpr int kMaxRowsPerCta = 32;
 // LOWRES (dense flow only): the flow is given at gh x gw and bilinearly resized to H x W in the kernel - the
 // resized flow is never written or read back; bit-identical to resizing first.
 template <int C, int U, int VIS, bool AFFINE, bool FULL, bool PACK = false, bool LOWRES = false>
-__global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const WarpFwdArgs a) {
+__global__ void __launch_bounds__(kCols, U >= 4 ? MT_WARP_MINB4 : MT_WARP_MINB) warp_fwd_kernel(const WarpFwdArgs a) {
     static_assert(!(AFFINE && LOWRES), "a theta needs no resize");
     pdl_sync();
     __shared__ float s_by[kMaxRowsPerCta];
@@ -192,25 +202,46 @@ __global__ void __launch_bounds__(kCols, MT_WARP_MINB) warp_fwd_kernel(const War
         float xa[C][U], va[U];
         if (__all_sync(0xffffffffu, interior)) {
             // ---------------- fast path ----------------
+            // Row reuse: a thread owns U vertically adjacent pixels, and where the flow is locally coherent the upper
+            // taps of pixel k are the lower taps of pixel k - 1 (same column, next source row).  Those lanes skip
+            // the two loads (predicated off) and take the registers of the row above.  A gather instruction costs the
+            // L1 one wavefront per 128-byte line its lanes touch, and the kernel is bound by exactly that: fewer
+            // lanes per tap instruction = fewer lines.  The values are the ones the loads would have returned.
             float c00[C + 1][U], c01[C + 1][U], c10[C + 1][U], c11[C + 1][U];
+            int o[U];
+            bool same[U];
 #pragma unroll
             for (int k = 0; k < U; ++k) {
-                const int o = (int)yn[k] * W + (int)xw[k];
+                o[k] = (int)yn[k] * W + (int)xw[k];
+                same[k] = kTapReuse && k > 0 && o[k] == o[k - 1] + W;
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const float *r0 = a.x + (xo + c * a.x_sc + o);
-                    const float *r1 = a.x + (xo + c * a.x_sc + o + W);
-                    tap_pair(r0, c00[c][k], c01[c][k]);
-                    tap_pair(r1, c10[c][k], c11[c][k]);
+                    const float *r0 = a.x + (xo + c * a.x_sc + o[k]);
+                    const float *r1 = a.x + (xo + c * a.x_sc + o[k] + W);
+                    c00[c][k] = 0.0f; c01[c][k] = 0.0f;
+                    if (!same[k]) { c00[c][k] = __ldg(r0); c01[c][k] = __ldg(r0 + 1); }
+                    c10[c][k] = __ldg(r1); c11[c][k] = __ldg(r1 + 1);
                 }
                 if (VIS == 2) {
-                    const float *r0 = vp + o;
-                    const float *r1 = vp + (o + W);
-                    tap_pair(r0, c00[C][k], c01[C][k]);
-                    tap_pair(r1, c10[C][k], c11[C][k]);
+                    const float *r0 = vp + o[k];
+                    const float *r1 = vp + (o[k] + W);
+                    c00[C][k] = 0.0f; c01[C][k] = 0.0f;
+                    if (!same[k]) { c00[C][k] = __ldg(r0); c01[C][k] = __ldg(r0 + 1); }
+                    c10[C][k] = __ldg(r1); c11[C][k] = __ldg(r1 + 1);
                 } else {
                     // nearest: rint (half-to-even) lands on one of the 4 interior taps: in bounds
                     c00[C][k] = __ldg(vp + ((int)rintf(iy[k]) * W + (int)rintf(ix[k])));
+                }
+            }
+#pragma unroll
+            for (int k = 1; k < U; ++k) {
+#pragma unroll
+                for (int c = 0; c < (VIS == 2 ? C + 1 : C); ++c) {
+                    c00[c][k] = same[k] ? c10[c][k - 1] : c00[c][k];
+                    c01[c][k] = same[k] ? c11[c][k - 1] : c01[c][k];
                 }
             }
 #pragma unroll
@@ -334,14 +365,30 @@ __device__ __forceinline__ void gather_taps(const float *__restrict__ x, int xo,
                                             const Taps<U> &t, Corners (&q)[C][U]) {
     if (__all_sync(0xffffffffu, t.interior)) {
 #pragma unroll
+        int o[U];      // row reuse as in warp_fwd_kernel's fast path: the upper taps of row slot k are the lower
+        bool same[U];  // taps of slot k - 1 where the flow is locally coherent; those lanes skip two loads
+#pragma unroll
         for (int k = 0; k < U; ++k) {
-            const int o = (int)t.yn[k] * sp.W + (int)t.xw[k];
+            o[k] = (int)t.yn[k] * sp.W + (int)t.xw[k];
+            same[k] = kTapReuse && k > 0 && o[k] == o[k - 1] + sp.W;
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const float *r0 = x + (xo + c * x_sc + o);
-                const float *r1 = x + (xo + c * x_sc + o + sp.W);
-                tap_pair(r0, q[c][k].nw, q[c][k].ne);
-                tap_pair(r1, q[c][k].sw, q[c][k].se);
+                const float *r0 = x + (xo + c * x_sc + o[k]);
+                const float *r1 = x + (xo + c * x_sc + o[k] + sp.W);
+                q[c][k].nw = 0.0f; q[c][k].ne = 0.0f;
+                if (!same[k]) { q[c][k].nw = __ldg(r0); q[c][k].ne = __ldg(r0 + 1); }
+                q[c][k].sw = __ldg(r1); q[c][k].se = __ldg(r1 + 1);
+            }
+        }
+#pragma unroll
+        for (int k = 1; k < U; ++k) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                q[c][k].nw = same[k] ? q[c][k - 1].sw : q[c][k].nw;
+                q[c][k].ne = same[k] ? q[c][k - 1].se : q[c][k].ne;
             }
         }
     } else {
@@ -360,7 +407,10 @@ __device__ __forceinline__ float interp_k(const Corners &q, const Taps<U> &t, in
            __fmaf_rn(q.ne, __fmul_rn(t.s[k], t.w[k]), __fmul_rn(q.nw, __fmul_rn(t.s[k], t.e[k])))));
 }
 
-constexpr int kRowsB = 2;  // rows per thread in the dense-flow kernels
+#ifndef MT_WARPB_ROWS
+#define MT_WARPB_ROWS 2
+#endif
+constexpr int kRowsB = MT_WARPB_ROWS;  // rows per thread in the dense-flow kernels
 
 // ---- backward w.r.t. the dense grid (generic upstream gradient) -------------
 struct WarpBwdArgs {

@@ -68,29 +68,6 @@ __device__ __forceinline__ Corners gather(const float *__restrict__ plane, const
     return c;
 }
 
-// Two horizontally adjacent taps r[0], r[1] of an interior pixel.  MT_TAP_PAIR = 1: one aligned 8-byte load covers
-// both when r is 8-byte aligned (every second pixel); otherwise it covers r[0] and a predicated 4-byte load fetches
-// r[1].  A gather instruction whose 32 lanes land on ~32 different source lines costs the L1 one wavefront per line:
-// the pair form issues 1.5 line visits per row of taps instead of 2.  The 8 bytes at (r & ~7) lie inside the
-// allocation r points into (allocations are >= 256-byte aligned), so the wide load never leaves it.
-#ifndef MT_TAP_PAIR
-#define MT_TAP_PAIR 0
-#endif
-__device__ __forceinline__ void tap_pair(const float *__restrict__ r, float &v0, float &v1) {
-#if MT_TAP_PAIR
-    const unsigned long long p = reinterpret_cast<unsigned long long>(r);
-    const bool odd = (p & 4ull) != 0;
-    const float2 w = __ldg(reinterpret_cast<const float2 *>(p & ~7ull));
-    float e = 0.0f;
-    if (odd) e = __ldg(r + 1);
-    v0 = odd ? w.y : w.x;
-    v1 = odd ? e : w.y;
-#else
-    v0 = __ldg(r);
-    v1 = __ldg(r + 1);
-#endif
-}
-
 __device__ __forceinline__ float interp(const Corners &c, const Bil &b) {
     // fma(se_v, se, fma(sw_v, sw, fma(ne_v, ne, nw_v * nw)))  (pinned order)
     return __fmaf_rn(c.se, b.se, __fmaf_rn(c.sw, b.sw, __fmaf_rn(c.ne, b.ne, __fmul_rn(c.nw, b.nw))));

@@ -591,6 +591,69 @@ def corr4d_vgg(feats_t, m_target, feats_r, m_refs):
     return out
 
 
+def corr4d_l1_fwd_raw(pred, feats_t, feats_r, m_target=None, m_refs=None, want_sign=True):
+    """mean |pred - corr4d_vgg(feats_t, m_target, feats_r, m_refs)| with the volume kept on chip
+    (model_dfpn.py:254-257).  -> (loss 0-d tensor, sign int8 (B,F,h,w,h,w) or None)."""
+    _need_cuda(feats_t, m_target, feats_r, m_refs, pred)
+    b, c, f, h, w = feats_r.shape
+    if tuple(pred.shape) != (b, f, h, w, h, w):
+        raise ValueError("corr4d_l1: pred must be (B,F,h,w,h,w) = %s, got %s" % ((b, f, h, w, h, w), tuple(pred.shape)))
+
+    def ok(t, lead):
+        return all(t.size(d) == 1 or (t.stride(d) > 0 and t.stride(d) % 4 == 0) for d in range(lead)) and \
+            t.stride(-1) == 1 and t.stride(-2) == w and t.data_ptr() % 16 == 0
+    ft = feats_t if ok(feats_t, 2) else _contig(feats_t)
+    fr = feats_r if ok(feats_r, 3) else _contig(feats_r)
+    pr = _contig(pred)
+    _lib.keep(ft), _lib.keep(fr), _lib.keep(pr)
+    mt = mr = None
+    mt_sb = mr_sb = mr_sf = MH = MW = 0
+    if m_target is not None:
+        mt, mr = _planes(m_target), _planes(m_refs)
+        MH, MW = mt.shape[-2:]
+        mt_sb, mr_sb, mr_sf = mt.stride(0), mr.stride(0), mr.stride(2)
+    loss = _empty((), dtype=torch.float32, device=fr.device)
+    sign = _empty(pr.shape, dtype=torch.int8, device=fr.device) if want_sign else None
+    ws = scratch(fr, "corr_l1", int(_lib.load().mt_corr4d_l1_workspace_bytes()))
+    _call("mt_corr4d_vgg_l1_fwd", _ptr(ft), ft.stride(0), ft.stride(1), _ptr(mt), mt_sb, _ptr(fr), fr.stride(0),
+          fr.stride(1), fr.stride(2), _ptr(mr), mr_sb, mr_sf, MH, MW, _ptr(pr), _ptr(loss), _ptr(sign), _ptr(ws),
+          ws.numel(), b, c, f, h, w, _stream(fr))
+    return loss, sign
+
+
+class Corr4dL1Fn(torch.autograd.Function):
+    """F.l1_loss(pred, correlation of the ground-truth features) with autograd w.r.t. ``pred``."""
+
+    @staticmethod
+    def forward(ctx, pred, feats_t, feats_r):
+        loss, sign = corr4d_l1_fwd_raw(pred.detach(), feats_t, feats_r, want_sign=ctx.needs_input_grad[0])
+        ctx.sign = sign
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        sign = ctx.sign
+        if sign is None:
+            return None, None, None
+        gp = _empty(sign.shape, dtype=torch.float32, device=sign.device)
+        gg = _contig(g.to(torch.float32))
+        _need_cuda(gg)
+        _lib.keep(gg)
+        _call("mt_corr4d_l1_bwd", _ptr(sign), _ptr(gg), _ptr(gp), sign.numel(), _stream(sign))
+        return gp, None, None
+
+
+def corr4d_l1_supported(c, p):
+    return corr4d_vgg_supported(c, p)
+
+
+def corr4d_l1(pred, feats_t, feats_r):
+    """model_dfpn.py:254-257: ``F.l1_loss(pred, correlation_masked_4d(feats_t, None, feats_r, None))`` in one
+    pass - the ground-truth volume never reaches HBM; differentiable w.r.t. ``pred``."""
+    _no_grad_inputs("corr4d_l1", feats_t, feats_r)
+    return Corr4dL1Fn.apply(pred, feats_t, feats_r)
+
+
 # --------------------------------------------------------------------------
 # K3 context matching
 # --------------------------------------------------------------------------

@@ -223,8 +223,8 @@ def _alignment_recons(x, v, x_aligned, flow, t, n_refs):
 
 def dfpn_compute_loss(self, corr, xs, vs, ys, xs_aligned, flows, flows_gt, flows_use, t, r_list):
     """Replaces DFPN.compute_loss (model_dfpn.py:210-293).  The VGG features of the ground truth (cuDNN) and
-    the L1 against the filled correlation volume are the reference's own calls; the unmasked correlation of
-    the ground truth (:254), the three flow losses (:259-267, all-ones mask never materialised, no host sync
+    are the reference's own calls; the unmasked correlation of the ground truth with its L1 against the filled
+    volume folded into the epilogue (:254-257), the three flow losses (:259-267, all-ones mask never materialised, no host sync
     for ``flows_use``) and the two reconstruction terms (:269-287) are kernels of this library."""
     import torch.nn.functional as F
     b, c, f, h, w = ys[2].size()
@@ -234,8 +234,12 @@ def dfpn_compute_loss(self, corr, xs, vs, ys, xs_aligned, flows, flows_gt, flows
             y_vgg_input = F.interpolate(y_vgg_input, (256, 256), mode='bilinear')
         y_vgg_feats = self.model_vgg(y_vgg_input)
     y_vgg_feats = y_vgg_feats[3].reshape(b, f, -1, 16, 16).transpose(1, 2)
-    corr_y = ops.corr4d(y_vgg_feats[:, :, t], None, y_vgg_feats[:, :, r_list], None)
-    corr_loss = F.l1_loss(corr, corr_y)
+    if ops.corr4d_l1_supported(y_vgg_feats.size(1), 16 * 16):
+        # :254-257 in one pass: the volume of the ground truth stays on chip, |corr - corr_y| is summed in the epilogue
+        corr_loss = ops.corr4d_l1(corr, y_vgg_feats[:, :, t], y_vgg_feats[:, :, r_list])
+    else:
+        corr_y = ops.corr4d(y_vgg_feats[:, :, t], None, y_vgg_feats[:, :, r_list], None)
+        corr_loss = F.l1_loss(corr, corr_y)
     flow_losses = [ops.masked_l1(flows[i], flows_gt[i], None, flows_use) for i in range(3)]
     recons_64 = _alignment_recons(xs[1], vs[1], xs_aligned[1], flows[1], t, len(r_list))
     recons_256 = _alignment_recons(xs[2], vs[2], xs_aligned[2], flows[2], t, len(r_list))

@@ -233,6 +233,14 @@ def chn_pack(x_t, v_t, x_al, v_al, v_map):
     return out
 
 
+def corr4d_l1(pred, feats_t, feats_r):
+    """8f-3 - F.l1_loss(corr, corr_y) with corr_y the unmasked correlation of the ground-truth features,
+    model_dfpn.py:254-257.  -> (loss as float64, d loss / d pred as float32)."""
+    corr_y = corr4d(feats_t, None, feats_r, None).astype(np.float64)
+    d = np.asarray(pred, np.float64) - corr_y
+    return float(np.abs(d).mean()), (np.sign(d) / d.size).astype(np.float32)
+
+
 def flow_pack(x_target, m_target, x_refs, m_refs, flow_pre):
     """8f-4 - FlowEstimator.forward's nn_input, model_dfpn.py:733-741."""
     x_target, m_target, x_refs, m_refs, flow_pre = _c(x_target), _c(m_target), _c(x_refs), _c(m_refs), _c(flow_pre)

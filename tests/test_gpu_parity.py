@@ -1045,8 +1045,8 @@ def test_dfpn_training_step_mirrors(mtb, name):
             sys.modules["master_thesis"] = saved
     assert len(res) == 8 and all(isinstance(a, plug.DeferredAlign) for a in res[4])
     # the hot path of the step is exactly these launches: no align_set, no mask_out, no x_aligned in HBM
-    assert sorted(plan.names()) == sorted(["mt_corr4d_fwd"] + ["mt_masked_l1_fwd"] * 3 + ["mt_warp_l1_fwd"] * 2 +
-                                          ["mt_warp_l1_bwd"] * 2 + ["mt_masked_l1_bwd"] * 3)
+    assert sorted(plan.names()) == sorted(["mt_corr4d_vgg_l1_fwd", "mt_corr4d_l1_bwd"] + ["mt_masked_l1_fwd"] * 3 +
+                                          ["mt_warp_l1_fwd"] * 2 + ["mt_warp_l1_bwd"] * 2 + ["mt_masked_l1_bwd"] * 3)
     # corr_loss compares a TF32 correlation of the ground truth with the given volume: |d| <= 7e-4 per element
     assert abs(float(items[0]) - float(g["items"][0])) <= 1e-3
     assert float(loss) - float(items[0]) == pytest.approx(float(g["loss"]) - float(g["items"][0]), rel=1e-5)
@@ -1148,3 +1148,82 @@ def test_flow_estimator_input_pack_full_size(mtb):
     want = oracle.flow_pack(x[:, :, t], m[:, :, t], x[:, :, r_list], m[:, :, r_list], flow)
     assert np.array_equal(host(got), want)
     assert torch.equal(xd, dev(x)) and torch.equal(md, dev(m))
+
+
+@pytest.mark.parametrize("rows,iters", [(2, 1), (4, 1), (2, 4), (4, 2)])
+@pytest.mark.parametrize("name", sorted(cases.WARP_CASES))
+def test_dfpn_align_tail_rows_per_thread(mtb, name, rows, iters):
+    """The direct-gather kernel with 2 / 4 vertically adjacent pixels per thread (taps of a shared source row are
+    loaded once and reused) and several row groups per CTA: bit-identical to the reference's golden vectors."""
+    x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES[name])
+    g = load_golden("warp_" + name)
+    try:
+        _set_tuning("MT_WARP_ROWS", rows)
+        _set_tuning("MT_WARP_ITERS", iters)
+        xa, va, vm = mtb.dfpn_align_tail(dev(x), dev(m), dev(m_t), dev(flow))
+    finally:
+        _set_tuning("MT_WARP_ROWS", 2)
+        _set_tuning("MT_WARP_ITERS", 1)
+    assert np.array_equal(host(xa), g["x_aligned"])
+    assert np.array_equal(host(va), g["v_aligned"]) and np.array_equal(host(vm), g["v_map"])
+
+
+# ---------------------------------------------------------------- 8f-3: F.l1_loss(corr, corr_y) in the epilogue
+_CORR_L1_VARIANTS = [(0, 0, -1), (128, 64, 0), (128, 128, 0), (128, 256, 0), (256, 64, 0), (256, 128, 0),
+                     (256, 256, 0), (0, 128, 1), (0, 256, 1)]
+
+
+@pytest.mark.parametrize("tm,tn,pair", _CORR_L1_VARIANTS)
+@pytest.mark.parametrize("name", ["real_nomask", "mid_masked", "big_masked"])
+def test_corr4d_l1_in_the_epilogue(mtb, name, tm, tn, pair):
+    """mt_corr4d_vgg_l1_fwd / mt_corr4d_l1_bwd (model_dfpn.py:254-257 without the ground-truth volume in HBM), every
+    tile variant and the CTA-pair kernel at 2 / 40 / 128 frames: the loss against the CPU oracle (TF32 bound) and
+    against the L1 of the volume the store-mode launch of the SAME variant writes (same accumulators: the signs are
+    identical, the loss agrees to summation order), the gradient against autograd's formula."""
+    from master_thesis_b200 import ops
+    spec = cases.CORR_CASES[name]
+    ft, _, fr, _ = cases.corr_inputs(spec)
+    b, c, f = fr.shape[:3]
+    r = np.random.RandomState(spec["seed"] + 40)
+    pred = r.random_sample((b, f, 16, 16, 16, 16)).astype(np.float32)
+    try:
+        _set_tuning("MT_CORR_TM", tm)
+        _set_tuning("MT_CORR_TN", tn)
+        _set_tuning("MT_CORR_2CTA", pair)
+        vol = ops.corr4d_vgg(dev(ft), None, dev(fr), None)
+        p = dev(pred)
+        p.view(-1)[::7] = vol.view(-1)[::7]                  # exact ties: sign 0, no gradient
+        p.requires_grad_(True)
+        loss = ops.corr4d_l1(p, dev(ft), dev(fr))
+        (loss * 3.0).backward()
+    finally:
+        _set_tuning("MT_CORR_TM", 0)
+        _set_tuning("MT_CORR_TN", 0)
+        _set_tuning("MT_CORR_2CTA", -1)
+    d = p.detach() - vol
+    assert float(loss) == pytest.approx(float(d.abs().double().mean()), rel=2e-6)
+    want_g = torch.sign(d) * (3.0 / d.numel())
+    assert torch.allclose(p.grad, want_g, rtol=1e-6, atol=0)
+    assert int((p.grad == 0).sum()) >= d.numel() // 7
+    o_loss, o_grad = oracle.corr4d_l1(host(p), ft, fr)
+    assert abs(float(loss) - o_loss) <= 1e-3                  # |corr_tf32 - corr_fp32| <= 2e-3 per element
+    # signs differ from the fp32 oracle only where |pred - corr| is inside the TF32 error band
+    flip = (host(p.grad) != 3.0 * o_grad) & (np.abs(host(d)) > 2e-3)
+    assert not flip.any()
+
+
+def test_corr4d_l1_strided_features_no_grad(mtb):
+    """The ground-truth features as DFPN.compute_loss hands them over (the transposed view of the VGG output,
+    model_dfpn.py:252) and a prediction that needs no gradient (validation): no sign tensor is written."""
+    from master_thesis_b200 import ops
+    spec = cases.DFPNLOSS_CASES["n5"]
+    *_, corr, _, _, _, feats = cases.dfpnloss_inputs(spec)
+    b, n = spec["b"], spec["n"]
+    t, r_list = n // 2, [i for i in range(n) if i != n // 2]
+    fy = dev(feats).reshape(b, n, -1, 16, 16).transpose(1, 2)
+    with torch.no_grad():
+        loss = ops.corr4d_l1(dev(corr), fy[:, :, t], fy[:, :, r_list])
+    fyh = feats.reshape(b, n, -1, 16, 16).transpose(0, 2, 1, 3, 4)
+    o_loss, _ = oracle.corr4d_l1(corr, fyh[:, :, t], fyh[:, :, r_list])
+    assert abs(float(loss) - o_loss) <= 1e-3
+    assert abs(float(loss) - float(load_golden("dfpnloss_n5")["items"][0])) <= 1e-3

@@ -269,3 +269,18 @@ def test_flow_estimator_input_pack(name):
     T = torch.from_numpy
     got = tp.flow_pack(T(x_t), T(m_t), T(x_r), T(m_r), cases.flowpack_view(T(base), spec))
     assert np.array_equal(got.numpy(), g["nn_input"])
+
+
+@pytest.mark.parametrize("name", sorted(cases.DFPNLOSS_CASES))
+def test_corr_l1_of_the_ground_truth_volume(name):
+    """8f-3: F.l1_loss(corr, corr_y) (model_dfpn.py:254-257) against the corr_loss item and the gradient the
+    unmodified DFPN.compute_loss produced."""
+    spec = cases.DFPNLOSS_CASES[name]
+    *_, corr, _, _, _, feats = cases.dfpnloss_inputs(spec)
+    g = load_golden("dfpnloss_" + name)
+    b, n = spec["b"], spec["n"]
+    t, r_list = n // 2, [i for i in range(n) if i != n // 2]
+    fy = feats.reshape(b, n, -1, 16, 16).transpose(0, 2, 1, 3, 4)
+    loss, grad = oracle.corr4d_l1(corr, fy[:, :, t], fy[:, :, r_list])
+    assert loss == pytest.approx(float(g["items"][0]), rel=1e-5)
+    assert float(np.abs(grad).astype(np.float64).sum()) == pytest.approx(float(g["g_corr_abs"]), rel=1e-5)
