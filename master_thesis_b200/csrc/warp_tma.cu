@@ -35,12 +35,11 @@
 namespace mt {
 namespace {
 
-// output tile: TW x TH pixels (32 x 32, 64 x 32, 64 x 16); (TW / 16) * (TH / 4) consumer warps (16 x 4 pixels each).
-// Up to 16 consumer warps: + a dedicated producer warp; 32 consumer warps are the 1024-thread limit, the consumer
-// warps then take turns as producer (one tile each)
-constexpr int staged_cons_warps(int tw, int th) { return (tw / 16) * (th / 4); }
-constexpr bool staged_own_producer(int tw, int th) { return staged_cons_warps(tw, th) <= 16; }
-constexpr int staged_threads(int tw, int th) { return (staged_cons_warps(tw, th) + (staged_own_producer(tw, th) ? 1 : 0)) * 32; }
+constexpr int kTileH = 32;          // output tile: TW x 32 pixels, TW = 32 or 64
+// TW / 2 consumer warps (16 x 4 pixels each); TW = 32: + a dedicated producer warp; TW = 64: 32 consumer
+// warps are the 1024-thread limit, the consumer warps take turns as producer (one tile each)
+constexpr bool staged_own_producer(int tw) { return tw == 32; }
+constexpr int staged_threads(int tw) { return (tw / 2 + (staged_own_producer(tw) ? 1 : 0)) * 32; }
 constexpr int kMaxTable = 1024;     // W, H <= 1024 (tables of the base grid in shared memory)
 
 struct TileDesc {  // written by the producer, read by the consumers after the full barrier
@@ -72,22 +71,21 @@ struct WarpStagedArgs {
     Sampler sp;
 };
 
-template <int TW, int TH, int BW, int BH, int STAGES>
+template <int TW, int BW, int BH, int STAGES>
 constexpr int staged_smem_bytes() {
-    return STAGES * (4 * BW * BH + TW * TH) * 4 + 2 * kMaxTable * 4 + STAGES * (int)sizeof(TileDesc) +
+    return STAGES * (4 * BW * BH + TW * kTileH) * 4 + 2 * kMaxTable * 4 + STAGES * (int)sizeof(TileDesc) +
            2 * STAGES * 8 + 128;
 }
 
 __device__ __forceinline__ float unnorm_t(float g, float sf, bool ac) { return unnormalize(g, sf, ac); }
 
 // AC: align_corners; FM: `vis` holds masks (v = 1 - m inside the frame, 0 outside)
-template <int TW, int TH, int BW, int BH, int STAGES, bool AC, bool FM>
-__global__ void __launch_bounds__(staged_threads(TW, TH), 1)
+template <int TW, int BW, int BH, int STAGES, bool AC, bool FM>
+__global__ void __launch_bounds__(staged_threads(TW), 1)
 warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_v,
                    const __grid_constant__ CUtensorMap map_t, const WarpStagedArgs a) {
     static_assert(BW % 32 == 16, "a source row must start 16 banks after the previous one (see the lane mapping)");
-    constexpr int kConsWarps = staged_cons_warps(TW, TH), kStagedThreads = staged_threads(TW, TH);
-    constexpr int kTileH = TH;
+    constexpr int kConsWarps = TW / 2, kStagedThreads = staged_threads(TW);
     constexpr int kPlane = BW * BH;
     constexpr int kStageFloats = 4 * kPlane + TW * kTileH;  // RGB + mask boxes, target-mask tile
     constexpr uint32_t kMtBytes = TW * kTileH * 4u;
@@ -183,7 +181,7 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (probe && i == 0) g_timeline[blockIdx.x * 8 + 2] = gtime();
     };
 
-    if constexpr (staged_own_producer(TW, TH)) {
+    if constexpr (staged_own_producer(TW)) {
         if (warp == kConsWarps) {
             // ===================== producer warp =====================
             // The descriptor of the next tile is prepared while its stage is still in use: between
@@ -216,7 +214,7 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const float wm2 = wmax - 1.0f, hm2 = hmax - 1.0f;
     int i = 0;
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++i) {
-        if constexpr (!staged_own_producer(TW, TH)) {
+        if constexpr (!staged_own_producer(TW)) {
             if (lane == 0 && warp == i % kConsWarps) {
                 const int tj = t + (STAGES - 1) * gridDim.x;
                 if (tj < a.n_tiles) issue(i + STAGES - 1, prepare(tj));
@@ -356,9 +354,8 @@ struct StagedHost {
     EncodeTiledFn enc;
 };
 
-template <int TW, int TH, int BW, int BH, int STAGES>
+template <int TW, int BW, int BH, int STAGES>
 int staged_go(const StagedHost &h) {
-    constexpr int kTileH = TH;
     const int W = h.W, H = h.H;
     const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + kTileH - 1) / kTileH;
     const int64_t n_tiles = (int64_t)h.B * h.F * tiles_x * tiles_y;
@@ -410,17 +407,17 @@ int staged_go(const StagedHost &h) {
     a.debug = tuning("MT_WARP_DBG", 0);
     int ctas = sm_count();
     if (ctas > n_tiles) ctas = (int)n_tiles;
-    constexpr int smem = staged_smem_bytes<TW, TH, BW, BH, STAGES>();
+    constexpr int smem = staged_smem_bytes<TW, BW, BH, STAGES>();
     static_assert(smem <= 227 * 1024, "stage ring exceeds the shared memory of an SM");
 #define MT_STAGED_GO(ACV, FMV)                                                                       \
     do {                                                                                             \
-        auto kern = warp_staged_kernel<TW, TH, BW, BH, STAGES, ACV, FMV>;                                \
+        auto kern = warp_staged_kernel<TW, BW, BH, STAGES, ACV, FMV>;                                \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
         if (e != cudaSuccess) {                                                                      \
             set_error("mt_warp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));               \
             return MT_ERR_CUDA;                                                                      \
         }                                                                                            \
-        launch(kern, dim3(ctas), dim3(staged_threads(TW, TH)), (size_t)smem, h.st, map_x, map_v, map_t, a); \
+        launch(kern, dim3(ctas), dim3(staged_threads(TW)), (size_t)smem, h.st, map_x, map_v, map_t, a); \
     } while (0)
     if (h.ac) { if (h.from_mask) MT_STAGED_GO(true, true); else MT_STAGED_GO(true, false); }
     else      { if (h.from_mask) MT_STAGED_GO(false, true); else MT_STAGED_GO(false, false); }
@@ -455,14 +452,8 @@ int warp_staged_launch(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_sf,
     h.B = B; h.F = F; h.H = H; h.W = W; h.ac = ac; h.from_mask = from_mask; h.st = st; h.enc = enc;
     // tile 64 x 32 (32 consumer warps, box 80 x 48, 3 stages of 68 KB) or 32 x 32 (16 warps, box 48 x 48,
     // 5 stages of 40 KB)
-    // (64 x 16 tiles: longer, fewer box rows per pixel - 128 rows of 320 / 448 B instead of 192 rows of 192 B)
-    const int tw = tuning("MT_WARP_TILE_W", 32), th = tuning("MT_WARP_TILE_H", 32);
-    if (tw == 64 && th == 16 && W >= 64) {
-        if (tuning("MT_WARP_BOX_W", 80) == 112) return staged_go<64, 16, 112, 32, 3>(h);
-        return staged_go<64, 16, 80, 32, 4>(h);
-    }
-    if (tw == 64 && W >= 64) return staged_go<64, 32, 80, 48, 3>(h);
-    return staged_go<32, 32, 48, 48, 5>(h);
+    if (tuning("MT_WARP_TILE_W", 32) == 64 && W >= 64) return staged_go<64, 80, 48, 3>(h);
+    return staged_go<32, 48, 48, 5>(h);
 }
 
 }  // namespace mt

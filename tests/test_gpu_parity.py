@@ -120,18 +120,15 @@ def _set_tuning(name, value):
     _lib.call("mt_set_tuning", name.encode(), value)
 
 
-@pytest.mark.parametrize("tile", [(32, 32, 0), (64, 32, 0), (64, 16, 80), (64, 16, 112)])
+@pytest.mark.parametrize("tile_w", [32, 64])
 @pytest.mark.parametrize("name", sorted(STAGED_CASES))
-def test_cpn_align_tail_staged(mtb, name, tile):
-    """Every tile shape of the staged kernel (tile width x height, box width) against the oracle and the direct kernel."""
+def test_cpn_align_tail_staged(mtb, name, tile_w):
+    """Both tile shapes of the staged kernel against the oracle and the direct kernel."""
     spec = STAGED_CASES[name]
     x, m, m_t, theta = cases.cpn_inputs(spec)
     oxa, ova, ovm = oracle.cpn_align_tail(x, m, m_t, theta=theta)
-    tile_w, tile_h, box_w = tile
     try:
         _set_tuning("MT_WARP_TILE_W", tile_w)
-        _set_tuning("MT_WARP_TILE_H", tile_h)
-        _set_tuning("MT_WARP_BOX_W", box_w or 80)
         _set_tuning("MT_WARP_STAGED", 1)
         xa, va, vm = mtb.cpn_align_tail(dev(x), dev(m), dev(m_t), dev(theta))
         _set_tuning("MT_WARP_STAGED", 0)
@@ -139,8 +136,6 @@ def test_cpn_align_tail_staged(mtb, name, tile):
     finally:
         _set_tuning("MT_WARP_STAGED", 1)
         _set_tuning("MT_WARP_TILE_W", DEFAULT_TILE_W)
-        _set_tuning("MT_WARP_TILE_H", 32)
-        _set_tuning("MT_WARP_BOX_W", 80)
     for got, direct, orc in ((xa, xd, oxa), (va, vd, ova), (vm, vmd, ovm)):
         assert np.array_equal(host(got), orc)           # staged kernel == oracle, bit for bit
         assert np.array_equal(host(direct), orc)        # direct-gather kernel == oracle
@@ -1227,3 +1222,17 @@ def test_corr4d_l1_strided_features_no_grad(mtb):
     o_loss, _ = oracle.corr4d_l1(corr, fyh[:, :, t], fyh[:, :, r_list])
     assert abs(float(loss) - o_loss) <= 1e-3
     assert abs(float(loss) - float(load_golden("dfpnloss_n5")["items"][0])) <= 1e-3
+
+
+def test_dfpn_align_tail_full_size(mtb):
+    """cfg2-size DFPN tail (32 frames of 256 x 256, the bench's flow statistics, plus a band of flow that leaves the
+    frame) and a 480 x 854 frame against the oracle, bit for bit."""
+    from master_thesis_b200 import synth
+    for (b, f, h, w, seed) in ((8, 4, 256, 256, 31), (1, 2, 480, 854, 32)):
+        x, m, _ = synth.frames(seed, b, f + 1, h, w)
+        flow = synth.dense_flow(seed + 1, b, f, h, w, 0.05, True)
+        flow[0, 0, :3] += 0.7                                   # a band that leaves the frame
+        xr, mr, m_t = x[:, :, 1:], m[:, :, 1:], m[:, :, 0]
+        xa, va, vm = mtb.dfpn_align_tail(dev(xr), dev(mr), dev(m_t), dev(flow))
+        oxa, ova, ovm = oracle.dfpn_align_tail(xr, mr, m_t, flow)
+        assert np.array_equal(host(xa), oxa) and np.array_equal(host(va), ova) and np.array_equal(host(vm), ovm)
