@@ -415,7 +415,7 @@ class Cfg3(Workload):
             elif name == "mt_corr4d_vgg_l1_fwd":
                 # features once, the prediction read (4 B) and the signs written (1 B) per volume element; no volume
                 n, pp = a["B"] * a["F"], (a["h"] * a["w"]) ** 2
-                out.append((name, 2, n * 524288 + a["B"] * 524288 + n * pp * 5, "tensor", n * CORR_FLOP))
+                out.append((name, 1, n * 524288 + a["B"] * 524288 + n * pp * 5, "tensor", n * CORR_FLOP))
             elif name == "mt_corr4d_l1_bwd":
                 out.append((name, 1, a["n"] * 5, "hbm"))             # signs read, gradient written
             elif name in ("mt_warp_l1_fwd", "mt_warp_l1_bwd"):

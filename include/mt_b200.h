@@ -264,9 +264,10 @@ MT_API int mt_corr4d_vgg_fwd(const float *feats_t, int64_t ft_sb, int64_t ft_sc,
  * folded into its epilogue: the volume of the ground-truth features is never written.  pred (B,F,P,P)
  * contiguous = the network's filled volume `corr`; loss[0] (device) = mean |pred - corr_y|; sign (B*F*P*P int8,
  * may be NULL when no gradient is needed) = sign(pred - corr_y), which is all the backward pass reads.
- * workspace: mt_corr4d_l1_workspace_bytes() bytes.  Tensor-core shapes only.  Launches the volume kernel and a
- * one-CTA fold of its partial sums (fixed order: deterministic for a given shape).
- * mt_corr4d_l1_bwd: g_pred[i] = sign[i] * grad_loss[0] / n   (n = B*F*P*P, a multiple of 16). */
+ * workspace: mt_corr4d_l1_workspace_bytes() bytes, ZEROED before the first call (the call leaves it re-armed).
+ * Tensor-core shapes only.  One launch: the last epilogue warp of the grid folds the partial sums (fixed order:
+ * deterministic for a given shape).
+ * mt_corr4d_l1_bwd: g_pred[i] = sign[i] * grad_loss[0] / n   (n = B*F*P*P, a multiple of 4). */
 MT_API int mt_corr4d_vgg_l1_fwd(const float *feats_t, int64_t ft_sb, int64_t ft_sc,
                          const float *m_target, int64_t mt_sb,
                          const float *feats_r, int64_t fr_sb, int64_t fr_sc, int64_t fr_sf,

@@ -52,6 +52,14 @@ namespace {
 constexpr int kTile = 256;        // largest output tile: TM rows (one or two UMMA M = 128 halves) x TN <= 256 columns
 constexpr int kBK = 32;
 constexpr int kUmmaK = 8;         // tf32: 32 B of K per instruction
+// griddepcontrol.launch_dependents right after the wait (pdl_sync, the library's default) lets the next kernel's CTAs
+// take their SM slots while this kernel runs.  For this kernel that is harmful: it holds ~200 KB of shared memory per
+// SM, the pre-launched CTAs arrive while the SM is in its maximum-shared-memory configuration, and because from then
+// on an SM is never empty between PDL-chained kernels the configuration (a few KB of L1) sticks - the gather kernels
+// that follow run with almost no L1.  Measured (profiles/r2_experiments.md, call Z): warp_l1_fwd at 256 x 256 77 ->
+// 121 us several launches after a correlation; cfg3 step 431 -> 364 us, cfg1 20.0 -> 18.4 us, default workload
+// 100.9 -> 97.7 us with the trigger left to the kernel's exit.  MT_CORR_EARLY_TRIGGER=1 restores the old behaviour.
+constexpr int kCorrEarlyTrigger = 0;
 constexpr bool kPairDefault = true;   // CTA-pair kernel for large batches (see the heuristic in corr4d_tc_launch_ex)
 
 // MN-major, SWIZZLE_128B_BASE32B shared-memory matrix descriptor (sm_100 "version 1").
@@ -112,11 +120,18 @@ struct CorrTcArgs {
     float *out;                                    // (B, F, P, P); unused in L1 mode
     // L1 mode (pred != NULL): the volume is not written; the epilogue compares it with `pred` (B, F, P, P) instead and
     // accumulates sum |pred - corr| (F.l1_loss(corr, corr_y), model_dfpn.py:254-257).  sign (optional):
-    // sign(pred - corr) as int8, all the backward pass needs.  partials: one float per (CTA, epilogue warp).
+    // sign(pred - corr) as int8, all the backward pass needs.  partials: one float per (CTA, epilogue warp); the last
+    // epilogue warp of the grid to finish (ticket) folds them in a fixed order and writes the mean to loss[0].
     const float *pred;
     signed char *sign;
     float *partials;
+    unsigned int *ticket;                          // zero between launches: counts the epilogue warps that are done
+    float *loss;
+    double inv_count;                              // 1 / (B F P P)
     int C, F, P, tiles_m, tiles_n, n_tiles;
+    // griddepcontrol.launch_dependents right after the wait (the library's default, see pdl_sync) or not at all
+    // (the next kernel of the stream is then scheduled as this kernel's CTAs exit): see corr4d_tc_launch_ex
+    int early_trigger;
 };
 
 // visibility of feature pixel p of plane `base` (see CorrTcArgs)
@@ -202,6 +217,29 @@ __device__ __forceinline__ void corr_epi_prefetch(const CorrTcArgs &a, int64_t o
     for (int c = 0; c < TN; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + c));
 }
 
+// L1 mode, end of an epilogue warp's tile loop: publish the warp's partial sum; the last warp of the grid to arrive
+// sums all n_slots partials (lane-strided, then a butterfly, in double: the order depends on the launch shape only),
+// writes the mean and re-arms the ticket.  No second launch (a one-CTA fold kernel cost 5.5 us, ncu g2).
+__device__ __forceinline__ void corr_l1_tail(const CorrTcArgs &a, float acc, int slot, int n_slots, int lane) {
+    acc = warp_sum(acc);
+    unsigned int t = 0u;
+    if (lane == 0) {
+        a.partials[slot] = acc;
+        __threadfence();
+        t = atomicAdd(a.ticket, 1u);
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t != (unsigned int)n_slots - 1u) return;
+    __threadfence();
+    double s = 0.0;
+    for (int i = lane; i < n_slots; i += 32) s += (double)__ldcg(a.partials + i);
+    s = warp_sum(s);
+    if (lane == 0) {
+        a.loss[0] = (float)(s * a.inv_count);
+        *a.ticket = 0u;
+    }
+}
+
 constexpr int kNormWarps = 8;     // one thread per row of the A tile / column of the B tile
 constexpr int kEpiWarps = 4;      // one per TMEM lane quarter
 constexpr int kThreadsP = (2 + kNormWarps + kEpiWarps) * 32;
@@ -280,7 +318,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     // everything above is on-chip setup and overlaps the tail of the previous kernel (PDL)
-    pdl_sync();
+    pdl_wait();
+    if (a.early_trigger) pdl_launch();
 
     const int tiles_per_frame = a.tiles_m * a.tiles_n;
     if (warp == 0) {
@@ -435,10 +474,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(tmem_empty + buf));
         }
-        if (a.pred) {  // one partial per (CTA, epilogue warp); summed in a fixed order by corr_l1_finish_kernel
-            l1_acc = warp_sum(l1_acc);
-            if (lane == 0) a.partials[blockIdx.x * kEpiWarps + ew] = l1_acc;
-        }
+        if (a.pred) corr_l1_tail(a, l1_acc, blockIdx.x * kEpiWarps + ew, gridDim.x * kEpiWarps, lane);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -575,7 +611,8 @@ corr_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     cluster_sync_all();  // barriers of both CTAs initialised before anyone arrives remotely
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    pdl_sync();
+    pdl_wait();
+    if (a.early_trigger) pdl_launch();
 
     const int tiles_per_frame = a.tiles_m * a.tiles_n;
     if (warp == 0) {
@@ -721,10 +758,7 @@ corr_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 mbar_arrive_remote(mapa_u32(smem_u32(tmem_empty + buf), other));
             }
         }
-        if (a.pred) {
-            l1_acc = warp_sum(l1_acc);
-            if (lane == 0) a.partials[blockIdx.x * kEpiWarps + ew] = l1_acc;
-        }
+        if (a.pred) corr_l1_tail(a, l1_acc, blockIdx.x * kEpiWarps + ew, gridDim.x * kEpiWarps, lane);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal it
@@ -733,53 +767,43 @@ corr_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
-// L1 mode, last step: the per-(CTA, epilogue warp) partial sums in a fixed order (double) -> mean
-__global__ void __launch_bounds__(256) corr_l1_finish_kernel(const float *__restrict__ partials, int n, double inv_count,
-                                                             float *__restrict__ loss) {
-    pdl_sync();
-    __shared__ double s[256];
-    double t = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256) t += (double)partials[i];
-    s[threadIdx.x] = t;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) loss[0] = (float)(s[0] * inv_count);
-}
-
-// backward of mean |pred - corr| w.r.t. pred: sign * grad / count; 16 elements per thread
+// backward of mean |pred - corr| w.r.t. pred: sign * grad / count.  Thread = 4 consecutive elements (one 4-byte load,
+// one coalesced 16-byte store), 4 such groups a block stride apart per thread for loads in flight.
 __global__ void __launch_bounds__(256) corr_l1_bwd_kernel(const signed char *__restrict__ sign,
                                                           const float *__restrict__ grad_loss, float inv_count,
-                                                          float *__restrict__ g_pred, int64_t n16) {
+                                                          float *__restrict__ g_pred, int64_t n4) {
     pdl_sync();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n16) return;
     const float g = __fmul_rn(__ldg(grad_loss), inv_count);
-    const int4 w = __ldcs(reinterpret_cast<const int4 *>(sign) + i);
-    const int ws[4] = {w.x, w.y, w.z, w.w};
-    float4 *o = reinterpret_cast<float4 *>(g_pred) + i * 4;
+    const int64_t i0 = (int64_t)blockIdx.x * (4 * 256) + threadIdx.x;
+    int w[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+        const int64_t i = i0 + k * 256;
+        w[k] = i < n4 ? __ldcs(reinterpret_cast<const int *>(sign) + i) : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = i0 + k * 256;
+        if (i >= n4) break;
         float4 r;
-        r.x = (float)(signed char)(ws[k] & 0xff) * g;
-        r.y = (float)(signed char)((ws[k] >> 8) & 0xff) * g;
-        r.z = (float)(signed char)((ws[k] >> 16) & 0xff) * g;
-        r.w = (float)(signed char)((ws[k] >> 24) & 0xff) * g;
-        __stcs(o + k, r);
+        r.x = (float)(signed char)(w[k] & 0xff) * g;
+        r.y = (float)(signed char)((w[k] >> 8) & 0xff) * g;
+        r.z = (float)(signed char)((w[k] >> 16) & 0xff) * g;
+        r.w = (float)(signed char)((w[k] >> 24) & 0xff) * g;
+        __stcs(reinterpret_cast<float4 *>(g_pred) + i, r);
     }
 }
 
 }  // namespace
 
-int64_t corr4d_l1_workspace_bytes() { return 2 * 148 * kEpiWarps * 4 * 2; }  // partials of up to 296 CTAs, with slack
+// ticket (16 bytes, zero between launches) + one partial per (CTA, epilogue warp) of up to 2 x 148 CTAs, with slack
+int64_t corr4d_l1_workspace_bytes() { return 16 + 2 * 148 * kEpiWarps * 4 * 2; }
 
 int corr4d_l1_bwd_launch(const signed char *sign, const float *grad_loss, float *g_pred, int64_t n, cudaStream_t st) {
-    MT_REQUIRE(n > 0 && n % 16 == 0 && aligned16(sign) && aligned16(g_pred), "mt_corr4d_l1_bwd: n must be a multiple of 16, pointers 16 B aligned");
-    const int64_t n16 = n / 16;
-    launch(corr_l1_bwd_kernel, dim3((unsigned)((n16 + 255) / 256)), dim3(256), 0, st, sign, grad_loss,
-           (float)(1.0 / (double)n), g_pred, n16);
+    MT_REQUIRE(n > 0 && n % 4 == 0 && aligned16(sign) && aligned16(g_pred), "mt_corr4d_l1_bwd: n must be a multiple of 4, pointers 16 B aligned");
+    const int64_t n4 = n / 4;
+    launch(corr_l1_bwd_kernel, dim3((unsigned)((n4 + 1023) / 1024)), dim3(256), 0, st, sign, grad_loss,
+           (float)(1.0 / (double)n), g_pred, n4);
     return launch_status("mt_corr4d_l1_bwd");
 }
 
@@ -876,13 +900,11 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
     a.msy = mask_mode ? (float)MH / (float)fh : 1.0f;
     a.msx = mask_mode ? (float)MW / (float)fw : 1.0f;
     a.out = out; a.C = C; a.F = F; a.P = P;
-    a.pred = l1 ? l1->pred : nullptr; a.sign = l1 ? l1->sign : nullptr; a.partials = l1 ? l1->partials : nullptr;
-    // L1 mode: after the volume kernel, the partial sums of its n_parts (CTA, epilogue warp) pairs are folded
-    auto finish = [&](int n_parts) {
-        if (!l1) return;
-        launch(corr_l1_finish_kernel, dim3(1), dim3(256), 0, st, (const float *)l1->partials, n_parts,
-               1.0 / ((double)B * F * P * P), l1->loss);
-    };
+    a.pred = l1 ? l1->pred : nullptr; a.sign = l1 ? l1->sign : nullptr; a.loss = l1 ? l1->loss : nullptr;
+    a.ticket = l1 ? reinterpret_cast<unsigned int *>(l1->partials) : nullptr;   // workspace: ticket header, then partials
+    a.partials = l1 ? l1->partials + 4 : nullptr;
+    a.inv_count = 1.0 / ((double)B * F * P * P);
+    a.early_trigger = tuning("MT_CORR_EARLY_TRIGGER", kCorrEarlyTrigger);
     a.tiles_m = P / (pair ? kTile : tm); a.tiles_n = P / tn;
     const int64_t n_tiles = (int64_t)B * F * a.tiles_m * a.tiles_n;
     MT_REQUIRE(n_tiles < (1ll << 30), "mt_corr4d_fwd: too many tiles");
@@ -915,7 +937,6 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
         if (tn == 256) MT_CORR_PAIR_GO(256, 6);  // 6 x 32 KB per CTA
         else MT_CORR_PAIR_GO(128, 8);            // 8 x 24 KB per CTA
 #undef MT_CORR_PAIR_GO
-        finish(2 * npairs * kEpiWarps);
         return launch_status("mt_corr4d_fwd");
     }
     int ctas = sm_count();
@@ -942,7 +963,6 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
         else MT_CORR_GO(128, 64, 8);                  // 8 x 24 KB
     }
 #undef MT_CORR_GO
-    finish(ctas * kEpiWarps);
     return launch_status("mt_corr4d_fwd");
 }
 

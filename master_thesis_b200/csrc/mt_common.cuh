@@ -65,7 +65,10 @@ constexpr int64_t kWorkspaceBytes = kWsTicketBytes + int64_t(kMaxReduceBlocks) *
 // First statement of every kernel.  wait: the previous kernel in the stream has completed
 // and its writes are visible.  launch_dependents AFTER the wait: the next kernel may only
 // be scheduled once every CTA of this one has started, so waiting CTAs can never occupy
-// the slots this kernel still needs.
+// the slots this kernel still needs.  Exception: the persistent kernels that hold ~200 KB of
+// shared memory per SM (corr_tc.cu, warp_tma.cu) only wait and leave the trigger to their
+// exit - dependents pre-launched beside them pin the SM's shared-memory / L1 split at its
+// maximum-shared-memory setting for the whole PDL chain behind them (corr_tc.cu kCorrEarlyTrigger).
 __device__ __forceinline__ void pdl_sync() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

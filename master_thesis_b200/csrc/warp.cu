@@ -41,7 +41,10 @@ constexpr int kIters = 1;      // forward kernel: row groups per thread (swept: 
 // all 32 in flight (SASS checked with cuobjdump; profiles/r1_experiments.md).  With a register
 // budget stated, all gathers of a thread are issued before the first use.
 #ifndef MT_WARP_MINB
-#define MT_WARP_MINB 6
+#define MT_WARP_MINB 8
+#endif
+#ifndef MT_WARP_MINB1
+#define MT_WARP_MINB1 10  // 1 row per thread: 13 taps in flight, more resident warps
 #endif
 #ifndef MT_WARP_MINB4
 #define MT_WARP_MINB4 4  // 4 rows per thread: 40 taps in flight need the registers
@@ -90,7 +93,7 @@ constexpr int kMaxRowsPerCta = 32;
 // LOWRES (dense flow only): the flow is given at gh x gw and bilinearly resized to H x W in the kernel - the
 // resized flow is never written or read back; bit-identical to resizing first.
 template <int C, int U, int VIS, bool AFFINE, bool FULL, bool PACK = false, bool LOWRES = false>
-__global__ void __launch_bounds__(kCols, U >= 4 ? MT_WARP_MINB4 : MT_WARP_MINB) warp_fwd_kernel(const WarpFwdArgs a) {
+__global__ void __launch_bounds__(kCols, U >= 4 ? MT_WARP_MINB4 : (U == 1 ? MT_WARP_MINB1 : MT_WARP_MINB)) warp_fwd_kernel(const WarpFwdArgs a) {
     static_assert(!(AFFINE && LOWRES), "a theta needs no resize");
     pdl_sync();
     __shared__ float s_by[kMaxRowsPerCta];
@@ -670,7 +673,8 @@ static int warp_fwd_impl(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_s
     }
     const bool affine = (flags & MT_GRID_AFFINE) != 0;
     const bool vis_bil = (flags & MT_VIS_BILINEAR) != 0;
-    const int rows = tuning("MT_WARP_ROWS", kRows) == 2 ? 2 : 4;
+    int rows = tuning("MT_WARP_ROWS", kRows);
+    rows = rows == 1 && !pack && !lowres ? 1 : (rows == 4 ? 4 : 2);
     int iters = tuning("MT_WARP_ITERS", kIters);
     if (iters < 1) iters = 1;
     if (iters * rows > kMaxRowsPerCta) iters = kMaxRowsPerCta / rows;
@@ -714,6 +718,7 @@ static int warp_fwd_impl(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_s
 #define MT_WARP_GO(CC, VV, AA, FF)                                                  \
     do {                                                                            \
         if (rows == 2) launch(warp_fwd_kernel<CC, 2, VV, AA, FF>, gridd, block, 0, st, a); \
+        else if (rows == 1) launch(warp_fwd_kernel<CC, 1, VV, AA, FF>, gridd, block, 0, st, a); \
         else launch(warp_fwd_kernel<CC, 4, VV, AA, FF>, gridd, block, 0, st, a);        \
     } while (0)
 #define MT_WARP_PICK(CC)                                                            \

@@ -69,6 +69,7 @@ struct WarpStagedArgs {
     int F, P, tiles_x, tiles_per_frame, n_tiles;
     int debug;  // MT_WARP_DBG (developer): bit 0 = never stage (every tile takes the direct path); bit 3 = timeline probe
     Sampler sp;
+    int early_trigger;  // griddepcontrol.launch_dependents right after the wait, or only at exit (see corr_tc.cu)
 };
 
 template <int TW, int BW, int BH, int STAGES>
@@ -117,7 +118,8 @@ warp_staged_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    pdl_sync();
+    pdl_wait();
+    if (a.early_trigger) pdl_launch();
     if (probe && threadIdx.x == 0) g_timeline[blockIdx.x * 8 + 1] = gtime();
 
     const float wmax = a.sp.wmax, hmax = a.sp.hmax;
@@ -405,6 +407,9 @@ int staged_go(const StagedHost &h) {
     a.F = h.F; a.P = H * W; a.tiles_x = tiles_x; a.tiles_per_frame = tiles_x * tiles_y; a.n_tiles = (int)n_tiles;
     a.sp = make_sampler(H, W, h.ac);
     a.debug = tuning("MT_WARP_DBG", 0);
+    // no early launch_dependents: this kernel holds ~200 KB of shared memory per SM, see kCorrEarlyTrigger in
+    // corr_tc.cu (cfg5 step 121.8 -> 109.8 us: the streaming kernels behind it get their L1 back)
+    a.early_trigger = tuning("MT_STAGED_EARLY_TRIGGER", 0);
     int ctas = sm_count();
     if (ctas > n_tiles) ctas = (int)n_tiles;
     constexpr int smem = staged_smem_bytes<TW, BW, BH, STAGES>();

@@ -104,6 +104,16 @@ def scratch(t, tag, nbytes):
     return ws
 
 
+def zeroed_scratch(t, tag, nbytes):
+    """Scratch that is zero when first handed out (ticket words the kernels re-arm themselves), per (tag, device, stream)."""
+    key = (tag, t.device.index, torch.cuda.current_stream(t.device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=t.device)
+        _workspaces[key] = ws
+    return ws
+
+
 def _planes(t, plane_dims=2):
     """Makes the trailing ``plane_dims`` dims one contiguous plane (copying only if needed)."""
     exp = 1
@@ -614,7 +624,7 @@ def corr4d_l1_fwd_raw(pred, feats_t, feats_r, m_target=None, m_refs=None, want_s
         mt_sb, mr_sb, mr_sf = mt.stride(0), mr.stride(0), mr.stride(2)
     loss = _empty((), dtype=torch.float32, device=fr.device)
     sign = _empty(pr.shape, dtype=torch.int8, device=fr.device) if want_sign else None
-    ws = scratch(fr, "corr_l1", int(_lib.load().mt_corr4d_l1_workspace_bytes()))
+    ws = zeroed_scratch(fr, "corr_l1", int(_lib.load().mt_corr4d_l1_workspace_bytes()))
     _call("mt_corr4d_vgg_l1_fwd", _ptr(ft), ft.stride(0), ft.stride(1), _ptr(mt), mt_sb, _ptr(fr), fr.stride(0),
           fr.stride(1), fr.stride(2), _ptr(mr), mr_sb, mr_sf, MH, MW, _ptr(pr), _ptr(loss), _ptr(sign), _ptr(ws),
           ws.numel(), b, c, f, h, w, _stream(fr))

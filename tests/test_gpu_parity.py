@@ -1145,10 +1145,10 @@ def test_flow_estimator_input_pack_full_size(mtb):
     assert torch.equal(xd, dev(x)) and torch.equal(md, dev(m))
 
 
-@pytest.mark.parametrize("rows,iters", [(2, 1), (4, 1), (2, 4), (4, 2)])
+@pytest.mark.parametrize("rows,iters", [(1, 1), (1, 3), (2, 1), (4, 1), (2, 4), (4, 2)])
 @pytest.mark.parametrize("name", sorted(cases.WARP_CASES))
 def test_dfpn_align_tail_rows_per_thread(mtb, name, rows, iters):
-    """The direct-gather kernel with 2 / 4 vertically adjacent pixels per thread (taps of a shared source row are
+    """The direct-gather kernel with 1 / 2 / 4 vertically adjacent pixels per thread (taps of a shared source row are
     loaded once and reused) and several row groups per CTA: bit-identical to the reference's golden vectors."""
     x, m, m_t, flow = cases.warp_inputs(cases.WARP_CASES[name])
     g = load_golden("warp_" + name)
