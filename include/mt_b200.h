@@ -164,7 +164,9 @@ MT_API int mt_mask_out(const float *flow, int64_t n, float *out, mt_stream_t str
 
 /* ---- masked L1  (LossesUtils.masked_l1, utils.py:139-169)            (a5)
  * y_hat, y: (B,C,F,P) strided (P contiguous); mask: (B,mask_c,F,P), mask_c in
- * {1,C}.  batch_mask: B device bytes or NULL (selection without the
+ * {1,C}, or NULL = all ones (torch.ones_like(y_hat), the flow losses model_dfpn.py:259-267;
+ * pass mask_c = C).  Axes that lie back to back in memory are folded into the plane by the
+ * launcher (a (B,F,H,W,2) flow becomes B planes of F*H*W*2 elements).  batch_mask: B device bytes or NULL (selection without the
  * reference's host sync, utils.py:158-165).  out3[0] = weight * l1 / den with
  * den = sum(mask)+1e-9 ('sum') or numel ('mean'); out3[1] = sum|.|;
  * out3[2] = den.  0 if nothing is selected.

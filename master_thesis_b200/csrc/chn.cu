@@ -295,35 +295,65 @@ struct L1Args {
     double mask_repeat;                // times every mask element is visited through stride-0 broadcasting
 };
 
+// One chunk = 256 * VEC consecutive elements of one (b, f) plane.  A CTA takes kL1Unroll chunks per trip (a grid stride
+// apart) and requests every operand of all of them before the first use: with one chunk per trip the kernel ran at
+// 0.46 of the HBM roofline (two 16-byte loads in flight per thread).  mask == NULL: all ones (never loaded).
+constexpr int kL1Unroll = 4;
+
+constexpr int kL1CtasPerSm = 2;   // resident CTAs the register budget is stated for; the grid is one such wave
+
 template <int VEC>
-__global__ void __launch_bounds__(256) masked_l1_fwd_kernel(const L1Args a) {
+__global__ void __launch_bounds__(256, kL1CtasPerSm) masked_l1_fwd_kernel(const L1Args a) {
     pdl_sync();
     __shared__ float red[3 * 32];
     float acc[3] = {0.0f, 0.0f, 0.0f};  // sum |.|, sum(mask), selected element count / P-chunks
-    for (int64_t ch = blockIdx.x; ch < a.total_chunks; ch += gridDim.x) {
-        const int64_t bf = ch / a.chunks;
-        const int b = (int)(bf / a.F), f = (int)(bf - (int64_t)b * a.F);
-        if (a.bm && !a.bm[b]) continue;
-        const int64_t p0 = ((ch - bf * a.chunks) * blockDim.x + threadIdx.x) * VEC;
-        if (p0 >= a.P) continue;
-        Vec<VEC> mk;
-        if (a.mask_c == 1) {
-            mk.load_stream(a.m + b * a.m_sb + f * a.m_sf + p0);
+    const unsigned int total = (unsigned int)a.total_chunks, chunks = (unsigned int)a.chunks;
+    const bool has_mask = a.m != nullptr;
+    for (unsigned int ch0 = blockIdx.x; ch0 < total; ch0 += gridDim.x * kL1Unroll) {
+        bool on[kL1Unroll];
+        int64_t oa[kL1Unroll], ob[kL1Unroll], om[kL1Unroll];
+        int nvalid[kL1Unroll];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[1] += mk.v[i];
+        for (int k = 0; k < kL1Unroll; ++k) {
+            const unsigned int ch = ch0 + k * gridDim.x;
+            on[k] = ch < total;
+            const unsigned int bf = on[k] ? ch / chunks : 0u;
+            const int b = (int)(bf / (unsigned int)a.F), f = (int)(bf - (unsigned int)b * (unsigned int)a.F);
+            const int64_t p0 = ((int64_t)(ch - bf * chunks) * blockDim.x + threadIdx.x) * VEC;
+            on[k] = on[k] && p0 < a.P && (!a.bm || a.bm[b]);
+            oa[k] = b * a.a_sb + f * a.a_sf + p0;
+            ob[k] = b * a.b_sb + f * a.b_sf + p0;
+            om[k] = b * a.m_sb + f * a.m_sf + p0;
+            nvalid[k] = VEC;
         }
+        Vec<VEC> mk[kL1Unroll];  // loaded per channel, or once (mask_c == 1) and kept
         for (int c = 0; c < a.C; ++c) {
-            if (a.mask_c != 1) {
-                mk.load_stream(a.m + b * a.m_sb + c * a.m_sc + f * a.m_sf + p0);
+            Vec<VEC> ya[kL1Unroll], yb[kL1Unroll];
+            const bool load_mask = has_mask && (a.mask_c != 1 || c == 0);
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) acc[1] += mk.v[i];
+            for (int k = 0; k < kL1Unroll; ++k) {
+                if (!on[k]) continue;
+                if (load_mask) mk[k].load_stream(a.m + om[k] + c * a.m_sc);
+                ya[k].load_stream(a.a + oa[k] + c * a.a_sc);
+                yb[k].load_stream(a.b + ob[k] + c * a.b_sc);
             }
-            Vec<VEC> ya, yb;
-            ya.load_stream(a.a + b * a.a_sb + c * a.a_sc + f * a.a_sf + p0);
-            yb.load_stream(a.b + b * a.b_sb + c * a.b_sc + f * a.b_sf + p0);
 #pragma unroll
-            for (int i = 0; i < VEC; ++i)  // |y_hat*mask - y*mask|   utils.py:166
-                acc[0] += fabsf(__fsub_rn(__fmul_rn(ya.v[i], mk.v[i]), __fmul_rn(yb.v[i], mk.v[i])));
+            for (int k = 0; k < kL1Unroll; ++k) {
+                if (!on[k]) continue;
+                if (has_mask) {
+                    if (load_mask) {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) acc[1] += mk[k].v[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i)  // |y_hat*mask - y*mask|   utils.py:166
+                        acc[0] += fabsf(__fsub_rn(__fmul_rn(ya[k].v[i], mk[k].v[i]), __fmul_rn(yb[k].v[i], mk[k].v[i])));
+                } else {
+                    acc[1] += (float)nvalid[k];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[0] += fabsf(__fsub_rn(ya[k].v[i], yb[k].v[i]));  // mask = 1
+                }
+            }
         }
     }
     // selected batch items (for the 'mean' divisor), counted once by CTA 0
@@ -363,7 +393,12 @@ __global__ void __launch_bounds__(256) masked_l1_bwd_kernel(const L1Args a) {
         Vec<VEC> g;
         if (sel) {
             Vec<VEC> mk, ya, yb;
-            mk.load_stream(a.m + b * a.m_sb + (a.mask_c == 1 ? 0 : c) * a.m_sc + f * a.m_sf + p0);
+            if (a.m) {
+                mk.load_stream(a.m + b * a.m_sb + (a.mask_c == 1 ? 0 : c) * a.m_sc + f * a.m_sf + p0);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) mk.v[i] = 1.0f;  // mask == NULL: all ones
+            }
             ya.load_stream(a.a + b * a.a_sb + c * a.a_sc + f * a.a_sf + p0);
             yb.load_stream(a.b + b * a.b_sb + c * a.b_sc + f * a.b_sf + p0);
 #pragma unroll
@@ -602,7 +637,7 @@ static int fill_l1(L1Args &a, const float *y_hat, int64_t a_sb, int64_t a_sc, in
                    const float *y, int64_t b_sb, int64_t b_sc, int64_t b_sf, const float *mask,
                    int64_t m_sb, int64_t m_sc, int64_t m_sf, const uint8_t *batch_mask, int B, int C,
                    int F, int64_t P, int mask_c, int reduction, float weight, const char *who) {
-    MT_REQUIRE(y_hat && y && mask, "%s: NULL input", who);
+    MT_REQUIRE(y_hat && y, "%s: NULL input", who);  // mask == NULL: all ones (torch.ones_like(y_hat), model_dfpn.py:259-267)
     MT_REQUIRE(B > 0 && C > 0 && F > 0 && P > 0, "%s: empty shape", who);
     MT_REQUIRE(mask_c == 1 || mask_c == C, "%s: mask_c must be 1 or C", who);
     MT_REQUIRE(reduction == MT_REDUCE_MEAN || reduction == MT_REDUCE_SUM, "%s: bad reduction", who);
@@ -612,11 +647,21 @@ static int fill_l1(L1Args &a, const float *y_hat, int64_t a_sb, int64_t a_sc, in
     a.m = mask; a.m_sb = m_sb; a.m_sc = m_sc; a.m_sf = m_sf;
     a.bm = batch_mask; a.B = B; a.C = C; a.F = F; a.P = P; a.mask_c = mask_c;
     a.reduction = reduction; a.weight = weight;
+    // Collapse axes that are back to back in memory into the plane: the flow losses arrive as (B, F, H, W, 2) =
+    // "B x C = F x F = H planes of W * 2 = 512 floats" - half a CTA per chunk and a channel loop of single loads.
+    const bool no_mask = mask == nullptr;
+    if (a.F > 1 && a.a_sf == a.P && a.b_sf == a.P && (no_mask || a.m_sf == a.P)) {
+        a.P *= a.F; a.F = 1; a.a_sf = a.b_sf = a.m_sf = 0;
+    }
+    // channels: only with a per-channel mask or none (a shared mask is visited once per (b, f, p), not per channel)
+    if (a.F == 1 && a.C > 1 && a.a_sc == a.P && a.b_sc == a.P && (no_mask || (a.mask_c == a.C && a.m_sc == a.P))) {
+        a.P *= a.C; a.C = 1; a.mask_c = 1; a.a_sc = a.b_sc = a.m_sc = 0;
+    }
     return MT_OK;
 }
 
 static bool l1_vec4(const L1Args &a) {
-    return mult4(a.P) && aligned16(a.a) && aligned16(a.b) && aligned16(a.m) && mult4(a.a_sb) &&
+    return mult4(a.P) && aligned16(a.a) && aligned16(a.b) && (!a.m || aligned16(a.m)) && mult4(a.a_sb) &&
            mult4(a.a_sc) && mult4(a.a_sf) && mult4(a.b_sb) && mult4(a.b_sc) && mult4(a.b_sf) &&
            mult4(a.m_sb) && mult4(a.m_sc) && mult4(a.m_sf);
 }
@@ -636,9 +681,12 @@ extern "C" int mt_masked_l1_fwd(const float *y_hat, int64_t a_sb, int64_t a_sc, 
     a.out3 = out3; a.ws = workspace; a.mask_repeat = (double)mask_repeat;
     const bool v4 = l1_vec4(a);
     const int vec = v4 ? 4 : 1;
-    a.chunks = (int)((P + 256 * vec - 1) / (256 * vec));
-    a.total_chunks = (int64_t)B * F * a.chunks;
-    const int nblk = reduce_blocks(a.total_chunks);
+    a.chunks = (int)((a.P + 256 * vec - 1) / (256 * vec));
+    a.total_chunks = (int64_t)a.B * a.F * a.chunks;
+    int64_t want = (a.total_chunks + kL1Unroll - 1) / kL1Unroll;
+    if (want > (int64_t)sm_count() * kL1CtasPerSm) want = (int64_t)sm_count() * kL1CtasPerSm;
+    const int nblk = (int)want;
+    MT_REQUIRE(a.total_chunks + (int64_t)nblk * kL1Unroll < (1ll << 32), "mt_masked_l1_fwd: too many chunks");
     if (v4) launch(masked_l1_fwd_kernel<4>, nblk, 256, 0, (cudaStream_t)stream, a);
     else launch(masked_l1_fwd_kernel<1>, nblk, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_masked_l1_fwd");
@@ -655,11 +703,11 @@ extern "C" int mt_masked_l1_bwd(const float *y_hat, int64_t a_sb, int64_t a_sc, 
                      batch_mask, B, C, F, P, mask_c, reduction, weight, "mt_masked_l1_bwd");
     if (rc) return rc;
     MT_REQUIRE(out3 && grad_out && (grad_y_hat || grad_y), "mt_masked_l1_bwd: NULL argument");
-    MT_REQUIRE((int64_t)B * F <= 65535, "mt_masked_l1_bwd: B*F > 65535");
+    MT_REQUIRE((int64_t)a.B * a.F <= 65535, "mt_masked_l1_bwd: B*F > 65535");
     a.out3_in = out3; a.grad_out = grad_out; a.ga = grad_y_hat; a.gb = grad_y;
     const bool v4 = l1_vec4(a) && aligned16(grad_y_hat) && aligned16(grad_y);
     const int vec = v4 ? 4 : 1;
-    dim3 grid((unsigned)((P + 256 * vec - 1) / (256 * vec)), B * F);
+    dim3 grid((unsigned)((a.P + 256 * vec - 1) / (256 * vec)), a.B * a.F);
     if (v4) launch(masked_l1_bwd_kernel<4>, grid, 256, 0, (cudaStream_t)stream, a);
     else launch(masked_l1_bwd_kernel<1>, grid, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_masked_l1_bwd");

@@ -283,16 +283,6 @@ def _lead3(t, nlead, plane_dims):
     return t, st[0], st[1], st[2]
 
 
-def _ones_plane(like, p):
-    """A cached plane of ones (the all-ones mask of the flow losses, model_dfpn.py:259-267)."""
-    key = ("ones", like.device.index)
-    buf = _workspaces.get(key)
-    if buf is None or buf.numel() < p:
-        buf = torch.ones(max(int(p), 1024), dtype=torch.float32, device=like.device)
-        _workspaces[key] = buf
-    return buf
-
-
 def _l1_layout(y_hat, y, mask):
     """(B, C, F, P) decomposition + strides of the three operands of masked_l1 (utils.py:139-169).
 
@@ -318,8 +308,8 @@ def _l1_layout(y_hat, y, mask):
     pd = nd - nlead
     a = _lead3(y_hat, nlead, pd)
     b_ = _lead3(y, nlead, pd)
-    if mask is None:     # torch.ones_like(y_hat): one cached plane of ones, visited per channel (mask_c = C)
-        return (a, b_, (_ones_plane(y_hat, P), 0, 0, 0)), B, C, F, P, C, 1
+    if mask is None:     # torch.ones_like(y_hat): never materialised, the kernels take mask = NULL as all ones
+        return (a, b_, (None, 0, 0, 0)), B, C, F, P, C, 1
     if mask.dim() > nd:
         raise RuntimeError("masked_l1: mask %s does not broadcast against %s" % (tuple(mask.shape), shape))
     mask = mask.reshape((1,) * (nd - mask.dim()) + tuple(mask.shape))

@@ -1236,3 +1236,42 @@ def test_dfpn_align_tail_full_size(mtb):
         xa, va, vm = mtb.dfpn_align_tail(dev(xr), dev(mr), dev(m_t), dev(flow))
         oxa, ova, ovm = oracle.dfpn_align_tail(xr, mr, m_t, flow)
         assert np.array_equal(host(xa), oxa) and np.array_equal(host(va), ova) and np.array_equal(host(vm), ovm)
+
+
+@pytest.mark.parametrize("reduction", ["sum", "mean"])
+def test_masked_l1_layouts(mtb, reduction):
+    """mt_masked_l1_fwd / _bwd over the memory layouts the launcher treats differently: everything folded into one plane
+    per sample (no mask / per-channel mask), frames folded only (mask shared by the channels), nothing folded (a strided
+    frame view; a mask broadcast over the frames), odd sizes on the scalar path, a batch selection - against the oracle."""
+    from master_thesis_b200 import ops
+    r = np.random.RandomState(77)
+    B, C, F, H, W = 3, 3, 4, 10, 12
+
+    def rnd(*shape):
+        return r.standard_normal(shape).astype(np.float32)
+
+    bm = np.array([True, False, True])
+    cases_ = {
+        "none": (rnd(B, C, F, H, W), rnd(B, C, F, H, W), None, bm),
+        "per_channel": (rnd(B, C, F, H, W), rnd(B, C, F, H, W), (r.random_sample((B, C, F, H, W)) < 0.6).astype(np.float32), None),
+        "shared": (rnd(B, C, F, H, W), rnd(B, C, F, H, W), (r.random_sample((B, 1, F, H, W)) < 0.6).astype(np.float32), bm),
+        "odd": (rnd(2, 3, 2, 5, 7), rnd(2, 3, 2, 5, 7), (r.random_sample((2, 1, 2, 5, 7)) < 0.5).astype(np.float32), None),
+        "flow": (rnd(B, F, H, W, 2), rnd(B, F, H, W, 2), None, bm),           # (B, F, H, W, 2): C = F, F = H, P = W * 2
+    }
+    for key, (ya, yb, mk, sel) in cases_.items():
+        a = dev(ya).requires_grad_(True)
+        loss = ops.masked_l1(a, dev(yb), None if mk is None else dev(mk), None if sel is None else dev(sel),
+                             reduction, 1.25)
+        loss.backward()
+        full = np.ones_like(ya) if mk is None else mk
+        want = oracle.masked_l1(ya, yb, full, sel, reduction, 1.25)
+        assert float(loss) == pytest.approx(want, rel=2e-6), key
+        wg = -oracle.masked_l1_bwd(ya, yb, full, sel, reduction, 1.25)   # the oracle returns d / d y = -d / d y_hat
+        assert np.abs(host(a.grad) - wg).max() <= 1e-6 * max(np.abs(wg).max(), 1e-30), key
+    # strided frame view (every second frame of a longer clip): nothing can be folded
+    big_a, big_b = rnd(B, C, 2 * F, H, W), rnd(B, C, 2 * F, H, W)
+    mk = (r.random_sample((B, 1, F, H, W)) < 0.6).astype(np.float32)
+    a = dev(big_a)[:, :, ::2]
+    loss = ops.masked_l1(a, dev(big_b)[:, :, ::2], dev(mk), None, reduction, 1.0)
+    want = oracle.masked_l1(big_a[:, :, ::2], big_b[:, :, ::2], mk, None, reduction, 1.0)
+    assert float(loss) == pytest.approx(want, rel=2e-6)
