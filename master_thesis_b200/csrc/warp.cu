@@ -52,6 +52,9 @@ constexpr int kIters = 1;      // forward kernel: row groups per thread (swept: 
 #ifndef MT_WARPB_MINB
 #define MT_WARPB_MINB 6
 #endif
+#ifndef MT_WARPL1B_MINB
+#define MT_WARPL1B_MINB 8  // fused-loss backward: 64 registers, no spills, 79.4 -> 75.4 us at cfg3 (the forward spills at 8)
+#endif
 
 // Forward-kernel arguments: every offset is a 32-bit ELEMENT offset (the launcher
 // checks the ranges), because 64-bit stride arithmetic dominated the per-thread
@@ -549,7 +552,7 @@ __global__ void __launch_bounds__(kCols, MT_WARPB_MINB) warp_l1_fwd_kernel(const
 // d loss / d flow in one pass: recomputes the sampling, never materialises
 // x_aligned or its gradient.
 template <int U>
-__global__ void __launch_bounds__(kCols, MT_WARPB_MINB) warp_l1_bwd_kernel(const WarpL1Args a) {
+__global__ void __launch_bounds__(kCols, MT_WARPL1B_MINB) warp_l1_bwd_kernel(const WarpL1Args a) {
     pdl_sync();
     const int W = a.sp.W, H = a.sp.H;
     const bool live = (int)(blockIdx.x * kCols + threadIdx.x) < W;
@@ -858,8 +861,10 @@ extern "C" int mt_warp_l1_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_
     MT_REQUIRE((int64_t)colb * B * F <= kMaxReduceBlocks,
                "mt_warp_l1_fwd: B*F*ceil(W/128) = %lld exceeds %d CTAs (split the batch)",
                (long long)colb * B * F, kMaxReduceBlocks);
-    // about 16 CTAs per SM in total; each CTA strides over the remaining row blocks
-    int64_t per_sm = tuning("MT_WARPL1_CTAS_PER_SM", 16);
+    // about one resident wave of CTAs (6 per SM at 80 registers); each CTA strides over the remaining row blocks.
+    // Swept at cfg3 (profiles/r2_experiments.md, call AC): 6 / 12 / 16 / 24 / 31 per SM = 77.9 / 77.1 / 77.6 / 76.6 / 79.0 us
+    // for the 256 x 256 launch, 16.1 / 16.7 / 19.0 / 22.0 / 24.0 us for the 64 x 64 one (fewer partials for the fold)
+    int64_t per_sm = tuning("MT_WARPL1_CTAS_PER_SM", 6);
     if (per_sm < 1) per_sm = 1;
     if (per_sm * sm_count() > kMaxReduceBlocks) per_sm = kMaxReduceBlocks / sm_count();
     int64_t cap = ((int64_t)sm_count() * per_sm) / ((int64_t)colb * B * F);
