@@ -52,6 +52,9 @@ constexpr int kIters = 1;      // forward kernel: row groups per thread (swept: 
 #ifndef MT_WARPB_MINB
 #define MT_WARPB_MINB 6
 #endif
+#ifndef MT_WARPL1F_MINB
+#define MT_WARPL1F_MINB 8  // fused-loss forward, loss only
+#endif
 #ifndef MT_WARPL1B_MINB
 #define MT_WARPL1B_MINB 8  // fused-loss backward: 64 registers, no spills, 79.4 -> 75.4 us at cfg3 (the forward spills at 8)
 #endif
@@ -483,8 +486,10 @@ __device__ __forceinline__ float mask_out_of(float gx, float gy) {
 
 // grid (col blocks, <= row blocks, frames); a CTA strides over row blocks so that the
 // number of partials stays within the reduction workspace
-template <int U>
-__global__ void __launch_bounds__(kCols, MT_WARPB_MINB) warp_l1_fwd_kernel(const WarpL1Args a) {
+// MAT: the aligned frames / visibilities are also written (a consumer asked for them); the loss-only instantiation
+// carries neither the stores nor the nearest-tap gather and fits the 64-register budget of 8 CTAs per SM.
+template <int U, bool MAT>
+__global__ void __launch_bounds__(kCols, MAT ? MT_WARPB_MINB : MT_WARPL1F_MINB) warp_l1_fwd_kernel(const WarpL1Args a) {
     pdl_sync();
     __shared__ float red[2 * 32];
     float acc[2] = {0.0f, 0.0f};  // sum |x_t*M - x_al*M| over 3 channels, sum M
@@ -532,9 +537,9 @@ __global__ void __launch_bounds__(kCols, MT_WARPB_MINB) warp_l1_fwd_kernel(const
             for (int c = 0; c < 3; ++c) {
                 const float r = interp_k<U>(q[c][k], t, k);
                 acc[0] += fabsf(__fsub_rn(__fmul_rn(xt[c][k], M), __fmul_rn(r, M)));
-                if (a.x_al) st_stream1(a.x_al + (((int)n * 3 + c) * a.P + p0 + k * W), r);
+                if (MAT && a.x_al) st_stream1(a.x_al + (((int)n * 3 + c) * a.P + p0 + k * W), r);
             }
-            if (a.v_al)
+            if (MAT && a.v_al)
                 st_stream1(a.v_al + (np0 + k * W),
                            nearest(a.vis + (b * a.vis_sb + f * a.vis_sf), t.ix[k], t.iy[k], a.sp, a.from_mask));
         }
@@ -861,17 +866,18 @@ extern "C" int mt_warp_l1_fwd(const float *x, int64_t x_sb, int64_t x_sc, int64_
     MT_REQUIRE((int64_t)colb * B * F <= kMaxReduceBlocks,
                "mt_warp_l1_fwd: B*F*ceil(W/128) = %lld exceeds %d CTAs (split the batch)",
                (long long)colb * B * F, kMaxReduceBlocks);
-    // about one resident wave of CTAs (6 per SM at 80 registers); each CTA strides over the remaining row blocks.
-    // Swept at cfg3 (profiles/r2_experiments.md, call AC): 6 / 12 / 16 / 24 / 31 per SM = 77.9 / 77.1 / 77.6 / 76.6 / 79.0 us
-    // for the 256 x 256 launch, 16.1 / 16.7 / 19.0 / 22.0 / 24.0 us for the 64 x 64 one (fewer partials for the fold)
-    int64_t per_sm = tuning("MT_WARPL1_CTAS_PER_SM", 6);
+    // about 16 CTAs per SM in total = two resident waves of the loss-only kernel (64 registers, 8 CTAs per SM); each CTA
+    // walks a strip of row blocks.  Swept at cfg3 (profiles/r2_experiments.md, calls AC / AD): loss-only kernel, 6 / 8 / 16
+    // per SM = 94.4 / 76.6 / 71.2 us at 256 x 256 and 17.4 / 15.3 / 16.6 us at 64 x 64
+    int64_t per_sm = tuning("MT_WARPL1_CTAS_PER_SM", 16);
     if (per_sm < 1) per_sm = 1;
     if (per_sm * sm_count() > kMaxReduceBlocks) per_sm = kMaxReduceBlocks / sm_count();
     int64_t cap = ((int64_t)sm_count() * per_sm) / ((int64_t)colb * B * F);
     if (cap < 1) cap = 1;
     if (gy > cap) gy = (int)cap;
     dim3 block(kCols), gridd(colb, gy, B * F);
-    launch(warp_l1_fwd_kernel<kRowsB>, gridd, block, 0, (cudaStream_t)stream, a);
+    if (a.x_al || a.v_al) launch(warp_l1_fwd_kernel<kRowsB, true>, gridd, block, 0, (cudaStream_t)stream, a);
+    else launch(warp_l1_fwd_kernel<kRowsB, false>, gridd, block, 0, (cudaStream_t)stream, a);
     return launch_status("mt_warp_l1_fwd");
 }
 
