@@ -441,7 +441,7 @@ struct L1x3Args {
 };
 
 template <int VEC>
-__global__ void __launch_bounds__(256) chn_l1x3_fwd_kernel(const L1x3Args a) {
+__global__ void __launch_bounds__(256, 3) chn_l1x3_fwd_kernel(const L1x3Args a) {
     pdl_sync();
     __shared__ float red[6 * 32];
     float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // sum |.| of the three terms, sum(mask) of the three
@@ -752,7 +752,11 @@ extern "C" int mt_chn_l1x3_fwd(const float *y_hat, int64_t yh_sb, int64_t yh_sc,
     const bool v4 = l1x3_vec4(a);
     a.chunks = (int)((P + (v4 ? 1024 : 256) - 1) / (v4 ? 1024 : 256));
     a.total_chunks = (int64_t)B * F * a.chunks;
-    const int nblk = reduce_blocks(a.total_chunks);
+    // one resident wave (3 CTAs of 72 registers per SM: all 11 operand loads of a chunk in flight), grid-stride over chunks
+    int64_t want = (int64_t)sm_count() * tuning("MT_L1X3_CTAS_PER_SM", 3);
+    if (want > a.total_chunks) want = a.total_chunks;
+    if (want > kMaxReduceBlocks) want = kMaxReduceBlocks;
+    const int nblk = want < 1 ? 1 : (int)want;
     if (v4) launch(chn_l1x3_fwd_kernel<4>, nblk, 256, 0, (cudaStream_t)stream, a);
     else launch(chn_l1x3_fwd_kernel<1>, nblk, 256, 0, (cudaStream_t)stream, a);
     return launch_status("mt_chn_l1x3_fwd");
