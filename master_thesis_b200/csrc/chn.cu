@@ -31,7 +31,7 @@ struct PackArgs {
 };
 
 template <int VEC>
-__global__ void __launch_bounds__(256) chn_pack_kernel(const PackArgs a) {
+__global__ void __launch_bounds__(256, 4) chn_pack_kernel(const PackArgs a) {
     pdl_sync();
     const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (p0 >= a.P) return;
@@ -75,18 +75,25 @@ struct CompArgs {
 };
 
 template <int VEC>
-__global__ void __launch_bounds__(256) chn_composite_fwd_kernel(const CompArgs a) {
+__global__ void __launch_bounds__(256, 4) chn_composite_fwd_kernel(const CompArgs a) {
     pdl_sync();
     const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (p0 >= a.P) return;
     const int n = blockIdx.y, b = n / a.F;
     Vec<VEC> vt;
     vt.load_cached(a.v_t + b * a.vt_sb + p0);
+    // all operands of the three channels are requested before the first store (the stores may alias the loads as far
+    // as the compiler knows: channel by channel it emitted three dependent round trips)
+    Vec<VEC> oo[3], xx[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        Vec<VEC> o, xt, yh, yc;
-        o.load_stream(a.nn_out + ((int64_t)n * 3 + c) * a.P + p0);
-        xt.load_cached(a.x_t + b * a.xt_sb + c * a.xt_sc + p0);
+        oo[c].load_stream(a.nn_out + ((int64_t)n * 3 + c) * a.P + p0);
+        xx[c].load_cached(a.x_t + b * a.xt_sb + c * a.xt_sc + p0);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        Vec<VEC> yh, yc;
+        const Vec<VEC> &o = oo[c], &xt = xx[c];
         const float m = chan_mean(c), s = chan_std(c);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
@@ -100,19 +107,24 @@ __global__ void __launch_bounds__(256) chn_composite_fwd_kernel(const CompArgs a
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256) chn_composite_bwd_kernel(const CompArgs a) {
+__global__ void __launch_bounds__(256, 4) chn_composite_bwd_kernel(const CompArgs a) {
     pdl_sync();
     const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (p0 >= a.P) return;
     const int n = blockIdx.y, b = n / a.F, f = n - b * a.F;
     Vec<VEC> vt;
     vt.load_cached(a.v_t + b * a.vt_sb + p0);
+    Vec<VEC> oo[3], gyy[3], gcc[3];  // every load before the first store, as in the forward kernel
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        Vec<VEC> o, gy, gc, g;
-        o.load_stream(a.nn_out + ((int64_t)n * 3 + c) * a.P + p0);
-        if (a.g_yhat) gy.load_stream(a.g_yhat + b * a.gy_sb + c * a.gy_sc + f * a.gy_sf + p0);
-        if (a.g_comp) gc.load_stream(a.g_comp + b * a.gc_sb + c * a.gc_sc + f * a.gc_sf + p0);
+        oo[c].load_stream(a.nn_out + ((int64_t)n * 3 + c) * a.P + p0);
+        if (a.g_yhat) gyy[c].load_stream(a.g_yhat + b * a.gy_sb + c * a.gy_sc + f * a.gy_sf + p0);
+        if (a.g_comp) gcc[c].load_stream(a.g_comp + b * a.gc_sb + c * a.gc_sc + f * a.gc_sf + p0);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        Vec<VEC> g;
+        const Vec<VEC> &o = oo[c], &gy = gyy[c], &gc = gcc[c];
         const float m = chan_mean(c), s = chan_std(c);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
@@ -492,7 +504,7 @@ __global__ void __launch_bounds__(256, 3) chn_l1x3_fwd_kernel(const L1x3Args a) 
 
 // grads w.r.t. y_hat (terms nh + vh, added as autograd accumulates them) and y_hat_comp (term nvh)
 template <int VEC>
-__global__ void __launch_bounds__(256) chn_l1x3_bwd_kernel(const L1x3Args a) {
+__global__ void __launch_bounds__(256, 4) chn_l1x3_bwd_kernel(const L1x3Args a) {
     pdl_sync();
     const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (p0 >= a.P) return;
@@ -505,12 +517,17 @@ __global__ void __launch_bounds__(256) chn_l1x3_bwd_kernel(const L1x3Args a) {
     m2.load_stream(a.vm + b * a.vm_sb + f * a.vm_sf + p0);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) m3.v[i] = __fsub_rn(__fsub_rn(1.0f, m1.v[i]), m2.v[i]);
+    Vec<VEC> yhh[3], ycc[3], ytt[3];  // every load before the first store
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        Vec<VEC> yh, yc, yt, gh, gc;
-        yh.load_stream(a.yh + b * a.yh_sb + c * a.yh_sc + f * a.yh_sf + p0);
-        yc.load_stream(a.yc + b * a.yc_sb + c * a.yc_sc + f * a.yc_sf + p0);
-        yt.load_cached(a.yt + b * a.yt_sb + c * a.yt_sc + p0);
+        yhh[c].load_stream(a.yh + b * a.yh_sb + c * a.yh_sc + f * a.yh_sf + p0);
+        ycc[c].load_stream(a.yc + b * a.yc_sb + c * a.yc_sc + f * a.yc_sf + p0);
+        ytt[c].load_cached(a.yt + b * a.yt_sb + c * a.yt_sc + p0);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        Vec<VEC> gh, gc;
+        const Vec<VEC> &yh = yhh[c], &yc = ycc[c], &yt = ytt[c];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             const float d1 = __fsub_rn(__fmul_rn(yh.v[i], m1.v[i]), __fmul_rn(yt.v[i], m1.v[i]));
