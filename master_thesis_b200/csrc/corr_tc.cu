@@ -842,13 +842,16 @@ int corr4d_tc_launch_ex(const float *ft, int64_t ft_sb, int64_t ft_sc, const flo
     int tm = tuning("MT_CORR_TM", 0), tn = tuning("MT_CORR_TN", 0);
     const bool tn_given = tn == 256 || tn == 128 || tn == 64, tm_given = tm == 256 || tm == 128;
     if (!tn_given || !tm_given) {
-        // graph-replayed step, cfg1 at 8 / 32 / 128 frames (profiles/r2_experiments.md): 20.5 us (128 x 64),
-        // 46.2 us (256 x 128), 168.0 us (256 x 256); the runners-up cost 2 - 25 % more
         const int sms = sm_count();
         int atm, atn;
+        // whole frames per CTA once the batch fills the machine; below that, split a frame into as many tiles as it takes
+        // to put a tile on ~85 % of the SMs.  Re-swept after the kernel stopped pre-launching its dependents
+        // (profiles/r2_experiments.md, calls AH / AI): 32 frames 256 x 128 -> 128 x 128: 21.3 -> 17.3 us (default step
+        // 98.4 -> 94.4 us); 16 frames 128 x 128 -> 128 x 64: 17.0 -> 15.9 us (step 26.7 -> 24.8 us)
+        const int need = (sms * 85 + frames * 100 - 1) / (frames * 100);  // tiles per frame wanted
         if (frames * 2 >= sms) { atm = 256; atn = 256; }
-        else if (frames * 5 >= sms) { atm = 256; atn = 128; }
-        else if (frames * 10 >= sms) { atm = 128; atn = 128; }
+        else if (need <= 2) { atm = 256; atn = 128; }
+        else if (need <= 4) { atm = 128; atn = 128; }
         else { atm = 128; atn = 64; }
         if (!tm_given) tm = tn_given ? 256 : atm;
         if (!tn_given) tn = atn;
