@@ -79,6 +79,7 @@ struct WarpFwdArgs {
     // (FlowsUtils.resize_flow(mode='bilinear'), utils.py:107-126 as called at model_dfpn.py:100-101)
     int gh, gw;
     float gsy, gsx;  // gh / H, gw / W in fp32
+    int early_trigger;  // griddepcontrol.launch_dependents right after the wait (default) or only at exit
 };
 constexpr int kMaxRowsPerCta = 32;
 
@@ -101,7 +102,8 @@ constexpr int kMaxRowsPerCta = 32;
 template <int C, int U, int VIS, bool AFFINE, bool FULL, bool PACK = false, bool LOWRES = false>
 __global__ void __launch_bounds__(kCols, U >= 4 ? MT_WARP_MINB4 : (U == 1 ? MT_WARP_MINB1 : MT_WARP_MINB)) warp_fwd_kernel(const WarpFwdArgs a) {
     static_assert(!(AFFINE && LOWRES), "a theta needs no resize");
-    pdl_sync();
+    pdl_wait();
+    if (a.early_trigger) pdl_launch();
     __shared__ float s_by[kMaxRowsPerCta];
     __shared__ Lin s_ly[LOWRES ? kMaxRowsPerCta : 1];
     const int W = a.sp.W, H = a.sp.H;
@@ -671,6 +673,7 @@ static int warp_fwd_impl(const float *x, int64_t x_sb, int64_t x_sc, int64_t x_s
     a.x_t = a.v_t = nullptr; a.nn_in = nullptr; a.xt_sb = a.xt_sc = a.vt_sb = 0;
     a.gh = lowres ? gh : H; a.gw = lowres ? gw : W;
     a.gsy = (float)a.gh / (float)H; a.gsx = (float)a.gw / (float)W;
+    a.early_trigger = tuning("MT_WARP_EARLY_TRIGGER", 1);
     if (pack) {
         MT_REQUIRE(C == 3 && m_target && pack->x_t && pack->v_t && pack->nn_in, "mt_warp_pack_fwd: C must be 3, no NULL input");
         MT_REQUIRE(pack->xt_sb >= 0 && pack->xt_sc >= 0 && pack->vt_sb >= 0 &&
