@@ -744,7 +744,12 @@ int launch_cm(CmArgs a, cudaStream_t st) {
     if constexpr (R <= 7) {
         int keep = 0;
         const int ctas = (mode == 2 && (int64_t)(2 * a.C + 1) * a.f * a.P < (1ll << 31)) ? cm_group_ctas<R>(&keep) : 0;
-        keep = max(0, min(keep, tuning("MT_CM_KEEP", 8)));  // batches parked in shared memory between the passes
+        // batches parked in shared memory between the passes.  Default 0 since the kernels ahead of this one stopped
+        // pinning the SMs' shared-memory split (corr_tc.cu kCorrEarlyTrigger): without dynamic shared memory the kernel
+        // runs with the full L1, which holds a CTA's most recent pass-1 lines for pass 2 - 44.0 -> 38.2 us per call at
+        // B = 8 (cfg2 step 61.9 -> 56.4 us); parking 2 batches in shared memory gave the same time as parking none
+        // while the split was pinned
+        keep = max(0, min(keep, tuning("MT_CM_KEEP", 0)));
         if (ctas > 0) {
             // samples in flight: as many as keep their features (C * f * P * 4 B each) within ~90 MB of L2
             const int64_t sample_bytes = (int64_t)a.C * a.f * a.P * 4;

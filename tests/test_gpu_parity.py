@@ -419,7 +419,7 @@ def test_cm_grouped_full_size(mtb, keep):
         out1, cmask1 = ops.cm_match(dcf, dvt, dva)
         out1, cmask1 = host(out1), host(cmask1)
     finally:
-        _set_tuning("MT_CM_KEEP", 8)
+        _set_tuning("MT_CM_KEEP", 0)
         _set_tuning("MT_CM_TABLE", 2)
     assert np.abs(gs - ogs).max() <= 1e-6 * max(1.0, np.abs(ogs).max())
     assert np.abs(out - oout).max() <= 1e-5 and np.abs(cmask - ocm).max() <= 2e-6
